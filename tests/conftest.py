@@ -1,0 +1,60 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_golden(name):
+    """Return (arrays-as-torch dict, meta dict or None) for tests/golden/<name>.npz."""
+    raw = np.load(os.path.join(GOLDEN, name + ".npz"))
+    out, meta = {}, None
+    for k in raw.files:
+        a = raw[k]
+        if a.dtype.kind in "US":
+            if k == "meta/json":
+                meta = json.loads(str(a))
+            else:
+                out[k] = json.loads(str(a))
+        else:
+            out[k] = torch.from_numpy(a)
+    return out, meta
+
+
+FORWARD_FIXTURES = ["fwd_TALLSIREN_FG", "fwd_SHORTSIREN_FG", "fwd_DOUBLESIREN_FG", "fwd_SingleSIREN_dg"]
+
+
+def fixture_inputs(name):
+    """Rebuild (state, z, cam2world, draws, meta, taps) of a forward fixture."""
+    from oracle import nerf_path as oracle
+
+    fx, meta = load_golden(name)
+    seed = meta.pop("seed")
+    siren_type = meta.pop("siren_type")
+    state = oracle.init_generator_state(siren_type, 256, 32, 256, seed=seed)
+    checksum = sum(float(v.double().abs().sum()) for v in state.values())
+    assert abs(checksum - float(fx["state/checksum"])) < 1e-9 * checksum, "torch CPU generator drifted"
+    z = (fx["in/volume"], fx["in/global"])
+    draws = {k[5:]: v for k, v in fx.items() if k.startswith("draw/")}
+    taps = {k[4:]: v for k, v in fx.items() if k.startswith("tap/")}
+    return state, siren_type, z, fx["in/cam2world"], draws, meta, taps
