@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Headline benchmark: rendered rays/s of the generator forward at 128x128, 24+24 hierarchical
+samples per ray, batch 8, synthetic 64^3 x 32 feature volume, random-init TALLSIREN_FG
+(BASELINE.json configs[1]) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--siren TYPE] [--precision bf16|fp32]
+
+A "step" is one ImplicitGenerator3d.forward over one batch (per GPU: weak scaling; rays shard
+across ranks with no data-path collective).  Rank 0 prints ONE JSON line.
+
+  value     rays/s with (volume, global feature, cam2world) already resident in HBM, CUDA-event timed,
+            max over ranks
+  e2e       rays/s through the public API with HOST buffers: every step copies that step's inputs
+            from pinned host memory and reads pixels + depth back (copies inside the timed region)
+  roofline  FiLM-SIREN MLP (cng_film_siren_fwd, the dominant kernel): algorithmic FLOPs per launch
+            / its CUDA-event duration measured live in a separate instrumented pass, against the
+            measured bf16 tensor peak of MEASURED_PEAKS.json
+  cpu_baseline  the torch-CPU oracle (a port of the reference's path; kind "port") on a bounded
+            sample of the same workload, all host threads
+``--impl reference`` times that CPU path alone (rank 0 only) and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "rendered_rays_per_sec_128x128_24+24spp"
+UNIT = "rays/s"
+FOV = 49.134342641202636
+WORKLOAD = dict(batch=8, img_size=128, num_steps=24, volume=64, channels=32, z_dim=256)
+SIREN_LAYERS = {"TALLSIREN_FG": 8, "SHORTSIREN_FG": 4, "DOUBLESIREN_FG": 2, "SingleSIREN_dg": 1}
+
+
+def mlp_flops_per_point(L: int, C: int = 32, H: int = 256) -> int:
+    """2*(C*256 + (L-1)*256^2 + 256*4)."""
+    return 2 * (C * H + (L - 1) * H * H + H * 4)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], tflops_burst=p["bf16_tflops"], tflops_sustained=p["bf16_tflops_sustained"], source="measured")
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+def render_meta(img_size, num_steps):
+    # configs/thousand/special.py:35-41 render parameters
+    return dict(img_size=img_size, fov=FOV, ray_start=0.25, ray_end=1.95, num_steps=num_steps, hierarchical_sample=True,
+                clamp_mode="relu", nerf_noise=0.0, white_back=True)
+
+
+def synthetic_inputs(batch, volume, seed):
+    """Feature volume ~ N(0, 0.3^2), global ~ N(0.19, 0.05^2), look-at cameras on a shell."""
+    from oracle import nerf_path as oracle  # camera helpers only (numpy/torch CPU), not on the timed path
+    g = torch.Generator().manual_seed(seed)
+    vol = torch.randn((batch, WORKLOAD["channels"], volume, volume, volume), generator=g) * 0.3
+    glob = torch.randn((batch, WORKLOAD["z_dim"]), generator=g) * 0.05 + 0.19
+    cam = oracle.look_at_cam2world(oracle.random_camera_origins(batch, 0.7, 1.5, "y", np.random.RandomState(seed)), "y")
+    return vol, glob, cam
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path
+# --------------------------------------------------------------------------------------------------
+def cpu_render_time(siren_type, img_size, num_steps, volume, reps, warmup):
+    from oracle import nerf_path as oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    state = oracle.init_generator_state(siren_type, seed=0)
+    vol, glob, cam = synthetic_inputs(1, volume, 0)
+    meta = render_meta(img_size, num_steps)
+    g = torch.Generator().manual_seed(1)
+    times = []
+    for i in range(warmup + reps):
+        draws = oracle.draw_randoms(1, img_size, num_steps, True, g)
+        t0 = time.perf_counter()
+        oracle.render(state, siren_type, (vol, glob), cam, draws, taps=False, **meta)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times
+
+
+def pick_cpu_sample(siren_type, budget_s, n_steps):
+    """Largest image size in {32, 64, 128} (batch 1, same 24+24 samples, same 64^3 volume) whose n_steps
+    renders fit the time budget, from a small calibration render."""
+    t = min(cpu_render_time(siren_type, 32, WORKLOAD["num_steps"], WORKLOAD["volume"], 1, 1))
+    per_ray = t / (32 * 32)
+    for img in (128, 64):
+        if per_ray * img * img * n_steps <= budget_s:
+            return img
+    return 32
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    img = pick_cpu_sample(args.siren, 150.0, args.steps + args.warmup)
+    times = cpu_render_time(args.siren, img, WORKLOAD["num_steps"], WORKLOAD["volume"], args.steps, args.warmup)
+    total = sum(times)
+    value = img * img * args.steps / total
+    sample = f"batch 1 of 8, {img}x{img} rays, 24+24 samples, 64^3x32 volume per step (torch-CPU oracle port of the reference path, fp32)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, "cpu"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, where):
+    return {"workload": "generator_render_128x128_24+24spp_batch8_vol64^3x32 (BASELINE configs[1])", "siren_type": args.siren,
+            "batch_per_gpu": WORKLOAD["batch"], "img_size": WORKLOAD["img_size"], "samples_per_ray": "24+24",
+            "feature_volume": "64^3 x 32ch fp32", "precision": args.precision if where == "gpu" else "fp32",
+            "l2": "no flush: per-step working set (268 MB volume + 2 x 403 MB gathered features) exceeds the 126 MB L2",
+            "parallelism": f"rays/images sharded over {args.gpus} GPU(s), no data-path collective"}
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in open(self.path).read().splitlines():
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power)}
+
+
+def run_gpu(args):
+    import torch.distributed as dist
+
+    from conditioned_nerf_gan_b200 import _lib, ops
+    from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d
+    from oracle import nerf_path as oracle  # state init + (rank 0) cpu_baseline only
+
+    _lib.load()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, img, S, V = WORKLOAD["batch"], WORKLOAD["img_size"], WORKLOAD["num_steps"], WORKLOAD["volume"]
+    R = img * img
+    L = SIREN_LAYERS[args.siren]
+    meta = render_meta(img, S)
+    gen = ImplicitGenerator3d(args.siren, WORKLOAD["z_dim"], WORKLOAD["channels"], 4, 256)
+    gen.load_state_dict(oracle.init_generator_state(args.siren, seed=0), strict=True)
+    gen = gen.to(dev).eval()
+    gen.set_device(dev)
+    gen.siren.precision = args.precision
+    vol_h, glob_h, cam_h = (t.pin_memory() for t in synthetic_inputs(B, V, seed=rank))
+    vol, glob, cam = vol_h.to(dev), glob_h.to(dev), cam_h.to(dev)
+    torch.manual_seed(rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step_resident():
+        with torch.no_grad():
+            return gen((vol, glob), cam, **meta)
+
+    pix_h = torch.empty((B, 3, img, img), dtype=torch.float32).pin_memory()
+    dep_h = torch.empty((B, img, img), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        v, g, c = vol_h.to(dev, non_blocking=True), glob_h.to(dev, non_blocking=True), cam_h.to(dev, non_blocking=True)
+        with torch.no_grad():
+            px, dp = gen((v, g), c, **meta)
+        pix_h.copy_(px, non_blocking=True)
+        dep_h.copy_(dp, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller holds the image on the host
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = ops.launch_count
+        start.record()
+        for _ in range(steps):
+            fn()
+        end.record()
+        barrier()
+        return max_over_ranks(start.elapsed_time(end)), ops.launch_count - n0
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total, launches = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+
+    # ---- roofline leg: per-entry-point CUDA-event durations over an instrumented pass of the same steps
+    ops.kernel_events = {}
+    for _ in range(args.steps):
+        step_resident()
+    torch.cuda.synchronize()
+    per_kernel = {k: [s.elapsed_time(e) for s, e in v] for k, v in ops.kernel_events.items()}
+    ops.kernel_events = None
+    mlp_ms = float(np.mean(per_kernel["cng_film_siren_fwd"]))
+    step_kernel_ms = {k: float(np.sum(v)) / args.steps for k, v in per_kernel.items()}
+    pk = peaks()
+    flops_per_launch = mlp_flops_per_point(L) * B * R * S            # one pass (coarse or fine) per launch
+    achieved = flops_per_launch / (mlp_ms * 1e-3) / 1e12
+    peak = pk["tflops_sustained"] if args.precision == "bf16" else None
+    roofline = {"kernel": "film_siren_tc_kernel (cng_film_siren_fwd)" if args.precision == "bf16" else "film_siren_simt_kernel",
+                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": (achieved / peak) if peak else None, "traffic": None,
+                "peak_source": f"{pk['source']} bf16 sustained (kernel timed inside a long step)",
+                "flops_per_launch": flops_per_launch, "ms_per_launch": mlp_ms,
+                "share_of_step": float(np.sum(per_kernel["cng_film_siren_fwd"]) / args.steps / sum(step_kernel_ms.values())),
+                "step_ms_by_entry_point": step_kernel_ms}
+
+    if rank == 0:
+        cores = os.cpu_count() or 1
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            img_cpu = pick_cpu_sample(args.siren, 25.0, 2)
+            t = min(cpu_render_time(args.siren, img_cpu, S, V, 1, 1))
+            cpu = {"value": img_cpu * img_cpu / t, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"batch 1 of 8, {img_cpu}x{img_cpu} rays, 24+24 samples, 64^3x32 volume, 1 timed render after 1 warm-up "
+                             f"(torch-CPU oracle port of the reference path, fp32, {cores} threads)"}
+        rays = world * B * R * args.steps
+        h2d = vol_h.numel() * 4 + glob_h.numel() * 4 + cam_h.numel() * 4
+        d2h = pix_h.numel() * 4 + dep_h.numel() * 4
+        line = {
+            "metric": METRIC, "value": rays / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": workload_config(args, "gpu"),
+            "e2e": {"value": rays / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--siren", default="TALLSIREN_FG", choices=sorted(SIREN_LAYERS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        print(f"note: --warmup {args.warmup} < 3 (timing rules ask for >= 3)", file=sys.stderr)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

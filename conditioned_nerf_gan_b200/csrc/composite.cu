@@ -1,0 +1,238 @@
+// K3: alpha compositing, one warp per ray.
+//
+// Replaces fancy_integration (generators/volumetric_rendering.py:18-70) and, in the MERGE
+// instantiation, also the coarse+fine cat/sort/gather (generators/generators.py:163-167), the
+// NCHW permute + `*2-1` (:182-183) and distance2depth (:185-186).
+//
+// Each lane owns IPL consecutive samples of the (depth-sorted) ray.  Transmittance is the
+// exclusive product of (1 - alpha + 1e-10): a lane-local running product combined with a
+// multiplicative Kogge-Stone scan across lanes (5 __shfl_up_sync steps), so the S' samples of
+// a ray are read exactly once and nothing but the per-ray results goes back to HBM.
+// Algorithmic bytes per ray: S'*(16+4) read (+4*S' noise) + 16 written (+4*S' if weights).
+#include "cng_common.cuh"
+
+namespace cng {
+
+struct CompositeParams {
+  const float* rgb_sigma;        // [n_rays, S, 4]   (MERGE: coarse)
+  const float* rgb_sigma_fine;   // MERGE only: [n_rays, S, 4]
+  const float* t;                // [n_rays, S]      (MERGE: coarse)
+  const float* t_fine;           // MERGE only
+  const float* noise;            // [n_rays, n] or NULL
+  const float* rays_d_cam;       // MERGE only: [R, 3]
+  long long n_rays;
+  int S;                         // samples per input array
+  int n;                         // samples composited per ray (S, or 2S when merging)
+  int R;                         // rays per image (MERGE)
+  float noise_std;
+  int clamp_mode, white_back, last_back;
+  float* rgb;                    // [n_rays, 3] or NULL
+  float* dist;                   // [n_rays] or NULL
+  float* weights;                // [n_rays, n] or NULL
+  float* pixels;                 // MERGE: [B, 3, R]
+  float* depth;                  // MERGE: [B, R]
+  int32_t* order;                // MERGE: [n_rays, n] or NULL
+};
+
+__device__ __forceinline__ float clamp_sigma(float s, int mode) {
+  if (mode == CNG_CLAMP_RELU) return fmaxf(s, 0.f);
+  return s > 20.f ? s : log1pf(expf(s));  // F.softplus(beta=1, threshold=20)
+}
+
+constexpr int kWarpsPerBlock = 8;
+
+template <int IPL, bool MERGE>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(CompositeParams p) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long ray = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + warp;
+  if (ray >= p.n_rays) return;
+  const int n = p.n;
+  const int S = p.S;
+
+  float* raw_t = nullptr;
+  float* srt_t = nullptr;
+  int* srt_i = nullptr;
+  if (MERGE) {
+    raw_t = smem + static_cast<size_t>(warp) * 3 * n;
+    srt_t = raw_t + n;
+    srt_i = reinterpret_cast<int*>(srt_t + n);
+    const bool two = p.rgb_sigma_fine != nullptr;
+    // concatenation order of the reference: fine first, then coarse (generators.py:163-164)
+    for (int e = lane; e < n; e += 32) {
+      float te;
+      if (two) te = e < S ? __ldg(p.t_fine + ray * S + e) : __ldg(p.t + ray * S + (e - S));
+      else te = __ldg(p.t + ray * S + e);
+      raw_t[e] = te;
+    }
+    __syncwarp();
+    // stable rank = #{j : t_j < t_e} + #{j < e : t_j == t_e}
+    for (int e = lane; e < n; e += 32) {
+      const float te = raw_t[e];
+      int rank = 0;
+      for (int j = 0; j < n; ++j) {
+        const float tj = raw_t[j];
+        rank += (tj < te) || (tj == te && j < e);
+      }
+      srt_t[rank] = te;
+      srt_i[rank] = e;
+    }
+    __syncwarp();
+  }
+
+  float alpha[IPL], fac[IPL], tt[IPL], cr[IPL], cg[IPL], cb[IPL];
+  float lane_prod = 1.f;
+#pragma unroll
+  for (int i = 0; i < IPL; ++i) {
+    const int s = lane * IPL + i;
+    alpha[i] = 0.f; fac[i] = 1.f; tt[i] = 0.f; cr[i] = cg[i] = cb[i] = 0.f;
+    if (s < n) {
+      float4 c;
+      float t0, t1 = 0.f;
+      if (MERGE) {
+        t0 = srt_t[s];
+        if (s + 1 < n) t1 = srt_t[s + 1];
+        const int e = srt_i[s];
+        const float4* src = (p.rgb_sigma_fine != nullptr && e < S)
+                                ? reinterpret_cast<const float4*>(p.rgb_sigma_fine) + ray * S + e
+                                : reinterpret_cast<const float4*>(p.rgb_sigma) + ray * S + (p.rgb_sigma_fine ? e - S : e);
+        c = __ldg(src);
+        if (p.order) p.order[ray * n + s] = e;
+      } else {
+        c = __ldg(reinterpret_cast<const float4*>(p.rgb_sigma) + ray * S + s);
+        t0 = __ldg(p.t + ray * S + s);
+        if (s + 1 < n) t1 = __ldg(p.t + ray * S + s + 1);
+      }
+      const float delta = (s + 1 < n) ? (t1 - t0) : 1e10f;
+      float sg = c.w;
+      if (p.noise != nullptr) sg = sg + __ldg(p.noise + ray * n + s) * p.noise_std;
+      sg = clamp_sigma(sg, p.clamp_mode);
+      const float a = 1.f - expf(-delta * sg);
+      alpha[i] = a;
+      fac[i] = (1.f - a) + 1e-10f;
+      tt[i] = t0; cr[i] = c.x; cg[i] = c.y; cb[i] = c.z;
+      lane_prod *= fac[i];
+    }
+  }
+  // exclusive multiplicative scan of lane_prod across the warp
+  float incl = lane_prod;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl *= up;
+  }
+  float T = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) T = 1.f;
+
+  float w[IPL];
+  float wsum = 0.f;
+#pragma unroll
+  for (int i = 0; i < IPL; ++i) {
+    w[i] = alpha[i] * T;
+    T *= fac[i];
+    wsum += w[i];
+  }
+  wsum = warp_sum(wsum);
+  if (p.last_back) {
+    // weights[:, :, -1] += 1 - weights_sum   (volumetric_rendering.py:54-55)
+    const int s_last = n - 1;
+    if (lane == s_last / IPL) {
+#pragma unroll
+      for (int i = 0; i < IPL; ++i)
+        if (lane * IPL + i == s_last) w[i] += 1.f - wsum;
+    }
+  }
+  float ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f;
+#pragma unroll
+  for (int i = 0; i < IPL; ++i) {
+    ar += w[i] * cr[i]; ag += w[i] * cg[i]; ab += w[i] * cb[i]; ad += w[i] * tt[i];
+    const int s = lane * IPL + i;
+    if (p.weights != nullptr && s < n) p.weights[ray * n + s] = w[i];
+  }
+  ar = warp_sum(ar); ag = warp_sum(ag); ab = warp_sum(ab); ad = warp_sum(ad);
+  if (p.white_back) { const float bg = 1.f - wsum; ar = ar + bg; ag = ag + bg; ab = ab + bg; }
+  if (lane == 0) {
+    if (p.rgb) { p.rgb[ray * 3 + 0] = ar; p.rgb[ray * 3 + 1] = ag; p.rgb[ray * 3 + 2] = ab; }
+    if (p.dist) p.dist[ray] = ad;
+    if (MERGE) {
+      const long long b = ray / p.R;
+      const int r = static_cast<int>(ray - b * p.R);
+      if (p.pixels) {
+        float* px = p.pixels + b * 3 * p.R + r;
+        px[0] = ar * 2.f - 1.f; px[p.R] = ag * 2.f - 1.f; px[2 * static_cast<size_t>(p.R)] = ab * 2.f - 1.f;
+      }
+      if (p.depth) p.depth[ray] = __ldg(p.rays_d_cam + 3 * r + 2) * ad;
+    }
+  }
+}
+
+template <bool MERGE>
+static int launch_composite(const CompositeParams& p, cudaStream_t stream) {
+  const int ipl = (p.n + 31) / 32;
+  const unsigned grid = static_cast<unsigned>((p.n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  const size_t smem = MERGE ? static_cast<size_t>(kWarpsPerBlock) * 3 * p.n * sizeof(float) : 0;
+#define CNG_LAUNCH(I)                                                                              \
+  {                                                                                               \
+    if (smem > 48 * 1024)                                                                         \
+      cudaFuncSetAttribute(composite_kernel<I, MERGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    composite_kernel<I, MERGE><<<grid, kWarpsPerBlock * 32, smem, stream>>>(p);                   \
+  }
+  if (ipl <= 1) CNG_LAUNCH(1)
+  else if (ipl <= 2) CNG_LAUNCH(2)
+  else if (ipl <= 4) CNG_LAUNCH(4)
+  else if (ipl <= 8) CNG_LAUNCH(8)
+  else if (ipl <= 16) CNG_LAUNCH(16)
+  else CNG_LAUNCH(32)
+#undef CNG_LAUNCH
+  return check_launch(MERGE ? "cng_merge_composite" : "cng_composite_fwd");
+}
+
+}  // namespace cng
+
+extern "C" {
+
+int cng_composite_fwd(const float* rgb_sigma, const float* t, const float* noise, long long n_rays, int S,
+                      float noise_std, int clamp_mode, int white_back, int last_back, float* rgb, float* dist,
+                      float* weights, cng_stream_t stream) {
+  CNG_REQUIRE(rgb_sigma && t, CNG_ERR_INVALID_ARGUMENT, "composite_fwd: NULL input");
+  CNG_REQUIRE(n_rays >= 0 && S >= 1, CNG_ERR_INVALID_ARGUMENT, "composite_fwd: n_rays=%lld S=%d", n_rays, S);
+  CNG_REQUIRE(S <= 1024, CNG_ERR_UNSUPPORTED, "composite_fwd: S=%d > 1024", S);
+  CNG_REQUIRE(clamp_mode == CNG_CLAMP_RELU || clamp_mode == CNG_CLAMP_SOFTPLUS, CNG_ERR_INVALID_ARGUMENT,
+              "composite_fwd: Need to choose clamp mode");
+  CNG_REQUIRE(n_rays / cng::kWarpsPerBlock < 0x7fffffffLL, CNG_ERR_UNSUPPORTED, "composite_fwd: too many rays");
+  if (n_rays == 0) return CNG_OK;
+  if (int e = cng_device_check()) return e;
+  cng::CompositeParams p{};
+  p.rgb_sigma = rgb_sigma; p.t = t; p.noise = (noise_std != 0.f) ? noise : nullptr;
+  CNG_REQUIRE(noise_std == 0.f || noise, CNG_ERR_INVALID_ARGUMENT, "composite_fwd: noise_std != 0 needs noise");
+  p.n_rays = n_rays; p.S = S; p.n = S; p.R = 1; p.noise_std = noise_std; p.clamp_mode = clamp_mode;
+  p.white_back = white_back; p.last_back = last_back; p.rgb = rgb; p.dist = dist; p.weights = weights;
+  return cng::launch_composite<false>(p, cng::as_stream(stream));
+}
+
+int cng_merge_composite(const float* rgb_sigma_fine, const float* rgb_sigma_coarse, const float* t_fine,
+                        const float* t_coarse, const float* noise, const float* rays_d_cam, int B, int R, int S,
+                        float noise_std, int clamp_mode, int white_back, int last_back, float* pixels, float* depth,
+                        float* rgb, float* dist, int32_t* order, cng_stream_t stream) {
+  CNG_REQUIRE(rgb_sigma_coarse && t_coarse && rays_d_cam, CNG_ERR_INVALID_ARGUMENT, "merge_composite: NULL input");
+  CNG_REQUIRE((rgb_sigma_fine == nullptr) == (t_fine == nullptr), CNG_ERR_INVALID_ARGUMENT,
+              "merge_composite: fine rgb_sigma and fine t must both be given or both be NULL");
+  CNG_REQUIRE(B >= 0 && R >= 1 && S >= 1, CNG_ERR_INVALID_ARGUMENT, "merge_composite: B=%d R=%d S=%d", B, R, S);
+  const int n = rgb_sigma_fine ? 2 * S : S;
+  CNG_REQUIRE(n <= 512, CNG_ERR_UNSUPPORTED, "merge_composite: %d samples per ray > 512", n);
+  CNG_REQUIRE(clamp_mode == CNG_CLAMP_RELU || clamp_mode == CNG_CLAMP_SOFTPLUS, CNG_ERR_INVALID_ARGUMENT,
+              "merge_composite: Need to choose clamp mode");
+  CNG_REQUIRE(noise_std == 0.f || noise, CNG_ERR_INVALID_ARGUMENT, "merge_composite: noise_std != 0 needs noise");
+  if (B == 0) return CNG_OK;
+  if (int e = cng_device_check()) return e;
+  cng::CompositeParams p{};
+  p.rgb_sigma = rgb_sigma_coarse; p.rgb_sigma_fine = rgb_sigma_fine; p.t = t_coarse; p.t_fine = t_fine;
+  p.noise = (noise_std != 0.f) ? noise : nullptr; p.rays_d_cam = rays_d_cam;
+  p.n_rays = static_cast<long long>(B) * R; p.S = S; p.n = n; p.R = R; p.noise_std = noise_std;
+  p.clamp_mode = clamp_mode; p.white_back = white_back; p.last_back = last_back;
+  p.rgb = rgb; p.dist = dist; p.weights = nullptr; p.pixels = pixels; p.depth = depth; p.order = order;
+  return cng::launch_composite<true>(p, cng::as_stream(stream));
+}
+
+}  // extern "C"

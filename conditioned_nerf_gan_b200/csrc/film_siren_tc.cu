@@ -1,0 +1,539 @@
+// K2 (throughput mode): FiLM-SIREN MLP on the 5th-gen tensor cores (tcgen05 + TMEM), all layers
+// fused, activations never leave the SM.
+//
+// Replaces, for the FG SIREN family (generators/siren.py:491-580, :583-668, :744-827, :983-1065):
+//   per layer  x = sin(freq * (x W^T + b) + phase)      FiLMLayer.forward :146-160
+//   head       rgb_sigma = [sigmoid](x Wf^T + bf)        :579 / :1064, _sigmoid_rgb :1227-1234
+//
+// Math as executed here
+//   * FiLM is folded into the operands once per forward (film_fold_kernel): W'_{b,l} =
+//     diag(freq_{b,l}) W_l rounded to bf16, shift_{b,l} = freq*b + phase kept in fp32, so the
+//     epilogue is sin(acc + shift) on the fp32 TMEM accumulator (the pre-activation is never
+//     rounded to bf16 -- SURVEY.md section 7 "precision of the MLP").
+//   * layer 0 (K = C = 32) runs as split-bf16: A = [x_hi | x_lo], B = [W'_hi | W'_hi] plus
+//     A = [x_hi], B = [W'_lo]  (hi*hi + lo*hi + hi*lo, ~2^-16 relative), because its rounding
+//     error is amplified by every later layer.
+//   * hidden layers: bf16 x bf16 -> fp32, K = 256 as 4 K-blocks of 64.
+//   * head: one N=16 MMA group (rows 4..15 of the operand are zero), bias + sigmoid in the epilogue.
+//
+// Kernel organisation (one persistent CTA per SM, 320 threads, cta_group::1)
+//   warps 0-3  epilogue of tile slot 0      warps 4-7  epilogue of tile slot 1
+//   warp  8    MMA issuer (one elected lane) + TMEM allocator
+//   warp  9    weight producer: cp.async.bulk (TMA unit, SASS UBLKCP) global -> smem ring,
+//              completion on mbarriers (complete_tx)
+//   Two 128-point tiles are in flight per CTA ("ping-pong"): while the tensor pipe runs layer l
+//   of one tile, the epilogue warps of the other tile run sin() on their accumulator and write
+//   the next layer's bf16 A operand back into shared memory (128B-swizzled, K-major), so MUFU and
+//   tensor pipe overlap.  TMEM: 2 accumulators x 256 fp32 columns = all 512 columns.
+//   Shared memory: 2 x 64 KB A tiles + 3 x 32 KB weight ring + 2 KB shift + barriers = 226.3 KB.
+//   Weight K-blocks are stored in global memory as ready-made shared-memory images (already
+//   swizzled) so a block is one contiguous 32 KB bulk copy; no tensor map is needed.
+//
+// Roofline: 2*(32*256*3 + 7*256^2 + 256*16) flop per point issued (algorithmic 935 936), 2048
+// sin per point.  Per 128-point tile-layer: 16 MMAs (128x256x16) = 2048 tensor cycles and 32768
+// sin = 2048 MUFU cycles at 16/clk/SM: the two pipes are balanced by construction.
+#include <cuda_bf16.h>
+
+#include "cng_common.cuh"
+
+namespace cng {
+
+constexpr int kHID = 256;
+constexpr int kC0 = 32;
+constexpr int kTileM = 128;
+constexpr int kChunkBytes = 32768;          // [256 n][64 k] bf16
+constexpr int kHeadBytes = 8192;            // 4 x [16 n][64 k] bf16
+constexpr int kABlockBytes = 16384;         // [128 m][64 k] bf16
+constexpr int kATileBytes = 4 * kABlockBytes;
+constexpr int kRing = 3;
+constexpr int kNumThreads = 320;
+constexpr uint32_t kSmemA = 0;
+constexpr uint32_t kSmemW = 2 * kATileBytes;                         // 131072
+constexpr uint32_t kSmemShift = kSmemW + kRing * kChunkBytes;        // 229376
+constexpr uint32_t kSmemBar = kSmemShift + 2 * kHID * 4;             // 231424
+constexpr uint32_t kSmemTotal = kSmemBar + 128;                      // 231552 <= 232448
+
+// ---- workspace layout ------------------------------------------------------------------------
+// per item: [L0c0][L0c1][L1c0..L1c3]...[L(L-1)c3][head]  then, after all items, shift[B][L][256]
+__host__ __device__ inline size_t item_image_bytes(int L) {
+  return static_cast<size_t>(2 + 4 * (L - 1)) * kChunkBytes + kHeadBytes;
+}
+__host__ __device__ inline size_t chunk_offset(int L, int l, int c) {     // l == L -> head
+  if (l == 0) return static_cast<size_t>(c) * kChunkBytes;
+  if (l < L) return static_cast<size_t>(2 + 4 * (l - 1) + c) * kChunkBytes;
+  return static_cast<size_t>(2 + 4 * (L - 1)) * kChunkBytes;
+}
+
+// byte offset of bf16 element (row, k) inside a [rows][64] K-major SWIZZLE_128B block
+__host__ __device__ inline uint32_t sw128_offset(int row, int k) {
+  return static_cast<uint32_t>(row) * 128u + ((((static_cast<uint32_t>(k) >> 3) ^ (row & 7)) << 4)) + (k & 7) * 2u;
+}
+
+// ---- fold kernel ---------------------------------------------------------------------------------
+struct FoldParams {
+  const float* w[16];
+  const float* b[16];
+  const float* freq;      // [B, L*HID]
+  const float* phase;     // [B, L*HID]
+  const float* final_w;   // [4, HID]
+  int B, L;
+  uint8_t* images;        // [B][item_image_bytes]
+  float* shift;           // [B][L][HID]
+};
+
+// one thread per (item, layer, row n, 8 consecutive k)
+__global__ void __launch_bounds__(256) film_fold_kernel(FoldParams p) {
+  const int L = p.L;
+  const long long per_item = 256LL * 4 /*layer0: 32/8*/ + static_cast<long long>(L - 1) * 256 * 32 + 16 * 32 /*head*/;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= per_item * p.B) return;
+  const int item = static_cast<int>(gid / per_item);
+  long long e = gid - static_cast<long long>(item) * per_item;
+  uint8_t* img = p.images + static_cast<size_t>(item) * item_image_bytes(L);
+  if (e < 256 * 4) {                                   // ---- layer 0: split bf16
+    const int n = static_cast<int>(e >> 2), k0 = static_cast<int>(e & 3) * 8;
+    const float fq = __ldg(p.freq + (static_cast<size_t>(item) * L + 0) * kHID + n);
+    __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = fq * __ldg(p.w[0] + n * kC0 + k0 + j);
+      hi[j] = __float2bfloat16_rn(v);
+      lo[j] = __float2bfloat16_rn(v - __bfloat162float(hi[j]));
+    }
+    uint8_t* c0 = img + chunk_offset(L, 0, 0);
+    uint8_t* c1 = img + chunk_offset(L, 0, 1);
+    *reinterpret_cast<uint4*>(c0 + sw128_offset(n, k0)) = *reinterpret_cast<uint4*>(hi);        // pairs with x_hi
+    *reinterpret_cast<uint4*>(c0 + sw128_offset(n, 32 + k0)) = *reinterpret_cast<uint4*>(hi);   // pairs with x_lo
+    *reinterpret_cast<uint4*>(c1 + sw128_offset(n, k0)) = *reinterpret_cast<uint4*>(lo);        // pairs with x_hi
+    *reinterpret_cast<uint4*>(c1 + sw128_offset(n, 32 + k0)) = make_uint4(0, 0, 0, 0);
+    if (k0 == 0) {
+      const float bias = __ldg(p.b[0] + n), ph = __ldg(p.phase + (static_cast<size_t>(item) * L + 0) * kHID + n);
+      p.shift[(static_cast<size_t>(item) * L + 0) * kHID + n] = __fadd_rn(__fmul_rn(fq, bias), ph);
+    }
+    return;
+  }
+  e -= 256 * 4;
+  if (e < static_cast<long long>(L - 1) * 256 * 32) {  // ---- hidden layers
+    const int l = 1 + static_cast<int>(e / (256 * 32));
+    const int r = static_cast<int>(e % (256 * 32));
+    const int n = r >> 5, k0 = (r & 31) * 8;
+    const float fq = __ldg(p.freq + (static_cast<size_t>(item) * L + l) * kHID + n);
+    __nv_bfloat16 hi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hi[j] = __float2bfloat16_rn(fq * __ldg(p.w[l] + n * kHID + k0 + j));
+    uint8_t* c = img + chunk_offset(L, l, k0 >> 6);
+    *reinterpret_cast<uint4*>(c + sw128_offset(n, k0 & 63)) = *reinterpret_cast<uint4*>(hi);
+    if (k0 == 0) {
+      const float bias = __ldg(p.b[l] + n), ph = __ldg(p.phase + (static_cast<size_t>(item) * L + l) * kHID + n);
+      p.shift[(static_cast<size_t>(item) * L + l) * kHID + n] = __fadd_rn(__fmul_rn(fq, bias), ph);
+    }
+    return;
+  }
+  e -= static_cast<long long>(L - 1) * 256 * 32;
+  {                                                    // ---- head: [16 n][256 k], rows >= 4 zero
+    const int n = static_cast<int>(e >> 5), k0 = static_cast<int>(e & 31) * 8;
+    __nv_bfloat16 hi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hi[j] = __float2bfloat16_rn(n < 4 ? __ldg(p.final_w + n * kHID + k0 + j) : 0.f);
+    uint8_t* c = img + chunk_offset(L, L, 0) + (k0 >> 6) * 2048;
+    *reinterpret_cast<uint4*>(c + sw128_offset(n, k0 & 63)) = *reinterpret_cast<uint4*>(hi);
+  }
+}
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Spin on try_wait; a protocol bug turns into a trap (launch failure) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 in
+// [0,14), LBO>>4 in [16,30) (=1, unused for swizzled K-major), SBO>>4 in [32,46) (8 rows x 128 B =
+// 1024), version=1 at bit 46, layout_type=2 (SWIZZLE_128B) at [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), K-major both, N>>3 at 17, M>>4 at 24
+__device__ __forceinline__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+#define CNG_TMEM_LD_32(taddr, v)                                                                                      \
+  asm volatile(                                                                                                       \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                       \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                       \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                       \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),   \
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),        \
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),       \
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                     \
+      : "r"(taddr)                                                                                                    \
+      : "memory")
+
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // first source -> upper half
+  return r;
+}
+
+struct TcParams {
+  const float* feat;        // [B, N, 32]
+  long long N;
+  int B, L;
+  const uint8_t* images;    // fold output
+  const float* shift;       // [B][L][256]
+  const float* final_b;     // [4]
+  int sigmoid_rgb;
+  float* out;               // [B, N, 4]
+  long long tiles_per_item;
+  long long total_tiles;
+};
+
+struct TileInfo {
+  int item;
+  long long n0;
+  int rows;
+};
+__device__ __forceinline__ TileInfo tile_info(const TcParams& p, long long t) {
+  TileInfo ti;
+  ti.item = static_cast<int>(t / p.tiles_per_item);
+  ti.n0 = (t - static_cast<long long>(ti.item) * p.tiles_per_item) * kTileM;
+  ti.rows = static_cast<int>(min(static_cast<long long>(kTileM), p.N - ti.n0));
+  return ti;
+}
+
+__global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t s_base = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = p.L;
+  const uint32_t bar0 = s_base + kSmemBar;
+  // barriers: w_full[3] @0, w_empty[3] @24, act_ready[2] @48, acc_full[2] @64, tmem ptr @96
+  auto w_full = [&](int s) { return bar0 + 8u * s; };
+  auto w_empty = [&](int s) { return bar0 + 24u + 8u * s; };
+  auto act_ready = [&](int x) { return bar0 + 48u + 8u * x; };
+  auto acc_full = [&](int x) { return bar0 + 64u + 8u * x; };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemBar + 96);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kRing; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+    for (int x = 0; x < 2; ++x) { mbar_init(act_ready(x), 128); mbar_init(acc_full(x), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_base + kSmemBar + 96), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const long long G = gridDim.x;
+  const long long first = blockIdx.x;
+
+  if (warp == 9) {
+    // =========================== weight producer ===========================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      for (long long t0 = first; t0 < p.total_tiles; t0 += 2 * G) {
+        const int nx = (t0 + G < p.total_tiles) ? 2 : 1;
+        int items[2];
+        items[0] = static_cast<int>(t0 / p.tiles_per_item);
+        items[1] = nx == 2 ? static_cast<int>((t0 + G) / p.tiles_per_item) : 0;
+        for (int l = 0; l <= L; ++l) {
+          const int nchunks = (l == 0) ? 2 : (l < L ? 4 : 1);
+          const uint32_t bytes = (l < L) ? kChunkBytes : kHeadBytes;
+          for (int x = 0; x < nx; ++x) {
+            const uint8_t* img = p.images + static_cast<size_t>(items[x]) * item_image_bytes(L);
+            for (int c = 0; c < nchunks; ++c) {
+              mbar_wait(w_empty(slot), phase ^ 1);
+              mbar_arrive_expect_tx(w_full(slot), bytes);
+              bulk_g2s(s_base + kSmemW + slot * kChunkBytes, img + chunk_offset(L, l, c), bytes, w_full(slot));
+              if (++slot == kRing) { slot = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      uint32_t act_phase[2] = {0, 0};
+      constexpr uint32_t idesc_main = make_idesc(128, 256);
+      constexpr uint32_t idesc_head = make_idesc(128, 16);
+      for (long long t0 = first; t0 < p.total_tiles; t0 += 2 * G) {
+        const int nx = (t0 + G < p.total_tiles) ? 2 : 1;
+        for (int l = 0; l <= L; ++l) {
+          const int nchunks = (l == 0) ? 2 : (l < L ? 4 : 1);
+          for (int x = 0; x < nx; ++x) {
+            mbar_wait(act_ready(x), act_phase[x]);
+            act_phase[x] ^= 1;
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(x) * kHID;
+            const uint32_t a_base = s_base + kSmemA + x * kATileBytes;
+            for (int c = 0; c < nchunks; ++c) {
+              mbar_wait(w_full(slot), phase);
+              tc_fence_after();
+              const uint32_t b_base = s_base + kSmemW + slot * kChunkBytes;
+              if (l < L) {
+                // layer 0: chunk 0 = 4 k-steps over [x_hi|x_lo], chunk 1 = 2 k-steps over [x_hi]
+                const int ksteps = (l == 0 && c == 1) ? 2 : 4;
+                const uint32_t a_blk = a_base + (l == 0 ? 0 : c * kABlockBytes);
+                for (int ks = 0; ks < ksteps; ++ks)
+                  tc_mma_bf16(d_tmem, make_desc(a_blk + ks * 32), make_desc(b_base + ks * 32), idesc_main, (c | ks) ? 1u : 0u);
+              } else {
+                for (int kb = 0; kb < 4; ++kb)
+                  for (int ks = 0; ks < 4; ++ks)
+                    tc_mma_bf16(d_tmem, make_desc(a_base + kb * kABlockBytes + ks * 32), make_desc(b_base + kb * 2048 + ks * 32),
+                                idesc_head, (kb | ks) ? 1u : 0u);
+              }
+              tc_commit(w_empty(slot));          // slot is free once these MMAs have read it
+              if (++slot == kRing) { slot = 0; phase ^= 1; }
+            }
+            tc_commit(acc_full(x));              // accumulator of tile x complete
+          }
+        }
+      }
+    }
+  } else {
+    // =========================== epilogue warps (slot x = warp / 4) ===========================
+    const int x = warp >> 2;
+    const int q = warp & 3;                       // TMEM lane quarter == warp_id % 4
+    const int row = q * 32 + lane;
+    const uint32_t a_base = kSmemA + x * kATileBytes;
+    float* shift_s = reinterpret_cast<float*>(smem + kSmemShift) + x * kHID;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(x) * kHID;
+    uint32_t acc_phase = 0;
+    const int tid_x = threadIdx.x & 127;
+    for (long long t = first + x * G; t < p.total_tiles; t += 2 * G) {
+      const TileInfo ti = tile_info(p, t);
+      // ---- features -> A block 0 as [x_hi(32) | x_lo(32)] ----
+      {
+        const float4* f = reinterpret_cast<const float4*>(p.feat + (static_cast<size_t>(ti.item) * p.N + ti.n0) * kC0);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = q * 32 + it * 4 + (lane >> 3);
+          const int c4 = lane & 7;                               // float4 index within the row: k = 4*c4
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < ti.rows) v = __ldg(f + r * 8 + c4);
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
+                              h3 = __float2bfloat16_rn(v.w);
+          uint2 hi, lo;
+          hi.x = pack_bf16(v.x, v.y); hi.y = pack_bf16(v.z, v.w);
+          lo.x = pack_bf16(v.x - __bfloat162float(h0), v.y - __bfloat162float(h1));
+          lo.y = pack_bf16(v.z - __bfloat162float(h2), v.w - __bfloat162float(h3));
+          *reinterpret_cast<uint2*>(smem + a_base + sw128_offset(r, 4 * c4)) = hi;
+          *reinterpret_cast<uint2*>(smem + a_base + sw128_offset(r, 32 + 4 * c4)) = lo;
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(act_ready(x));
+      for (int l = 0; l < L; ++l) {
+        // ---- this layer's shift vector -> smem (all 4 warps of the slot are past the previous one) ----
+        named_bar_sync(1 + x, 128);
+        reinterpret_cast<float2*>(shift_s)[tid_x] =
+            __ldg(reinterpret_cast<const float2*>(p.shift + (static_cast<size_t>(ti.item) * L + l) * kHID) + tid_x);
+        named_bar_sync(1 + x, 128);
+        mbar_wait(acc_full(x), acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < 8; ++cc) {
+          uint32_t v[32];
+          CNG_TMEM_LD_32(t_lane + cc * 32, v);
+          tmem_ld_wait();
+          uint32_t o[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 sh = *reinterpret_cast<const float4*>(shift_s + cc * 32 + j);
+            const float a0 = __sinf(__uint_as_float(v[j + 0]) + sh.x);
+            const float a1 = __sinf(__uint_as_float(v[j + 1]) + sh.y);
+            const float a2 = __sinf(__uint_as_float(v[j + 2]) + sh.z);
+            const float a3 = __sinf(__uint_as_float(v[j + 3]) + sh.w);
+            o[j / 2] = pack_bf16(a0, a1);
+            o[j / 2 + 1] = pack_bf16(a2, a3);
+          }
+          // 32 columns = 64 bytes = 4 x 16-byte chunks of K-block cc/2, logical chunk (cc&1)*4 + i
+          uint8_t* blk = smem + a_base + (cc >> 1) * kABlockBytes + row * 128;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int chunk = ((cc & 1) * 4 + i) ^ (row & 7);
+            *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        mbar_arrive(act_ready(x));
+      }
+      // ---- head: 4 accumulator columns -> bias, sigmoid(rgb), store ----
+      mbar_wait(acc_full(x), acc_phase);
+      acc_phase ^= 1;
+      tc_fence_after();
+      {
+        uint32_t r0, r1, r2, r3;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                     : "r"(t_lane)
+                     : "memory");
+        tmem_ld_wait();
+        float4 o;
+        const float4 fb = __ldg(reinterpret_cast<const float4*>(p.final_b));
+        o.x = __uint_as_float(r0) + fb.x;
+        o.y = __uint_as_float(r1) + fb.y;
+        o.z = __uint_as_float(r2) + fb.z;
+        o.w = __uint_as_float(r3) + fb.w;
+        if (p.sigmoid_rgb) {
+          o.x = 1.f / (1.f + __expf(-o.x));
+          o.y = 1.f / (1.f + __expf(-o.y));
+          o.z = 1.f / (1.f + __expf(-o.z));
+        }
+        if (row < ti.rows) reinterpret_cast<float4*>(p.out)[static_cast<size_t>(ti.item) * p.N + ti.n0 + row] = o;
+      }
+      tc_fence_before();   // orders the TMEM reads above before the next tile's first MMA (via act_ready)
+    }
+  }
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+size_t film_siren_tc_workspace(int B, int L) {
+  return static_cast<size_t>(B) * item_image_bytes(L) + static_cast<size_t>(B) * L * kHID * sizeof(float);
+}
+
+int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, int L, const float* const* w,
+                         const float* const* b, const float* freq, const float* phase, const float* final_w,
+                         const float* final_b_dev, int sigmoid_rgb, void* workspace, size_t workspace_bytes, float* out,
+                         cudaStream_t stream) {
+  CNG_REQUIRE(HID == kHID && C == kC0, CNG_ERR_UNSUPPORTED, "film_siren_fwd(bf16): needs HID=256, C=32 (got %d, %d)", HID, C);
+  CNG_REQUIRE(L >= 1 && L <= 16, CNG_ERR_UNSUPPORTED, "film_siren_fwd(bf16): L=%d", L);
+  CNG_REQUIRE(workspace != nullptr && workspace_bytes >= film_siren_tc_workspace(B, L), CNG_ERR_WORKSPACE,
+              "film_siren_fwd(bf16): workspace %zu < %zu bytes", workspace_bytes, film_siren_tc_workspace(B, L));
+  CNG_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 127) == 0, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd(bf16): workspace not 128-byte aligned");
+  CNG_REQUIRE((reinterpret_cast<uintptr_t>(feat) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, CNG_ERR_INVALID_ARGUMENT,
+              "film_siren_fwd(bf16): feat/out not 16-byte aligned");
+  FoldParams fp{};
+  for (int l = 0; l < L; ++l) { fp.w[l] = w[l]; fp.b[l] = b[l]; }
+  fp.freq = freq; fp.phase = phase; fp.final_w = final_w; fp.B = B; fp.L = L;
+  fp.images = static_cast<uint8_t*>(workspace);
+  fp.shift = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + static_cast<size_t>(B) * item_image_bytes(L));
+  const long long per_item = 256LL * 4 + static_cast<long long>(L - 1) * 256 * 32 + 16 * 32;
+  const long long fold_threads = per_item * B;
+  film_fold_kernel<<<static_cast<unsigned>((fold_threads + 255) / 256), 256, 0, stream>>>(fp);
+  if (int e = check_launch("cng_film_siren_fwd(bf16): fold")) return e;
+
+  TcParams p{};
+  p.feat = feat; p.N = N; p.B = B; p.L = L; p.images = fp.images; p.shift = fp.shift;
+  CNG_REQUIRE((reinterpret_cast<uintptr_t>(final_b_dev) & 15) == 0, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd(bf16): final_b not 16-byte aligned");
+  p.final_b = final_b_dev;
+  cudaError_t ce = cudaSuccess;
+  p.sigmoid_rgb = sigmoid_rgb; p.out = out;
+  p.tiles_per_item = (N + kTileM - 1) / kTileM;
+  p.total_tiles = p.tiles_per_item * B;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ce = cudaFuncSetAttribute(film_siren_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTotal));
+    if (ce != cudaSuccess) return fail(static_cast<int>(ce), "film_siren_fwd(bf16): smem attribute: %s", cudaGetErrorString(ce));
+    attr_set = true;
+  }
+  const long long grid = min(static_cast<long long>(sm_count()), p.total_tiles);
+  film_siren_tc_kernel<<<static_cast<unsigned>(grid), kNumThreads, kSmemTotal, stream>>>(p);
+  return check_launch("cng_film_siren_fwd(bf16)");
+}
+
+// defined in film_siren_simt.cu
+int film_siren_simt_launch(const float* feat, int B, long long N, int C, int HID, int L, const float* const* w,
+                           const float* const* b, const float* freq, const float* phase, const float* final_w,
+                           const float* final_b, int sigmoid_rgb, float* out, cudaStream_t stream);
+
+}  // namespace cng
+
+extern "C" {
+
+size_t cng_film_siren_workspace_bytes(int B, int C, int HID, int L, int precision) {
+  (void)C; (void)HID;
+  if (precision != CNG_PREC_BF16 || B <= 0 || L <= 0) return 0;
+  return cng::film_siren_tc_workspace(B, L);
+}
+
+int cng_film_siren_fwd(const float* feat, int B, long long N, int C, int HID, int L, const float* const* layer_w_host,
+                       const float* const* layer_b_host, const float* freq, const float* phase, const float* final_w,
+                       const float* final_b, int sigmoid_rgb, int precision, void* workspace, size_t workspace_bytes,
+                       float* rgb_sigma, cng_stream_t stream) {
+  CNG_REQUIRE(feat && layer_w_host && layer_b_host && freq && phase && final_w && final_b && rgb_sigma,
+              CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd: NULL pointer");
+  CNG_REQUIRE(B >= 0 && N >= 0 && C >= 1 && HID >= 1 && L >= 1, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd: bad shape");
+  for (int l = 0; l < L && l < 16; ++l)
+    CNG_REQUIRE(layer_w_host[l] && layer_b_host[l], CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd: NULL layer %d", l);
+  if (B == 0 || N == 0) return CNG_OK;
+  if (int e = cng_device_check()) return e;
+  if (precision == CNG_PREC_FP32)
+    return cng::film_siren_simt_launch(feat, B, N, C, HID, L, layer_w_host, layer_b_host, freq, phase, final_w, final_b,
+                                       sigmoid_rgb, rgb_sigma, cng::as_stream(stream));
+  if (precision == CNG_PREC_BF16)
+    return cng::film_siren_tc_launch(feat, B, N, C, HID, L, layer_w_host, layer_b_host, freq, phase, final_w, final_b,
+                                     sigmoid_rgb, workspace, workspace_bytes, rgb_sigma, cng::as_stream(stream));
+  return cng::fail(CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd: unknown precision %d", precision);
+}
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+// K4: inverse-CDF importance resampling, one warp per ray, CDF + binary search in shared memory.
+//
+// Replaces sample_pdf (generators/volumetric_rendering.py:297-342, det=False) and, in the
+// FROM_COARSE instantiation, its call site (generators/generators.py:123-136: midpoints of the
+// coarse distances as bins, weights[1:-1] + 1e-5 as weights).
+//
+// Bit-exactness contract (oracle/nerf_path.py::resample_pdf): the weight sum and the CDF are
+// accumulated sequentially in float64 and rounded to fp32 per element -- which is what
+// torch.cumsum does for fp32 on CPU -- so the searchsorted indices are reproducible bit for bit.
+// One lane walks the row (M <= ~100 in production; the row lives in shared memory), all lanes
+// then divide, search and interpolate in parallel with IEEE fp32 ops in the reference's order
+// (no FMA contraction: every op is an explicit __f*_rn intrinsic).
+// Algorithmic bytes per ray: 4*((M+1) + M + K) read + 4*K written (+8*K if indices are emitted).
+#include "cng_common.cuh"
+
+namespace cng {
+
+struct PdfParams {
+  const float* bins;      // [n, M+1]            (FROM_COARSE: t_coarse [n, S])
+  const float* weights;   // [n, M]              (FROM_COARSE: raw coarse weights [n, S])
+  const float* u;         // [n, K]
+  long long n;
+  int M, K, S;
+  float eps;
+  float* samples;         // [n, K]
+  int64_t* inds;          // [n, K] or NULL
+};
+
+constexpr int kPdfWarps = 8;
+
+template <bool FROM_COARSE>
+__global__ void __launch_bounds__(kPdfWarps * 32) sample_pdf_kernel(PdfParams p) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long ray = static_cast<long long>(blockIdx.x) * kPdfWarps + warp;
+  if (ray >= p.n) return;
+  const int M = p.M;
+  const int stride = 2 * (M + 1) + 2;           // cdf[M+1], bins[M+1]
+  float* cdf = smem + static_cast<size_t>(warp) * stride;
+  float* bins = cdf + (M + 1);
+
+  // ---- load bins and weights (+eps) -------------------------------------------------------
+  if (FROM_COARSE) {
+    const float* tc = p.bins + ray * p.S;
+    const float* wc = p.weights + ray * p.S;
+    for (int j = lane; j <= M; j += 32)           // z_vals_mid = 0.5 * (z[:-1] + z[1:])   (:126)
+      bins[j] = __fmul_rn(0.5f, __fadd_rn(__ldg(tc + j), __ldg(tc + j + 1)));
+    for (int j = lane; j < M; j += 32)            // (weights + 1e-5)[1:-1], then + eps     (:124, :311)
+      cdf[j + 1] = __fadd_rn(__fadd_rn(__ldg(wc + j + 1), 1e-5f), p.eps);
+  } else {
+    for (int j = lane; j <= M; j += 32) bins[j] = __ldg(p.bins + ray * (M + 1) + j);
+    for (int j = lane; j < M; j += 32) cdf[j + 1] = __fadd_rn(__ldg(p.weights + ray * M + j), p.eps);
+  }
+  __syncwarp();
+  // ---- total (float64 sequential, one lane) ------------------------------------------------
+  float total;
+  {
+    double acc = 0.0;
+    if (lane == 0)
+      for (int j = 1; j <= M; ++j) acc += static_cast<double>(cdf[j]);
+    total = __shfl_sync(0xffffffffu, static_cast<float>(acc), 0);
+  }
+  // ---- pdf = w / total (parallel), cdf = cumsum in float64 (one lane) ----------------------
+  for (int j = lane + 1; j <= M; j += 32) cdf[j] = __fdiv_rn(cdf[j], total);
+  __syncwarp();
+  if (lane == 0) {
+    double acc = 0.0;
+    cdf[0] = 0.f;
+    for (int j = 1; j <= M; ++j) {
+      acc += static_cast<double>(cdf[j]);
+      cdf[j] = static_cast<float>(acc);
+    }
+  }
+  __syncwarp();
+  // ---- searchsorted(cdf, u, right=False) + lerp ---------------------------------------------
+  for (int k = lane; k < p.K; k += 32) {
+    const float u = __ldg(p.u + ray * p.K + k);
+    int lo = 0, hi = M + 1;                       // first i in [0, M+1] with cdf[i] >= u
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cdf[mid] < u) lo = mid + 1; else hi = mid;
+    }
+    const int ind = lo;
+    const int below = max(ind - 1, 0);
+    const int above = min(ind, M);
+    const float c0 = cdf[below], c1 = cdf[above];
+    const float b0 = bins[below], b1 = bins[above];
+    float denom = __fsub_rn(c1, c0);
+    if (denom < p.eps) denom = 1.f;
+    const float frac = __fdiv_rn(__fsub_rn(u, c0), denom);
+    p.samples[ray * p.K + k] = __fadd_rn(b0, __fmul_rn(frac, __fsub_rn(b1, b0)));
+    if (p.inds) p.inds[ray * p.K + k] = ind;
+  }
+}
+
+template <bool FROM_COARSE>
+static int launch_pdf(const PdfParams& p, cudaStream_t stream, const char* what) {
+  const unsigned grid = static_cast<unsigned>((p.n + kPdfWarps - 1) / kPdfWarps);
+  const size_t smem = static_cast<size_t>(kPdfWarps) * (2 * (p.M + 1) + 2) * sizeof(float);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(sample_pdf_kernel<FROM_COARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  sample_pdf_kernel<FROM_COARSE><<<grid, kPdfWarps * 32, smem, stream>>>(p);
+  return check_launch(what);
+}
+
+}  // namespace cng
+
+extern "C" {
+
+int cng_sample_pdf(const float* bins, const float* weights, const float* u, long long n, int M, int K, float eps,
+                   float* samples, int64_t* inds, cng_stream_t stream) {
+  CNG_REQUIRE(bins && weights && u && samples, CNG_ERR_INVALID_ARGUMENT, "sample_pdf: NULL pointer");
+  CNG_REQUIRE(n >= 0 && M >= 1 && K >= 1, CNG_ERR_INVALID_ARGUMENT, "sample_pdf: n=%lld M=%d K=%d", n, M, K);
+  CNG_REQUIRE(M <= 2047, CNG_ERR_UNSUPPORTED, "sample_pdf: M=%d > 2047", M);
+  if (n == 0) return CNG_OK;
+  if (int e = cng_device_check()) return e;
+  cng::PdfParams p{bins, weights, u, n, M, K, 0, eps, samples, inds};
+  return cng::launch_pdf<false>(p, cng::as_stream(stream), "cng_sample_pdf");
+}
+
+int cng_resample_from_coarse(const float* t_coarse, const float* weights, const float* u, long long n, int S,
+                             float* t_fine, int64_t* inds, cng_stream_t stream) {
+  CNG_REQUIRE(t_coarse && weights && u && t_fine, CNG_ERR_INVALID_ARGUMENT, "resample_from_coarse: NULL pointer");
+  CNG_REQUIRE(n >= 0 && S >= 3, CNG_ERR_INVALID_ARGUMENT, "resample_from_coarse: n=%lld S=%d (need S >= 3)", n, S);
+  CNG_REQUIRE(S <= 2049, CNG_ERR_UNSUPPORTED, "resample_from_coarse: S=%d > 2049", S);
+  if (n == 0) return CNG_OK;
+  if (int e = cng_device_check()) return e;
+  // bins = S-1 midpoints, weights = S-2 interior weights, N_importance = S
+  cng::PdfParams p{t_coarse, weights, u, n, S - 2, S, S, 1e-5f, t_fine, inds};
+  return cng::launch_pdf<true>(p, cng::as_stream(stream), "cng_resample_from_coarse");
+}
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+"""FiLM-SIREN decoders of the feature-volume + global-feature ("FG") family, host side.
+
+Mirror of the reference classes ``TALLSIREN_FG`` (generators/siren.py:491-580), ``SHORTSIREN_FG``
+(:583-668), ``DOUBLESIREN_FG`` (:744-827) and ``SingleSIREN_dg`` (:983-1065): same constructor
+keywords, same ``forward(points, z, img_size, num_steps) -> rgb_sigma[B,N,4]``, same parameter
+names (``network.{i}.layer.{weight,bias}``, ``final_layer.*``, ``mapping_network.*``) so reference
+checkpoints ``load_state_dict`` strictly, same initial distributions.  The arithmetic is not
+PyTorch: the trilinear lookup is ``cng_gather_points`` and the whole MLP is ``cng_film_siren_fwd``
+(one fused kernel; tcgen05 bf16 or exact fp32), see include/cng_b200.h.
+
+The config spellings ``TALLSIREN_dg`` / ``SHORTSIREN_dg`` / ``DoubleSIREN_dg``
+(configs/thousand/direct_volume/dg.py:8,51,55) resolve to the same classes.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import List, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+
+__all__ = ["FiLMLayer", "TALLSIREN_FG", "SHORTSIREN_FG", "DOUBLESIREN_FG", "SingleSIREN_dg",
+           "TALLSIREN_dg", "SHORTSIREN_dg", "DoubleSIREN_dg", "DOUBLESIREN_dg", "default_precision"]
+
+
+def default_precision() -> str:
+    """'bf16' (tcgen05 tensor-core path) unless CNG_PRECISION=fp32 selects the exact FFMA path."""
+    return os.environ.get("CNG_PRECISION", "bf16")
+
+
+class FiLMLayer(nn.Module):
+    """Parameter holder for one ``sin(freq * (W x + b) + phase)`` layer (siren.py:146-160).
+
+    Only ``layer`` (an ``nn.Linear``) carries state; the arithmetic runs inside the fused kernel.
+    """
+
+    def __init__(self, input_dim: int, hidden_dim: int, drop_out_prob: float = 0):
+        super().__init__()
+        self.layer = nn.Linear(input_dim, hidden_dim)
+        self.drop_out_prob = drop_out_prob
+        if drop_out_prob:
+            raise NotImplementedError("FiLM dropout > 0 is not built (every shipped config uses 0, special.py:39)")
+
+
+def _uniform_(linear: nn.Linear, bound: float) -> None:
+    with torch.no_grad():
+        linear.weight.uniform_(-bound, bound)
+
+
+class _FiLMSirenFG(nn.Module):
+    num_layers = 0          # FiLM layers
+    freq_div = 25.0         # frequency_init(freq_div), siren.py:134-143
+    sigmoid_rgb = True      # _sigmoid_rgb on the head (siren.py:579) or raw rgb (:1064)
+
+    def __init__(self, input_dim=3, z_dim=100, hidden_dim=256, output_dim=4, drop_out=0, device=None):
+        super().__init__()
+        self.device = device
+        self.input_dim, self.z_dim, self.hidden_dim, self.output_dim = input_dim, z_dim, hidden_dim, output_dim
+        self.network = nn.ModuleList(
+            [FiLMLayer(input_dim if i == 0 else hidden_dim, hidden_dim, drop_out) for i in range(self.num_layers)])
+        self.final_layer = nn.Linear(hidden_dim, 4)
+        self.mapping_network = nn.Linear(z_dim, self.num_layers * hidden_dim * 2)
+        for i, film in enumerate(self.network):
+            fan_in = film.layer.weight.shape[-1]
+            # first_layer_film_sine_init (siren.py:40-44) overrides frequency_init on layer 0
+            _uniform_(film.layer, 1.0 / fan_in if i == 0 else math.sqrt(6.0 / fan_in) / self.freq_div)
+        _uniform_(self.final_layer, math.sqrt(6.0 / hidden_dim) / self.freq_div)
+        self.precision = default_precision()
+
+    # -- pieces shared with ImplicitGenerator3d ------------------------------------------------
+    def film_parameters(self, global_feature: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """siren.py:550-553: freq = first half * 15 + 30, phase = second half.  [B, L*HID] each."""
+        fo = F.linear(global_feature.float(), self.mapping_network.weight.float(), self.mapping_network.bias.float())
+        half = fo.shape[-1] // 2
+        return (fo[..., :half] * 15 + 30).contiguous(), fo[..., half:].contiguous()
+
+    def layer_parameters(self) -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
+        return [f.layer.weight for f in self.network], [f.layer.bias for f in self.network]
+
+    def mlp(self, feat: torch.Tensor, freq: torch.Tensor, phase: torch.Tensor) -> torch.Tensor:
+        """feat [B,N,C] -> rgb_sigma [B,N,4] through the fused FiLM-SIREN kernel."""
+        ws, bs = self.layer_parameters()
+        return ops.film_siren_fwd(feat, ws, bs, freq, phase, self.final_layer.weight, self.final_layer.bias,
+                                  self.sigmoid_rgb, self.precision)
+
+    @staticmethod
+    def split_z(z):
+        if not isinstance(z, (tuple, list)) or len(z) != 2:
+            raise ValueError("the FG SIREN family needs z = (feature_volume [B,C,D,H,W], global_feature [B,z_dim]) "
+                             "(unet.return_global=True, generators/unet3d.py:635-638)")
+        return z[0], z[1]
+
+    def forward(self, points: torch.Tensor, z, img_size: int, num_steps: int) -> torch.Tensor:
+        """points [B, N, 3] world space (N == img_size**2 * num_steps in the reference's callers;
+        any N works here), z = (feature_volume, global_feature).  Returns rgb_sigma [B, N, 4]."""
+        volume, global_feature = self.split_z(z)
+        if torch.is_grad_enabled() and (volume.requires_grad or global_feature.requires_grad
+                                        or any(p.requires_grad for p in self.parameters())):
+            from .autograd import siren_forward_with_grad
+            return siren_forward_with_grad(self, points, volume, global_feature)
+        freq, phase = self.film_parameters(global_feature)
+        feat = ops.gather_points(ops.volume_to_channels_last(volume), points)
+        return self.mlp(feat, freq, phase)
+
+
+class TALLSIREN_FG(_FiLMSirenFG):
+    num_layers, freq_div, sigmoid_rgb = 8, 25.0, True
+
+
+class SHORTSIREN_FG(_FiLMSirenFG):
+    num_layers, freq_div, sigmoid_rgb = 4, 12.0, True
+
+
+class DOUBLESIREN_FG(_FiLMSirenFG):
+    num_layers, freq_div, sigmoid_rgb = 2, 12.0, True
+
+
+class SingleSIREN_dg(_FiLMSirenFG):
+    num_layers, freq_div, sigmoid_rgb = 1, 25.0, False
+
+
+# config spellings
+TALLSIREN_dg = TALLSIREN_FG
+SHORTSIREN_dg = SHORTSIREN_FG
+DoubleSIREN_dg = DOUBLESIREN_FG
+DOUBLESIREN_dg = DOUBLESIREN_FG

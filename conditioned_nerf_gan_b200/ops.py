@@ -1,0 +1,270 @@
+"""Torch-tensor front end of the C ABI (include/cng_b200.h): device pointers, sizes and the
+current CUDA stream go down through ctypes; tensors stay owned by PyTorch.
+
+Every function here launches hand-written sm_100a kernels from libcng_b200.so.  There is no CPU
+or eager-PyTorch fallback: a tensor that is not on a CUDA device raises, a missing library
+raises at import of ``_lib.load()``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+CLAMP_MODES = {"relu": _lib.CLAMP_RELU, "softplus": _lib.CLAMP_SOFTPLUS}
+PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+
+# number of kernel launches issued through this module (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def _count(n: int = 1) -> None:
+    global launch_count
+    launch_count += n
+
+
+# Optional per-entry-point device timing (bench.py's roofline leg): when `kernel_events` is a dict,
+# every C-ABI call is bracketed by CUDA events recorded on the launching stream.
+kernel_events = None
+
+
+class _timed:
+    __slots__ = ("name", "start")
+
+    def __init__(self, name: str):
+        self.name = name
+        self.start = None
+
+    def __enter__(self):
+        if kernel_events is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.start is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            kernel_events.setdefault(self.name, []).append((self.start, end))
+        return False
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: tensor is on {t.device}; the rendering path has no CPU implementation")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(t: torch.Tensor):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def clamp_code(clamp_mode) -> int:
+    """Reference: `raise "Need to choose clamp mode"` is a TypeError in py3
+    (generators/volumetric_rendering.py:41-46)."""
+    if clamp_mode not in CLAMP_MODES:
+        raise TypeError("Need to choose clamp mode")
+    return CLAMP_MODES[clamp_mode]
+
+
+def volume_to_channels_last(vol: torch.Tensor) -> torch.Tensor:
+    """[B,C,D,H,W] -> [B,D,H,W,C] (cng_volume_to_channels_last)."""
+    vol = _f32(vol, "volume")
+    B, C, D, H, W = vol.shape
+    out = torch.empty((B, D, H, W, C), dtype=torch.float32, device=vol.device)
+    with torch.cuda.device(vol.device), _timed("cng_volume_to_channels_last"):
+        _lib.call("cng_volume_to_channels_last", _ptr(vol), _ptr(out), B, C, D, H, W, _stream(vol))
+    _count()
+    return out
+
+
+def raymarch_gather_coarse(vol_cl, cam2world, rays_d_cam, t_lin, u_jitter, img_w, img_h, want_points=False):
+    """K1 coarse.  Returns feat[B,R,S,C], t[B,R,S], points[B,R,S,3] or None."""
+    vol_cl = _f32(vol_cl, "vol_ndhwc")
+    B, D, H, W, C = vol_cl.shape
+    cam2world = _f32(cam2world, "cam2world")
+    rays_d_cam = _f32(rays_d_cam, "rays_d_cam")
+    t_lin = _f32(t_lin, "t_lin")
+    S = t_lin.numel()
+    R = img_w * img_h
+    if cam2world.shape != (B, 4, 4):
+        raise ValueError(f"cam2world {tuple(cam2world.shape)} does not match volume batch {B}")
+    if u_jitter is not None:
+        u_jitter = _f32(u_jitter, "u_jitter")
+        if u_jitter.numel() != B * R * S:
+            raise ValueError("u_jitter must hold B*R*S draws")
+    dev = vol_cl.device
+    feat = torch.empty((B, R, S, C), dtype=torch.float32, device=dev)
+    t_out = torch.empty((B, R, S), dtype=torch.float32, device=dev)
+    pts = torch.empty((B, R, S, 3), dtype=torch.float32, device=dev) if want_points else None
+    with torch.cuda.device(dev), _timed("cng_raymarch_gather_coarse"):
+        _lib.call("cng_raymarch_gather_coarse", _ptr(vol_cl), B, C, D, H, W, _ptr(cam2world), _ptr(rays_d_cam),
+                  _ptr(t_lin), _ptr(u_jitter), img_w, img_h, S, _ptr(feat), _ptr(t_out), _ptr(pts), _stream(vol_cl))
+    _count()
+    return feat, t_out, pts
+
+
+def raymarch_gather_fine(vol_cl, cam2world, rays_d_cam, t_fine, img_w, img_h, want_points=False):
+    """K1 fine.  t_fine [B,R,S].  Returns feat[B,R,S,C], points or None."""
+    vol_cl = _f32(vol_cl, "vol_ndhwc")
+    B, D, H, W, C = vol_cl.shape
+    cam2world = _f32(cam2world, "cam2world")
+    rays_d_cam = _f32(rays_d_cam, "rays_d_cam")
+    t_fine = _f32(t_fine, "t_fine")
+    R = img_w * img_h
+    S = t_fine.numel() // (B * R)
+    dev = vol_cl.device
+    feat = torch.empty((B, R, S, C), dtype=torch.float32, device=dev)
+    pts = torch.empty((B, R, S, 3), dtype=torch.float32, device=dev) if want_points else None
+    with torch.cuda.device(dev), _timed("cng_raymarch_gather_fine"):
+        _lib.call("cng_raymarch_gather_fine", _ptr(vol_cl), B, C, D, H, W, _ptr(cam2world), _ptr(rays_d_cam),
+                  _ptr(t_fine), img_w, img_h, S, _ptr(feat), _ptr(pts), _stream(vol_cl))
+    _count()
+    return feat, pts
+
+
+def gather_points(vol_cl, points, want_index=False):
+    """Trilinear lookup at caller-supplied world points [B,N,3] -> feat[B,N,C] (+ corner index)."""
+    vol_cl = _f32(vol_cl, "vol_ndhwc")
+    B, D, H, W, C = vol_cl.shape
+    points = _f32(points, "points")
+    if points.dim() != 3 or points.shape[0] != B or points.shape[2] != 3:
+        raise ValueError(f"points must be [B={B}, N, 3], got {tuple(points.shape)}")
+    N = points.shape[1]
+    dev = vol_cl.device
+    feat = torch.empty((B, N, C), dtype=torch.float32, device=dev)
+    idx = torch.empty((B, N, 3), dtype=torch.int32, device=dev) if want_index else None
+    with torch.cuda.device(dev), _timed("cng_gather_points"):
+        _lib.call("cng_gather_points", _ptr(vol_cl), B, C, D, H, W, _ptr(points), N, _ptr(feat), _ptr(idx), _stream(vol_cl))
+    _count()
+    return (feat, idx) if want_index else feat
+
+
+def film_siren_fwd(feat, layer_w: Sequence[torch.Tensor], layer_b: Sequence[torch.Tensor], freq, phase, final_w,
+                   final_b, sigmoid_rgb: bool, precision: str = "bf16") -> torch.Tensor:
+    """K2.  feat [B,N,C], freq/phase [B,L*HID] -> rgb_sigma [B,N,4]."""
+    if precision not in PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
+    feat = _f32(feat, "feat")
+    B, N, C = feat.shape
+    L = len(layer_w)
+    ws = [_f32(w, f"layer_w[{i}]") for i, w in enumerate(layer_w)]
+    bs = [_f32(b, f"layer_b[{i}]") for i, b in enumerate(layer_b)]
+    HID = ws[0].shape[0]
+    freq, phase = _f32(freq, "freq"), _f32(phase, "phase")
+    if freq.shape != (B, L * HID) or phase.shape != (B, L * HID):
+        raise ValueError(f"freq/phase must be [B={B}, L*HID={L * HID}], got {tuple(freq.shape)} / {tuple(phase.shape)}")
+    final_w, final_b = _f32(final_w, "final_w"), _f32(final_b, "final_b")
+    dev = feat.device
+    out = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
+    w_arr = (ctypes.c_void_p * L)(*[w.data_ptr() for w in ws])
+    b_arr = (ctypes.c_void_p * L)(*[b.data_ptr() for b in bs])
+    code = PRECISIONS[precision]
+    lib = _lib.load()
+    ws_bytes = int(lib.cng_film_siren_workspace_bytes(B, C, HID, L, code))
+    workspace = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev) if ws_bytes else None
+    with torch.cuda.device(dev), _timed("cng_film_siren_fwd"):
+        _lib.call("cng_film_siren_fwd", _ptr(feat), B, N, C, HID, L, w_arr, b_arr, _ptr(freq), _ptr(phase), _ptr(final_w),
+                  _ptr(final_b), int(bool(sigmoid_rgb)), code, _ptr(workspace), ws_bytes, _ptr(out), _stream(feat))
+    _count(2 if code == _lib.PREC_BF16 else 1)
+    return out
+
+
+def composite_fwd(rgb_sigma, t, noise, noise_std: float, clamp_mode, white_back=False, last_back=False,
+                  want_weights=True) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+    """K3.  rgb_sigma [..., S, 4], t [..., S(,1)] -> rgb [..., 3], dist [...], weights [..., S]."""
+    code = clamp_code(clamp_mode)
+    rgb_sigma = _f32(rgb_sigma, "rgb_sigma")
+    S = rgb_sigma.shape[-2]
+    lead = rgb_sigma.shape[:-2]
+    n_rays = rgb_sigma.numel() // (4 * S)
+    t = _f32(t, "t").reshape(n_rays, S)
+    if noise is not None and noise_std != 0:
+        noise = _f32(noise, "noise").reshape(n_rays, S)
+    else:
+        noise = None
+    dev = rgb_sigma.device
+    rgb = torch.empty((*lead, 3), dtype=torch.float32, device=dev)
+    dist = torch.empty(tuple(lead), dtype=torch.float32, device=dev)
+    weights = torch.empty((*lead, S), dtype=torch.float32, device=dev) if want_weights else None
+    with torch.cuda.device(dev), _timed("cng_composite_fwd"):
+        _lib.call("cng_composite_fwd", _ptr(rgb_sigma), _ptr(t), _ptr(noise), n_rays, S, float(noise_std), code,
+                  int(bool(white_back)), int(bool(last_back)), _ptr(rgb), _ptr(dist), _ptr(weights), _stream(rgb_sigma))
+    _count()
+    return rgb, dist, weights
+
+
+def sample_pdf(bins, weights, u, eps: float = 1e-5, want_inds=False):
+    """K4.  bins [n,M+1], weights [n,M], u [n,K] -> samples [n,K] (+ int64 searchsorted indices)."""
+    bins, weights, u = _f32(bins, "bins"), _f32(weights, "weights"), _f32(u, "u")
+    n, M = weights.shape
+    if bins.shape != (n, M + 1):
+        raise ValueError(f"bins must be [n, M+1] = {(n, M + 1)}, got {tuple(bins.shape)}")
+    K = u.shape[1]
+    dev = bins.device
+    samples = torch.empty((n, K), dtype=torch.float32, device=dev)
+    inds = torch.empty((n, K), dtype=torch.int64, device=dev) if want_inds else None
+    with torch.cuda.device(dev), _timed("cng_sample_pdf"):
+        _lib.call("cng_sample_pdf", _ptr(bins), _ptr(weights), _ptr(u), n, M, K, float(eps), _ptr(samples), _ptr(inds), _stream(bins))
+    _count()
+    return (samples, inds) if want_inds else samples
+
+
+def resample_from_coarse(t_coarse, weights, u, want_inds=False):
+    """The sample_pdf call site of the generator fused: t_coarse, weights, u all [n,S] -> t_fine [n,S]."""
+    t_coarse, weights, u = _f32(t_coarse, "t_coarse"), _f32(weights, "weights"), _f32(u, "u")
+    S = t_coarse.shape[-1]
+    n = t_coarse.numel() // S
+    if weights.numel() != n * S or u.numel() != n * S:
+        raise ValueError("t_coarse, weights and u must all hold n*S values")
+    dev = t_coarse.device
+    t_fine = torch.empty((n, S), dtype=torch.float32, device=dev)
+    inds = torch.empty((n, S), dtype=torch.int64, device=dev) if want_inds else None
+    with torch.cuda.device(dev), _timed("cng_resample_from_coarse"):
+        _lib.call("cng_resample_from_coarse", _ptr(t_coarse), _ptr(weights), _ptr(u), n, S, _ptr(t_fine), _ptr(inds), _stream(t_coarse))
+    _count()
+    return (t_fine, inds) if want_inds else t_fine
+
+
+def merge_composite(rgb_sigma_fine, rgb_sigma_coarse, t_fine, t_coarse, noise, rays_d_cam, B, img_h, img_w, noise_std,
+                    clamp_mode, white_back=False, last_back=False, taps=False):
+    """K3 final.  Returns pixels [B,3,H,W], depth [B,H,W] (+ dict of taps)."""
+    code = clamp_code(clamp_mode)
+    rgb_sigma_coarse = _f32(rgb_sigma_coarse, "rgb_sigma_coarse")
+    t_coarse = _f32(t_coarse, "t_coarse")
+    R = img_h * img_w
+    S = rgb_sigma_coarse.numel() // (B * R * 4)
+    two = rgb_sigma_fine is not None
+    if two:
+        rgb_sigma_fine, t_fine = _f32(rgb_sigma_fine, "rgb_sigma_fine"), _f32(t_fine, "t_fine")
+    n = 2 * S if two else S
+    noise = _f32(noise, "noise") if (noise is not None and noise_std != 0) else None
+    rays_d_cam = _f32(rays_d_cam, "rays_d_cam")
+    dev = rgb_sigma_coarse.device
+    pixels = torch.empty((B, 3, img_h, img_w), dtype=torch.float32, device=dev)
+    depth = torch.empty((B, img_h, img_w), dtype=torch.float32, device=dev)
+    rgb = dist = order = None
+    if taps:
+        rgb = torch.empty((B, R, 3), dtype=torch.float32, device=dev)
+        dist = torch.empty((B, R), dtype=torch.float32, device=dev)
+        order = torch.empty((B, R, n), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev), _timed("cng_merge_composite"):
+        _lib.call("cng_merge_composite", _ptr(rgb_sigma_fine) if two else None, _ptr(rgb_sigma_coarse),
+                  _ptr(t_fine) if two else None, _ptr(t_coarse), _ptr(noise), _ptr(rays_d_cam), B, R, S, float(noise_std),
+                  code, int(bool(white_back)), int(bool(last_back)), _ptr(pixels), _ptr(depth), _ptr(rgb), _ptr(dist),
+                  _ptr(order), _stream(rgb_sigma_coarse))
+    _count()
+    if taps:
+        return pixels, depth, {"rgb": rgb, "dist": dist, "order": order}
+    return pixels, depth

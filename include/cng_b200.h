@@ -1,0 +1,189 @@
+/*
+ * cng_b200.h -- C ABI of the B200-native rendering hot path of the conditioned pi-GAN style
+ * NeRF-GAN (drop-in for zzhuolun/conditioned-nerf-gan's ImplicitGenerator3d.forward).
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; the
+ * boundary it exposes is the Python class contract `ImplicitGenerator3d.forward(z, cam2worlds,
+ * **curriculum)`.  Each entry point below replaces one block of stock-ATen launches on that
+ * path and cites the reference lines it replaces (paths relative to the reference checkout).
+ * The Python host mirror (conditioned_nerf_gan_b200/generators/*.py) binds these with ctypes;
+ * INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in `_host`;
+ *   - tensors are dense, row-major, fp32 unless stated; shapes are written [outer, ..., inner];
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - functions return 0 on success, a negative CNG_ERR_* code for argument errors, or a
+ *     positive cudaError_t; cng_last_error() gives a thread-local message.  Nothing is thrown,
+ *     nothing falls back to the CPU: without a CUDA device every compute call fails with
+ *     CNG_ERR_NO_DEVICE (or the CUDA error) and leaves the outputs untouched;
+ *   - no call synchronises the device; outputs are valid in stream order.
+ *
+ * Symbols: R = rays per image (img_h * img_w), S = coarse samples per ray (`num_steps`),
+ * C = feature channels, (D, H, W) = feature-volume extent (z, y, x), L = FiLM layers,
+ * HID = hidden width (256).
+ */
+#ifndef CNG_B200_H_
+#define CNG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNG_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define CNG_API __attribute__((visibility("default")))
+#else
+#define CNG_API
+#endif
+
+typedef void* cng_stream_t;
+
+enum {
+  CNG_OK = 0,
+  CNG_ERR_INVALID_ARGUMENT = -1, /* NULL pointer, non-positive size, misaligned buffer        */
+  CNG_ERR_UNSUPPORTED = -2,      /* shape outside what the kernels are built for              */
+  CNG_ERR_NO_DEVICE = -3,        /* no sm_100 device visible                                  */
+  CNG_ERR_WORKSPACE = -4         /* workspace too small (see *_workspace_bytes)               */
+};
+
+/* reference: `clamp_mode` kwarg of fancy_integration, volumetric_rendering.py:41-46 */
+enum { CNG_CLAMP_RELU = 0, CNG_CLAMP_SOFTPLUS = 1 };
+
+/* arithmetic of the FiLM-SIREN contractions */
+enum {
+  CNG_PREC_FP32 = 0,   /* fp32 FFMA tiles (exact-mode; reference inference is pure fp32)       */
+  CNG_PREC_BF16 = 1    /* tcgen05 bf16 x bf16 -> fp32 TMEM accumulators; layer 0 split-bf16    */
+};
+
+CNG_API int cng_abi_version(void);
+CNG_API const char* cng_last_error(void);
+/* 0 if an sm_100 device is current and the kernels can launch, else an error code. */
+CNG_API int cng_device_check(void);
+
+/* ------------------------------------------------------------------------------------------
+ * a1 helper (host): the per-pixel camera-space directions and the coarse distances.
+ * Replaces get_initial_rays_trig, generators/volumetric_rendering.py:73-100 (host part).
+ * rays_d_cam_host [img_h*img_w, 3], t_lin_host [S].  Ray p = row*img_w + col, x = lin(-1,1,W)[col],
+ * y = lin(-1,1,H)[row], z = 1/tan(fov/2) (float64 tan), normalised.  The Python mirror instead
+ * builds these tables with the same torch ops as the reference so they agree to the last bit.
+ * ---------------------------------------------------------------------------------------- */
+CNG_API int cng_camera_tables_host(int img_w, int img_h, int S, double fov_deg, double ray_start,
+                           double ray_end, float* rays_d_cam_host, float* t_lin_host);
+
+/* ------------------------------------------------------------------------------------------
+ * a4 prologue: NCDHW -> NDHWC so that one trilinear corner is one contiguous C*4-byte line.
+ * The reference hands F.grid_sample an NCDHW volume (generators/siren.py:555-571).
+ * ---------------------------------------------------------------------------------------- */
+CNG_API int cng_volume_to_channels_last(const float* vol_ncdhw, float* vol_ndhwc, int B, int C, int D,
+                                int H, int W, cng_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1 coarse: sample generation + stratified jitter + cam->world + trilinear gather, fused.
+ * Replaces get_initial_rays_trig (volumetric_rendering.py:73-100), perturb_points (:103-110),
+ * transform_sampled_points (:113-199) and the F.grid_sample + reshape/permute block of every
+ * feature-volume SIREN (generators/siren.py:555-571).
+ *   vol_ndhwc  [B, D, H, W, C]      cam2world [B, 4, 4]
+ *   rays_d_cam [R, 3]               t_lin [S]
+ *   u_jitter   [B, R, S] uniform draws (the reference's torch.rand at :106), NULL = no jitter
+ *   feat       [B, R, S, C] out     t_out [B, R, S] out (jittered distances)
+ *   points_out [B, R, S, 3] out, may be NULL (world-space sample positions, for taps/tests)
+ * Requires C % 4 == 0, C <= 128, S >= 2, img_w * img_h == R.
+ * ---------------------------------------------------------------------------------------- */
+CNG_API int cng_raymarch_gather_coarse(const float* vol_ndhwc, int B, int C, int D, int H, int W,
+                               const float* cam2world, const float* rays_d_cam,
+                               const float* t_lin, const float* u_jitter, int img_w, int img_h,
+                               int S, float* feat, float* t_out, float* points_out,
+                               cng_stream_t stream);
+
+/* K1 fine: p = o + d * t_fine in world space (generators/generators.py:138-145) + gather.
+ *   t_fine [B, R, S];  feat [B, R, S, C] out;  points_out [B, R, S, 3] out or NULL. */
+CNG_API int cng_raymarch_gather_fine(const float* vol_ndhwc, int B, int C, int D, int H, int W,
+                             const float* cam2world, const float* rays_d_cam,
+                             const float* t_fine, int img_w, int img_h, int S, float* feat,
+                             float* points_out, cng_stream_t stream);
+
+/* Gather at caller-supplied world points: the lookup inside `siren(points, z, img_size,
+ * num_steps)` (generators/siren.py:555-571) when it is called directly (extract_shapes.py:63-68).
+ *   points [B, N, 3];  feat [B, N, C] out;  corner_idx [B, N, 3] int32 out or NULL: floor of the
+ *   clamped continuous voxel index per axis (x, y, z) -- exposed so tests can pin the indexing. */
+CNG_API int cng_gather_points(const float* vol_ndhwc, int B, int C, int D, int H, int W,
+                      const float* points, long long N, float* feat, int32_t* corner_idx,
+                      cng_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2: FiLM-SIREN MLP, all layers fused, activations never leave the SM.
+ * Replaces, per layer, addmm + expand + mul + add + sin (FiLMLayer.forward, siren.py:146-160;
+ * loops at :573-577, :661-665, :820-824, :1058-1062) and the head nn.Linear(256,4) +
+ * _sigmoid_rgb (:579, :1227-1234).
+ *   feat [B, N, C]; layer_w_host / layer_b_host: HOST arrays of L device pointers to
+ *   nn.Linear weight [HID, K_l] (K_0 = C, else HID) and bias [HID];
+ *   freq, phase [B, L*HID] (freq already `*15+30`, siren.py:550-553);
+ *   final_w [4, HID], final_b [4]; rgb_sigma [B, N, 4] out.
+ * CNG_PREC_BF16 needs HID == 256, C == 32 and a workspace of cng_film_siren_workspace_bytes().
+ * ---------------------------------------------------------------------------------------- */
+CNG_API size_t cng_film_siren_workspace_bytes(int B, int C, int HID, int L, int precision);
+CNG_API int cng_film_siren_fwd(const float* feat, int B, long long N, int C, int HID, int L,
+                       const float* const* layer_w_host, const float* const* layer_b_host,
+                       const float* freq, const float* phase, const float* final_w,
+                       const float* final_b, int sigmoid_rgb, int precision, void* workspace,
+                       size_t workspace_bytes, float* rgb_sigma, cng_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3: alpha compositing, one warp per ray, exclusive-cumprod transmittance by warp shuffles.
+ * Replaces fancy_integration (volumetric_rendering.py:18-70).
+ *   rgb_sigma [n_rays, S, 4]; t [n_rays, S]; noise [n_rays, S] (the reference's randn at :39)
+ *   or NULL when noise_std == 0; outputs rgb [n_rays, 3], dist [n_rays], weights [n_rays, S]
+ *   (any may be NULL).  S <= 1024.
+ * ---------------------------------------------------------------------------------------- */
+CNG_API int cng_composite_fwd(const float* rgb_sigma, const float* t, const float* noise,
+                      long long n_rays, int S, float noise_std, int clamp_mode, int white_back,
+                      int last_back, float* rgb, float* dist, float* weights,
+                      cng_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4: inverse-CDF importance resampling, CDF + binary search in shared memory.
+ * Replaces sample_pdf (volumetric_rendering.py:297-342, det=False).
+ *   bins [n, M+1]; weights [n, M]; u [n, K] uniform draws (torch.rand at :321);
+ *   samples [n, K] out; inds [n, K] int64 out or NULL (= torch.searchsorted(cdf, u), :324).
+ * Bit-exact against the oracle: sum and CDF accumulate sequentially in float64 and round to
+ * fp32 per element (what torch.cumsum does on CPU); the search and the lerp use IEEE fp32 ops
+ * in the reference's order.  M <= 2047.
+ * ---------------------------------------------------------------------------------------- */
+CNG_API int cng_sample_pdf(const float* bins, const float* weights, const float* u, long long n, int M,
+                   int K, float eps, float* samples, int64_t* inds, cng_stream_t stream);
+
+/* The sample_pdf call site fused (generators/generators.py:123-136): bins = midpoints of
+ * t_coarse, weights = (w[1:-1] + 1e-5), N_importance = S.
+ *   t_coarse, weights [n, S]; u [n, S]; t_fine [n, S] out; inds [n, S] int64 out or NULL. */
+CNG_API int cng_resample_from_coarse(const float* t_coarse, const float* weights, const float* u,
+                             long long n, int S, float* t_fine, int64_t* inds,
+                             cng_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3 final: merge coarse+fine by depth (stable: fine first), composite, format the image.
+ * Replaces cat/sort/gather (generators/generators.py:163-167), the final fancy_integration
+ * (:172-180), the NCHW permute `*2-1` (:182-183) and distance2depth (:185-186,
+ * volumetric_rendering.py:345-356).
+ *   rgb_sigma_fine / _coarse [B*R, S, 4]; t_fine / t_coarse [B*R, S]; noise [B*R, 2S] or NULL;
+ *   rays_d_cam [R, 3]; outputs pixels [B, 3, img_h, img_w], depth [B, img_h, img_w];
+ *   optional taps rgb [B*R, 3], dist [B*R], order [B*R, 2S] int32 (index into the fine-first
+ *   concatenation), may be NULL.   2S <= 512.
+ * With rgb_sigma_fine == NULL the coarse samples alone are composited (hierarchical_sample
+ * False) and noise is [B*R, S].
+ * ---------------------------------------------------------------------------------------- */
+CNG_API int cng_merge_composite(const float* rgb_sigma_fine, const float* rgb_sigma_coarse,
+                        const float* t_fine, const float* t_coarse, const float* noise,
+                        const float* rays_d_cam, int B, int R, int S, float noise_std,
+                        int clamp_mode, int white_back, int last_back, float* pixels,
+                        float* depth, float* rgb, float* dist, int32_t* order,
+                        cng_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNG_B200_H_ */

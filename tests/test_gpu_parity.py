@@ -1,0 +1,447 @@
+"""Parity of every kernel of libcng_b200 (called through the C ABI via conditioned_nerf_gan_b200.ops)
+against the torch-CPU oracle on identical inputs and identical random draws.  B200 only (-m gpu).
+
+Tolerances (BASELINE.json north_star): sample_pdf indices, merge order and voxel corner indices
+bit-exact; fp32 compositing <= 1e-5 relative; bf16 MLP <= 1e-2 max-abs with PSNR >= 40 dB.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import FORWARD_FIXTURES, fixture_inputs, load_golden
+from oracle import nerf_path as oracle
+
+pytestmark = pytest.mark.gpu
+
+FOV = 49.134342641202636
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from conditioned_nerf_gan_b200 import _lib, ops as _ops
+    _lib.load()
+    return _ops
+
+
+def dev(t):
+    return t.to("cuda")
+
+
+# ------------------------------------------------------------------------------------------------
+# a4: layout + trilinear lookup
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(1, 32, 8, 8, 8), (2, 32, 16, 12, 10), (1, 4, 5, 6, 7), (3, 64, 7, 9, 33)])
+def test_channels_last_exact(ops, shape):
+    g = torch.Generator().manual_seed(0)
+    v = torch.randn(shape, generator=g)
+    out = ops.volume_to_channels_last(dev(v)).cpu()
+    assert torch.equal(out, v.permute(0, 2, 3, 4, 1).contiguous())
+
+
+def test_gather_points_golden_and_index_bit_exact(ops):
+    fx, _ = load_golden("functions")
+    vol, pts = fx["tri/volume"], fx["tri/points"]
+    feat, idx = ops.gather_points(ops.volume_to_channels_last(dev(vol)), dev(pts), want_index=True)
+    assert torch.allclose(feat.cpu(), fx["tri/features"], rtol=0, atol=2e-6)
+    for b in range(vol.shape[0]):
+        _, idx_ref = oracle.trilinear_manual(vol[b].numpy(), pts[b].numpy())
+        assert np.array_equal(idx[b].cpu().numpy(), idx_ref), "voxel corner index differs from the reference formula"
+
+
+@pytest.mark.parametrize("C,D,H,W,N", [(32, 64, 64, 64, 20000), (32, 16, 20, 24, 5000), (8, 5, 6, 7, 1000), (32, 32, 32, 32, 1)])
+def test_gather_points_random_inside_and_outside(ops, C, D, H, W, N):
+    g = torch.Generator().manual_seed(1)
+    B = 2
+    vol = torch.randn((B, C, D, H, W), generator=g)
+    pts = (torch.rand((B, N, 3), generator=g) * 2 - 1) * 0.75       # part of them outside [-0.6, 0.6]^3: border clamp
+    pts[:, :8] = torch.tensor([[-0.6, -0.6, -0.6], [0.6, 0.6, 0.6], [0, 0, 0], [0.6, -0.6, 0.0], [5, 5, 5], [-5, 0, 5],
+                               [0.6 - 1e-7, 0.59999, -0.59999], [1e-9, -1e-9, 0.3]])[: min(8, N)]
+    feat, idx = ops.gather_points(ops.volume_to_channels_last(dev(vol)), dev(pts), want_index=True)
+    grid = (pts / 0.6).reshape(B, 1, 1, N, 3)
+    ref = torch.nn.functional.grid_sample(vol, grid, mode="bilinear", align_corners=False, padding_mode="border")
+    ref = ref.reshape(B, C, N).permute(0, 2, 1)
+    assert torch.allclose(feat.cpu(), ref, rtol=0, atol=5e-6)
+    _, idx_ref = oracle.trilinear_manual(vol[1].numpy(), pts[1].numpy())
+    assert np.array_equal(idx[1].cpu().numpy(), idx_ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# a1-a3 (+a4), a10: fused ray march
+# ------------------------------------------------------------------------------------------------
+def _ray_setup(B, img, S, V, seed=0):
+    from conditioned_nerf_gan_b200.generators.volumetric_rendering import camera_tables
+    g = torch.Generator().manual_seed(seed)
+    vol = torch.randn((B, 32, V, V, V), generator=g) * 0.3
+    cam = oracle.look_at_cam2world(oracle.random_camera_origins(B, 0.7, 1.5, "y", np.random.RandomState(seed)), "y")
+    u = torch.rand((B, img * img, S, 1), generator=g)
+    rays, t_lin = camera_tables((img, img), S, FOV, 0.25, 1.95, "cuda")
+    return vol, cam, u, rays, t_lin
+
+
+@pytest.mark.parametrize("B,img,S,V", [(2, 16, 6, 16), (1, 64, 12, 32), (3, 10, 5, 8), (2, 32, 24, 64)])
+def test_raymarch_coarse_vs_oracle(ops, B, img, S, V):
+    vol, cam, u, rays, t_lin = _ray_setup(B, img, S, V)
+    feat, t, pts = ops.raymarch_gather_coarse(ops.volume_to_channels_last(dev(vol)), dev(cam), rays, t_lin, dev(u), img, img,
+                                              want_points=True)
+    p_cam, t_ref, d_cam = oracle.camera_rays(B, S, img, FOV, 0.25, 1.95)
+    p_cam, t_ref = oracle.jitter_samples(p_cam, t_ref, d_cam, u)
+    p_ref, _, _ = oracle.camera_to_world(p_cam, d_cam, cam)
+    assert torch.equal(t.cpu(), t_ref.squeeze(-1)), "jittered distances must be bit-identical (same fp32 ops)"
+    assert torch.allclose(pts.cpu(), p_ref, rtol=0, atol=5e-7)      # bmm vs fma chain: <= 2 ulp at |p| <= 2
+    # the gather is checked on the kernel's own points, so the 1-ulp position differences do not compound
+    f_ref = oracle.trilinear_lookup(vol, pts.cpu().reshape(B, -1, 3), img, S)
+    assert torch.allclose(feat.cpu().reshape(B, -1, 32), f_ref, rtol=0, atol=5e-6)
+
+
+def test_raymarch_coarse_no_jitter_and_odd_image(ops):
+    B, img_w, img_h, S, V = 1, 12, 8, 4, 8      # not a multiple of the 8x4 pixel patch in x
+    vol, cam, _, _, _ = _ray_setup(B, 8, S, V)
+    from conditioned_nerf_gan_b200.generators.volumetric_rendering import camera_tables
+    rays, t_lin = camera_tables((img_w, img_h), S, FOV, 0.25, 1.95, "cuda")
+    feat, t, pts = ops.raymarch_gather_coarse(ops.volume_to_channels_last(dev(vol)), dev(cam), rays, t_lin, None, img_w, img_h,
+                                              want_points=True)
+    assert torch.equal(t.cpu(), t_lin.cpu().expand(B, img_w * img_h, S))
+    d = rays.cpu()
+    p_ref = (d[:, None, :] * t_lin.cpu()[None, :, None]) @ cam[0, :3, :3].T + cam[0, :3, 3]
+    assert torch.allclose(pts.cpu()[0], p_ref, rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,img,S,V", [(2, 16, 6, 16), (1, 32, 24, 32)])
+def test_raymarch_fine_vs_oracle(ops, B, img, S, V):
+    vol, cam, u, rays, _ = _ray_setup(B, img, S, V, seed=3)
+    t_fine = 0.25 + 1.7 * u                                                   # [B,R,S,1]
+    feat, pts = ops.raymarch_gather_fine(ops.volume_to_channels_last(dev(vol)), dev(cam), rays, dev(t_fine), img, img,
+                                         want_points=True)
+    _, _, d_cam = oracle.camera_rays(B, S, img, FOV, 0.25, 1.95)
+    _, d_w, o_w = oracle.camera_to_world(torch.zeros(B, img * img, S, 3), d_cam, cam)
+    p_ref = oracle.fine_points(o_w, d_w, t_fine)
+    assert torch.allclose(pts.cpu(), p_ref, rtol=0, atol=5e-7)
+    f_ref = oracle.trilinear_lookup(vol, pts.cpu().reshape(B, -1, 3), img, S)
+    assert torch.allclose(feat.cpu().reshape(B, -1, 32), f_ref, rtol=0, atol=5e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# a5-a7: FiLM-SIREN MLP
+# ------------------------------------------------------------------------------------------------
+def _mlp_setup(siren_type, B, N, feat_std, seed=0):
+    state = oracle.init_generator_state(siren_type, seed=seed)
+    spec = oracle.SIREN_SPECS[oracle.resolve_siren_type(siren_type)]
+    ws = [state[f"siren.network.{i}.layer.weight"] for i in range(spec["layers"])]
+    bs = [state[f"siren.network.{i}.layer.bias"] for i in range(spec["layers"])]
+    g = torch.Generator().manual_seed(seed + 10)
+    feat = torch.randn((B, N, 32), generator=g) * feat_std
+    glob = torch.randn((B, 256), generator=g) * 0.05 + 0.19
+    freq, phase = oracle.film_parameters(glob, state["siren.mapping_network.weight"], state["siren.mapping_network.bias"])
+    fw, fb = state["siren.final_layer.weight"], state["siren.final_layer.bias"]
+    ref = oracle.film_siren_mlp(feat, ws, bs, freq, phase, fw, fb, spec["sigmoid_rgb"])
+    return spec, ws, bs, feat, freq, phase, fw, fb, ref
+
+
+def _run_mlp(ops, precision, spec, ws, bs, feat, freq, phase, fw, fb):
+    out = ops.film_siren_fwd(dev(feat), [dev(w) for w in ws], [dev(b) for b in bs], dev(freq), dev(phase), dev(fw), dev(fb),
+                             spec["sigmoid_rgb"], precision)
+    torch.cuda.synchronize()
+    return out.cpu()
+
+
+@pytest.mark.parametrize("siren_type", ["TALLSIREN_FG", "SHORTSIREN_FG", "DOUBLESIREN_FG", "SingleSIREN_dg"])
+@pytest.mark.parametrize("B,N", [(2, 1000), (1, 64), (3, 129)])
+def test_film_siren_fp32_vs_oracle(ops, siren_type, B, N):
+    spec, ws, bs, feat, freq, phase, fw, fb, ref = _mlp_setup(siren_type, B, N, 0.3)
+    out = _run_mlp(ops, "fp32", spec, ws, bs, feat, freq, phase, fw, fb)
+    err = (out - ref).abs().max().item()
+    print(f"{siren_type} fp32 max-abs err {err:.3e}")
+    assert err < 5e-4, err       # fp32 accumulation-order differences amplified by freq ~ 30 per layer
+
+
+@pytest.mark.parametrize("siren_type,tol", [("TALLSIREN_FG", 1e-2), ("SHORTSIREN_FG", 3e-2), ("DOUBLESIREN_FG", 1e-2), ("SingleSIREN_dg", 1e-2)])
+@pytest.mark.parametrize("B,N", [(2, 4096), (1, 100), (3, 129), (1, 128 * 300 + 5)])
+def test_film_siren_bf16_vs_oracle(ops, siren_type, tol, B, N):
+    """tcgen05 path.  Features ~ N(0, 0.3^2) (std of a random-init UNet3D output)."""
+    spec, ws, bs, feat, freq, phase, fw, fb, ref = _mlp_setup(siren_type, B, N, 0.3)
+    out = _run_mlp(ops, "bf16", spec, ws, bs, feat, freq, phase, fw, fb)
+    assert torch.isfinite(out).all()
+    err = (out - ref).abs().max().item()
+    rms = (out - ref).pow(2).mean().sqrt().item()
+    print(f"{siren_type} bf16 B={B} N={N}: max-abs err {err:.3e}, rms {rms:.3e}")
+    assert err < tol, err
+
+
+def test_film_siren_bf16_matches_fp32_kernel_on_large_batch(ops):
+    """Every tile of a multi-wave launch (more tiles than 2 x 148 CTAs) is computed and lands in its slot."""
+    spec, ws, bs, feat, freq, phase, fw, fb, _ = _mlp_setup("DOUBLESIREN_FG", 2, 128 * 700 + 17, 0.3)
+    a = _run_mlp(ops, "bf16", spec, ws, bs, feat, freq, phase, fw, fb)
+    b = _run_mlp(ops, "fp32", spec, ws, bs, feat, freq, phase, fw, fb)
+    assert (a - b).abs().max().item() < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# a8: compositing
+# ------------------------------------------------------------------------------------------------
+def _assert_rel(a, b, rel=1e-5, floor=1e-6, what=""):
+    a, b = a.double(), b.double()
+    bad = (a - b).abs() > rel * b.abs() + floor
+    assert not bad.any(), f"{what}: {int(bad.sum())} elements beyond {rel} relative, worst {(a - b).abs().max().item():.3e}"
+
+
+def test_composite_golden_cases(ops):
+    fx, _ = load_golden("functions")
+    for i in range(5):
+        cfg = fx[f"comp/case{i}/cfg"]
+        rgb, dist, w = ops.composite_fwd(dev(fx["comp/rgb_sigma"]), dev(fx["comp/t"]), dev(fx["comp/noise"]), cfg["noise_std"],
+                                         cfg["clamp_mode"], cfg["white_back"], cfg["last_back"])
+        _assert_rel(rgb.cpu(), fx[f"comp/case{i}/rgb"], what=f"case{i} rgb")
+        _assert_rel(dist.cpu().unsqueeze(-1), fx[f"comp/case{i}/dist"], what=f"case{i} dist")
+        _assert_rel(w.cpu().unsqueeze(-1), fx[f"comp/case{i}/weights"], what=f"case{i} weights")
+
+
+@pytest.mark.parametrize("S", [1, 2, 12, 24, 31, 32, 33, 48, 64, 96, 128, 256, 1000])
+@pytest.mark.parametrize("clamp,noise_std,white,last", [("relu", 0.0, True, False), ("softplus", 0.7, False, True)])
+def test_composite_vs_oracle(ops, S, clamp, noise_std, white, last):
+    g = torch.Generator().manual_seed(S)
+    B, R = 2, 301
+    rs = torch.randn((B, R, S, 4), generator=g)
+    rs[..., :3] = torch.sigmoid(rs[..., :3])
+    rs[..., 3] *= 8
+    t = torch.sort(torch.rand((B, R, S, 1), generator=g) * 1.7 + 0.25, dim=2).values
+    noise = torch.randn((B, R, S, 1), generator=g)
+    rgb, dist, w = ops.composite_fwd(dev(rs), dev(t), dev(noise), noise_std, clamp, white, last)
+    r_rgb, r_dist, r_w = oracle.composite(rs, t, noise, noise_std, clamp, white, last)
+    _assert_rel(rgb.cpu(), r_rgb, what="rgb")
+    _assert_rel(dist.cpu(), r_dist.squeeze(-1), what="dist")
+    _assert_rel(w.cpu(), r_w.squeeze(-1), what="weights")
+
+
+def test_composite_properties_full_size(ops):
+    """c2-size properties: weights in [0,1], sum <= 1; empty space on a white background is white;
+    the result is linear in the colours."""
+    n, S = 131072, 48
+    g = torch.Generator(device="cuda").manual_seed(0)
+    rs = torch.randn((n, S, 4), generator=g, device="cuda")
+    rs[..., :3] = torch.sigmoid(rs[..., :3])
+    t = torch.sort(torch.rand((n, S), generator=g, device="cuda") * 1.7 + 0.25, dim=1).values
+    rgb, dist, w = ops.composite_fwd(rs, t, None, 0.0, "relu", True, False)
+    assert (w >= 0).all() and (w <= 1).all() and (w.sum(-1) <= 1 + 1e-5).all()
+    assert (dist >= 0).all() and (dist <= t[:, -1] + 1e-5).all()
+    rs2 = rs.clone()
+    rs2[..., :3] *= 0.5
+    rgb2, _, w2 = ops.composite_fwd(rs2, t, None, 0.0, "relu", False, False)
+    rgb1, _, _ = ops.composite_fwd(rs, t, None, 0.0, "relu", False, False)
+    assert torch.equal(w, w2) and torch.allclose(rgb2, rgb1 * 0.5, rtol=1e-6, atol=1e-7)
+    empty = rs.clone()
+    empty[..., 3] = -1.0
+    rgb0, dist0, w0 = ops.composite_fwd(empty, t, None, 0.0, "relu", True, False)
+    assert torch.equal(rgb0, torch.ones_like(rgb0)) and torch.equal(dist0, torch.zeros_like(dist0)) and not w0.any()
+
+
+# ------------------------------------------------------------------------------------------------
+# a9: importance resampling (bit-exact)
+# ------------------------------------------------------------------------------------------------
+def test_sample_pdf_golden_bit_exact(ops):
+    fx, _ = load_golden("functions")
+    samples, inds = ops.sample_pdf(dev(fx["pdf/bins"]), dev(fx["pdf/weights"]), dev(fx["pdf/u"]), want_inds=True)
+    assert inds.dtype == torch.int64
+    assert torch.equal(inds.cpu(), fx["pdf/inds"]), "searchsorted indices differ from the reference's golden vector"
+    o_s, o_i, _, _ = oracle.resample_pdf(fx["pdf/bins"], fx["pdf/weights"], fx["pdf/u"])
+    assert torch.equal(inds.cpu(), o_i) and torch.equal(samples.cpu(), o_s)
+
+
+@pytest.mark.parametrize("n,M,K", [(1000, 22, 24), (257, 1, 5), (64, 46, 48), (33, 254, 256), (5, 2047, 64), (3000, 10, 12)])
+def test_sample_pdf_vs_oracle_bit_exact(ops, n, M, K):
+    g = torch.Generator().manual_seed(M)
+    bins = torch.sort(torch.rand((n, M + 1), generator=g) * 1.7 + 0.25, dim=1).values
+    w = torch.rand((n, M), generator=g) ** 4
+    w[0] = 0                                   # all-zero row: uniform pdf
+    w[1] = 0
+    w[1, M // 2] = 1                           # spike
+    if M > 3:
+        w[2, : M // 2] = 0                     # leading empty bins: repeated cdf values
+    u = torch.rand((n, K), generator=g)
+    u[3, 0], u[3, -1] = 0.0, 1.0 - 2 ** -24    # extremes of torch.rand's range
+    samples, inds = ops.sample_pdf(dev(bins), dev(w), dev(u), want_inds=True)
+    o_s, o_i, _, _ = oracle.resample_pdf(bins, w, u)
+    assert torch.equal(inds.cpu(), o_i), f"{int((inds.cpu() != o_i).sum())} indices differ"
+    assert torch.equal(samples.cpu(), o_s), f"max diff {(samples.cpu() - o_s).abs().max().item():.3e}"
+
+
+@pytest.mark.parametrize("S", [3, 6, 12, 24, 48, 96])
+def test_resample_from_coarse_bit_exact(ops, S):
+    g = torch.Generator().manual_seed(S)
+    n = 2000
+    t = torch.sort(torch.rand((n, S), generator=g) * 1.7 + 0.25, dim=1).values
+    w = torch.rand((n, S), generator=g) ** 6
+    u = torch.rand((n, S), generator=g)
+    t_fine, inds = ops.resample_from_coarse(dev(t), dev(w), dev(u), want_inds=True)
+    o_s, o_i, _, _ = oracle.coarse_to_fine_t(w.reshape(1, n, S, 1), t.reshape(1, n, S, 1), u, S)
+    assert torch.equal(inds.cpu(), o_i) and torch.equal(t_fine.cpu(), o_s)
+
+
+def test_sample_pdf_properties_full_size(ops):
+    """c5-size: 1M rays x 64 bins.  Monotone in u, inside the bin range, deterministic."""
+    n, M, K = 1 << 20, 63, 64
+    g = torch.Generator(device="cuda").manual_seed(0)
+    bins = torch.sort(torch.rand((n, M + 1), generator=g, device="cuda") * 1.7 + 0.25, dim=1).values
+    w = torch.rand((n, M), generator=g, device="cuda") ** 4
+    u = torch.sort(torch.rand((n, K), generator=g, device="cuda"), dim=1).values
+    s1, i1 = ops.sample_pdf(bins, w, u, want_inds=True)
+    s2 = ops.sample_pdf(bins, w, u)
+    assert torch.equal(s1, s2)
+    assert (i1[:, 1:] >= i1[:, :-1]).all() and int(i1.min()) >= 0 and int(i1.max()) <= M + 1
+    assert (s1[:, 1:] >= s1[:, :-1] - 1e-6).all()
+    assert (s1 >= bins[:, :1] - 1e-6).all() and (s1 <= bins[:, -1:] + 1e-6).all()
+    # against the oracle on a slice the CPU finishes in a second
+    o_s, o_i, _, _ = oracle.resample_pdf(bins[:4096].cpu(), w[:4096].cpu(), u[:4096].cpu())
+    assert torch.equal(i1[:4096].cpu(), o_i) and torch.equal(s1[:4096].cpu(), o_s)
+
+
+# ------------------------------------------------------------------------------------------------
+# a11 + a8 + a12: merge, composite, image formatting
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,img,S", [(2, 8, 6), (1, 16, 24), (2, 4, 48), (1, 4, 100)])
+@pytest.mark.parametrize("white,last,noise_std,clamp", [(True, False, 0.0, "relu"), (False, True, 0.5, "softplus")])
+def test_merge_composite_vs_oracle(ops, B, img, S, white, last, noise_std, clamp):
+    from conditioned_nerf_gan_b200.generators.volumetric_rendering import camera_tables
+    g = torch.Generator().manual_seed(S + img)
+    R = img * img
+    fine = torch.randn((B, R, S, 4), generator=g)
+    coarse = torch.randn((B, R, S, 4), generator=g)
+    for x in (fine, coarse):
+        x[..., :3] = torch.sigmoid(x[..., :3])
+        x[..., 3] *= 6
+    t_c = torch.sort(torch.rand((B, R, S, 1), generator=g) * 1.7 + 0.25, dim=2).values
+    t_f = torch.sort(torch.rand((B, R, S, 1), generator=g) * 1.7 + 0.25, dim=2).values
+    t_f[0, 0, :3] = t_c[0, 0, :3]                 # exact ties: stable order puts the fine sample first
+    t_f[0, 1] = t_f[0, 1, 0]                      # a run of equal fine distances
+    noise = torch.randn((B, R, 2 * S, 1), generator=g)
+    rays, _ = camera_tables((img, img), S, FOV, 0.25, 1.95, "cuda")
+    pixels, depth, taps = ops.merge_composite(dev(fine), dev(coarse), dev(t_f), dev(t_c), dev(noise), rays, B, img, img,
+                                              noise_std, clamp, white, last, taps=True)
+    all_out, all_t, order = oracle.merge_by_depth(fine, coarse, t_f, t_c)
+    assert torch.equal(taps["order"].cpu().long(), order.squeeze(-1)), "merge order differs from the stable sort"
+    rgb, dist, _ = oracle.composite(all_out, all_t, noise, noise_std, clamp, white, last)
+    _assert_rel(taps["rgb"].cpu(), rgb, what="rgb")
+    _assert_rel(taps["dist"].cpu(), dist.squeeze(-1), what="dist")
+    pix_ref = rgb.reshape(B, img, img, 3).permute(0, 3, 1, 2) * 2 - 1
+    assert torch.allclose(pixels.cpu(), pix_ref, rtol=0, atol=2e-5)
+    depth_ref = (rays.cpu()[None, :, 2:] * dist).reshape(B, img, img)
+    _assert_rel(depth.cpu(), depth_ref, what="depth")
+
+
+def test_merge_composite_coarse_only(ops):
+    from conditioned_nerf_gan_b200.generators.volumetric_rendering import camera_tables
+    g = torch.Generator().manual_seed(4)
+    B, img, S = 2, 8, 12
+    coarse = torch.randn((B, img * img, S, 4), generator=g)
+    t_c = torch.sort(torch.rand((B, img * img, S, 1), generator=g) + 0.25, dim=2).values
+    rays, _ = camera_tables((img, img), S, FOV, 0.25, 1.95, "cuda")
+    pixels, depth, taps = ops.merge_composite(None, dev(coarse), None, dev(t_c), None, rays, B, img, img, 0.0, "relu", True, False, taps=True)
+    rgb, dist, _ = oracle.composite(coarse, t_c, torch.zeros_like(t_c), 0.0, "relu", True, False)
+    _assert_rel(taps["rgb"].cpu(), rgb, what="rgb")
+    assert torch.equal(taps["order"].cpu().long(), torch.arange(S).expand(B, img * img, S))
+
+
+# ------------------------------------------------------------------------------------------------
+# whole forward through ImplicitGenerator3d against the golden vectors recorded from the reference
+# ------------------------------------------------------------------------------------------------
+def _generator(siren_type, state, precision):
+    from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d
+    gen = ImplicitGenerator3d(siren_type, 256, 32, 4, 256)
+    gen.load_state_dict(state, strict=True)
+    gen = gen.to("cuda")
+    gen.set_device(torch.device("cuda"))
+    gen.siren.precision = precision
+    return gen
+
+
+@pytest.mark.parametrize("name", FORWARD_FIXTURES)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_forward_vs_reference_golden(name, precision):
+    state, siren_type, z, cam, draws, meta, taps = fixture_inputs(name)
+    gen = _generator(siren_type, state, precision)
+    zc = (dev(z[0]), dev(z[1]))
+    d = {k: dev(v) for k, v in draws.items()}
+    with torch.no_grad():
+        out = gen._render(zc[0], zc[1], dev(cam), meta["img_size"], meta["fov"], meta["ray_start"], meta["ray_end"],
+                          meta["num_steps"], meta["hierarchical_sample"], dict(meta, draws=d), taps=True)
+        pixels, depth = gen(zc, dev(cam), draws=d, **meta)
+    torch.cuda.synchronize()
+    assert torch.equal(pixels, out["pixels"]) and torch.equal(depth, out["depth"]), "forward is not deterministic"
+    B, img, S = cam.shape[0], meta["img_size"], meta["num_steps"]
+    assert pixels.shape == (B, 3, img, img) and depth.shape == (B, img, img) and pixels.is_contiguous()
+    assert torch.allclose(out["points_coarse"].cpu(), taps["points_coarse"].reshape(B, -1, S, 3), rtol=0, atol=5e-7)
+    mlp_tol = 5e-4 if precision == "fp32" else (3e-2 if "SHORT" in name else 1e-2)
+    err_c = (out["rgb_sigma_coarse"].cpu() - taps["rgb_sigma_coarse"].reshape(B, -1, S, 4)).abs().max().item()
+    psnr = oracle.psnr(pixels.cpu(), taps["pixels"])
+    err_p = (pixels.cpu() - taps["pixels"]).abs().max().item()
+    print(f"{name} {precision}: coarse rgb_sigma max-abs {err_c:.3e}; pixels max-abs {err_p:.3e}, PSNR {psnr:.1f} dB")
+    assert err_c < mlp_tol
+    assert psnr >= (60.0 if precision == "fp32" else 40.0)
+    if precision == "fp32":
+        assert err_p < 2e-3
+        assert torch.allclose(depth.cpu(), taps["depth"], rtol=0, atol=2e-3)
+
+
+def test_forward_draws_follow_reference_rng_order():
+    """Without replayed draws the generator consumes torch's CUDA generator in the reference's order and
+    shapes (rand[B,R,S,1], randn[B,R,S,1], rand[B*R,S], randn[B,R,2S,1])."""
+    state, siren_type, z, cam, _, meta, _ = fixture_inputs("fwd_DOUBLESIREN_FG")
+    gen = _generator(siren_type, state, "fp32")
+    B, R, S = cam.shape[0], meta["img_size"] ** 2, meta["num_steps"]
+    zc = (dev(z[0]), dev(z[1]))
+    torch.manual_seed(123)
+    with torch.no_grad():
+        a, _ = gen(zc, dev(cam), **meta)
+    torch.manual_seed(123)
+    d = {"u_jitter": torch.rand((B, R, S, 1), device="cuda"), "noise_coarse": torch.randn((B, R, S, 1), device="cuda"),
+         "u_resample": torch.rand((B * R, S), device="cuda"), "noise_final": torch.randn((B, R, 2 * S, 1), device="cuda")}
+    with torch.no_grad():
+        b, _ = gen(zc, dev(cam), draws=d, **meta)
+    assert torch.equal(a, b)
+
+
+def test_siren_secondary_boundary(ops):
+    """gen.siren(points, z, img_size, num_steps) as called by extract_shapes.py:63-68."""
+    state, siren_type, z, cam, draws, meta, taps = fixture_inputs("fwd_TALLSIREN_FG")
+    gen = _generator(siren_type, state, "fp32")
+    B, S, img = cam.shape[0], meta["num_steps"], meta["img_size"]
+    pts = taps["points_coarse"].reshape(B, -1, 3)
+    with torch.no_grad():
+        out = gen.siren(dev(pts), (dev(z[0]), dev(z[1])), img, S)
+    assert out.shape == (B, pts.shape[1], 4)
+    assert (out.cpu() - taps["rgb_sigma_coarse"].reshape(B, -1, 4)).abs().max().item() < 5e-4
+
+
+def test_staged_forward_matches_forward():
+    state, siren_type, z, cam, draws, meta, _ = fixture_inputs("fwd_DOUBLESIREN_FG")
+    gen = _generator(siren_type, state, "fp32")
+    meta = dict(meta, nerf_noise=0.0)
+    B = cam.shape[0]
+    d = {k: dev(v) for k, v in draws.items()}
+    zc = (dev(z[0]), dev(z[1]))
+    with torch.no_grad():
+        full, depth_full = gen(zc, dev(cam), draws=d, **meta)
+    R, S = meta["img_size"] ** 2, meta["num_steps"]
+    for b in range(B):
+        db = {"u_jitter": d["u_jitter"][b:b + 1], "noise_coarse": d["noise_coarse"][b:b + 1],
+              "u_resample": d["u_resample"][b * R:(b + 1) * R], "noise_final": d["noise_final"][b:b + 1]}
+        px, dp = gen.staged_forward((zc[0][b:b + 1], zc[1][b:b + 1]), dev(cam[b:b + 1]), max_batch_size=1, draws=db, **meta)
+        assert torch.equal(px[0], full[b]) and torch.equal(dp[0], depth_full[b])
+    # one object, several poses, chunked
+    poses = dev(cam[:1]).expand(3, 4, 4).contiguous()
+    torch.manual_seed(0)
+    px, dp = gen.staged_forward((zc[0][:1], zc[1][:1]), poses, max_batch_size=2, **meta)
+    assert px.shape == (3, 3, meta["img_size"], meta["img_size"]) and torch.isfinite(px).all()
+
+
+def test_errors_on_device(ops):
+    with pytest.raises(TypeError):
+        ops.composite_fwd(torch.zeros(2, 4, 4, device="cuda"), torch.zeros(2, 4, device="cuda"), None, 0.0, "tanh")
+    with pytest.raises(ValueError):
+        ops.sample_pdf(torch.zeros(2, 4, device="cuda"), torch.zeros(2, 4, device="cuda"), torch.zeros(2, 3, device="cuda"))
+    from conditioned_nerf_gan_b200 import _lib
+    v = torch.zeros((1, 4, 4, 4, 6), device="cuda")     # C = 6: not a multiple of 4
+    with pytest.raises(_lib.CngError):
+        ops.gather_points(v, torch.zeros((1, 3, 3), device="cuda"))
+    # empty batch / empty point set: no-op
+    out = ops.composite_fwd(torch.zeros(0, 4, 4, device="cuda"), torch.zeros(0, 4, device="cuda"), None, 0.0, "relu")
+    assert out[0].shape == (0, 3)

@@ -1,0 +1,118 @@
+"""CPU-only checks of the host-side mirror of the reference's generator interface."""
+import pytest
+import torch
+
+from conditioned_nerf_gan_b200 import ops
+from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d, siren, volumetric_rendering as vr
+from oracle import nerf_path as oracle
+
+META = dict(img_size=8, fov=49.134342641202636, ray_start=0.25, ray_end=1.95, num_steps=6,
+            hierarchical_sample=True, clamp_mode="relu", nerf_noise=0.0, white_back=True,
+            # keys of the curriculum dict the generator must ignore
+            batch_size=4, topk_v=0.6, fade_steps=10000, unique_lr=False, betas=(0, 0.9), z_lambda=0)
+
+
+def make_z(B=1, V=8):
+    return torch.zeros((B, 32, V, V, V)), torch.zeros((B, 256))
+
+
+@pytest.mark.parametrize("name,layers", [("TALLSIREN_FG", 8), ("SHORTSIREN_FG", 4), ("DOUBLESIREN_FG", 2), ("SingleSIREN_dg", 1),
+                                         ("TALLSIREN_dg", 8), ("SHORTSIREN_dg", 4), ("DoubleSIREN_dg", 2)])
+def test_state_dict_layout_matches_reference(name, layers):
+    gen = ImplicitGenerator3d(siren_type=name, z_dim=256, input_dim=32, output_dim=4, hidden_dim=256)
+    ref_state = oracle.init_generator_state(name)
+    assert set(gen.state_dict().keys()) == set(ref_state.keys())
+    for k, v in gen.state_dict().items():
+        assert v.shape == ref_state[k].shape, k
+    gen.load_state_dict(ref_state, strict=True)
+    assert len(gen.siren.network) == layers
+    assert gen.epoch == 0 and gen.step == 0
+    gen.set_device("cpu")
+    assert gen.device == "cpu" and gen.siren.device == "cpu"
+    assert gen.siren.training
+    gen.eval()
+    assert not gen.siren.training
+
+
+def test_init_distributions():
+    torch.manual_seed(0)
+    for name, div in (("TALLSIREN_FG", 25.0), ("SHORTSIREN_FG", 12.0)):
+        s = ImplicitGenerator3d(name, 256, 32, 4, 256).siren
+        assert s.network[0].layer.weight.abs().max() <= 1 / 32            # first_layer_film_sine_init
+        bound = (6 / 256) ** 0.5 / div
+        assert bound * 0.98 < s.network[1].layer.weight.abs().max() <= bound
+        assert s.final_layer.weight.abs().max() <= bound
+        assert s.mapping_network.weight.shape == (2 * len(s.network) * 256, 256)
+
+
+def test_unknown_siren_type_is_attribute_error():
+    with pytest.raises(AttributeError):
+        ImplicitGenerator3d("NOPE", 256, 32, 4, 256)
+
+
+def test_missing_curriculum_keys_raise_keyerror():
+    gen = ImplicitGenerator3d("DOUBLESIREN_FG", 256, 32, 4, 256)
+    cam = torch.eye(4).unsqueeze(0)
+    for missing in ("clamp_mode", "nerf_noise"):
+        meta = {k: v for k, v in META.items() if k != missing}
+        with torch.no_grad(), pytest.raises(KeyError):
+            gen(make_z(), cam, **meta)
+
+
+def test_unknown_clamp_mode_is_type_error():
+    gen = ImplicitGenerator3d("DOUBLESIREN_FG", 256, 32, 4, 256)
+    meta = dict(META, clamp_mode=None)
+    with torch.no_grad(), pytest.raises(TypeError):
+        gen(make_z(), torch.eye(4).unsqueeze(0), **meta)
+    with pytest.raises(TypeError):
+        vr.fancy_integration(torch.zeros(1, 2, 4, 4), torch.zeros(1, 2, 4, 1), "cpu", clamp_mode="tanh")
+
+
+def test_z_must_be_volume_and_global():
+    gen = ImplicitGenerator3d("DOUBLESIREN_FG", 256, 32, 4, 256)
+    with torch.no_grad(), pytest.raises(ValueError):
+        gen(torch.zeros(1, 32, 8, 8, 8), torch.eye(4).unsqueeze(0), **META)
+
+
+def test_no_cpu_fallback():
+    """CPU tensors must be refused, not rendered by some eager path."""
+    gen = ImplicitGenerator3d("DOUBLESIREN_FG", 256, 32, 4, 256)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU implementation"):
+        gen(make_z(), torch.eye(4).unsqueeze(0), **META)
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        ops.sample_pdf(torch.zeros(2, 5), torch.ones(2, 4), torch.rand(2, 3))
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        vr.fancy_integration(torch.zeros(1, 2, 4, 4), torch.zeros(1, 2, 4, 1), "cpu", clamp_mode="relu")
+
+
+def test_camera_tables_bitwise_equal_oracle():
+    for img, S in ((8, 6), (64, 12), (128, 24)):
+        rays, t = vr.camera_tables((img, img), S, META["fov"], 0.25, 1.95, "cpu")
+        _, t_ref, d_ref = oracle.camera_rays(1, S, img, META["fov"], 0.25, 1.95)
+        assert torch.equal(rays, d_ref[0]) and torch.equal(t, t_ref[0, 0, :, 0])
+    pts, z, d = vr.get_initial_rays_trig(2, 6, "cpu", META["fov"], (8, 8), 0.25, 1.95)
+    p_ref, z_ref, d_ref = oracle.camera_rays(2, 6, 8, META["fov"], 0.25, 1.95)
+    assert torch.equal(pts, p_ref) and torch.equal(z, z_ref) and torch.equal(d, d_ref)
+
+
+def test_camera_helpers_match_oracle():
+    import numpy as np
+    np.random.seed(5)
+    o = vr.sample_camera_positions("cpu", "y", 0.7, 1.5, 6)
+    o_ref = oracle.random_camera_origins(6, 0.7, 1.5, "y", np.random.RandomState(5))
+    assert torch.equal(o, o_ref)
+    assert torch.equal(vr.create_cam2world_matrix(o, "y"), oracle.look_at_cam2world(o, "y"))
+    assert torch.equal(vr.create_cam2world_matrix(o, "z"), oracle.look_at_cam2world(o, "z"))
+
+
+def test_grad_mode_fails_loudly_until_backward_exists():
+    from conditioned_nerf_gan_b200.generators import autograd
+    if getattr(autograd, "HAS_BACKWARD", False):
+        pytest.skip("backward kernels are built")
+    gen = ImplicitGenerator3d("DOUBLESIREN_FG", 256, 32, 4, 256)
+    with pytest.raises(NotImplementedError):
+        gen(make_z(), torch.eye(4).unsqueeze(0), **META)
+
+
+def test_alias_classes():
+    assert siren.TALLSIREN_dg is siren.TALLSIREN_FG and siren.DoubleSIREN_dg is siren.DOUBLESIREN_FG
