@@ -195,8 +195,8 @@ extern "C" {
 int cng_composite_fwd(const float* rgb_sigma, const float* t, const float* noise, long long n_rays, int S,
                       float noise_std, int clamp_mode, int white_back, int last_back, float* rgb, float* dist,
                       float* weights, cng_stream_t stream) {
-  CNG_REQUIRE(rgb_sigma && t, CNG_ERR_INVALID_ARGUMENT, "composite_fwd: NULL input");
   CNG_REQUIRE(n_rays >= 0 && S >= 1, CNG_ERR_INVALID_ARGUMENT, "composite_fwd: n_rays=%lld S=%d", n_rays, S);
+  CNG_REQUIRE(n_rays == 0 || (rgb_sigma && t), CNG_ERR_INVALID_ARGUMENT, "composite_fwd: NULL input");
   CNG_REQUIRE(S <= 1024, CNG_ERR_UNSUPPORTED, "composite_fwd: S=%d > 1024", S);
   CNG_REQUIRE(clamp_mode == CNG_CLAMP_RELU || clamp_mode == CNG_CLAMP_SOFTPLUS, CNG_ERR_INVALID_ARGUMENT,
               "composite_fwd: Need to choose clamp mode");
@@ -215,10 +215,10 @@ int cng_merge_composite(const float* rgb_sigma_fine, const float* rgb_sigma_coar
                         const float* t_coarse, const float* noise, const float* rays_d_cam, int B, int R, int S,
                         float noise_std, int clamp_mode, int white_back, int last_back, float* pixels, float* depth,
                         float* rgb, float* dist, int32_t* order, cng_stream_t stream) {
-  CNG_REQUIRE(rgb_sigma_coarse && t_coarse && rays_d_cam, CNG_ERR_INVALID_ARGUMENT, "merge_composite: NULL input");
+  CNG_REQUIRE(B >= 0 && R >= 1 && S >= 1, CNG_ERR_INVALID_ARGUMENT, "merge_composite: B=%d R=%d S=%d", B, R, S);
+  CNG_REQUIRE(B == 0 || (rgb_sigma_coarse && t_coarse && rays_d_cam), CNG_ERR_INVALID_ARGUMENT, "merge_composite: NULL input");
   CNG_REQUIRE((rgb_sigma_fine == nullptr) == (t_fine == nullptr), CNG_ERR_INVALID_ARGUMENT,
               "merge_composite: fine rgb_sigma and fine t must both be given or both be NULL");
-  CNG_REQUIRE(B >= 0 && R >= 1 && S >= 1, CNG_ERR_INVALID_ARGUMENT, "merge_composite: B=%d R=%d S=%d", B, R, S);
   const int n = rgb_sigma_fine ? 2 * S : S;
   CNG_REQUIRE(n <= 512, CNG_ERR_UNSUPPORTED, "merge_composite: %d samples per ray > 512", n);
   CNG_REQUIRE(clamp_mode == CNG_CLAMP_RELU || clamp_mode == CNG_CLAMP_SOFTPLUS, CNG_ERR_INVALID_ARGUMENT,

@@ -520,9 +520,10 @@ int cng_film_siren_fwd(const float* feat, int B, long long N, int C, int HID, in
                        const float* const* layer_b_host, const float* freq, const float* phase, const float* final_w,
                        const float* final_b, int sigmoid_rgb, int precision, void* workspace, size_t workspace_bytes,
                        float* rgb_sigma, cng_stream_t stream) {
+  CNG_REQUIRE(B >= 0 && N >= 0 && C >= 1 && HID >= 1 && L >= 1, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd: bad shape");
+  if (B == 0 || N == 0) return CNG_OK;
   CNG_REQUIRE(feat && layer_w_host && layer_b_host && freq && phase && final_w && final_b && rgb_sigma,
               CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd: NULL pointer");
-  CNG_REQUIRE(B >= 0 && N >= 0 && C >= 1 && HID >= 1 && L >= 1, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd: bad shape");
   for (int l = 0; l < L && l < 16; ++l)
     CNG_REQUIRE(layer_w_host[l] && layer_b_host[l], CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd: NULL layer %d", l);
   if (B == 0 || N == 0) return CNG_OK;

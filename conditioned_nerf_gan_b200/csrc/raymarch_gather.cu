@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256) channels_last_kernel(const float* __restr
 }
 
 static int check_volume(const void* vol, int B, int C, int D, int H, int W, const char* who) {
-  CNG_REQUIRE(vol != nullptr, CNG_ERR_INVALID_ARGUMENT, "%s: NULL volume", who);
+  CNG_REQUIRE(vol != nullptr || B == 0, CNG_ERR_INVALID_ARGUMENT, "%s: NULL volume", who);
   CNG_REQUIRE(B >= 0 && C >= 1 && D >= 1 && H >= 1 && W >= 1, CNG_ERR_INVALID_ARGUMENT, "%s: bad volume shape", who);
   CNG_REQUIRE(C % 4 == 0 && C <= 128, CNG_ERR_UNSUPPORTED, "%s: C=%d (need C %% 4 == 0 and C <= 128)", who, C);
   CNG_REQUIRE((reinterpret_cast<uintptr_t>(vol) & 15) == 0, CNG_ERR_INVALID_ARGUMENT, "%s: volume not 16-byte aligned", who);
@@ -243,8 +243,8 @@ static int raymarch_common(bool fine, const float* vol, int B, int C, int D, int
                            cng_stream_t stream) {
   const char* who = fine ? "raymarch_gather_fine" : "raymarch_gather_coarse";
   if (int e = cng::check_volume(vol, B, C, D, H, W, who)) return e;
-  CNG_REQUIRE(cam2world && rays_d_cam && feat, CNG_ERR_INVALID_ARGUMENT, "%s: NULL pointer", who);
-  CNG_REQUIRE(fine ? (t_fine != nullptr) : (t_lin != nullptr && t_out != nullptr), CNG_ERR_INVALID_ARGUMENT,
+  CNG_REQUIRE(B == 0 || (cam2world && rays_d_cam && feat), CNG_ERR_INVALID_ARGUMENT, "%s: NULL pointer", who);
+  CNG_REQUIRE(B == 0 || (fine ? (t_fine != nullptr) : (t_lin != nullptr && t_out != nullptr)), CNG_ERR_INVALID_ARGUMENT,
               "%s: NULL distance buffer", who);
   CNG_REQUIRE(img_w >= 1 && img_h >= 1 && S >= (fine ? 1 : 2), CNG_ERR_INVALID_ARGUMENT, "%s: img=%dx%d S=%d", who, img_w, img_h, S);
   CNG_REQUIRE(B <= 65535, CNG_ERR_UNSUPPORTED, "%s: B=%d > 65535", who, B);
@@ -279,8 +279,8 @@ int cng_raymarch_gather_fine(const float* vol_ndhwc, int B, int C, int D, int H,
 int cng_gather_points(const float* vol_ndhwc, int B, int C, int D, int H, int W, const float* points, long long N,
                       float* feat, int32_t* corner_idx, cng_stream_t stream) {
   if (int e = cng::check_volume(vol_ndhwc, B, C, D, H, W, "gather_points")) return e;
-  CNG_REQUIRE(points && feat, CNG_ERR_INVALID_ARGUMENT, "gather_points: NULL pointer");
   CNG_REQUIRE(N >= 0, CNG_ERR_INVALID_ARGUMENT, "gather_points: N=%lld", N);
+  CNG_REQUIRE(static_cast<long long>(B) * N == 0 || (points && feat), CNG_ERR_INVALID_ARGUMENT, "gather_points: NULL pointer");
   CNG_REQUIRE((reinterpret_cast<uintptr_t>(feat) & 15) == 0, CNG_ERR_INVALID_ARGUMENT, "gather_points: feat not 16-byte aligned");
   const long long total = static_cast<long long>(B) * N;
   if (total == 0) return CNG_OK;

@@ -110,8 +110,8 @@ extern "C" {
 
 int cng_sample_pdf(const float* bins, const float* weights, const float* u, long long n, int M, int K, float eps,
                    float* samples, int64_t* inds, cng_stream_t stream) {
-  CNG_REQUIRE(bins && weights && u && samples, CNG_ERR_INVALID_ARGUMENT, "sample_pdf: NULL pointer");
   CNG_REQUIRE(n >= 0 && M >= 1 && K >= 1, CNG_ERR_INVALID_ARGUMENT, "sample_pdf: n=%lld M=%d K=%d", n, M, K);
+  CNG_REQUIRE(n == 0 || (bins && weights && u && samples), CNG_ERR_INVALID_ARGUMENT, "sample_pdf: NULL pointer");
   CNG_REQUIRE(M <= 2047, CNG_ERR_UNSUPPORTED, "sample_pdf: M=%d > 2047", M);
   if (n == 0) return CNG_OK;
   if (int e = cng_device_check()) return e;
@@ -121,8 +121,8 @@ int cng_sample_pdf(const float* bins, const float* weights, const float* u, long
 
 int cng_resample_from_coarse(const float* t_coarse, const float* weights, const float* u, long long n, int S,
                              float* t_fine, int64_t* inds, cng_stream_t stream) {
-  CNG_REQUIRE(t_coarse && weights && u && t_fine, CNG_ERR_INVALID_ARGUMENT, "resample_from_coarse: NULL pointer");
   CNG_REQUIRE(n >= 0 && S >= 3, CNG_ERR_INVALID_ARGUMENT, "resample_from_coarse: n=%lld S=%d (need S >= 3)", n, S);
+  CNG_REQUIRE(n == 0 || (t_coarse && weights && u && t_fine), CNG_ERR_INVALID_ARGUMENT, "resample_from_coarse: NULL pointer");
   CNG_REQUIRE(S <= 2049, CNG_ERR_UNSUPPORTED, "resample_from_coarse: S=%d > 2049", S);
   if (n == 0) return CNG_OK;
   if (int e = cng_device_check()) return e;

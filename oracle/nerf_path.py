@@ -52,6 +52,7 @@ __all__ = [
     "draw_randoms",
     "render",
     "psnr",
+    "far_plane_sigma",
 ]
 
 # generators/siren.py:555 (and every other feature-volume variant): the voxel grid spans the
@@ -442,8 +443,21 @@ def render(state, siren_type, z, cam2worlds, draws, *, img_size, fov, ray_start,
     out["pixels"] = rgb.reshape(B, img_size, img_size, 3).permute(0, 3, 1, 2).contiguous() * 2 - 1
     out["depth"] = (d_cam[..., -1:] * dist).reshape(B, img_size, img_size).contiguous()  # vr.py:345-356
     if taps:
-        out.update(rgb=rgb, dist=dist, weights_final=w_all)
+        out.update(rgb=rgb, dist=dist, weights_final=w_all, rgb_sigma_all=all_out, noise_final=final_noise)
     return out
+
+
+def far_plane_sigma(out: Dict[str, torch.Tensor], nerf_noise: float) -> torch.Tensor:
+    """Density (+ noise) of the farthest composited sample of every ray, [B, R], from ``render(taps=True)``.
+
+    generators/volumetric_rendering.py:34-35 gives that sample delta = 1e10, so with clamp_mode "relu" its
+    alpha is the STEP function [sigma > 0] (1 - exp(-1e10 * relu(sigma))): the reference image is
+    discontinuous in that one value, and a pixel whose far-plane |sigma| is below the arithmetic tolerance
+    of the MLP (bf16 here, fp16 under the reference's own autocast) is decided by the sign of a number that
+    is zero within tolerance.  Image-level comparisons of a reduced-precision path therefore either use
+    clamp_mode "softplus" (alpha_last == 1 always) or exclude those pixels and report their fraction.
+    """
+    return out["rgb_sigma_all"][:, :, -1, 3] + out["noise_final"][:, :, -1, 0] * nerf_noise
 
 
 def psnr(a: torch.Tensor, b: torch.Tensor, data_range: float = 2.0) -> float:
