@@ -16,16 +16,20 @@
 //   * hidden layers: bf16 x bf16 -> fp32, K = 256 as 4 K-blocks of 64.
 //   * head: one N=16 MMA group (rows 4..15 of the operand are zero), bias + sigmoid in the epilogue.
 //
-// Kernel organisation (one persistent CTA per SM, 320 threads, cta_group::1)
-//   warps 0-3  epilogue of tile slot 0      warps 4-7  epilogue of tile slot 1
-//   warp  8    MMA issuer (one elected lane) + TMEM allocator
-//   warp  9    weight producer: cp.async.bulk (TMA unit, SASS UBLKCP) global -> smem ring,
-//              completion on mbarriers (complete_tx)
+// Kernel organisation (one persistent CTA per SM, 576 threads, cta_group::1)
+//   warps 0-7   epilogue of tile slot 0     warps 8-15  epilogue of tile slot 1
+//               (warp w works on TMEM lanes 32*(w%4).. and on accumulator columns 128*((w>>2)&1)..)
+//   warp  16    MMA issuer (one elected lane) + TMEM allocator
+//   warp  17    weight producer: cp.async.bulk (TMA unit, SASS UBLKCP) global -> smem ring,
+//               completion on mbarriers (complete_tx)
+//   The FiLM shift is not added in the epilogue: after an epilogue warp has read a block of
+//   accumulator columns it writes the NEXT layer's shift into them (tcgen05.st) and every MMA
+//   accumulates on top, so the epilogue per element is FMUL(1/2pi) + MUFU.SIN + half a pack.
 //   Two 128-point tiles are in flight per CTA ("ping-pong"): while the tensor pipe runs layer l
 //   of one tile, the epilogue warps of the other tile run sin() on their accumulator and write
 //   the next layer's bf16 A operand back into shared memory (128B-swizzled, K-major), so MUFU and
 //   tensor pipe overlap.  TMEM: 2 accumulators x 256 fp32 columns = all 512 columns.
-//   Shared memory: 2 x 64 KB A tiles + 3 x 32 KB weight ring + 2 KB shift + barriers = 226.3 KB.
+//   Shared memory: 2 x 64 KB A tiles + 3 x 32 KB weight ring + barriers = 224.1 KB.
 //   Weight K-blocks are stored in global memory as ready-made shared-memory images (already
 //   swizzled) so a block is one contiguous 32 KB bulk copy; no tensor map is needed.
 //
@@ -33,6 +37,7 @@
 // sin per point.  Per 128-point tile-layer: 16 MMAs (128x256x16) = 2048 tensor cycles and 32768
 // sin = 2048 MUFU cycles at 16/clk/SM: the two pipes are balanced by construction.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "cng_common.cuh"
 
@@ -46,12 +51,15 @@ constexpr int kHeadBytes = 8192;            // 4 x [16 n][64 k] bf16
 constexpr int kABlockBytes = 16384;         // [128 m][64 k] bf16
 constexpr int kATileBytes = 4 * kABlockBytes;
 constexpr int kRing = 3;
-constexpr int kNumThreads = 320;
+constexpr int kDefaultPolyOneIn = 0;   // measured: the MUFU unit is not the limiter, offloading sines only adds issue pressure
+constexpr int kEpiWarpsPerSlot = 8;
+constexpr int kMmaWarp = 2 * kEpiWarpsPerSlot;
+constexpr int kProducerWarp = kMmaWarp + 1;
+constexpr int kNumThreads = 32 * (kProducerWarp + 1);
 constexpr uint32_t kSmemA = 0;
 constexpr uint32_t kSmemW = 2 * kATileBytes;                         // 131072
-constexpr uint32_t kSmemShift = kSmemW + kRing * kChunkBytes;        // 229376
-constexpr uint32_t kSmemBar = kSmemShift + 2 * kHID * 4;             // 231424
-constexpr uint32_t kSmemTotal = kSmemBar + 128;                      // 231552 <= 232448
+constexpr uint32_t kSmemBar = kSmemW + kRing * kChunkBytes;          // 229376
+constexpr uint32_t kSmemTotal = kSmemBar + 128;                      // 229504 <= 232448
 
 // ---- workspace layout ------------------------------------------------------------------------
 // per item: [L0c0][L0c1][L1c0..L1c3]...[L(L-1)c3][head]  then, after all items, shift[B][L][256]
@@ -152,20 +160,26 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Spin on try_wait; a protocol bug turns into a trap (launch failure) instead of a hung GPU.
+// try_wait suspends the thread in hardware (up to the hint) instead of spinning through issue slots
+// that the other tile slot's epilogue warps need; a protocol bug turns into a trap (launch failure)
+// after ~4 s instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
-  const long long t0 = clock64();
-  for (;;) {
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)
         : "memory");
     if (ok) break;
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if ((it & 63u) == 63u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) __trap();
+    }
   }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -221,6 +235,51 @@ __device__ __forceinline__ constexpr uint32_t make_idesc(int M, int N) {
       : "memory")
 
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 16 consecutive fp32 columns of this warp's 32 lanes <- the same 16 values in every lane
+__device__ __forceinline__ void tmem_st_16(uint32_t taddr, const float4& a, const float4& b, const float4& c, const float4& d) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w), "f"(c.x), "f"(c.y),
+        "f"(c.z), "f"(c.w), "f"(d.x), "f"(d.y), "f"(d.z), "f"(d.w)
+      : "memory");
+}
+// 32 shift values (warp-uniform address) held in registers, loaded one block ahead of their use so the
+// L2 latency of the load is hidden behind the sines of the previous block
+struct Shift32 {
+  float4 v[8];
+  __device__ __forceinline__ void load(const float* __restrict__ shift) {
+    const float4* s4 = reinterpret_cast<const float4*>(shift);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __ldg(s4 + i);
+  }
+  // 32 accumulator columns starting at `taddr` <- the 32 values, identical in every lane
+  __device__ __forceinline__ void store(uint32_t taddr) const {
+    tmem_st_16(taddr, v[0], v[1], v[2], v[3]);
+    tmem_st_16(taddr + 16, v[4], v[5], v[6], v[7]);
+  }
+};
+
+// sin(x) on the FMA/ALU pipes, for the share of elements taken off the MUFU unit: u = x/pi, k = rint(u)
+// (magic-number rounding), f = u - k in [-0.5, 0.5], sin(x) = (-1)^k sin(pi f) with an odd degree-5 minimax
+// polynomial (max error 6.8e-5, below half a bf16 ulp of the result it feeds).
+__device__ __forceinline__ float sin_fma(float x) {
+  const float kMagic = 12582912.f;                      // 1.5 * 2^23
+  const float t = fmaf(x, 0.31830988618379067f, kMagic);
+  const float k = t - kMagic;
+  const float f = fmaf(x, 0.31830988618379067f, -k);
+  const float f2 = f * f;
+  float p = fmaf(f2, 2.2995474338531494f, -5.136905193328857f);
+  p = fmaf(p, f2, 3.1406400203704834f);
+  const uint32_t sign = __float_as_uint(t) << 31;       // parity of k
+  return __uint_as_float(__float_as_uint(p * f) ^ sign);
+}
+template <int kPolyOneIn>
+__device__ __forceinline__ float film_sin(float x, int j) {
+  if (kPolyOneIn > 0 && (j % (kPolyOneIn > 0 ? kPolyOneIn : 1)) == kPolyOneIn - 1) return sin_fma(x);
+  return __sinf(x);
+}
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   uint32_t r;
@@ -254,6 +313,8 @@ __device__ __forceinline__ TileInfo tile_info(const TcParams& p, long long t) {
   return ti;
 }
 
+// kPolyOneIn: 0 = every sine on the MUFU unit; n > 0 = one element in n uses sin_fma instead
+template <int kPolyOneIn>
 __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t s_base = smem_u32(smem);
@@ -269,10 +330,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kRing; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
-    for (int x = 0; x < 2; ++x) { mbar_init(act_ready(x), 128); mbar_init(acc_full(x), 1); }
+    for (int x = 0; x < 2; ++x) { mbar_init(act_ready(x), 32 * kEpiWarpsPerSlot); mbar_init(acc_full(x), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_base + kSmemBar + 96), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -284,7 +345,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
   const long long G = gridDim.x;
   const long long first = blockIdx.x;
 
-  if (warp == 9) {
+  if (warp == kProducerWarp) {
     // =========================== weight producer ===========================
     if (lane == 0) {
       int slot = 0;
@@ -309,7 +370,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
         }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       int slot = 0;
@@ -336,7 +397,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
                 const int ksteps = (l == 0 && c == 1) ? 2 : 4;
                 const uint32_t a_blk = a_base + (l == 0 ? 0 : c * kABlockBytes);
                 for (int ks = 0; ks < ksteps; ++ks)
-                  tc_mma_bf16(d_tmem, make_desc(a_blk + ks * 32), make_desc(b_base + ks * 32), idesc_main, (c | ks) ? 1u : 0u);
+                  tc_mma_bf16(d_tmem, make_desc(a_blk + ks * 32), make_desc(b_base + ks * 32), idesc_main, 1u);   // D holds the shift
               } else {
                 for (int kb = 0; kb < 4; ++kb)
                   for (int ks = 0; ks < 4; ++ks)
@@ -352,22 +413,29 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
       }
     }
   } else {
-    // =========================== epilogue warps (slot x = warp / 4) ===========================
-    const int x = warp >> 2;
+    // =========================== epilogue warps (slot x = warp / 8) ===========================
+    const int x = warp / kEpiWarpsPerSlot;
     const int q = warp & 3;                       // TMEM lane quarter == warp_id % 4
+    const int half = (warp >> 2) & 1;             // accumulator columns [128*half, 128*half + 128)
     const int row = q * 32 + lane;
     const uint32_t a_base = kSmemA + x * kATileBytes;
-    float* shift_s = reinterpret_cast<float*>(smem + kSmemShift) + x * kHID;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(x) * kHID;
     uint32_t acc_phase = 0;
-    const int tid_x = threadIdx.x & 127;
     for (long long t = first + x * G; t < p.total_tiles; t += 2 * G) {
       const TileInfo ti = tile_info(p, t);
+      const float* shift_item = p.shift + static_cast<size_t>(ti.item) * L * kHID;
+      // ---- accumulator <- shift of layer 0 (the previous tile's head has been read: acc_full wait below) ----
+      Shift32 sh;
+#pragma unroll 1
+      for (int cc = 4 * half; cc < 4 * half + 4; ++cc) {
+        sh.load(shift_item + cc * 32);
+        sh.store(t_lane + cc * 32);
+      }
       // ---- features -> A block 0 as [x_hi(32) | x_lo(32)] ----
       {
         const float4* f = reinterpret_cast<const float4*>(p.feat + (static_cast<size_t>(ti.item) * p.N + ti.n0) * kC0);
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
+        for (int it = 4 * half; it < 4 * half + 4; ++it) {
           const int r = q * 32 + it * 4 + (lane >> 3);
           const int c4 = lane & 7;                               // float4 index within the row: k = 4*c4
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -382,33 +450,29 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
           *reinterpret_cast<uint2*>(smem + a_base + sw128_offset(r, 32 + 4 * c4)) = lo;
         }
       }
+      tmem_st_wait();
+      tc_fence_before();
       fence_proxy_async();
       mbar_arrive(act_ready(x));
       for (int l = 0; l < L; ++l) {
-        // ---- this layer's shift vector -> smem (all 4 warps of the slot are past the previous one) ----
-        named_bar_sync(1 + x, 128);
-        reinterpret_cast<float2*>(shift_s)[tid_x] =
-            __ldg(reinterpret_cast<const float2*>(p.shift + (static_cast<size_t>(ti.item) * L + l) * kHID) + tid_x);
-        named_bar_sync(1 + x, 128);
+        const bool more = l + 1 < L;
+        const float* shift_next = shift_item + (more ? l + 1 : l) * kHID;
+        sh.load(shift_next + 4 * half * 32);                       // in flight while waiting for the accumulator
         mbar_wait(acc_full(x), acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
 #pragma unroll 1
-        for (int cc = 0; cc < 8; ++cc) {
+        for (int cc = 4 * half; cc < 4 * half + 4; ++cc) {
           uint32_t v[32];
           CNG_TMEM_LD_32(t_lane + cc * 32, v);
           tmem_ld_wait();
+          // the columns just read take the next layer's shift; the next MMA accumulates on top of it
+          if (more) sh.store(t_lane + cc * 32);
+          if (cc + 1 < 4 * half + 4) sh.load(shift_next + (cc + 1) * 32);   // next block's shift, used after these sines
           uint32_t o[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 sh = *reinterpret_cast<const float4*>(shift_s + cc * 32 + j);
-            const float a0 = __sinf(__uint_as_float(v[j + 0]) + sh.x);
-            const float a1 = __sinf(__uint_as_float(v[j + 1]) + sh.y);
-            const float a2 = __sinf(__uint_as_float(v[j + 2]) + sh.z);
-            const float a3 = __sinf(__uint_as_float(v[j + 3]) + sh.w);
-            o[j / 2] = pack_bf16(a0, a1);
-            o[j / 2 + 1] = pack_bf16(a2, a3);
-          }
+          for (int j = 0; j < 32; j += 2)
+            o[j / 2] = pack_bf16(film_sin<kPolyOneIn>(__uint_as_float(v[j]), j), film_sin<kPolyOneIn>(__uint_as_float(v[j + 1]), j + 1));
           // 32 columns = 64 bytes = 4 x 16-byte chunks of K-block cc/2, logical chunk (cc&1)*4 + i
           uint8_t* blk = smem + a_base + (cc >> 1) * kABlockBytes + row * 128;
 #pragma unroll
@@ -417,15 +481,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
             *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
           }
         }
+        tmem_st_wait();
         tc_fence_before();
         fence_proxy_async();
         mbar_arrive(act_ready(x));
       }
-      // ---- head: 4 accumulator columns -> bias, sigmoid(rgb), store ----
+      // ---- head: 4 accumulator columns -> bias, sigmoid(rgb), store (the column-half-0 warps hold them) ----
       mbar_wait(acc_full(x), acc_phase);
       acc_phase ^= 1;
       tc_fence_after();
-      {
+      if (half == 0) {
         uint32_t r0, r1, r2, r3;
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
@@ -445,13 +510,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
         }
         if (row < ti.rows) reinterpret_cast<float4*>(p.out)[static_cast<size_t>(ti.item) * p.N + ti.n0 + row] = o;
       }
-      tc_fence_before();   // orders the TMEM reads above before the next tile's first MMA (via act_ready)
+      tc_fence_before();   // orders the TMEM reads above before the next tile's stores / first MMA (via act_ready)
     }
   }
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
@@ -490,14 +555,23 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
   p.sigmoid_rgb = sigmoid_rgb; p.out = out;
   p.tiles_per_item = (N + kTileM - 1) / kTileM;
   p.total_tiles = p.tiles_per_item * B;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ce = cudaFuncSetAttribute(film_siren_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTotal));
+  // share of the sines evaluated on the FMA pipe instead of the MUFU unit (tuning knob, default from measurement)
+  static const int poly = [] {
+    const char* e = getenv("CNG_TC_POLY");
+    const int v = e ? atoi(e) : kDefaultPolyOneIn;
+    return (v == 0 || v == 2 || v == 3 || v == 4 || v == 8) ? v : kDefaultPolyOneIn;
+  }();
+  using KernelFn = void (*)(TcParams);
+  const KernelFn fn = poly == 0 ? film_siren_tc_kernel<0> : poly == 2 ? film_siren_tc_kernel<2> : poly == 3 ? film_siren_tc_kernel<3>
+                      : poly == 4 ? film_siren_tc_kernel<4> : film_siren_tc_kernel<8>;
+  static bool attr_set[9] = {};
+  if (!attr_set[poly]) {
+    ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTotal));
     if (ce != cudaSuccess) return fail(static_cast<int>(ce), "film_siren_fwd(bf16): smem attribute: %s", cudaGetErrorString(ce));
-    attr_set = true;
+    attr_set[poly] = true;
   }
   const long long grid = min(static_cast<long long>(sm_count()), p.total_tiles);
-  film_siren_tc_kernel<<<static_cast<unsigned>(grid), kNumThreads, kSmemTotal, stream>>>(p);
+  fn<<<static_cast<unsigned>(grid), kNumThreads, kSmemTotal, stream>>>(p);
   return check_launch("cng_film_siren_fwd(bf16)");
 }
 
