@@ -35,6 +35,12 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     "cng_sample_pdf": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "cng_resample_from_coarse": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p]),
+    "cng_merge_composite_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                        c_float, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "cng_scatter_points": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p]),
+    "cng_volume_from_channels_last": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "cng_film_sin_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
+    "cng_film_sin_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cng_merge_composite": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                                     c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

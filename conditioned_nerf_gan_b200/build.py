@@ -15,7 +15,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libcng_b200.so")
 STAMP = os.path.join(PKG, "csrc", ".build_stamp")
-SOURCES = ["cng_api.cu", "raymarch_gather.cu", "film_siren_simt.cu", "film_siren_tc.cu", "composite.cu", "sample_pdf.cu"]
+SOURCES = ["cng_api.cu", "raymarch_gather.cu", "film_siren_simt.cu", "film_siren_tc.cu", "composite.cu", "sample_pdf.cu", "backward.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -1,16 +1,237 @@
-"""Autograd bridge of the rendering path (a14: backward of a4-a8).  Filled in by the backward
-kernels; until then a call that needs gradients fails loudly instead of silently detaching."""
+"""Autograd bridge of the rendering path.
+
+The forward kernels stay the no-grad ones (K1, K2, K3', nothing saved per layer); each stage is a
+``torch.autograd.Function`` whose backward launches the kernels of csrc/backward.cu:
+
+    _ToChannelsLast   NCDHW <-> NDHWC                               cng_volume_{to,from}_channels_last
+    _Gather*          d feat -> d volume (scatter-add)               cng_scatter_points
+    _FilmSiren        d rgb_sigma -> d feat, d W/b, d freq/phase     activations recomputed per chunk:
+                      cng_film_sin_apply / cng_film_sin_grad (FiLM + sin / cos halves) around the
+                      layer GEMMs, which in this round are cuBLAS bf16 x bf16 -> fp32 (``torch.mm``
+                      with ``out_dtype``) -- library GEMMs, NOT hand-written tcgen05 yet
+    _MergeComposite   d pixels, d depth -> d rgb_sigma (fine, coarse)  cng_merge_composite_bwd
+
+Sample positions, distances and the coarse weights used for resampling carry no gradient, exactly
+as in the reference (``torch.no_grad()`` blocks at generators/generators.py:57 and :111); the FiLM
+mapping network (siren.py:550-553, a [B,256] x [256,4096] Linear) stays a differentiable torch op.
+"""
 from __future__ import annotations
+
+from typing import List
+
+import torch
+
+from .. import ops
+from .volumetric_rendering import camera_tables
+
+HAS_BACKWARD = True
+CHUNK_ROWS = 1 << 19          # points per recompute chunk of the MLP backward (~6.5 GB of temporaries at L = 8)
+
+
+class _ToChannelsLast(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, volume):
+        return ops.volume_to_channels_last(volume)
+
+    @staticmethod
+    def backward(ctx, d_cl):
+        return ops.volume_from_channels_last(d_cl.contiguous())
+
+
+def _scatter(vol_shape, points, d_feat):
+    dvol = torch.zeros(vol_shape, dtype=torch.float32, device=d_feat.device)
+    ops.scatter_points(dvol, points, d_feat.contiguous())
+    return dvol
+
+
+class _GatherCoarse(torch.autograd.Function):
+    """K1 coarse; differentiable w.r.t. the (channels-last) volume only."""
+
+    @staticmethod
+    def forward(ctx, vol_cl, cam2world, rays_d_cam, t_lin, u_jitter, img_size):
+        feat, t, pts = ops.raymarch_gather_coarse(vol_cl, cam2world, rays_d_cam, t_lin, u_jitter, img_size, img_size, want_points=True)
+        ctx.save_for_backward(pts)
+        ctx.vol_shape = vol_cl.shape
+        ctx.mark_non_differentiable(t)
+        return feat, t
+
+    @staticmethod
+    def backward(ctx, d_feat, _d_t):
+        (pts,) = ctx.saved_tensors
+        return _scatter(ctx.vol_shape, pts, d_feat), None, None, None, None, None
+
+
+class _GatherFine(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vol_cl, cam2world, rays_d_cam, t_fine, img_size):
+        feat, pts = ops.raymarch_gather_fine(vol_cl, cam2world, rays_d_cam, t_fine, img_size, img_size, want_points=True)
+        ctx.save_for_backward(pts)
+        ctx.vol_shape = vol_cl.shape
+        return feat
+
+    @staticmethod
+    def backward(ctx, d_feat):
+        (pts,) = ctx.saved_tensors
+        return _scatter(ctx.vol_shape, pts, d_feat), None, None, None, None
+
+
+class _GatherPoints(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vol_cl, points):
+        ctx.save_for_backward(points)
+        ctx.vol_shape = vol_cl.shape
+        return ops.gather_points(vol_cl, points)
+
+    @staticmethod
+    def backward(ctx, d_feat):
+        (points,) = ctx.saved_tensors
+        return _scatter(ctx.vol_shape, points, d_feat), None
+
+
+class _FilmSiren(torch.autograd.Function):
+    """K2 forward (fused, nothing saved per layer); backward recomputes the activations chunk by chunk."""
+
+    @staticmethod
+    def forward(ctx, feat, freq, phase, final_w, final_b, sigmoid_rgb, precision, *wb):
+        L = len(wb) // 2
+        ws, bs = list(wb[:L]), list(wb[L:])
+        out = ops.film_siren_fwd(feat, ws, bs, freq, phase, final_w, final_b, sigmoid_rgb, precision)
+        ctx.save_for_backward(feat, freq, phase, final_w, final_b, out, *wb)
+        ctx.sigmoid_rgb, ctx.L = sigmoid_rgb, L
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        feat, freq, phase, final_w, final_b, out, *wb = ctx.saved_tensors
+        L, H = ctx.L, final_w.shape[1]
+        ws, bs = [w.detach().float() for w in wb[:L]], [b.detach().float() for b in wb[L:]]
+        ws_bf = [w.to(torch.bfloat16) for w in ws]
+        fw = final_w.detach().float()
+        B, N, C = feat.shape
+        dev = feat.device
+        d_out = d_out.contiguous().float()
+        d_feat = torch.empty_like(feat)
+        d_freq = torch.zeros((B, L * H), dtype=torch.float32, device=dev)
+        d_phase = torch.zeros((B, L * H), dtype=torch.float32, device=dev)
+        d_ws = [torch.zeros_like(w) for w in ws]
+        d_bs = [torch.zeros_like(b) for b in bs]
+        d_fw = torch.zeros_like(fw)
+        d_fb = torch.zeros((4,), dtype=torch.float32, device=dev)
+        for b in range(B):
+            fr, ph = freq[b].detach().float(), phase[b].detach().float()
+            dph_before = d_phase[b].clone()
+            for r0 in range(0, N, CHUNK_ROWS):
+                r1 = min(N, r0 + CHUNK_ROWS)
+                x0 = feat[b, r0:r1].detach()
+                # ---- recompute: z_l = x_l W_l^T (fp32 out), x_{l+1} = bf16(sin(freq (z_l + b_l) + phase))
+                zs: List[torch.Tensor] = []
+                xs: List[torch.Tensor] = [x0]
+                for l in range(L):
+                    if l == 0:
+                        z = x0 @ ws[0].t()                                   # K = 32: fp32, like the split-bf16 layer 0 of K2
+                    else:
+                        z = torch.mm(xs[l], ws_bf[l].t(), out_dtype=torch.float32)
+                    zs.append(z)
+                    xs.append(ops.film_sin_apply(z, bs[l], fr[l * H:(l + 1) * H], ph[l * H:(l + 1) * H]))
+                # ---- head: out = x_L Wf^T + bf, rgb = sigmoid(out[:, :3])
+                d_o = d_out[b, r0:r1].clone()
+                if ctx.sigmoid_rgb:
+                    rgb = out[b, r0:r1, :3]
+                    d_o[:, :3] *= rgb * (1 - rgb)
+                d_o_bf = d_o.to(torch.bfloat16)
+                d_fw += torch.mm(d_o_bf.t(), xs[L], out_dtype=torch.float32)
+                d_fb += d_o.sum(0)
+                dy = (d_o @ fw).to(torch.bfloat16)
+                # ---- layers, last to first
+                for l in reversed(range(L)):
+                    sl = slice(l * H, (l + 1) * H)
+                    dz = ops.film_sin_grad(dy, zs[l], bs[l], fr[sl], ph[sl], d_freq[b, sl], d_phase[b, sl])
+                    zs[l] = None
+                    if l == 0:
+                        dzf = dz.float()
+                        d_ws[0] += dzf.t() @ x0
+                        d_feat[b, r0:r1] = dzf @ ws[0]
+                    else:
+                        d_ws[l] += torch.mm(dz.t(), xs[l], out_dtype=torch.float32)
+                        dy = torch.mm(dz, ws_bf[l])
+                    xs[l + 1] = None
+            # d b_l = sum_p dz = freq * sum_p du  (this item's share of d_phase)
+            dph_item = d_phase[b] - dph_before
+            for l in range(L):
+                d_bs[l] += fr[l * H:(l + 1) * H] * dph_item[l * H:(l + 1) * H]
+        return (d_feat, d_freq, d_phase, d_fw.to(final_w.dtype), d_fb.to(final_b.dtype), None, None,
+                *[g.to(p.dtype) for g, p in zip(d_ws, wb[:L])], *[g.to(p.dtype) for g, p in zip(d_bs, wb[L:])])
+
+
+class _MergeComposite(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fine, coarse, t_fine, t_coarse, noise, rays_d_cam, B, img_size, noise_std, clamp_mode, white_back, last_back):
+        pixels, depth = ops.merge_composite(fine, coarse, t_fine, t_coarse, noise, rays_d_cam, B, img_size, img_size, noise_std,
+                                            clamp_mode, white_back, last_back)
+        ctx.save_for_backward(fine, coarse, t_fine, t_coarse, noise, rays_d_cam)
+        ctx.cfg = (B, img_size, noise_std, clamp_mode, white_back, last_back)
+        return pixels, depth
+
+    @staticmethod
+    def backward(ctx, d_pixels, d_depth):
+        fine, coarse, t_fine, t_coarse, noise, rays_d_cam = ctx.saved_tensors
+        B, img_size, noise_std, clamp_mode, white_back, last_back = ctx.cfg
+        d_fine, d_coarse = ops.merge_composite_bwd(fine, coarse, t_fine, t_coarse, noise, rays_d_cam,
+                                                   d_pixels.contiguous() if d_pixels is not None else None,
+                                                   d_depth.contiguous() if d_depth is not None else None,
+                                                   B, img_size, img_size, noise_std, clamp_mode, white_back, last_back)
+        if fine is not None:
+            d_fine = d_fine.view_as(fine)
+        return d_fine, d_coarse.view_as(coarse), None, None, None, None, None, None, None, None, None, None
+
+
+def _mlp(net, feat, freq, phase):
+    ws, bs = net.layer_parameters()
+    return _FilmSiren.apply(feat, freq, phase, net.final_layer.weight, net.final_layer.bias, net.sigmoid_rgb, net.precision, *ws, *bs)
 
 
 def render_with_grad(gen, volume, global_feature, cam2worlds, img_size, fov, ray_start, ray_end, num_steps,
                      hierarchical_sample, kwargs):
-    raise NotImplementedError(
-        "ImplicitGenerator3d.forward was called with gradients enabled, but the backward kernels of the rendering "
-        "path are not built yet; wrap the call in torch.no_grad() (there is no eager-PyTorch fallback)")
+    """generators/generators.py:33-187 with gradients to the SIREN parameters, the feature volume and the
+    global feature.  Same launch sequence as ``ImplicitGenerator3d._render``."""
+    clamp_mode, nerf_noise = kwargs["clamp_mode"], kwargs["nerf_noise"]
+    white_back, last_back = kwargs.get("white_back", False), kwargs.get("last_back", False)
+    ops.clamp_code(clamp_mode)
+    draws = kwargs.get("draws") or {}
+    net = gen.siren
+    B, S, R = cam2worlds.shape[0], int(num_steps), int(img_size) ** 2
+    dev = cam2worlds.device
+    rays_d_cam, t_lin = camera_tables((img_size, img_size), S, fov, ray_start, ray_end, dev)
+
+    def draw(name, fn, shape):
+        t = draws.get(name)
+        return fn(shape, device=dev) if t is None else t.to(dev)
+
+    vol_cl = _ToChannelsLast.apply(volume.float())
+    freq, phase = net.film_parameters(global_feature)
+    C = vol_cl.shape[-1]
+    u_jitter = draw("u_jitter", torch.rand, (B, R, S, 1))
+    feat_c, t_c = _GatherCoarse.apply(vol_cl, cam2worlds, rays_d_cam, t_lin, u_jitter, img_size)
+    coarse = _mlp(net, feat_c.view(B, R * S, C), freq, phase)
+    if hierarchical_sample:
+        with torch.no_grad():
+            noise_c = draw("noise_coarse", torch.randn, (B, R, S, 1))
+            _, _, w_c = ops.composite_fwd(coarse.detach().view(B, R, S, 4), t_c, noise_c, nerf_noise, clamp_mode)
+            u_re = draw("u_resample", torch.rand, (B * R, S))
+            t_f = ops.resample_from_coarse(t_c, w_c, u_re)
+        feat_f = _GatherFine.apply(vol_cl, cam2worlds, rays_d_cam, t_f, img_size)
+        fine = _mlp(net, feat_f.view(B, R * S, C), freq, phase)
+        noise_f = draw("noise_final", torch.randn, (B, R, 2 * S, 1))
+        return _MergeComposite.apply(fine, coarse, t_f, t_c, noise_f, rays_d_cam, B, img_size, nerf_noise, clamp_mode,
+                                     white_back, last_back)
+    noise_f = draw("noise_final" if "noise_final" in draws else "noise_coarse", torch.randn, (B, R, S, 1))
+    return _MergeComposite.apply(None, coarse, None, t_c, noise_f, rays_d_cam, B, img_size, nerf_noise, clamp_mode,
+                                 white_back, last_back)
 
 
 def siren_forward_with_grad(net, points, volume, global_feature):
-    raise NotImplementedError(
-        "siren.forward was called with gradients enabled, but the backward kernels are not built yet; wrap the "
-        "call in torch.no_grad() (there is no eager-PyTorch fallback)")
+    """``siren(points, z, img_size, num_steps)`` with gradients (siren.py:540-580)."""
+    vol_cl = _ToChannelsLast.apply(volume.float())
+    freq, phase = net.film_parameters(global_feature)
+    feat = _GatherPoints.apply(vol_cl, points.detach())
+    return _mlp(net, feat, freq, phase)

@@ -74,9 +74,11 @@ class _FiLMSirenFG(nn.Module):
     # -- pieces shared with ImplicitGenerator3d ------------------------------------------------
     def film_parameters(self, global_feature: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """siren.py:550-553: freq = first half * 15 + 30, phase = second half.  [B, L*HID] each."""
-        fo = F.linear(global_feature.float(), self.mapping_network.weight.float(), self.mapping_network.bias.float())
-        half = fo.shape[-1] // 2
-        return (fo[..., :half] * 15 + 30).contiguous(), fo[..., half:].contiguous()
+        # fp32 even under the trainer's autocast: freq ~ 30 multiplies the pre-activations
+        with torch.autocast(device_type=global_feature.device.type, enabled=False):
+            fo = F.linear(global_feature.float(), self.mapping_network.weight.float(), self.mapping_network.bias.float())
+            half = fo.shape[-1] // 2
+            return (fo[..., :half] * 15 + 30).contiguous(), fo[..., half:].contiguous()
 
     def layer_parameters(self) -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
         return [f.layer.weight for f in self.network], [f.layer.bias for f in self.network]

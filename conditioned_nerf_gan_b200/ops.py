@@ -268,3 +268,84 @@ def merge_composite(rgb_sigma_fine, rgb_sigma_coarse, t_fine, t_coarse, noise, r
     if taps:
         return pixels, depth, {"rgb": rgb, "dist": dist, "order": order}
     return pixels, depth
+
+
+# --------------------------------------------------------------------------------------------------
+# backward entry points
+# --------------------------------------------------------------------------------------------------
+def merge_composite_bwd(rgb_sigma_fine, rgb_sigma_coarse, t_fine, t_coarse, noise, rays_d_cam, d_pixels, d_depth, B, img_h,
+                        img_w, noise_std, clamp_mode, white_back=False, last_back=False):
+    """Backward of merge_composite.  Returns (d_rgb_sigma_fine or None, d_rgb_sigma_coarse), each [B*R, S, 4]."""
+    code = clamp_code(clamp_mode)
+    rgb_sigma_coarse, t_coarse = _f32(rgb_sigma_coarse, "rgb_sigma_coarse"), _f32(t_coarse, "t_coarse")
+    R = img_h * img_w
+    S = rgb_sigma_coarse.numel() // (B * R * 4)
+    two = rgb_sigma_fine is not None
+    if two:
+        rgb_sigma_fine, t_fine = _f32(rgb_sigma_fine, "rgb_sigma_fine"), _f32(t_fine, "t_fine")
+    noise = _f32(noise, "noise") if (noise is not None and noise_std != 0) else None
+    rays_d_cam = _f32(rays_d_cam, "rays_d_cam")
+    d_pixels = _f32(d_pixels, "d_pixels") if d_pixels is not None else None
+    d_depth = _f32(d_depth, "d_depth") if d_depth is not None else None
+    dev = rgb_sigma_coarse.device
+    d_coarse = torch.empty((B * R, S, 4), dtype=torch.float32, device=dev)
+    d_fine = torch.empty((B * R, S, 4), dtype=torch.float32, device=dev) if two else None
+    with torch.cuda.device(dev), _timed("cng_merge_composite_bwd"):
+        _lib.call("cng_merge_composite_bwd", _ptr(rgb_sigma_fine) if two else None, _ptr(rgb_sigma_coarse),
+                  _ptr(t_fine) if two else None, _ptr(t_coarse), _ptr(noise), _ptr(rays_d_cam), _ptr(d_pixels), _ptr(d_depth),
+                  B, R, S, float(noise_std), code, int(bool(white_back)), int(bool(last_back)), _ptr(d_fine), _ptr(d_coarse),
+                  _stream(rgb_sigma_coarse))
+    _count()
+    return d_fine, d_coarse
+
+
+def scatter_points(dvol_cl, points, dfeat) -> None:
+    """dvol_cl [B,D,H,W,C] += trilinear-weighted dfeat [B,N,C] at points [B,N,3] (in place)."""
+    if not (dvol_cl.is_cuda and dvol_cl.dtype == torch.float32 and dvol_cl.is_contiguous()):
+        raise RuntimeError("scatter_points: dvol_cl must be a contiguous fp32 CUDA tensor (the rendering path has no CPU implementation)")
+    B, D, H, W, C = dvol_cl.shape
+    points, dfeat = _f32(points, "points"), _f32(dfeat, "dfeat")
+    N = points.numel() // (3 * B)
+    with torch.cuda.device(dvol_cl.device), _timed("cng_scatter_points"):
+        _lib.call("cng_scatter_points", _ptr(dvol_cl), B, C, D, H, W, _ptr(points), N, _ptr(dfeat), _stream(dvol_cl))
+    _count()
+
+
+def volume_from_channels_last(vol_cl: torch.Tensor) -> torch.Tensor:
+    """[B,D,H,W,C] -> [B,C,D,H,W]."""
+    vol_cl = _f32(vol_cl, "vol_ndhwc")
+    B, D, H, W, C = vol_cl.shape
+    out = torch.empty((B, C, D, H, W), dtype=torch.float32, device=vol_cl.device)
+    with torch.cuda.device(vol_cl.device), _timed("cng_volume_from_channels_last"):
+        _lib.call("cng_volume_from_channels_last", _ptr(vol_cl), _ptr(out), B, C, D, H, W, _stream(vol_cl))
+    _count()
+    return out
+
+
+def film_sin_apply(z, bias, freq, phase) -> torch.Tensor:
+    """bf16(sin(freq * (z + bias) + phase)); z [P,HID] fp32, bias/freq/phase [HID]."""
+    z = _f32(z, "z")
+    P, HID = z.shape
+    y = torch.empty((P, HID), dtype=torch.bfloat16, device=z.device)
+    with torch.cuda.device(z.device), _timed("cng_film_sin_apply"):
+        _lib.call("cng_film_sin_apply", _ptr(z), _ptr(_f32(bias, "bias")), _ptr(_f32(freq, "freq")), _ptr(_f32(phase, "phase")),
+                  P, HID, _ptr(y), _stream(z))
+    _count()
+    return y
+
+
+def film_sin_grad(dy_bf16, z, bias, freq, phase, dfreq, dphase) -> torch.Tensor:
+    """Returns dz (bf16 [P,HID]); accumulates into dfreq / dphase (fp32 [HID], in place)."""
+    z = _f32(z, "z")
+    P, HID = z.shape
+    if not (dy_bf16.is_cuda and dy_bf16.dtype == torch.bfloat16 and dy_bf16.is_contiguous() and dy_bf16.shape == z.shape):
+        raise RuntimeError("film_sin_grad: dy must be a contiguous bf16 CUDA tensor of z's shape")
+    for name, t in (("dfreq", dfreq), ("dphase", dphase)):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == HID):
+            raise RuntimeError(f"film_sin_grad: {name} must be a contiguous fp32 CUDA tensor with HID elements")
+    dz = torch.empty((P, HID), dtype=torch.bfloat16, device=z.device)
+    with torch.cuda.device(z.device), _timed("cng_film_sin_grad"):
+        _lib.call("cng_film_sin_grad", _ptr(dy_bf16), _ptr(z), _ptr(_f32(bias, "bias")), _ptr(_f32(freq, "freq")),
+                  _ptr(_f32(phase, "phase")), P, HID, _ptr(dz), _ptr(dfreq), _ptr(dphase), _stream(z))
+    _count()
+    return dz

@@ -183,6 +183,45 @@ CNG_API int cng_merge_composite(const float* rgb_sigma_fine, const float* rgb_si
                         float* depth, float* rgb, float* dist, int32_t* order,
                         cng_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Backward: what autograd computes for generators/generators.py:102-180
+ * when the trainer calls loss.backward() (utils.py:711).  Sample positions carry no gradient
+ * (built under torch.no_grad(), generators.py:57,111).
+ * ---------------------------------------------------------------------------------------- */
+
+/* Backward of cng_merge_composite: d_pixels [B,3,img_h,img_w] and/or d_depth [B,img_h,img_w]
+ * (either may be NULL) -> d_rgb_sigma_fine / d_rgb_sigma_coarse [B*R, S, 4] (every element is
+ * written).  Forward inputs are passed again; the merge order, alpha and transmittance are
+ * recomputed.  With rgb_sigma_fine == NULL it is the backward of a plain fancy_integration
+ * (volumetric_rendering.py:18-70) over the coarse samples. */
+CNG_API int cng_merge_composite_bwd(const float* rgb_sigma_fine, const float* rgb_sigma_coarse,
+                            const float* t_fine, const float* t_coarse, const float* noise,
+                            const float* rays_d_cam, const float* d_pixels, const float* d_depth,
+                            int B, int R, int S, float noise_std, int clamp_mode, int white_back,
+                            int last_back, float* d_rgb_sigma_fine, float* d_rgb_sigma_coarse,
+                            cng_stream_t stream);
+
+/* Backward of the trilinear lookup w.r.t. the volume (F.grid_sample backward, siren.py:555-571):
+ * dvol_ndhwc [B,D,H,W,C] += trilinear weights * dfeat [B,N,C] at points [B,N,3] (vector
+ * red.global.add).  The caller zero-fills dvol_ndhwc first. */
+CNG_API int cng_scatter_points(float* dvol_ndhwc, int B, int C, int D, int H, int W, const float* points,
+                       long long N, const float* dfeat, cng_stream_t stream);
+
+/* NDHWC -> NCDHW: the volume gradient back in the layout of the encoder's output. */
+CNG_API int cng_volume_from_channels_last(const float* vol_ndhwc, float* vol_ncdhw, int B, int C, int D,
+                                  int H, int W, cng_stream_t stream);
+
+/* Elementwise halves of FiLMLayer (siren.py:153-157) around the GEMMs of the activation-
+ * recomputing backward; z [P,HID] fp32 is the Linear output WITHOUT bias, bias/freq/phase [HID]:
+ *   apply: y = bf16(sin(freq * (z + bias) + phase))                              [P,HID] bf16
+ *   grad:  du = dy * cos(freq*(z+bias)+phase); dz = bf16(du * freq);
+ *          dfreq += sum_p du * (z+bias); dphase += sum_p du   (atomic accumulation, HID == 256) */
+CNG_API int cng_film_sin_apply(const float* z, const float* bias, const float* freq, const float* phase,
+                       long long P, int HID, void* y_bf16, cng_stream_t stream);
+CNG_API int cng_film_sin_grad(const void* dy_bf16, const float* z, const float* bias, const float* freq,
+                      const float* phase, long long P, int HID, void* dz_bf16, float* dfreq,
+                      float* dphase, cng_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,7 @@ __all__ = [
     "render",
     "psnr",
     "far_plane_sigma",
+    "render_with_grad",
 ]
 
 # generators/siren.py:555 (and every other feature-volume variant): the voxel grid spans the
@@ -405,29 +406,48 @@ def draw_randoms(batch, img_size, num_steps, hierarchical=True, generator: Optio
     return d
 
 
-@torch.no_grad()
 def render(state, siren_type, z, cam2worlds, draws, *, img_size, fov, ray_start, ray_end, num_steps,
            hierarchical_sample, clamp_mode, nerf_noise, white_back=False, last_back=False,
            taps: bool = True, **_ignored) -> Dict[str, torch.Tensor]:
     """generators/generators.py:33-187 (ImplicitGenerator3d.forward) with replayed draws.
 
     Returns a dict with ``pixels`` [B,3,H,W], ``depth`` [B,H,W] and (``taps=True``) every
-    intermediate the parity tests compare against.
+    intermediate the parity tests compare against.  Runs without autograd; ``render_with_grad``
+    is the same code with the reference's grad / no-grad structure.
     """
+    with torch.no_grad():
+        return _render(state, siren_type, z, cam2worlds, draws, img_size=img_size, fov=fov, ray_start=ray_start, ray_end=ray_end,
+                       num_steps=num_steps, hierarchical_sample=hierarchical_sample, clamp_mode=clamp_mode, nerf_noise=nerf_noise,
+                       white_back=white_back, last_back=last_back, taps=taps)
+
+
+def render_with_grad(state, siren_type, z, cam2worlds, draws, **meta):
+    """As ``render`` but differentiable w.r.t. ``state`` tensors, the volume and the global feature, with the
+    reference's structure: rays and resampling under torch.no_grad() (generators.py:57, :111), both SIREN
+    passes and the final composite with grad (:102-107, :155-160, :172-180)."""
+    meta = {k: v for k, v in meta.items() if k in ("img_size", "fov", "ray_start", "ray_end", "num_steps", "hierarchical_sample",
+                                                    "clamp_mode", "nerf_noise", "white_back", "last_back")}
+    return _render(state, siren_type, z, cam2worlds, draws, taps=False, **meta)
+
+
+def _render(state, siren_type, z, cam2worlds, draws, *, img_size, fov, ray_start, ray_end, num_steps,
+            hierarchical_sample, clamp_mode, nerf_noise, white_back=False, last_back=False, taps=True):
     B = cam2worlds.shape[0]
     R, S = img_size * img_size, num_steps
     out: Dict[str, torch.Tensor] = {}
-    pts_cam, t, d_cam = camera_rays(B, S, img_size, fov, ray_start, ray_end)
-    pts_cam, t = jitter_samples(pts_cam, t, d_cam, draws["u_jitter"])
-    pts_w, d_w, o_w = camera_to_world(pts_cam, d_cam, cam2worlds)
+    with torch.no_grad():
+        pts_cam, t, d_cam = camera_rays(B, S, img_size, fov, ray_start, ray_end)
+        pts_cam, t = jitter_samples(pts_cam, t, d_cam, draws["u_jitter"])
+        pts_w, d_w, o_w = camera_to_world(pts_cam, d_cam, cam2worlds)
     coarse = siren_forward(state, siren_type, pts_w.reshape(B, R * S, 3), z, img_size, S).reshape(B, R, S, 4)
     if taps:
         out.update(points_coarse=pts_w, t_coarse=t, dirs_world=d_w, origins_world=o_w, rgb_sigma_coarse=coarse)
     if hierarchical_sample:
-        _, _, w = composite(coarse, t, draws["noise_coarse"], nerf_noise, clamp_mode)
-        t_fine, inds, below, above = coarse_to_fine_t(w, t, draws["u_resample"], S)
-        t_fine = t_fine.reshape(B, R, S, 1)
-        pts_f = fine_points(o_w, d_w, t_fine)
+        with torch.no_grad():
+            _, _, w = composite(coarse, t, draws["noise_coarse"], nerf_noise, clamp_mode)
+            t_fine, inds, below, above = coarse_to_fine_t(w, t, draws["u_resample"], S)
+            t_fine = t_fine.reshape(B, R, S, 1)
+            pts_f = fine_points(o_w, d_w, t_fine)
         fine = siren_forward(state, siren_type, pts_f.reshape(B, R * S, 3), z, img_size, S).reshape(B, R, -1, 4)
         all_out, all_t, order = merge_by_depth(fine, coarse, t_fine, t)
         final_noise = draws["noise_final"]
