@@ -18,6 +18,12 @@ across ranks with no data-path collective).  Rank 0 prints ONE JSON line.
   cpu_baseline  the torch-CPU oracle (a port of the reference's path; kind "port") on a bounded
             sample of the same workload, all host threads
 ``--impl reference`` times that CPU path alone (rank 0 only) and prints the same line shape.
+
+Other workloads of BASELINE.json (not the driver's default line):
+  --workload train   generator-only train step at 128x128, 48+48 samples, GLOBAL batch 32 split over the N
+                     ranks (strong scaling): forward with grad + backward kernels + NCCL gradient all-reduce
+                     (DDP) + Adam; the encoder and the discriminator are out of scope and absent
+  --workload video   256x256, 48+48 samples, 64 poses of one object sharded over the N ranks (config 4)
 """
 from __future__ import annotations
 
@@ -306,6 +312,155 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def _setup_ranks(args):
+    import torch.distributed as dist
+    from conditioned_nerf_gan_b200 import _lib, parallel
+    _lib.load()
+    rank, world, local = parallel.init_distributed("nccl")
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    return rank, world, local, dev, barrier, max_over_ranks
+
+
+def _timed_steps(fn, steps, warmup, barrier, max_over_ranks):
+    from conditioned_nerf_gan_b200 import ops
+    for _ in range(warmup):
+        fn()
+    barrier()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = ops.launch_count
+    start.record()
+    for _ in range(steps):
+        fn()
+    end.record()
+    barrier()
+    return max_over_ranks(start.elapsed_time(end)), ops.launch_count - n0
+
+
+def run_train(args):
+    """Generator-only train step (BASELINE config 3 minus the out-of-scope encoder / discriminator)."""
+    import torch.distributed as dist
+    from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d
+    from oracle import nerf_path as oracle
+    rank, world, local, dev, barrier, max_over_ranks = _setup_ranks(args)
+    GLOBAL_B, img, S, V = 32, 128, 48, 64
+    if GLOBAL_B % world:
+        raise SystemExit("global batch 32 must divide by the number of GPUs")
+    b = GLOBAL_B // world
+    meta = render_meta(img, S)
+    meta["nerf_noise"] = 0.5
+    gen = ImplicitGenerator3d(args.siren, 256, 32, 4, 256)
+    gen.load_state_dict(oracle.init_generator_state(args.siren, seed=0), strict=True)
+    gen = gen.to(dev)
+    gen.set_device(dev)
+    gen.siren.precision = args.precision
+    model = gen
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(gen, device_ids=[local], find_unused_parameters=True)   # utils.py:322-326
+    opt = torch.optim.Adam(gen.parameters(), lr=5e-5, betas=(0.0, 0.9))
+    vol_h, glob_h, cam_h = (t.pin_memory() for t in synthetic_inputs(b, V, seed=rank))
+    target_h = (torch.rand((b, 3, img, img), generator=torch.Generator().manual_seed(100 + rank)) * 2 - 1).pin_memory()
+    losses = []
+
+    def step():
+        vol = vol_h.to(dev, non_blocking=True).requires_grad_(True)      # stands for the encoder output: receives a gradient
+        glob = glob_h.to(dev, non_blocking=True).requires_grad_(True)
+        cam, target = cam_h.to(dev, non_blocking=True), target_h.to(dev, non_blocking=True)
+        opt.zero_grad(set_to_none=True)
+        pixels, depth = model((vol, glob), cam, **meta)
+        loss = torch.nn.functional.mse_loss(pixels, target) + 0.1 * depth.mean()         # photo + depth terms (utils.py:673-706)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(gen.parameters(), 1.0)                               # utils.py:726-729
+        opt.step()
+        losses.append(loss.detach())
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, launches = _timed_steps(step, args.steps, args.warmup, barrier, max_over_ranks)
+    clocks = sampler.stop() if sampler else None
+    final_loss = float(losses[-1].item())        # device->host read of the step's result
+    if rank == 0:
+        L = SIREN_LAYERS[args.siren]
+        pts = GLOBAL_B * img * img * 2 * S
+        line = {"metric": "train_images_per_sec_128x128_48+48spp_global_batch32_generator_only", "value": GLOBAL_B * args.steps / (ms * 1e-3),
+                "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "generator_train_step_128x128_48+48spp_global_batch32 (BASELINE configs[2] without the out-of-scope U-Net encoder and discriminator)",
+                           "siren_type": args.siren, "batch_per_gpu": b, "optimizer": "Adam", "grad_allreduce": "DDP/NCCL" if world > 1 else "none",
+                           "backward": "hand-written compositing/scatter/FiLM-sin kernels + cuBLAS bf16 layer GEMMs (activation recompute)"},
+                "e2e": {"value": GLOBAL_B * args.steps / (ms * 1e-3), "unit": "images/s",
+                        "h2d_bytes_per_step": int((vol_h.numel() + glob_h.numel() + cam_h.numel() + target_h.numel()) * 4), "d2h_bytes_per_step": 4},
+                "gpu_launches": launches, "clocks": clocks, "final_loss": final_loss,
+                "mlp_flops_per_step_fwd": mlp_flops_per_point(L) * pts}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_video(args):
+    """BASELINE config 4: 64 poses of one object, 256x256, 48+48 samples, poses sharded over the ranks."""
+    import torch.distributed as dist
+    from conditioned_nerf_gan_b200 import parallel
+    from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d
+    from oracle import nerf_path as oracle
+    rank, world, local, dev, barrier, max_over_ranks = _setup_ranks(args)
+    P, img, S, V = 64, 256, 48, 64
+    gen = ImplicitGenerator3d(args.siren, 256, 32, 4, 256)
+    gen.load_state_dict(oracle.init_generator_state(args.siren, seed=0), strict=True)
+    gen = gen.to(dev).eval()
+    gen.set_device(dev)
+    gen.siren.precision = args.precision
+    vol, glob, _ = synthetic_inputs(1, V, seed=0)
+    z = (vol.to(dev), glob.to(dev))
+    parallel.broadcast_z(z, src=0)
+    # camera spiral around the object (inference.py:442-477 style), fov sweep 60 -> 30 (inference.py:459)
+    k = torch.arange(P, dtype=torch.float32) / P
+    theta, phi, r = 2 * np.pi * k, 0.35 * np.pi + 0.15 * np.pi * torch.sin(2 * np.pi * k), 1.2
+    origin = torch.stack([r * torch.sin(phi) * torch.cos(theta), r * torch.cos(phi), r * torch.sin(phi) * torch.sin(theta)], -1)
+    poses = oracle.look_at_cam2world(origin, "y").to(dev)
+    fov = [60.0 - 30.0 * (i // 8) / (P // 8 - 1) for i in range(P)]        # piecewise constant so that chunks of 8 share a fov
+    meta = {kk: v for kk, v in render_meta(img, S).items() if kk != "fov"}
+    frames_h = torch.empty((P, 3, img, img), dtype=torch.float32).pin_memory() if rank == 0 else None
+
+    def step():
+        pixels, depth = parallel.render_poses_sharded(gen, z, poses, fov=fov, max_batch_size=4, **meta)
+        if rank == 0:
+            frames_h.copy_(pixels, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, launches = _timed_steps(step, args.steps, args.warmup, barrier, max_over_ranks)
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        rays = P * img * img * args.steps
+        line = {"metric": "video_rays_per_sec_256x256_48+48spp_64poses", "value": rays / (ms * 1e-3), "unit": "rays/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": "staged_forward video render 256x256, 48+48 samples, 64 poses, one 64^3x32 object (BASELINE configs[3])",
+                           "siren_type": args.siren, "frames_per_s": P * args.steps / (ms * 1e-3), "poses_per_gpu": P // world,
+                           "parallelism": f"poses sharded over {world} GPU(s); one all_gather of frames per step"},
+                "e2e": {"value": rays / (ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(P * 3 * img * img * 4)},
+                "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -315,11 +470,16 @@ def main():
     ap.add_argument("--siren", default="TALLSIREN_FG", choices=sorted(SIREN_LAYERS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="render", choices=["render", "train", "video"])
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         print(f"note: --warmup {args.warmup} < 3 (timing rules ask for >= 3)", file=sys.stderr)
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "train":
+        run_train(args)
+    elif args.workload == "video":
+        run_video(args)
     else:
         run_gpu(args)
 

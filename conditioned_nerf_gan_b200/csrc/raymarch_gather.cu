@@ -92,6 +92,7 @@ __device__ __forceinline__ float4 trilinear_c4(const float4* __restrict__ vol, i
 
 struct RayParams {
   const float4* vol;        // [B, D, H, W, C/4]
+  long long vol_item_stride; // in float4 units; 0 = every batch item reads item 0's volume
   int B, C4, D, H, W;
   const float* cam2world;   // [B, 16]
   const float* rays_d_cam;  // [R, 3]
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(kPointsPerBlock * kLanesPerPoint) raymarch_gat
   const float m20 = __ldg(M + 8), m21 = __ldg(M + 9), m22 = __ldg(M + 10), m23 = __ldg(M + 11);
   const float dx = __ldg(p.rays_d_cam + 3 * ray), dy = __ldg(p.rays_d_cam + 3 * ray + 1), dz = __ldg(p.rays_d_cam + 3 * ray + 2);
   const size_t base = (static_cast<size_t>(b) * p.R + ray) * p.S;
-  const float4* vol = p.vol + static_cast<size_t>(b) * p.D * p.H * p.W * p.C4;
+  const float4* vol = p.vol + static_cast<size_t>(b) * p.vol_item_stride;
   float wx = 0.f, wy = 0.f, wz = 0.f, spacing = 0.f;
   if (FINE) {
     // world-space direction: bmm(cam2world[:3,:3], d_cam)      (volumetric_rendering.py:172-180)
@@ -237,7 +238,7 @@ int cng_volume_to_channels_last(const float* vol_ncdhw, float* vol_ndhwc, int B,
   return cng::check_launch("cng_volume_to_channels_last");
 }
 
-static int raymarch_common(bool fine, const float* vol, int B, int C, int D, int H, int W, const float* cam2world,
+static int raymarch_common(bool fine, const float* vol, long long vol_item_stride, int B, int C, int D, int H, int W, const float* cam2world,
                            const float* rays_d_cam, const float* t_lin, const float* u_jitter, const float* t_fine,
                            int img_w, int img_h, int S, float* feat, float* t_out, float* points_out,
                            cng_stream_t stream) {
@@ -252,7 +253,9 @@ static int raymarch_common(bool fine, const float* vol, int B, int C, int D, int
   if (B == 0) return CNG_OK;
   if (int e = cng_device_check()) return e;
   cng::RayParams p{};
-  p.vol = reinterpret_cast<const float4*>(vol); p.B = B; p.C4 = C / 4; p.D = D; p.H = H; p.W = W;
+  CNG_REQUIRE(vol_item_stride == 0 || vol_item_stride == static_cast<long long>(C) * D * H * W, CNG_ERR_INVALID_ARGUMENT,
+              "%s: vol_item_stride must be 0 (shared volume) or C*D*H*W", who);
+  p.vol = reinterpret_cast<const float4*>(vol); p.vol_item_stride = vol_item_stride / 4; p.B = B; p.C4 = C / 4; p.D = D; p.H = H; p.W = W;
   p.cam2world = cam2world; p.rays_d_cam = rays_d_cam; p.t_lin = t_lin; p.u_jitter = u_jitter; p.t_fine = t_fine;
   p.img_w = img_w; p.img_h = img_h; p.R = img_w * img_h; p.S = S;
   p.feat = reinterpret_cast<float4*>(feat); p.t_out = t_out; p.points_out = points_out;
@@ -262,17 +265,17 @@ static int raymarch_common(bool fine, const float* vol, int B, int C, int D, int
   return cng::check_launch(who);
 }
 
-int cng_raymarch_gather_coarse(const float* vol_ndhwc, int B, int C, int D, int H, int W, const float* cam2world,
+int cng_raymarch_gather_coarse(const float* vol_ndhwc, long long vol_item_stride, int B, int C, int D, int H, int W, const float* cam2world,
                                const float* rays_d_cam, const float* t_lin, const float* u_jitter, int img_w,
                                int img_h, int S, float* feat, float* t_out, float* points_out, cng_stream_t stream) {
-  return raymarch_common(false, vol_ndhwc, B, C, D, H, W, cam2world, rays_d_cam, t_lin, u_jitter, nullptr, img_w, img_h,
+  return raymarch_common(false, vol_ndhwc, vol_item_stride, B, C, D, H, W, cam2world, rays_d_cam, t_lin, u_jitter, nullptr, img_w, img_h,
                          S, feat, t_out, points_out, stream);
 }
 
-int cng_raymarch_gather_fine(const float* vol_ndhwc, int B, int C, int D, int H, int W, const float* cam2world,
+int cng_raymarch_gather_fine(const float* vol_ndhwc, long long vol_item_stride, int B, int C, int D, int H, int W, const float* cam2world,
                              const float* rays_d_cam, const float* t_fine, int img_w, int img_h, int S, float* feat,
                              float* points_out, cng_stream_t stream) {
-  return raymarch_common(true, vol_ndhwc, B, C, D, H, W, cam2world, rays_d_cam, nullptr, nullptr, t_fine, img_w, img_h, S,
+  return raymarch_common(true, vol_ndhwc, vol_item_stride, B, C, D, H, W, cam2world, rays_d_cam, nullptr, nullptr, t_fine, img_w, img_h, S,
                          feat, nullptr, points_out, stream);
 }
 

@@ -142,7 +142,7 @@ class ImplicitGenerator3d(nn.Module):
                 stop -= 1
             n = stop - start
             if shared:
-                v = vol_cl.expand(n, -1, -1, -1, -1).contiguous() if n > 1 else vol_cl
+                v = vol_cl                                                 # K1 reads item 0's volume for every pose (stride 0)
                 f = tuple(t.expand(n, -1).contiguous() for t in film)
             else:
                 v, f = vol_cl[start:stop], tuple(t[start:stop] for t in film)

@@ -92,14 +92,16 @@ def volume_to_channels_last(vol: torch.Tensor) -> torch.Tensor:
 def raymarch_gather_coarse(vol_cl, cam2world, rays_d_cam, t_lin, u_jitter, img_w, img_h, want_points=False):
     """K1 coarse.  Returns feat[B,R,S,C], t[B,R,S], points[B,R,S,3] or None."""
     vol_cl = _f32(vol_cl, "vol_ndhwc")
-    B, D, H, W, C = vol_cl.shape
+    Bv, D, H, W, C = vol_cl.shape
     cam2world = _f32(cam2world, "cam2world")
     rays_d_cam = _f32(rays_d_cam, "rays_d_cam")
     t_lin = _f32(t_lin, "t_lin")
     S = t_lin.numel()
     R = img_w * img_h
-    if cam2world.shape != (B, 4, 4):
-        raise ValueError(f"cam2world {tuple(cam2world.shape)} does not match volume batch {B}")
+    B = cam2world.shape[0]
+    if cam2world.shape != (B, 4, 4) or Bv not in (1, B):
+        raise ValueError(f"cam2world {tuple(cam2world.shape)} does not match volume batch {Bv}")
+    stride = 0 if (Bv == 1 and B > 1) else C * D * H * W      # one object seen from B cameras shares its volume
     if u_jitter is not None:
         u_jitter = _f32(u_jitter, "u_jitter")
         if u_jitter.numel() != B * R * S:
@@ -109,7 +111,7 @@ def raymarch_gather_coarse(vol_cl, cam2world, rays_d_cam, t_lin, u_jitter, img_w
     t_out = torch.empty((B, R, S), dtype=torch.float32, device=dev)
     pts = torch.empty((B, R, S, 3), dtype=torch.float32, device=dev) if want_points else None
     with torch.cuda.device(dev), _timed("cng_raymarch_gather_coarse"):
-        _lib.call("cng_raymarch_gather_coarse", _ptr(vol_cl), B, C, D, H, W, _ptr(cam2world), _ptr(rays_d_cam),
+        _lib.call("cng_raymarch_gather_coarse", _ptr(vol_cl), stride, B, C, D, H, W, _ptr(cam2world), _ptr(rays_d_cam),
                   _ptr(t_lin), _ptr(u_jitter), img_w, img_h, S, _ptr(feat), _ptr(t_out), _ptr(pts), _stream(vol_cl))
     _count()
     return feat, t_out, pts
@@ -118,17 +120,21 @@ def raymarch_gather_coarse(vol_cl, cam2world, rays_d_cam, t_lin, u_jitter, img_w
 def raymarch_gather_fine(vol_cl, cam2world, rays_d_cam, t_fine, img_w, img_h, want_points=False):
     """K1 fine.  t_fine [B,R,S].  Returns feat[B,R,S,C], points or None."""
     vol_cl = _f32(vol_cl, "vol_ndhwc")
-    B, D, H, W, C = vol_cl.shape
+    Bv, D, H, W, C = vol_cl.shape
     cam2world = _f32(cam2world, "cam2world")
     rays_d_cam = _f32(rays_d_cam, "rays_d_cam")
     t_fine = _f32(t_fine, "t_fine")
     R = img_w * img_h
+    B = cam2world.shape[0]
+    if Bv not in (1, B):
+        raise ValueError(f"cam2world {tuple(cam2world.shape)} does not match volume batch {Bv}")
+    stride = 0 if (Bv == 1 and B > 1) else C * D * H * W
     S = t_fine.numel() // (B * R)
     dev = vol_cl.device
     feat = torch.empty((B, R, S, C), dtype=torch.float32, device=dev)
     pts = torch.empty((B, R, S, 3), dtype=torch.float32, device=dev) if want_points else None
     with torch.cuda.device(dev), _timed("cng_raymarch_gather_fine"):
-        _lib.call("cng_raymarch_gather_fine", _ptr(vol_cl), B, C, D, H, W, _ptr(cam2world), _ptr(rays_d_cam),
+        _lib.call("cng_raymarch_gather_fine", _ptr(vol_cl), stride, B, C, D, H, W, _ptr(cam2world), _ptr(rays_d_cam),
                   _ptr(t_fine), img_w, img_h, S, _ptr(feat), _ptr(pts), _stream(vol_cl))
     _count()
     return feat, pts

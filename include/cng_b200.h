@@ -88,13 +88,15 @@ CNG_API int cng_volume_to_channels_last(const float* vol_ncdhw, float* vol_ndhwc
  * transform_sampled_points (:113-199) and the F.grid_sample + reshape/permute block of every
  * feature-volume SIREN (generators/siren.py:555-571).
  *   vol_ndhwc  [B, D, H, W, C]      cam2world [B, 4, 4]
+ *   vol_item_stride = C*D*H*W floats, or 0 when all B cameras look at ONE object whose volume is
+ *                     vol_ndhwc[0] (video rendering, inference.py:441-486)
  *   rays_d_cam [R, 3]               t_lin [S]
  *   u_jitter   [B, R, S] uniform draws (the reference's torch.rand at :106), NULL = no jitter
  *   feat       [B, R, S, C] out     t_out [B, R, S] out (jittered distances)
  *   points_out [B, R, S, 3] out, may be NULL (world-space sample positions, for taps/tests)
  * Requires C % 4 == 0, C <= 128, S >= 2, img_w * img_h == R.
  * ---------------------------------------------------------------------------------------- */
-CNG_API int cng_raymarch_gather_coarse(const float* vol_ndhwc, int B, int C, int D, int H, int W,
+CNG_API int cng_raymarch_gather_coarse(const float* vol_ndhwc, long long vol_item_stride, int B, int C, int D, int H, int W,
                                const float* cam2world, const float* rays_d_cam,
                                const float* t_lin, const float* u_jitter, int img_w, int img_h,
                                int S, float* feat, float* t_out, float* points_out,
@@ -102,7 +104,7 @@ CNG_API int cng_raymarch_gather_coarse(const float* vol_ndhwc, int B, int C, int
 
 /* K1 fine: p = o + d * t_fine in world space (generators/generators.py:138-145) + gather.
  *   t_fine [B, R, S];  feat [B, R, S, C] out;  points_out [B, R, S, 3] out or NULL. */
-CNG_API int cng_raymarch_gather_fine(const float* vol_ndhwc, int B, int C, int D, int H, int W,
+CNG_API int cng_raymarch_gather_fine(const float* vol_ndhwc, long long vol_item_stride, int B, int C, int D, int H, int W,
                              const float* cam2world, const float* rays_d_cam,
                              const float* t_fine, int img_w, int img_h, int S, float* feat,
                              float* points_out, cng_stream_t stream);
