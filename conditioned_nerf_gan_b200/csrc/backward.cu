@@ -17,6 +17,7 @@
 #include <cuda_bf16.h>
 
 #include "cng_common.cuh"
+#include "merge_sort.cuh"
 
 namespace cng {
 
@@ -52,38 +53,16 @@ __device__ __forceinline__ float warp_excl_suffix_sum(float v, int lane) {
 
 template <int IPL>
 __global__ void __launch_bounds__(kBwdWarps * 32) composite_bwd_kernel(CompositeBwdParams p) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const long long ray = static_cast<long long>(blockIdx.x) * kBwdWarps + warp;
   if (ray >= p.n_rays) return;
   const int n = p.n, S = p.S;
   const bool two = p.rgb_sigma_fine != nullptr;
-  float* raw_t = smem + static_cast<size_t>(warp) * 3 * n;
-  float* srt_t = raw_t + n;
-  int* srt_i = reinterpret_cast<int*>(srt_t + n);
-  for (int e = lane; e < n; e += 32) {
-    float te;
-    if (two) te = e < S ? __ldg(p.t_fine + ray * S + e) : __ldg(p.t + ray * S + (e - S));
-    else te = __ldg(p.t + ray * S + e);
-    raw_t[e] = te;
-  }
-  __syncwarp();
-  if (two) {
-    for (int e = lane; e < n; e += 32) {
-      const float te = raw_t[e];
-      int rank = 0;
-      for (int j = 0; j < n; ++j) {
-        const float tj = raw_t[j];
-        rank += (tj < te) || (tj == te && j < e);
-      }
-      srt_t[rank] = te;
-      srt_i[rank] = e;
-    }
-  } else {
-    for (int e = lane; e < n; e += 32) { srt_t[e] = raw_t[e]; srt_i[e] = e; }
-  }
-  __syncwarp();
+  const int n2 = next_pow2_min32(n);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem) + static_cast<size_t>(warp) * n2;
+  load_and_sort_ray(keys, two ? p.t_fine : nullptr, p.t, ray, S, n, n2, lane);
 
   const long long b = ray / p.R;
   const int r = static_cast<int>(ray - b * p.R);
@@ -105,9 +84,10 @@ __global__ void __launch_bounds__(kBwdWarps * 32) composite_bwd_kernel(Composite
     alpha[i] = 0.f; fac[i] = 1.f; e1[i] = 1.f; dl[i] = 0.f; pre[i] = 0.f; G[i] = 0.f; src[i] = -1;
     col[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (s < n) {
-      const float t0 = srt_t[s];
-      const float t1 = (s + 1 < n) ? srt_t[s + 1] : 0.f;
-      const int e = srt_i[s];
+      const unsigned long long k0 = keys[s];
+      const float t0 = key_t(k0);
+      const float t1 = (s + 1 < n) ? key_t(keys[s + 1]) : 0.f;
+      const int e = key_src(k0);
       src[i] = e;
       const float4* sp = (two && e < S) ? reinterpret_cast<const float4*>(p.rgb_sigma_fine) + ray * S + e
                                         : reinterpret_cast<const float4*>(p.rgb_sigma) + ray * S + (two ? e - S : e);
@@ -190,7 +170,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32) composite_bwd_kernel(Composite
 template <int IPL>
 static void launch_cbwd(const CompositeBwdParams& p, cudaStream_t stream) {
   const unsigned grid = static_cast<unsigned>((p.n_rays + kBwdWarps - 1) / kBwdWarps);
-  const size_t smem = static_cast<size_t>(kBwdWarps) * 3 * p.n * sizeof(float);
+  const size_t smem = static_cast<size_t>(kBwdWarps) * next_pow2_min32(p.n) * sizeof(unsigned long long);
   if (smem > 48 * 1024) cudaFuncSetAttribute(composite_bwd_kernel<IPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   composite_bwd_kernel<IPL><<<grid, kBwdWarps * 32, smem, stream>>>(p);
 }

@@ -10,6 +10,7 @@
 // a ray are read exactly once and nothing but the per-ray results goes back to HBM.
 // Algorithmic bytes per ray: S'*(16+4) read (+4*S' noise) + 16 written (+4*S' if weights).
 #include "cng_common.cuh"
+#include "merge_sort.cuh"
 
 namespace cng {
 
@@ -43,7 +44,7 @@ constexpr int kWarpsPerBlock = 8;
 
 template <int IPL, bool MERGE>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(CompositeParams p) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const long long ray = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + warp;
@@ -51,34 +52,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
   const int n = p.n;
   const int S = p.S;
 
-  float* raw_t = nullptr;
-  float* srt_t = nullptr;
-  int* srt_i = nullptr;
+  unsigned long long* keys = nullptr;
   if (MERGE) {
-    raw_t = smem + static_cast<size_t>(warp) * 3 * n;
-    srt_t = raw_t + n;
-    srt_i = reinterpret_cast<int*>(srt_t + n);
-    const bool two = p.rgb_sigma_fine != nullptr;
-    // concatenation order of the reference: fine first, then coarse (generators.py:163-164)
-    for (int e = lane; e < n; e += 32) {
-      float te;
-      if (two) te = e < S ? __ldg(p.t_fine + ray * S + e) : __ldg(p.t + ray * S + (e - S));
-      else te = __ldg(p.t + ray * S + e);
-      raw_t[e] = te;
-    }
-    __syncwarp();
-    // stable rank = #{j : t_j < t_e} + #{j < e : t_j == t_e}
-    for (int e = lane; e < n; e += 32) {
-      const float te = raw_t[e];
-      int rank = 0;
-      for (int j = 0; j < n; ++j) {
-        const float tj = raw_t[j];
-        rank += (tj < te) || (tj == te && j < e);
-      }
-      srt_t[rank] = te;
-      srt_i[rank] = e;
-    }
-    __syncwarp();
+    // concatenation order of the reference: fine first, then coarse (generators.py:163-164); stable sort by t
+    const int n2 = next_pow2_min32(n);
+    keys = reinterpret_cast<unsigned long long*>(smem) + static_cast<size_t>(warp) * n2;
+    load_and_sort_ray(keys, p.rgb_sigma_fine ? p.t_fine : nullptr, p.t, ray, S, n, n2, lane);
   }
 
   float alpha[IPL], fac[IPL], tt[IPL], cr[IPL], cg[IPL], cb[IPL];
@@ -91,9 +70,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
       float4 c;
       float t0, t1 = 0.f;
       if (MERGE) {
-        t0 = srt_t[s];
-        if (s + 1 < n) t1 = srt_t[s + 1];
-        const int e = srt_i[s];
+        const unsigned long long k0 = keys[s];
+        t0 = key_t(k0);
+        if (s + 1 < n) t1 = key_t(keys[s + 1]);
+        const int e = key_src(k0);
         const float4* src = (p.rgb_sigma_fine != nullptr && e < S)
                                 ? reinterpret_cast<const float4*>(p.rgb_sigma_fine) + ray * S + e
                                 : reinterpret_cast<const float4*>(p.rgb_sigma) + ray * S + (p.rgb_sigma_fine ? e - S : e);
@@ -171,7 +151,7 @@ template <bool MERGE>
 static int launch_composite(const CompositeParams& p, cudaStream_t stream) {
   const int ipl = (p.n + 31) / 32;
   const unsigned grid = static_cast<unsigned>((p.n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  const size_t smem = MERGE ? static_cast<size_t>(kWarpsPerBlock) * 3 * p.n * sizeof(float) : 0;
+  const size_t smem = MERGE ? static_cast<size_t>(kWarpsPerBlock) * next_pow2_min32(p.n) * sizeof(unsigned long long) : 0;
 #define CNG_LAUNCH(I)                                                                              \
   {                                                                                               \
     if (smem > 48 * 1024)                                                                         \

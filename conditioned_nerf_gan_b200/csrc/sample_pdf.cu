@@ -5,11 +5,11 @@
 // coarse distances as bins, weights[1:-1] + 1e-5 as weights).
 //
 // Bit-exactness contract (oracle/nerf_path.py::resample_pdf): the weight sum and the CDF are
-// accumulated sequentially in float64 and rounded to fp32 per element -- which is what
-// torch.cumsum does for fp32 on CPU -- so the searchsorted indices are reproducible bit for bit.
-// One lane walks the row (M <= ~100 in production; the row lives in shared memory), all lanes
-// then divide, search and interpolate in parallel with IEEE fp32 ops in the reference's order
-// (no FMA contraction: every op is an explicit __f*_rn intrinsic).
+// accumulated in float64 and rounded to fp32 per element -- which is what torch.cumsum does for
+// fp32 on CPU -- so the searchsorted indices are reproducible bit for bit.  The float64 sums are
+// exact for normalised weights (see the kernel), so a lane-blocked warp scan replaces the
+// sequential loop; the divide, the search and the lerp run in parallel with IEEE fp32 ops in
+// the reference's order (no FMA contraction: every op is an explicit __f*_rn intrinsic).
 // Algorithmic bytes per ray: 4*((M+1) + M + K) read + 4*K written (+8*K if indices are emitted).
 #include "cng_common.cuh"
 
@@ -53,25 +53,36 @@ __global__ void __launch_bounds__(kPdfWarps * 32) sample_pdf_kernel(PdfParams p)
     for (int j = lane; j < M; j += 32) cdf[j + 1] = __fadd_rn(__ldg(p.weights + ray * M + j), p.eps);
   }
   __syncwarp();
-  // ---- total (float64 sequential, one lane) ------------------------------------------------
-  float total;
-  {
-    double acc = 0.0;
-    if (lane == 0)
-      for (int j = 1; j <= M; ++j) acc += static_cast<double>(cdf[j]);
-    total = __shfl_sync(0xffffffffu, static_cast<float>(acc), 0);
+  // ---- total and CDF in float64 ------------------------------------------------------------------
+  // The oracle (and torch.cumsum on CPU) accumulates fp32 values sequentially in float64.  Every pdf value
+  // is an fp32 number in [~1e-8, 1] (weights carry +eps), so every partial sum is a multiple of 2^-50 that
+  // is <= ~1: it fits the 53-bit float64 significand, float64 addition is EXACT here, and any association
+  // order -- the lane-blocked scan below included -- produces the same bits as the sequential loop.
+  const int per = ((M + 31) >> 5) | 1;            // contiguous elements per lane; odd, so the lanes hit distinct banks
+  const int j0 = 1 + lane * per, j1 = min(M + 1, j0 + per);
+  double part = 0.0;
+  for (int j = j0; j < j1; ++j) part += static_cast<double>(cdf[j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  const float total = static_cast<float>(part);
+  double run = 0.0;
+  for (int j = j0; j < j1; ++j) {
+    const float pdf = __fdiv_rn(cdf[j], total);
+    cdf[j] = pdf;
+    run += static_cast<double>(pdf);
   }
-  // ---- pdf = w / total (parallel), cdf = cumsum in float64 (one lane) ----------------------
-  for (int j = lane + 1; j <= M; j += 32) cdf[j] = __fdiv_rn(cdf[j], total);
-  __syncwarp();
-  if (lane == 0) {
-    double acc = 0.0;
-    cdf[0] = 0.f;
-    for (int j = 1; j <= M; ++j) {
-      acc += static_cast<double>(cdf[j]);
-      cdf[j] = static_cast<float>(acc);
-    }
+  double incl = run;                              // inclusive scan of the lane totals
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
   }
+  double acc = incl - run;                        // sum of all earlier lanes
+  for (int j = j0; j < j1; ++j) {
+    acc += static_cast<double>(cdf[j]);
+    cdf[j] = static_cast<float>(acc);
+  }
+  if (lane == 0) cdf[0] = 0.f;
   __syncwarp();
   // ---- searchsorted(cdf, u, right=False) + lerp ---------------------------------------------
   for (int k = lane; k < p.K; k += 32) {
