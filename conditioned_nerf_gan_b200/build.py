@@ -15,8 +15,11 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libcng_b200.so")
 STAMP = os.path.join(PKG, "csrc", ".build_stamp")
-SOURCES = ["cng_api.cu", "raymarch_gather.cu", "film_siren_simt.cu", "film_siren_tc.cu", "composite.cu", "sample_pdf.cu", "backward.cu"]
+SOURCES = ["cng_api.cu", "raymarch_gather.cu", "film_siren_simt.cu", "film_siren_tc.cu", "film_siren_tc2.cu", "composite.cu", "sample_pdf.cu", "backward.cu"]
+# CNG_TC_EPI_WARPS (4 or 8): epilogue warps per tile slot of the one-CTA-per-SM tcgen05 kernel (film_siren_tc.cu)
+EPI_WARPS = os.environ.get("CNG_TC_EPI_WARPS", "8")
 NVCC_FLAGS = [
+    f"-DCNG_TC_EPI_WARPS={EPI_WARPS}",
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
 ]
@@ -31,7 +34,8 @@ def _nvcc() -> str:
 
 def _digest() -> str:
     h = hashlib.sha256()
-    paths = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "cng_common.cuh"), os.path.join(ROOT, "include", "cng_b200.h")]
+    paths = [os.path.join(CSRC, s) for s in SOURCES] + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
+    paths.append(os.path.join(ROOT, "include", "cng_b200.h"))
     for path in paths:
         with open(path, "rb") as f:
             h.update(f.read())

@@ -41,18 +41,19 @@
 
 #include "cng_common.cuh"
 
+#include "film_siren_tc_common.cuh"
+
+#ifndef CNG_TC_EPI_WARPS
+#define CNG_TC_EPI_WARPS 8
+#endif
+
 namespace cng {
 
-constexpr int kHID = 256;
-constexpr int kC0 = 32;
-constexpr int kTileM = 128;
-constexpr int kChunkBytes = 32768;          // [256 n][64 k] bf16
-constexpr int kHeadBytes = 8192;            // 4 x [16 n][64 k] bf16
-constexpr int kABlockBytes = 16384;         // [128 m][64 k] bf16
-constexpr int kATileBytes = 4 * kABlockBytes;
 constexpr int kRing = 3;
+constexpr int kDefaultCtaGroup = 1;   // measured: the pair kernel pays ~1300 cycles of cross-CTA hand-off per layer
 constexpr int kDefaultPolyOneIn = 0;   // measured: the MUFU unit is not the limiter, offloading sines only adds issue pressure
-constexpr int kEpiWarpsPerSlot = 8;
+constexpr int kEpiWarpsPerSlot = CNG_TC_EPI_WARPS;   // 4 or 8 (build-time knob, see build.py)
+constexpr int kBlocksPerWarp = 32 / kEpiWarpsPerSlot;      // 32-column accumulator blocks per epilogue warp
 constexpr int kMmaWarp = 2 * kEpiWarpsPerSlot;
 constexpr int kProducerWarp = kMmaWarp + 1;
 constexpr int kNumThreads = 32 * (kProducerWarp + 1);
@@ -61,21 +62,9 @@ constexpr uint32_t kSmemW = 2 * kATileBytes;                         // 131072
 constexpr uint32_t kSmemBar = kSmemW + kRing * kChunkBytes;          // 229376
 constexpr uint32_t kSmemTotal = kSmemBar + 128;                      // 229504 <= 232448
 
-// ---- workspace layout ------------------------------------------------------------------------
-// per item: [L0c0][L0c1][L1c0..L1c3]...[L(L-1)c3][head]  then, after all items, shift[B][L][256]
-__host__ __device__ inline size_t item_image_bytes(int L) {
-  return static_cast<size_t>(2 + 4 * (L - 1)) * kChunkBytes + kHeadBytes;
-}
-__host__ __device__ inline size_t chunk_offset(int L, int l, int c) {     // l == L -> head
-  if (l == 0) return static_cast<size_t>(c) * kChunkBytes;
-  if (l < L) return static_cast<size_t>(2 + 4 * (l - 1) + c) * kChunkBytes;
-  return static_cast<size_t>(2 + 4 * (L - 1)) * kChunkBytes;
-}
+int film_siren_tc2_launch(TcParams p, cudaStream_t stream);   // film_siren_tc2.cu
 
-// byte offset of bf16 element (row, k) inside a [rows][64] K-major SWIZZLE_128B block
-__host__ __device__ inline uint32_t sw128_offset(int row, int k) {
-  return static_cast<uint32_t>(row) * 128u + ((((static_cast<uint32_t>(k) >> 3) ^ (row & 7)) << 4)) + (k & 7) * 2u;
-}
+static long long* g_tc_trace = nullptr;   // debug hook, see cng_internal_set_tc_trace
 
 // ---- fold kernel ---------------------------------------------------------------------------------
 struct FoldParams {
@@ -148,172 +137,6 @@ __global__ void __launch_bounds__(256) film_fold_kernel(FoldParams p) {
   }
 }
 
-// ---- PTX wrappers ----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// try_wait suspends the thread in hardware (up to the hint) instead of spinning through issue slots
-// that the other tile slot's epilogue warps need; a protocol bug turns into a trap (launch failure)
-// after ~4 s instead of a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  long long t0 = 0;
-  for (uint32_t it = 0;; ++it) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(20000u)
-        : "memory");
-    if (ok) break;
-    if ((it & 63u) == 63u) {
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 8000000000LL) __trap();
-    }
-  }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 in
-// [0,14), LBO>>4 in [16,30) (=1, unused for swizzled K-major), SBO>>4 in [32,46) (8 rows x 128 B =
-// 1024), version=1 at bit 46, layout_type=2 (SWIZZLE_128B) at [61,64).
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
-// cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), K-major both, N>>3 at 17, M>>4 at 24
-__device__ __forceinline__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
-}
-
-#define CNG_TMEM_LD_32(taddr, v)                                                                                      \
-  asm volatile(                                                                                                       \
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                       \
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                       \
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                       \
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),   \
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),        \
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),       \
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                     \
-      : "r"(taddr)                                                                                                    \
-      : "memory")
-
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// 16 consecutive fp32 columns of this warp's 32 lanes <- the same 16 values in every lane
-__device__ __forceinline__ void tmem_st_16(uint32_t taddr, const float4& a, const float4& b, const float4& c, const float4& d) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w), "f"(c.x), "f"(c.y),
-        "f"(c.z), "f"(c.w), "f"(d.x), "f"(d.y), "f"(d.z), "f"(d.w)
-      : "memory");
-}
-// 32 shift values (warp-uniform address) held in registers, loaded one block ahead of their use so the
-// L2 latency of the load is hidden behind the sines of the previous block
-struct Shift32 {
-  float4 v[8];
-  __device__ __forceinline__ void load(const float* __restrict__ shift) {
-    const float4* s4 = reinterpret_cast<const float4*>(shift);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __ldg(s4 + i);
-  }
-  // 32 accumulator columns starting at `taddr` <- the 32 values, identical in every lane
-  __device__ __forceinline__ void store(uint32_t taddr) const {
-    tmem_st_16(taddr, v[0], v[1], v[2], v[3]);
-    tmem_st_16(taddr + 16, v[4], v[5], v[6], v[7]);
-  }
-};
-
-// sin(x) on the FMA/ALU pipes, for the share of elements taken off the MUFU unit: u = x/pi, k = rint(u)
-// (magic-number rounding), f = u - k in [-0.5, 0.5], sin(x) = (-1)^k sin(pi f) with an odd degree-5 minimax
-// polynomial (max error 6.8e-5, below half a bf16 ulp of the result it feeds).
-__device__ __forceinline__ float sin_fma(float x) {
-  const float kMagic = 12582912.f;                      // 1.5 * 2^23
-  const float t = fmaf(x, 0.31830988618379067f, kMagic);
-  const float k = t - kMagic;
-  const float f = fmaf(x, 0.31830988618379067f, -k);
-  const float f2 = f * f;
-  float p = fmaf(f2, 2.2995474338531494f, -5.136905193328857f);
-  p = fmaf(p, f2, 3.1406400203704834f);
-  const uint32_t sign = __float_as_uint(t) << 31;       // parity of k
-  return __uint_as_float(__float_as_uint(p * f) ^ sign);
-}
-template <int kPolyOneIn>
-__device__ __forceinline__ float film_sin(float x, int j) {
-  if (kPolyOneIn > 0 && (j % (kPolyOneIn > 0 ? kPolyOneIn : 1)) == kPolyOneIn - 1) return sin_fma(x);
-  return __sinf(x);
-}
-
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // first source -> upper half
-  return r;
-}
-
-struct TcParams {
-  const float* feat;        // [B, N, 32]
-  long long N;
-  int B, L;
-  const uint8_t* images;    // fold output
-  const float* shift;       // [B][L][256]
-  const float* final_b;     // [4]
-  int sigmoid_rgb;
-  float* out;               // [B, N, 4]
-  long long tiles_per_item;
-  long long total_tiles;
-};
-
-struct TileInfo {
-  int item;
-  long long n0;
-  int rows;
-};
-__device__ __forceinline__ TileInfo tile_info(const TcParams& p, long long t) {
-  TileInfo ti;
-  ti.item = static_cast<int>(t / p.tiles_per_item);
-  ti.n0 = (t - static_cast<long long>(ti.item) * p.tiles_per_item) * kTileM;
-  ti.rows = static_cast<int>(min(static_cast<long long>(kTileM), p.N - ti.n0));
-  return ti;
-}
-
-// kPolyOneIn: 0 = every sine on the MUFU unit; n > 0 = one element in n uses sin_fma instead
 template <int kPolyOneIn>
 __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -347,23 +170,26 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
 
   if (warp == kProducerWarp) {
     // =========================== weight producer ===========================
-    if (lane == 0) {
+    {
+      const bool elected = elect_one();
       int slot = 0;
       uint32_t phase = 0;
       for (long long t0 = first; t0 < p.total_tiles; t0 += 2 * G) {
         const int nx = (t0 + G < p.total_tiles) ? 2 : 1;
-        int items[2];
-        items[0] = static_cast<int>(t0 / p.tiles_per_item);
-        items[1] = nx == 2 ? static_cast<int>((t0 + G) / p.tiles_per_item) : 0;
+        const int item0 = static_cast<int>(t0 / p.tiles_per_item);
+        const int item1 = nx == 2 ? static_cast<int>((t0 + G) / p.tiles_per_item) : 0;
         for (int l = 0; l <= L; ++l) {
           const int nchunks = (l == 0) ? 2 : (l < L ? 4 : 1);
           const uint32_t bytes = (l < L) ? kChunkBytes : kHeadBytes;
           for (int x = 0; x < nx; ++x) {
-            const uint8_t* img = p.images + static_cast<size_t>(items[x]) * item_image_bytes(L);
+            const uint8_t* img = p.images + static_cast<size_t>(x == 0 ? item0 : item1) * item_image_bytes(L);
             for (int c = 0; c < nchunks; ++c) {
               mbar_wait(w_empty(slot), phase ^ 1);
-              mbar_arrive_expect_tx(w_full(slot), bytes);
-              bulk_g2s(s_base + kSmemW + slot * kChunkBytes, img + chunk_offset(L, l, c), bytes, w_full(slot));
+              if (elected) {
+                mbar_arrive_expect_tx(w_full(slot), bytes);
+                bulk_g2s(s_base + kSmemW + slot * kChunkBytes, img + chunk_offset(L, l, c), bytes, w_full(slot));
+              }
+              __syncwarp();
               if (++slot == kRing) { slot = 0; phase ^= 1; }
             }
           }
@@ -372,42 +198,59 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
     }
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // The whole warp runs the loop (warp-uniform control flow keeps descriptors and barrier addresses in
+    // uniform registers); one elected lane issues the tcgen05 instructions.  Measured with the lane-0-only
+    // version: ~150 cycles per MMA issue + ~130 per commit on the issuing thread, i.e. issue-bound.
+    {
+      const bool elected = elect_one();
       int slot = 0;
-      uint32_t phase = 0;
-      uint32_t act_phase[2] = {0, 0};
+      uint32_t phase = 0, act_phase = 0;           // act_phase: bit x = parity of act_ready(x)
       constexpr uint32_t idesc_main = make_idesc(128, 256);
       constexpr uint32_t idesc_head = make_idesc(128, 16);
-      for (long long t0 = first; t0 < p.total_tiles; t0 += 2 * G) {
+      int iter = 0;
+      for (long long t0 = first; t0 < p.total_tiles; t0 += 2 * G, ++iter) {
         const int nx = (t0 + G < p.total_tiles) ? 2 : 1;
         for (int l = 0; l <= L; ++l) {
           const int nchunks = (l == 0) ? 2 : (l < L ? 4 : 1);
           for (int x = 0; x < nx; ++x) {
-            mbar_wait(act_ready(x), act_phase[x]);
-            act_phase[x] ^= 1;
+            mbar_wait(act_ready(x), (act_phase >> x) & 1u);
+            act_phase ^= 1u << x;
             tc_fence_after();
+            if (elected) trace_event(p.trace, iter, l, x, 0);
             const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(x) * kHID;
-            const uint32_t a_base = s_base + kSmemA + x * kATileBytes;
+            const uint64_t a_desc0 = make_desc(s_base + kSmemA + x * kATileBytes);
             for (int c = 0; c < nchunks; ++c) {
               mbar_wait(w_full(slot), phase);
               tc_fence_after();
-              const uint32_t b_base = s_base + kSmemW + slot * kChunkBytes;
-              if (l < L) {
-                // layer 0: chunk 0 = 4 k-steps over [x_hi|x_lo], chunk 1 = 2 k-steps over [x_hi]
-                const int ksteps = (l == 0 && c == 1) ? 2 : 4;
-                const uint32_t a_blk = a_base + (l == 0 ? 0 : c * kABlockBytes);
-                for (int ks = 0; ks < ksteps; ++ks)
-                  tc_mma_bf16(d_tmem, make_desc(a_blk + ks * 32), make_desc(b_base + ks * 32), idesc_main, 1u);   // D holds the shift
-              } else {
-                for (int kb = 0; kb < 4; ++kb)
-                  for (int ks = 0; ks < 4; ++ks)
-                    tc_mma_bf16(d_tmem, make_desc(a_base + kb * kABlockBytes + ks * 32), make_desc(b_base + kb * 2048 + ks * 32),
-                                idesc_head, (kb | ks) ? 1u : 0u);
+              const uint64_t b_desc = make_desc(s_base + kSmemW + slot * kChunkBytes);
+              if (elected) {
+                if (l < L) {
+                  // layer 0: chunk 0 = 4 k-steps over [x_hi|x_lo], chunk 1 = 2 k-steps over [x_hi]
+                  const uint64_t a_desc = a_desc0 + (l == 0 ? 0 : c * (kABlockBytes >> 4));
+                  tc_mma_bf16(d_tmem, a_desc, b_desc, idesc_main, 1u);                 // D holds the shift: always accumulate
+                  tc_mma_bf16(d_tmem, a_desc + 2, b_desc + 2, idesc_main, 1u);         // +32 bytes = one K step of 16 bf16
+                  if (!(l == 0 && c == 1)) {
+                    tc_mma_bf16(d_tmem, a_desc + 4, b_desc + 4, idesc_main, 1u);
+                    tc_mma_bf16(d_tmem, a_desc + 6, b_desc + 6, idesc_main, 1u);
+                  }
+                } else {
+#pragma unroll
+                  for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                      tc_mma_bf16(d_tmem, a_desc0 + kb * (kABlockBytes >> 4) + 2 * ks, b_desc + kb * (2048 >> 4) + 2 * ks, idesc_head,
+                                  (kb | ks) ? 1u : 0u);
+                }
+                tc_commit(w_empty(slot));          // slot is free once these MMAs have read it
               }
-              tc_commit(w_empty(slot));          // slot is free once these MMAs have read it
+              __syncwarp();
               if (++slot == kRing) { slot = 0; phase ^= 1; }
             }
-            tc_commit(acc_full(x));              // accumulator of tile x complete
+            if (elected) {
+              tc_commit(acc_full(x));              // accumulator of tile x complete
+              trace_event(p.trace, iter, l, x, 1);
+            }
+            __syncwarp();
           }
         }
       }
@@ -416,18 +259,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
     // =========================== epilogue warps (slot x = warp / 8) ===========================
     const int x = warp / kEpiWarpsPerSlot;
     const int q = warp & 3;                       // TMEM lane quarter == warp_id % 4
-    const int half = (warp >> 2) & 1;             // accumulator columns [128*half, 128*half + 128)
+    const int half = (warp % kEpiWarpsPerSlot) >> 2;   // column group: blocks [kBlocksPerWarp*half, kBlocksPerWarp*(half+1))
+    constexpr int kB = kBlocksPerWarp;
     const int row = q * 32 + lane;
     const uint32_t a_base = kSmemA + x * kATileBytes;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(x) * kHID;
     uint32_t acc_phase = 0;
-    for (long long t = first + x * G; t < p.total_tiles; t += 2 * G) {
+    int iter = 0;
+    const bool tracer = (warp % kEpiWarpsPerSlot) == 0 && lane == 0;
+    for (long long t = first + x * G; t < p.total_tiles; t += 2 * G, ++iter) {
       const TileInfo ti = tile_info(p, t);
       const float* shift_item = p.shift + static_cast<size_t>(ti.item) * L * kHID;
       // ---- accumulator <- shift of layer 0 (the previous tile's head has been read: acc_full wait below) ----
       Shift32 sh;
 #pragma unroll 1
-      for (int cc = 4 * half; cc < 4 * half + 4; ++cc) {
+      for (int cc = kB * half; cc < kB * half + kB; ++cc) {
         sh.load(shift_item + cc * 32);
         sh.store(t_lane + cc * 32);
       }
@@ -435,7 +281,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
       {
         const float4* f = reinterpret_cast<const float4*>(p.feat + (static_cast<size_t>(ti.item) * p.N + ti.n0) * kC0);
 #pragma unroll
-        for (int it = 4 * half; it < 4 * half + 4; ++it) {
+        for (int it = kB * half; it < kB * half + kB; ++it) {
           const int r = q * 32 + it * 4 + (lane >> 3);
           const int c4 = lane & 7;                               // float4 index within the row: k = 4*c4
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -457,18 +303,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
       for (int l = 0; l < L; ++l) {
         const bool more = l + 1 < L;
         const float* shift_next = shift_item + (more ? l + 1 : l) * kHID;
-        sh.load(shift_next + 4 * half * 32);                       // in flight while waiting for the accumulator
+        sh.load(shift_next + kB * half * 32);                      // in flight while waiting for the accumulator
         mbar_wait(acc_full(x), acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
-#pragma unroll 1
-        for (int cc = 4 * half; cc < 4 * half + 4; ++cc) {
-          uint32_t v[32];
-          CNG_TMEM_LD_32(t_lane + cc * 32, v);
-          tmem_ld_wait();
-          // the columns just read take the next layer's shift; the next MMA accumulates on top of it
-          if (more) sh.store(t_lane + cc * 32);
-          if (cc + 1 < 4 * half + 4) sh.load(shift_next + (cc + 1) * 32);   // next block's shift, used after these sines
+        if (tracer) trace_event(p.trace, iter, l, x, 2);
+        auto finish_block = [&](const uint32_t (&v)[32], int cc) {
           uint32_t o[16];
 #pragma unroll
           for (int j = 0; j < 32; j += 2)
@@ -480,10 +320,41 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
             const int chunk = ((cc & 1) * 4 + i) ^ (row & 7);
             *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
           }
+        };
+        if constexpr (kEpiWarpsPerSlot == 4) {
+          // 320-thread CTA: enough registers to keep the TMEM load of block i+1 in flight under the sines of block i
+          uint32_t va[32], vb[32];
+          CNG_TMEM_LD_32(t_lane + (kB * half) * 32, va);
+#pragma unroll
+          for (int i = 0; i < kB; i += 2) {
+            const int cc = kB * half + i;
+            tmem_ld_wait();
+            CNG_TMEM_LD_32(t_lane + (cc + 1) * 32, vb);
+            if (more) sh.store(t_lane + cc * 32);
+            sh.load(shift_next + (cc + 1) * 32);
+            finish_block(va, cc);
+            tmem_ld_wait();
+            if (i + 2 < kB) CNG_TMEM_LD_32(t_lane + (cc + 2) * 32, va);
+            if (more) sh.store(t_lane + (cc + 1) * 32);
+            if (i + 2 < kB) sh.load(shift_next + (cc + 2) * 32);
+            finish_block(vb, cc + 1);
+          }
+        } else {
+#pragma unroll 1
+          for (int cc = kB * half; cc < kB * half + kB; ++cc) {
+            uint32_t v[32];
+            CNG_TMEM_LD_32(t_lane + cc * 32, v);
+            tmem_ld_wait();
+            // the columns just read take the next layer's shift; the next MMA accumulates on top of it
+            if (more) sh.store(t_lane + cc * 32);
+            if (cc + 1 < kB * half + kB) sh.load(shift_next + (cc + 1) * 32);   // next block's shift, used after these sines
+            finish_block(v, cc);
+          }
         }
         tmem_st_wait();
         tc_fence_before();
         fence_proxy_async();
+        if (tracer) trace_event(p.trace, iter, l, x, 3);
         mbar_arrive(act_ready(x));
       }
       // ---- head: 4 accumulator columns -> bias, sigmoid(rgb), store (the column-half-0 warps hold them) ----
@@ -548,6 +419,7 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
   if (int e = check_launch("cng_film_siren_fwd(bf16): fold")) return e;
 
   TcParams p{};
+  p.trace = g_tc_trace;
   p.feat = feat; p.N = N; p.B = B; p.L = L; p.images = fp.images; p.shift = fp.shift;
   CNG_REQUIRE((reinterpret_cast<uintptr_t>(final_b_dev) & 15) == 0, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd(bf16): final_b not 16-byte aligned");
   p.final_b = final_b_dev;
@@ -555,6 +427,13 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
   p.sigmoid_rgb = sigmoid_rgb; p.out = out;
   p.tiles_per_item = (N + kTileM - 1) / kTileM;
   p.total_tiles = p.tiles_per_item * B;
+  // CTA-pair kernel (film_siren_tc2.cu, cta_group::2) unless CNG_TC_CG=1 asks for the one-CTA-per-SM kernel below
+  static const int cta_group = [] {
+    const char* e = getenv("CNG_TC_CG");
+    const int v = e ? atoi(e) : kDefaultCtaGroup;
+    return (v == 1 || v == 2) ? v : kDefaultCtaGroup;
+  }();
+  if (cta_group == 2 && sm_count() >= 2) return film_siren_tc2_launch(p, stream);
   // share of the sines evaluated on the FMA pipe instead of the MUFU unit (tuning knob, default from measurement)
   static const int poly = [] {
     const char* e = getenv("CNG_TC_POLY");
@@ -583,6 +462,10 @@ int film_siren_simt_launch(const float* feat, int B, long long N, int C, int HID
 }  // namespace cng
 
 extern "C" {
+
+// Debug hook (not part of the ABI in include/cng_b200.h): device buffer of 4*9*2*8 int64 that receives the clock64
+// timeline of CTA 0 of the next cta_group::1 launches; NULL switches it off.  Used by tools/trace_tc.py.
+CNG_API void cng_internal_set_tc_trace(void* dev_buffer) { cng::g_tc_trace = static_cast<long long*>(dev_buffer); }
 
 size_t cng_film_siren_workspace_bytes(int B, int C, int HID, int L, int precision) {
   (void)C; (void)HID;
