@@ -260,10 +260,32 @@ def run_gpu(args):
         barrier()
         return max_over_ranks(start.elapsed_time(end)), ops.launch_count - n0
 
+    from conditioned_nerf_gan_b200.streaming import render_host_batches
+
+    def e2e_pipelined(steps):
+        """The public host-buffer API: every step's inputs start in pinned host memory and its image ends there;
+        H2D of step i+1 and D2H of step i-1 overlap the kernels of step i (three streams, two buffer sets)."""
+        n = 0
+        for px_h, dp_h in render_host_batches(gen, ((vol_h, glob_h, cam_h) for _ in range(steps)), meta, device=dev):
+            n += 1
+        assert n == steps
+        torch.cuda.synchronize()
+
+    def timed_e2e(steps, warmup):
+        e2e_pipelined(warmup)
+        barrier()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        e2e_pipelined(steps)
+        end.record()
+        barrier()
+        return max_over_ranks(start.elapsed_time(end))
+
     sampler = ClockSampler(local) if rank == 0 else None
     ms_total, launches = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
-    ms_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    ms_e2e_sync, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    ms_e2e = timed_e2e(args.steps, max(2, args.warmup // 2))
 
     # ---- roofline leg: per-entry-point CUDA-event durations over an instrumented pass of the same steps
     ops.kernel_events = {}
@@ -304,7 +326,8 @@ def run_gpu(args):
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": workload_config(args, "gpu"),
             "e2e": {"value": rays / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps, "api": "streaming.render_host_batches (H2D / kernels / D2H on three streams, double-buffered)",
+                    "unpipelined_value": rays / (ms_e2e_sync * 1e-3)},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

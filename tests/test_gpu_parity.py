@@ -478,3 +478,26 @@ def test_errors_on_device(ops):
     # empty batch / empty point set: no-op
     out = ops.composite_fwd(torch.zeros(0, 4, 4, device="cuda"), torch.zeros(0, 4, device="cuda"), None, 0.0, "relu")
     assert out[0].shape == (0, 3)
+
+
+def test_streaming_host_batches_match_direct_calls():
+    """render_host_batches (three streams, buffers in flight) returns, in order, exactly what direct calls return."""
+    from conditioned_nerf_gan_b200.streaming import render_host_batches
+    state, siren_type, z, cam, draws, meta, _ = fixture_inputs("fwd_DOUBLESIREN_FG")
+    gen = _generator(siren_type, state, "fp32")
+    meta = dict(meta, nerf_noise=0.0)
+    d = {k: dev(v) for k, v in draws.items()}
+    batches = []
+    for k in range(5):
+        g = torch.Generator().manual_seed(k)
+        batches.append(((z[0] + 0.01 * k).pin_memory(), z[1].pin_memory(), cam.pin_memory()))
+    expect = []
+    with torch.no_grad():
+        for vol, glob, c in batches:
+            px, dp = gen((dev(vol), dev(glob)), dev(c), draws=d, **meta)
+            expect.append((px.cpu(), dp.cpu()))
+    got = [(px.clone(), dp.clone()) for px, dp in render_host_batches(gen, batches, dict(meta, draws=d))]
+    assert len(got) == len(expect)
+    for (a, b), (c, e) in zip(got, expect):
+        assert torch.equal(a, c) and torch.equal(b, e)
+    assert list(render_host_batches(gen, [], dict(meta, draws=d))) == []
