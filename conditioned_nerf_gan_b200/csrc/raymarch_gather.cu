@@ -105,27 +105,88 @@ struct RayParams {
   float* points_out;        // [B, R, S, 3] or NULL
 };
 
-// grid = (ceil(R / 32), B); block = 256 threads = 32 points x 8 lanes.
+// Voxel-corner record of one sample point, computed once (phase A) and broadcast by shuffles (phase B).
+struct CornerRec {
+  int base;                               // ((z0 * H + y0) * W + x0), in voxels
+  int flags;                              // bit0: x0+1 in range, bit1: y0+1, bit2: z0+1
+  float xl, xh, yl, yh, zl, zh;
+};
+
+__device__ __forceinline__ CornerRec corner_record(float px, float py, float pz, int D, int H, int W) {
+  CornerRec r;
+  int x0, y0, z0;
+  axis_index(px, W, x0, r.xl, r.xh);
+  axis_index(py, H, y0, r.yl, r.yh);
+  axis_index(pz, D, z0, r.zl, r.zh);
+  r.base = (z0 * H + y0) * W + x0;
+  r.flags = (x0 + 1 <= W - 1 ? 1 : 0) | (y0 + 1 <= H - 1 ? 2 : 0) | (z0 + 1 <= D - 1 ? 4 : 0);
+  return r;
+}
+
+// 8 lanes x float4 = the 32 channels of ONE point: 8 independent 16-byte loads per lane, ATen's accumulation order.
+__device__ __forceinline__ float4 gather_c4(const float4* __restrict__ vol, int H, int W, int C4, const CornerRec& r, int cg4) {
+  const bool xin = r.flags & 1, yin = r.flags & 2, zin = r.flags & 4;
+  const size_t sx = xin ? C4 : 0, sy = yin ? static_cast<size_t>(W) * C4 : 0, sz = zin ? static_cast<size_t>(H) * W * C4 : 0;
+  const float4* b = vol + static_cast<size_t>(r.base) * C4 + cg4;
+  const float4 v000 = __ldg(b), v001 = __ldg(b + sx), v010 = __ldg(b + sy), v011 = __ldg(b + sy + sx);
+  const float4 v100 = __ldg(b + sz), v101 = __ldg(b + sz + sx), v110 = __ldg(b + sz + sy), v111 = __ldg(b + sz + sy + sx);
+  const float w000 = __fmul_rn(__fmul_rn(r.xl, r.yl), r.zl);
+  const float w001 = xin ? __fmul_rn(__fmul_rn(r.xh, r.yl), r.zl) : 0.f;
+  const float w010 = yin ? __fmul_rn(__fmul_rn(r.xl, r.yh), r.zl) : 0.f;
+  const float w011 = (xin && yin) ? __fmul_rn(__fmul_rn(r.xh, r.yh), r.zl) : 0.f;
+  const float w100 = zin ? __fmul_rn(__fmul_rn(r.xl, r.yl), r.zh) : 0.f;
+  const float w101 = (xin && zin) ? __fmul_rn(__fmul_rn(r.xh, r.yl), r.zh) : 0.f;
+  const float w110 = (yin && zin) ? __fmul_rn(__fmul_rn(r.xl, r.yh), r.zh) : 0.f;
+  const float w111 = (xin && yin && zin) ? __fmul_rn(__fmul_rn(r.xh, r.yh), r.zh) : 0.f;
+  float4 o;
+#define CNG_ACC(comp)                                                          \
+  o.comp = __fmul_rn(v000.comp, w000);                                         \
+  o.comp = __fadd_rn(o.comp, __fmul_rn(v001.comp, w001));                      \
+  o.comp = __fadd_rn(o.comp, __fmul_rn(v010.comp, w010));                      \
+  o.comp = __fadd_rn(o.comp, __fmul_rn(v011.comp, w011));                      \
+  o.comp = __fadd_rn(o.comp, __fmul_rn(v100.comp, w100));                      \
+  o.comp = __fadd_rn(o.comp, __fmul_rn(v101.comp, w101));                      \
+  o.comp = __fadd_rn(o.comp, __fmul_rn(v110.comp, w110));                      \
+  o.comp = __fadd_rn(o.comp, __fmul_rn(v111.comp, w111));
+  CNG_ACC(x) CNG_ACC(y) CNG_ACC(z) CNG_ACC(w)
+#undef CNG_ACC
+  return o;
+}
+
+__device__ __forceinline__ CornerRec shfl_record(const CornerRec& r, int src) {
+  CornerRec o;
+  o.base = __shfl_sync(0xffffffffu, r.base, src);
+  o.flags = __shfl_sync(0xffffffffu, r.flags, src);
+  o.xl = __shfl_sync(0xffffffffu, r.xl, src); o.xh = __shfl_sync(0xffffffffu, r.xh, src);
+  o.yl = __shfl_sync(0xffffffffu, r.yl, src); o.yh = __shfl_sync(0xffffffffu, r.yh, src);
+  o.zl = __shfl_sync(0xffffffffu, r.zl, src); o.zh = __shfl_sync(0xffffffffu, r.zh, src);
+  return o;
+}
+
+// grid = (ceil(R / 32), B); block = 8 warps.  The block owns an 8x4 pixel patch (32 rays, lane = ray in phase A);
+// warp w marches the samples s = w, w + 8, ...  Phase A: one lane = one ray, position + voxel index arithmetic once
+// per point (it used to be repeated by the 8 lanes that share a point).  Phase B: 8 rounds, each serving 4 of the
+// warp's 32 points with 8 lanes x float4 per point; the corner record travels by warp shuffle.
 template <bool FINE>
-__global__ void __launch_bounds__(kPointsPerBlock * kLanesPerPoint) raymarch_gather_kernel(RayParams p) {
-  const int sub = threadIdx.x & (kLanesPerPoint - 1);
-  const int pt = threadIdx.x / kLanesPerPoint;
+__global__ void __launch_bounds__(256) raymarch_gather_kernel(RayParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
   int ray;
   if ((p.img_w % kTileW) == 0 && (p.img_h % kTileH) == 0) {
     const int tiles_x = p.img_w / kTileW;
     const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
-    ray = (ty * kTileH + pt / kTileW) * p.img_w + tx * kTileW + (pt % kTileW);
+    ray = (ty * kTileH + lane / kTileW) * p.img_w + tx * kTileW + (lane % kTileW);
   } else {
-    ray = blockIdx.x * kPointsPerBlock + pt;
+    ray = blockIdx.x * kPointsPerBlock + lane;
   }
-  if (ray >= p.R) return;
+  const bool live = ray < p.R;
+  const int rr = live ? ray : p.R - 1;                       // dead lanes shadow a valid ray and skip their stores
   const float* M = p.cam2world + 16 * b;
   const float m00 = __ldg(M + 0), m01 = __ldg(M + 1), m02 = __ldg(M + 2), m03 = __ldg(M + 3);
   const float m10 = __ldg(M + 4), m11 = __ldg(M + 5), m12 = __ldg(M + 6), m13 = __ldg(M + 7);
   const float m20 = __ldg(M + 8), m21 = __ldg(M + 9), m22 = __ldg(M + 10), m23 = __ldg(M + 11);
-  const float dx = __ldg(p.rays_d_cam + 3 * ray), dy = __ldg(p.rays_d_cam + 3 * ray + 1), dz = __ldg(p.rays_d_cam + 3 * ray + 2);
-  const size_t base = (static_cast<size_t>(b) * p.R + ray) * p.S;
+  const float dx = __ldg(p.rays_d_cam + 3 * rr), dy = __ldg(p.rays_d_cam + 3 * rr + 1), dz = __ldg(p.rays_d_cam + 3 * rr + 2);
+  const size_t base = (static_cast<size_t>(b) * p.R + rr) * p.S;
   const float4* vol = p.vol + static_cast<size_t>(b) * p.vol_item_stride;
   float wx = 0.f, wy = 0.f, wz = 0.f, spacing = 0.f;
   if (FINE) {
@@ -136,8 +197,9 @@ __global__ void __launch_bounds__(kPointsPerBlock * kLanesPerPoint) raymarch_gat
   } else {
     spacing = __fsub_rn(__ldg(p.t_lin + 1), __ldg(p.t_lin));    // z_vals[...,1] - z_vals[...,0]
   }
-#pragma unroll 2
-  for (int s = 0; s < p.S; ++s) {
+  const int sub = lane & 7, grp = lane >> 3;
+  for (int s = warp; s < p.S; s += 8) {
+    // ---- phase A: this lane's ray, sample s ----
     float px, py, pz;
     if (FINE) {
       const float t = __ldg(p.t_fine + base + s);
@@ -156,18 +218,29 @@ __global__ void __launch_bounds__(kPointsPerBlock * kLanesPerPoint) raymarch_gat
         cy = __fadd_rn(cy, __fmul_rn(off, dy));
         cz = __fadd_rn(cz, __fmul_rn(off, dz));
       }
-      if (sub == 0) p.t_out[base + s] = tj;
+      if (live) p.t_out[base + s] = tj;
       // cam2world @ [p, 1]
       px = fmaf(m02, cz, fmaf(m01, cy, fmaf(m00, cx, m03)));
       py = fmaf(m12, cz, fmaf(m11, cy, fmaf(m10, cx, m13)));
       pz = fmaf(m22, cz, fmaf(m21, cy, fmaf(m20, cx, m23)));
     }
-    if (p.points_out != nullptr && sub == 0) {
+    if (p.points_out != nullptr && live) {
       float* o = p.points_out + 3 * (base + s);
       o[0] = px; o[1] = py; o[2] = pz;
     }
-    for (int cg = sub; cg < p.C4; cg += kLanesPerPoint)
-      p.feat[(base + s) * p.C4 + cg] = trilinear_c4(vol, p.D, p.H, p.W, p.C4, px, py, pz, cg, nullptr);
+    const CornerRec mine = corner_record(px, py, pz, p.D, p.H, p.W);
+    const long long my_row = live ? static_cast<long long>(base + s) : -1;
+    // ---- phase B: 4 points per round, 8 lanes x float4 each ----
+#pragma unroll 2
+    for (int round = 0; round < 8; ++round) {
+      const int src = round * 4 + grp;
+      const CornerRec r = shfl_record(mine, src);
+      const long long row = __shfl_sync(0xffffffffu, my_row, src);
+      for (int cg = sub; cg < p.C4; cg += kLanesPerPoint) {
+        const float4 f = gather_c4(vol, p.H, p.W, p.C4, r, cg);
+        if (row >= 0) p.feat[row * p.C4 + cg] = f;
+      }
+    }
   }
 }
 
