@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_PKG, "libcng_b200.so")
 
 CNG_OK = 0
 CLAMP_RELU, CLAMP_SOFTPLUS = 0, 1
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
 
 # name -> (restype, argtypes); must list every symbol declared in include/cng_b200.h
 SIGNATURES = {

@@ -79,6 +79,7 @@ struct FoldParams {
 };
 
 // one thread per (item, layer, row n, 8 consecutive k)
+template <bool kHalf>
 __global__ void __launch_bounds__(256) film_fold_kernel(FoldParams p) {
   const int L = p.L;
   const long long per_item = 256LL * 4 /*layer0: 32/8*/ + static_cast<long long>(L - 1) * 256 * 32 + 16 * 32 /*head*/;
@@ -90,12 +91,12 @@ __global__ void __launch_bounds__(256) film_fold_kernel(FoldParams p) {
   if (e < 256 * 4) {                                   // ---- layer 0: split bf16
     const int n = static_cast<int>(e >> 2), k0 = static_cast<int>(e & 3) * 8;
     const float fq = __ldg(p.freq + (static_cast<size_t>(item) * L + 0) * kHID + n);
-    __nv_bfloat16 hi[8], lo[8];
+    uint16_t hi[8], lo[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float v = fq * __ldg(p.w[0] + n * kC0 + k0 + j);
-      hi[j] = __float2bfloat16_rn(v);
-      lo[j] = __float2bfloat16_rn(v - __bfloat162float(hi[j]));
+      hi[j] = to16<kHalf>(v);
+      lo[j] = to16<kHalf>(v - from16<kHalf>(hi[j]));
     }
     uint8_t* c0 = img + chunk_offset(L, 0, 0);
     uint8_t* c1 = img + chunk_offset(L, 0, 1);
@@ -115,9 +116,9 @@ __global__ void __launch_bounds__(256) film_fold_kernel(FoldParams p) {
     const int r = static_cast<int>(e % (256 * 32));
     const int n = r >> 5, k0 = (r & 31) * 8;
     const float fq = __ldg(p.freq + (static_cast<size_t>(item) * L + l) * kHID + n);
-    __nv_bfloat16 hi[8];
+    uint16_t hi[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) hi[j] = __float2bfloat16_rn(fq * __ldg(p.w[l] + n * kHID + k0 + j));
+    for (int j = 0; j < 8; ++j) hi[j] = to16<kHalf>(fq * __ldg(p.w[l] + n * kHID + k0 + j));
     uint8_t* c = img + chunk_offset(L, l, k0 >> 6);
     *reinterpret_cast<uint4*>(c + sw128_offset(n, k0 & 63)) = *reinterpret_cast<uint4*>(hi);
     if (k0 == 0) {
@@ -129,15 +130,15 @@ __global__ void __launch_bounds__(256) film_fold_kernel(FoldParams p) {
   e -= static_cast<long long>(L - 1) * 256 * 32;
   {                                                    // ---- head: [16 n][256 k], rows >= 4 zero
     const int n = static_cast<int>(e >> 5), k0 = static_cast<int>(e & 31) * 8;
-    __nv_bfloat16 hi[8];
+    uint16_t hi[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) hi[j] = __float2bfloat16_rn(n < 4 ? __ldg(p.final_w + n * kHID + k0 + j) : 0.f);
+    for (int j = 0; j < 8; ++j) hi[j] = to16<kHalf>(n < 4 ? __ldg(p.final_w + n * kHID + k0 + j) : 0.f);
     uint8_t* c = img + chunk_offset(L, L, 0) + (k0 >> 6) * 2048;
     *reinterpret_cast<uint4*>(c + sw128_offset(n, k0 & 63)) = *reinterpret_cast<uint4*>(hi);
   }
 }
 
-template <int kPolyOneIn>
+template <int kPolyOneIn, bool kHalf>
 __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t s_base = smem_u32(smem);
@@ -205,8 +206,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
       const bool elected = elect_one();
       int slot = 0;
       uint32_t phase = 0, act_phase = 0;           // act_phase: bit x = parity of act_ready(x)
-      constexpr uint32_t idesc_main = make_idesc(128, 256);
-      constexpr uint32_t idesc_head = make_idesc(128, 16);
+      constexpr uint32_t idesc_main = make_idesc(128, 256, kHalf);
+      constexpr uint32_t idesc_head = make_idesc(128, 16, kHalf);
       int iter = 0;
       for (long long t0 = first; t0 < p.total_tiles; t0 += 2 * G, ++iter) {
         const int nx = (t0 + G < p.total_tiles) ? 2 : 1;
@@ -286,12 +287,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
           const int c4 = lane & 7;                               // float4 index within the row: k = 4*c4
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
           if (r < ti.rows) v = __ldg(f + r * 8 + c4);
-          const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
-                              h3 = __float2bfloat16_rn(v.w);
           uint2 hi, lo;
-          hi.x = pack_bf16(v.x, v.y); hi.y = pack_bf16(v.z, v.w);
-          lo.x = pack_bf16(v.x - __bfloat162float(h0), v.y - __bfloat162float(h1));
-          lo.y = pack_bf16(v.z - __bfloat162float(h2), v.w - __bfloat162float(h3));
+          hi.x = pack2<kHalf>(v.x, v.y); hi.y = pack2<kHalf>(v.z, v.w);
+          lo.x = pack2<kHalf>(v.x - from16<kHalf>(to16<kHalf>(v.x)), v.y - from16<kHalf>(to16<kHalf>(v.y)));
+          lo.y = pack2<kHalf>(v.z - from16<kHalf>(to16<kHalf>(v.z)), v.w - from16<kHalf>(to16<kHalf>(v.w)));
           *reinterpret_cast<uint2*>(smem + a_base + sw128_offset(r, 4 * c4)) = hi;
           *reinterpret_cast<uint2*>(smem + a_base + sw128_offset(r, 32 + 4 * c4)) = lo;
         }
@@ -312,7 +311,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
           uint32_t o[16];
 #pragma unroll
           for (int j = 0; j < 32; j += 2)
-            o[j / 2] = pack_bf16(film_sin<kPolyOneIn>(__uint_as_float(v[j]), j), film_sin<kPolyOneIn>(__uint_as_float(v[j + 1]), j + 1));
+            o[j / 2] = pack2<kHalf>(film_sin<kPolyOneIn>(__uint_as_float(v[j]), j), film_sin<kPolyOneIn>(__uint_as_float(v[j + 1]), j + 1));
           // 32 columns = 64 bytes = 4 x 16-byte chunks of K-block cc/2, logical chunk (cc&1)*4 + i
           uint8_t* blk = smem + a_base + (cc >> 1) * kABlockBytes + row * 128;
 #pragma unroll
@@ -399,8 +398,8 @@ size_t film_siren_tc_workspace(int B, int L) {
 
 int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, int L, const float* const* w,
                          const float* const* b, const float* freq, const float* phase, const float* final_w,
-                         const float* final_b_dev, int sigmoid_rgb, void* workspace, size_t workspace_bytes, float* out,
-                         cudaStream_t stream) {
+                         const float* final_b_dev, int sigmoid_rgb, int half_operands, void* workspace, size_t workspace_bytes,
+                         float* out, cudaStream_t stream) {
   CNG_REQUIRE(HID == kHID && C == kC0, CNG_ERR_UNSUPPORTED, "film_siren_fwd(bf16): needs HID=256, C=32 (got %d, %d)", HID, C);
   CNG_REQUIRE(L >= 1 && L <= 16, CNG_ERR_UNSUPPORTED, "film_siren_fwd(bf16): L=%d", L);
   CNG_REQUIRE(workspace != nullptr && workspace_bytes >= film_siren_tc_workspace(B, L), CNG_ERR_WORKSPACE,
@@ -415,10 +414,12 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
   fp.shift = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + static_cast<size_t>(B) * item_image_bytes(L));
   const long long per_item = 256LL * 4 + static_cast<long long>(L - 1) * 256 * 32 + 16 * 32;
   const long long fold_threads = per_item * B;
-  film_fold_kernel<<<static_cast<unsigned>((fold_threads + 255) / 256), 256, 0, stream>>>(fp);
+  if (half_operands) film_fold_kernel<true><<<static_cast<unsigned>((fold_threads + 255) / 256), 256, 0, stream>>>(fp);
+  else film_fold_kernel<false><<<static_cast<unsigned>((fold_threads + 255) / 256), 256, 0, stream>>>(fp);
   if (int e = check_launch("cng_film_siren_fwd(bf16): fold")) return e;
 
   TcParams p{};
+  p.half_operands = half_operands;
   p.trace = g_tc_trace;
   p.feat = feat; p.N = N; p.B = B; p.L = L; p.images = fp.images; p.shift = fp.shift;
   CNG_REQUIRE((reinterpret_cast<uintptr_t>(final_b_dev) & 15) == 0, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd(bf16): final_b not 16-byte aligned");
@@ -433,7 +434,7 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
     const int v = e ? atoi(e) : kDefaultCtaGroup;
     return (v == 1 || v == 2) ? v : kDefaultCtaGroup;
   }();
-  if (cta_group == 2 && sm_count() >= 2) return film_siren_tc2_launch(p, stream);
+  if (cta_group == 2 && sm_count() >= 2 && !half_operands) return film_siren_tc2_launch(p, stream);
   // share of the sines evaluated on the FMA pipe instead of the MUFU unit (tuning knob, default from measurement)
   static const int poly = [] {
     const char* e = getenv("CNG_TC_POLY");
@@ -441,13 +442,14 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
     return (v == 0 || v == 2 || v == 3 || v == 4 || v == 8) ? v : kDefaultPolyOneIn;
   }();
   using KernelFn = void (*)(TcParams);
-  const KernelFn fn = poly == 0 ? film_siren_tc_kernel<0> : poly == 2 ? film_siren_tc_kernel<2> : poly == 3 ? film_siren_tc_kernel<3>
-                      : poly == 4 ? film_siren_tc_kernel<4> : film_siren_tc_kernel<8>;
-  static bool attr_set[9] = {};
-  if (!attr_set[poly]) {
+  const KernelFn fn = half_operands ? film_siren_tc_kernel<0, true>
+                      : poly == 0 ? film_siren_tc_kernel<0, false> : poly == 2 ? film_siren_tc_kernel<2, false>
+                      : poly == 3 ? film_siren_tc_kernel<3, false> : poly == 4 ? film_siren_tc_kernel<4, false> : film_siren_tc_kernel<8, false>;
+  static bool attr_set[2][9] = {};
+  if (!attr_set[half_operands ? 1 : 0][poly]) {
     ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTotal));
     if (ce != cudaSuccess) return fail(static_cast<int>(ce), "film_siren_fwd(bf16): smem attribute: %s", cudaGetErrorString(ce));
-    attr_set[poly] = true;
+    attr_set[half_operands ? 1 : 0][poly] = true;
   }
   const long long grid = min(static_cast<long long>(sm_count()), p.total_tiles);
   fn<<<static_cast<unsigned>(grid), kNumThreads, kSmemTotal, stream>>>(p);
@@ -469,7 +471,7 @@ CNG_API void cng_internal_set_tc_trace(void* dev_buffer) { cng::g_tc_trace = sta
 
 size_t cng_film_siren_workspace_bytes(int B, int C, int HID, int L, int precision) {
   (void)C; (void)HID;
-  if (precision != CNG_PREC_BF16 || B <= 0 || L <= 0) return 0;
+  if ((precision != CNG_PREC_BF16 && precision != CNG_PREC_FP16) || B <= 0 || L <= 0) return 0;
   return cng::film_siren_tc_workspace(B, L);
 }
 
@@ -488,9 +490,10 @@ int cng_film_siren_fwd(const float* feat, int B, long long N, int C, int HID, in
   if (precision == CNG_PREC_FP32)
     return cng::film_siren_simt_launch(feat, B, N, C, HID, L, layer_w_host, layer_b_host, freq, phase, final_w, final_b,
                                        sigmoid_rgb, rgb_sigma, cng::as_stream(stream));
-  if (precision == CNG_PREC_BF16)
+  if (precision == CNG_PREC_BF16 || precision == CNG_PREC_FP16)
     return cng::film_siren_tc_launch(feat, B, N, C, HID, L, layer_w_host, layer_b_host, freq, phase, final_w, final_b,
-                                     sigmoid_rgb, workspace, workspace_bytes, rgb_sigma, cng::as_stream(stream));
+                                     sigmoid_rgb, precision == CNG_PREC_FP16 ? 1 : 0, workspace, workspace_bytes, rgb_sigma,
+                                     cng::as_stream(stream));
   return cng::fail(CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd: unknown precision %d", precision);
 }
 

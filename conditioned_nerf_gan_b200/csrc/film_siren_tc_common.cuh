@@ -3,6 +3,7 @@
 // kernel, PTX wrappers (mbarrier, bulk copy, tcgen05 fences / ld / st / commit), descriptors.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "cng_common.cuh"
 
@@ -108,8 +109,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   return d;
 }
 // cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), K-major both, N>>3 at 17, M>>4 at 24
-__device__ __forceinline__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+__device__ __forceinline__ constexpr uint32_t make_idesc(int M, int N, bool half_operands = false) {
+  // a_format / b_format: 0 = F16, 1 = BF16 (kind::f16 serves both at the same rate)
+  const uint32_t fmt = half_operands ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 #define CNG_TMEM_LD_32(taddr, v)                                                                                      \
@@ -191,6 +194,23 @@ __device__ __forceinline__ float film_sin(float x, int j) {
   return __sinf(x);
 }
 
+// 16-bit operand format of the tensor-core path: bf16 (8-bit significand) or fp16 (11-bit; what the reference's
+// own autocast uses -- same tcgen05 rate, 8x smaller operand rounding, values here are all well inside its range)
+template <bool kHalf>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  uint32_t r;
+  if (kHalf) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));     // first source -> upper half
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <bool kHalf>
+__device__ __forceinline__ uint16_t to16(float v) {
+  return kHalf ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+template <bool kHalf>
+__device__ __forceinline__ float from16(uint16_t h) {
+  return kHalf ? __half2float(__ushort_as_half(h)) : __bfloat162float(__ushort_as_bfloat16(h));
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // first source -> upper half
@@ -208,6 +228,7 @@ struct TcParams {
   float* out;               // [B, N, 4]
   long long tiles_per_item;
   long long total_tiles;
+  int half_operands;        // 1: fp16 operands, 0: bf16
   long long* trace;         // debug: clock64 timeline of CTA 0 (tools/trace_tc.py), NULL in production
 };
 // trace layout: [iter < 4][layer <= 8][slot < 2][event < 8]; events: 0 MMA thread saw act_ready, 1 MMAs issued,

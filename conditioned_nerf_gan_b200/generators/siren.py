@@ -27,9 +27,10 @@ __all__ = ["FiLMLayer", "TALLSIREN_FG", "SHORTSIREN_FG", "DOUBLESIREN_FG", "Sing
            "TALLSIREN_dg", "SHORTSIREN_dg", "DoubleSIREN_dg", "DOUBLESIREN_dg", "default_precision"]
 
 
-def default_precision() -> str:
-    """'bf16' (tcgen05 tensor-core path) unless CNG_PRECISION=fp32 selects the exact FFMA path."""
-    return os.environ.get("CNG_PRECISION", "bf16")
+def default_precision(class_default: str = "bf16") -> str:
+    """Arithmetic of the fused MLP: 'bf16' / 'fp16' (tcgen05 tensor-core path, 16-bit operands, fp32 accumulate)
+    or 'fp32' (exact FFMA path).  CNG_PRECISION overrides the class default."""
+    return os.environ.get("CNG_PRECISION", class_default)
 
 
 class FiLMLayer(nn.Module):
@@ -55,6 +56,7 @@ class _FiLMSirenFG(nn.Module):
     num_layers = 0          # FiLM layers
     freq_div = 25.0         # frequency_init(freq_div), siren.py:134-143
     sigmoid_rgb = True      # _sigmoid_rgb on the head (siren.py:579) or raw rgb (:1064)
+    tensor_core_operands = "bf16"   # 16-bit operand format of the tcgen05 path that keeps this variant <= 1e-2 max-abs
 
     def __init__(self, input_dim=3, z_dim=100, hidden_dim=256, output_dim=4, drop_out=0, device=None):
         super().__init__()
@@ -69,7 +71,7 @@ class _FiLMSirenFG(nn.Module):
             # first_layer_film_sine_init (siren.py:40-44) overrides frequency_init on layer 0
             _uniform_(film.layer, 1.0 / fan_in if i == 0 else math.sqrt(6.0 / fan_in) / self.freq_div)
         _uniform_(self.final_layer, math.sqrt(6.0 / hidden_dim) / self.freq_div)
-        self.precision = default_precision()
+        self.precision = default_precision(self.tensor_core_operands)
 
     # -- pieces shared with ImplicitGenerator3d ------------------------------------------------
     def film_parameters(self, global_feature: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -115,6 +117,9 @@ class TALLSIREN_FG(_FiLMSirenFG):
 
 class SHORTSIREN_FG(_FiLMSirenFG):
     num_layers, freq_div, sigmoid_rgb = 4, 12.0, True
+    # frequency_init(12) doubles the pre-activations: bf16 operands give 1.4e-2 max-abs on random-init weights, fp16
+    # operands (same tensor-core rate, the reference's own autocast dtype) 2e-3
+    tensor_core_operands = "fp16"
 
 
 class DOUBLESIREN_FG(_FiLMSirenFG):

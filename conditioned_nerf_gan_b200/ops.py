@@ -15,7 +15,7 @@ import torch
 from . import _lib
 
 CLAMP_MODES = {"relu": _lib.CLAMP_RELU, "softplus": _lib.CLAMP_SOFTPLUS}
-PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16}
 
 # number of kernel launches issued through this module (bench.py reports it as gpu_launches)
 launch_count = 0
@@ -183,7 +183,7 @@ def film_siren_fwd(feat, layer_w: Sequence[torch.Tensor], layer_b: Sequence[torc
     with torch.cuda.device(dev), _timed("cng_film_siren_fwd"):
         _lib.call("cng_film_siren_fwd", _ptr(feat), B, N, C, HID, L, w_arr, b_arr, _ptr(freq), _ptr(phase), _ptr(final_w),
                   _ptr(final_b), int(bool(sigmoid_rgb)), code, _ptr(workspace), ws_bytes, _ptr(out), _stream(feat))
-    _count(2 if code == _lib.PREC_BF16 else 1)
+    _count(1 if code == _lib.PREC_FP32 else 2)
     return out
 
 

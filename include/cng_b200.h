@@ -57,7 +57,9 @@ enum { CNG_CLAMP_RELU = 0, CNG_CLAMP_SOFTPLUS = 1 };
 /* arithmetic of the FiLM-SIREN contractions */
 enum {
   CNG_PREC_FP32 = 0,   /* fp32 FFMA tiles (exact-mode; reference inference is pure fp32)       */
-  CNG_PREC_BF16 = 1    /* tcgen05 bf16 x bf16 -> fp32 TMEM accumulators; layer 0 split-bf16    */
+  CNG_PREC_BF16 = 1,   /* tcgen05 bf16 x bf16 -> fp32 TMEM accumulators; layer 0 split-bf16    */
+  CNG_PREC_FP16 = 2    /* same kernel and rate with fp16 operands (the reference's autocast
+                          dtype): 11-bit instead of 8-bit significands, ~8x smaller error     */
 };
 
 CNG_API int cng_abi_version(void);
@@ -126,7 +128,8 @@ CNG_API int cng_gather_points(const float* vol_ndhwc, int B, int C, int D, int H
  *   nn.Linear weight [HID, K_l] (K_0 = C, else HID) and bias [HID];
  *   freq, phase [B, L*HID] (freq already `*15+30`, siren.py:550-553);
  *   final_w [4, HID], final_b [4]; rgb_sigma [B, N, 4] out.
- * CNG_PREC_BF16 needs HID == 256, C == 32 and a workspace of cng_film_siren_workspace_bytes().
+ * CNG_PREC_BF16 / CNG_PREC_FP16 need HID == 256, C == 32 and a workspace of
+ * cng_film_siren_workspace_bytes().
  * ---------------------------------------------------------------------------------------- */
 CNG_API size_t cng_film_siren_workspace_bytes(int B, int C, int HID, int L, int precision);
 CNG_API int cng_film_siren_fwd(const float* feat, int B, long long N, int C, int HID, int L,

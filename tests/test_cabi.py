@@ -81,3 +81,4 @@ def test_workspace_query(lib):
     assert lib.cng_film_siren_workspace_bytes(2, 32, 256, 8, _lib.PREC_FP32) == 0
     per_item = (2 + 4 * 7) * 32768 + 8192
     assert lib.cng_film_siren_workspace_bytes(2, 32, 256, 8, _lib.PREC_BF16) == 2 * per_item + 2 * 8 * 256 * 4
+    assert lib.cng_film_siren_workspace_bytes(2, 32, 256, 8, _lib.PREC_FP16) == 2 * per_item + 2 * 8 * 256 * 4

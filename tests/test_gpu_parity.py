@@ -154,16 +154,20 @@ def test_film_siren_fp32_vs_oracle(ops, siren_type, B, N):
     assert err < 5e-4, err       # fp32 accumulation-order differences amplified by freq ~ 30 per layer
 
 
-@pytest.mark.parametrize("siren_type,tol", [("TALLSIREN_FG", 1e-2), ("SHORTSIREN_FG", 3e-2), ("DOUBLESIREN_FG", 1e-2), ("SingleSIREN_dg", 1e-2)])
+@pytest.mark.parametrize("siren_type", ["TALLSIREN_FG", "SHORTSIREN_FG", "DOUBLESIREN_FG", "SingleSIREN_dg"])
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
 @pytest.mark.parametrize("B,N", [(2, 4096), (1, 100), (3, 129), (1, 128 * 300 + 5)])
-def test_film_siren_bf16_vs_oracle(ops, siren_type, tol, B, N):
-    """tcgen05 path.  Features ~ N(0, 0.3^2) (std of a random-init UNet3D output)."""
+def test_film_siren_tensor_core_vs_oracle(ops, siren_type, precision, B, N):
+    """tcgen05 path, bf16 or fp16 operands.  Features ~ N(0, 0.3^2) (std of a random-init UNet3D output).
+    Bar: 1e-2 max-abs.  bf16 operands miss it on SHORTSIREN_FG (frequency_init(12) doubles the pre-activations; measured
+    1.4e-2, which is why that class defaults to fp16 operands); fp16 operands meet it everywhere."""
     spec, ws, bs, feat, freq, phase, fw, fb, ref = _mlp_setup(siren_type, B, N, 0.3)
-    out = _run_mlp(ops, "bf16", spec, ws, bs, feat, freq, phase, fw, fb)
+    out = _run_mlp(ops, precision, spec, ws, bs, feat, freq, phase, fw, fb)
     assert torch.isfinite(out).all()
     err = (out - ref).abs().max().item()
     rms = (out - ref).pow(2).mean().sqrt().item()
-    print(f"{siren_type} bf16 B={B} N={N}: max-abs err {err:.3e}, rms {rms:.3e}")
+    print(f"{siren_type} {precision} B={B} N={N}: max-abs err {err:.3e}, rms {rms:.3e}")
+    tol = 3e-2 if (precision == "bf16" and siren_type == "SHORTSIREN_FG") else 1e-2
     assert err < tol, err
 
 
@@ -354,7 +358,7 @@ def _generator(siren_type, state, precision):
 
 
 @pytest.mark.parametrize("name", FORWARD_FIXTURES)
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
 def test_forward_vs_reference_golden(name, precision):
     state, siren_type, z, cam, draws, meta, taps = fixture_inputs(name)
     gen = _generator(siren_type, state, precision)
@@ -369,7 +373,7 @@ def test_forward_vs_reference_golden(name, precision):
     B, img, S = cam.shape[0], meta["img_size"], meta["num_steps"]
     assert pixels.shape == (B, 3, img, img) and depth.shape == (B, img, img) and pixels.is_contiguous()
     assert torch.allclose(out["points_coarse"].cpu(), taps["points_coarse"].reshape(B, -1, S, 3), rtol=0, atol=5e-7)
-    mlp_tol = 5e-4 if precision == "fp32" else (3e-2 if "SHORT" in name else 1e-2)
+    mlp_tol = 5e-4 if precision == "fp32" else (3e-2 if ("SHORT" in name and precision == "bf16") else 1e-2)
     err_c = (out["rgb_sigma_coarse"].cpu() - taps["rgb_sigma_coarse"].reshape(B, -1, S, 4)).abs().max().item()
     err_p = (pixels.cpu() - taps["pixels"]).abs().max().item()
     psnr_full = oracle.psnr(pixels.cpu(), taps["pixels"])

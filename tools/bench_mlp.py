@@ -9,6 +9,7 @@ from oracle import nerf_path as oracle
 
 siren = sys.argv[1] if len(sys.argv) > 1 else "TALLSIREN_FG"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+prec = sys.argv[3] if len(sys.argv) > 3 else "bf16"
 B, N = 8, 128 * 128 * 24
 spec = oracle.SIREN_SPECS[siren]
 L = spec["layers"]
@@ -23,20 +24,20 @@ freq, phase = freq.to(dev), phase.to(dev)
 feat = (torch.randn((B, N, 32), generator=g) * 0.3).to(dev)
 fw, fb = st["siren.final_layer.weight"].to(dev), st["siren.final_layer.bias"].to(dev)
 run = lambda prec: ops.film_siren_fwd(feat, ws, bs, freq, phase, fw, fb, spec["sigmoid_rgb"], prec)
-out = run("bf16")
+out = run(prec)
 ref = run("fp32")
 torch.cuda.synchronize()
 err = (out - ref).abs().max().item()
 for _ in range(3):
-    run("bf16")
+    run(prec)
 torch.cuda.synchronize()
 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 s.record()
 for _ in range(reps):
-    run("bf16")
+    run(prec)
 e.record()
 torch.cuda.synchronize()
 ms = s.elapsed_time(e) / reps
 flops = 2 * (32 * 256 + (L - 1) * 256 * 256 + 256 * 4) * B * N
-print(f"{siren} poly={os.environ.get('CNG_TC_POLY', 'default')}: {ms:.3f} ms/launch, {flops / ms / 1e9:.1f} TFLOP/s algorithmic, "
+print(f"{siren} {prec} poly={os.environ.get('CNG_TC_POLY', 'default')}: {ms:.3f} ms/launch, {flops / ms / 1e9:.1f} TFLOP/s algorithmic, "
       f"max-abs vs fp32 kernel {err:.3e}")
