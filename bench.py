@@ -299,10 +299,15 @@ def run_gpu(args):
     pk = peaks()
     flops_per_launch = mlp_flops_per_point(L) * B * R * S            # one pass (coarse or fine) per launch
     achieved = flops_per_launch / (mlp_ms * 1e-3) / 1e12
-    peak = pk["tflops_sustained"] if args.precision == "bf16" else None
-    roofline = {"kernel": "film_siren_tc_kernel (cng_film_siren_fwd)" if args.precision == "bf16" else "film_siren_simt_kernel",
+    peak = pk["tflops_sustained"] if args.precision != "fp32" else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "k2_dram_traffic.json")
+    if args.precision != "fp32" and os.path.exists(tpath):
+        traffic = json.load(open(tpath))["dram_bytes_per_launch"]      # from the committed ncu --set full capture
+    roofline = {"kernel": "film_siren_tc_kernel (cng_film_siren_fwd)" if args.precision != "fp32" else "film_siren_simt_kernel",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": (achieved / peak) if peak else None, "traffic": None,
+                "frac": (achieved / peak) if peak else None, "traffic": traffic,
+                "algorithmic_bytes_per_launch": B * R * S * (WORKLOAD["channels"] * 4 + 16) + B * ((2 + 4 * (L - 1)) * 32768 + 8192),
                 "peak_source": f"{pk['source']} bf16 sustained (kernel timed inside a long step)",
                 "flops_per_launch": flops_per_launch, "ms_per_launch": mlp_ms,
                 "share_of_step": float(np.sum(per_kernel["cng_film_siren_fwd"]) / args.steps / sum(step_kernel_ms.values())),
@@ -323,7 +328,7 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": rays / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": workload_config(args, "gpu"),
             "e2e": {"value": rays / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "api": "streaming.render_host_batches (H2D / kernels / D2H on three streams, double-buffered)",
@@ -491,7 +496,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--siren", default="TALLSIREN_FG", choices=sorted(SIREN_LAYERS))
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="render", choices=["render", "train", "video"])
     args = ap.parse_args()

@@ -261,29 +261,51 @@ __global__ void __launch_bounds__(256) film_sin_apply_kernel(const float* __rest
 }
 
 // du = dy * cos(u), u = freq*(z+b)+phase;  dz = du*freq (bf16 out);  dfreq += sum_p du*(z+b);  dphase += sum_p du
-// block = 256 threads = one column each (HID == 256), walks kRows rows; grid = ceil(P / kRows)
+// block = 256 threads = 64 column groups (4 columns each, HID == 256) x 4 row lanes; walks kGradRows rows with
+// 8-byte (dy, dz) and 16-byte (z) accesses; the column sums go through shared memory and one atomicAdd per column.
 constexpr int kGradRows = 128;
 __global__ void __launch_bounds__(256) film_sin_grad_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ z,
                                                              const float* __restrict__ bias, const float* __restrict__ freq,
                                                              const float* __restrict__ phase, long long P,
                                                              __nv_bfloat16* __restrict__ dz, float* __restrict__ dfreq,
                                                              float* __restrict__ dphase) {
-  const int c = threadIdx.x;
-  const float b = __ldg(bias + c), f = __ldg(freq + c), ph = __ldg(phase + c);
+  __shared__ float red[2][4][256];
+  const int cgp = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int c = cgp * 4;
+  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c));
+  const float4 f4 = __ldg(reinterpret_cast<const float4*>(freq + c));
+  const float4 p4 = __ldg(reinterpret_cast<const float4*>(phase + c));
   const long long r0 = static_cast<long long>(blockIdx.x) * kGradRows;
   const long long r1 = min(P, r0 + kGradRows);
-  float af = 0.f, ap = 0.f;
+  float af[4] = {0.f, 0.f, 0.f, 0.f}, ap[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
-  for (long long r = r0; r < r1; ++r) {
-    const float zb = __ldg(z + r * 256 + c) + b;
-    const float g = __bfloat162float(dy[r * 256 + c]);
-    const float du = g * cosf(fmaf(f, zb, ph));
-    af = fmaf(du, zb, af);
-    ap += du;
-    dz[r * 256 + c] = __float2bfloat16_rn(du * f);
+  for (long long r = r0 + ty; r < r1; r += 4) {
+    const float4 zv = __ldg(reinterpret_cast<const float4*>(z + r * 256 + c));
+    const uint2 g2 = __ldg(reinterpret_cast<const uint2*>(dy + r * 256 + c));
+    const __nv_bfloat162 g01 = *reinterpret_cast<const __nv_bfloat162*>(&g2.x), g23 = *reinterpret_cast<const __nv_bfloat162*>(&g2.y);
+    const float g[4] = {__low2float(g01), __high2float(g01), __low2float(g23), __high2float(g23)};
+    const float zb[4] = {zv.x + b4.x, zv.y + b4.y, zv.z + b4.z, zv.w + b4.w};
+    const float fr[4] = {f4.x, f4.y, f4.z, f4.w}, ph[4] = {p4.x, p4.y, p4.z, p4.w};
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float du = g[k] * cosf(fmaf(fr[k], zb[k], ph[k]));
+      af[k] = fmaf(du, zb[k], af[k]);
+      ap[k] += du;
+      o[k] = du * fr[k];
+    }
+    __nv_bfloat162 o01 = __floats2bfloat162_rn(o[0], o[1]), o23 = __floats2bfloat162_rn(o[2], o[3]);
+    uint2 w2;
+    w2.x = *reinterpret_cast<uint32_t*>(&o01);
+    w2.y = *reinterpret_cast<uint32_t*>(&o23);
+    *reinterpret_cast<uint2*>(dz + r * 256 + c) = w2;
   }
-  atomicAdd(dfreq + c, af);
-  atomicAdd(dphase + c, ap);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { red[0][ty][c + k] = af[k]; red[1][ty][c + k] = ap[k]; }
+  __syncthreads();
+  const int col = threadIdx.x;
+  atomicAdd(dfreq + col, red[0][0][col] + red[0][1][col] + red[0][2][col] + red[0][3][col]);
+  atomicAdd(dphase + col, red[1][0][col] + red[1][1][col] + red[1][2][col] + red[1][3][col]);
 }
 
 }  // namespace cng

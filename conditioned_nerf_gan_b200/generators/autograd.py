@@ -31,11 +31,16 @@ CHUNK_ROWS = 1 << 19          # points per recompute chunk of the MLP backward (
 class _ToChannelsLast(torch.autograd.Function):
     @staticmethod
     def forward(ctx, volume):
-        return ops.volume_to_channels_last(volume)
+        out = ops.volume_to_channels_last(volume)
+        ctx.was_view = out.data_ptr() == volume.data_ptr()       # channels_last_3d input: no copy was made
+        return out.contiguous() if ctx.was_view else out
 
     @staticmethod
     def backward(ctx, d_cl):
-        return ops.volume_from_channels_last(d_cl.contiguous())
+        d_cl = d_cl.contiguous()
+        if ctx.was_view:                                          # gradient in the encoder's own (channels-last) format
+            return d_cl.permute(0, 4, 1, 2, 3)
+        return ops.volume_from_channels_last(d_cl)
 
 
 def _scatter(vol_shape, points, d_feat):
@@ -117,6 +122,8 @@ class _FilmSiren(torch.autograd.Function):
         d_bs = [torch.zeros_like(b) for b in bs]
         d_fw = torch.zeros_like(fw)
         d_fb = torch.zeros((4,), dtype=torch.float32, device=dev)
+        fw_bf = fw.to(torch.bfloat16)
+        tf32_was = torch.backends.cuda.matmul.allow_tf32
         for b in range(B):
             fr, ph = freq[b].detach().float(), phase[b].detach().float()
             dph_before = d_phase[b].clone()
@@ -125,10 +132,13 @@ class _FilmSiren(torch.autograd.Function):
                 x0 = feat[b, r0:r1].detach()
                 # ---- recompute: z_l = x_l W_l^T (fp32 out), x_{l+1} = bf16(sin(freq (z_l + b_l) + phase))
                 zs: List[torch.Tensor] = []
-                xs: List[torch.Tensor] = [x0]
+                xs: List[torch.Tensor] = [x0.to(torch.bfloat16)]
                 for l in range(L):
                     if l == 0:
-                        z = x0 @ ws[0].t()                                   # K = 32: fp32, like the split-bf16 layer 0 of K2
+                        # K = 32: TF32 tensor cores (11-bit operands, fp32 accumulate) instead of an fp32 SIMT sgemm
+                        torch.backends.cuda.matmul.allow_tf32 = True
+                        z = x0 @ ws[0].t()
+                        torch.backends.cuda.matmul.allow_tf32 = tf32_was
                     else:
                         z = torch.mm(xs[l], ws_bf[l].t(), out_dtype=torch.float32)
                     zs.append(z)
@@ -141,18 +151,16 @@ class _FilmSiren(torch.autograd.Function):
                 d_o_bf = d_o.to(torch.bfloat16)
                 d_fw += torch.mm(d_o_bf.t(), xs[L], out_dtype=torch.float32)
                 d_fb += d_o.sum(0)
-                dy = (d_o @ fw).to(torch.bfloat16)
+                dy = torch.mm(d_o_bf, fw_bf)                                   # [P,4] x [4,HID] -> bf16 [P,HID]
                 # ---- layers, last to first
                 for l in reversed(range(L)):
                     sl = slice(l * H, (l + 1) * H)
                     dz = ops.film_sin_grad(dy, zs[l], bs[l], fr[sl], ph[sl], d_freq[b, sl], d_phase[b, sl])
                     zs[l] = None
+                    d_ws[l] += torch.mm(dz.t(), xs[l], out_dtype=torch.float32)
                     if l == 0:
-                        dzf = dz.float()
-                        d_ws[0] += dzf.t() @ x0
-                        d_feat[b, r0:r1] = dzf @ ws[0]
+                        d_feat[b, r0:r1] = torch.mm(dz, ws_bf[0], out_dtype=torch.float32)
                     else:
-                        d_ws[l] += torch.mm(dz.t(), xs[l], out_dtype=torch.float32)
                         dy = torch.mm(dz, ws_bf[l])
                     xs[l + 1] = None
             # d b_l = sum_p dz = freq * sum_p du  (this item's share of d_phase)

@@ -79,7 +79,14 @@ def clamp_code(clamp_mode) -> int:
 
 
 def volume_to_channels_last(vol: torch.Tensor) -> torch.Tensor:
-    """[B,C,D,H,W] -> [B,D,H,W,C] (cng_volume_to_channels_last)."""
+    """[B,C,D,H,W] -> [B,D,H,W,C] (cng_volume_to_channels_last).
+
+    A volume the encoder already emits in ``torch.channels_last_3d`` memory format IS the kernel's layout: its
+    storage is returned as a view and no kernel runs (the encoder emitting the volume in the
+    gather kernel's layout)."""
+    if (isinstance(vol, torch.Tensor) and vol.is_cuda and vol.dtype == torch.float32 and vol.dim() == 5
+            and not vol.is_contiguous() and vol.is_contiguous(memory_format=torch.channels_last_3d)):
+        return vol.permute(0, 2, 3, 4, 1)
     vol = _f32(vol, "volume")
     B, C, D, H, W = vol.shape
     out = torch.empty((B, D, H, W, C), dtype=torch.float32, device=vol.device)

@@ -174,3 +174,20 @@ def test_siren_boundary_backward_and_amp():
     assert vol.grad is not None and torch.isfinite(vol.grad).all() and float(vol.grad.abs().max()) > 0
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in gen.parameters())
     torch.nn.utils.clip_grad_norm_(gen.parameters(), 1.0)
+
+
+def test_backward_with_channels_last_3d_volume():
+    from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d
+    state, siren_type, z, cam, draws, meta, _ = fixture_inputs("fwd_DOUBLESIREN_FG")
+    gen = ImplicitGenerator3d(siren_type, 256, 32, 4, 256)
+    gen.load_state_dict(state, strict=True)
+    gen = gen.to("cuda")
+    gen.siren.precision = "fp32"
+    d = {k: dev(v) for k, v in draws.items()}
+    grads = []
+    for fmt in (torch.contiguous_format, torch.channels_last_3d):
+        vol = dev(z[0]).contiguous(memory_format=fmt).requires_grad_(True)
+        pixels, depth = gen((vol, dev(z[1])), dev(cam), draws=d, **meta)
+        (pixels.sum() + depth.sum()).backward()
+        grads.append(vol.grad.contiguous())
+    assert torch.allclose(grads[0], grads[1], rtol=1e-5, atol=1e-6)

@@ -505,3 +505,23 @@ def test_streaming_host_batches_match_direct_calls():
     for (a, b), (c, e) in zip(got, expect):
         assert torch.equal(a, c) and torch.equal(b, e)
     assert list(render_host_batches(gen, [], dict(meta, draws=d))) == []
+
+
+def test_channels_last_3d_volume_needs_no_layout_kernel(ops):
+    """An encoder output in torch.channels_last_3d memory format is consumed in place (no layout kernel, same image)."""
+    state, siren_type, z, cam, draws, meta, _ = fixture_inputs("fwd_TALLSIREN_FG")
+    gen = _generator(siren_type, state, "fp32")
+    d = {k: dev(v) for k, v in draws.items()}
+    vol = dev(z[0])
+    vol_cl3d = vol.contiguous(memory_format=torch.channels_last_3d)
+    assert not vol_cl3d.is_contiguous()
+    n0 = ops.launch_count
+    with torch.no_grad():
+        a, da = gen((vol, dev(z[1])), dev(cam), draws=d, **meta)
+    n1 = ops.launch_count
+    with torch.no_grad():
+        b, db = gen((vol_cl3d, dev(z[1])), dev(cam), draws=d, **meta)
+    n2 = ops.launch_count
+    assert torch.equal(a, b) and torch.equal(da, db)
+    assert (n2 - n1) == (n1 - n0) - 1
+    assert ops.volume_to_channels_last(vol_cl3d).data_ptr() == vol_cl3d.data_ptr()
