@@ -46,6 +46,9 @@
 #ifndef CNG_TC_EPI_WARPS
 #define CNG_TC_EPI_WARPS 8
 #endif
+#ifndef CNG_TC_EPI_PIPELINE
+#define CNG_TC_EPI_PIPELINE 0
+#endif
 
 namespace cng {
 
@@ -320,8 +323,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
             *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
           }
         };
-        if constexpr (kEpiWarpsPerSlot == 4) {
-          // 320-thread CTA: enough registers to keep the TMEM load of block i+1 in flight under the sines of block i
+        if constexpr (kEpiWarpsPerSlot == 4 || CNG_TC_EPI_PIPELINE) {
+          // keep the TMEM load of block i+1 in flight under the sines of block i (needs 2 x 32 accumulator registers)
           uint32_t va[32], vb[32];
           CNG_TMEM_LD_32(t_lane + (kB * half) * 32, va);
 #pragma unroll

@@ -31,16 +31,78 @@ __device__ __forceinline__ void warp_bitonic_sort(unsigned long long* keys, int 
   }
 }
 
+// The same network with the keys in registers: key index i = slot * 32 + lane.  Exchanges at distance >= 32 are
+// register swaps inside a lane, smaller distances are warp shuffles; no shared-memory traffic and no __syncwarp.
+template <int SLOTS>
+__device__ __forceinline__ void warp_bitonic_sort_regs(unsigned long long (&key)[SLOTS], int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32 * SLOTS; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int js = j >> 5;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+          if ((s & js) == 0) {
+            const bool up = ((s * 32) & k) == 0;                 // k >= 64 here: the direction depends on the slot only
+            const unsigned long long a = key[s], b = key[s | js];
+            if ((a > b) == up) { key[s] = b; key[s | js] = a; }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+          const unsigned long long a = key[s];
+          const unsigned long long o = __shfl_xor_sync(0xffffffffu, a, j);
+          const bool up = (((s * 32 + lane) & k) == 0);
+          const bool lower = (lane & j) == 0;
+          const unsigned long long mn = a < o ? a : o, mx = a < o ? o : a;
+          key[s] = (lower == up) ? mn : mx;
+        }
+      }
+    }
+  }
+}
+
 __host__ __device__ inline int next_pow2_min32(int n) {
   int p = 32;
   while (p < n) p <<= 1;
   return p;
 }
 
+// Register-sort variant of load_and_sort_ray for n2 == 32 * SLOTS; the sorted keys are written to keys[] once.
+template <int SLOTS>
+__device__ __forceinline__ void load_and_sort_ray_regs(unsigned long long* keys, const float* __restrict__ t_fine,
+                                                       const float* __restrict__ t_coarse, long long ray, int S, int n, int lane) {
+  const bool two = t_fine != nullptr;
+  unsigned long long key[SLOTS];
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int e = s * 32 + lane;
+    key[s] = ~0ull;
+    if (e < n) {
+      const float te = two ? (e < S ? __ldg(t_fine + ray * S + e) : __ldg(t_coarse + ray * S + (e - S))) : __ldg(t_coarse + ray * S + e);
+      key[s] = (static_cast<unsigned long long>(sortable_bits(te)) << 32) | static_cast<unsigned>(e);
+    }
+  }
+  if (two) warp_bitonic_sort_regs<SLOTS>(key, lane);
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) keys[s * 32 + lane] = key[s];
+  __syncwarp();
+}
+
 // Loads the ray's distances (fine first, then coarse; or coarse only), sorts, and leaves keys[s] = (t, source index).
 __device__ __forceinline__ void load_and_sort_ray(unsigned long long* keys, const float* __restrict__ t_fine,
                                                   const float* __restrict__ t_coarse, long long ray, int S, int n, int n2, int lane) {
   const bool two = t_fine != nullptr;
+  // up to 256 keys: sort in registers (1 to 8 keys per lane)
+  switch (n2) {
+    case 32: load_and_sort_ray_regs<1>(keys, t_fine, t_coarse, ray, S, n, lane); return;
+    case 64: load_and_sort_ray_regs<2>(keys, t_fine, t_coarse, ray, S, n, lane); return;
+    case 128: load_and_sort_ray_regs<4>(keys, t_fine, t_coarse, ray, S, n, lane); return;
+    case 256: load_and_sort_ray_regs<8>(keys, t_fine, t_coarse, ray, S, n, lane); return;
+    default: break;
+  }
   for (int e = lane; e < n2; e += 32) {
     unsigned long long key = ~0ull;
     if (e < n) {

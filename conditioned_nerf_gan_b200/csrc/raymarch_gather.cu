@@ -264,21 +264,23 @@ __global__ void __launch_bounds__(256) gather_points_kernel(const float4* __rest
 
 // NCDHW -> NDHWC: block = one run of 32 voxels x all channels, staged through shared memory so
 // both the reads (32 consecutive voxels of one channel) and the writes (32 voxels x C floats,
-// contiguous) are full 128-byte lines.
-__global__ void __launch_bounds__(256) channels_last_kernel(const float* __restrict__ src, float* __restrict__ dst, int C,
+// contiguous) are full 128-byte lines.  CT = C when known at compile time (32: shifts instead of divisions).
+template <int CT>
+__global__ void __launch_bounds__(256) channels_last_kernel(const float* __restrict__ src, float* __restrict__ dst, int C_rt,
                                                              long long vox) {
   extern __shared__ float tile[];   // [C][33]
+  const int C = CT > 0 ? CT : C_rt;
   const long long v0 = static_cast<long long>(blockIdx.x) * 32;
   const int b = blockIdx.y;
   const float* s = src + static_cast<size_t>(b) * C * vox;
   float* d = dst + static_cast<size_t>(b) * C * vox;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int c = w; c < C; c += 8) {
-    const long long v = v0 + lane;
-    tile[c * 33 + lane] = v < vox ? __ldg(s + static_cast<size_t>(c) * vox + v) : 0.f;
-  }
+  const long long v = v0 + lane;
+#pragma unroll 4
+  for (int c = w; c < C; c += 8) tile[c * 33 + lane] = v < vox ? __ldg(s + static_cast<size_t>(c) * vox + v) : 0.f;
   __syncthreads();
   const int nv = static_cast<int>(min(32LL, vox - v0));
+#pragma unroll 4
   for (int e = threadIdx.x; e < nv * C; e += 256) {
     const int vv = e / C, c = e - vv * C;
     d[(v0 + vv) * C + c] = tile[c * 33 + vv];
@@ -306,8 +308,9 @@ int cng_volume_to_channels_last(const float* vol_ncdhw, float* vol_ndhwc, int B,
   if (int e = cng_device_check()) return e;
   const long long vox = static_cast<long long>(D) * H * W;
   dim3 grid(static_cast<unsigned>((vox + 31) / 32), B);
-  cng::channels_last_kernel<<<grid, 256, static_cast<size_t>(C) * 33 * sizeof(float), cng::as_stream(stream)>>>(
-      vol_ncdhw, vol_ndhwc, C, vox);
+  const size_t smem = static_cast<size_t>(C) * 33 * sizeof(float);
+  if (C == 32) cng::channels_last_kernel<32><<<grid, 256, smem, cng::as_stream(stream)>>>(vol_ncdhw, vol_ndhwc, C, vox);
+  else cng::channels_last_kernel<0><<<grid, 256, smem, cng::as_stream(stream)>>>(vol_ncdhw, vol_ndhwc, C, vox);
   return cng::check_launch("cng_volume_to_channels_last");
 }
 

@@ -525,3 +525,68 @@ def test_channels_last_3d_volume_needs_no_layout_kernel(ops):
     assert torch.equal(a, b) and torch.equal(da, db)
     assert (n2 - n1) == (n1 - n0) - 1
     assert ops.volume_to_channels_last(vol_cl3d).data_ptr() == vol_cl3d.data_ptr()
+
+
+def test_config1_full_size_vs_oracle():
+    """BASELINE configs[0] at full size: 64x64, 12+12 samples, batch 1, 32^3 x 32 volume, TALLSIREN_FG -- the reference's own
+    CPU-runnable case, rendered by the CUDA path (fp32 and bf16 modes) and by the oracle on the same draws."""
+    B, img, S, V = 1, 64, 12, 32
+    siren_type = "TALLSIREN_FG"
+    state = oracle.init_generator_state(siren_type, seed=21)
+    g = torch.Generator().manual_seed(22)
+    z = (torch.randn((B, 32, V, V, V), generator=g) * 0.3, torch.randn((B, 256), generator=g) * 0.05 + 0.19)
+    cam = oracle.look_at_cam2world(oracle.random_camera_origins(B, 0.7, 1.5, "y", np.random.RandomState(23)), "y")
+    draws = oracle.draw_randoms(B, img, S, True, g)
+    meta = dict(img_size=img, fov=FOV, ray_start=0.25, ray_end=1.95, num_steps=S, hierarchical_sample=True,
+                clamp_mode="relu", nerf_noise=0.0, white_back=True)
+    ref = oracle.render(state, siren_type, z, cam, draws, **meta)
+    decided = (oracle.far_plane_sigma(ref, 0.0).abs() >= 2e-2).reshape(B, 1, img, img).expand(B, 3, img, img)
+    d = {k: dev(v) for k, v in draws.items()}
+    for precision, min_psnr in (("fp32", 60.0), ("bf16", 40.0)):
+        gen = _generator(siren_type, state, precision)
+        with torch.no_grad():
+            out = gen._render(dev(z[0]), dev(z[1]), dev(cam), img, FOV, 0.25, 1.95, S, True, dict(meta, draws=d), taps=True)
+        pixels = out["pixels"].cpu()
+        if precision == "fp32":
+            assert torch.equal(out["t_coarse"].cpu(), ref["t_coarse"].squeeze(-1))
+            assert torch.equal(out["merge_order"].cpu().long(), ref["merge_order"].squeeze(-1)), "merge order differs at full size"
+            # resampling indices: bit-exact when fed the kernel's own coarse weights (the oracle's differ in the last ulps)
+            o_s, o_i, _, _ = oracle.coarse_to_fine_t(out["weights_coarse"].cpu().unsqueeze(-1), out["t_coarse"].cpu().unsqueeze(-1),
+                                                     draws["u_resample"], S)
+            assert torch.equal(out["resample_inds"].cpu(), o_i) and torch.equal(out["t_fine"].cpu().reshape(-1, S), o_s)
+            assert oracle.psnr(pixels, ref["pixels"]) >= min_psnr
+            assert torch.allclose(out["depth"].cpu(), ref["depth"], atol=2e-3)
+        else:
+            assert oracle.psnr(pixels[decided], ref["pixels"][decided]) >= min_psnr
+        print(f"config 1 {precision}: PSNR {oracle.psnr(pixels, ref['pixels']):.1f} dB whole image, decided {decided.float().mean().item():.1%}")
+
+
+def test_config2_full_size_properties():
+    """BASELINE configs[1] at full size (batch 8, 128x128, 24+24, 64^3): finite, in range, deterministic, and every image of
+    the batch equals the same image rendered alone (rays and images are independent: the sharding argument of DESIGN.md 6)."""
+    B, img, S, V = 8, 128, 24, 64
+    siren_type = "TALLSIREN_FG"
+    state = oracle.init_generator_state(siren_type, seed=0)
+    gen = _generator(siren_type, state, "bf16")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    vol = torch.randn((B, 32, V, V, V), generator=g, device="cuda") * 0.3
+    glob = torch.randn((B, 256), generator=g, device="cuda") * 0.05 + 0.19
+    cam = dev(oracle.look_at_cam2world(oracle.random_camera_origins(B, 0.7, 1.5, "y", np.random.RandomState(1)), "y"))
+    R = img * img
+    d = {"u_jitter": torch.rand((B, R, S, 1), generator=g, device="cuda"), "noise_coarse": torch.zeros((B, R, S, 1), device="cuda"),
+         "u_resample": torch.rand((B * R, S), generator=g, device="cuda"), "noise_final": torch.zeros((B, R, 2 * S, 1), device="cuda")}
+    meta = dict(img_size=img, fov=FOV, ray_start=0.25, ray_end=1.95, num_steps=S, hierarchical_sample=True,
+                clamp_mode="relu", nerf_noise=0.0, white_back=True)
+    with torch.no_grad():
+        a, da = gen((vol, glob), cam, draws=d, **meta)
+        b, db = gen((vol, glob), cam, draws=d, **meta)
+    assert torch.equal(a, b) and torch.equal(da, db)
+    assert torch.isfinite(a).all() and torch.isfinite(da).all()
+    assert float(a.min()) >= -1 - 1e-5 and float(a.max()) <= 1 + 1e-5
+    assert float(da.min()) >= 0 and float(da.max()) <= 1.95 + 1e-4
+    for i in (0, 5):
+        di = {"u_jitter": d["u_jitter"][i:i + 1], "noise_coarse": d["noise_coarse"][i:i + 1],
+              "u_resample": d["u_resample"][i * R:(i + 1) * R], "noise_final": d["noise_final"][i:i + 1]}
+        with torch.no_grad():
+            s, ds = gen((vol[i:i + 1], glob[i:i + 1]), cam[i:i + 1], draws=di, **meta)
+        assert torch.equal(s[0], a[i]) and torch.equal(ds[0], da[i])
