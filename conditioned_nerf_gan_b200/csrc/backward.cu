@@ -15,6 +15,7 @@
 // One warp per ray for the compositing backward: the forward quantities (merge order, alpha,
 // transmittance) are recomputed, the suffix sum over later samples is a reverse warp scan.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "cng_common.cuh"
 #include "merge_sort.cuh"
@@ -308,9 +309,53 @@ __global__ void __launch_bounds__(256) film_sin_grad_kernel(const __nv_bfloat16*
   atomicAdd(dphase + col, red[1][0][col] + red[1][1][col] + red[1][2][col] + red[1][3][col]);
 }
 
+// dz = dy * g (bf16 x fp16 -> bf16), colsum[c] += sum_p dz[p][c];  g = freq * cos(u) dumped by the training-mode forward.
+// Same thread layout as film_sin_grad_kernel.
+__global__ void __launch_bounds__(256) film_grad_from_g_kernel(const __nv_bfloat16* __restrict__ dy, const __half* __restrict__ g,
+                                                                long long P, __nv_bfloat16* __restrict__ dz, float* __restrict__ colsum) {
+  __shared__ float red[4][256];
+  const int cgp = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int c = cgp * 4;
+  const long long r0 = static_cast<long long>(blockIdx.x) * kGradRows;
+  const long long r1 = min(P, r0 + kGradRows);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (long long r = r0 + ty; r < r1; r += 4) {
+    const uint2 a2 = __ldg(reinterpret_cast<const uint2*>(dy + r * 256 + c));
+    const uint2 b2 = __ldg(reinterpret_cast<const uint2*>(g + r * 256 + c));
+    const __nv_bfloat162 a01 = *reinterpret_cast<const __nv_bfloat162*>(&a2.x), a23 = *reinterpret_cast<const __nv_bfloat162*>(&a2.y);
+    const float2 b01 = __half22float2(*reinterpret_cast<const __half2*>(&b2.x)), b23 = __half22float2(*reinterpret_cast<const __half2*>(&b2.y));
+    const float o0 = __low2float(a01) * b01.x, o1 = __high2float(a01) * b01.y;
+    const float o2 = __low2float(a23) * b23.x, o3 = __high2float(a23) * b23.y;
+    acc[0] += o0; acc[1] += o1; acc[2] += o2; acc[3] += o3;
+    __nv_bfloat162 o01 = __floats2bfloat162_rn(o0, o1), o23 = __floats2bfloat162_rn(o2, o3);
+    uint2 w2;
+    w2.x = *reinterpret_cast<uint32_t*>(&o01);
+    w2.y = *reinterpret_cast<uint32_t*>(&o23);
+    *reinterpret_cast<uint2*>(dz + r * 256 + c) = w2;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) red[ty][c + k] = acc[k];
+  __syncthreads();
+  const int col = threadIdx.x;
+  atomicAdd(colsum + col, red[0][col] + red[1][col] + red[2][col] + red[3][col]);
+}
+
 }  // namespace cng
 
 extern "C" {
+
+int cng_film_grad_from_g(const void* dy_bf16, const void* g_f16, long long P, int HID, void* dz_bf16, float* colsum, cng_stream_t stream) {
+  CNG_REQUIRE(P >= 0, CNG_ERR_INVALID_ARGUMENT, "film_grad_from_g: P=%lld", P);
+  CNG_REQUIRE(HID == 256, CNG_ERR_UNSUPPORTED, "film_grad_from_g: HID=%d (only 256 is built)", HID);
+  if (P == 0) return CNG_OK;
+  CNG_REQUIRE(dy_bf16 && g_f16 && dz_bf16 && colsum, CNG_ERR_INVALID_ARGUMENT, "film_grad_from_g: NULL pointer");
+  CNG_REQUIRE((P + cng::kGradRows - 1) / cng::kGradRows < 0x7fffffffLL, CNG_ERR_UNSUPPORTED, "film_grad_from_g: too many rows");
+  if (int e = cng_device_check()) return e;
+  cng::film_grad_from_g_kernel<<<static_cast<unsigned>((P + cng::kGradRows - 1) / cng::kGradRows), 256, 0, cng::as_stream(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy_bf16), static_cast<const __half*>(g_f16), P, static_cast<__nv_bfloat16*>(dz_bf16), colsum);
+  return cng::check_launch("cng_film_grad_from_g");
+}
 
 int cng_merge_composite_bwd(const float* rgb_sigma_fine, const float* rgb_sigma_coarse, const float* t_fine,
                             const float* t_coarse, const float* noise, const float* rays_d_cam, const float* d_pixels,

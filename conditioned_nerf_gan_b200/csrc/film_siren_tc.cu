@@ -141,7 +141,8 @@ __global__ void __launch_bounds__(256) film_fold_kernel(FoldParams p) {
   }
 }
 
-template <int kPolyOneIn, bool kHalf>
+// kTrain: additionally stream x_{l+1} and g_l = freq*cos(u_l) of every layer to HBM (p.dump_x / p.dump_g) for the backward
+template <int kPolyOneIn, bool kHalf, bool kTrain = false>
 __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t s_base = smem_u32(smem);
@@ -305,12 +306,39 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
       for (int l = 0; l < L; ++l) {
         const bool more = l + 1 < L;
         const float* shift_next = shift_item + (more ? l + 1 : l) * kHID;
-        sh.load(shift_next + kB * half * 32);                      // in flight while waiting for the accumulator
+        if (!kTrain) sh.load(shift_next + kB * half * 32);         // in flight while waiting for the accumulator
         mbar_wait(acc_full(x), acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
         if (tracer) trace_event(p.trace, iter, l, x, 2);
         auto finish_block = [&](const uint32_t (&v)[32], int cc) {
+          if constexpr (kTrain) {
+            // 8 columns at a time: sin -> shared-memory operand AND global dump (bf16), freq*cos -> global dump (fp16)
+            const size_t drow = ((static_cast<size_t>(l) * p.B + ti.item) * p.N + ti.n0 + row) * kHID + cc * 32;
+            const float* fq = p.freq + (static_cast<size_t>(ti.item) * L + l) * kHID + cc * 32;
+            uint8_t* blk = smem + a_base + (cc >> 1) * kABlockBytes + row * 128;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 f0 = __ldg(reinterpret_cast<const float4*>(fq + 8 * i)), f1 = __ldg(reinterpret_cast<const float4*>(fq + 8 * i + 4));
+              const float fr[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+              uint32_t xs[4], xo[4], gs[4];
+#pragma unroll
+              for (int j = 0; j < 8; j += 2) {
+                const float u0 = __uint_as_float(v[8 * i + j]), u1 = __uint_as_float(v[8 * i + j + 1]);
+                const float s0 = __sinf(u0), s1 = __sinf(u1);
+                xs[j / 2] = pack2<false>(s0, s1);                  // dump: bf16, the dtype of the gradient GEMMs
+                xo[j / 2] = pack2<kHalf>(s0, s1);                  // next layer's tensor-core operand
+                gs[j / 2] = pack2<true>(fr[j] * __cosf(u0), fr[j + 1] * __cosf(u1));     // fp16: |g| <= |freq| ~ 45, 11-bit significand
+              }
+              const int chunk = ((cc & 1) * 4 + i) ^ (row & 7);
+              *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(xo[0], xo[1], xo[2], xo[3]);
+              if (row < ti.rows) {
+                *reinterpret_cast<uint4*>(p.dump_x + drow + 8 * i) = make_uint4(xs[0], xs[1], xs[2], xs[3]);
+                *reinterpret_cast<uint4*>(p.dump_g + drow + 8 * i) = make_uint4(gs[0], gs[1], gs[2], gs[3]);
+              }
+            }
+            return;
+          }
           uint32_t o[16];
 #pragma unroll
           for (int j = 0; j < 32; j += 2)
@@ -348,8 +376,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
             CNG_TMEM_LD_32(t_lane + cc * 32, v);
             tmem_ld_wait();
             // the columns just read take the next layer's shift; the next MMA accumulates on top of it
-            if (more) sh.store(t_lane + cc * 32);
-            if (cc + 1 < kB * half + kB) sh.load(shift_next + (cc + 1) * 32);   // next block's shift, used after these sines
+            if (kTrain) {                                          // register budget: no prefetch, load and store back to back
+              if (more) { sh.load(shift_next + cc * 32); sh.store(t_lane + cc * 32); }
+            } else {
+              if (more) sh.store(t_lane + cc * 32);
+              if (cc + 1 < kB * half + kB) sh.load(shift_next + (cc + 1) * 32);   // next block's shift, used after these sines
+            }
             finish_block(v, cc);
           }
         }
@@ -402,7 +434,7 @@ size_t film_siren_tc_workspace(int B, int L) {
 int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, int L, const float* const* w,
                          const float* const* b, const float* freq, const float* phase, const float* final_w,
                          const float* final_b_dev, int sigmoid_rgb, int half_operands, void* workspace, size_t workspace_bytes,
-                         float* out, cudaStream_t stream) {
+                         float* out, void* dump_x, void* dump_g, cudaStream_t stream) {
   CNG_REQUIRE(HID == kHID && C == kC0, CNG_ERR_UNSUPPORTED, "film_siren_fwd(bf16): needs HID=256, C=32 (got %d, %d)", HID, C);
   CNG_REQUIRE(L >= 1 && L <= 16, CNG_ERR_UNSUPPORTED, "film_siren_fwd(bf16): L=%d", L);
   CNG_REQUIRE(workspace != nullptr && workspace_bytes >= film_siren_tc_workspace(B, L), CNG_ERR_WORKSPACE,
@@ -417,12 +449,16 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
   fp.shift = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + static_cast<size_t>(B) * item_image_bytes(L));
   const long long per_item = 256LL * 4 + static_cast<long long>(L - 1) * 256 * 32 + 16 * 32;
   const long long fold_threads = per_item * B;
-  if (half_operands) film_fold_kernel<true><<<static_cast<unsigned>((fold_threads + 255) / 256), 256, 0, stream>>>(fp);
+  if (half_operands || dump_x != nullptr) film_fold_kernel<true><<<static_cast<unsigned>((fold_threads + 255) / 256), 256, 0, stream>>>(fp);
   else film_fold_kernel<false><<<static_cast<unsigned>((fold_threads + 255) / 256), 256, 0, stream>>>(fp);
   if (int e = check_launch("cng_film_siren_fwd(bf16): fold")) return e;
 
   TcParams p{};
-  p.half_operands = half_operands;
+  p.half_operands = (dump_x != nullptr) ? 1 : half_operands;     // the recompute runs with fp16 operands (11-bit significands)
+  p.dump_x = static_cast<__nv_bfloat16*>(dump_x); p.dump_g = static_cast<__nv_bfloat16*>(dump_g); p.freq = freq;
+  CNG_REQUIRE((dump_x == nullptr) == (dump_g == nullptr), CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd_train: dump_x and dump_g go together");
+  CNG_REQUIRE(((reinterpret_cast<uintptr_t>(dump_x) | reinterpret_cast<uintptr_t>(dump_g)) & 15) == 0, CNG_ERR_INVALID_ARGUMENT,
+              "film_siren_fwd_train: dump buffers not 16-byte aligned");
   p.trace = g_tc_trace;
   p.feat = feat; p.N = N; p.B = B; p.L = L; p.images = fp.images; p.shift = fp.shift;
   CNG_REQUIRE((reinterpret_cast<uintptr_t>(final_b_dev) & 15) == 0, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd(bf16): final_b not 16-byte aligned");
@@ -437,7 +473,7 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
     const int v = e ? atoi(e) : kDefaultCtaGroup;
     return (v == 1 || v == 2) ? v : kDefaultCtaGroup;
   }();
-  if (cta_group == 2 && sm_count() >= 2 && !half_operands) return film_siren_tc2_launch(p, stream);
+  if (cta_group == 2 && sm_count() >= 2 && !half_operands && p.dump_x == nullptr) return film_siren_tc2_launch(p, stream);
   // share of the sines evaluated on the FMA pipe instead of the MUFU unit (tuning knob, default from measurement)
   static const int poly = [] {
     const char* e = getenv("CNG_TC_POLY");
@@ -445,14 +481,16 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
     return (v == 0 || v == 2 || v == 3 || v == 4 || v == 8) ? v : kDefaultPolyOneIn;
   }();
   using KernelFn = void (*)(TcParams);
-  const KernelFn fn = half_operands ? film_siren_tc_kernel<0, true>
+  const bool train = p.dump_x != nullptr;
+  const KernelFn fn = train ? film_siren_tc_kernel<0, true, true> : half_operands ? film_siren_tc_kernel<0, true>
                       : poly == 0 ? film_siren_tc_kernel<0, false> : poly == 2 ? film_siren_tc_kernel<2, false>
                       : poly == 3 ? film_siren_tc_kernel<3, false> : poly == 4 ? film_siren_tc_kernel<4, false> : film_siren_tc_kernel<8, false>;
-  static bool attr_set[2][9] = {};
-  if (!attr_set[half_operands ? 1 : 0][poly]) {
+  static bool attr_set[3][9] = {};
+  const int variant = train ? 2 : (half_operands ? 1 : 0);
+  if (!attr_set[variant][poly]) {
     ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTotal));
     if (ce != cudaSuccess) return fail(static_cast<int>(ce), "film_siren_fwd(bf16): smem attribute: %s", cudaGetErrorString(ce));
-    attr_set[half_operands ? 1 : 0][poly] = true;
+    attr_set[variant][poly] = true;
   }
   const long long grid = min(static_cast<long long>(sm_count()), p.total_tiles);
   fn<<<static_cast<unsigned>(grid), kNumThreads, kSmemTotal, stream>>>(p);
@@ -496,8 +534,23 @@ int cng_film_siren_fwd(const float* feat, int B, long long N, int C, int HID, in
   if (precision == CNG_PREC_BF16 || precision == CNG_PREC_FP16)
     return cng::film_siren_tc_launch(feat, B, N, C, HID, L, layer_w_host, layer_b_host, freq, phase, final_w, final_b,
                                      sigmoid_rgb, precision == CNG_PREC_FP16 ? 1 : 0, workspace, workspace_bytes, rgb_sigma,
-                                     cng::as_stream(stream));
+                                     nullptr, nullptr, cng::as_stream(stream));
   return cng::fail(CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd: unknown precision %d", precision);
+}
+
+int cng_film_siren_fwd_train(const float* feat, int B, long long N, int C, int HID, int L, const float* const* layer_w_host,
+                             const float* const* layer_b_host, const float* freq, const float* phase, const float* final_w,
+                             const float* final_b, int sigmoid_rgb, void* workspace, size_t workspace_bytes, float* rgb_sigma,
+                             void* x_dump_bf16, void* g_dump_bf16, cng_stream_t stream) {
+  CNG_REQUIRE(B >= 0 && N >= 0 && C >= 1 && HID >= 1 && L >= 1, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd_train: bad shape");
+  if (B == 0 || N == 0) return CNG_OK;
+  CNG_REQUIRE(feat && layer_w_host && layer_b_host && freq && phase && final_w && final_b && rgb_sigma && x_dump_bf16 && g_dump_bf16,
+              CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd_train: NULL pointer");
+  for (int l = 0; l < L && l < 16; ++l)
+    CNG_REQUIRE(layer_w_host[l] && layer_b_host[l], CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd_train: NULL layer %d", l);
+  if (int e = cng_device_check()) return e;
+  return cng::film_siren_tc_launch(feat, B, N, C, HID, L, layer_w_host, layer_b_host, freq, phase, final_w, final_b, sigmoid_rgb, 0,
+                                   workspace, workspace_bytes, rgb_sigma, x_dump_bf16, g_dump_bf16, cng::as_stream(stream));
 }
 
 }  // extern "C"

@@ -229,6 +229,11 @@ struct TcParams {
   long long tiles_per_item;
   long long total_tiles;
   int half_operands;        // 1: fp16 operands, 0: bf16
+  // training-mode dump (backward recompute): per layer l the layer output x_{l+1} = sin(u_l) and the local derivative
+  // g_l = freq * cos(u_l), [L][B][N][256] each, x as bf16 (a GEMM operand next to bf16 gradients), g as fp16; NULL in inference
+  __nv_bfloat16* dump_x;
+  __nv_bfloat16* dump_g;    // holds fp16 bit patterns
+  const float* freq;        // [B, L*256], only read when dumping
   long long* trace;         // debug: clock64 timeline of CTA 0 (tools/trace_tc.py), NULL in production
 };
 // trace layout: [iter < 4][layer <= 8][slot < 2][event < 8]; events: 0 MMA thread saw act_ready, 1 MMAs issued,

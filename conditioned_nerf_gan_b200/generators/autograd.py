@@ -5,9 +5,10 @@ The forward kernels stay the no-grad ones (K1, K2, K3', nothing saved per layer)
 
     _ToChannelsLast   NCDHW <-> NDHWC                               cng_volume_{to,from}_channels_last
     _Gather*          d feat -> d volume (scatter-add)               cng_scatter_points
-    _FilmSiren        d rgb_sigma -> d feat, d W/b, d freq/phase     activations recomputed per chunk:
-                      cng_film_sin_apply / cng_film_sin_grad (FiLM + sin / cos halves) around the
-                      layer GEMMs, which in this round are cuBLAS bf16 x bf16 -> fp32 (``torch.mm``
+    _FilmSiren        d rgb_sigma -> d feat, d W/b, d freq/phase     activations recomputed per chunk by the
+                      training-mode K2 (cng_film_siren_fwd_train: the fused tcgen05 forward that also
+                      streams x_{l+1} and g_l = freq*cos(u_l) per layer), cng_film_grad_from_g for
+                      dz = dy*g; the dgrad / wgrad GEMMs are cuBLAS bf16 x bf16 -> fp32 (``torch.mm``
                       with ``out_dtype``) -- library GEMMs, NOT hand-written tcgen05 yet
     _MergeComposite   d pixels, d depth -> d rgb_sigma (fine, coarse)  cng_merge_composite_bwd
 
@@ -107,11 +108,17 @@ class _FilmSiren(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out):
+        """Chunked recompute: the training-mode K2 (cng_film_siren_fwd_train) re-runs the fused forward on a chunk of
+        points and streams every layer's output x_{l+1} and local derivative g_l = freq*cos(u_l) to HBM (bf16); then, per
+        layer from last to first:  dz = dy*g (cng_film_grad_from_g, with column sums),  dW += dz^T x_l and dy = dz W_l
+        (cuBLAS bf16 GEMMs, fp32 accumulate),  db = colsum(dz),  dphase = colsum(dz)/freq,
+        dfreq = rowsum(W * dW_chunk)/freq + b * dphase."""
         feat, freq, phase, final_w, final_b, out, *wb = ctx.saved_tensors
         L, H = ctx.L, final_w.shape[1]
         ws, bs = [w.detach().float() for w in wb[:L]], [b.detach().float() for b in wb[L:]]
         ws_bf = [w.to(torch.bfloat16) for w in ws]
-        fw = final_w.detach().float()
+        fw, fb = final_w.detach().float(), final_b.detach().float()
+        fw_bf = fw.to(torch.bfloat16)
         B, N, C = feat.shape
         dev = feat.device
         d_out = d_out.contiguous().float()
@@ -122,51 +129,40 @@ class _FilmSiren(torch.autograd.Function):
         d_bs = [torch.zeros_like(b) for b in bs]
         d_fw = torch.zeros_like(fw)
         d_fb = torch.zeros((4,), dtype=torch.float32, device=dev)
-        fw_bf = fw.to(torch.bfloat16)
-        tf32_was = torch.backends.cuda.matmul.allow_tf32
         for b in range(B):
-            fr, ph = freq[b].detach().float(), phase[b].detach().float()
-            dph_before = d_phase[b].clone()
+            fr_all, ph_all = freq[b:b + 1].detach().float().contiguous(), phase[b:b + 1].detach().float().contiguous()
+            safe_fr = torch.where(fr_all[0].abs() < 1e-12, torch.ones_like(fr_all[0]), fr_all[0])
             for r0 in range(0, N, CHUNK_ROWS):
                 r1 = min(N, r0 + CHUNK_ROWS)
-                x0 = feat[b, r0:r1].detach()
-                # ---- recompute: z_l = x_l W_l^T (fp32 out), x_{l+1} = bf16(sin(freq (z_l + b_l) + phase))
-                zs: List[torch.Tensor] = []
-                xs: List[torch.Tensor] = [x0.to(torch.bfloat16)]
-                for l in range(L):
-                    if l == 0:
-                        # K = 32: TF32 tensor cores (11-bit operands, fp32 accumulate) instead of an fp32 SIMT sgemm
-                        torch.backends.cuda.matmul.allow_tf32 = True
-                        z = x0 @ ws[0].t()
-                        torch.backends.cuda.matmul.allow_tf32 = tf32_was
-                    else:
-                        z = torch.mm(xs[l], ws_bf[l].t(), out_dtype=torch.float32)
-                    zs.append(z)
-                    xs.append(ops.film_sin_apply(z, bs[l], fr[l * H:(l + 1) * H], ph[l * H:(l + 1) * H]))
+                x0 = feat[b:b + 1, r0:r1].detach().contiguous()
+                _, xs, gs = ops.film_siren_fwd_train(x0, ws, bs, fr_all, ph_all, fw, fb, ctx.sigmoid_rgb)
+                xs, gs = xs[:, 0], gs[:, 0]                                    # [L, P, H]
                 # ---- head: out = x_L Wf^T + bf, rgb = sigmoid(out[:, :3])
                 d_o = d_out[b, r0:r1].clone()
                 if ctx.sigmoid_rgb:
                     rgb = out[b, r0:r1, :3]
                     d_o[:, :3] *= rgb * (1 - rgb)
                 d_o_bf = d_o.to(torch.bfloat16)
-                d_fw += torch.mm(d_o_bf.t(), xs[L], out_dtype=torch.float32)
+                d_fw += torch.mm(d_o_bf.t(), xs[L - 1], out_dtype=torch.float32)
                 d_fb += d_o.sum(0)
-                dy = torch.mm(d_o_bf, fw_bf)                                   # [P,4] x [4,HID] -> bf16 [P,HID]
-                # ---- layers, last to first
+                dy = torch.mm(d_o_bf, fw_bf)                                   # [P,4] x [4,H] -> bf16 [P,H]
+                x0_bf = x0[0].to(torch.bfloat16)
                 for l in reversed(range(L)):
                     sl = slice(l * H, (l + 1) * H)
-                    dz = ops.film_sin_grad(dy, zs[l], bs[l], fr[sl], ph[sl], d_freq[b, sl], d_phase[b, sl])
-                    zs[l] = None
-                    d_ws[l] += torch.mm(dz.t(), xs[l], out_dtype=torch.float32)
+                    colsum = torch.zeros((H,), dtype=torch.float32, device=dev)
+                    dz = ops.film_grad_from_g(dy, gs[l], colsum)
+                    x_in = xs[l - 1] if l > 0 else x0_bf
+                    dW = torch.mm(dz.t(), x_in, out_dtype=torch.float32)       # this chunk's share, [H, K_l]
+                    d_ws[l] += dW
+                    d_bs[l] += colsum
+                    dph = colsum / safe_fr[sl]
+                    d_phase[b, sl] += dph
+                    d_freq[b, sl] += (ws[l] * dW).sum(1) / safe_fr[sl] + bs[l] * dph
                     if l == 0:
                         d_feat[b, r0:r1] = torch.mm(dz, ws_bf[0], out_dtype=torch.float32)
                     else:
                         dy = torch.mm(dz, ws_bf[l])
-                    xs[l + 1] = None
-            # d b_l = sum_p dz = freq * sum_p du  (this item's share of d_phase)
-            dph_item = d_phase[b] - dph_before
-            for l in range(L):
-                d_bs[l] += fr[l * H:(l + 1) * H] * dph_item[l * H:(l + 1) * H]
+                del xs, gs
         return (d_feat, d_freq, d_phase, d_fw.to(final_w.dtype), d_fb.to(final_b.dtype), None, None,
                 *[g.to(p.dtype) for g, p in zip(d_ws, wb[:L])], *[g.to(p.dtype) for g, p in zip(d_bs, wb[L:])])
 

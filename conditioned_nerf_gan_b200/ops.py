@@ -362,3 +362,44 @@ def film_sin_grad(dy_bf16, z, bias, freq, phase, dfreq, dphase) -> torch.Tensor:
                   _ptr(_f32(phase, "phase")), P, HID, _ptr(dz), _ptr(dfreq), _ptr(dphase), _stream(z))
     _count()
     return dz
+
+
+def film_siren_fwd_train(feat, layer_w, layer_b, freq, phase, final_w, final_b, sigmoid_rgb: bool):
+    """Training-mode K2: rgb_sigma [B,N,4] plus the per-layer dumps x [L,B,N,HID] (bf16) and g = freq*cos(u) [L,B,N,HID] (fp16)."""
+    feat = _f32(feat, "feat")
+    B, N, C = feat.shape
+    L = len(layer_w)
+    ws = [_f32(w, f"layer_w[{i}]") for i, w in enumerate(layer_w)]
+    bs = [_f32(b, f"layer_b[{i}]") for i, b in enumerate(layer_b)]
+    HID = ws[0].shape[0]
+    freq, phase = _f32(freq, "freq"), _f32(phase, "phase")
+    final_w, final_b = _f32(final_w, "final_w"), _f32(final_b, "final_b")
+    dev = feat.device
+    out = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
+    xs = torch.empty((L, B, N, HID), dtype=torch.bfloat16, device=dev)
+    gs = torch.empty((L, B, N, HID), dtype=torch.float16, device=dev)
+    w_arr = (ctypes.c_void_p * L)(*[w.data_ptr() for w in ws])
+    b_arr = (ctypes.c_void_p * L)(*[b.data_ptr() for b in bs])
+    lib = _lib.load()
+    ws_bytes = int(lib.cng_film_siren_workspace_bytes(B, C, HID, L, _lib.PREC_BF16))
+    workspace = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev), _timed("cng_film_siren_fwd_train"):
+        _lib.call("cng_film_siren_fwd_train", _ptr(feat), B, N, C, HID, L, w_arr, b_arr, _ptr(freq), _ptr(phase), _ptr(final_w),
+                  _ptr(final_b), int(bool(sigmoid_rgb)), _ptr(workspace), ws_bytes, _ptr(out), _ptr(xs), _ptr(gs), _stream(feat))
+    _count(2)
+    return out, xs, gs
+
+
+def film_grad_from_g(dy_bf16, g_bf16, colsum) -> torch.Tensor:
+    """dz = dy * g (dy, dz bf16, g fp16, [P,HID]); accumulates the column sums of dz into colsum (fp32 [HID], in place)."""
+    for name, t, dt in (("dy", dy_bf16, torch.bfloat16), ("g", g_bf16, torch.float16)):
+        if not (t.is_cuda and t.dtype == dt and t.is_contiguous()):
+            raise RuntimeError(f"film_grad_from_g: {name} must be a contiguous {dt} CUDA tensor")
+    P, HID = dy_bf16.shape
+    if g_bf16.shape != dy_bf16.shape or not (colsum.is_cuda and colsum.dtype == torch.float32 and colsum.is_contiguous() and colsum.numel() == HID):
+        raise RuntimeError("film_grad_from_g: shape mismatch")
+    dz = torch.empty((P, HID), dtype=torch.bfloat16, device=dy_bf16.device)
+    with torch.cuda.device(dy_bf16.device), _timed("cng_film_grad_from_g"):
+        _lib.call("cng_film_grad_from_g", _ptr(dy_bf16), _ptr(g_bf16), P, HID, _ptr(dz), _ptr(colsum), _stream(dy_bf16))
+    _count()
+    return dz

@@ -227,6 +227,21 @@ CNG_API int cng_film_sin_grad(const void* dy_bf16, const float* z, const float* 
                       const float* phase, long long P, int HID, void* dz_bf16, float* dfreq,
                       float* dphase, cng_stream_t stream);
 
+/* Training-mode forward of K2 for the backward's activation recompute: the same fused tcgen05 kernel (bf16
+ * operands) that ALSO streams, for every FiLM layer l, its output x_{l+1} = sin(u_l) and its local derivative
+ * g_l = freq * cos(u_l) to HBM, x_dump (bf16) / g_dump (fp16) [L, B, N, HID].  With them the layer backward is
+ *   dz_l = dy_l * g_l (cng_film_grad_from_g),  dW_l = dz_l^T x_l,  dy_{l-1} = dz_l W_l,  db_l = colsum(dz_l),
+ *   dphase_l = colsum(dz_l) / freq_l,  dfreq_l = rowsum(W_l * dW_l) / freq_l + b_l * dphase_l. */
+CNG_API int cng_film_siren_fwd_train(const float* feat, int B, long long N, int C, int HID, int L,
+                             const float* const* layer_w_host, const float* const* layer_b_host,
+                             const float* freq, const float* phase, const float* final_w,
+                             const float* final_b, int sigmoid_rgb, void* workspace,
+                             size_t workspace_bytes, float* rgb_sigma, void* x_dump_bf16,
+                             void* g_dump_f16, cng_stream_t stream);
+/* dz = dy * g elementwise (dy, dz bf16, g fp16, all [P,HID]); colsum [HID] += column sums of dz (fp32, atomic). HID == 256. */
+CNG_API int cng_film_grad_from_g(const void* dy_bf16, const void* g_f16, long long P, int HID, void* dz_bf16,
+                         float* colsum, cng_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

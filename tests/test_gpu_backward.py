@@ -153,7 +153,7 @@ def test_generator_backward_vs_oracle_autograd(name):
         e, c = rel_l2(got[k].cpu(), r), cosine(got[k].cpu(), r)
         worst = max(worst, e)
         print(f"  {name} {k}: rel-L2 {e:.3e} cos {c:.6f} |ref| {float(r.norm()):.3e}")
-        assert c > 0.999 and e < 5e-2, (k, e, c)
+        assert c > 0.9995 and e < 2e-2, (k, e, c)
     print(f"{name}: worst relative L2 gradient error {worst:.3e}")
 
 
