@@ -144,6 +144,9 @@ __global__ void __launch_bounds__(256) film_fold_kernel(FoldParams p) {
 // kTrain: additionally stream x_{l+1} and g_l = freq*cos(u_l) of every layer to HBM (p.dump_x / p.dump_g) for the backward
 template <int kPolyOneIn, bool kHalf, bool kTrain = false>
 __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams p) {
+  // training mode gives one weight-ring slot (32 KB) to the per-warp staging buffers of the activation dumps
+  constexpr int kRingN = kTrain ? kRing - 1 : kRing;
+  constexpr uint32_t kSmemStage = kSmemW + kRingN * kChunkBytes;     // 16 epilogue warps x 2 KB (kTrain only)
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t s_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemBar + 96);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kRing; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+    for (int s = 0; s < kRingN; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
     for (int x = 0; x < 2; ++x) { mbar_init(act_ready(x), 32 * kEpiWarpsPerSlot); mbar_init(acc_full(x), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
                 bulk_g2s(s_base + kSmemW + slot * kChunkBytes, img + chunk_offset(L, l, c), bytes, w_full(slot));
               }
               __syncwarp();
-              if (++slot == kRing) { slot = 0; phase ^= 1; }
+              if (++slot == kRingN) { slot = 0; phase ^= 1; }
             }
           }
         }
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
                 tc_commit(w_empty(slot));          // slot is free once these MMAs have read it
               }
               __syncwarp();
-              if (++slot == kRing) { slot = 0; phase ^= 1; }
+              if (++slot == kRingN) { slot = 0; phase ^= 1; }
             }
             if (elected) {
               tc_commit(acc_full(x));              // accumulator of tile x complete
@@ -313,30 +316,48 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
         if (tracer) trace_event(p.trace, iter, l, x, 2);
         auto finish_block = [&](const uint32_t (&v)[32], int cc) {
           if constexpr (kTrain) {
-            // 8 columns at a time: sin -> shared-memory operand AND global dump (bf16), freq*cos -> global dump (fp16)
-            const size_t drow = ((static_cast<size_t>(l) * p.B + ti.item) * p.N + ti.n0 + row) * kHID + cc * 32;
+            // sin -> next layer's operand (shared memory A tile) and bf16 dump; freq*cos -> fp16 dump.  The dumps are
+            // row-major [point][256] in HBM; a lane owns one row, so its 64 bytes go through a 2 KB per-warp staging
+            // buffer and leave as 8 rows x 64 B per store instruction (8 LSU wavefronts instead of 32).
+            uint8_t* stage = smem + kSmemStage + warp * 2048;
+            const size_t dbase = ((static_cast<size_t>(l) * p.B + ti.item) * p.N + ti.n0 + q * 32) * kHID + cc * 32;   // row q*32 of the tile
             const float* fq = p.freq + (static_cast<size_t>(ti.item) * L + l) * kHID + cc * 32;
             uint8_t* blk = smem + a_base + (cc >> 1) * kABlockBytes + row * 128;
+            auto copy_out = [&](__nv_bfloat16* dst) {
+              __syncwarp();
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int rl = k * 8 + (lane >> 2), ch = lane & 3;
+                const uint4 val = *reinterpret_cast<const uint4*>(stage + (rl * 4 + (ch ^ ((rl >> 1) & 3))) * 16);
+                if (q * 32 + rl < ti.rows) *reinterpret_cast<uint4*>(dst + dbase + static_cast<size_t>(rl) * kHID + ch * 8) = val;
+              }
+              __syncwarp();
+            };
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint32_t xs[4], xo[4];
+#pragma unroll
+              for (int j = 0; j < 8; j += 2) {
+                const float s0 = __sinf(__uint_as_float(v[8 * i + j])), s1 = __sinf(__uint_as_float(v[8 * i + j + 1]));
+                xs[j / 2] = pack2<false>(s0, s1);                  // dump: bf16, the dtype of the gradient GEMMs
+                xo[j / 2] = pack2<kHalf>(s0, s1);                  // next layer's tensor-core operand
+              }
+              const int chunk = ((cc & 1) * 4 + i) ^ (row & 7);
+              *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(xo[0], xo[1], xo[2], xo[3]);
+              *reinterpret_cast<uint4*>(stage + (lane * 4 + (i ^ ((lane >> 1) & 3))) * 16) = make_uint4(xs[0], xs[1], xs[2], xs[3]);
+            }
+            copy_out(p.dump_x);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float4 f0 = __ldg(reinterpret_cast<const float4*>(fq + 8 * i)), f1 = __ldg(reinterpret_cast<const float4*>(fq + 8 * i + 4));
               const float fr[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-              uint32_t xs[4], xo[4], gs[4];
+              uint32_t gs[4];
 #pragma unroll
-              for (int j = 0; j < 8; j += 2) {
-                const float u0 = __uint_as_float(v[8 * i + j]), u1 = __uint_as_float(v[8 * i + j + 1]);
-                const float s0 = __sinf(u0), s1 = __sinf(u1);
-                xs[j / 2] = pack2<false>(s0, s1);                  // dump: bf16, the dtype of the gradient GEMMs
-                xo[j / 2] = pack2<kHalf>(s0, s1);                  // next layer's tensor-core operand
-                gs[j / 2] = pack2<true>(fr[j] * __cosf(u0), fr[j + 1] * __cosf(u1));     // fp16: |g| <= |freq| ~ 45, 11-bit significand
-              }
-              const int chunk = ((cc & 1) * 4 + i) ^ (row & 7);
-              *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(xo[0], xo[1], xo[2], xo[3]);
-              if (row < ti.rows) {
-                *reinterpret_cast<uint4*>(p.dump_x + drow + 8 * i) = make_uint4(xs[0], xs[1], xs[2], xs[3]);
-                *reinterpret_cast<uint4*>(p.dump_g + drow + 8 * i) = make_uint4(gs[0], gs[1], gs[2], gs[3]);
-              }
+              for (int j = 0; j < 8; j += 2)
+                gs[j / 2] = pack2<true>(fr[j] * __cosf(__uint_as_float(v[8 * i + j])), fr[j + 1] * __cosf(__uint_as_float(v[8 * i + j + 1])));
+              *reinterpret_cast<uint4*>(stage + (lane * 4 + (i ^ ((lane >> 1) & 3))) * 16) = make_uint4(gs[0], gs[1], gs[2], gs[3]);
             }
+            copy_out(p.dump_g);
             return;
           }
           uint32_t o[16];
