@@ -28,6 +28,7 @@ SIGNATURES = {
     "cng_raymarch_gather_fine": (c_int, [c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                          c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "cng_gather_points": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p]),
+    "cng_film_parameters": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "cng_film_siren_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "cng_film_siren_fwd": (c_int, [c_void_p, c_int, c_longlong, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),

@@ -126,6 +126,27 @@ __global__ void __launch_bounds__(256, 1) film_siren_simt_kernel(SimtParams p) {
   }
 }
 
+// a5: FiLM parameters.  freq = 15 * (W g + b)[:half] + 30, phase = (W g + b)[half:]   (generators/siren.py:550-553).
+// One thread per output, fixed left-to-right fp32 accumulation over z_dim: the result for an item does not depend on how
+// many items are in the batch (cuBLAS picks batch-size-dependent kernels, which breaks that by an ulp).
+__global__ void __launch_bounds__(256) film_parameters_kernel(const float* __restrict__ glob, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, int z_dim, int n_out,
+                                                               float* __restrict__ freq, float* __restrict__ phase) {
+  extern __shared__ float g_s[];
+  const int b = blockIdx.y;
+  for (int k = threadIdx.x; k < z_dim; k += blockDim.x) g_s[k] = __ldg(glob + static_cast<size_t>(b) * z_dim + k);
+  __syncthreads();
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_out) return;
+  const float* wr = w + static_cast<size_t>(o) * z_dim;
+  float acc = 0.f;
+  for (int k = 0; k < z_dim; ++k) acc = fmaf(g_s[k], __ldg(wr + k), acc);
+  acc += __ldg(bias + o);
+  const int half = n_out / 2;
+  if (o < half) freq[static_cast<size_t>(b) * half + o] = fmaf(acc, 15.f, 30.f);
+  else phase[static_cast<size_t>(b) * half + (o - half)] = acc;
+}
+
 int film_siren_simt_launch(const float* feat, int B, long long N, int C, int HID, int L, const float* const* w,
                            const float* const* b, const float* freq, const float* phase, const float* final_w,
                            const float* final_b, int sigmoid_rgb, float* out, cudaStream_t stream) {
@@ -146,3 +167,15 @@ int film_siren_simt_launch(const float* feat, int B, long long N, int C, int HID
 }
 
 }  // namespace cng
+
+extern "C" int cng_film_parameters(const float* global_feature, const float* map_w, const float* map_b, int B, int z_dim, int n_out,
+                                   float* freq, float* phase, cng_stream_t stream) {
+  CNG_REQUIRE(B >= 0 && z_dim >= 1 && n_out >= 2 && n_out % 2 == 0, CNG_ERR_INVALID_ARGUMENT, "film_parameters: B=%d z_dim=%d n_out=%d", B, z_dim, n_out);
+  CNG_REQUIRE(z_dim <= 8192 && B <= 65535, CNG_ERR_UNSUPPORTED, "film_parameters: z_dim=%d B=%d", z_dim, B);
+  if (B == 0) return CNG_OK;
+  CNG_REQUIRE(global_feature && map_w && map_b && freq && phase, CNG_ERR_INVALID_ARGUMENT, "film_parameters: NULL pointer");
+  if (int e = cng_device_check()) return e;
+  dim3 grid((n_out + 255) / 256, B);
+  cng::film_parameters_kernel<<<grid, 256, z_dim * sizeof(float), cng::as_stream(stream)>>>(global_feature, map_w, map_b, z_dim, n_out, freq, phase);
+  return cng::check_launch("cng_film_parameters");
+}

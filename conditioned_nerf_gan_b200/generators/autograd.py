@@ -212,7 +212,7 @@ def render_with_grad(gen, volume, global_feature, cam2worlds, img_size, fov, ray
         return fn(shape, device=dev) if t is None else t.to(dev)
 
     vol_cl = _ToChannelsLast.apply(volume.float())
-    freq, phase = net.film_parameters(global_feature)
+    freq, phase = net.film_parameters(global_feature, B, dev)
     C = vol_cl.shape[-1]
     u_jitter = draw("u_jitter", torch.rand, (B, R, S, 1))
     feat_c, t_c = _GatherCoarse.apply(vol_cl, cam2worlds, rays_d_cam, t_lin, u_jitter, img_size)
@@ -236,6 +236,6 @@ def render_with_grad(gen, volume, global_feature, cam2worlds, img_size, fov, ray
 def siren_forward_with_grad(net, points, volume, global_feature):
     """``siren(points, z, img_size, num_steps)`` with gradients (siren.py:540-580)."""
     vol_cl = _ToChannelsLast.apply(volume.float())
-    freq, phase = net.film_parameters(global_feature)
+    freq, phase = net.film_parameters(global_feature, volume.shape[0], volume.device)
     feat = _GatherPoints.apply(vol_cl, points.detach())
     return _mlp(net, feat, freq, phase)

@@ -54,7 +54,8 @@ class ImplicitGenerator3d(nn.Module):
         ``last_back`` default to False, every other key is ignored."""
         volume, global_feature = self.siren.split_z(z)
         needs_grad = torch.is_grad_enabled() and (
-            volume.requires_grad or global_feature.requires_grad or any(p.requires_grad for p in self.siren.parameters()))
+            volume.requires_grad or (global_feature is not None and global_feature.requires_grad)
+            or any(p.requires_grad for p in self.siren.parameters()))
         if needs_grad:
             from .autograd import render_with_grad
             return render_with_grad(self, volume, global_feature, cam2worlds, img_size, fov, ray_start, ray_end,
@@ -78,7 +79,7 @@ class ImplicitGenerator3d(nn.Module):
         rays_d_cam, t_lin = camera_tables((img_size, img_size), S, fov, ray_start, ray_end, dev)
         if vol_cl is None:
             vol_cl = ops.volume_to_channels_last(volume)
-        freq, phase = film if film is not None else net.film_parameters(global_feature)
+        freq, phase = film if film is not None else net.film_parameters(global_feature, B, dev)
         C = vol_cl.shape[-1]
         out: Dict[str, torch.Tensor] = {}
 
@@ -132,7 +133,7 @@ class ImplicitGenerator3d(nn.Module):
         kwargs.setdefault("clamp_mode", "relu")
         fovs = [float(fov)] * P if not hasattr(fov, "__len__") else [float(f) for f in fov]
         vol_cl = ops.volume_to_channels_last(volume)
-        film = self.siren.film_parameters(global_feature)
+        film = self.siren.film_parameters(global_feature, volume.shape[0], cam2worlds.device)
         pixels = torch.empty((P, 3, img_size, img_size), dtype=torch.float32, device=cam2worlds.device)
         depth = torch.empty((P, img_size, img_size), dtype=torch.float32, device=cam2worlds.device)
         start = 0

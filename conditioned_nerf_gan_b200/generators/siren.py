@@ -23,7 +23,7 @@ import torch.nn.functional as F
 
 from .. import ops
 
-__all__ = ["FiLMLayer", "TALLSIREN_FG", "SHORTSIREN_FG", "DOUBLESIREN_FG", "SingleSIREN_dg",
+__all__ = ["FiLMLayer", "SirenLayer", "TALLSIREN_FG", "SHORTSIREN_FG", "DOUBLESIREN_FG", "SingleSIREN_dg", "SHORTSIREN_F",
            "TALLSIREN_dg", "SHORTSIREN_dg", "DoubleSIREN_dg", "DOUBLESIREN_dg", "default_precision"]
 
 
@@ -47,6 +47,9 @@ class FiLMLayer(nn.Module):
             raise NotImplementedError("FiLM dropout > 0 is not built (every shipped config uses 0, special.py:39)")
 
 
+SirenLayer = FiLMLayer     # siren.py:180-199: the unmodulated layer holds the same single nn.Linear
+
+
 def _uniform_(linear: nn.Linear, bound: float) -> None:
     with torch.no_grad():
         linear.weight.uniform_(-bound, bound)
@@ -57,15 +60,17 @@ class _FiLMSirenFG(nn.Module):
     freq_div = 25.0         # frequency_init(freq_div), siren.py:134-143
     sigmoid_rgb = True      # _sigmoid_rgb on the head (siren.py:579) or raw rgb (:1064)
     tensor_core_operands = "bf16"   # 16-bit operand format of the tcgen05 path that keeps this variant <= 1e-2 max-abs
+    film = True             # False: plain sin(W x + b) layers, no mapping network, z is the feature volume alone
 
-    def __init__(self, input_dim=3, z_dim=100, hidden_dim=256, output_dim=4, drop_out=0, device=None):
+    def __init__(self, input_dim=3, z_dim=100, hidden_dim=256, output_dim=4, drop_out=0, device=None, **kwargs):
         super().__init__()
         self.device = device
         self.input_dim, self.z_dim, self.hidden_dim, self.output_dim = input_dim, z_dim, hidden_dim, output_dim
         self.network = nn.ModuleList(
             [FiLMLayer(input_dim if i == 0 else hidden_dim, hidden_dim, drop_out) for i in range(self.num_layers)])
         self.final_layer = nn.Linear(hidden_dim, 4)
-        self.mapping_network = nn.Linear(z_dim, self.num_layers * hidden_dim * 2)
+        if self.film:
+            self.mapping_network = nn.Linear(z_dim, self.num_layers * hidden_dim * 2)
         for i, film in enumerate(self.network):
             fan_in = film.layer.weight.shape[-1]
             # first_layer_film_sine_init (siren.py:40-44) overrides frequency_init on layer 0
@@ -74,9 +79,18 @@ class _FiLMSirenFG(nn.Module):
         self.precision = default_precision(self.tensor_core_operands)
 
     # -- pieces shared with ImplicitGenerator3d ------------------------------------------------
-    def film_parameters(self, global_feature: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """siren.py:550-553: freq = first half * 15 + 30, phase = second half.  [B, L*HID] each."""
-        # fp32 even under the trainer's autocast: freq ~ 30 multiplies the pre-activations
+    def film_parameters(self, global_feature, batch: int = 1, device=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """siren.py:550-553: freq = first half * 15 + 30, phase = second half.  [B, L*HID] each.
+        Unmodulated variants (``film = False``): freq = 1, phase = 0 for ``batch`` items."""
+        if not self.film:
+            n = self.num_layers * self.hidden_dim
+            dev = device if device is not None else self.final_layer.weight.device
+            return torch.ones((batch, n), device=dev), torch.zeros((batch, n), device=dev)
+        needs_grad = torch.is_grad_enabled() and (global_feature.requires_grad or self.mapping_network.weight.requires_grad)
+        if global_feature.is_cuda and not needs_grad:
+            # inference: the library's own kernel (batch-size independent rounding, one launch)
+            return ops.film_parameters(global_feature.detach(), self.mapping_network.weight.detach(), self.mapping_network.bias.detach())
+        # training: a differentiable torch op; fp32 even under the trainer's autocast (freq ~ 30 multiplies the pre-activations)
         with torch.autocast(device_type=global_feature.device.type, enabled=False):
             fo = F.linear(global_feature.float(), self.mapping_network.weight.float(), self.mapping_network.bias.float())
             half = fo.shape[-1] // 2
@@ -91,8 +105,11 @@ class _FiLMSirenFG(nn.Module):
         return ops.film_siren_fwd(feat, ws, bs, freq, phase, self.final_layer.weight, self.final_layer.bias,
                                   self.sigmoid_rgb, self.precision)
 
-    @staticmethod
-    def split_z(z):
+    def split_z(self, z):
+        if not self.film:
+            if isinstance(z, (tuple, list)):
+                raise ValueError(f"{type(self).__name__} takes the feature volume alone as z (generators/siren.py:867)")
+            return z, None
         if not isinstance(z, (tuple, list)) or len(z) != 2:
             raise ValueError("the FG SIREN family needs z = (feature_volume [B,C,D,H,W], global_feature [B,z_dim]) "
                              "(unet.return_global=True, generators/unet3d.py:635-638)")
@@ -102,11 +119,11 @@ class _FiLMSirenFG(nn.Module):
         """points [B, N, 3] world space (N == img_size**2 * num_steps in the reference's callers;
         any N works here), z = (feature_volume, global_feature).  Returns rgb_sigma [B, N, 4]."""
         volume, global_feature = self.split_z(z)
-        if torch.is_grad_enabled() and (volume.requires_grad or global_feature.requires_grad
+        if torch.is_grad_enabled() and (volume.requires_grad or (global_feature is not None and global_feature.requires_grad)
                                         or any(p.requires_grad for p in self.parameters())):
             from .autograd import siren_forward_with_grad
             return siren_forward_with_grad(self, points, volume, global_feature)
-        freq, phase = self.film_parameters(global_feature)
+        freq, phase = self.film_parameters(global_feature, volume.shape[0], volume.device)
         feat = ops.gather_points(ops.volume_to_channels_last(volume), points)
         return self.mlp(feat, freq, phase)
 
@@ -128,6 +145,13 @@ class DOUBLESIREN_FG(_FiLMSirenFG):
 
 class SingleSIREN_dg(_FiLMSirenFG):
     num_layers, freq_div, sigmoid_rgb = 1, 25.0, False
+
+
+class SHORTSIREN_F(_FiLMSirenFG):
+    """generators/siren.py:830-904: feature volume only, four plain ``sin(W x + b)`` layers (SirenLayer), no FiLM, no
+    mapping network; ``z`` is the feature volume.  Runs on the same kernels with freq = 1, phase = 0."""
+    num_layers, freq_div, sigmoid_rgb, film = 4, 12.0, True, False
+    tensor_core_operands = "fp16"
 
 
 # config spellings (SURVEY.md appendix C)

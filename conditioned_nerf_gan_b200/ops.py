@@ -164,6 +164,21 @@ def gather_points(vol_cl, points, want_index=False):
     return (feat, idx) if want_index else feat
 
 
+def film_parameters(global_feature, map_w, map_b) -> Tuple[torch.Tensor, torch.Tensor]:
+    """a5: freq = 15 * linear(global)[:half] + 30, phase = linear(global)[half:]; each [B, n_out/2].  No autograd."""
+    g, w, b = _f32(global_feature, "global_feature"), _f32(map_w, "map_w"), _f32(map_b, "map_b")
+    B, z_dim = g.shape
+    n_out = w.shape[0]
+    if w.shape[1] != z_dim:
+        raise ValueError(f"global feature has {z_dim} channels, the mapping network expects {w.shape[1]}")
+    freq = torch.empty((B, n_out // 2), dtype=torch.float32, device=g.device)
+    phase = torch.empty((B, n_out // 2), dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device), _timed("cng_film_parameters"):
+        _lib.call("cng_film_parameters", _ptr(g), _ptr(w), _ptr(b), B, z_dim, n_out, _ptr(freq), _ptr(phase), _stream(g))
+    _count()
+    return freq, phase
+
+
 def film_siren_fwd(feat, layer_w: Sequence[torch.Tensor], layer_b: Sequence[torch.Tensor], freq, phase, final_w,
                    final_b, sigmoid_rgb: bool, precision: str = "bf16") -> torch.Tensor:
     """K2.  feat [B,N,C], freq/phase [B,L*HID] -> rgb_sigma [B,N,4]."""

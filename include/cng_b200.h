@@ -131,6 +131,12 @@ CNG_API int cng_gather_points(const float* vol_ndhwc, int B, int C, int D, int H
  * CNG_PREC_BF16 / CNG_PREC_FP16 need HID == 256, C == 32 and a workspace of
  * cng_film_siren_workspace_bytes().
  * ---------------------------------------------------------------------------------------- */
+/* a5: FiLM parameters of the mapping network (nn.Linear(z_dim, 2*L*HID) on the global feature, siren.py:550-553):
+ *   out = map_w [n_out, z_dim] . global_feature [B, z_dim] + map_b;  freq [B, n_out/2] = out[:, :n_out/2] * 15 + 30,
+ *   phase [B, n_out/2] = out[:, n_out/2:].  Fixed accumulation order per output: independent of the batch size. */
+CNG_API int cng_film_parameters(const float* global_feature, const float* map_w, const float* map_b, int B,
+                        int z_dim, int n_out, float* freq, float* phase, cng_stream_t stream);
+
 CNG_API size_t cng_film_siren_workspace_bytes(int B, int C, int HID, int L, int precision);
 CNG_API int cng_film_siren_fwd(const float* feat, int B, long long N, int C, int HID, int L,
                        const float* const* layer_w_host, const float* const* layer_b_host,

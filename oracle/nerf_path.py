@@ -68,6 +68,9 @@ SIREN_SPECS = {
     "SHORTSIREN_FG": {"layers": 4, "freq_init": 12.0, "sigmoid_rgb": True},
     "DOUBLESIREN_FG": {"layers": 2, "freq_init": 12.0, "sigmoid_rgb": True},
     "SingleSIREN_dg": {"layers": 1, "freq_init": 25.0, "sigmoid_rgb": False},
+    # generators/siren.py:830-904: feature volume only, plain SirenLayer = sin(W x + b) (:180-199), no mapping network;
+    # z is the feature volume itself (no global feature)
+    "SHORTSIREN_F": {"layers": 4, "freq_init": 12.0, "sigmoid_rgb": True, "film": False},
 }
 
 # configs/thousand/direct_volume/dg.py:8,51,55,59 spell the classes differently from
@@ -110,6 +113,8 @@ def init_generator_state(
         state[f"siren.network.{i}.layer.bias"] = uniform((hidden_dim,), 1.0 / math.sqrt(fan_in))
     state["siren.final_layer.weight"] = uniform((4, hidden_dim), math.sqrt(6.0 / hidden_dim) / spec["freq_init"])
     state["siren.final_layer.bias"] = uniform((4,), 1.0 / math.sqrt(hidden_dim))
+    if not spec.get("film", True):
+        return state
     n_map = spec["layers"] * hidden_dim * 2
     state["siren.mapping_network.weight"] = uniform((n_map, z_dim), 1.0 / math.sqrt(z_dim))
     state["siren.mapping_network.bias"] = uniform((n_map,), 1.0 / math.sqrt(z_dim))
@@ -297,9 +302,14 @@ def _split_state(state, siren_type):
 
 def siren_forward(state, siren_type, pts_world, z, img_size, num_steps):
     """``SIREN.forward(points, z, img_size, num_steps)`` for the FG family (siren.py:540-580)."""
-    volume, global_feature = z
     spec, ws, bs = _split_state(state, siren_type)
-    freq, phase = film_parameters(global_feature, state["siren.mapping_network.weight"], state["siren.mapping_network.bias"])
+    if spec.get("film", True):
+        volume, global_feature = z
+        freq, phase = film_parameters(global_feature, state["siren.mapping_network.weight"], state["siren.mapping_network.bias"])
+    else:
+        volume = z                                   # siren.py:867: forward(points, feature_volume, ...); sin(1 * x + 0) == sin(x)
+        n = spec["layers"] * ws[0].shape[0]
+        freq, phase = torch.ones((volume.shape[0], n)), torch.zeros((volume.shape[0], n))
     feat = trilinear_lookup(volume, pts_world, img_size, num_steps)
     return film_siren_mlp(feat, ws, bs, freq, phase, state["siren.final_layer.weight"],
                           state["siren.final_layer.bias"], spec["sigmoid_rgb"])

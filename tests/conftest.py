@@ -41,7 +41,7 @@ def load_golden(name):
     return out, meta
 
 
-FORWARD_FIXTURES = ["fwd_TALLSIREN_FG", "fwd_SHORTSIREN_FG", "fwd_DOUBLESIREN_FG", "fwd_SingleSIREN_dg"]
+FORWARD_FIXTURES = ["fwd_TALLSIREN_FG", "fwd_SHORTSIREN_FG", "fwd_DOUBLESIREN_FG", "fwd_SingleSIREN_dg", "fwd_SHORTSIREN_F"]
 
 
 def fixture_inputs(name):
@@ -54,7 +54,8 @@ def fixture_inputs(name):
     state = oracle.init_generator_state(siren_type, 256, 32, 256, seed=seed)
     checksum = sum(float(v.double().abs().sum()) for v in state.values())
     assert abs(checksum - float(fx["state/checksum"])) < 1e-9 * checksum, "torch CPU generator drifted"
-    z = (fx["in/volume"], fx["in/global"])
+    film = oracle.SIREN_SPECS[oracle.resolve_siren_type(siren_type)].get("film", True)
+    z = (fx["in/volume"], fx["in/global"]) if film else fx["in/volume"]      # unmodulated variants take the volume alone
     draws = {k[5:]: v for k, v in fx.items() if k.startswith("draw/")}
     taps = {k[4:]: v for k, v in fx.items() if k.startswith("tap/")}
     return state, siren_type, z, fx["in/cam2world"], draws, meta, taps

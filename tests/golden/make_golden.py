@@ -56,7 +56,8 @@ class Replay:
 
 def run_reference_forward(siren_type, state, z, cam, draws, meta):
     ref_name = oracle.resolve_siren_type(siren_type)
-    gen = ref_gen.ImplicitGenerator3d(ref_name, z_dim=z[1].shape[1], input_dim=z[0].shape[1], output_dim=4, hidden_dim=256)
+    vol0 = z[0] if isinstance(z, tuple) else z
+    gen = ref_gen.ImplicitGenerator3d(ref_name, z_dim=256, input_dim=vol0.shape[1], output_dim=4, hidden_dim=256)
     gen.load_state_dict(state, strict=True)
     gen.set_device(torch.device("cpu"))
     gen.eval()
@@ -134,7 +135,8 @@ def make_forward_fixture(siren_type, seed, hierarchical=True, clamp_mode="relu",
                 white_back=white_back, last_back=last_back,
                 # extra curriculum keys the generator must ignore (configs/thousand/default.py)
                 batch_size=B, gen_lr=5e-5, fade_steps=10000, z_lambda=0)
-    taps = run_reference_forward(siren_type, state, (vol, glob), cam, draws, meta)
+    film = oracle.SIREN_SPECS[oracle.resolve_siren_type(siren_type)].get("film", True)
+    taps = run_reference_forward(siren_type, state, (vol, glob) if film else vol, cam, draws, meta)
     # parameters are NOT stored (MBs): they are regenerated from the seed by
     # oracle.init_generator_state; a float64 checksum detects a drifting torch CPU generator.
     fx = {"state/checksum": np.array(sum(float(v.double().abs().sum()) for v in state.values()))}
@@ -208,6 +210,7 @@ def main():
     out["fwd_SHORTSIREN_FG"] = make_forward_fixture("SHORTSIREN_dg", 12, clamp_mode="softplus", nerf_noise=0.5, white_back=False, last_back=True)
     out["fwd_DOUBLESIREN_FG"] = make_forward_fixture("DoubleSIREN_dg", 13, hierarchical=False, white_back=True)
     out["fwd_SingleSIREN_dg"] = make_forward_fixture("SingleSIREN_dg", 14, nerf_noise=1.0)
+    out["fwd_SHORTSIREN_F"] = make_forward_fixture("SHORTSIREN_F", 15)
     out["functions"] = make_function_fixture()
     for name, fx in out.items():
         path = os.path.join(HERE, name + ".npz")

@@ -116,15 +116,19 @@ def test_film_sin_elementwise_halves(ops):
 
 def _oracle_grads(state, siren_type, z, cam, draws, meta, d_pix, d_dep):
     st = {k: v.clone().requires_grad_(True) for k, v in state.items()}
-    vol, glob = z[0].clone().requires_grad_(True), z[1].clone().requires_grad_(True)
-    out = oracle.render_with_grad(st, siren_type, (vol, glob), cam, draws, **meta)
+    film = isinstance(z, tuple)
+    vol = (z[0] if film else z).clone().requires_grad_(True)
+    glob = z[1].clone().requires_grad_(True) if film else None
+    out = oracle.render_with_grad(st, siren_type, (vol, glob) if film else vol, cam, draws, **meta)
     ((out["pixels"] * d_pix).sum() + (out["depth"] * d_dep).sum()).backward()
     grads = {k: v.grad for k, v in st.items()}
-    grads["volume"], grads["global"] = vol.grad, glob.grad
+    grads["volume"] = vol.grad
+    if film:
+        grads["global"] = glob.grad
     return out, grads
 
 
-@pytest.mark.parametrize("name", ["fwd_TALLSIREN_FG", "fwd_SHORTSIREN_FG", "fwd_DOUBLESIREN_FG", "fwd_SingleSIREN_dg"])
+@pytest.mark.parametrize("name", ["fwd_TALLSIREN_FG", "fwd_SHORTSIREN_FG", "fwd_DOUBLESIREN_FG", "fwd_SingleSIREN_dg", "fwd_SHORTSIREN_F"])
 def test_generator_backward_vs_oracle_autograd(name):
     """loss = <pixels, G1> + <depth, G2>; gradients w.r.t. every SIREN parameter, the volume and the global feature."""
     from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d
@@ -138,14 +142,18 @@ def test_generator_backward_vs_oracle_autograd(name):
     gen = gen.to("cuda")
     gen.set_device(torch.device("cuda"))
     gen.siren.precision = "fp32"
-    vol, glob = dev(z[0]).requires_grad_(True), dev(z[1]).requires_grad_(True)
-    pixels, depth = gen((vol, glob), dev(cam), draws={k: dev(v) for k, v in draws.items()}, **meta)
+    film = isinstance(z, tuple)
+    vol = dev(z[0] if film else z).requires_grad_(True)
+    glob = dev(z[1]).requires_grad_(True) if film else None
+    pixels, depth = gen((vol, glob) if film else vol, dev(cam), draws={k: dev(v) for k, v in draws.items()}, **meta)
     assert pixels.requires_grad and depth.requires_grad
     assert torch.allclose(pixels.detach().cpu(), ref_out["pixels"], atol=2e-3)
     ((pixels * dev(d_pix)).sum() + (depth * dev(d_dep)).sum()).backward()
     torch.cuda.synchronize()
     got = {"siren." + k: p.grad for k, p in gen.siren.named_parameters()}
-    got["volume"], got["global"] = vol.grad, glob.grad
+    got["volume"] = vol.grad
+    if film:
+        got["global"] = glob.grad
     worst = 0.0
     for k, r in ref.items():
         assert got[k] is not None, f"no gradient for {k}"

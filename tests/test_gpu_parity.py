@@ -27,6 +27,11 @@ def dev(t):
     return t.to("cuda")
 
 
+def dev_z(z):
+    """z = (volume, global) for the FiLM variants, the volume alone for the unmodulated ones."""
+    return tuple(dev(t) for t in z) if isinstance(z, tuple) else dev(z)
+
+
 # ------------------------------------------------------------------------------------------------
 # a4: layout + trilinear lookup
 # ------------------------------------------------------------------------------------------------
@@ -362,10 +367,11 @@ def _generator(siren_type, state, precision):
 def test_forward_vs_reference_golden(name, precision):
     state, siren_type, z, cam, draws, meta, taps = fixture_inputs(name)
     gen = _generator(siren_type, state, precision)
-    zc = (dev(z[0]), dev(z[1]))
+    zc = dev_z(z)
+    vol_d, glob_d = gen.siren.split_z(zc)
     d = {k: dev(v) for k, v in draws.items()}
     with torch.no_grad():
-        out = gen._render(zc[0], zc[1], dev(cam), meta["img_size"], meta["fov"], meta["ray_start"], meta["ray_end"],
+        out = gen._render(vol_d, glob_d, dev(cam), meta["img_size"], meta["fov"], meta["ray_start"], meta["ray_end"],
                           meta["num_steps"], meta["hierarchical_sample"], dict(meta, draws=d), taps=True)
         pixels, depth = gen(zc, dev(cam), draws=d, **meta)
     torch.cuda.synchronize()
@@ -374,6 +380,8 @@ def test_forward_vs_reference_golden(name, precision):
     assert pixels.shape == (B, 3, img, img) and depth.shape == (B, img, img) and pixels.is_contiguous()
     assert torch.allclose(out["points_coarse"].cpu(), taps["points_coarse"].reshape(B, -1, S, 3), rtol=0, atol=5e-7)
     mlp_tol = 5e-4 if precision == "fp32" else (3e-2 if ("SHORT" in name and precision == "bf16") else 1e-2)
+    if name == "fwd_SHORTSIREN_F" and precision == "bf16":
+        mlp_tol = 1e-2       # no freq ~ 30 in front of the pre-activations: bf16 operands are comfortably inside the bar
     err_c = (out["rgb_sigma_coarse"].cpu() - taps["rgb_sigma_coarse"].reshape(B, -1, S, 4)).abs().max().item()
     err_p = (pixels.cpu() - taps["pixels"]).abs().max().item()
     psnr_full = oracle.psnr(pixels.cpu(), taps["pixels"])
@@ -549,7 +557,12 @@ def test_config1_full_size_vs_oracle():
         pixels = out["pixels"].cpu()
         if precision == "fp32":
             assert torch.equal(out["t_coarse"].cpu(), ref["t_coarse"].squeeze(-1))
-            assert torch.equal(out["merge_order"].cpu().long(), ref["merge_order"].squeeze(-1)), "merge order differs at full size"
+            # merge order: bit-exact against a stable sort of the kernel's OWN distances (its t_fine differ from the oracle's by
+            # ulps of the coarse weights, so near-ties may legitimately swap relative to the oracle's order)
+            all_t = torch.cat([out["t_fine"].cpu().reshape(B, -1, S), out["t_coarse"].cpu()], dim=-1)
+            order = torch.sort(all_t, dim=-1, stable=True).indices
+            assert torch.equal(out["merge_order"].cpu().long(), order), "merge order differs from the stable sort at full size"
+            assert (out["merge_order"].cpu().long() != ref["merge_order"].squeeze(-1)).float().mean().item() < 1e-3
             # resampling indices: bit-exact when fed the kernel's own coarse weights (the oracle's differ in the last ulps)
             o_s, o_i, _, _ = oracle.coarse_to_fine_t(out["weights_coarse"].cpu().unsqueeze(-1), out["t_coarse"].cpu().unsqueeze(-1),
                                                      draws["u_resample"], S)
@@ -583,10 +596,24 @@ def test_config2_full_size_properties():
     assert torch.equal(a, b) and torch.equal(da, db)
     assert torch.isfinite(a).all() and torch.isfinite(da).all()
     assert float(a.min()) >= -1 - 1e-5 and float(a.max()) <= 1 + 1e-5
-    assert float(da.min()) >= 0 and float(da.max()) <= 1.95 + 1e-4
+    assert float(da.min()) >= 0 and float(da.max()) <= 1.95 + 0.5 * 1.7 / (S - 1) + 1e-4      # last sample jitters by up to half a spacing
     for i in (0, 5):
         di = {"u_jitter": d["u_jitter"][i:i + 1], "noise_coarse": d["noise_coarse"][i:i + 1],
               "u_resample": d["u_resample"][i * R:(i + 1) * R], "noise_final": d["noise_final"][i:i + 1]}
         with torch.no_grad():
             s, ds = gen((vol[i:i + 1], glob[i:i + 1]), cam[i:i + 1], draws=di, **meta)
         assert torch.equal(s[0], a[i]) and torch.equal(ds[0], da[i])
+
+
+def test_film_parameters_kernel(ops):
+    """a5: mapping network on the library's own kernel: matches the oracle and does not depend on the batch size."""
+    st = oracle.init_generator_state("TALLSIREN_FG", seed=3)
+    g = torch.Generator().manual_seed(4)
+    glob = torch.randn((8, 256), generator=g) * 0.05 + 0.19
+    w, b = st["siren.mapping_network.weight"], st["siren.mapping_network.bias"]
+    freq, phase = ops.film_parameters(dev(glob), dev(w), dev(b))
+    f_ref, p_ref = oracle.film_parameters(glob, w, b)
+    assert freq.shape == f_ref.shape and phase.shape == p_ref.shape
+    assert torch.allclose(freq.cpu(), f_ref, rtol=0, atol=2e-5) and torch.allclose(phase.cpu(), p_ref, rtol=0, atol=2e-6)
+    f1, p1 = ops.film_parameters(dev(glob[3:4]), dev(w), dev(b))
+    assert torch.equal(f1[0], freq[3]) and torch.equal(p1[0], phase[3])

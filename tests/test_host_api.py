@@ -116,3 +116,16 @@ def test_grad_mode_fails_loudly_until_backward_exists():
 
 def test_alias_classes():
     assert siren.TALLSIREN_dg is siren.TALLSIREN_FG and siren.DoubleSIREN_dg is siren.DOUBLESIREN_FG
+
+
+def test_unmodulated_variant_layout():
+    """SHORTSIREN_F (generators/siren.py:830-904): no mapping network, z is the feature volume alone."""
+    gen = ImplicitGenerator3d("SHORTSIREN_F", 256, 32, 4, 256)
+    ref_state = oracle.init_generator_state("SHORTSIREN_F")
+    assert set(gen.state_dict().keys()) == set(ref_state.keys())
+    assert not any("mapping_network" in k for k in ref_state)
+    gen.load_state_dict(ref_state, strict=True)
+    freq, phase = gen.siren.film_parameters(None, 3, "cpu")
+    assert freq.shape == (3, 4 * 256) and bool((freq == 1).all()) and bool((phase == 0).all())
+    with torch.no_grad(), pytest.raises(ValueError):
+        gen((torch.zeros(1, 32, 8, 8, 8), torch.zeros(1, 256)), torch.eye(4).unsqueeze(0), **META)
