@@ -127,24 +127,45 @@ __global__ void __launch_bounds__(256, 1) film_siren_simt_kernel(SimtParams p) {
 }
 
 // a5: FiLM parameters.  freq = 15 * (W g + b)[:half] + 30, phase = (W g + b)[half:]   (generators/siren.py:550-553).
-// One thread per output, fixed left-to-right fp32 accumulation over z_dim: the result for an item does not depend on how
-// many items are in the batch (cuBLAS picks batch-size-dependent kernels, which breaks that by an ulp).
+// One warp per output row: lanes stride over z_dim (coalesced weight reads), fixed shuffle-tree reduction, so the result
+// for an item does not depend on how many items are in the batch (cuBLAS picks batch-size-dependent kernels, which
+// breaks that by an ulp).  Items are processed in chunks of kFilmItems per block so a weight row is read once per chunk.
+constexpr int kFilmItems = 8;
 __global__ void __launch_bounds__(256) film_parameters_kernel(const float* __restrict__ glob, const float* __restrict__ w,
-                                                               const float* __restrict__ bias, int z_dim, int n_out,
+                                                               const float* __restrict__ bias, int B, int z_dim, int n_out,
                                                                float* __restrict__ freq, float* __restrict__ phase) {
-  extern __shared__ float g_s[];
-  const int b = blockIdx.y;
-  for (int k = threadIdx.x; k < z_dim; k += blockDim.x) g_s[k] = __ldg(glob + static_cast<size_t>(b) * z_dim + k);
+  extern __shared__ float g_s[];                       // [kFilmItems][z_dim]
+  const int b0 = blockIdx.y * kFilmItems;
+  const int nb = min(kFilmItems, B - b0);
+  for (int e = threadIdx.x; e < nb * z_dim; e += blockDim.x) g_s[e] = __ldg(glob + static_cast<size_t>(b0) * z_dim + e);
   __syncthreads();
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (o >= n_out) return;
   const float* wr = w + static_cast<size_t>(o) * z_dim;
-  float acc = 0.f;
-  for (int k = 0; k < z_dim; ++k) acc = fmaf(g_s[k], __ldg(wr + k), acc);
-  acc += __ldg(bias + o);
+  float acc[kFilmItems];
+#pragma unroll
+  for (int i = 0; i < kFilmItems; ++i) acc[i] = 0.f;
+  for (int k = lane; k < z_dim; k += 32) {
+    const float wv = __ldg(wr + k);
+#pragma unroll
+    for (int i = 0; i < kFilmItems; ++i)
+      if (i < nb) acc[i] = fmaf(g_s[i * z_dim + k], wv, acc[i]);
+  }
+  const float bv = __ldg(bias + o);
   const int half = n_out / 2;
-  if (o < half) freq[static_cast<size_t>(b) * half + o] = fmaf(acc, 15.f, 30.f);
-  else phase[static_cast<size_t>(b) * half + (o - half)] = acc;
+#pragma unroll
+  for (int i = 0; i < kFilmItems; ++i) {
+    if (i >= nb) break;
+    float v = acc[i];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    v += bv;
+    if (lane == 0) {
+      if (o < half) freq[static_cast<size_t>(b0 + i) * half + o] = fmaf(v, 15.f, 30.f);
+      else phase[static_cast<size_t>(b0 + i) * half + (o - half)] = v;
+    }
+  }
 }
 
 int film_siren_simt_launch(const float* feat, int B, long long N, int C, int HID, int L, const float* const* w,
@@ -171,11 +192,12 @@ int film_siren_simt_launch(const float* feat, int B, long long N, int C, int HID
 extern "C" int cng_film_parameters(const float* global_feature, const float* map_w, const float* map_b, int B, int z_dim, int n_out,
                                    float* freq, float* phase, cng_stream_t stream) {
   CNG_REQUIRE(B >= 0 && z_dim >= 1 && n_out >= 2 && n_out % 2 == 0, CNG_ERR_INVALID_ARGUMENT, "film_parameters: B=%d z_dim=%d n_out=%d", B, z_dim, n_out);
-  CNG_REQUIRE(z_dim <= 8192 && B <= 65535, CNG_ERR_UNSUPPORTED, "film_parameters: z_dim=%d B=%d", z_dim, B);
+  CNG_REQUIRE(z_dim <= 1024 && B <= 65535 * 8, CNG_ERR_UNSUPPORTED, "film_parameters: z_dim=%d B=%d", z_dim, B);
   if (B == 0) return CNG_OK;
   CNG_REQUIRE(global_feature && map_w && map_b && freq && phase, CNG_ERR_INVALID_ARGUMENT, "film_parameters: NULL pointer");
   if (int e = cng_device_check()) return e;
-  dim3 grid((n_out + 255) / 256, B);
-  cng::film_parameters_kernel<<<grid, 256, z_dim * sizeof(float), cng::as_stream(stream)>>>(global_feature, map_w, map_b, z_dim, n_out, freq, phase);
+  dim3 grid((n_out + 7) / 8, (B + cng::kFilmItems - 1) / cng::kFilmItems);
+  cng::film_parameters_kernel<<<grid, 256, static_cast<size_t>(cng::kFilmItems) * z_dim * sizeof(float), cng::as_stream(stream)>>>(
+      global_feature, map_w, map_b, B, z_dim, n_out, freq, phase);
   return cng::check_launch("cng_film_parameters");
 }
