@@ -54,6 +54,8 @@ __all__ = [
     "psnr",
     "far_plane_sigma",
     "render_with_grad",
+    "dense_grid_samples",
+    "video_camera_origins",
 ]
 
 # generators/siren.py:555 (and every other feature-volume variant): the voxel grid spans the
@@ -488,6 +490,47 @@ def far_plane_sigma(out: Dict[str, torch.Tensor], nerf_noise: float) -> torch.Te
     clamp_mode "softplus" (alpha_last == 1 always) or exclude those pixels and report their fraction.
     """
     return out["rgb_sigma_all"][:, :, -1, 3] + out["noise_final"][:, :, -1, 0] * nerf_noise
+
+
+def dense_grid_samples(N: int, voxel_origin=(0, 0, 0), cube_length: float = 2.0):
+    """extract_shapes.py:15-37 (create_samples): [1, N^3, 3] sample positions, z fastest; the x / y indices come from a
+    float division and are deliberately left non-integer, as in the reference."""
+    corner = np.array(voxel_origin) - cube_length / 2
+    voxel_size = cube_length / (N - 1)
+    idx = torch.arange(0, N ** 3, 1, dtype=torch.int64)
+    s = torch.zeros(N ** 3, 3)
+    s[:, 2] = idx % N
+    s[:, 1] = (idx.float() / N) % N
+    s[:, 0] = ((idx.float() / N) / N) % N
+    s[:, 0] = (s[:, 0] * voxel_size) + corner[2]
+    s[:, 1] = (s[:, 1] * voxel_size) + corner[1]
+    s[:, 2] = (s[:, 2] * voxel_size) + corner[0]
+    return s.unsqueeze(0), corner, voxel_size
+
+
+def video_camera_origins(num_frames: int, fps: int, r_start: float, r_end: float, up: str = "y"):
+    """inference.py:442-470: camera origins [F,3] (float32 tensor) and the fov ramp [F] of ``render_video``."""
+    theta0 = np.linspace(1e-5, np.pi / 2 - 1e-5, num_frames // 2)
+    phi0 = np.linspace(0, np.pi * 2, num_frames // 2)
+    theta1 = np.linspace(np.pi / 2 - 1e-5, 1e-5, num_frames // 4)
+    phi11 = np.linspace(np.pi * 2, np.pi * 5 / 4, fps)
+    phi12 = np.asarray([np.pi * 5 / 4] * (num_frames // 4 - fps))
+    theta21 = np.linspace(1e-5, np.pi / 4 - 1e-5, fps)
+    theta22 = np.asarray([np.pi / 4 - 1e-5] * (num_frames // 4 - fps))
+    phi2 = np.linspace(np.pi * 5 / 4, 0, num_frames // 4)
+    theta = np.concatenate([theta0, theta1, theta21, theta22], axis=0)
+    phi = np.concatenate([phi0, phi11, phi12, phi2], axis=0)
+    r = np.linspace(r_start, r_end, num_frames)
+    fov = np.linspace(60, 30, num_frames)
+    o = np.zeros((num_frames, 3))
+    o[:, 0] = r * np.sin(theta) * np.cos(phi)
+    if up == "z":
+        o[:, 1] = r * np.sin(theta) * np.sin(phi)
+        o[:, 2] = r * np.cos(theta)
+    else:
+        o[:, 2] = r * np.sin(theta) * np.sin(phi)
+        o[:, 1] = r * np.cos(theta)
+    return torch.from_numpy(o).type(torch.float32), fov
 
 
 def psnr(a: torch.Tensor, b: torch.Tensor, data_range: float = 2.0) -> float:

@@ -617,3 +617,48 @@ def test_film_parameters_kernel(ops):
     assert torch.allclose(freq.cpu(), f_ref, rtol=0, atol=2e-5) and torch.allclose(phase.cpu(), p_ref, rtol=0, atol=2e-6)
     f1, p1 = ops.film_parameters(dev(glob[3:4]), dev(w), dev(b))
     assert torch.equal(f1[0], freq[3]) and torch.equal(p1[0], phase[3])
+
+
+def test_sample_generator_sigma_grid():
+    """extract_shapes.sample_generator (extract_shapes.py:40-78): dense sigma grid through gen.siren, chunked."""
+    from conditioned_nerf_gan_b200 import extract_shapes
+    state, siren_type, z, cam, draws, meta, _ = fixture_inputs("fwd_TALLSIREN_FG")
+    gen = _generator(siren_type, state, "fp32")
+    N = 20
+    z1 = (z[0][:1], z[1][:1])
+    grid = extract_shapes.sample_generator(gen, dev_z(z1), voxel_resolution=N, cube_length=1.2, max_points=3000)
+    assert grid.shape == (N, N, N) and grid.dtype == np.float32
+    pts, _, _ = oracle.dense_grid_samples(N, (0, 0, 0), 1.2)
+    vol = z1[0]
+    feat = torch.nn.functional.grid_sample(vol, (pts / 0.6).reshape(1, 1, 1, -1, 3), mode="bilinear", align_corners=False,
+                                           padding_mode="border").reshape(1, 32, -1).permute(0, 2, 1)
+    spec, ws, bs = oracle._split_state(state, siren_type)
+    freq, phase = oracle.film_parameters(z1[1], state["siren.mapping_network.weight"], state["siren.mapping_network.bias"])
+    ref = oracle.film_siren_mlp(feat, ws, bs, freq, phase, state["siren.final_layer.weight"], state["siren.final_layer.bias"], True)
+    assert np.abs(grid.reshape(-1) - ref[0, :, 3].numpy()).max() < 5e-4
+
+
+def test_inference_drivers():
+    """generate_img (utils.py:60-82) and the video frame loop (inference.py:441-486) on staged_forward."""
+    from conditioned_nerf_gan_b200 import inference
+    state, siren_type, z, cam, draws, meta, _ = fixture_inputs("fwd_DOUBLESIREN_FG")
+    gen = _generator(siren_type, state, "fp32")
+    meta = dict(meta, nerf_noise=0.0, cam_r_start=0.9, cam_r_end=1.3, hierarchical_sample=True)
+    img, depth3 = inference.generate_img(gen, dev_z(z), dev(cam), {k: v for k, v in meta.items() if not k.startswith("cam_r")})
+    B = cam.shape[0]
+    assert img.device.type == "cpu" and img.shape == (B, 3, meta["img_size"], meta["img_size"])
+    assert depth3.shape == (B, 3, meta["img_size"], meta["img_size"]) and torch.equal(depth3[:, 0], depth3[:, 2])
+    z1 = (dev(z[0][:1]), dev(z[1][:1]))
+    torch.manual_seed(0)
+    frames = inference.render_video_frames(gen, z1, meta, num_frames=8, fps=2, max_batch_size=3)
+    assert frames.shape == (8, 3, meta["img_size"], meta["img_size"]) and frames.device.type == "cpu" and torch.isfinite(frames).all()
+    # frame k equals a direct forward with that pose and that fov
+    cam2world, fov = inference.video_camera_path(8, 2, 0.9, 1.3, "y", "cuda")
+    R, S = meta["img_size"] ** 2, meta["num_steps"]
+    d = {"u_jitter": torch.rand((1, R, S, 1), device="cuda"), "noise_coarse": torch.zeros((1, R, S, 1), device="cuda"),
+         "u_resample": torch.rand((R, S), device="cuda"), "noise_final": torch.zeros((1, R, 2 * S, 1), device="cuda")}
+    m = {kk: v for kk, v in meta.items() if kk not in ("fov", "cam_r_start", "cam_r_end")}
+    with torch.no_grad():
+        a, _ = gen(z1, cam2world[5:6], fov=float(fov[5]), draws=d, **m)
+        b, _ = gen.staged_forward(z1, cam2world[5:6], fov=[float(fov[5])], draws=d, **m)
+    assert torch.equal(a, b)

@@ -129,3 +129,24 @@ def test_unmodulated_variant_layout():
     assert freq.shape == (3, 4 * 256) and bool((freq == 1).all()) and bool((phase == 0).all())
     with torch.no_grad(), pytest.raises(ValueError):
         gen((torch.zeros(1, 32, 8, 8, 8), torch.zeros(1, 256)), torch.eye(4).unsqueeze(0), **META)
+
+
+def test_dense_grid_samples_match_oracle():
+    """extract_shapes.create_samples mirror: same order, same (quirky, non-integer x / y index) coordinates."""
+    from conditioned_nerf_gan_b200 import extract_shapes
+    for N, origin, length in ((8, (0, 0, 0), 2.0), (16, (0.1, -0.2, 0.0), 1.2)):
+        mine, corner, vs = extract_shapes.create_samples(N, origin, length)
+        ref, corner_ref, vs_ref = oracle.dense_grid_samples(N, origin, length)
+        assert torch.equal(mine, ref) and vs == vs_ref and (corner == corner_ref).all()
+    assert mine.shape == (1, 16 ** 3, 3)
+
+
+def test_video_camera_path_matches_oracle():
+    from conditioned_nerf_gan_b200 import inference
+    for up in ("y", "z"):
+        cam, fov = inference.video_camera_path(64, 8, 0.9, 1.3, up, "cpu")
+        o_ref, fov_ref = oracle.video_camera_origins(64, 8, 0.9, 1.3, up)
+        assert torch.equal(cam, oracle.look_at_cam2world(o_ref, up)) and (fov == fov_ref).all()
+        assert cam.shape == (64, 4, 4) and fov[0] == 60 and fov[-1] == 30
+    with pytest.raises(ValueError):
+        inference.video_camera_path(30, 8, 0.9, 1.3)
