@@ -662,3 +662,29 @@ def test_inference_drivers():
         a, _ = gen(z1, cam2world[5:6], fov=float(fov[5]), draws=d, **m)
         b, _ = gen.staged_forward(z1, cam2world[5:6], fov=[float(fov[5])], draws=d, **m)
     assert torch.equal(a, b)
+
+
+def test_cuda_graph_replay_matches_eager():
+    """graphs.GraphedRender: the captured forward replays to the same image as the eager call (replayed draws), also
+    after the inputs change."""
+    from conditioned_nerf_gan_b200.graphs import GraphedRender
+    state, siren_type, z, cam, draws, meta, _ = fixture_inputs("fwd_TALLSIREN_FG")
+    gen = _generator(siren_type, state, "bf16")
+    d = {k: dev(v) for k, v in draws.items()}
+    zc, camc = dev_z(z), dev(cam)
+    render = GraphedRender(gen, zc, camc, draws=d, **meta)
+    with torch.no_grad():
+        a, da = gen(zc, camc, draws=d, **meta)
+    b, db = render(zc, camc)
+    assert torch.equal(a, b) and torch.equal(da, db)
+    z2 = (zc[0] * 0.5, zc[1] + 0.01)
+    cam2 = camc.flip(0).contiguous()
+    with torch.no_grad():
+        a2, da2 = gen(z2, cam2, draws=d, **meta)
+    b2, db2 = render(z2, cam2)
+    assert torch.equal(a2, b2) and torch.equal(da2, db2) and not torch.equal(a2, a)
+    # without replayed draws the captured torch.rand / randn advance with every replay
+    render2 = GraphedRender(gen, zc, camc, **dict(meta, nerf_noise=0.0))
+    p1 = render2(zc, camc)[0].clone()
+    p2 = render2(zc, camc)[0].clone()
+    assert torch.isfinite(p1).all() and not torch.equal(p1, p2)
