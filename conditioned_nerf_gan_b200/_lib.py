@@ -10,7 +10,8 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_longlong, c_size_t, c_void_p
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libcng_b200.so")
+# CNG_LIB points at an alternative build of the same ABI (A/B experiments of kernel variants in one gpurun call)
+LIB_PATH = os.environ.get("CNG_LIB") or os.path.join(_PKG, "libcng_b200.so")
 
 CNG_OK = 0
 CLAMP_RELU, CLAMP_SOFTPLUS = 0, 1

@@ -44,8 +44,11 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu for sm_100a and link the shared library. Returns its path."""
+def build(force: bool = False, verbose: bool = False, out: str = None, extra_flags=()) -> str:
+    """Compile every .cu for sm_100a and link the shared library. Returns its path.
+    ``out`` / ``extra_flags`` build an experimental variant next to the default library (see _lib.CNG_LIB)."""
+    if out is not None:
+        return _build_variant(out, list(extra_flags), verbose)
     digest = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest:
         return LIB
@@ -74,6 +77,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with open(STAMP, "w") as f:
         f.write(digest)
     return LIB
+
+
+def _build_variant(out: str, extra_flags, verbose: bool) -> str:
+    nvcc = _nvcc()
+    tmp = os.path.join(CSRC, "_variant")
+    os.makedirs(tmp, exist_ok=True)
+    procs, objs = [], []
+    for s in SOURCES:
+        obj = os.path.join(tmp, s.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c", os.path.join(CSRC, s), "-o", obj]
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for s, pr in procs:
+        o, _ = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {s}:\n{o}")
+        if verbose and o:
+            print(o)
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, *objs], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}")
+    return out
 
 
 if __name__ == "__main__":
