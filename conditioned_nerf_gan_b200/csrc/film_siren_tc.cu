@@ -49,6 +49,9 @@
 #ifndef CNG_TC_EPI_PIPELINE
 #define CNG_TC_EPI_PIPELINE 0
 #endif
+#ifndef CNG_TC_EPI_GROUPED
+#define CNG_TC_EPI_GROUPED 0
+#endif
 
 namespace cng {
 
@@ -360,17 +363,30 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
             copy_out(p.dump_g);
             return;
           }
+          // 32 columns = 64 bytes = 4 x 16-byte chunks of K-block cc/2, logical chunk (cc&1)*4 + i
+          uint8_t* blk = smem + a_base + (cc >> 1) * kABlockBytes + row * 128;
+#if CNG_TC_EPI_GROUPED
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {                 // one chunk (8 sines, 4 packs, 1 store) at a time
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 8; j += 2)
+              o[j / 2] = pack2<kHalf>(film_sin<kPolyOneIn>(__uint_as_float(v[8 * i + j]), 8 * i + j),
+                                      film_sin<kPolyOneIn>(__uint_as_float(v[8 * i + j + 1]), 8 * i + j + 1));
+            const int chunk = ((cc & 1) * 4 + i) ^ (row & 7);
+            *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+#else
           uint32_t o[16];
 #pragma unroll
           for (int j = 0; j < 32; j += 2)
             o[j / 2] = pack2<kHalf>(film_sin<kPolyOneIn>(__uint_as_float(v[j]), j), film_sin<kPolyOneIn>(__uint_as_float(v[j + 1]), j + 1));
-          // 32 columns = 64 bytes = 4 x 16-byte chunks of K-block cc/2, logical chunk (cc&1)*4 + i
-          uint8_t* blk = smem + a_base + (cc >> 1) * kABlockBytes + row * 128;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int chunk = ((cc & 1) * 4 + i) ^ (row & 7);
             *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
           }
+#endif
         };
         if constexpr (kEpiWarpsPerSlot == 4 || CNG_TC_EPI_PIPELINE) {
           // keep the TMEM load of block i+1 in flight under the sines of block i (needs 2 x 32 accumulator registers)

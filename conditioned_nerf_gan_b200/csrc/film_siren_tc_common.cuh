@@ -7,6 +7,10 @@
 
 #include "cng_common.cuh"
 
+#ifndef CNG_MBAR_HINT_NS
+#define CNG_MBAR_HINT_NS 20000     // suspend-time hint of mbarrier.try_wait (A/B knob)
+#endif
+
 namespace cng {
 
 constexpr int kHID = 256;
@@ -57,7 +61,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(20000u)
+        : "r"(bar), "r"(parity), "r"(static_cast<uint32_t>(CNG_MBAR_HINT_NS))
         : "memory");
     if (ok) break;
     if ((it & 63u) == 63u) {
