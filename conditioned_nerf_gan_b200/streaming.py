@@ -43,8 +43,14 @@ def render_host_batches(generator, batches: Iterable[Sequence[torch.Tensor]], me
     it = iter(batches)
 
     def stage(slot: _Slot, batch) -> None:
+        # persistent device buffers per slot (no allocator traffic in steady state); the kernels that last read them
+        # must be done before they are overwritten
+        if slot.inputs is None or any(d.shape != h.shape or d.dtype != h.dtype for d, h in zip(slot.inputs, batch)):
+            slot.inputs = tuple(torch.empty(h.shape, dtype=h.dtype, device=device) for h in batch)
+        copy_in.wait_event(slot.compute_done)
         with torch.cuda.stream(copy_in):
-            slot.inputs = tuple(t.to(device, non_blocking=True) for t in batch)
+            for d, h in zip(slot.inputs, batch):
+                d.copy_(h, non_blocking=True)
             slot.h2d_done.record(copy_in)
 
     def take(slot: _Slot):
@@ -65,12 +71,9 @@ def render_host_batches(generator, batches: Iterable[Sequence[torch.Tensor]], me
                 yield take(nslot)
             stage(nslot, nxt)
         compute.wait_event(slot.h2d_done)
-        for t in slot.inputs:
-            t.record_stream(compute)
         vol, glob, cam = slot.inputs
         pixels, dep = generator((vol, glob), cam, **metadata)
         slot.compute_done.record(compute)
-        slot.inputs = None
         copy_out.wait_event(slot.compute_done)
         with torch.cuda.stream(copy_out):
             if slot.pixels_h is None or slot.pixels_h.shape != pixels.shape:

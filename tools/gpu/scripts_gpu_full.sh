@@ -8,6 +8,9 @@ timeout 600 python bench.py --steps 20 --warmup 5 --precision fp16 --no-cpu-base
 timeout 600 python bench.py --workload train --steps 4 --warmup 3 > gpurun_out/bench_train.log 2>&1; echo "train exit $?" >> gpurun_out/summary.txt
 timeout 600 python bench.py --workload video --steps 4 --warmup 3 > gpurun_out/bench_video.log 2>&1; echo "video exit $?" >> gpurun_out/summary.txt
 timeout 200 python tools/trace_tc.py 1 > gpurun_out/trace1.log 2>&1
+timeout 600 python tools/bench_c5.py --json gpurun_out/c5.json > gpurun_out/c5.log 2>&1; echo "c5 exit $?" >> gpurun_out/summary.txt
+timeout 300 python tools/profile_train.py 4 > gpurun_out/profile_train.log 2>&1; echo "profile_train exit $?" >> gpurun_out/summary.txt
+timeout 300 python tools/bench_graph.py > gpurun_out/graph.log 2>&1
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/plain.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
