@@ -290,9 +290,16 @@ def run_gpu(args):
     ms_e2e = min(e2e_passes)
 
     # ---- roofline leg: per-entry-point CUDA-event durations over an instrumented pass of the same steps
+    # (the timed steps above go through the one-call cng_render_fwd; here the same kernels are launched entry point by entry
+    # point so that each one can be bracketed by events)
+    def step_by_stage():
+        with torch.no_grad():
+            return gen((vol, glob), cam, fused_call=False, **meta)
+
+    step_by_stage()
     ops.kernel_events = {}
     for _ in range(args.steps):
-        step_resident()
+        step_by_stage()
     torch.cuda.synchronize()
     per_kernel = {k: [s.elapsed_time(e) for s, e in v] for k, v in ops.kernel_events.items()}
     ops.kernel_events = None

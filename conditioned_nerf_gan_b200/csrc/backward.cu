@@ -33,6 +33,8 @@ struct CompositeBwdParams {
   const float* rays_d_cam;       // [R, 3]
   const float* d_pixels;         // [B, 3, R] or NULL
   const float* d_depth;          // [B, R] or NULL
+  const float* d_rgb;            // un-formatted gradients (plain fancy_integration backward): [n_rays, 3] or NULL
+  const float* d_dist;           // [n_rays] or NULL
   long long n_rays;
   int S, n, R;
   float noise_std;
@@ -73,6 +75,8 @@ __global__ void __launch_bounds__(kBwdWarps * 32) composite_bwd_kernel(Composite
     g0 = 2.f * __ldg(dp); g1 = 2.f * __ldg(dp + p.R); g2 = 2.f * __ldg(dp + 2 * static_cast<size_t>(p.R));
   }
   if (p.d_depth) gd = __ldg(p.d_depth + ray) * __ldg(p.rays_d_cam + 3 * r + 2);
+  if (p.d_rgb) { g0 = __ldg(p.d_rgb + ray * 3); g1 = __ldg(p.d_rgb + ray * 3 + 1); g2 = __ldg(p.d_rgb + ray * 3 + 2); }
+  if (p.d_dist) gd = __ldg(p.d_dist + ray);
   const float gsum = g0 + g1 + g2;
 
   float alpha[IPL], fac[IPL], e1[IPL], dl[IPL], pre[IPL], G[IPL];
@@ -386,6 +390,30 @@ int cng_merge_composite_bwd(const float* rgb_sigma_fine, const float* rgb_sigma_
   else if (ipl <= 8) cng::launch_cbwd<8>(p, st);
   else cng::launch_cbwd<16>(p, st);
   return cng::check_launch("cng_merge_composite_bwd");
+}
+
+int cng_composite_bwd(const float* rgb_sigma, const float* t, const float* noise, const float* d_rgb, const float* d_dist, long long n_rays,
+                      int S, float noise_std, int clamp_mode, int white_back, int last_back, float* d_rgb_sigma, cng_stream_t stream) {
+  CNG_REQUIRE(n_rays >= 0 && S >= 1, CNG_ERR_INVALID_ARGUMENT, "composite_bwd: n_rays=%lld S=%d", n_rays, S);
+  CNG_REQUIRE(S <= 512, CNG_ERR_UNSUPPORTED, "composite_bwd: S=%d > 512", S);
+  if (n_rays == 0) return CNG_OK;
+  CNG_REQUIRE(rgb_sigma && t && d_rgb_sigma, CNG_ERR_INVALID_ARGUMENT, "composite_bwd: NULL pointer");
+  CNG_REQUIRE(clamp_mode == CNG_CLAMP_RELU || clamp_mode == CNG_CLAMP_SOFTPLUS, CNG_ERR_INVALID_ARGUMENT, "composite_bwd: Need to choose clamp mode");
+  CNG_REQUIRE(noise_std == 0.f || noise, CNG_ERR_INVALID_ARGUMENT, "composite_bwd: noise_std != 0 needs noise");
+  CNG_REQUIRE(n_rays / cng::kBwdWarps < 0x7fffffffLL, CNG_ERR_UNSUPPORTED, "composite_bwd: too many rays");
+  if (int e = cng_device_check()) return e;
+  cng::CompositeBwdParams p{};
+  p.rgb_sigma = rgb_sigma; p.t = t; p.noise = (noise_std != 0.f) ? noise : nullptr; p.d_rgb = d_rgb; p.d_dist = d_dist;
+  p.n_rays = n_rays; p.S = S; p.n = S; p.R = 1; p.noise_std = noise_std; p.clamp_mode = clamp_mode;
+  p.white_back = white_back; p.last_back = last_back; p.d_rgb_sigma = d_rgb_sigma;
+  const int ipl = (S + 31) / 32;
+  cudaStream_t st = cng::as_stream(stream);
+  if (ipl <= 1) cng::launch_cbwd<1>(p, st);
+  else if (ipl <= 2) cng::launch_cbwd<2>(p, st);
+  else if (ipl <= 4) cng::launch_cbwd<4>(p, st);
+  else if (ipl <= 8) cng::launch_cbwd<8>(p, st);
+  else cng::launch_cbwd<16>(p, st);
+  return cng::check_launch("cng_composite_bwd");
 }
 
 int cng_scatter_points(float* dvol_ndhwc, int B, int C, int D, int H, int W, const float* points, long long N,

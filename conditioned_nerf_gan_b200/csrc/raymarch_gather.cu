@@ -21,6 +21,10 @@
 //   w_lo = (i0 + 1) - i, w_hi = i - i0;  corners accumulated in ATen's order tnw..bse.
 #include "cng_common.cuh"
 
+#ifndef CNG_K1_MIN_BLOCKS
+#define CNG_K1_MIN_BLOCKS 3     // resident blocks per SM the register allocation aims at (A/B knob)
+#endif
+
 namespace cng {
 
 constexpr int kLanesPerPoint = 8;
@@ -168,7 +172,7 @@ __device__ __forceinline__ CornerRec shfl_record(const CornerRec& r, int src) {
 // per point (it used to be repeated by the 8 lanes that share a point).  Phase B: 8 rounds, each serving 4 of the
 // warp's 32 points with 8 lanes x float4 per point; the corner record travels by warp shuffle.
 template <bool FINE>
-__global__ void __launch_bounds__(256) raymarch_gather_kernel(RayParams p) {
+__global__ void __launch_bounds__(256, CNG_K1_MIN_BLOCKS) raymarch_gather_kernel(RayParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
   int ray;

@@ -12,6 +12,8 @@ is five kernel launches per SIREN pass instead of ~100 eager ATen kernels:
     K2  cng_film_siren_fwd           fine pass
     K3' cng_merge_composite          merge by depth + composite + NCHW image + depth (a11, a8, a12)
 
+sequenced by ONE C-ABI call, ``cng_render_fwd`` (the stage-by-stage path remains for the taps the tests compare).
+
 Random draws are made with ``torch.rand`` / ``torch.randn`` on the device in the reference's order
 and shapes (rand[B,R,S,1], randn[B,R,S,1], rand[B*R,S], randn[B,R,2S,1]), or taken
 from the optional ``draws`` keyword (a dict with keys u_jitter, noise_coarse, u_resample,
@@ -86,6 +88,23 @@ class ImplicitGenerator3d(nn.Module):
         def draw(name, fn, shape):
             t = draws.get(name)
             return fn(shape, device=dev) if t is None else t.to(dev)
+
+        if not taps and kwargs.get("fused_call", True):
+            # production path: one C-ABI call (cng_render_fwd) sequences K1, K2, K3, K4, K1', K2, K3'; draws in the reference's order
+            u_jitter = draw("u_jitter", torch.rand, (B, R, S, 1))
+            ws, bs = net.layer_parameters()
+            if hierarchical_sample:
+                noise_c = draw("noise_coarse", torch.randn, (B, R, S, 1))
+                u_re = draw("u_resample", torch.rand, (B * R, S))
+                noise_f = draw("noise_final", torch.randn, (B, R, 2 * S, 1))
+            else:
+                noise_c, u_re = None, None
+                noise_f = draw("noise_final" if "noise_final" in draws else "noise_coarse", torch.randn, (B, R, S, 1))
+            out["pixels"], out["depth"] = ops.render_fwd(vol_cl, cam2worlds, rays_d_cam, t_lin, ws, bs, freq, phase, net.final_layer.weight,
+                                                         net.final_layer.bias, net.sigmoid_rgb, net.precision, u_jitter, noise_c, u_re,
+                                                         noise_f, img_size, img_size, hierarchical_sample, nerf_noise, clamp_mode,
+                                                         white_back, last_back)
+            return out
 
         u_jitter = draw("u_jitter", torch.rand, (B, R, S, 1))
         feat_c, t_c, pts_c = ops.raymarch_gather_coarse(vol_cl, cam2worlds, rays_d_cam, t_lin, u_jitter, img_size,

@@ -103,8 +103,31 @@ def fancy_integration(rgb_sigma, z_vals, device, noise_std=0.5, last_back=False,
     ops.clamp_code(clamp_mode)    # TypeError("Need to choose clamp mode") before anything is drawn
     if noise is None:
         noise = torch.randn(z_vals.shape, device=rgb_sigma.device)
-    rgb, dist, w = ops.composite_fwd(rgb_sigma, z_vals, noise, noise_std, clamp_mode, white_back, last_back)
+    if torch.is_grad_enabled() and rgb_sigma.requires_grad:
+        rgb, dist, w = _CompositeFn.apply(rgb_sigma, z_vals, noise, noise_std, clamp_mode, white_back, last_back)
+    else:
+        rgb, dist, w = ops.composite_fwd(rgb_sigma, z_vals, noise, noise_std, clamp_mode, white_back, last_back)
     return rgb, dist.unsqueeze(-1), w.unsqueeze(-1)
+
+
+class _CompositeFn(torch.autograd.Function):
+    """fancy_integration with gradients to rgb_sigma (cng_composite_bwd); the returned weights are not differentiable
+    (the generator only uses them under no_grad, generators.py:111-121)."""
+
+    @staticmethod
+    def forward(ctx, rgb_sigma, z_vals, noise, noise_std, clamp_mode, white_back, last_back):
+        rgb, dist, w = ops.composite_fwd(rgb_sigma, z_vals, noise, noise_std, clamp_mode, white_back, last_back)
+        ctx.save_for_backward(rgb_sigma, z_vals, noise)
+        ctx.cfg = (noise_std, clamp_mode, white_back, last_back)
+        ctx.mark_non_differentiable(w)
+        return rgb, dist, w
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_dist, _d_w):
+        rgb_sigma, z_vals, noise = ctx.saved_tensors
+        noise_std, clamp_mode, white_back, last_back = ctx.cfg
+        d = ops.composite_bwd(rgb_sigma, z_vals, noise, d_rgb, d_dist, noise_std, clamp_mode, white_back, last_back)
+        return d, None, None, None, None, None, None
 
 
 def sample_pdf(bins, weights, N_importance, det=False, eps=1e-5, u=None, return_inds=False):

@@ -418,3 +418,70 @@ def film_grad_from_g(dy_bf16, g_bf16, colsum) -> torch.Tensor:
         _lib.call("cng_film_grad_from_g", _ptr(dy_bf16), _ptr(g_bf16), P, HID, _ptr(dz), _ptr(colsum), _stream(dy_bf16))
     _count()
     return dz
+
+
+def composite_bwd(rgb_sigma, t, noise, d_rgb, d_dist, noise_std: float, clamp_mode, white_back=False, last_back=False) -> torch.Tensor:
+    """Backward of composite_fwd w.r.t. rgb_sigma: d_rgb [..., 3] and / or d_dist [...] (None allowed) -> [..., S, 4]."""
+    code = clamp_code(clamp_mode)
+    rgb_sigma = _f32(rgb_sigma, "rgb_sigma")
+    S = rgb_sigma.shape[-2]
+    n_rays = rgb_sigma.numel() // (4 * S)
+    t = _f32(t, "t").reshape(n_rays, S)
+    noise = _f32(noise, "noise").reshape(n_rays, S) if (noise is not None and noise_std != 0) else None
+    d_rgb = _f32(d_rgb, "d_rgb").reshape(n_rays, 3) if d_rgb is not None else None
+    d_dist = _f32(d_dist, "d_dist").reshape(n_rays) if d_dist is not None else None
+    out = torch.empty_like(rgb_sigma)
+    with torch.cuda.device(rgb_sigma.device), _timed("cng_composite_bwd"):
+        _lib.call("cng_composite_bwd", _ptr(rgb_sigma), _ptr(t), _ptr(noise), _ptr(d_rgb), _ptr(d_dist), n_rays, S, float(noise_std), code,
+                  int(bool(white_back)), int(bool(last_back)), _ptr(out), _stream(rgb_sigma))
+    _count()
+    return out
+
+
+def render_fwd(vol_cl, cam2world, rays_d_cam, t_lin, layer_w, layer_b, freq, phase, final_w, final_b, sigmoid_rgb, precision,
+               u_jitter, noise_coarse, u_resample, noise_final, img_w, img_h, hierarchical, noise_std, clamp_mode,
+               white_back=False, last_back=False):
+    """The whole forward in one C-ABI call (cng_render_fwd).  Returns pixels [B,3,H,W], depth [B,H,W]."""
+    if precision not in PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
+    code = clamp_code(clamp_mode)
+    vol_cl = _f32(vol_cl, "vol_ndhwc")
+    Bv, D, H, W, C = vol_cl.shape
+    cam2world, rays_d_cam, t_lin = _f32(cam2world, "cam2world"), _f32(rays_d_cam, "rays_d_cam"), _f32(t_lin, "t_lin")
+    B, S, R = cam2world.shape[0], t_lin.numel(), img_w * img_h
+    if Bv not in (1, B):
+        raise ValueError(f"cam2world {tuple(cam2world.shape)} does not match volume batch {Bv}")
+    stride = 0 if (Bv == 1 and B > 1) else C * D * H * W
+    L = len(layer_w)
+    ws = [_f32(w, f"layer_w[{i}]") for i, w in enumerate(layer_w)]
+    bs = [_f32(b, f"layer_b[{i}]") for i, b in enumerate(layer_b)]
+    HID = ws[0].shape[0]
+    freq, phase, final_w, final_b = _f32(freq, "freq"), _f32(phase, "phase"), _f32(final_w, "final_w"), _f32(final_b, "final_b")
+    if freq.shape != (B, L * HID) or phase.shape != (B, L * HID):
+        raise ValueError(f"freq/phase must be [B={B}, L*HID={L * HID}]")
+    u_jitter = _f32(u_jitter, "u_jitter") if u_jitter is not None else None
+    use_noise = noise_std != 0
+    noise_coarse = _f32(noise_coarse, "noise_coarse") if (use_noise and noise_coarse is not None) else None
+    noise_final = _f32(noise_final, "noise_final") if (use_noise and noise_final is not None) else None
+    u_resample = _f32(u_resample, "u_resample") if hierarchical else None
+    for name, t, n in (("u_jitter", u_jitter, B * R * S), ("noise_coarse", noise_coarse, B * R * S), ("u_resample", u_resample, B * R * S),
+                       ("noise_final", noise_final, B * R * S * (2 if hierarchical else 1))):
+        if t is not None and t.numel() != n:
+            raise ValueError(f"{name} must hold {n} draws, got {t.numel()}")
+    dev = vol_cl.device
+    pcode = PRECISIONS[precision]
+    lib = _lib.load()
+    ws_bytes = int(lib.cng_render_workspace_bytes(B, img_w, img_h, S, C, HID, L, int(bool(hierarchical)), pcode))
+    workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    pixels = torch.empty((B, 3, img_h, img_w), dtype=torch.float32, device=dev)
+    depth = torch.empty((B, img_h, img_w), dtype=torch.float32, device=dev)
+    w_arr = (ctypes.c_void_p * L)(*[w.data_ptr() for w in ws])
+    b_arr = (ctypes.c_void_p * L)(*[b.data_ptr() for b in bs])
+    with torch.cuda.device(dev), _timed("cng_render_fwd"):
+        _lib.call("cng_render_fwd", _ptr(vol_cl), stride, B, C, D, H, W, _ptr(cam2world), _ptr(rays_d_cam), _ptr(t_lin), img_w, img_h, S,
+                  HID, L, w_arr, b_arr, _ptr(freq), _ptr(phase), _ptr(final_w), _ptr(final_b), int(bool(sigmoid_rgb)), pcode,
+                  _ptr(u_jitter), _ptr(noise_coarse), _ptr(u_resample), _ptr(noise_final), int(bool(hierarchical)), float(noise_std), code,
+                  int(bool(white_back)), int(bool(last_back)), _ptr(workspace), ws_bytes, _ptr(pixels), _ptr(depth), _stream(vol_cl))
+    n_mlp = 1 if pcode == _lib.PREC_FP32 else 2
+    _count((2 + 2 * n_mlp + 3) if hierarchical else (2 + n_mlp))
+    return pixels, depth

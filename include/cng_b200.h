@@ -212,6 +212,12 @@ CNG_API int cng_merge_composite_bwd(const float* rgb_sigma_fine, const float* rg
                             int last_back, float* d_rgb_sigma_fine, float* d_rgb_sigma_coarse,
                             cng_stream_t stream);
 
+/* Backward of cng_composite_fwd (plain fancy_integration, volumetric_rendering.py:18-70): d_rgb [n_rays, 3] and / or
+ * d_dist [n_rays] (either may be NULL; the `weights` output carries no gradient here) -> d_rgb_sigma [n_rays, S, 4]. */
+CNG_API int cng_composite_bwd(const float* rgb_sigma, const float* t, const float* noise, const float* d_rgb,
+                      const float* d_dist, long long n_rays, int S, float noise_std, int clamp_mode,
+                      int white_back, int last_back, float* d_rgb_sigma, cng_stream_t stream);
+
 /* Backward of the trilinear lookup w.r.t. the volume (F.grid_sample backward, siren.py:555-571):
  * dvol_ndhwc [B,D,H,W,C] += trilinear weights * dfeat [B,N,C] at points [B,N,3] (vector
  * red.global.add).  The caller zero-fills dvol_ndhwc first. */
@@ -232,6 +238,27 @@ CNG_API int cng_film_sin_apply(const float* z, const float* bias, const float* f
 CNG_API int cng_film_sin_grad(const void* dy_bf16, const float* z, const float* bias, const float* freq,
                       const float* phase, long long P, int HID, void* dz_bf16, float* dfreq,
                       float* dphase, cng_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The whole forward of ImplicitGenerator3d.forward (generators/generators.py:33-187) in one call: K1 coarse, K2, K3,
+ * K4, K1 fine, K2, K3' sequenced on `stream` with every intermediate in `workspace`
+ * (cng_render_workspace_bytes, 256-byte aligned).  Inputs: the NDHWC volume (vol_item_stride as in
+ * cng_raymarch_gather_coarse), the camera tables, the SIREN parameters with freq / phase from cng_film_parameters,
+ * and the four random draws of the reference in its order: u_jitter [B,R,S], noise_coarse [B,R,S] (or NULL),
+ * u_resample [B*R,S], noise_final [B,R,2S] (or NULL; [B,R,S] when hierarchical == 0).
+ * Outputs: pixels [B,3,img_h,img_w], depth [B,img_h,img_w].
+ * ---------------------------------------------------------------------------------------- */
+CNG_API size_t cng_render_workspace_bytes(int B, int img_w, int img_h, int S, int C, int HID, int L,
+                                  int hierarchical, int precision);
+CNG_API int cng_render_fwd(const float* vol_ndhwc, long long vol_item_stride, int B, int C, int D, int H, int W,
+                   const float* cam2world, const float* rays_d_cam, const float* t_lin, int img_w,
+                   int img_h, int S, int HID, int L, const float* const* layer_w_host,
+                   const float* const* layer_b_host, const float* freq, const float* phase,
+                   const float* final_w, const float* final_b, int sigmoid_rgb, int precision,
+                   const float* u_jitter, const float* noise_coarse, const float* u_resample,
+                   const float* noise_final, int hierarchical, float noise_std, int clamp_mode,
+                   int white_back, int last_back, void* workspace, size_t workspace_bytes,
+                   float* pixels, float* depth, cng_stream_t stream);
 
 /* Training-mode forward of K2 for the backward's activation recompute: the same fused tcgen05 kernel (bf16
  * operands) that ALSO streams, for every FiLM layer l, its output x_{l+1} = sin(u_l) and its local derivative

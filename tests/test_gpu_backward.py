@@ -199,3 +199,27 @@ def test_backward_with_channels_last_3d_volume():
         (pixels.sum() + depth.sum()).backward()
         grads.append(vol.grad.contiguous())
     assert torch.allclose(grads[0], grads[1], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("S,clamp,noise_std,white,last", [(12, "relu", 0.0, True, False), (48, "softplus", 0.4, False, True), (100, "relu", 0.2, True, True)])
+def test_fancy_integration_autograd(S, clamp, noise_std, white, last):
+    """volumetric_rendering.fancy_integration with gradients (cng_composite_bwd) against autograd through the oracle."""
+    from conditioned_nerf_gan_b200.generators import volumetric_rendering as vr
+    g = torch.Generator().manual_seed(S)
+    B, R = 2, 37
+    rs = torch.randn((B, R, S, 4), generator=g)
+    rs[..., :3] = torch.sigmoid(rs[..., :3])
+    rs[..., 3] *= 3
+    t = torch.sort(torch.rand((B, R, S, 1), generator=g) * 1.7 + 0.25, dim=2).values
+    noise = torch.randn((B, R, S, 1), generator=g)
+    g_rgb, g_dist = torch.randn((B, R, 3), generator=g), torch.randn((B, R, 1), generator=g)
+    r_ref = rs.clone().requires_grad_(True)
+    rgb, dist, _ = oracle.composite(r_ref, t, noise, noise_std, clamp, white, last)
+    ((rgb * g_rgb).sum() + (dist * g_dist).sum()).backward()
+    r_dev = dev(rs).requires_grad_(True)
+    rgb_d, dist_d, w_d = vr.fancy_integration(r_dev, dev(t), "cuda", noise_std=noise_std, last_back=last, white_back=white, clamp_mode=clamp,
+                                              noise=dev(noise))
+    assert not w_d.requires_grad
+    ((rgb_d * dev(g_rgb)).sum() + (dist_d * dev(g_dist)).sum()).backward()
+    scale = float(r_ref.grad.abs().max())
+    assert torch.allclose(r_dev.grad.cpu(), r_ref.grad, rtol=2e-4, atol=2e-5 * max(scale, 1.0))
