@@ -54,16 +54,21 @@ int cng_abi_version(void) { return CNG_ABI_VERSION; }
 const char* cng_last_error(void) { return cng::g_err; }
 
 int cng_device_check(void) {
+  // the verdict per device ordinal is cached after the first successful check (it is asked before every launch)
+  static bool ok_cache[64] = {};
+  int dev = -1;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && ok_cache[dev]) return CNG_OK;
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0) {
     cudaGetLastError();
     return cng::fail(CNG_ERR_NO_DEVICE, "no CUDA device visible (%s)", e == cudaSuccess ? "count == 0" : cudaGetErrorString(e));
   }
-  int dev = 0, major = 0;
+  int major = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
   if (major != 10) return cng::fail(CNG_ERR_NO_DEVICE, "device %d is sm_%d0, kernels are built for sm_100a only", dev, major);
+  if (dev >= 0 && dev < 64) ok_cache[dev] = true;
   return CNG_OK;
 }
 

@@ -26,7 +26,7 @@ from .. import ops
 from .volumetric_rendering import camera_tables
 
 HAS_BACKWARD = True
-CHUNK_ROWS = 1 << 19          # points per recompute chunk of the MLP backward (~6.5 GB of temporaries at L = 8)
+CHUNK_ROWS = 1 << 20          # points per recompute chunk of the MLP backward (~8.6 GB of x / g dumps at L = 8)
 
 
 class _ToChannelsLast(torch.autograd.Function):
