@@ -15,7 +15,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libcng_b200.so")
 STAMP = os.path.join(PKG, "csrc", ".build_stamp")
-SOURCES = ["cng_api.cu", "raymarch_gather.cu", "film_siren_simt.cu", "film_siren_tc.cu", "film_siren_tc2.cu", "composite.cu", "sample_pdf.cu", "backward.cu", "render.cu"]
+SOURCES = ["cng_api.cu", "raymarch_gather.cu", "film_siren_simt.cu", "film_siren_tc.cu", "film_siren_tc2.cu", "film_siren_tc3.cu", "composite.cu", "sample_pdf.cu", "backward.cu", "render.cu"]
 # CNG_TC_EPI_WARPS (4 or 8): epilogue warps per tile slot of the one-CTA-per-SM tcgen05 kernel (film_siren_tc.cu)
 EPI_WARPS = os.environ.get("CNG_TC_EPI_WARPS", "8")
 EPI_PIPELINE = os.environ.get("CNG_TC_EPI_PIPELINE", "0")    # 1: double-buffer the epilogue's TMEM loads

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32) composite_bwd_kernel(Composite
   const int n = p.n, S = p.S;
   const bool two = p.rgb_sigma_fine != nullptr;
   const int n2 = next_pow2_min32(n);
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem) + static_cast<size_t>(warp) * n2;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem) + static_cast<size_t>(warp) * merge_smem_words(n, S);
   load_and_sort_ray(keys, two ? p.t_fine : nullptr, p.t, ray, S, n, n2, lane);
 
   const long long b = ray / p.R;
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32) composite_bwd_kernel(Composite
 template <int IPL>
 static void launch_cbwd(const CompositeBwdParams& p, cudaStream_t stream) {
   const unsigned grid = static_cast<unsigned>((p.n_rays + kBwdWarps - 1) / kBwdWarps);
-  const size_t smem = static_cast<size_t>(kBwdWarps) * next_pow2_min32(p.n) * sizeof(unsigned long long);
+  const size_t smem = static_cast<size_t>(kBwdWarps) * merge_smem_words(p.n, p.S) * sizeof(unsigned long long);
   if (smem > 48 * 1024) cudaFuncSetAttribute(composite_bwd_kernel<IPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   composite_bwd_kernel<IPL><<<grid, kBwdWarps * 32, smem, stream>>>(p);
 }

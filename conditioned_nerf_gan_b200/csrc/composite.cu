@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
   if (MERGE) {
     // concatenation order of the reference: fine first, then coarse (generators.py:163-164); stable sort by t
     const int n2 = next_pow2_min32(n);
-    keys = reinterpret_cast<unsigned long long*>(smem) + static_cast<size_t>(warp) * n2;
+    keys = reinterpret_cast<unsigned long long*>(smem) + static_cast<size_t>(warp) * merge_smem_words(n, S);
     load_and_sort_ray(keys, p.rgb_sigma_fine ? p.t_fine : nullptr, p.t, ray, S, n, n2, lane);
   }
 
@@ -151,7 +151,7 @@ template <bool MERGE>
 static int launch_composite(const CompositeParams& p, cudaStream_t stream) {
   const int ipl = (p.n + 31) / 32;
   const unsigned grid = static_cast<unsigned>((p.n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  const size_t smem = MERGE ? static_cast<size_t>(kWarpsPerBlock) * next_pow2_min32(p.n) * sizeof(unsigned long long) : 0;
+  const size_t smem = MERGE ? static_cast<size_t>(kWarpsPerBlock) * merge_smem_words(p.n, p.S) * sizeof(unsigned long long) : 0;
 #define CNG_LAUNCH(I)                                                                              \
   {                                                                                               \
     if (smem > 48 * 1024)                                                                         \

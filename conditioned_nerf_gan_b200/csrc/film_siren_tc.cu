@@ -69,6 +69,8 @@ constexpr uint32_t kSmemBar = kSmemW + kRing * kChunkBytes;          // 229376
 constexpr uint32_t kSmemTotal = kSmemBar + 128;                      // 229504 <= 232448
 
 int film_siren_tc2_launch(TcParams p, cudaStream_t stream);   // film_siren_tc2.cu
+int film_siren_tc3_launch(TcParams p, int poly, cudaStream_t stream);   // film_siren_tc3.cu
+constexpr int kDefaultKernelVersion = 1;   // 3: layer-pipelined kernel (film_siren_tc3.cu); 1: the two-tile ping-pong kernel below
 
 static long long* g_tc_trace = nullptr;   // debug hook, see cng_internal_set_tc_trace
 
@@ -517,8 +519,14 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
     const int v = e ? atoi(e) : kDefaultPolyOneIn;
     return (v == 0 || v == 2 || v == 3 || v == 4 || v == 8) ? v : kDefaultPolyOneIn;
   }();
-  using KernelFn = void (*)(TcParams);
   const bool train = p.dump_x != nullptr;
+  static const int version = [] {
+    const char* e = getenv("CNG_TC_V");
+    const int v = e ? atoi(e) : kDefaultKernelVersion;
+    return (v == 1 || v == 3) ? v : kDefaultKernelVersion;
+  }();
+  if (version == 3 && !train && L <= 8) return film_siren_tc3_launch(p, poly, stream);
+  using KernelFn = void (*)(TcParams);
   const KernelFn fn = train ? film_siren_tc_kernel<0, true, true> : half_operands ? film_siren_tc_kernel<0, true>
                       : poly == 0 ? film_siren_tc_kernel<0, false> : poly == 2 ? film_siren_tc_kernel<2, false>
                       : poly == 3 ? film_siren_tc_kernel<3, false> : poly == 4 ? film_siren_tc_kernel<4, false> : film_siren_tc_kernel<8, false>;

@@ -91,10 +91,67 @@ __device__ __forceinline__ void load_and_sort_ray_regs(unsigned long long* keys,
   __syncwarp();
 }
 
+// Fast path of load_and_sort_ray when the coarse distances are already non-decreasing (they are: stratified jitter never
+// crosses a neighbour): sort only the S fine keys in registers, then MERGE -- the rank of a key in the merged order is its
+// rank in its own list plus the number of keys of the other list that precede it (binary search in shared memory).
+// Keys are unique (t bits, source index), fine indices < coarse indices, so this is exactly the stable fine-first order.
+// scratch: 2 * 32*SLOTS + ... 64-bit words after keys[0..n): fine list at keys + n2, coarse list at keys + n2 + 32*SLOTS.
+template <int SLOTS>
+__device__ __forceinline__ void sort_fine_and_merge(unsigned long long* keys, unsigned long long* fine_s, unsigned long long* coarse_s,
+                                                    const float* __restrict__ t_fine, const float* __restrict__ t_coarse, long long ray,
+                                                    int S, int lane) {
+  unsigned long long key[SLOTS];
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int e = s * 32 + lane;
+    key[s] = ~0ull;
+    if (e < S) key[s] = (static_cast<unsigned long long>(sortable_bits(__ldg(t_fine + ray * S + e))) << 32) | static_cast<unsigned>(e);
+  }
+  warp_bitonic_sort_regs<SLOTS>(key, lane);
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) fine_s[s * 32 + lane] = key[s];
+  for (int e = lane; e < S; e += 32)
+    coarse_s[e] = (static_cast<unsigned long long>(sortable_bits(__ldg(t_coarse + ray * S + e))) << 32) | static_cast<unsigned>(S + e);
+  __syncwarp();
+  auto lower_bound = [&](const unsigned long long* a, unsigned long long k) {     // number of a[0..S) that are < k
+    int lo = 0, hi = S;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (a[mid] < k) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  };
+  for (int e = lane; e < S; e += 32) {
+    const unsigned long long kf = fine_s[e], kc = coarse_s[e];
+    keys[e + lower_bound(coarse_s, kf)] = kf;
+    keys[e + lower_bound(fine_s, kc)] = kc;
+  }
+  __syncwarp();
+}
+
+// true iff t_coarse[ray, 0..S) is non-decreasing (warp vote)
+__device__ __forceinline__ bool coarse_is_sorted(const float* __restrict__ t_coarse, long long ray, int S, int lane) {
+  bool ok = true;
+  for (int e = lane; e + 1 < S; e += 32) ok = ok && (__ldg(t_coarse + ray * S + e) <= __ldg(t_coarse + ray * S + e + 1));
+  return __all_sync(0xffffffffu, ok);
+}
+
+// 64-bit words of shared memory one warp needs for n samples (S per list)
+__host__ __device__ inline int merge_smem_words(int n, int S) { return next_pow2_min32(n) + next_pow2_min32(S) + S; }
+
 // Loads the ray's distances (fine first, then coarse; or coarse only), sorts, and leaves keys[s] = (t, source index).
 __device__ __forceinline__ void load_and_sort_ray(unsigned long long* keys, const float* __restrict__ t_fine,
                                                   const float* __restrict__ t_coarse, long long ray, int S, int n, int n2, int lane) {
   const bool two = t_fine != nullptr;
+  if (two && S <= 128 && coarse_is_sorted(t_coarse, ray, S, lane)) {
+    unsigned long long* fine_s = keys + n2;
+    unsigned long long* coarse_s = fine_s + next_pow2_min32(S);
+    switch (next_pow2_min32(S)) {
+      case 32: sort_fine_and_merge<1>(keys, fine_s, coarse_s, t_fine, t_coarse, ray, S, lane); return;
+      case 64: sort_fine_and_merge<2>(keys, fine_s, coarse_s, t_fine, t_coarse, ray, S, lane); return;
+      default: sort_fine_and_merge<4>(keys, fine_s, coarse_s, t_fine, t_coarse, ray, S, lane); return;
+    }
+  }
   // up to 256 keys: sort in registers (1 to 8 keys per lane)
   switch (n2) {
     case 32: load_and_sort_ray_regs<1>(keys, t_fine, t_coarse, ray, S, n, lane); return;

@@ -39,5 +39,6 @@ e.record()
 torch.cuda.synchronize()
 ms = s.elapsed_time(e) / reps
 flops = 2 * (32 * 256 + (L - 1) * 256 * 256 + 256 * 4) * B * N
-print(f"{siren} {prec} poly={os.environ.get('CNG_TC_POLY', 'default')}: {ms:.3f} ms/launch, {flops / ms / 1e9:.1f} TFLOP/s algorithmic, "
+chk = int(out.view(torch.int32).long().sum().item())
+print(f"{siren} {prec} v={os.environ.get('CNG_TC_V', 'default')} bits-checksum {chk} poly={os.environ.get('CNG_TC_POLY', 'default')}: {ms:.3f} ms/launch, {flops / ms / 1e9:.1f} TFLOP/s algorithmic, "
       f"max-abs vs fp32 kernel {err:.3e}")
