@@ -18,7 +18,7 @@ STAMP = os.path.join(PKG, "csrc", ".build_stamp")
 SOURCES = ["cng_api.cu", "raymarch_gather.cu", "film_siren_simt.cu", "film_siren_tc.cu", "film_siren_tc2.cu", "film_siren_tc3.cu", "composite.cu", "sample_pdf.cu", "backward.cu", "render.cu"]
 # CNG_TC_EPI_WARPS (4 or 8): epilogue warps per tile slot of the one-CTA-per-SM tcgen05 kernel (film_siren_tc.cu)
 EPI_WARPS = os.environ.get("CNG_TC_EPI_WARPS", "8")
-EPI_PIPELINE = os.environ.get("CNG_TC_EPI_PIPELINE", "0")    # 1: double-buffer the epilogue's TMEM loads
+EPI_PIPELINE = os.environ.get("CNG_TC_EPI_PIPELINE", "1")    # 1: double-buffer the epilogue's TMEM loads
 NVCC_FLAGS = [
     f"-DCNG_TC_EPI_WARPS={EPI_WARPS}", f"-DCNG_TC_EPI_PIPELINE={EPI_PIPELINE}",
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

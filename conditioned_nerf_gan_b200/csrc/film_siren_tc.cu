@@ -47,7 +47,7 @@
 #define CNG_TC_EPI_WARPS 8
 #endif
 #ifndef CNG_TC_EPI_PIPELINE
-#define CNG_TC_EPI_PIPELINE 0
+#define CNG_TC_EPI_PIPELINE 1
 #endif
 #ifndef CNG_TC_EPI_GROUPED
 #define CNG_TC_EPI_GROUPED 0
@@ -66,7 +66,8 @@ constexpr int kNumThreads = 32 * (kProducerWarp + 1);
 constexpr uint32_t kSmemA = 0;
 constexpr uint32_t kSmemW = 2 * kATileBytes;                         // 131072
 constexpr uint32_t kSmemBar = kSmemW + kRing * kChunkBytes;          // 229376
-constexpr uint32_t kSmemTotal = kSmemBar + 128;                      // 229504 <= 232448
+constexpr uint32_t kSmemShift = kSmemBar + 128;                      // FiLM shift row of the layer each slot is working on: [2][256] fp32
+constexpr uint32_t kSmemTotal = kSmemShift + 2 * kHID * 4;           // 231552 <= 232448
 
 int film_siren_tc2_launch(TcParams p, cudaStream_t stream);   // film_siren_tc2.cu
 int film_siren_tc3_launch(TcParams p, int poly, cudaStream_t stream);   // film_siren_tc3.cu
@@ -226,21 +227,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
         for (int l = 0; l <= L; ++l) {
           const int nchunks = (l == 0) ? 2 : (l < L ? 4 : 1);
           for (int x = 0; x < nx; ++x) {
-            mbar_wait(act_ready(x), (act_phase >> x) & 1u);
+            mbar_wait_lean(act_ready(x), (act_phase >> x) & 1u);
             act_phase ^= 1u << x;
             tc_fence_after();
             if (elected) trace_event(p.trace, iter, l, x, 0);
             const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(x) * kHID;
             const uint64_t a_desc0 = make_desc(s_base + kSmemA + x * kATileBytes);
             for (int c = 0; c < nchunks; ++c) {
-              mbar_wait(w_full(slot), phase);
+              mbar_wait_lean(w_full(slot), phase);
               tc_fence_after();
               const uint64_t b_desc = make_desc(s_base + kSmemW + slot * kChunkBytes);
               if (elected) {
                 if (l < L) {
                   // layer 0: chunk 0 = 4 k-steps over [x_hi|x_lo], chunk 1 = 2 k-steps over [x_hi]
                   const uint64_t a_desc = a_desc0 + (l == 0 ? 0 : c * (kABlockBytes >> 4));
-                  tc_mma_bf16(d_tmem, a_desc, b_desc, idesc_main, 1u);                 // D holds the shift: always accumulate
+                  tc_mma_bf16(d_tmem, a_desc, b_desc, idesc_main, c ? 1u : 0u);        // first k-step of the layer overwrites
                   tc_mma_bf16(d_tmem, a_desc + 2, b_desc + 2, idesc_main, 1u);         // +32 bytes = one K step of 16 bf16
                   if (!(l == 0 && c == 1)) {
                     tc_mma_bf16(d_tmem, a_desc + 4, b_desc + 4, idesc_main, 1u);
@@ -280,16 +281,31 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
     uint32_t acc_phase = 0;
     int iter = 0;
     const bool tracer = (warp % kEpiWarpsPerSlot) == 0 && lane == 0;
+    // FiLM shift: the row of the layer in flight lives in shared memory (1 KB per slot) and is added to the accumulator
+    // in registers (LDS.128, warp-broadcast).  The next row is fetched into a register at the start of a layer's
+    // epilogue and published after it, between two barriers of the slot's warps, while the tensor pipe runs the next
+    // layer -- off the critical chain.  (Measured on the pipelined kernel: pre-storing the shift in the accumulator
+    // with tcgen05.st put an L2-latency load and a TMEM store on every block's chain, ~900 cycles per layer.)
+    constexpr int kSlotThreads = 32 * kEpiWarpsPerSlot;
+    constexpr int kRowPerThread = kHID / kSlotThreads;
+    const int ts = (warp % kEpiWarpsPerSlot) * 32 + lane;
+    float* row_x = reinterpret_cast<float*>(smem + kSmemShift) + x * kHID;
+    float row_next[kRowPerThread];
+    auto publish_row = [&]() {
+      named_bar_sync(1 + x, kSlotThreads);            // every warp of the slot is done reading the old row
+#pragma unroll
+      for (int i = 0; i < kRowPerThread; ++i) row_x[ts + i * kSlotThreads] = row_next[i];
+      named_bar_sync(1 + x, kSlotThreads);
+    };
     for (long long t = first + x * G; t < p.total_tiles; t += 2 * G, ++iter) {
       const TileInfo ti = tile_info(p, t);
       const float* shift_item = p.shift + static_cast<size_t>(ti.item) * L * kHID;
-      // ---- accumulator <- shift of layer 0 (the previous tile's head has been read: acc_full wait below) ----
-      Shift32 sh;
-#pragma unroll 1
-      for (int cc = kB * half; cc < kB * half + kB; ++cc) {
-        sh.load(shift_item + cc * 32);
-        sh.store(t_lane + cc * 32);
+      // ---- shift row of layer 0 -> shared memory (prefetched during the previous tile's last layer, see below) ----
+      if (iter == 0) {
+#pragma unroll
+        for (int i = 0; i < kRowPerThread; ++i) row_next[i] = __ldg(shift_item + ts + i * kSlotThreads);
       }
+      publish_row();
       // ---- features -> A block 0 as [x_hi(32) | x_lo(32)] ----
       {
         const float4* f = reinterpret_cast<const float4*>(p.feat + (static_cast<size_t>(ti.item) * p.N + ti.n0) * kC0);
@@ -307,19 +323,34 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
           *reinterpret_cast<uint2*>(smem + a_base + sw128_offset(r, 32 + 4 * c4)) = lo;
         }
       }
-      tmem_st_wait();
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(act_ready(x));
       for (int l = 0; l < L; ++l) {
         const bool more = l + 1 < L;
-        const float* shift_next = shift_item + (more ? l + 1 : l) * kHID;
-        if (!kTrain) sh.load(shift_next + kB * half * 32);         // in flight while waiting for the accumulator
+        {                                                          // next row: this tile's layer l+1, or the next tile's layer 0
+          const long long tn = t + 2 * G;
+          const float* src = more ? shift_item + (l + 1) * kHID
+                                  : p.shift + static_cast<size_t>(tn < p.total_tiles ? tn / p.tiles_per_item : ti.item) * L * kHID;
+#pragma unroll
+          for (int i = 0; i < kRowPerThread; ++i) row_next[i] = __ldg(src + ts + i * kSlotThreads);
+        }
         mbar_wait(acc_full(x), acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
         if (tracer) trace_event(p.trace, iter, l, x, 2);
-        auto finish_block = [&](const uint32_t (&v)[32], int cc) {
+        auto finish_block = [&](uint32_t (&v)[32], int cc) {
+          {
+            const float4* rs = reinterpret_cast<const float4*>(row_x + cc * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 sv = rs[i];
+              v[4 * i] = __float_as_uint(__uint_as_float(v[4 * i]) + sv.x);
+              v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + sv.y);
+              v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + sv.z);
+              v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + sv.w);
+            }
+          }
           if constexpr (kTrain) {
             // sin -> next layer's operand (shared memory A tile) and bf16 dump; freq*cos -> fp16 dump.  The dumps are
             // row-major [point][256] in HBM; a lane owns one row, so its 64 bytes go through a 2 KB per-warp staging
@@ -399,13 +430,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
             const int cc = kB * half + i;
             tmem_ld_wait();
             CNG_TMEM_LD_32(t_lane + (cc + 1) * 32, vb);
-            if (more) sh.store(t_lane + cc * 32);
-            sh.load(shift_next + (cc + 1) * 32);
             finish_block(va, cc);
             tmem_ld_wait();
             if (i + 2 < kB) CNG_TMEM_LD_32(t_lane + (cc + 2) * 32, va);
-            if (more) sh.store(t_lane + (cc + 1) * 32);
-            if (i + 2 < kB) sh.load(shift_next + (cc + 2) * 32);
             finish_block(vb, cc + 1);
           }
         } else {
@@ -414,21 +441,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
             uint32_t v[32];
             CNG_TMEM_LD_32(t_lane + cc * 32, v);
             tmem_ld_wait();
-            // the columns just read take the next layer's shift; the next MMA accumulates on top of it
-            if (kTrain) {                                          // register budget: no prefetch, load and store back to back
-              if (more) { sh.load(shift_next + cc * 32); sh.store(t_lane + cc * 32); }
-            } else {
-              if (more) sh.store(t_lane + cc * 32);
-              if (cc + 1 < kB * half + kB) sh.load(shift_next + (cc + 1) * 32);   // next block's shift, used after these sines
-            }
             finish_block(v, cc);
           }
         }
-        tmem_st_wait();
         tc_fence_before();
         fence_proxy_async();
         if (tracer) trace_event(p.trace, iter, l, x, 3);
         mbar_arrive(act_ready(x));
+        if (more) publish_row();        // the last layer's prefetch (next tile's layer 0) is published at the top of the tile loop
       }
       // ---- head: 4 accumulator columns -> bias, sigmoid(rgb), store (the column-half-0 warps hold them) ----
       mbar_wait(acc_full(x), acc_phase);

@@ -55,27 +55,6 @@ constexpr uint32_t kSmemTab = kSmemBar + 512;                         // FiLM sh
 constexpr int kMaxL = 8;
 constexpr uint32_t kSmemTotal = kSmemTab + kMaxL * kHID * 4;          // 221696
 
-// Lean mbarrier wait for the MMA-issuing warp (its loop is instruction-latency bound: every SASS instruction between
-// two tcgen05.mma issues is ~4 cycles of exposed latency).  Fast path = one try_wait + one branch; a protocol bug
-// still ends in a trap instead of a hung GPU.
-__device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      ".reg .u32 n;\n\t"
-      "mov.u32 n, 0;\n\t"
-      "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-      "@p bra DONE;\n\t"
-      "add.u32 n, n, 1;\n\t"
-      "setp.lt.u32 p, n, 4000000;\n\t"
-      "@p bra LAB_WAIT;\n\t"
-      "trap;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity), "r"(static_cast<uint32_t>(CNG_MBAR_HINT_NS))
-      : "memory");
-}
-
 template <int N>
 __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&v)[N]) {
   static_assert(N == 4 || N == 8 || N == 16, "columns per warp per sub-block");

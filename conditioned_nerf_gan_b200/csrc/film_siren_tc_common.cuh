@@ -71,6 +71,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// Lean mbarrier wait for the MMA-issuing warp (its loop is instruction-latency bound: every SASS instruction between
+// two tcgen05.mma issues is ~4 cycles of exposed latency).  Fast path = one try_wait + one branch; a protocol bug
+// still ends in a trap instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 p, n, 4000000;\n\t"
+      "@p bra LAB_WAIT;\n\t"
+      "trap;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity), "r"(static_cast<uint32_t>(CNG_MBAR_HINT_NS))
+      : "memory");
+}
+
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)

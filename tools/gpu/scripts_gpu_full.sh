@@ -8,6 +8,10 @@ timeout 600 python bench.py --steps 20 --warmup 5 --precision fp16 --no-cpu-base
 timeout 600 python bench.py --workload train --steps 4 --warmup 3 > gpurun_out/bench_train.log 2>&1; echo "train exit $?" >> gpurun_out/summary.txt
 timeout 600 python bench.py --workload video --steps 4 --warmup 3 > gpurun_out/bench_video.log 2>&1; echo "video exit $?" >> gpurun_out/summary.txt
 timeout 200 python tools/trace_tc.py 1 > gpurun_out/trace1.log 2>&1
+: > gpurun_out/mlp_ab.log
+for v in 1 3; do for pl in 0 8 4; do CNG_TC_V=$v CNG_TC_POLY=$pl timeout 200 python tools/bench_mlp.py TALLSIREN_FG 30 2>&1 | tail -1 >> gpurun_out/mlp_ab.log; done; done
+for s in SHORTSIREN_FG DOUBLESIREN_FG SingleSIREN_dg; do timeout 200 python tools/bench_mlp.py $s 30 2>&1 | tail -1 >> gpurun_out/mlp_ab.log; done
+timeout 200 python tools/bench_mlp.py SHORTSIREN_FG 30 fp16 2>&1 | tail -1 >> gpurun_out/mlp_ab.log
 timeout 600 python tools/bench_c5.py --json gpurun_out/c5.json > gpurun_out/c5.log 2>&1; echo "c5 exit $?" >> gpurun_out/summary.txt
 timeout 300 python tools/profile_train.py 4 > gpurun_out/profile_train.log 2>&1; echo "profile_train exit $?" >> gpurun_out/summary.txt
 timeout 300 python tools/bench_graph.py > gpurun_out/graph.log 2>&1
@@ -20,3 +24,4 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:film
 echo "ncu full exit $?" >> gpurun_out/summary.txt
 cat gpurun_out/summary.txt; tail -3 gpurun_out/pytest_gpu.log; tail -2 gpurun_out/smoke.log
 for f in bench bench_fp16 bench_train bench_video; do python tools/show_bench.py gpurun_out/$f.log; done
+cat gpurun_out/mlp_ab.log
