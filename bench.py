@@ -20,7 +20,9 @@ across ranks with no data-path collective).  Rank 0 prints ONE JSON line.
 ``--impl reference`` times that CPU path alone (rank 0 only) and prints the same line shape.
 
 Other workloads of BASELINE.json (not the driver's default line):
-  --workload train   generator-only train step at 128x128, 48+48 samples, GLOBAL batch 32 split over the N
+  --workload train   full GAN train step (U-Net encoder + generator + discriminator, config 3) at 128x128, 48+48 samples,
+                     GLOBAL batch 32 split over the N ranks; --workload train_generator times the generator's share alone
+  (train_generator)  generator-only train step at 128x128, 48+48 samples, GLOBAL batch 32 split over the N
                      ranks (strong scaling): forward with grad + backward kernels + NCCL gradient all-reduce
                      (DDP) + Adam; the encoder and the discriminator are out of scope and absent
   --workload video   256x256, 48+48 samples, 64 poses of one object sharded over the N ranks (config 4)
@@ -391,6 +393,68 @@ def _timed_steps(fn, steps, warmup, barrier, max_over_ranks):
 
 
 def run_train(args):
+    """Full GAN train step of BASELINE config 3: 3D U-Net encoder + FiLM-SIREN generator (CUDA rendering path, forward and
+    backward) + progressive discriminator with R1, following utils.py:621-842 (conditioned_nerf_gan_b200/training.py)."""
+    import torch.distributed as dist
+    from conditioned_nerf_gan_b200.discriminators import ProgressiveDiscriminator
+    from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d
+    from conditioned_nerf_gan_b200.generators.unet3d import UNet3D
+    from conditioned_nerf_gan_b200.generators.volumetric_rendering import create_cam2world_matrix, sample_camera_positions
+    from conditioned_nerf_gan_b200.training import GanTrainStep
+    rank, world, local, dev, barrier, max_over_ranks = _setup_ranks(args)
+    GLOBAL_B, img, S, V = 32, 128, 48, 64
+    if GLOBAL_B % world:
+        raise SystemExit("global batch 32 must divide by the number of GPUs")
+    b = GLOBAL_B // world
+    torch.manual_seed(0)                                            # same random-init weights on every rank (reference init distributions)
+    np.random.seed(rank)
+    gen = ImplicitGenerator3d(args.siren, 256, 32, 4, 256)
+    gen.siren.precision = args.precision
+    enc = UNet3D(in_channels=4, out_channels=32, f_maps=32, num_levels=4, is_segmentation=False, final_sigmoid=False, return_global=True)   # configs/thousand/special.py:53-62
+    disc = ProgressiveDiscriminator()
+    gen, enc, disc = gen.to(dev), enc.to(dev), disc.to(dev)
+    md = dict(render_meta(img, S), nerf_noise=1.0, batch_split=1, r1_lambda=10, grad_clip=1, betas=(0.0, 0.9), weight_decay=0,
+              gen_lr=10e-6, disc_lr=10e-5, enc_lr=2e-5, photo_loss=True, depth_loss=False, depth_loss_weight=1, enable_discriminator=True,
+              random_gen_img=True, cam_r_start=0.7, cam_r_end=1.5, fade_steps=2000)                                  # configs/thousand/default.py:42-81, special.py:29-41
+    trainer = GanTrainStep(gen, enc, disc, md, dev, amp=True, ddp=world > 1, local_rank=local)
+    g = torch.Generator().manual_seed(100 + rank)
+    occ = (torch.rand((b, 1, V, V, V), generator=g) < 0.05).float()
+    voxel_h = torch.cat([occ, torch.rand((b, 3, V, V, V), generator=g) * occ], dim=1).pin_memory()       # ~5 % occupied, U[0,1) colours (SURVEY 8d)
+    img_h = (torch.rand((b, 3, img, img), generator=g) * 2 - 1).pin_memory()
+    cam_h = create_cam2world_matrix(sample_camera_positions("cpu", "y", 0.7, 1.5, b), "y", "cpu").pin_memory()
+    results = []
+
+    def step():
+        sample = {"img": img_h.to(dev, non_blocking=True), "voxel": voxel_h.to(dev, non_blocking=True), "cam2world": cam_h.to(dev, non_blocking=True)}
+        losses = trainer.step(sample)
+        results.append(float(losses["d_loss"].item()) + float(losses["g_loss"].item()))     # device->host read of the step's result
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, launches = _timed_steps(step, args.steps, args.warmup, barrier, max_over_ranks)
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        L = SIREN_LAYERS[args.siren]
+        pts = GLOBAL_B * img * img * 2 * S
+        val = GLOBAL_B * args.steps / (ms * 1e-3)
+        line = {"metric": "train_images_per_sec_128x128_48+48spp_global_batch32", "value": val,
+                "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "full GAN train step (3D U-Net encoder + FiLM-SIREN generator + progressive discriminator, D step with R1 then G/E step) "
+                                       "128x128, 48+48spp, global batch 32 (BASELINE configs[2])",
+                           "siren_type": args.siren, "batch_per_gpu": b, "batch_split": 1, "amp": "autocast fp16 + GradScaler (as utils.py:643,711)",
+                           "optimizers": "Adam x3", "grad_allreduce": "DDP/NCCL, once per optimizer step" if world > 1 else "none",
+                           "encoder": "cuDNN (library), channels_last_3d, emits the NDHWC volume zero-copy", "discriminator": "cuDNN (library)",
+                           "generator": "hand-written CUDA path: forward x2 (no-grad for the D step, with grad for the G step) + backward"},
+                "e2e": {"value": val, "unit": "images/s",
+                        "h2d_bytes_per_step": int((voxel_h.numel() + img_h.numel() + cam_h.numel()) * 4), "d2h_bytes_per_step": 8},
+                "gpu_launches": launches, "clocks": clocks, "final_loss": results[-1],
+                "mlp_flops_per_step": 3 * 2 * mlp_flops_per_point(L) * pts}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_train_generator(args):
     """Generator-only train step (BASELINE config 3 minus the out-of-scope encoder / discriminator)."""
     import torch.distributed as dist
     from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d
@@ -507,12 +571,14 @@ def main():
     ap.add_argument("--siren", default="TALLSIREN_FG", choices=sorted(SIREN_LAYERS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="render", choices=["render", "train", "video"])
+    ap.add_argument("--workload", default="render", choices=["render", "train", "train_generator", "video"])
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         print(f"note: --warmup {args.warmup} < 3 (timing rules ask for >= 3)", file=sys.stderr)
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "train_generator":
+        run_train_generator(args)
     elif args.workload == "train":
         run_train(args)
     elif args.workload == "video":

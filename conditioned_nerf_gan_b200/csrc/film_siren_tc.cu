@@ -57,7 +57,7 @@ namespace cng {
 
 constexpr int kRing = 3;
 constexpr int kDefaultCtaGroup = 1;   // measured: the pair kernel pays ~1300 cycles of cross-CTA hand-off per layer
-constexpr int kDefaultPolyOneIn = 0;   // measured: the MUFU unit is not the limiter, offloading sines only adds issue pressure
+constexpr int kDefaultPolyOneIn = 8;   // one sine in 8 on the FMA pipe: measured 2.77 -> 2.68 ms per launch once the shift handling left the epilogue chain (it was neutral before)
 constexpr int kEpiWarpsPerSlot = CNG_TC_EPI_WARPS;   // 4 or 8 (build-time knob, see build.py)
 constexpr int kBlocksPerWarp = 32 / kEpiWarpsPerSlot;      // 32-column accumulator blocks per epilogue warp
 constexpr int kMmaWarp = 2 * kEpiWarpsPerSlot;
@@ -547,7 +547,8 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
   }();
   if (version == 3 && !train && L <= 8) return film_siren_tc3_launch(p, poly, stream);
   using KernelFn = void (*)(TcParams);
-  const KernelFn fn = train ? film_siren_tc_kernel<0, true, true> : half_operands ? film_siren_tc_kernel<0, true>
+  const KernelFn fn = train ? film_siren_tc_kernel<0, true, true>
+                      : half_operands ? (poly == 0 ? film_siren_tc_kernel<0, true> : poly == 4 ? film_siren_tc_kernel<4, true> : film_siren_tc_kernel<8, true>)
                       : poly == 0 ? film_siren_tc_kernel<0, false> : poly == 2 ? film_siren_tc_kernel<2, false>
                       : poly == 3 ? film_siren_tc_kernel<3, false> : poly == 4 ? film_siren_tc_kernel<4, false> : film_siren_tc_kernel<8, false>;
   static bool attr_set[3][9] = {};

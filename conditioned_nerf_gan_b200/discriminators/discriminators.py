@@ -1,0 +1,129 @@
+"""Progressive CoordConv discriminator: the consumer of the rendering path's images in training.
+
+Mirrors ``discriminators/discriminators.py:87-199`` (``ProgressiveDiscriminator``) with the same module tree, so the
+state-dict keys are the reference's (``layers.{i}.network.{0,2}.conv.*``, ``layers.{i}.proj.*``,
+``fromRGB.{i}.model.0.*``, ``final_layer.*``) and checkpoints load strictly; ``forward(input, alpha, instance_noise=0,
+cond=None, **kwargs)`` has the reference's signature (every curriculum key is passed and ignored, ``utils.py:663``).
+
+B200-first differences (results agree to fp32 summation order):
+  * ``CoordConv`` (``:87-103``) does not materialise ``cat([x, xx, yy])``.  The convolution is linear in its input
+    channels, so conv(cat[x, coords]) = conv_x(x) + conv_c(coords): the second term does not depend on the image, is
+    computed once per call on a cached ``[1, 2, H, W]`` grid (the reference rebuilds the grid on the CPU and copies it
+    to the device in every CoordConv of every forward, ``:49-76``) and is broadcast over the batch.  Zero padding
+    commutes with the split, double backward (R1 penalty, ``utils.py:805-813``) goes through stock conv2d;
+  * convolutions are cuDNN library calls (out of the hot-path scope).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class GlobalAveragePooling(nn.Module):
+    def forward(self, x):
+        return x.mean([2, 3])
+
+
+class AdapterBlock(nn.Module):
+    """1x1 conv + LeakyReLU(0.2) from image channels (discriminators.py:21-30)."""
+
+    def __init__(self, output_channels: int, input_channels: int = 3):
+        super().__init__()
+        self.model = nn.Sequential(nn.Conv2d(input_channels, output_channels, 1, padding=0), nn.LeakyReLU(0.2))
+
+    def forward(self, input):
+        return self.model(input)
+
+
+def kaiming_leaky_init(m):
+    """discriminators.py:32-37 (matches Linear layers only -- as in the reference, the conv layers keep their default init)."""
+    if m.__class__.__name__.find("Linear") != -1:
+        torch.nn.init.kaiming_normal_(m.weight, a=0.2, mode="fan_in", nonlinearity="leaky_relu")
+
+
+_GRID_CACHE: Dict[Tuple, torch.Tensor] = {}
+
+
+def coord_grid(h: int, w: int, device, dtype) -> torch.Tensor:
+    """[1, 2, h, w]: channel 0 varies along dim 2 (rows) as -1 + 2 i / (h - 1), channel 1 along dim 3 -- the two
+    channels ``AddCoords`` appends (discriminators.py:49-66; its x_dim is the tensor's dim 2)."""
+    key = (h, w, str(device), dtype)
+    g = _GRID_CACHE.get(key)
+    if g is None:
+        ii = torch.arange(h, device=device, dtype=torch.float32) / (h - 1) * 2 - 1
+        jj = torch.arange(w, device=device, dtype=torch.float32) / (w - 1) * 2 - 1
+        g = torch.stack([ii[:, None].expand(h, w), jj[None, :].expand(h, w)])[None].to(dtype).contiguous()
+        _GRID_CACHE[key] = g
+    return g
+
+
+class CoordConv(nn.Module):
+    """conv2d over [x, xx, yy] without building the concatenation (see the module docstring)."""
+
+    def __init__(self, in_channels: int, out_channels: int, with_r: bool = False, **kwargs):
+        super().__init__()
+        if with_r:
+            raise NotImplementedError("with_r is never used by the reference's discriminators")
+        self.in_channels = in_channels
+        self.conv = nn.Conv2d(in_channels + 2, out_channels, **kwargs)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        c = self.conv
+        w = c.weight
+        y = F.conv2d(x, w[:, : self.in_channels], None, c.stride, c.padding, c.dilation, c.groups)
+        grid = coord_grid(x.shape[2], x.shape[3], x.device, torch.float32)
+        pos = F.conv2d(grid.to(w.dtype), w[:, self.in_channels:], c.bias, c.stride, c.padding, c.dilation, c.groups)
+        return y + pos.to(y.dtype)
+
+
+class ResidualCoordConvBlock(nn.Module):
+    """discriminators.py:106-135."""
+
+    def __init__(self, inplanes: int, planes: int, kernel_size: int = 3, stride: int = 1, downsample: bool = False, groups: int = 1):
+        super().__init__()
+        p = kernel_size // 2
+        self.network = nn.Sequential(
+            CoordConv(inplanes, planes, kernel_size=kernel_size, stride=stride, padding=p),
+            nn.LeakyReLU(0.2, inplace=True),
+            CoordConv(planes, planes, kernel_size=kernel_size, padding=p),
+            nn.LeakyReLU(0.2, inplace=True),
+        )
+        self.network.apply(kaiming_leaky_init)
+        self.proj = nn.Conv2d(inplanes, planes, 1) if inplanes != planes else None
+        self.downsample = downsample
+
+    def forward(self, identity):
+        y = self.network(identity)
+        if self.downsample:
+            y = F.avg_pool2d(y, 2)
+            identity = F.avg_pool2d(identity, 2)
+        identity = identity if self.proj is None else self.proj(identity)
+        return (y + identity) / math.sqrt(2)
+
+
+class ProgressiveDiscriminator(nn.Module):
+    """discriminators.py:138-199: eight residual CoordConv blocks, entered at the block matching the image size, with the
+    progressive-GAN fade-in of the next-lower resolution after the first block."""
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        self.epoch = 0
+        self.step = 0
+        planes = [16, 32, 64, 128, 256, 400, 400, 400, 400]
+        self.layers = nn.ModuleList(ResidualCoordConvBlock(planes[i], planes[i + 1], downsample=True) for i in range(8))
+        self.fromRGB = nn.ModuleList(AdapterBlock(p) for p in planes)
+        self.final_layer = nn.Conv2d(400, 1, 2)
+        self.img_size_to_layer = {2: 8, 4: 7, 8: 6, 16: 5, 32: 4, 64: 3, 128: 2, 256: 1, 512: 0}
+
+    def forward(self, input, alpha, instance_noise=0, cond=None, **kwargs):
+        start = self.img_size_to_layer[input.shape[-1]]
+        x = self.fromRGB[start](input)
+        for i, layer in enumerate(self.layers[start:]):
+            if i == 1:
+                x = alpha * x + (1 - alpha) * self.fromRGB[start + 1](F.interpolate(input, scale_factor=0.5, mode="nearest"))
+            x = layer(x)
+        return self.final_layer(x).reshape(x.shape[0], 1)

@@ -1,0 +1,150 @@
+"""3D U-Net voxel encoder: the producer of the rendering path's input.
+
+Mirrors ``generators/unet3d.py:793-827`` (``UNet3D`` = ``Abstract3DUNet`` with ``DoubleConv`` blocks, ``:488-638``)
+closely enough that a reference checkpoint loads strictly: same module tree, hence the same state-dict keys
+(``encoders.{i}.basic_module.SingleConv{1,2}.{groupnorm,conv}.*``, ``decoders.{i}. ...``, ``final_conv.*``),
+same constructor arguments (``configs/thousand/special.py:53-62``), same return convention
+(``fv`` or ``(fv, global)``, ``unet3d.py:635-638``).
+
+What is different, B200-first:
+  * the convolutions are library calls (cuDNN through ``torch``, as SURVEY.md section 2 row 5 prescribes) but the
+    whole network runs in ``channels_last_3d`` memory format, so the final 1x1x1 convolution writes the feature
+    volume directly as NDHWC -- the layout the ray-march/gather kernel reads (one trilinear corner of all 32
+    channels = one 128-byte line).  ``ImplicitGenerator3d`` takes such a tensor zero-copy (no
+    ``cng_volume_to_channels_last`` launch, no 2 x 33.5 MB per image of layout traffic) and its backward hands the
+    scatter-added volume gradient back in the same layout;
+  * the bottleneck's global feature is one ``mean`` over the spatial axes instead of building an ``nn.AvgPool3d``
+    module per call (``unet3d.py:616-619``).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Union
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def number_of_features_per_level(init_channel_number: int, num_levels: int) -> List[int]:
+    """unet3d.py:13-14"""
+    return [init_channel_number * 2 ** k for k in range(num_levels)]
+
+
+class SingleConv(nn.Sequential):
+    """One conv layer with its normalisation / non-linearity in the given order (unet3d.py:21-132).
+    Letters: c conv3d, r ReLU, l LeakyReLU(0.1), e ELU, g GroupNorm, b BatchNorm3d."""
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: int = 3, order: str = "gcr", num_groups: int = 8, padding: int = 1):
+        super().__init__()
+        if "c" not in order:
+            raise AssertionError("Conv layer MUST be present")
+        if order[0] in "rle":
+            raise AssertionError("Non-linearity cannot be the first operation in the layer")
+        for i, ch in enumerate(order):
+            before_conv = i < order.index("c")
+            if ch == "c":
+                bias = not ("g" in order or "b" in order)        # learnable bias only without a normalisation layer
+                self.add_module("conv", nn.Conv3d(in_channels, out_channels, kernel_size, padding=padding, bias=bias))
+            elif ch == "g":
+                channels = in_channels if before_conv else out_channels
+                groups = 1 if channels < num_groups else num_groups
+                if channels % groups:
+                    raise AssertionError(f"Expected number of channels in input to be divisible by num_groups. num_channels={channels}, num_groups={groups}")
+                self.add_module("groupnorm", nn.GroupNorm(num_groups=groups, num_channels=channels))
+            elif ch == "b":
+                self.add_module("batchnorm", nn.BatchNorm3d(in_channels if before_conv else out_channels))
+            elif ch == "r":
+                self.add_module("ReLU", nn.ReLU(inplace=True))
+            elif ch == "l":
+                self.add_module("LeakyReLU", nn.LeakyReLU(negative_slope=0.1, inplace=True))
+            elif ch == "e":
+                self.add_module("ELU", nn.ELU(inplace=True))
+            else:
+                raise ValueError(f"Unsupported layer type '{ch}'. MUST be one of ['b', 'g', 'r', 'l', 'e', 'c']")
+
+
+class DoubleConv(nn.Sequential):
+    """Two SingleConv layers; channel plan of unet3d.py:157-192."""
+
+    def __init__(self, in_channels: int, out_channels: int, encoder: bool, kernel_size: int = 3, order: str = "gcr", num_groups: int = 8):
+        super().__init__()
+        if encoder:
+            mid = max(out_channels // 2, in_channels)
+            plan = ((in_channels, mid), (mid, out_channels))
+        else:
+            plan = ((in_channels, out_channels), (out_channels, out_channels))
+        for i, (ci, co) in enumerate(plan, start=1):
+            self.add_module(f"SingleConv{i}", SingleConv(ci, co, kernel_size, order, num_groups))
+
+
+class Encoder(nn.Module):
+    """Optional 2x2x2 max pooling + DoubleConv (unet3d.py:268-323)."""
+
+    def __init__(self, in_channels: int, out_channels: int, apply_pooling: bool = True, conv_layer_order: str = "gcr", num_groups: int = 8):
+        super().__init__()
+        self.pooling = nn.MaxPool3d(kernel_size=(2, 2, 2)) if apply_pooling else None
+        self.basic_module = DoubleConv(in_channels, out_channels, encoder=True, order=conv_layer_order, num_groups=num_groups)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.pooling is not None:
+            x = self.pooling(x)
+        return self.basic_module(x)
+
+
+class Decoder(nn.Module):
+    """Nearest-neighbour upsampling to the skip connection's size, channel concatenation (skip first), DoubleConv
+    (unet3d.py:326-403, 405-452)."""
+
+    def __init__(self, in_channels: int, out_channels: int, conv_layer_order: str = "gcr", num_groups: int = 8):
+        super().__init__()
+        self.basic_module = DoubleConv(in_channels, out_channels, encoder=False, order=conv_layer_order, num_groups=num_groups)
+
+    def forward(self, encoder_features: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+        x = F.interpolate(x, size=encoder_features.shape[2:], mode="nearest")
+        return self.basic_module(torch.cat((encoder_features, x), dim=1))
+
+
+class UNet3D(nn.Module):
+    """``UNet3D(in_channels, out_channels, final_sigmoid=True, f_maps=64, layer_order="gcr", num_groups=8, num_levels=4,
+    is_segmentation=True, return_global=False)`` -- unet3d.py:793-827.
+
+    ``forward(voxels[B, in_channels, D, H, W])`` returns the feature volume ``[B, out_channels, D, H, W]`` (logical NCDHW
+    shape, NDHWC strides) or ``(volume, global[B, f_maps[-1]])`` when ``return_global``."""
+
+    def __init__(self, in_channels: int, out_channels: int, final_sigmoid: bool = True, f_maps: Union[int, Sequence[int]] = 64,
+                 layer_order: str = "gcr", num_groups: int = 8, num_levels: int = 4, is_segmentation: bool = True,
+                 testing: bool = False, return_global: bool = False, **kwargs):
+        super().__init__()
+        self.testing = testing
+        if isinstance(f_maps, int):
+            f_maps = number_of_features_per_level(f_maps, num_levels=num_levels)
+        f_maps = list(f_maps)
+        self.encoders = nn.ModuleList(
+            Encoder(in_channels if i == 0 else f_maps[i - 1], f, apply_pooling=i > 0, conv_layer_order=layer_order, num_groups=num_groups)
+            for i, f in enumerate(f_maps))
+        rev = f_maps[::-1]
+        self.decoders = nn.ModuleList(
+            Decoder(rev[i] + rev[i + 1], rev[i + 1], conv_layer_order=layer_order, num_groups=num_groups) for i in range(len(rev) - 1))
+        self.final_conv = nn.Conv3d(f_maps[0], out_channels, 1)
+        if is_segmentation:
+            self.final_activation = nn.Sigmoid() if final_sigmoid else nn.Softmax(dim=1)
+        else:
+            self.final_activation = None
+        self.return_global = return_global
+
+    def forward(self, x: torch.Tensor):
+        if x.is_cuda:       # cuDNN runs the whole network NDHWC; the CPU kernels (tests only) stay NCDHW until the output
+            x = x.contiguous(memory_format=torch.channels_last_3d)
+        skips = []
+        for encoder in self.encoders:
+            x = encoder(x)
+            skips.insert(0, x)
+        global_features = x.mean(dim=(2, 3, 4)) if self.return_global else None      # full-extent average pool of the bottleneck
+        for decoder, skip in zip(self.decoders, skips[1:]):
+            x = decoder(skip, x)
+        x = self.final_conv(x)
+        if self.testing and self.final_activation is not None:
+            x = self.final_activation(x)
+        if x.dim() == 5 and not x.is_contiguous(memory_format=torch.channels_last_3d):
+            x = x.contiguous(memory_format=torch.channels_last_3d)                    # the layout the gather kernel reads
+        return (x, global_features) if self.return_global else x

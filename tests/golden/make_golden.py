@@ -204,8 +204,68 @@ def make_function_fixture(seed=7):
     return fx
 
 
+class ReplayedRefGenerator(torch.nn.Module):
+    """The unmodified reference generator with torch.rand / torch.randn replayed from ``metadata["draws"]`` on every forward."""
+
+    def __init__(self, gen):
+        super().__init__()
+        self.gen = gen
+
+    def forward(self, z, cam2worlds, **md):
+        draws = md["draws"]
+        meta = {k: v for k, v in md.items() if k != "draws"}
+        rp = Replay([("rand", draws["u_jitter"]), ("randn", draws["noise_coarse"]), ("rand", draws["u_resample"]), ("randn", draws["noise_final"])])
+        orig = torch.rand, torch.randn
+        torch.rand, torch.randn = rp.rand, rp.randn
+        try:
+            return self.gen(z, cam2worlds, **meta)
+        finally:
+            torch.rand, torch.randn = orig
+
+
+def make_train_step_fixture(steps=2):
+    """Two optimisation steps of the reference's train step (oracle/train_step.py follows utils.py:621-842) on the REFERENCE's
+    generator, U-Net and discriminator; also pins the U-Net / discriminator outputs themselves."""
+    import types as _types
+    tix = _types.ModuleType("tkinter.tix")
+    tix.Tree = object
+    sys.modules.setdefault("tkinter.tix", tix)
+    import generators.unet3d as ref_unet
+    import discriminators.discriminators as ref_disc
+    from oracle import train_step as ts
+
+    md = ts.tiny_config()
+    gen = ref_gen.ImplicitGenerator3d(oracle.resolve_siren_type(ts.TINY_SIREN), z_dim=ts.TINY_ZDIM, input_dim=32, output_dim=4, hidden_dim=256)
+    gen.load_state_dict(oracle.init_generator_state(ts.TINY_SIREN, z_dim=ts.TINY_ZDIM, seed=0), strict=True)
+    gen.set_device(torch.device("cpu"))
+    enc = ref_unet.UNet3D(**ts.TINY_UNET)
+    disc = ref_disc.ProgressiveDiscriminator()
+    ts.fill_params(enc, 1)
+    ts.fill_params(disc, 2)
+    sample = ts.tiny_sample()
+    fx = {}
+    with torch.no_grad():
+        fv, glob = enc(sample["voxel"])
+        fx["unet/volume"], fx["unet/global"] = fv.numpy(), glob.numpy()
+        for size in (16, 64):
+            img = torch.rand((2, 3, size, size), generator=torch.Generator().manual_seed(size)) * 2 - 1
+            fx[f"disc/in{size}"], fx[f"disc/out{size}"] = img.numpy(), disc(img, 0.3).numpy()
+    harness = ts.RefTrainStep(ReplayedRefGenerator(gen), enc, disc, dict(md, draws=ts.tiny_draws()), alpha=0.3)
+    for i in range(steps):
+        rec = harness.step(sample)
+        for k, v in rec.items():
+            fx[f"step{i}/{k}"] = np.array(v, dtype=np.float64)
+        print(f"train step {i}:", {k: round(v, 6) for k, v in rec.items()})
+    return fx
+
+
 def main():
     out = {}
+    if "--train-only" in sys.argv:
+        fx = make_train_step_fixture()
+        np.savez_compressed(os.path.join(HERE, "train_step.npz"), **fx)
+        return
+    out["train_step"] = make_train_step_fixture()
     out["fwd_TALLSIREN_FG"] = make_forward_fixture("TALLSIREN_FG", 11)
     out["fwd_SHORTSIREN_FG"] = make_forward_fixture("SHORTSIREN_dg", 12, clamp_mode="softplus", nerf_noise=0.5, white_back=False, last_back=True)
     out["fwd_DOUBLESIREN_FG"] = make_forward_fixture("DoubleSIREN_dg", 13, hierarchical=False, white_back=True)

@@ -1,0 +1,130 @@
+"""The callers either side of the rendering path (BASELINE config 3): 3D U-Net encoder,
+progressive discriminator and the GAN train step, against tests/golden/train_step.npz -- recorded by
+tests/golden/make_golden.py from the REFERENCE's own unet3d.UNet3D, ProgressiveDiscriminator and ImplicitGenerator3d."""
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import nerf_path as oracle
+from oracle import train_step as ts
+
+
+def _modules():
+    from conditioned_nerf_gan_b200.discriminators import ProgressiveDiscriminator
+    from conditioned_nerf_gan_b200.generators.unet3d import UNet3D
+    enc, disc = UNet3D(**ts.TINY_UNET), ProgressiveDiscriminator()
+    ts.fill_params(enc, 1)
+    ts.fill_params(disc, 2)
+    return enc, disc
+
+
+def test_state_dict_keys_are_the_reference_layout():
+    enc, disc = _modules()
+    ek, dk = list(enc.state_dict()), list(disc.state_dict())
+    assert ek[:3] == ["encoders.0.basic_module.SingleConv1.groupnorm.weight", "encoders.0.basic_module.SingleConv1.groupnorm.bias",
+                      "encoders.0.basic_module.SingleConv1.conv.weight"]
+    assert ek[-2:] == ["final_conv.weight", "final_conv.bias"] and any(k.startswith("decoders.0.basic_module.SingleConv2.") for k in ek)
+    assert dk[:4] == ["layers.0.network.0.conv.weight", "layers.0.network.0.conv.bias", "layers.0.network.2.conv.weight", "layers.0.network.2.conv.bias"]
+    assert "layers.0.proj.weight" in dk and "fromRGB.8.model.0.bias" in dk and dk[-2:] == ["final_layer.weight", "final_layer.bias"]
+    assert disc.state_dict()["layers.0.network.0.conv.weight"].shape == (32, 18, 3, 3)     # 16 + 2 coordinate channels
+    # the full-size encoder of configs/thousand/special.py:53-62
+    from conditioned_nerf_gan_b200.generators.unet3d import UNet3D
+    full = UNet3D(in_channels=4, out_channels=32, f_maps=32, num_levels=4, is_segmentation=False, final_sigmoid=False, return_global=True)
+    assert 4.0e6 < sum(p.numel() for p in full.parameters()) < 4.2e6          # 4.08 M parameters
+
+
+def test_unet_and_discriminator_match_reference_outputs():
+    fx, _ = load_golden("train_step")
+    enc, disc = _modules()
+    sample = ts.tiny_sample()
+    with torch.no_grad():
+        fv, glob = enc(sample["voxel"])
+        assert fv.shape == fx["unet/volume"].shape and fv.is_contiguous(memory_format=torch.channels_last_3d)
+        torch.testing.assert_close(fv.contiguous(), fx["unet/volume"], rtol=1e-4, atol=2e-5)
+        torch.testing.assert_close(glob, fx["unet/global"], rtol=1e-4, atol=1e-6)
+        for size in (16, 64):
+            torch.testing.assert_close(disc(fx[f"disc/in{size}"], 0.3), fx[f"disc/out{size}"], rtol=1e-4, atol=1e-6)
+
+
+def test_discriminator_ignores_curriculum_keys_and_fades_in():
+    _, disc = _modules()
+    img = torch.rand((1, 3, 32, 32)) * 2 - 1
+    a = disc(img, 1.0, cond=None, img_size=32, fov=30, batch_split=2)
+    b = disc(img, 0.0)
+    assert a.shape == (1, 1) and not torch.allclose(a, b)
+    with pytest.raises(KeyError):
+        disc(torch.rand((1, 3, 24, 24)), 1.0)          # img_size_to_layer lookup, discriminators.py:185-187
+
+
+def test_train_step_harness_with_our_encoder_and_discriminator_matches_reference_modules():
+    """oracle.RefTrainStep (utils.py:621-842 restated) around THIS repository's U-Net / discriminator and the oracle's
+    renderer reproduces the losses and gradient norms recorded with the reference's three modules."""
+    fx, _ = load_golden("train_step")
+    enc, disc = _modules()
+    gen = ts.OracleGenerator(ts.TINY_SIREN, oracle.init_generator_state(ts.TINY_SIREN, z_dim=ts.TINY_ZDIM, seed=0))
+    harness = ts.RefTrainStep(gen, enc, disc, dict(ts.tiny_config(), draws=ts.tiny_draws()), alpha=0.3)
+    sample = ts.tiny_sample()
+    for i in range(2):
+        rec = harness.step(sample)
+        for k, v in rec.items():
+            want = float(fx[f"step{i}/{k}"])
+            assert abs(v - want) <= 2e-3 * abs(want) + 1e-5, (i, k, v, want)
+
+
+@pytest.mark.gpu
+def test_gan_train_step_matches_reference_on_gpu():
+    """The product's GanTrainStep (CUDA rendering path in exact-fp32 mode, cuDNN U-Net / discriminator) against the
+    reference-recorded losses and gradient norms of two consecutive optimisation steps."""
+    from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d
+    from conditioned_nerf_gan_b200.training import GanTrainStep
+    fx, _ = load_golden("train_step")
+    dev = torch.device("cuda")
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        enc, disc = _modules()
+        gen = ImplicitGenerator3d(ts.TINY_SIREN, ts.TINY_ZDIM, 32, 4, 256)
+        gen.load_state_dict(oracle.init_generator_state(ts.TINY_SIREN, z_dim=ts.TINY_ZDIM, seed=0), strict=True)
+        gen.siren.precision = "fp32"
+        enc, disc, gen = enc.to(dev), disc.to(dev), gen.to(dev)
+        md = dict(ts.tiny_config(), draws={k: v.to(dev) for k, v in ts.tiny_draws().items()})
+        trainer = GanTrainStep(gen, enc, disc, md, dev, amp=False)
+        trainer.alpha = 0.3
+        sample = {k: v.to(dev) for k, v in ts.tiny_sample().items()}
+        for i in range(2):
+            trainer.train_discriminator(sample)
+            trainer.train_generator(sample)
+            got = {"d_loss": trainer.losses["d_loss"], "g_loss": trainer.losses["g_loss"], "photo_loss": trainer.losses["photo_loss"],
+                   "norm_D": trainer.grad_norms["D"], "norm_G": trainer.grad_norms["G"], "norm_E": trainer.grad_norms["E"]}
+            for k, v in got.items():
+                want = float(fx[f"step{i}/{k}"])
+                tol = 2e-2 if k.startswith("norm") else 2e-3          # gradient norms: fp32 backward of the MLP recompute (bf16 GEMMs)
+                assert abs(float(v) - want) <= tol * abs(want) + 1e-5, (i, k, float(v), want)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+@pytest.mark.gpu
+def test_gan_train_step_amp_full_api():
+    """step() under autocast + GradScaler with the tensor-core MLP, random discriminator cameras, batch_split 2: finite
+    losses, parameters move, counters advance, the encoder's volume arrives in the gather kernel's layout."""
+    from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d
+    from conditioned_nerf_gan_b200.training import GanTrainStep
+    dev = torch.device("cuda")
+    enc, disc = _modules()
+    gen = ImplicitGenerator3d(ts.TINY_SIREN, ts.TINY_ZDIM, 32, 4, 256)
+    gen.load_state_dict(oracle.init_generator_state(ts.TINY_SIREN, z_dim=ts.TINY_ZDIM, seed=0), strict=True)
+    enc, disc, gen = enc.to(dev), disc.to(dev), gen.to(dev)
+    md = dict(ts.tiny_config(), random_gen_img=True, batch_split=2)
+    trainer = GanTrainStep(gen, enc, disc, md, dev, amp=True)
+    sample = {k: v.to(dev) for k, v in ts.tiny_sample().items()}
+    before = [p.detach().clone() for m in (gen, enc, disc) for p in list(m.parameters())[:2]]
+    for _ in range(2):
+        losses = trainer.step(sample)
+    assert all(torch.isfinite(v).all() for v in losses.values()), losses
+    after = [p.detach() for m in (gen, enc, disc) for p in list(m.parameters())[:2]]
+    assert any(not torch.equal(a, b) for a, b in zip(before, after))
+    assert gen.step == 2 and disc.step == 2 and trainer.metadata["nerf_noise"] == pytest.approx(1.0 - 1 / 5000.0)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        fv, _ = enc(sample["voxel"])
+    assert fv.is_contiguous(memory_format=torch.channels_last_3d)
