@@ -11,7 +11,13 @@ B200-first differences (results agree to fp32 summation order):
     computed once per call on a cached ``[1, 2, H, W]`` grid (the reference rebuilds the grid on the CPU and copies it
     to the device in every CoordConv of every forward, ``:49-76``) and is broadcast over the batch.  Zero padding
     commutes with the split, double backward (R1 penalty, ``utils.py:805-813``) goes through stock conv2d;
-  * convolutions are cuDNN library calls (out of the hot-path scope).
+  * convolutions are cuDNN library calls (out of the hot-path scope), but their autograd is spelled
+    out (``conv2d_r1``): the R1 penalty differentiates the image gradient once more, and PyTorch's generic
+    ``_convolution_double_backward`` forms the weight term as a convolution with batch and channels swapped -- an
+    ``[C, N, H, W] * [C', N, H, W]`` problem with a 128 x 128 "filter" that cuDNN only serves with its legacy SGEMM
+    kernels (measured on B200, batch 8 at 128^2: 2 launches of 88 ms, 250 of the 254 ms of one discriminator update).
+    Here the input gradient is its own autograd node whose backward is a plain convolution (w.r.t. the upstream
+    gradient) and a plain weight-gradient (w.r.t. the filter): the same numbers from tensor-core kernels.
 """
 from __future__ import annotations
 
@@ -21,6 +27,66 @@ from typing import Dict, Tuple
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+
+class _ConvInputGrad(torch.autograd.Function):
+    """gx = d conv2d(x, w) / dx contracted with gy (a transposed convolution), differentiable a second time:
+    d gx / d gy contracted with ggx = conv2d(ggx, w);  d gx / d w contracted with ggx = weight-gradient(ggx, gy)."""
+
+    @staticmethod
+    def forward(ctx, gy, w, x_shape, stride, padding):
+        ctx.save_for_backward(gy, w)
+        ctx.cfg = (x_shape, stride, padding)
+        return torch.nn.grad.conv2d_input(x_shape, w, gy, stride=stride, padding=padding)
+
+    @staticmethod
+    def backward(ctx, ggx):
+        gy, w = ctx.saved_tensors
+        _, stride, padding = ctx.cfg
+        ggx = ggx.to(w.dtype)
+        d_gy = F.conv2d(ggx, w, None, stride, padding) if ctx.needs_input_grad[0] else None
+        d_w = torch.nn.grad.conv2d_weight(ggx, w.shape, gy, stride=stride, padding=padding) if ctx.needs_input_grad[1] else None
+        return d_gy, d_w, None, None, None
+
+
+class _Conv2dR1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, stride, padding):
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (stride, padding, b is not None)
+        return F.conv2d(x, w, b, stride, padding)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        stride, padding, has_bias = ctx.cfg
+        gy = gy.contiguous()
+        gx = _ConvInputGrad.apply(gy, w, x.shape, stride, padding) if ctx.needs_input_grad[0] else None
+        gw = torch.nn.grad.conv2d_weight(x, w.shape, gy, stride=stride, padding=padding) if ctx.needs_input_grad[1] else None
+        gb = gy.sum((0, 2, 3)) if (has_bias and ctx.needs_input_grad[2]) else None
+        return gx, gw, gb, None, None
+
+
+def conv2d_r1(x, w, b=None, stride=1, padding=0):
+    """``F.conv2d`` (groups 1, dilation 1) whose double backward stays on the library's fast kernels (module docstring).
+    Follows autocast: operands are cast once here, the function itself runs with autocast off."""
+    stride = (stride, stride) if isinstance(stride, int) else tuple(stride)
+    padding = (padding, padding) if isinstance(padding, int) else tuple(padding)
+    if x.is_cuda and torch.is_autocast_enabled():
+        dt = torch.get_autocast_dtype('cuda')
+        x, w, b = x.to(dt), w.to(dt), (b.to(dt) if b is not None else None)
+        with torch.autocast("cuda", enabled=False):
+            return _Conv2dR1.apply(x, w, b, stride, padding)
+    if w.dtype != x.dtype:
+        w, b = w.to(x.dtype), (b.to(x.dtype) if b is not None else None)
+    return _Conv2dR1.apply(x, w, b, stride, padding)
+
+
+class R1Conv2d(nn.Conv2d):
+    """``nn.Conv2d`` (same parameters, same state-dict keys) routed through ``conv2d_r1``."""
+
+    def forward(self, x):
+        return conv2d_r1(x, self.weight, self.bias, self.stride, self.padding)
 
 
 class GlobalAveragePooling(nn.Module):
@@ -33,7 +99,7 @@ class AdapterBlock(nn.Module):
 
     def __init__(self, output_channels: int, input_channels: int = 3):
         super().__init__()
-        self.model = nn.Sequential(nn.Conv2d(input_channels, output_channels, 1, padding=0), nn.LeakyReLU(0.2))
+        self.model = nn.Sequential(R1Conv2d(input_channels, output_channels, 1, padding=0), nn.LeakyReLU(0.2))
 
     def forward(self, input):
         return self.model(input)
@@ -74,9 +140,9 @@ class CoordConv(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         c = self.conv
         w = c.weight
-        y = F.conv2d(x, w[:, : self.in_channels], None, c.stride, c.padding, c.dilation, c.groups)
+        y = conv2d_r1(x, w[:, : self.in_channels].contiguous(), None, c.stride, c.padding)
         grid = coord_grid(x.shape[2], x.shape[3], x.device, torch.float32)
-        pos = F.conv2d(grid.to(w.dtype), w[:, self.in_channels:], c.bias, c.stride, c.padding, c.dilation, c.groups)
+        pos = F.conv2d(grid.to(w.dtype), w[:, self.in_channels:], c.bias, c.stride, c.padding)      # no image on this path: stock autograd
         return y + pos.to(y.dtype)
 
 
@@ -93,7 +159,7 @@ class ResidualCoordConvBlock(nn.Module):
             nn.LeakyReLU(0.2, inplace=True),
         )
         self.network.apply(kaiming_leaky_init)
-        self.proj = nn.Conv2d(inplanes, planes, 1) if inplanes != planes else None
+        self.proj = R1Conv2d(inplanes, planes, 1) if inplanes != planes else None
         self.downsample = downsample
 
     def forward(self, identity):
@@ -116,7 +182,7 @@ class ProgressiveDiscriminator(nn.Module):
         planes = [16, 32, 64, 128, 256, 400, 400, 400, 400]
         self.layers = nn.ModuleList(ResidualCoordConvBlock(planes[i], planes[i + 1], downsample=True) for i in range(8))
         self.fromRGB = nn.ModuleList(AdapterBlock(p) for p in planes)
-        self.final_layer = nn.Conv2d(400, 1, 2)
+        self.final_layer = R1Conv2d(400, 1, 2)
         self.img_size_to_layer = {2: 8, 4: 7, 8: 6, 16: 5, 32: 4, 64: 3, 128: 2, 256: 1, 512: 0}
 
     def forward(self, input, alpha, instance_noise=0, cond=None, **kwargs):

@@ -25,6 +25,9 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+FORCE_CONTIGUOUS = False     # tools/bench_unet.py: run the network NCDHW (the library then converts layouts per convolution)
+
+
 def number_of_features_per_level(init_channel_number: int, num_levels: int) -> List[int]:
     """unet3d.py:13-14"""
     return [init_channel_number * 2 ** k for k in range(num_levels)]
@@ -133,7 +136,7 @@ class UNet3D(nn.Module):
         self.return_global = return_global
 
     def forward(self, x: torch.Tensor):
-        if x.is_cuda:       # cuDNN runs the whole network NDHWC; the CPU kernels (tests only) stay NCDHW until the output
+        if x.is_cuda and not FORCE_CONTIGUOUS:       # cuDNN runs the whole network NDHWC; the CPU kernels (tests only) stay NCDHW until the output
             x = x.contiguous(memory_format=torch.channels_last_3d)
         skips = []
         for encoder in self.encoders:

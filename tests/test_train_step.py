@@ -128,3 +128,24 @@ def test_gan_train_step_amp_full_api():
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
         fv, _ = enc(sample["voxel"])
     assert fv.is_contiguous(memory_format=torch.channels_last_3d)
+
+
+def test_conv2d_r1_double_backward_equals_stock_autograd():
+    """conv2d_r1 spells out the convolution's first and second derivative (fast kernels for the R1 penalty): values, gradients
+    and the gradient of an R1-style penalty must equal torch's own autograd through F.conv2d (float64, strides 1 and 2)."""
+    from conditioned_nerf_gan_b200.discriminators.discriminators import conv2d_r1
+    g = torch.Generator().manual_seed(3)
+    for stride, padding, k in ((1, 1, 3), (2, 1, 3), (1, 0, 1), (1, 0, 2)):
+        x0 = torch.randn((2, 5, 9, 8), generator=g, dtype=torch.float64)
+        w0 = torch.randn((7, 5, k, k), generator=g, dtype=torch.float64) * 0.3
+        b0 = torch.randn((7,), generator=g, dtype=torch.float64)
+        res = []
+        for fn in (conv2d_r1, torch.nn.functional.conv2d):
+            x, w, b = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+            y = torch.tanh(fn(x, w, b, stride, padding))
+            gx = torch.autograd.grad(y.sum(), x, create_graph=True)[0]
+            loss = y.square().mean() + 0.5 * (gx.reshape(2, -1).norm(2, dim=1) ** 2).mean()
+            loss.backward()
+            res.append((y.detach(), gx.detach(), x.grad, w.grad, b.grad))
+        for a, b_ in zip(*res):
+            torch.testing.assert_close(a, b_, rtol=1e-10, atol=1e-12)
