@@ -71,9 +71,12 @@ constexpr uint32_t kSmemTotal = kSmemShift + 2 * kHID * 4;           // 231552 <
 
 int film_siren_tc2_launch(TcParams p, cudaStream_t stream);   // film_siren_tc2.cu
 int film_siren_tc3_launch(TcParams p, int poly, cudaStream_t stream);   // film_siren_tc3.cu
-constexpr int kDefaultKernelVersion = 1;   // 3: layer-pipelined kernel (film_siren_tc3.cu); 1: the two-tile ping-pong kernel below
+// 1: the two-tile ping-pong kernel below, 8 epilogue warps bound to each tile slot; 2: the same with all 16 epilogue warps
+// shared between the slots; 3: the layer-pipelined kernel (film_siren_tc3.cu).  All three give bit-identical results.
+constexpr int kDefaultKernelVersion = 1;   // measured (profiles/r1g_k2_versions.txt): 1 and 2 within 1-2 % on TALLSIREN_FG, 1 ahead for fewer layers, 3 behind by 10 %
 
 static long long* g_tc_trace = nullptr;   // debug hook, see cng_internal_set_tc_trace
+static int g_tc_version = 0;              // 0: CNG_TC_V / default; 1 or 3: forced (cng_internal_set_tc_version, tests and A/B tools)
 
 // ---- fold kernel ---------------------------------------------------------------------------------
 struct FoldParams {
@@ -148,8 +151,13 @@ __global__ void __launch_bounds__(256) film_fold_kernel(FoldParams p) {
 }
 
 // kTrain: additionally stream x_{l+1} and g_l = freq*cos(u_l) of every layer to HBM (p.dump_x / p.dump_g) for the backward
-template <int kPolyOneIn, bool kHalf, bool kTrain = false>
+// kShared: all 16 epilogue warps work on whichever tile's accumulator is complete (slot 0, then slot 1, then slot 0 ...)
+// instead of 8 warps bound to each slot.  A tile's epilogue then takes about as long as the other tile's MMAs and the
+// two strictly alternate: the tensor pipe runs back to back ("what the K2 numbers taught").
+template <int kPolyOneIn, bool kHalf, bool kTrain = false, bool kShared = false>
 __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams p) {
+  static_assert(!(kShared && kTrain), "the shared epilogue is an inference path");
+  static_assert(!kShared || kEpiWarpsPerSlot == 8, "the shared epilogue uses all 16 epilogue warps");
   // training mode gives one weight-ring slot (32 KB) to the per-warp staging buffers of the activation dumps
   constexpr int kRingN = kTrain ? kRing - 1 : kRing;
   constexpr uint32_t kSmemStage = kSmemW + kRingN * kChunkBytes;     // 16 epilogue warps x 2 KB (kTrain only)
@@ -167,7 +175,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kRingN; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
-    for (int x = 0; x < 2; ++x) { mbar_init(act_ready(x), 32 * kEpiWarpsPerSlot); mbar_init(acc_full(x), 1); }
+    for (int x = 0; x < 2; ++x) { mbar_init(act_ready(x), kShared ? 2 * kEpiWarpsPerSlot : 32 * kEpiWarpsPerSlot); mbar_init(acc_full(x), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {
@@ -267,6 +275,136 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
             __syncwarp();
           }
         }
+      }
+    }
+  } else if constexpr (kShared) {
+    // =========================== epilogue warps, shared between the two tile slots ===========================
+    const int q = warp & 3;                       // TMEM lane quarter == warp_id % 4
+    const int cg = warp >> 2;                     // column group: accumulator blocks [2*cg, 2*cg + 2) of 32 columns
+    const int row = q * 32 + lane;
+    const int tid = threadIdx.x;                  // 0..511
+    uint32_t acc_phase = 0;                       // bit x = parity of acc_full(x)
+    int iter = 0;
+    const bool tracer = warp == 0 && lane == 0;
+    float* rows = reinterpret_cast<float*>(smem + kSmemShift);          // [2 slots][256]: shift row of the layer in flight
+    float row_next[2] = {0.f, 0.f};                                     // threads 0..255: element tid of slot 0 / 1's next row
+    auto signal = [&](uint32_t bar) {
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
+    auto publish_row = [&](int x) {
+      named_bar_sync(1, 512);                     // every epilogue warp is done reading slot x's old row
+      if (tid < kHID) rows[x * kHID + tid] = row_next[x];
+      named_bar_sync(1, 512);
+    };
+    for (long long t0 = first; t0 < p.total_tiles; t0 += 2 * G, ++iter) {
+      const int nx = (t0 + G < p.total_tiles) ? 2 : 1;
+      TileInfo ti[2];
+      const float* shift_item[2];
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        ti[x] = tile_info(p, x < nx ? t0 + x * G : t0);
+        shift_item[x] = p.shift + static_cast<size_t>(ti[x].item) * L * kHID;
+      }
+      // ---- per slot: layer-0 shift row, features -> A block 0 as [x_hi(32) | x_lo(32)] ----
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        if (x >= nx) continue;
+        if (iter == 0 && tid < kHID) row_next[x] = __ldg(shift_item[x] + tid);
+        publish_row(x);
+        const float4* f = reinterpret_cast<const float4*>(p.feat + (static_cast<size_t>(ti[x].item) * p.N + ti[x].n0) * kC0);
+        const uint32_t a_base = kSmemA + x * kATileBytes;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int idx = tid + 512 * i, r = idx >> 3, c4 = idx & 7;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < ti[x].rows) v = __ldg(f + idx);
+          uint2 hi, lo;
+          hi.x = pack2<kHalf>(v.x, v.y); hi.y = pack2<kHalf>(v.z, v.w);
+          lo.x = pack2<kHalf>(v.x - from16<kHalf>(to16<kHalf>(v.x)), v.y - from16<kHalf>(to16<kHalf>(v.y)));
+          lo.y = pack2<kHalf>(v.z - from16<kHalf>(to16<kHalf>(v.z)), v.w - from16<kHalf>(to16<kHalf>(v.w)));
+          *reinterpret_cast<uint2*>(smem + a_base + sw128_offset(r, 4 * c4)) = hi;
+          *reinterpret_cast<uint2*>(smem + a_base + sw128_offset(r, 32 + 4 * c4)) = lo;
+        }
+        signal(act_ready(x));
+      }
+      for (int l = 0; l < L; ++l) {
+        const bool more = l + 1 < L;
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+          if (x >= nx) continue;
+          if (tid < kHID) {                        // next row of this slot: layer l+1 of this tile, or layer 0 of its next tile
+            const long long tn = t0 + x * G + 2 * G;
+            const float* src = more ? shift_item[x] + (l + 1) * kHID
+                                    : p.shift + static_cast<size_t>(tn < p.total_tiles ? tn / p.tiles_per_item : ti[x].item) * L * kHID;
+            row_next[x] = __ldg(src + tid);
+          }
+          const uint32_t a_base = kSmemA + x * kATileBytes;
+          const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(x) * kHID;
+          const float* row_x = rows + x * kHID;
+          mbar_wait(acc_full(x), (acc_phase >> x) & 1u);
+          acc_phase ^= 1u << x;
+          tc_fence_after();
+          if (tracer) trace_event(p.trace, iter, l, x, 2);
+          uint32_t va[32], vb[32];
+          CNG_TMEM_LD_32(t_lane + (2 * cg) * 32, va);
+          tmem_ld_wait();
+          CNG_TMEM_LD_32(t_lane + (2 * cg + 1) * 32, vb);
+          auto finish = [&](uint32_t (&v)[32], int cc) {
+            const float4* rs = reinterpret_cast<const float4*>(row_x + cc * 32);
+            uint8_t* blk = smem + a_base + (cc >> 1) * kABlockBytes + row * 128;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {                       // one 16-byte chunk (8 columns) at a time
+              const float4 s0 = rs[2 * i], s1 = rs[2 * i + 1];
+              const float sh[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+              uint32_t o[4];
+#pragma unroll
+              for (int j = 0; j < 8; j += 2)
+                o[j / 2] = pack2<kHalf>(film_sin<kPolyOneIn>(__uint_as_float(v[8 * i + j]) + sh[j], 8 * i + j),
+                                        film_sin<kPolyOneIn>(__uint_as_float(v[8 * i + j + 1]) + sh[j + 1], 8 * i + j + 1));
+              const int chunk = ((cc & 1) * 4 + i) ^ (row & 7);
+              *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+          };
+          finish(va, 2 * cg);
+          tmem_ld_wait();
+          finish(vb, 2 * cg + 1);
+          if (tracer) trace_event(p.trace, iter, l, x, 3);
+          signal(act_ready(x));
+          if (more) publish_row(x);        // the next tile's layer-0 row is published at the top of the tile loop
+        }
+      }
+      // ---- head: 4 accumulator columns -> bias, sigmoid(rgb), store (column group 0 holds them) ----
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        if (x >= nx) continue;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(x) * kHID;
+        mbar_wait(acc_full(x), (acc_phase >> x) & 1u);
+        acc_phase ^= 1u << x;
+        tc_fence_after();
+        if (cg == 0) {
+          uint32_t r0, r1, r2, r3;
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                       : "r"(t_lane)
+                       : "memory");
+          tmem_ld_wait();
+          float4 o;
+          const float4 fb = __ldg(reinterpret_cast<const float4*>(p.final_b));
+          o.x = __uint_as_float(r0) + fb.x;
+          o.y = __uint_as_float(r1) + fb.y;
+          o.z = __uint_as_float(r2) + fb.z;
+          o.w = __uint_as_float(r3) + fb.w;
+          if (p.sigmoid_rgb) {
+            o.x = 1.f / (1.f + __expf(-o.x));
+            o.y = 1.f / (1.f + __expf(-o.y));
+            o.z = 1.f / (1.f + __expf(-o.z));
+          }
+          if (row < ti[x].rows) reinterpret_cast<float4*>(p.out)[static_cast<size_t>(ti[x].item) * p.N + ti[x].n0 + row] = o;
+        }
+        tc_fence_before();   // orders the TMEM reads above before the next tile's first MMA (via act_ready)
       }
     }
   } else {
@@ -543,16 +681,21 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
   static const int version = [] {
     const char* e = getenv("CNG_TC_V");
     const int v = e ? atoi(e) : kDefaultKernelVersion;
-    return (v == 1 || v == 3) ? v : kDefaultKernelVersion;
+    return (v >= 1 && v <= 3) ? v : kDefaultKernelVersion;
   }();
-  if (version == 3 && !train && L <= 8) return film_siren_tc3_launch(p, poly, stream);
+  const int ver = g_tc_version ? g_tc_version : version;
+  if (ver == 3 && !train && L <= 8) return film_siren_tc3_launch(p, poly, stream);
+  const bool shared = (ver == 2) && !train;
   using KernelFn = void (*)(TcParams);
+  const int pl = (poly == 0 || poly == 4) ? poly : 8;          // shared mode and fp16 come in these three flavours
   const KernelFn fn = train ? film_siren_tc_kernel<0, true, true>
-                      : half_operands ? (poly == 0 ? film_siren_tc_kernel<0, true> : poly == 4 ? film_siren_tc_kernel<4, true> : film_siren_tc_kernel<8, true>)
+                      : shared ? (half_operands ? (pl == 0 ? film_siren_tc_kernel<0, true, false, true> : pl == 4 ? film_siren_tc_kernel<4, true, false, true> : film_siren_tc_kernel<8, true, false, true>)
+                                                : (pl == 0 ? film_siren_tc_kernel<0, false, false, true> : pl == 4 ? film_siren_tc_kernel<4, false, false, true> : film_siren_tc_kernel<8, false, false, true>))
+                      : half_operands ? (pl == 0 ? film_siren_tc_kernel<0, true> : pl == 4 ? film_siren_tc_kernel<4, true> : film_siren_tc_kernel<8, true>)
                       : poly == 0 ? film_siren_tc_kernel<0, false> : poly == 2 ? film_siren_tc_kernel<2, false>
                       : poly == 3 ? film_siren_tc_kernel<3, false> : poly == 4 ? film_siren_tc_kernel<4, false> : film_siren_tc_kernel<8, false>;
-  static bool attr_set[3][9] = {};
-  const int variant = train ? 2 : (half_operands ? 1 : 0);
+  static bool attr_set[5][9] = {};
+  const int variant = train ? 2 : (half_operands ? 1 : 0) + (shared ? 3 : 0);
   if (!attr_set[variant][poly]) {
     ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTotal));
     if (ce != cudaSuccess) return fail(static_cast<int>(ce), "film_siren_fwd(bf16): smem attribute: %s", cudaGetErrorString(ce));
@@ -575,6 +718,10 @@ extern "C" {
 // Debug hook (not part of the ABI in include/cng_b200.h): device buffer of 4*9*2*8 int64 that receives the clock64
 // timeline of CTA 0 of the next cta_group::1 launches; NULL switches it off.  Used by tools/trace_tc.py.
 CNG_API void cng_internal_set_tc_trace(void* dev_buffer) { cng::g_tc_trace = static_cast<long long*>(dev_buffer); }
+
+// Debug hook: which tcgen05 kernel serves cng_film_siren_fwd -- 1 / 2 the two-tile ping-pong kernel (this file) with slot-bound /
+// shared epilogue warps, 3 the layer-pipelined kernel (film_siren_tc3.cu), 0 back to CNG_TC_V / the built-in default.
+CNG_API void cng_internal_set_tc_version(int v) { cng::g_tc_version = (v >= 1 && v <= 3) ? v : 0; }
 
 size_t cng_film_siren_workspace_bytes(int B, int C, int HID, int L, int precision) {
   (void)C; (void)HID;

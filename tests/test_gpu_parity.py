@@ -184,6 +184,35 @@ def test_film_siren_bf16_matches_fp32_kernel_on_large_batch(ops):
     assert (a - b).abs().max().item() < 1e-2
 
 
+@pytest.mark.parametrize("siren_type", ["TALLSIREN_FG", "SHORTSIREN_FG", "DOUBLESIREN_FG", "SingleSIREN_dg"])
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("B,N", [(1, 100), (3, 129), (5, 128 * 9), (2, 128 * 700 + 17)])
+def test_film_siren_pipelined_kernel_is_bit_identical_to_ping_pong_kernel(ops, siren_type, precision, B, N):
+    """The layer-pipelined tcgen05 kernel (film_siren_tc3.cu: one tile per CTA, double-buffered accumulator, the next
+    layer's MMAs follow the epilogue sub-block by sub-block) against the two-tile ping-pong kernel (film_siren_tc.cu):
+    same operands, same accumulation order, same sine -> the same bits; also within the oracle tolerance.  Covers ragged
+    last tiles, item changes inside a CTA's tile sequence (B > 1) and multi-wave launches."""
+    import ctypes
+    from conditioned_nerf_gan_b200 import _lib
+    lib = _lib.load()
+    lib.cng_internal_set_tc_version.argtypes = [ctypes.c_int]
+    lib.cng_internal_set_tc_version.restype = None
+    spec, ws, bs, feat, freq, phase, fw, fb, ref = _mlp_setup(siren_type, B, N, 0.3)
+    try:
+        lib.cng_internal_set_tc_version(1)
+        a = _run_mlp(ops, precision, spec, ws, bs, feat, freq, phase, fw, fb)
+        lib.cng_internal_set_tc_version(3)
+        b = _run_mlp(ops, precision, spec, ws, bs, feat, freq, phase, fw, fb)
+        lib.cng_internal_set_tc_version(2)          # ping-pong kernel with the epilogue warps shared between the slots
+        c = _run_mlp(ops, precision, spec, ws, bs, feat, freq, phase, fw, fb)
+    finally:
+        lib.cng_internal_set_tc_version(0)
+    assert torch.equal(a, b), f"max |v1 - v3| = {(a - b).abs().max().item():.3e}"
+    assert torch.equal(a, c), f"max |v1 - v2| = {(a - c).abs().max().item():.3e}"
+    tol = 3e-2 if (precision == "bf16" and siren_type == "SHORTSIREN_FG") else 1e-2
+    assert (b - ref).abs().max().item() < tol
+
+
 # ------------------------------------------------------------------------------------------------
 # a8: compositing
 # ------------------------------------------------------------------------------------------------
