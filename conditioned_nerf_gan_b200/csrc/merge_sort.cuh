@@ -143,13 +143,14 @@ __host__ __device__ inline int merge_smem_words(int n, int S) { return next_pow2
 __device__ __forceinline__ void load_and_sort_ray(unsigned long long* keys, const float* __restrict__ t_fine,
                                                   const float* __restrict__ t_coarse, long long ray, int S, int n, int n2, int lane) {
   const bool two = t_fine != nullptr;
-  if (two && S <= 128 && coarse_is_sorted(t_coarse, ray, S, lane)) {
+  if (two && S <= 256 && coarse_is_sorted(t_coarse, ray, S, lane)) {
     unsigned long long* fine_s = keys + n2;
     unsigned long long* coarse_s = fine_s + next_pow2_min32(S);
     switch (next_pow2_min32(S)) {
       case 32: sort_fine_and_merge<1>(keys, fine_s, coarse_s, t_fine, t_coarse, ray, S, lane); return;
       case 64: sort_fine_and_merge<2>(keys, fine_s, coarse_s, t_fine, t_coarse, ray, S, lane); return;
-      default: sort_fine_and_merge<4>(keys, fine_s, coarse_s, t_fine, t_coarse, ray, S, lane); return;
+      case 128: sort_fine_and_merge<4>(keys, fine_s, coarse_s, t_fine, t_coarse, ray, S, lane); return;
+      default: sort_fine_and_merge<8>(keys, fine_s, coarse_s, t_fine, t_coarse, ray, S, lane); return;
     }
   }
   // up to 256 keys: sort in registers (1 to 8 keys per lane)

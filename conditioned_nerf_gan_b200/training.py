@@ -52,7 +52,8 @@ class GanTrainStep:
         self.metadata = dict(metadata)
         self.generator, self.encoder, self.discriminator = generator, encoder, discriminator
         self.amp, self.amp_dtype = amp and self.device.type == "cuda", amp_dtype
-        wrap = (lambda m, unused: torch.nn.parallel.DistributedDataParallel(m, device_ids=[local_rank], find_unused_parameters=unused)) \
+        ids = [local_rank] if self.device.type == "cuda" else None          # gloo / CPU (tests): no device ids
+        wrap = (lambda m, unused: torch.nn.parallel.DistributedDataParallel(m, device_ids=ids, find_unused_parameters=unused)) \
             if ddp else (lambda m, unused: m)
         # utils.py:321-326, 344-348, 385-389: generator and discriminator with find_unused_parameters, the encoder without
         self.generator_ddp = wrap(generator, True)

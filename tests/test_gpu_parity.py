@@ -335,7 +335,7 @@ def test_sample_pdf_properties_full_size(ops):
 # ------------------------------------------------------------------------------------------------
 # a11 + a8 + a12: merge, composite, image formatting
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("B,img,S", [(2, 8, 6), (1, 16, 24), (2, 4, 48), (1, 4, 100)])
+@pytest.mark.parametrize("B,img,S", [(2, 8, 6), (1, 16, 24), (2, 4, 48), (1, 4, 100), (1, 4, 128), (1, 3, 200), (1, 3, 256), (1, 2, 300)])
 @pytest.mark.parametrize("white,last,noise_std,clamp", [(True, False, 0.0, "relu"), (False, True, 0.5, "softplus")])
 def test_merge_composite_vs_oracle(ops, B, img, S, white, last, noise_std, clamp):
     from conditioned_nerf_gan_b200.generators.volumetric_rendering import camera_tables
@@ -350,6 +350,7 @@ def test_merge_composite_vs_oracle(ops, B, img, S, white, last, noise_std, clamp
     t_f = torch.sort(torch.rand((B, R, S, 1), generator=g) * 1.7 + 0.25, dim=2).values
     t_f[0, 0, :3] = t_c[0, 0, :3]                 # exact ties: stable order puts the fine sample first
     t_f[0, 1] = t_f[0, 1, 0]                      # a run of equal fine distances
+    t_c[0, 2] = t_c[0, 2].flip(0)                 # a ray whose coarse distances are NOT sorted: the general sort, not the sort-fine-and-merge path
     noise = torch.randn((B, R, 2 * S, 1), generator=g)
     rays, _ = camera_tables((img, img), S, FOV, 0.25, 1.95, "cuda")
     pixels, depth, taps = ops.merge_composite(dev(fine), dev(coarse), dev(t_f), dev(t_c), dev(noise), rays, B, img, img,

@@ -73,6 +73,70 @@ def test_world2_gloo(P):
     mp.spawn(_worker, args=(2, port, P), nprocs=2, join=True)
 
 
+def _train_worker(rank, world, port, out):
+    """The GAN train step under DDP (gloo, CPU): each rank trains on its shard of the batch; gradients are averaged once per
+    optimizer step (micro-batches under no_sync), so both ranks hold identical parameters afterwards and they equal a
+    single-process step on the whole batch."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    parallel.init_distributed("gloo")
+    from conditioned_nerf_gan_b200.discriminators import ProgressiveDiscriminator
+    from conditioned_nerf_gan_b200.generators.unet3d import UNet3D
+    from conditioned_nerf_gan_b200.training import GanTrainStep
+    from oracle import nerf_path as oracle
+    from oracle import train_step as ts
+    torch.set_num_threads(2)
+    enc, disc = UNet3D(**ts.TINY_UNET), ProgressiveDiscriminator()
+    ts.fill_params(enc, 1)
+    ts.fill_params(disc, 2)
+    gen = ts.OracleGenerator(ts.TINY_SIREN, oracle.init_generator_state(ts.TINY_SIREN, z_dim=ts.TINY_ZDIM, seed=0))
+    sample = ts.tiny_sample()
+    draws = ts.tiny_draws()
+    lo, hi = parallel.shard_range(ts.TINY_BATCH, rank, world)
+    R = ts.tiny_config()["img_size"] ** 2
+    shard = {k: v[lo:hi] for k, v in sample.items()}
+    shard_draws = {k: (v[lo * R:hi * R] if k == "u_resample" else v[lo:hi]) for k, v in draws.items()}
+    md = dict(ts.tiny_config(), draws=shard_draws, r1_lambda=0)      # R1 is a per-rank mean of per-sample terms: same average either way
+    tr = GanTrainStep(gen, enc, disc, md, "cpu", amp=False, ddp=True)
+    tr.alpha = 0.3
+    tr.train_discriminator(shard)
+    tr.train_generator(shard)
+    flat = torch.cat([p.detach().reshape(-1) for m in (gen, enc, disc) for p in m.parameters()])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    assert torch.equal(gathered[0], gathered[1]), "ranks diverged after one DDP step"
+    if rank == 0:
+        torch.save({"norm_G": float(tr.grad_norms["G"]), "norm_E": float(tr.grad_norms["E"]), "norm_D": float(tr.grad_norms["D"]),
+                    "g_loss": float(tr.losses["g_loss"]), "checksum": float(flat.double().abs().sum())}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_gan_train_step(tmp_path):
+    from conditioned_nerf_gan_b200.discriminators import ProgressiveDiscriminator
+    from conditioned_nerf_gan_b200.generators.unet3d import UNet3D
+    from conditioned_nerf_gan_b200.training import GanTrainStep
+    from oracle import nerf_path as oracle
+    from oracle import train_step as ts
+    out = str(tmp_path / "ddp.pt")
+    mp.spawn(_train_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    ddp = torch.load(out)
+    # single process, whole batch
+    enc, disc = UNet3D(**ts.TINY_UNET), ProgressiveDiscriminator()
+    ts.fill_params(enc, 1)
+    ts.fill_params(disc, 2)
+    gen = ts.OracleGenerator(ts.TINY_SIREN, oracle.init_generator_state(ts.TINY_SIREN, z_dim=ts.TINY_ZDIM, seed=0))
+    tr = GanTrainStep(gen, enc, disc, dict(ts.tiny_config(), draws=ts.tiny_draws(), r1_lambda=0), "cpu", amp=False)
+    tr.alpha = 0.3
+    sample = ts.tiny_sample()
+    tr.train_discriminator(sample)
+    tr.train_generator(sample)
+    flat = torch.cat([p.detach().reshape(-1) for m in (gen, enc, disc) for p in m.parameters()])
+    # the generator / encoder see the mean over the batch of per-image losses: DDP's average of per-rank means is the same number
+    for k in ("norm_G", "norm_E", "norm_D"):
+        assert abs(ddp[k] - float(tr.grad_norms[k[-1]])) <= 2e-3 * abs(ddp[k]) + 1e-6, (k, ddp[k], float(tr.grad_norms[k[-1]]))
+    assert abs(ddp["checksum"] - float(flat.double().abs().sum())) <= 1e-5 * ddp["checksum"]
+
+
 def test_shard_range_partitions():
     for n in (0, 1, 7, 64, 65):
         for world in (1, 2, 3, 8):
