@@ -72,12 +72,27 @@ def render_meta(img_size, num_steps):
 
 def synthetic_inputs(batch, volume, seed):
     """Feature volume ~ N(0, 0.3^2), global ~ N(0.19, 0.05^2), look-at cameras on a shell."""
-    from oracle import nerf_path as oracle  # camera helpers only (numpy/torch CPU), not on the timed path
+    from conditioned_nerf_gan_b200.generators.volumetric_rendering import create_cam2world_matrix, sample_camera_positions
     g = torch.Generator().manual_seed(seed)
     vol = torch.randn((batch, WORKLOAD["channels"], volume, volume, volume), generator=g) * 0.3
     glob = torch.randn((batch, WORKLOAD["z_dim"]), generator=g) * 0.05 + 0.19
-    cam = oracle.look_at_cam2world(oracle.random_camera_origins(batch, 0.7, 1.5, "y", np.random.RandomState(seed)), "y")
+    st = np.random.get_state()
+    np.random.seed(seed)                      # sample_camera_positions draws from numpy's global generator, as the reference's does
+    cam = create_cam2world_matrix(sample_camera_positions("cpu", "y", 0.7, 1.5, batch), "y", "cpu")
+    np.random.set_state(st)
     return vol, glob, cam
+
+
+def random_init_generator(siren_type):
+    """Random-init weights of the named architecture: the module's own constructor applies the reference's init
+    (frequency_init / first_layer_film_sine_init, generators/siren.py:40-44, 134-143); seeded so that every rank and both
+    bench arms of one run build the same network."""
+    from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d
+    rng = torch.random.get_rng_state()
+    torch.manual_seed(0)
+    gen = ImplicitGenerator3d(siren_type, WORKLOAD["z_dim"], WORKLOAD["channels"], 4, 256)
+    torch.random.set_rng_state(rng)
+    return gen
 
 
 # --------------------------------------------------------------------------------------------------
@@ -193,8 +208,6 @@ def run_gpu(args):
     import torch.distributed as dist
 
     from conditioned_nerf_gan_b200 import _lib, ops
-    from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d
-    from oracle import nerf_path as oracle  # state init + (rank 0) cpu_baseline only
 
     _lib.load()
     rank = int(os.environ.get("RANK", "0"))
@@ -212,8 +225,7 @@ def run_gpu(args):
     R = img * img
     L = SIREN_LAYERS[args.siren]
     meta = render_meta(img, S)
-    gen = ImplicitGenerator3d(args.siren, WORKLOAD["z_dim"], WORKLOAD["channels"], 4, 256)
-    gen.load_state_dict(oracle.init_generator_state(args.siren, seed=0), strict=True)
+    gen = random_init_generator(args.siren)
     gen = gen.to(dev).eval()
     gen.set_device(dev)
     gen.siren.precision = args.precision
@@ -457,8 +469,6 @@ def run_train(args):
 def run_train_generator(args):
     """Generator-only train step (BASELINE config 3 minus the out-of-scope encoder / discriminator)."""
     import torch.distributed as dist
-    from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d
-    from oracle import nerf_path as oracle
     rank, world, local, dev, barrier, max_over_ranks = _setup_ranks(args)
     GLOBAL_B, img, S, V = 32, 128, 48, 64
     if GLOBAL_B % world:
@@ -466,8 +476,7 @@ def run_train_generator(args):
     b = GLOBAL_B // world
     meta = render_meta(img, S)
     meta["nerf_noise"] = 0.5
-    gen = ImplicitGenerator3d(args.siren, 256, 32, 4, 256)
-    gen.load_state_dict(oracle.init_generator_state(args.siren, seed=0), strict=True)
+    gen = random_init_generator(args.siren)
     gen = gen.to(dev)
     gen.set_device(dev)
     gen.siren.precision = args.precision
@@ -517,12 +526,10 @@ def run_video(args):
     """BASELINE config 4: 64 poses of one object, 256x256, 48+48 samples, poses sharded over the ranks."""
     import torch.distributed as dist
     from conditioned_nerf_gan_b200 import parallel
-    from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d
-    from oracle import nerf_path as oracle
+    from conditioned_nerf_gan_b200.generators.volumetric_rendering import create_cam2world_matrix
     rank, world, local, dev, barrier, max_over_ranks = _setup_ranks(args)
     P, img, S, V = 64, 256, 48, 64
-    gen = ImplicitGenerator3d(args.siren, 256, 32, 4, 256)
-    gen.load_state_dict(oracle.init_generator_state(args.siren, seed=0), strict=True)
+    gen = random_init_generator(args.siren)
     gen = gen.to(dev).eval()
     gen.set_device(dev)
     gen.siren.precision = args.precision
@@ -533,7 +540,7 @@ def run_video(args):
     k = torch.arange(P, dtype=torch.float32) / P
     theta, phi, r = 2 * np.pi * k, 0.35 * np.pi + 0.15 * np.pi * torch.sin(2 * np.pi * k), 1.2
     origin = torch.stack([r * torch.sin(phi) * torch.cos(theta), r * torch.cos(phi), r * torch.sin(phi) * torch.sin(theta)], -1)
-    poses = oracle.look_at_cam2world(origin, "y").to(dev)
+    poses = create_cam2world_matrix(origin, "y", "cpu").to(dev)
     fov = [60.0 - 30.0 * (i // 8) / (P // 8 - 1) for i in range(P)]        # piecewise constant so that chunks of 8 share a fov
     meta = {kk: v for kk, v in render_meta(img, S).items() if kk != "fov"}
     frames_h = torch.empty((P, 3, img, img), dtype=torch.float32).pin_memory() if rank == 0 else None

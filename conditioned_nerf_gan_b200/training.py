@@ -60,7 +60,10 @@ class GanTrainStep:
         self.encoder_ddp = wrap(encoder, False)
         self.discriminator_ddp = wrap(discriminator, True) if discriminator is not None else None
         md = self.metadata
-        adam = lambda params, lr: torch.optim.Adam(params, lr=lr, betas=tuple(float(b) for b in md.get("betas", (0, 0.9))), weight_decay=md.get("weight_decay", 0))
+        # utils.py:327-338, 353-358, 392-397; fused=True on CUDA: one multi-tensor kernel per optimizer step instead of a
+        # dozen foreach launches (the 8-GPU step at 4 images per GPU is launch-bound), same update rule
+        adam = lambda params, lr: torch.optim.Adam(params, lr=lr, betas=tuple(float(b) for b in md.get("betas", (0, 0.9))),
+                                                   weight_decay=md.get("weight_decay", 0), fused=self.device.type == "cuda")
         self.optimizer_G = adam(self.generator_ddp.parameters(), md["gen_lr"])
         self.optimizer_E = adam(self.encoder_ddp.parameters(), md["enc_lr"])
         self.optimizer_D = adam(self.discriminator_ddp.parameters(), md["disc_lr"]) if discriminator is not None else None
