@@ -31,6 +31,7 @@ struct SimtParams {
   int sigmoid_rgb;
   float* out;              // [B, N, 4]
   long long tiles_per_item;
+  unsigned res_save_mask, res_add_mask;    // residual blocks (generators/siren.py:218-230), see film_siren_tc_common.cuh
 };
 
 // HID is fixed at 256 (one output per (lane, j) pair: 32 lanes x 8).
@@ -42,6 +43,7 @@ __global__ void __launch_bounds__(256, 1) film_siren_simt_kernel(SimtParams p) {
   float* act1 = act0 + kSimtTM * LD;            // [64][LD]
   float* wc = act1 + kSimtTM * LD;              // [16][HID]
   float* wf = wc + kSimtKC * HID;               // [HID][4]
+  float* res = wf + HID * 4;                    // [64][LD], only allocated when a residual mask is set
 
   const int tid = threadIdx.x, lane = tid & 31, ty = tid >> 5;
   const long long item = blockIdx.x / p.tiles_per_item;
@@ -106,9 +108,15 @@ __global__ void __launch_bounds__(256, 1) film_siren_simt_kernel(SimtParams p) {
     for (int j = 0; j < 8; ++j) {
       const int o = lane + 32 * j;
       const float bias = __ldg(p.b[l] + o), fq = __ldg(fr + o), pq = __ldg(ph + o);
+      const bool add = (p.res_add_mask >> l) & 1u, save = (p.res_save_mask >> l) & 1u;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        outb[(ty * 8 + i) * LD + o] = sinf(__fadd_rn(__fmul_rn(fq, __fadd_rn(acc[i][j], bias)), pq));
+      for (int i = 0; i < 8; ++i) {
+        float u = __fadd_rn(__fmul_rn(fq, __fadd_rn(acc[i][j], bias)), pq);
+        if (add) u = __fadd_rn(res[(ty * 8 + i) * LD + o], u);          // sin(x + fc2(net)), ResSirenBlock.forward
+        const float y = sinf(u);
+        outb[(ty * 8 + i) * LD + o] = y;
+        if (save) res[(ty * 8 + i) * LD + o] = y;                       // same thread reads it back: no barrier needed
+      }
     }
     float* tmp = in; in = outb; outb = tmp;
   }
@@ -170,7 +178,8 @@ __global__ void __launch_bounds__(256) film_parameters_kernel(const float* __res
 
 int film_siren_simt_launch(const float* feat, int B, long long N, int C, int HID, int L, const float* const* w,
                            const float* const* b, const float* freq, const float* phase, const float* final_w,
-                           const float* final_b, int sigmoid_rgb, float* out, cudaStream_t stream) {
+                           const float* final_b, int sigmoid_rgb, float* out, cudaStream_t stream, unsigned res_save_mask,
+                           unsigned res_add_mask) {
   CNG_REQUIRE(HID == 256, CNG_ERR_UNSUPPORTED, "film_siren_fwd(fp32): HID=%d (only 256 is built)", HID);
   CNG_REQUIRE(L >= 1 && L <= kSimtMaxL, CNG_ERR_UNSUPPORTED, "film_siren_fwd(fp32): L=%d", L);
   CNG_REQUIRE(C >= 1 && C <= 256, CNG_ERR_UNSUPPORTED, "film_siren_fwd(fp32): C=%d", C);
@@ -178,10 +187,11 @@ int film_siren_simt_launch(const float* feat, int B, long long N, int C, int HID
   p.feat = feat; p.N = N; p.B = B; p.C = C; p.HID = HID; p.L = L;
   for (int l = 0; l < L; ++l) { p.w[l] = w[l]; p.b[l] = b[l]; }
   p.freq = freq; p.phase = phase; p.final_w = final_w; p.final_b = final_b; p.sigmoid_rgb = sigmoid_rgb; p.out = out;
+  p.res_save_mask = res_save_mask; p.res_add_mask = res_add_mask;
   p.tiles_per_item = (N + kSimtTM - 1) / kSimtTM;
   const long long blocks = p.tiles_per_item * B;
   CNG_REQUIRE(blocks < 0x7fffffffLL, CNG_ERR_UNSUPPORTED, "film_siren_fwd(fp32): too many tiles");
-  const size_t smem = (2 * kSimtTM * (256 + 4) + kSimtKC * 256 + 256 * 4) * sizeof(float);
+  const size_t smem = ((2 + ((res_save_mask | res_add_mask) ? 1 : 0)) * kSimtTM * (256 + 4) + kSimtKC * 256 + 256 * 4) * sizeof(float);
   cudaFuncSetAttribute(film_siren_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   film_siren_simt_kernel<<<static_cast<unsigned>(blocks), 256, smem, stream>>>(p);
   return check_launch("cng_film_siren_fwd(fp32)");

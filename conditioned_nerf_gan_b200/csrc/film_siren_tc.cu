@@ -429,6 +429,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
     const int ts = (warp % kEpiWarpsPerSlot) * 32 + lane;
     float* row_x = reinterpret_cast<float*>(smem + kSmemShift) + x * kHID;
     float row_next[kRowPerThread];
+    const bool res_mode = (p.res_save_mask | p.res_add_mask) != 0u;
     auto publish_row = [&]() {
       named_bar_sync(1 + x, kSlotThreads);            // every warp of the slot is done reading the old row
 #pragma unroll
@@ -487,6 +488,26 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
               v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + sv.y);
               v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + sv.z);
               v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + sv.w);
+            }
+          }
+          if (res_mode) {                                          // warp-uniform; only the residual SIREN variants
+            float4* rsd = reinterpret_cast<float4*>(p.res_scratch) + (static_cast<size_t>(blockIdx.x) * 2 + x) * (kHID / 4) * kTileM;
+            if ((p.res_add_mask >> l) & 1u) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 r4 = rsd[static_cast<size_t>(cc * 8 + i) * kTileM + row];
+                v[4 * i] = __float_as_uint(__uint_as_float(v[4 * i]) + r4.x);
+                v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + r4.y);
+                v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + r4.z);
+                v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + r4.w);
+              }
+            }
+            if ((p.res_save_mask >> l) & 1u) {                     // this layer's output in fp32 (the operand copy below is 16-bit)
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                rsd[static_cast<size_t>(cc * 8 + i) * kTileM + row] =
+                    make_float4(__sinf(__uint_as_float(v[4 * i])), __sinf(__uint_as_float(v[4 * i + 1])),
+                                __sinf(__uint_as_float(v[4 * i + 2])), __sinf(__uint_as_float(v[4 * i + 3])));
             }
           }
           if constexpr (kTrain) {
@@ -631,7 +652,8 @@ size_t film_siren_tc_workspace(int B, int L) {
 int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, int L, const float* const* w,
                          const float* const* b, const float* freq, const float* phase, const float* final_w,
                          const float* final_b_dev, int sigmoid_rgb, int half_operands, void* workspace, size_t workspace_bytes,
-                         float* out, void* dump_x, void* dump_g, cudaStream_t stream) {
+                         float* out, void* dump_x, void* dump_g, cudaStream_t stream, unsigned res_save_mask = 0, unsigned res_add_mask = 0,
+                         float* res_scratch = nullptr) {
   CNG_REQUIRE(HID == kHID && C == kC0, CNG_ERR_UNSUPPORTED, "film_siren_fwd(bf16): needs HID=256, C=32 (got %d, %d)", HID, C);
   CNG_REQUIRE(L >= 1 && L <= 16, CNG_ERR_UNSUPPORTED, "film_siren_fwd(bf16): L=%d", L);
   CNG_REQUIRE(workspace != nullptr && workspace_bytes >= film_siren_tc_workspace(B, L), CNG_ERR_WORKSPACE,
@@ -657,6 +679,9 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
   CNG_REQUIRE(((reinterpret_cast<uintptr_t>(dump_x) | reinterpret_cast<uintptr_t>(dump_g)) & 15) == 0, CNG_ERR_INVALID_ARGUMENT,
               "film_siren_fwd_train: dump buffers not 16-byte aligned");
   p.trace = g_tc_trace;
+  p.res_save_mask = res_save_mask; p.res_add_mask = res_add_mask; p.res_scratch = res_scratch;
+  CNG_REQUIRE(((res_save_mask | res_add_mask) == 0) || res_scratch != nullptr, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd: residual masks without a scratch buffer");
+  CNG_REQUIRE(((res_save_mask | res_add_mask) >> L) == 0, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd: residual mask bit beyond layer %d", L - 1);
   p.feat = feat; p.N = N; p.B = B; p.L = L; p.images = fp.images; p.shift = fp.shift;
   CNG_REQUIRE((reinterpret_cast<uintptr_t>(final_b_dev) & 15) == 0, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd(bf16): final_b not 16-byte aligned");
   p.final_b = final_b_dev;
@@ -683,7 +708,7 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
     const int v = e ? atoi(e) : kDefaultKernelVersion;
     return (v >= 1 && v <= 3) ? v : kDefaultKernelVersion;
   }();
-  const int ver = g_tc_version ? g_tc_version : version;
+  const int ver = (res_save_mask | res_add_mask) ? 1 : (g_tc_version ? g_tc_version : version);     // residual blocks: the slot-bound kernel
   if (ver == 3 && !train && L <= 8) return film_siren_tc3_launch(p, poly, stream);
   const bool shared = (ver == 2) && !train;
   using KernelFn = void (*)(TcParams);
@@ -709,7 +734,8 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
 // defined in film_siren_simt.cu
 int film_siren_simt_launch(const float* feat, int B, long long N, int C, int HID, int L, const float* const* w,
                            const float* const* b, const float* freq, const float* phase, const float* final_w,
-                           const float* final_b, int sigmoid_rgb, float* out, cudaStream_t stream);
+                           const float* final_b, int sigmoid_rgb, float* out, cudaStream_t stream, unsigned res_save_mask = 0,
+                           unsigned res_add_mask = 0);
 
 }  // namespace cng
 
@@ -749,6 +775,37 @@ int cng_film_siren_fwd(const float* feat, int B, long long N, int C, int HID, in
                                      sigmoid_rgb, precision == CNG_PREC_FP16 ? 1 : 0, workspace, workspace_bytes, rgb_sigma,
                                      nullptr, nullptr, cng::as_stream(stream));
   return cng::fail(CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd: unknown precision %d", precision);
+}
+
+size_t cng_film_siren_res_scratch_bytes(void) {
+  if (cng_device_check() != CNG_OK) return 0;
+  return static_cast<size_t>(cng::sm_count()) * 2 * cng::kResScratchPerSlot;
+}
+
+int cng_film_siren_fwd_res(const float* feat, int B, long long N, int C, int HID, int L, const float* const* layer_w_host,
+                           const float* const* layer_b_host, const float* freq, const float* phase, const float* final_w,
+                           const float* final_b, int sigmoid_rgb, int precision, unsigned res_save_mask, unsigned res_add_mask,
+                           void* workspace, size_t workspace_bytes, void* res_scratch, size_t res_scratch_bytes, float* rgb_sigma,
+                           cng_stream_t stream) {
+  CNG_REQUIRE(B >= 0 && N >= 0 && C >= 1 && HID >= 1 && L >= 1, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd_res: bad shape");
+  if (B == 0 || N == 0) return CNG_OK;
+  CNG_REQUIRE(feat && layer_w_host && layer_b_host && freq && phase && final_w && final_b && rgb_sigma,
+              CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd_res: NULL pointer");
+  for (int l = 0; l < L && l < 16; ++l)
+    CNG_REQUIRE(layer_w_host[l] && layer_b_host[l], CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd_res: NULL layer %d", l);
+  CNG_REQUIRE(L <= 16 && ((res_save_mask | res_add_mask) >> L) == 0, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd_res: mask bit beyond layer %d", L - 1);
+  if (int e = cng_device_check()) return e;
+  if (precision == CNG_PREC_FP32)
+    return cng::film_siren_simt_launch(feat, B, N, C, HID, L, layer_w_host, layer_b_host, freq, phase, final_w, final_b,
+                                       sigmoid_rgb, rgb_sigma, cng::as_stream(stream), res_save_mask, res_add_mask);
+  CNG_REQUIRE(precision == CNG_PREC_BF16 || precision == CNG_PREC_FP16, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd_res: unknown precision %d", precision);
+  CNG_REQUIRE((res_save_mask | res_add_mask) == 0 || (res_scratch != nullptr && res_scratch_bytes >= cng_film_siren_res_scratch_bytes() &&
+                                                      (reinterpret_cast<uintptr_t>(res_scratch) & 15) == 0),
+              CNG_ERR_WORKSPACE, "film_siren_fwd_res: residual scratch %zu < %zu bytes (or misaligned)", res_scratch_bytes,
+              cng_film_siren_res_scratch_bytes());
+  return cng::film_siren_tc_launch(feat, B, N, C, HID, L, layer_w_host, layer_b_host, freq, phase, final_w, final_b, sigmoid_rgb,
+                                   precision == CNG_PREC_FP16 ? 1 : 0, workspace, workspace_bytes, rgb_sigma, nullptr, nullptr,
+                                   cng::as_stream(stream), res_save_mask, res_add_mask, static_cast<float*>(res_scratch));
 }
 
 int cng_film_siren_fwd_train(const float* feat, int B, long long N, int C, int HID, int L, const float* const* layer_w_host,

@@ -260,7 +260,13 @@ struct TcParams {
   __nv_bfloat16* dump_g;    // holds fp16 bit patterns
   const float* freq;        // [B, L*256], only read when dumping
   long long* trace;         // debug: clock64 timeline of CTA 0 (tools/trace_tc.py), NULL in production
+  // residual blocks (TALLSIREN_dRes, generators/siren.py:218-230): bit l of res_save_mask = layer l's output is kept as the
+  // residual, bit l of res_add_mask = the kept residual is added to layer l's pre-activation.  res_scratch: per CTA and
+  // tile slot a [64 column quads][128 rows] float4 block (128 KB, stays in L2), lane-contiguous so every access coalesces.
+  uint32_t res_save_mask, res_add_mask;
+  float* res_scratch;
 };
+constexpr size_t kResScratchPerSlot = static_cast<size_t>(kHID / 4) * kTileM * sizeof(float4);      // 131072
 // trace layout: [iter < 4][layer <= 8][slot < 2][event < 8]; events: 0 MMA thread saw act_ready, 1 MMAs issued,
 // 2 epilogue (warp 0 of the slot) saw acc_full, 3 epilogue done (before its arrive), 4 cycles the MMA thread
 // spent waiting for weight blocks of this slot-layer, 5 cycles it spent issuing MMAs + commits

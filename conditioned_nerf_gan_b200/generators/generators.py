@@ -59,6 +59,9 @@ class ImplicitGenerator3d(nn.Module):
             volume.requires_grad or (global_feature is not None and global_feature.requires_grad)
             or any(p.requires_grad for p in self.siren.parameters()))
         if needs_grad:
+            if self.siren.res_add_mask:
+                raise NotImplementedError(f"{type(self.siren).__name__}: the backward of the residual blocks is not built; render under "
+                                          "torch.no_grad() (or freeze the generator and detach z)")
             from .autograd import render_with_grad
             return render_with_grad(self, volume, global_feature, cam2worlds, img_size, fov, ray_start, ray_end,
                                     num_steps, hierarchical_sample, kwargs)
@@ -89,7 +92,7 @@ class ImplicitGenerator3d(nn.Module):
             t = draws.get(name)
             return fn(shape, device=dev) if t is None else t.to(dev)
 
-        if not taps and kwargs.get("fused_call", True):
+        if not taps and kwargs.get("fused_call", True) and not net.res_add_mask:
             # production path: one C-ABI call (cng_render_fwd) sequences K1, K2, K3, K4, K1', K2, K3'; draws in the reference's order
             u_jitter = draw("u_jitter", torch.rand, (B, R, S, 1))
             ws, bs = net.layer_parameters()

@@ -23,7 +23,7 @@ import torch.nn.functional as F
 
 from .. import ops
 
-__all__ = ["FiLMLayer", "SirenLayer", "TALLSIREN_FG", "SHORTSIREN_FG", "DOUBLESIREN_FG", "SingleSIREN_dg", "SHORTSIREN_F",
+__all__ = ["FiLMLayer", "SirenLayer", "ResSirenBlock", "TALLSIREN_dRes", "TALLSIREN_FG", "SHORTSIREN_FG", "DOUBLESIREN_FG", "SingleSIREN_dg", "SHORTSIREN_F",
            "TALLSIREN_dg", "SHORTSIREN_dg", "DoubleSIREN_dg", "DOUBLESIREN_dg", "default_precision"]
 
 
@@ -96,14 +96,22 @@ class _FiLMSirenFG(nn.Module):
             half = fo.shape[-1] // 2
             return (fo[..., :half] * 15 + 30).contiguous(), fo[..., half:].contiguous()
 
+    res_save_mask = 0       # residual blocks, see cng_film_siren_fwd_res (include/cng_b200.h)
+    res_add_mask = 0
+
+    def linear_layers(self) -> List[nn.Linear]:
+        """The network's linear layers in execution order."""
+        return [f.layer for f in self.network]
+
     def layer_parameters(self) -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
-        return [f.layer.weight for f in self.network], [f.layer.bias for f in self.network]
+        lin = self.linear_layers()
+        return [m.weight for m in lin], [m.bias for m in lin]
 
     def mlp(self, feat: torch.Tensor, freq: torch.Tensor, phase: torch.Tensor) -> torch.Tensor:
         """feat [B,N,C] -> rgb_sigma [B,N,4] through the fused FiLM-SIREN kernel."""
         ws, bs = self.layer_parameters()
         return ops.film_siren_fwd(feat, ws, bs, freq, phase, self.final_layer.weight, self.final_layer.bias,
-                                  self.sigmoid_rgb, self.precision)
+                                  self.sigmoid_rgb, self.precision, self.res_save_mask, self.res_add_mask)
 
     def split_z(self, z):
         if not self.film:
@@ -121,6 +129,8 @@ class _FiLMSirenFG(nn.Module):
         volume, global_feature = self.split_z(z)
         if torch.is_grad_enabled() and (volume.requires_grad or (global_feature is not None and global_feature.requires_grad)
                                         or any(p.requires_grad for p in self.parameters())):
+            if self.res_add_mask:
+                raise NotImplementedError(f"{type(self).__name__}: the backward of the residual blocks is not built; call under torch.no_grad()")
             from .autograd import siren_forward_with_grad
             return siren_forward_with_grad(self, points, volume, global_feature)
         freq, phase = self.film_parameters(global_feature, volume.shape[0], volume.device)
@@ -152,6 +162,46 @@ class SHORTSIREN_F(_FiLMSirenFG):
     mapping network; ``z`` is the feature volume.  Runs on the same kernels with freq = 1, phase = 0."""
     num_layers, freq_div, sigmoid_rgb, film = 4, 12.0, True, False
     tensor_core_operands = "fp16"
+
+
+class ResSirenBlock(nn.Module):
+    """Parameter holder of ``y = sin(x + fc2(sin(fc1 x)))`` (siren.py:218-230); the arithmetic runs inside the fused kernel."""
+
+    def __init__(self, hidden_dim: int):
+        super().__init__()
+        self.fc1 = nn.Linear(hidden_dim, hidden_dim)
+        self.fc2 = nn.Linear(hidden_dim, hidden_dim)
+
+
+class TALLSIREN_dRes(_FiLMSirenFG):
+    """generators/siren.py:333-408 (configs/thousand/direct_volume/dRes.py): feature volume only; SirenLayer, two residual
+    blocks, SirenLayer, raw ``nn.Linear(hidden, 4)`` head (no sigmoid on rgb); the first layer reads ``z_dim`` features
+    (``input_dim = z_dim``, :355).  Six linear layers on the same fused kernels (freq = 1, phase = 0); the block input is
+    kept in fp32 next to the kernel's 16-bit operand tile and added to the second layer's pre-activation
+    (``cng_film_siren_fwd_res``).  State-dict keys as in the reference: ``network.0.layer.*``, ``network.{1,2}.fc{1,2}.*``,
+    ``network.3.layer.*``, ``final_layer.*``.  Inference only in this round: the backward of the residual blocks is not built
+    and asking for gradients raises."""
+    num_layers, freq_div, sigmoid_rgb, film = 6, 25.0, False, False
+    res_save_mask, res_add_mask = 0b000101, 0b010100
+
+    def __init__(self, input_dim=3, z_dim=100, hidden_dim=256, output_dim=4, drop_out=0, device=None, **kwargs):
+        nn.Module.__init__(self)
+        input_dim = z_dim
+        self.device = device
+        self.input_dim, self.z_dim, self.hidden_dim, self.output_dim = input_dim, z_dim, hidden_dim, output_dim
+        self.network = nn.ModuleList([SirenLayer(input_dim, hidden_dim, drop_out), ResSirenBlock(hidden_dim), ResSirenBlock(hidden_dim),
+                                      SirenLayer(hidden_dim, hidden_dim, drop_out)])
+        self.final_layer = nn.Linear(hidden_dim, 4)
+        for i, lin in enumerate(self.linear_layers()):
+            fan_in = lin.weight.shape[-1]
+            # network.apply(frequency_init(25)) then network[0].apply(first_layer_film_sine_init), siren.py:372-375
+            _uniform_(lin, 1.0 / fan_in if i == 0 else math.sqrt(6.0 / fan_in) / self.freq_div)
+        _uniform_(self.final_layer, math.sqrt(6.0 / hidden_dim) / self.freq_div)
+        self.precision = default_precision(self.tensor_core_operands)
+
+    def linear_layers(self) -> List[nn.Linear]:
+        n = self.network
+        return [n[0].layer, n[1].fc1, n[1].fc2, n[2].fc1, n[2].fc2, n[3].layer]
 
 
 # config spellings (SURVEY.md appendix C)

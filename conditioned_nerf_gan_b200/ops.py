@@ -179,9 +179,24 @@ def film_parameters(global_feature, map_w, map_b) -> Tuple[torch.Tensor, torch.T
     return freq, phase
 
 
+_RES_SCRATCH = {}
+
+
+def _res_scratch(dev) -> torch.Tensor:
+    """Device buffer for the kept activations of residual blocks (cng_film_siren_res_scratch_bytes, one per device)."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    buf = _RES_SCRATCH.get(key)
+    if buf is None:
+        with torch.cuda.device(dev):
+            n = int(_lib.load().cng_film_siren_res_scratch_bytes())
+        buf = _RES_SCRATCH[key] = torch.empty((max(n, 16),), dtype=torch.uint8, device=dev)
+    return buf
+
+
 def film_siren_fwd(feat, layer_w: Sequence[torch.Tensor], layer_b: Sequence[torch.Tensor], freq, phase, final_w,
-                   final_b, sigmoid_rgb: bool, precision: str = "bf16") -> torch.Tensor:
-    """K2.  feat [B,N,C], freq/phase [B,L*HID] -> rgb_sigma [B,N,4]."""
+                   final_b, sigmoid_rgb: bool, precision: str = "bf16", res_save_mask: int = 0, res_add_mask: int = 0) -> torch.Tensor:
+    """K2.  feat [B,N,C], freq/phase [B,L*HID] -> rgb_sigma [B,N,4].  ``res_*_mask``: residual blocks, see
+    cng_film_siren_fwd_res in include/cng_b200.h."""
     if precision not in PRECISIONS:
         raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
     feat = _f32(feat, "feat")
@@ -202,6 +217,14 @@ def film_siren_fwd(feat, layer_w: Sequence[torch.Tensor], layer_b: Sequence[torc
     lib = _lib.load()
     ws_bytes = int(lib.cng_film_siren_workspace_bytes(B, C, HID, L, code))
     workspace = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev) if ws_bytes else None
+    if res_save_mask or res_add_mask:
+        scratch = _res_scratch(dev) if code != _lib.PREC_FP32 else None
+        with torch.cuda.device(dev), _timed("cng_film_siren_fwd"):
+            _lib.call("cng_film_siren_fwd_res", _ptr(feat), B, N, C, HID, L, w_arr, b_arr, _ptr(freq), _ptr(phase), _ptr(final_w),
+                      _ptr(final_b), int(bool(sigmoid_rgb)), code, int(res_save_mask), int(res_add_mask), _ptr(workspace), ws_bytes,
+                      _ptr(scratch), scratch.numel() if scratch is not None else 0, _ptr(out), _stream(feat))
+        _count(1 if code == _lib.PREC_FP32 else 2)
+        return out
     with torch.cuda.device(dev), _timed("cng_film_siren_fwd"):
         _lib.call("cng_film_siren_fwd", _ptr(feat), B, N, C, HID, L, w_arr, b_arr, _ptr(freq), _ptr(phase), _ptr(final_w),
                   _ptr(final_b), int(bool(sigmoid_rgb)), code, _ptr(workspace), ws_bytes, _ptr(out), _stream(feat))

@@ -144,6 +144,19 @@ CNG_API int cng_film_siren_fwd(const float* feat, int B, long long N, int C, int
                        const float* final_b, int sigmoid_rgb, int precision, void* workspace,
                        size_t workspace_bytes, float* rgb_sigma, cng_stream_t stream);
 
+/* K2 with residual blocks (TALLSIREN_dRes, generators/siren.py:218-230, 333-408: y = sin(x + fc2(sin(fc1 x)))).  The
+ * network is passed as its flat list of L linear layers; bit l of res_save_mask = layer l's output is kept as "x",
+ * bit l of res_add_mask = the kept x is added to layer l's pre-activation (a layer may do both: add, then keep).
+ * res_scratch: cng_film_siren_res_scratch_bytes() of device memory for the 16-bit modes (the kept activations of the
+ * tiles in flight, fp32, L2-resident), unused for CNG_PREC_FP32.  Masks 0 = cng_film_siren_fwd. */
+CNG_API size_t cng_film_siren_res_scratch_bytes(void);
+CNG_API int cng_film_siren_fwd_res(const float* feat, int B, long long N, int C, int HID, int L,
+                           const float* const* layer_w_host, const float* const* layer_b_host,
+                           const float* freq, const float* phase, const float* final_w, const float* final_b,
+                           int sigmoid_rgb, int precision, unsigned res_save_mask, unsigned res_add_mask,
+                           void* workspace, size_t workspace_bytes, void* res_scratch, size_t res_scratch_bytes,
+                           float* rgb_sigma, cng_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * K3: alpha compositing, one warp per ray, exclusive-cumprod transmittance by warp shuffles.
  * Replaces fancy_integration (volumetric_rendering.py:18-70).

@@ -32,6 +32,7 @@ import torch.nn.functional as F
 __all__ = [
     "VOXEL_LENGTH",
     "SIREN_SPECS",
+    "layer_keys",
     "resolve_siren_type",
     "init_generator_state",
     "camera_rays",
@@ -73,7 +74,18 @@ SIREN_SPECS = {
     # generators/siren.py:830-904: feature volume only, plain SirenLayer = sin(W x + b) (:180-199), no mapping network;
     # z is the feature volume itself (no global feature)
     "SHORTSIREN_F": {"layers": 4, "freq_init": 12.0, "sigmoid_rgb": True, "film": False},
+    # generators/siren.py:333-408: SirenLayer, ResSirenBlock x2 (:218-230: y = sin(x + fc2(sin(fc1 x)))), SirenLayer, raw head;
+    # feature volume only.  "layers" counts the linear layers in execution order; bit l of res_save: layer l's output is the
+    # block input "x" kept for later, bit l of res_add: the kept x is added to layer l's pre-activation.
+    "TALLSIREN_dRes": {"layers": 6, "freq_init": 25.0, "sigmoid_rgb": False, "film": False, "res_save": 0b000101, "res_add": 0b010100,
+                       "keys": ["network.0.layer", "network.1.fc1", "network.1.fc2", "network.2.fc1", "network.2.fc2", "network.3.layer"]},
 }
+
+
+def layer_keys(siren_type: str):
+    """State-dict prefixes (below ``siren.``) of the linear layers in execution order."""
+    spec = SIREN_SPECS[resolve_siren_type(siren_type)]
+    return spec.get("keys") or [f"network.{i}.layer" for i in range(spec["layers"])]
 
 # configs/thousand/direct_volume/dg.py:8,51,55,59 spell the classes differently from
 # generators/siren.py (SURVEY.md appendix C).
@@ -108,11 +120,11 @@ def init_generator_state(
         return (torch.rand(shape, generator=g) * 2 - 1) * bound
 
     state: Dict[str, torch.Tensor] = {}
-    for i in range(spec["layers"]):
+    for i, key in enumerate(layer_keys(siren_type)):
         fan_in = input_dim if i == 0 else hidden_dim
         w_bound = 1.0 / fan_in if i == 0 else math.sqrt(6.0 / fan_in) / spec["freq_init"]
-        state[f"siren.network.{i}.layer.weight"] = uniform((hidden_dim, fan_in), w_bound)
-        state[f"siren.network.{i}.layer.bias"] = uniform((hidden_dim,), 1.0 / math.sqrt(fan_in))
+        state[f"siren.{key}.weight"] = uniform((hidden_dim, fan_in), w_bound)
+        state[f"siren.{key}.bias"] = uniform((hidden_dim,), 1.0 / math.sqrt(fan_in))
     state["siren.final_layer.weight"] = uniform((4, hidden_dim), math.sqrt(6.0 / hidden_dim) / spec["freq_init"])
     state["siren.final_layer.bias"] = uniform((4,), 1.0 / math.sqrt(hidden_dim))
     if not spec.get("film", True):
@@ -276,7 +288,7 @@ def film_parameters(global_feature, map_weight, map_bias):
     return fo[..., :half] * 15 + 30, fo[..., half:]
 
 
-def film_siren_mlp(feat, layer_weights, layer_biases, freq, phase, final_w, final_b, sigmoid_rgb=True):
+def film_siren_mlp(feat, layer_weights, layer_biases, freq, phase, final_w, final_b, sigmoid_rgb=True, res_save=0, res_add=0):
     """generators/siren.py:573-579 + FiLMLayer.forward :153-160 + _sigmoid_rgb :1227-1234.
 
     feat [B,N,K0]; freq/phase [B, L*H]; returns rgb_sigma [B,N,4] (rgb through sigmoid iff
@@ -284,11 +296,17 @@ def film_siren_mlp(feat, layer_weights, layer_biases, freq, phase, final_w, fina
     """
     x = feat
     H = layer_weights[0].shape[0]
+    kept = None
     for i, (w, b) in enumerate(zip(layer_weights, layer_biases)):
         x = F.linear(x, w, b)
         fr = freq[:, i * H:(i + 1) * H].unsqueeze(1).expand_as(x)
         ph = phase[:, i * H:(i + 1) * H].unsqueeze(1).expand_as(x)
-        x = torch.sin(fr * x + ph)
+        u = fr * x + ph
+        if (res_add >> i) & 1:
+            u = kept + u                                 # ResSirenBlock.forward, siren.py:228: sin(x + net)
+        x = torch.sin(u)
+        if (res_save >> i) & 1:
+            kept = x
     out = F.linear(x, final_w, final_b)
     if sigmoid_rgb:
         out = torch.cat([torch.sigmoid(out[..., :3]), out[..., -1:]], dim=-1)
@@ -297,8 +315,8 @@ def film_siren_mlp(feat, layer_weights, layer_biases, freq, phase, final_w, fina
 
 def _split_state(state, siren_type):
     spec = SIREN_SPECS[resolve_siren_type(siren_type)]
-    ws = [state[f"siren.network.{i}.layer.weight"] for i in range(spec["layers"])]
-    bs = [state[f"siren.network.{i}.layer.bias"] for i in range(spec["layers"])]
+    ws = [state[f"siren.{k}.weight"] for k in layer_keys(siren_type)]
+    bs = [state[f"siren.{k}.bias"] for k in layer_keys(siren_type)]
     return spec, ws, bs
 
 
@@ -314,7 +332,7 @@ def siren_forward(state, siren_type, pts_world, z, img_size, num_steps):
         freq, phase = torch.ones((volume.shape[0], n)), torch.zeros((volume.shape[0], n))
     feat = trilinear_lookup(volume, pts_world, img_size, num_steps)
     return film_siren_mlp(feat, ws, bs, freq, phase, state["siren.final_layer.weight"],
-                          state["siren.final_layer.bias"], spec["sigmoid_rgb"])
+                          state["siren.final_layer.bias"], spec["sigmoid_rgb"], spec.get("res_save", 0), spec.get("res_add", 0))
 
 
 # --------------------------------------------------------------------------------------------

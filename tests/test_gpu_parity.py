@@ -131,12 +131,15 @@ def test_raymarch_fine_vs_oracle(ops, B, img, S, V):
 def _mlp_setup(siren_type, B, N, feat_std, seed=0):
     state = oracle.init_generator_state(siren_type, seed=seed)
     spec = oracle.SIREN_SPECS[oracle.resolve_siren_type(siren_type)]
-    ws = [state[f"siren.network.{i}.layer.weight"] for i in range(spec["layers"])]
-    bs = [state[f"siren.network.{i}.layer.bias"] for i in range(spec["layers"])]
+    ws = [state[f"siren.{k}.weight"] for k in oracle.layer_keys(siren_type)]
+    bs = [state[f"siren.{k}.bias"] for k in oracle.layer_keys(siren_type)]
     g = torch.Generator().manual_seed(seed + 10)
     feat = torch.randn((B, N, 32), generator=g) * feat_std
     glob = torch.randn((B, 256), generator=g) * 0.05 + 0.19
-    freq, phase = oracle.film_parameters(glob, state["siren.mapping_network.weight"], state["siren.mapping_network.bias"])
+    if spec.get("film", True):
+        freq, phase = oracle.film_parameters(glob, state["siren.mapping_network.weight"], state["siren.mapping_network.bias"])
+    else:
+        freq, phase = torch.ones((B, spec["layers"] * 256)), torch.zeros((B, spec["layers"] * 256))
     fw, fb = state["siren.final_layer.weight"], state["siren.final_layer.bias"]
     ref = oracle.film_siren_mlp(feat, ws, bs, freq, phase, fw, fb, spec["sigmoid_rgb"])
     return spec, ws, bs, feat, freq, phase, fw, fb, ref
@@ -211,6 +214,26 @@ def test_film_siren_pipelined_kernel_is_bit_identical_to_ping_pong_kernel(ops, s
     assert torch.equal(a, c), f"max |v1 - v2| = {(a - c).abs().max().item():.3e}"
     tol = 3e-2 if (precision == "bf16" and siren_type == "SHORTSIREN_FG") else 1e-2
     assert (b - ref).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 3e-2), ("fp16", 5e-3)])
+@pytest.mark.parametrize("B,N", [(1, 100), (3, 129), (2, 128 * 700 + 17)])
+def test_film_siren_residual_blocks_vs_oracle(ops, precision, tol, B, N):
+    """cng_film_siren_fwd_res: TALLSIREN_dRes as six linear layers with the block input kept and re-added (siren.py:218-230,
+    333-408); ragged tiles, several items, more tiles than CTAs (the kept activations live in a per-CTA scratch).  The
+    random-init network is nearly constant (outputs ~ 0.02), so the weights are amplified (hidden x6, head x10, features
+    ~ N(0,1)) until the residual paths move the output by 0.4 -- a wrong or missing residual cannot hide in the tolerance."""
+    spec, ws, bs, feat, freq, phase, fw, fb, _ = _mlp_setup("TALLSIREN_dRes", B, N, 1.0)
+    ws = [ws[0] * 12] + [w * 6 for w in ws[1:]]
+    fw = fw * 10
+    ref = oracle.film_siren_mlp(feat, ws, bs, freq, phase, fw, fb, spec["sigmoid_rgb"], spec["res_save"], spec["res_add"])
+    plain = oracle.film_siren_mlp(feat, ws, bs, freq, phase, fw, fb, spec["sigmoid_rgb"])
+    assert (ref - plain).abs().max().item() > 0.2
+    out = ops.film_siren_fwd(dev(feat), [dev(w) for w in ws], [dev(b) for b in bs], dev(freq), dev(phase), dev(fw), dev(fb),
+                             spec["sigmoid_rgb"], precision, spec["res_save"], spec["res_add"]).cpu()
+    err = (out - ref).abs().max().item()
+    print(f"TALLSIREN_dRes {precision} B={B} N={N}: max-abs err {err:.3e} (residual effect {(ref - plain).abs().max().item():.2f})")
+    assert err < tol, err
 
 
 # ------------------------------------------------------------------------------------------------
@@ -396,7 +419,8 @@ def test_merge_composite_coarse_only(ops):
 # ------------------------------------------------------------------------------------------------
 def _generator(siren_type, state, precision):
     from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d
-    gen = ImplicitGenerator3d(siren_type, 256, 32, 4, 256)
+    z_dim = 32 if siren_type == "TALLSIREN_dRes" else 256      # that class reads z_dim features (configs/thousand/direct_volume/dRes.py)
+    gen = ImplicitGenerator3d(siren_type, z_dim, 32, 4, 256)
     gen.load_state_dict(state, strict=True)
     gen = gen.to("cuda")
     gen.set_device(torch.device("cuda"))
@@ -422,7 +446,7 @@ def test_forward_vs_reference_golden(name, precision):
     assert pixels.shape == (B, 3, img, img) and depth.shape == (B, img, img) and pixels.is_contiguous()
     assert torch.allclose(out["points_coarse"].cpu(), taps["points_coarse"].reshape(B, -1, S, 3), rtol=0, atol=5e-7)
     mlp_tol = 5e-4 if precision == "fp32" else (3e-2 if ("SHORT" in name and precision == "bf16") else 1e-2)
-    if name == "fwd_SHORTSIREN_F" and precision == "bf16":
+    if name in ("fwd_SHORTSIREN_F", "fwd_TALLSIREN_dRes") and precision == "bf16":
         mlp_tol = 1e-2       # no freq ~ 30 in front of the pre-activations: bf16 operands are comfortably inside the bar
     err_c = (out["rgb_sigma_coarse"].cpu() - taps["rgb_sigma_coarse"].reshape(B, -1, S, 4)).abs().max().item()
     err_p = (pixels.cpu() - taps["pixels"]).abs().max().item()

@@ -131,6 +131,21 @@ def test_unmodulated_variant_layout():
         gen((torch.zeros(1, 32, 8, 8, 8), torch.zeros(1, 256)), torch.eye(4).unsqueeze(0), **META)
 
 
+def test_residual_variant_layout():
+    """TALLSIREN_dRes (generators/siren.py:333-408): the reference's module tree and keys, input_dim = z_dim, no mapping network,
+    raw head; gradients are refused loudly (the backward of the residual blocks is not built)."""
+    gen = ImplicitGenerator3d("TALLSIREN_dRes", 32, 3, 4, 256)          # input_dim is overridden by z_dim, as in the reference
+    ref_state = oracle.init_generator_state("TALLSIREN_dRes", input_dim=32)
+    assert list(gen.state_dict().keys()) == list(ref_state.keys())
+    assert "siren.network.1.fc2.weight" in ref_state and "siren.network.3.layer.bias" in ref_state
+    gen.load_state_dict(ref_state, strict=True)
+    assert gen.siren.res_save_mask == 0b000101 and gen.siren.res_add_mask == 0b010100 and not gen.siren.sigmoid_rgb
+    ws, bs = gen.siren.layer_parameters()
+    assert [tuple(w.shape) for w in ws] == [(256, 32)] + [(256, 256)] * 5 and len(bs) == 6
+    with pytest.raises(NotImplementedError):
+        gen(torch.zeros(1, 32, 8, 8, 8), torch.eye(4).unsqueeze(0), **META)
+
+
 def test_dense_grid_samples_match_oracle():
     """extract_shapes.create_samples mirror: same order, same (quirky, non-integer x / y index) coordinates."""
     from conditioned_nerf_gan_b200 import extract_shapes
