@@ -823,4 +823,23 @@ int cng_film_siren_fwd_train(const float* feat, int B, long long N, int C, int H
                                    workspace, workspace_bytes, rgb_sigma, x_dump_bf16, g_dump_bf16, cng::as_stream(stream));
 }
 
+int cng_film_siren_fwd_train_res(const float* feat, int B, long long N, int C, int HID, int L, const float* const* layer_w_host,
+                             const float* const* layer_b_host, const float* freq, const float* phase, const float* final_w,
+                             const float* final_b, int sigmoid_rgb, void* workspace, size_t workspace_bytes, float* rgb_sigma,
+                             void* x_dump_bf16, void* g_dump_bf16, unsigned res_save_mask, unsigned res_add_mask, void* res_scratch,
+                                 size_t res_scratch_bytes, cng_stream_t stream) {
+  CNG_REQUIRE(B >= 0 && N >= 0 && C >= 1 && HID >= 1 && L >= 1, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd_train: bad shape");
+  if (B == 0 || N == 0) return CNG_OK;
+  CNG_REQUIRE(feat && layer_w_host && layer_b_host && freq && phase && final_w && final_b && rgb_sigma && x_dump_bf16 && g_dump_bf16,
+              CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd_train: NULL pointer");
+  for (int l = 0; l < L && l < 16; ++l)
+    CNG_REQUIRE(layer_w_host[l] && layer_b_host[l], CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd_train: NULL layer %d", l);
+  if (int e = cng_device_check()) return e;
+  CNG_REQUIRE((res_save_mask | res_add_mask) == 0 || (res_scratch != nullptr && res_scratch_bytes >= cng_film_siren_res_scratch_bytes()),
+              CNG_ERR_WORKSPACE, "film_siren_fwd_train_res: residual scratch %zu < %zu bytes", res_scratch_bytes, cng_film_siren_res_scratch_bytes());
+  return cng::film_siren_tc_launch(feat, B, N, C, HID, L, layer_w_host, layer_b_host, freq, phase, final_w, final_b, sigmoid_rgb, 0,
+                                   workspace, workspace_bytes, rgb_sigma, x_dump_bf16, g_dump_bf16, cng::as_stream(stream), res_save_mask, res_add_mask,
+                                   static_cast<float*>(res_scratch));
+}
+
 }  // extern "C"

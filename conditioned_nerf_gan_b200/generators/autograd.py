@@ -98,12 +98,12 @@ class _FilmSiren(torch.autograd.Function):
     """K2 forward (fused, nothing saved per layer); backward recomputes the activations chunk by chunk."""
 
     @staticmethod
-    def forward(ctx, feat, freq, phase, final_w, final_b, sigmoid_rgb, precision, *wb):
+    def forward(ctx, feat, freq, phase, final_w, final_b, sigmoid_rgb, precision, res_save, res_add, *wb):
         L = len(wb) // 2
         ws, bs = list(wb[:L]), list(wb[L:])
-        out = ops.film_siren_fwd(feat, ws, bs, freq, phase, final_w, final_b, sigmoid_rgb, precision)
+        out = ops.film_siren_fwd(feat, ws, bs, freq, phase, final_w, final_b, sigmoid_rgb, precision, res_save, res_add)
         ctx.save_for_backward(feat, freq, phase, final_w, final_b, out, *wb)
-        ctx.sigmoid_rgb, ctx.L = sigmoid_rgb, L
+        ctx.sigmoid_rgb, ctx.L, ctx.res_save, ctx.res_add = sigmoid_rgb, L, res_save, res_add
         return out
 
     @staticmethod
@@ -112,7 +112,10 @@ class _FilmSiren(torch.autograd.Function):
         points and streams every layer's output x_{l+1} and local derivative g_l = freq*cos(u_l) to HBM (bf16); then, per
         layer from last to first:  dz = dy*g (cng_film_grad_from_g, with column sums),  dW += dz^T x_l and dy = dz W_l
         (cuBLAS bf16 GEMMs, fp32 accumulate),  db = colsum(dz),  dphase = colsum(dz)/freq,
-        dfreq = rowsum(W * dW_chunk)/freq + b * dphase."""
+        dfreq = rowsum(W * dW_chunk)/freq + b * dphase.
+        Residual blocks (``res_add`` / ``res_save`` masks, siren.py:218-230): g_l is taken at the pre-activation that includes
+        the re-added block input, so the per-layer rule is unchanged; the kept activation (output of the last ``save`` layer
+        before l) additionally receives dz_l of the adding layer."""
         feat, freq, phase, final_w, final_b, out, *wb = ctx.saved_tensors
         L, H = ctx.L, final_w.shape[1]
         ws, bs = [w.detach().float() for w in wb[:L]], [b.detach().float() for b in wb[L:]]
@@ -135,7 +138,8 @@ class _FilmSiren(torch.autograd.Function):
             for r0 in range(0, N, CHUNK_ROWS):
                 r1 = min(N, r0 + CHUNK_ROWS)
                 x0 = feat[b:b + 1, r0:r1].detach().contiguous()
-                _, xs, gs = ops.film_siren_fwd_train(x0, ws, bs, fr_all, ph_all, fw, fb, ctx.sigmoid_rgb)
+                _, xs, gs = ops.film_siren_fwd_train(x0, ws, bs, fr_all, ph_all, fw, fb, ctx.sigmoid_rgb, ctx.res_save, ctx.res_add)
+                pending = {}                                                   # save layer -> gradient arriving through the skip
                 xs, gs = xs[:, 0], gs[:, 0]                                    # [L, P, H]
                 # ---- head: out = x_L Wf^T + bf, rgb = sigmoid(out[:, :3])
                 d_o = d_out[b, r0:r1].clone()
@@ -151,6 +155,9 @@ class _FilmSiren(torch.autograd.Function):
                     sl = slice(l * H, (l + 1) * H)
                     colsum = torch.zeros((H,), dtype=torch.float32, device=dev)
                     dz = ops.film_grad_from_g(dy, gs[l], colsum)
+                    if (ctx.res_add >> l) & 1:
+                        kept = max(s for s in range(l) if (ctx.res_save >> s) & 1)
+                        pending[kept] = dz
                     x_in = xs[l - 1] if l > 0 else x0_bf
                     dW = torch.mm(dz.t(), x_in, out_dtype=torch.float32)       # this chunk's share, [H, K_l]
                     d_ws[l] += dW
@@ -162,8 +169,10 @@ class _FilmSiren(torch.autograd.Function):
                         d_feat[b, r0:r1] = torch.mm(dz, ws_bf[0], out_dtype=torch.float32)
                     else:
                         dy = torch.mm(dz, ws_bf[l])
+                        if (l - 1) in pending:
+                            dy = dy + pending.pop(l - 1)
                 del xs, gs
-        return (d_feat, d_freq, d_phase, d_fw.to(final_w.dtype), d_fb.to(final_b.dtype), None, None,
+        return (d_feat, d_freq, d_phase, d_fw.to(final_w.dtype), d_fb.to(final_b.dtype), None, None, None, None,
                 *[g.to(p.dtype) for g, p in zip(d_ws, wb[:L])], *[g.to(p.dtype) for g, p in zip(d_bs, wb[L:])])
 
 
@@ -191,7 +200,8 @@ class _MergeComposite(torch.autograd.Function):
 
 def _mlp(net, feat, freq, phase):
     ws, bs = net.layer_parameters()
-    return _FilmSiren.apply(feat, freq, phase, net.final_layer.weight, net.final_layer.bias, net.sigmoid_rgb, net.precision, *ws, *bs)
+    return _FilmSiren.apply(feat, freq, phase, net.final_layer.weight, net.final_layer.bias, net.sigmoid_rgb, net.precision,
+                            net.res_save_mask, net.res_add_mask, *ws, *bs)
 
 
 def render_with_grad(gen, volume, global_feature, cam2worlds, img_size, fov, ray_start, ray_end, num_steps,

@@ -59,9 +59,6 @@ class ImplicitGenerator3d(nn.Module):
             volume.requires_grad or (global_feature is not None and global_feature.requires_grad)
             or any(p.requires_grad for p in self.siren.parameters()))
         if needs_grad:
-            if self.siren.res_add_mask:
-                raise NotImplementedError(f"{type(self.siren).__name__}: the backward of the residual blocks is not built; render under "
-                                          "torch.no_grad() (or freeze the generator and detach z)")
             from .autograd import render_with_grad
             return render_with_grad(self, volume, global_feature, cam2worlds, img_size, fov, ray_start, ray_end,
                                     num_steps, hierarchical_sample, kwargs)

@@ -129,8 +129,6 @@ class _FiLMSirenFG(nn.Module):
         volume, global_feature = self.split_z(z)
         if torch.is_grad_enabled() and (volume.requires_grad or (global_feature is not None and global_feature.requires_grad)
                                         or any(p.requires_grad for p in self.parameters())):
-            if self.res_add_mask:
-                raise NotImplementedError(f"{type(self).__name__}: the backward of the residual blocks is not built; call under torch.no_grad()")
             from .autograd import siren_forward_with_grad
             return siren_forward_with_grad(self, points, volume, global_feature)
         freq, phase = self.film_parameters(global_feature, volume.shape[0], volume.device)
@@ -179,8 +177,8 @@ class TALLSIREN_dRes(_FiLMSirenFG):
     (``input_dim = z_dim``, :355).  Six linear layers on the same fused kernels (freq = 1, phase = 0); the block input is
     kept in fp32 next to the kernel's 16-bit operand tile and added to the second layer's pre-activation
     (``cng_film_siren_fwd_res``).  State-dict keys as in the reference: ``network.0.layer.*``, ``network.{1,2}.fc{1,2}.*``,
-    ``network.3.layer.*``, ``final_layer.*``.  Inference only in this round: the backward of the residual blocks is not built
-    and asking for gradients raises."""
+    ``network.3.layer.*``, ``final_layer.*``.  The backward recomputes through the training-mode kernel like the FG
+    family; the kept activation receives the adding layer's dz on top of its own gradient (``generators/autograd.py``)."""
     num_layers, freq_div, sigmoid_rgb, film = 6, 25.0, False, False
     res_save_mask, res_add_mask = 0b000101, 0b010100
 

@@ -402,7 +402,8 @@ def film_sin_grad(dy_bf16, z, bias, freq, phase, dfreq, dphase) -> torch.Tensor:
     return dz
 
 
-def film_siren_fwd_train(feat, layer_w, layer_b, freq, phase, final_w, final_b, sigmoid_rgb: bool):
+def film_siren_fwd_train(feat, layer_w, layer_b, freq, phase, final_w, final_b, sigmoid_rgb: bool, res_save_mask: int = 0,
+                         res_add_mask: int = 0):
     """Training-mode K2: rgb_sigma [B,N,4] plus the per-layer dumps x [L,B,N,HID] (bf16) and g = freq*cos(u) [L,B,N,HID] (fp16)."""
     feat = _f32(feat, "feat")
     B, N, C = feat.shape
@@ -422,8 +423,14 @@ def film_siren_fwd_train(feat, layer_w, layer_b, freq, phase, final_w, final_b, 
     ws_bytes = int(lib.cng_film_siren_workspace_bytes(B, C, HID, L, _lib.PREC_BF16))
     workspace = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev), _timed("cng_film_siren_fwd_train"):
-        _lib.call("cng_film_siren_fwd_train", _ptr(feat), B, N, C, HID, L, w_arr, b_arr, _ptr(freq), _ptr(phase), _ptr(final_w),
-                  _ptr(final_b), int(bool(sigmoid_rgb)), _ptr(workspace), ws_bytes, _ptr(out), _ptr(xs), _ptr(gs), _stream(feat))
+        if res_save_mask or res_add_mask:
+            scratch = _res_scratch(dev)
+            _lib.call("cng_film_siren_fwd_train_res", _ptr(feat), B, N, C, HID, L, w_arr, b_arr, _ptr(freq), _ptr(phase), _ptr(final_w),
+                      _ptr(final_b), int(bool(sigmoid_rgb)), _ptr(workspace), ws_bytes, _ptr(out), _ptr(xs), _ptr(gs),
+                      int(res_save_mask), int(res_add_mask), _ptr(scratch), scratch.numel(), _stream(feat))
+        else:
+            _lib.call("cng_film_siren_fwd_train", _ptr(feat), B, N, C, HID, L, w_arr, b_arr, _ptr(freq), _ptr(phase), _ptr(final_w),
+                      _ptr(final_b), int(bool(sigmoid_rgb)), _ptr(workspace), ws_bytes, _ptr(out), _ptr(xs), _ptr(gs), _stream(feat))
     _count(2)
     return out, xs, gs
 

@@ -284,6 +284,16 @@ CNG_API int cng_film_siren_fwd_train(const float* feat, int B, long long N, int 
                              const float* final_b, int sigmoid_rgb, void* workspace,
                              size_t workspace_bytes, float* rgb_sigma, void* x_dump_bf16,
                              void* g_dump_f16, cng_stream_t stream);
+/* The same for a network with residual blocks (masks and scratch as in cng_film_siren_fwd_res); g_l is the derivative at the
+ * pre-activation INCLUDING the re-added block input, so the layer backward above holds unchanged and the kept activation
+ * receives dz_l of the adding layer on top of its own gradient. */
+CNG_API int cng_film_siren_fwd_train_res(const float* feat, int B, long long N, int C, int HID, int L,
+                                 const float* const* layer_w_host, const float* const* layer_b_host,
+                                 const float* freq, const float* phase, const float* final_w,
+                                 const float* final_b, int sigmoid_rgb, void* workspace,
+                                 size_t workspace_bytes, float* rgb_sigma, void* x_dump_bf16,
+                                 void* g_dump_f16, unsigned res_save_mask, unsigned res_add_mask,
+                                 void* res_scratch, size_t res_scratch_bytes, cng_stream_t stream);
 /* dz = dy * g elementwise (dy, dz bf16, g fp16, all [P,HID]); colsum [HID] += column sums of dz (fp32, atomic). HID == 256. */
 CNG_API int cng_film_grad_from_g(const void* dy_bf16, const void* g_f16, long long P, int HID, void* dz_bf16,
                          float* colsum, cng_stream_t stream);

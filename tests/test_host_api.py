@@ -133,7 +133,7 @@ def test_unmodulated_variant_layout():
 
 def test_residual_variant_layout():
     """TALLSIREN_dRes (generators/siren.py:333-408): the reference's module tree and keys, input_dim = z_dim, no mapping network,
-    raw head; gradients are refused loudly (the backward of the residual blocks is not built)."""
+    raw head."""
     gen = ImplicitGenerator3d("TALLSIREN_dRes", 32, 3, 4, 256)          # input_dim is overridden by z_dim, as in the reference
     ref_state = oracle.init_generator_state("TALLSIREN_dRes", input_dim=32)
     assert list(gen.state_dict().keys()) == list(ref_state.keys())
@@ -142,8 +142,6 @@ def test_residual_variant_layout():
     assert gen.siren.res_save_mask == 0b000101 and gen.siren.res_add_mask == 0b010100 and not gen.siren.sigmoid_rgb
     ws, bs = gen.siren.layer_parameters()
     assert [tuple(w.shape) for w in ws] == [(256, 32)] + [(256, 256)] * 5 and len(bs) == 6
-    with pytest.raises(NotImplementedError):
-        gen(torch.zeros(1, 32, 8, 8, 8), torch.eye(4).unsqueeze(0), **META)
 
 
 def test_dense_grid_samples_match_oracle():

@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -s -p no:cacheprovider -k "residual or dRes or film_siren" > gpurun_out/pytest_dres.log 2>&1; echo "pytest exit $?"
-grep -E "dRes|passed|failed|Error|error" gpurun_out/pytest_dres.log | tail -30
+timeout 900 python -m pytest tests/test_gpu_backward.py -q -m gpu -x -s -p no:cacheprovider -k "generator_backward" > gpurun_out/pytest_dres.log 2>&1; echo "pytest exit $?"
+grep -E "worst|passed|failed|Error|error|dRes siren" gpurun_out/pytest_dres.log | tail -30
