@@ -23,7 +23,7 @@ import torch.nn.functional as F
 
 from .. import ops
 
-__all__ = ["FiLMLayer", "SirenLayer", "ResSirenBlock", "TALLSIREN_dRes", "TALLSIREN_FG", "SHORTSIREN_FG", "DOUBLESIREN_FG", "SingleSIREN_dg", "SHORTSIREN_F",
+__all__ = ["FiLMLayer", "SirenLayer", "ResSirenBlock", "TALLSIREN_dRes", "TALLSIREN_dResLong", "SHORTSIREN_FRes", "TALLSIREN_FG", "SHORTSIREN_FG", "DOUBLESIREN_FG", "SingleSIREN_dg", "SHORTSIREN_F",
            "TALLSIREN_dg", "SHORTSIREN_dg", "DoubleSIREN_dg", "DOUBLESIREN_dg", "default_precision"]
 
 
@@ -171,35 +171,66 @@ class ResSirenBlock(nn.Module):
         self.fc2 = nn.Linear(hidden_dim, hidden_dim)
 
 
-class TALLSIREN_dRes(_FiLMSirenFG):
-    """generators/siren.py:333-408 (configs/thousand/direct_volume/dRes.py): feature volume only; SirenLayer, two residual
-    blocks, SirenLayer, raw ``nn.Linear(hidden, 4)`` head (no sigmoid on rgb); the first layer reads ``z_dim`` features
-    (``input_dim = z_dim``, :355).  Six linear layers on the same fused kernels (freq = 1, phase = 0); the block input is
-    kept in fp32 next to the kernel's 16-bit operand tile and added to the second layer's pre-activation
-    (``cng_film_siren_fwd_res``).  State-dict keys as in the reference: ``network.0.layer.*``, ``network.{1,2}.fc{1,2}.*``,
-    ``network.3.layer.*``, ``final_layer.*``.  The backward recomputes through the training-mode kernel like the FG
-    family; the kept activation receives the adding layer's dz on top of its own gradient (``generators/autograd.py``)."""
-    num_layers, freq_div, sigmoid_rgb, film = 6, 25.0, False, False
-    res_save_mask, res_add_mask = 0b000101, 0b010100
+class _ResSiren(_FiLMSirenFG):
+    """Feature-volume-only decoders built from ``SirenLayer`` and ``ResSirenBlock`` (siren.py:333-488, 906-979): SirenLayer,
+    ``num_blocks`` residual blocks, SirenLayer, ``nn.Linear(hidden, 4)`` head.  2 + 2 * num_blocks linear layers on the fused
+    kernels (freq = 1, phase = 0); a block's input is kept in fp32 next to the kernel's 16-bit operand tile and added to its
+    second layer's pre-activation (``cng_film_siren_fwd_res``).  State-dict keys as in the reference: ``network.0.layer.*``,
+    ``network.{1..num_blocks}.fc{1,2}.*``, ``network.{num_blocks+1}.layer.*``, ``final_layer.*``.  The backward recomputes
+    through the training-mode kernel like the FG family; the kept activation receives the adding layer's dz on top of its own
+    gradient (``generators/autograd.py``)."""
+    film = False
+    num_blocks = 0
+    input_from_z_dim = False          # TALLSIREN_dRes / _dResLong read z_dim features (``input_dim = z_dim``, siren.py:355, :433)
 
     def __init__(self, input_dim=3, z_dim=100, hidden_dim=256, output_dim=4, drop_out=0, device=None, **kwargs):
         nn.Module.__init__(self)
-        input_dim = z_dim
+        if self.input_from_z_dim:
+            input_dim = z_dim
         self.device = device
         self.input_dim, self.z_dim, self.hidden_dim, self.output_dim = input_dim, z_dim, hidden_dim, output_dim
-        self.network = nn.ModuleList([SirenLayer(input_dim, hidden_dim, drop_out), ResSirenBlock(hidden_dim), ResSirenBlock(hidden_dim),
-                                      SirenLayer(hidden_dim, hidden_dim, drop_out)])
+        self.network = nn.ModuleList([SirenLayer(input_dim, hidden_dim, drop_out)] + [ResSirenBlock(hidden_dim) for _ in range(self.num_blocks)]
+                                     + [SirenLayer(hidden_dim, hidden_dim, drop_out)])
         self.final_layer = nn.Linear(hidden_dim, 4)
         for i, lin in enumerate(self.linear_layers()):
             fan_in = lin.weight.shape[-1]
-            # network.apply(frequency_init(25)) then network[0].apply(first_layer_film_sine_init), siren.py:372-375
+            # network.apply(frequency_init(f)) then network[0].apply(first_layer_film_sine_init), siren.py:372-375
             _uniform_(lin, 1.0 / fan_in if i == 0 else math.sqrt(6.0 / fan_in) / self.freq_div)
         _uniform_(self.final_layer, math.sqrt(6.0 / hidden_dim) / self.freq_div)
         self.precision = default_precision(self.tensor_core_operands)
 
     def linear_layers(self) -> List[nn.Linear]:
         n = self.network
-        return [n[0].layer, n[1].fc1, n[1].fc2, n[2].fc1, n[2].fc2, n[3].layer]
+        out = [n[0].layer]
+        for b in range(1, 1 + self.num_blocks):
+            out += [n[b].fc1, n[b].fc2]
+        return out + [n[1 + self.num_blocks].layer]
+
+
+def _res_masks(num_blocks: int) -> Tuple[int, int]:
+    """(save, add): layer 0 and every fc2 keep their output; every fc2 (layers 2, 4, ...) adds the kept one."""
+    save = 1 | sum(1 << (2 * b) for b in range(1, num_blocks))
+    add = sum(1 << (2 * b) for b in range(1, num_blocks + 1))
+    return save, add
+
+
+class TALLSIREN_dRes(_ResSiren):
+    """siren.py:333-408 (configs/thousand/direct_volume/dRes.py): two residual blocks, raw head."""
+    num_blocks, num_layers, freq_div, sigmoid_rgb, input_from_z_dim = 2, 6, 25.0, False, True
+    res_save_mask, res_add_mask = _res_masks(2)
+
+
+class TALLSIREN_dResLong(_ResSiren):
+    """siren.py:411-488: four residual blocks, raw head."""
+    num_blocks, num_layers, freq_div, sigmoid_rgb, input_from_z_dim = 4, 10, 25.0, False, True
+    res_save_mask, res_add_mask = _res_masks(4)
+
+
+class SHORTSIREN_FRes(_ResSiren):
+    """siren.py:906-979: one residual block, frequency_init(12), sigmoid on rgb, ``input_dim`` features."""
+    num_blocks, num_layers, freq_div, sigmoid_rgb = 1, 4, 12.0, True
+    res_save_mask, res_add_mask = _res_masks(1)
+    tensor_core_operands = "fp16"
 
 
 # config spellings (SURVEY.md appendix C)

@@ -79,6 +79,12 @@ SIREN_SPECS = {
     # block input "x" kept for later, bit l of res_add: the kept x is added to layer l's pre-activation.
     "TALLSIREN_dRes": {"layers": 6, "freq_init": 25.0, "sigmoid_rgb": False, "film": False, "res_save": 0b000101, "res_add": 0b010100,
                        "keys": ["network.0.layer", "network.1.fc1", "network.1.fc2", "network.2.fc1", "network.2.fc2", "network.3.layer"]},
+    # :411-488: the same with four residual blocks
+    "TALLSIREN_dResLong": {"layers": 10, "freq_init": 25.0, "sigmoid_rgb": False, "film": False, "res_save": 0b0001010101, "res_add": 0b0101010100,
+                           "keys": ["network.0.layer"] + [f"network.{b}.fc{i}" for b in (1, 2, 3, 4) for i in (1, 2)] + ["network.5.layer"]},
+    # :906-979: one residual block, frequency_init(12), sigmoid on rgb
+    "SHORTSIREN_FRes": {"layers": 4, "freq_init": 12.0, "sigmoid_rgb": True, "film": False, "res_save": 0b0001, "res_add": 0b0100,
+                        "keys": ["network.0.layer", "network.1.fc1", "network.1.fc2", "network.2.layer"]},
 }
 
 

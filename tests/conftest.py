@@ -41,7 +41,7 @@ def load_golden(name):
     return out, meta
 
 
-FORWARD_FIXTURES = ["fwd_TALLSIREN_FG", "fwd_SHORTSIREN_FG", "fwd_DOUBLESIREN_FG", "fwd_SingleSIREN_dg", "fwd_SHORTSIREN_F", "fwd_TALLSIREN_dRes"]
+FORWARD_FIXTURES = ["fwd_TALLSIREN_FG", "fwd_SHORTSIREN_FG", "fwd_DOUBLESIREN_FG", "fwd_SingleSIREN_dg", "fwd_SHORTSIREN_F", "fwd_TALLSIREN_dRes", "fwd_TALLSIREN_dResLong", "fwd_SHORTSIREN_FRes"]
 
 
 def fixture_inputs(name):

@@ -57,7 +57,7 @@ class Replay:
 def run_reference_forward(siren_type, state, z, cam, draws, meta):
     ref_name = oracle.resolve_siren_type(siren_type)
     vol0 = z[0] if isinstance(z, tuple) else z
-    z_dim = vol0.shape[1] if ref_name == "TALLSIREN_dRes" else 256      # that class sets input_dim = z_dim (siren.py:355)
+    z_dim = vol0.shape[1] if ref_name in ("TALLSIREN_dRes", "TALLSIREN_dResLong") else 256      # those classes set input_dim = z_dim (siren.py:355, :433)
     gen = ref_gen.ImplicitGenerator3d(ref_name, z_dim=z_dim, input_dim=vol0.shape[1], output_dim=4, hidden_dim=256)
     gen.load_state_dict(state, strict=True)
     gen.set_device(torch.device("cpu"))
@@ -264,6 +264,8 @@ def main():
     out = {}
     if "--dres-only" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "fwd_TALLSIREN_dRes.npz"), **make_forward_fixture("TALLSIREN_dRes", 16))
+        np.savez_compressed(os.path.join(HERE, "fwd_TALLSIREN_dResLong.npz"), **make_forward_fixture("TALLSIREN_dResLong", 17, hierarchical=False))
+        np.savez_compressed(os.path.join(HERE, "fwd_SHORTSIREN_FRes.npz"), **make_forward_fixture("SHORTSIREN_FRes", 18, clamp_mode="softplus", nerf_noise=0.3))
         return
     if "--train-only" in sys.argv:
         fx = make_train_step_fixture()
@@ -276,6 +278,8 @@ def main():
     out["fwd_SingleSIREN_dg"] = make_forward_fixture("SingleSIREN_dg", 14, nerf_noise=1.0)
     out["fwd_SHORTSIREN_F"] = make_forward_fixture("SHORTSIREN_F", 15)
     out["fwd_TALLSIREN_dRes"] = make_forward_fixture("TALLSIREN_dRes", 16)
+    out["fwd_TALLSIREN_dResLong"] = make_forward_fixture("TALLSIREN_dResLong", 17, hierarchical=False)
+    out["fwd_SHORTSIREN_FRes"] = make_forward_fixture("SHORTSIREN_FRes", 18, clamp_mode="softplus", nerf_noise=0.3)
     out["functions"] = make_function_fixture()
     for name, fx in out.items():
         path = os.path.join(HERE, name + ".npz")

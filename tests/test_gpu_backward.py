@@ -129,7 +129,7 @@ def _oracle_grads(state, siren_type, z, cam, draws, meta, d_pix, d_dep):
 
 
 @pytest.mark.parametrize("name", ["fwd_TALLSIREN_FG", "fwd_SHORTSIREN_FG", "fwd_DOUBLESIREN_FG", "fwd_SingleSIREN_dg", "fwd_SHORTSIREN_F",
-                                  "fwd_TALLSIREN_dRes"])
+                                  "fwd_TALLSIREN_dRes", "fwd_TALLSIREN_dResLong", "fwd_SHORTSIREN_FRes"])
 def test_generator_backward_vs_oracle_autograd(name):
     """loss = <pixels, G1> + <depth, G2>; gradients w.r.t. every SIREN parameter, the volume and the global feature."""
     from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d
@@ -138,7 +138,7 @@ def test_generator_backward_vs_oracle_autograd(name):
     g = torch.Generator().manual_seed(1)
     d_pix, d_dep = torch.randn((B, 3, img, img), generator=g), torch.randn((B, img, img), generator=g)
     ref_out, ref = _oracle_grads(state, siren_type, z, cam, draws, meta, d_pix, d_dep)
-    gen = ImplicitGenerator3d(siren_type, 32 if siren_type == "TALLSIREN_dRes" else 256, 32, 4, 256)
+    gen = ImplicitGenerator3d(siren_type, 32 if siren_type in ("TALLSIREN_dRes", "TALLSIREN_dResLong") else 256, 32, 4, 256)
     gen.load_state_dict(state, strict=True)
     gen = gen.to("cuda")
     gen.set_device(torch.device("cuda"))

@@ -142,6 +142,13 @@ def test_residual_variant_layout():
     assert gen.siren.res_save_mask == 0b000101 and gen.siren.res_add_mask == 0b010100 and not gen.siren.sigmoid_rgb
     ws, bs = gen.siren.layer_parameters()
     assert [tuple(w.shape) for w in ws] == [(256, 32)] + [(256, 256)] * 5 and len(bs) == 6
+    for name, zd, L, save, add in (("TALLSIREN_dResLong", 32, 10, 0b0001010101, 0b0101010100), ("SHORTSIREN_FRes", 256, 4, 0b0001, 0b0100)):
+        g2 = ImplicitGenerator3d(name, zd, 32, 4, 256)
+        st = oracle.init_generator_state(name, input_dim=32)
+        assert list(g2.state_dict().keys()) == list(st.keys())
+        g2.load_state_dict(st, strict=True)
+        assert (g2.siren.res_save_mask, g2.siren.res_add_mask, len(g2.siren.linear_layers())) == (save, add, L)
+        assert oracle.SIREN_SPECS[name]["res_save"] == save and oracle.SIREN_SPECS[name]["res_add"] == add
 
 
 def test_dense_grid_samples_match_oracle():
