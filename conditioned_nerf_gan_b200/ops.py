@@ -183,8 +183,11 @@ _RES_SCRATCH = {}
 
 
 def _res_scratch(dev) -> torch.Tensor:
-    """Device buffer for the kept activations of residual blocks (cng_film_siren_res_scratch_bytes, one per device)."""
-    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    """Device buffer for the kept activations of residual blocks (cng_film_siren_res_scratch_bytes), one per device AND
+    stream: launches on the same stream are ordered, launches on different streams must not share it."""
+    with torch.cuda.device(dev):
+        stream_id = torch.cuda.current_stream().cuda_stream
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(), stream_id)
     buf = _RES_SCRATCH.get(key)
     if buf is None:
         with torch.cuda.device(dev):
