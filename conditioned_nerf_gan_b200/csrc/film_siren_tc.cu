@@ -154,10 +154,13 @@ __global__ void __launch_bounds__(256) film_fold_kernel(FoldParams p) {
 // kShared: all 16 epilogue warps work on whichever tile's accumulator is complete (slot 0, then slot 1, then slot 0 ...)
 // instead of 8 warps bound to each slot.  A tile's epilogue then takes about as long as the other tile's MMAs and the
 // two strictly alternate: the tensor pipe runs back to back ("what the K2 numbers taught").
-template <int kPolyOneIn, bool kHalf, bool kTrain = false, bool kShared = false>
+// kRes: residual blocks (res_save_mask / res_add_mask of TcParams).  A separate instantiation: merely having the branch in the
+// epilogue costs the plain networks 4-5 % (same-box A/B, 2.95 vs 2.81 ms).
+template <int kPolyOneIn, bool kHalf, bool kTrain = false, bool kShared = false, bool kRes = false>
 __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams p) {
+  static_assert(!(kShared && kRes), "residual blocks run on the slot-bound epilogue");
   static_assert(!(kShared && kTrain), "the shared epilogue is an inference path");
-  static_assert(!kShared || kEpiWarpsPerSlot == 8, "the shared epilogue uses all 16 epilogue warps");
+  // (built with CNG_TC_EPI_WARPS=4 the shared mode is not instantiated: shared_kernel() below returns nullptr)
   // training mode gives one weight-ring slot (32 KB) to the per-warp staging buffers of the activation dumps
   constexpr int kRingN = kTrain ? kRing - 1 : kRing;
   constexpr uint32_t kSmemStage = kSmemW + kRingN * kChunkBytes;     // 16 epilogue warps x 2 KB (kTrain only)
@@ -429,7 +432,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
     const int ts = (warp % kEpiWarpsPerSlot) * 32 + lane;
     float* row_x = reinterpret_cast<float*>(smem + kSmemShift) + x * kHID;
     float row_next[kRowPerThread];
-    const bool res_mode = (p.res_save_mask | p.res_add_mask) != 0u;
+    constexpr bool res_mode = kRes;
     auto publish_row = [&]() {
       named_bar_sync(1 + x, kSlotThreads);            // every warp of the slot is done reading the old row
 #pragma unroll
@@ -490,7 +493,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
               v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + sv.w);
             }
           }
-          if (res_mode) {                                          // warp-uniform; only the residual SIREN variants
+          if constexpr (res_mode) {                                // only the residual SIREN variants' instantiations
             float4* rsd = reinterpret_cast<float4*>(p.res_scratch) + (static_cast<size_t>(blockIdx.x) * 2 + x) * (kHID / 4) * kTileM;
             if ((p.res_add_mask >> l) & 1u) {
 #pragma unroll
@@ -645,6 +648,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
   }
 }
 
+// the shared-epilogue instantiations exist only in the default 8-warps-per-slot build
+template <int kPoly, bool kHalf>
+static void (*shared_kernel())(TcParams) {
+  if constexpr (kEpiWarpsPerSlot == 8) return film_siren_tc_kernel<kPoly, kHalf, false, true>;
+  else return nullptr;
+}
+
 size_t film_siren_tc_workspace(int B, int L) {
   return static_cast<size_t>(B) * item_image_bytes(L) + static_cast<size_t>(B) * L * kHID * sizeof(float);
 }
@@ -710,17 +720,20 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
   }();
   const int ver = (res_save_mask | res_add_mask) ? 1 : (g_tc_version ? g_tc_version : version);     // residual blocks: the slot-bound kernel
   if (ver == 3 && !train && L <= 8) return film_siren_tc3_launch(p, poly, stream);
-  const bool shared = (ver == 2) && !train;
+  const bool shared = (ver == 2) && !train && kEpiWarpsPerSlot == 8;
   using KernelFn = void (*)(TcParams);
   const int pl = (poly == 0 || poly == 4) ? poly : 8;          // shared mode and fp16 come in these three flavours
-  const KernelFn fn = train ? film_siren_tc_kernel<0, true, true>
-                      : shared ? (half_operands ? (pl == 0 ? film_siren_tc_kernel<0, true, false, true> : pl == 4 ? film_siren_tc_kernel<4, true, false, true> : film_siren_tc_kernel<8, true, false, true>)
-                                                : (pl == 0 ? film_siren_tc_kernel<0, false, false, true> : pl == 4 ? film_siren_tc_kernel<4, false, false, true> : film_siren_tc_kernel<8, false, false, true>))
+  const bool res = (res_save_mask | res_add_mask) != 0;
+  const KernelFn fn = res ? (train ? film_siren_tc_kernel<0, true, true, false, true>
+                                   : half_operands ? film_siren_tc_kernel<8, true, false, false, true> : film_siren_tc_kernel<8, false, false, false, true>)
+                      : train ? film_siren_tc_kernel<0, true, true>
+                      : shared ? (half_operands ? (pl == 0 ? shared_kernel<0, true>() : pl == 4 ? shared_kernel<4, true>() : shared_kernel<8, true>())
+                                                : (pl == 0 ? shared_kernel<0, false>() : pl == 4 ? shared_kernel<4, false>() : shared_kernel<8, false>()))
                       : half_operands ? (pl == 0 ? film_siren_tc_kernel<0, true> : pl == 4 ? film_siren_tc_kernel<4, true> : film_siren_tc_kernel<8, true>)
                       : poly == 0 ? film_siren_tc_kernel<0, false> : poly == 2 ? film_siren_tc_kernel<2, false>
                       : poly == 3 ? film_siren_tc_kernel<3, false> : poly == 4 ? film_siren_tc_kernel<4, false> : film_siren_tc_kernel<8, false>;
-  static bool attr_set[5][9] = {};
-  const int variant = train ? 2 : (half_operands ? 1 : 0) + (shared ? 3 : 0);
+  static bool attr_set[8][9] = {};
+  const int variant = res ? 5 + (train ? 2 : half_operands ? 1 : 0) : train ? 2 : (half_operands ? 1 : 0) + (shared ? 3 : 0);
   if (!attr_set[variant][poly]) {
     ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTotal));
     if (ce != cudaSuccess) return fail(static_cast<int>(ce), "film_siren_fwd(bf16): smem attribute: %s", cudaGetErrorString(ce));

@@ -132,39 +132,37 @@ class _FilmSiren(torch.autograd.Function):
         d_bs = [torch.zeros_like(b) for b in bs]
         d_fw = torch.zeros_like(fw)
         d_fb = torch.zeros((4,), dtype=torch.float32, device=dev)
+        kept_of = {l: max(s_ for s_ in range(l) if (ctx.res_save >> s_) & 1) for l in range(L) if (ctx.res_add >> l) & 1}
+        b_stack = torch.stack(bs)                                                  # [L, H]
         for b in range(B):
             fr_all, ph_all = freq[b:b + 1].detach().float().contiguous(), phase[b:b + 1].detach().float().contiguous()
-            safe_fr = torch.where(fr_all[0].abs() < 1e-12, torch.ones_like(fr_all[0]), fr_all[0])
+            safe_fr = torch.where(fr_all[0].abs() < 1e-12, torch.ones_like(fr_all[0]), fr_all[0]).view(L, H)
+            # per item: weight gradients and column sums are accumulated over the chunks and turned into db / dphase / dfreq
+            # once at the end (they depend on the item's freq) -- the chunk loop below is 4 launches per layer
+            dW_item = [torch.zeros_like(w) for w in ws]
+            colsum = torch.zeros((L, H), dtype=torch.float32, device=dev)
             for r0 in range(0, N, CHUNK_ROWS):
                 r1 = min(N, r0 + CHUNK_ROWS)
                 x0 = feat[b:b + 1, r0:r1].detach().contiguous()
                 _, xs, gs = ops.film_siren_fwd_train(x0, ws, bs, fr_all, ph_all, fw, fb, ctx.sigmoid_rgb, ctx.res_save, ctx.res_add)
-                pending = {}                                                   # save layer -> gradient arriving through the skip
                 xs, gs = xs[:, 0], gs[:, 0]                                    # [L, P, H]
                 # ---- head: out = x_L Wf^T + bf, rgb = sigmoid(out[:, :3])
-                d_o = d_out[b, r0:r1].clone()
+                d_o = d_out[b, r0:r1]
                 if ctx.sigmoid_rgb:
                     rgb = out[b, r0:r1, :3]
-                    d_o[:, :3] *= rgb * (1 - rgb)
+                    d_o = torch.cat([d_o[:, :3] * (rgb * (1 - rgb)), d_o[:, 3:]], dim=1)
                 d_o_bf = d_o.to(torch.bfloat16)
                 d_fw += torch.mm(d_o_bf.t(), xs[L - 1], out_dtype=torch.float32)
                 d_fb += d_o.sum(0)
                 dy = torch.mm(d_o_bf, fw_bf)                                   # [P,4] x [4,H] -> bf16 [P,H]
                 x0_bf = x0[0].to(torch.bfloat16)
+                pending = {}                                                   # save layer -> gradient arriving through the skip
                 for l in reversed(range(L)):
-                    sl = slice(l * H, (l + 1) * H)
-                    colsum = torch.zeros((H,), dtype=torch.float32, device=dev)
-                    dz = ops.film_grad_from_g(dy, gs[l], colsum)
-                    if (ctx.res_add >> l) & 1:
-                        kept = max(s for s in range(l) if (ctx.res_save >> s) & 1)
-                        pending[kept] = dz
+                    dz = ops.film_grad_from_g(dy, gs[l], colsum[l])
+                    if l in kept_of:
+                        pending[kept_of[l]] = dz
                     x_in = xs[l - 1] if l > 0 else x0_bf
-                    dW = torch.mm(dz.t(), x_in, out_dtype=torch.float32)       # this chunk's share, [H, K_l]
-                    d_ws[l] += dW
-                    d_bs[l] += colsum
-                    dph = colsum / safe_fr[sl]
-                    d_phase[b, sl] += dph
-                    d_freq[b, sl] += (ws[l] * dW).sum(1) / safe_fr[sl] + bs[l] * dph
+                    dW_item[l] += torch.mm(dz.t(), x_in, out_dtype=torch.float32)   # this chunk's share, [H, K_l]
                     if l == 0:
                         d_feat[b, r0:r1] = torch.mm(dz, ws_bf[0], out_dtype=torch.float32)
                     else:
@@ -172,6 +170,13 @@ class _FilmSiren(torch.autograd.Function):
                         if (l - 1) in pending:
                             dy = dy + pending.pop(l - 1)
                 del xs, gs
+            dph = colsum / safe_fr                                             # [L, H]
+            d_phase[b] += dph.reshape(-1)
+            wdw = torch.stack([(ws[l] * dW_item[l]).sum(1) for l in range(L)])  # [L, H]
+            d_freq[b] += (wdw / safe_fr + b_stack * dph).reshape(-1)
+            for l in range(L):
+                d_ws[l] += dW_item[l]
+                d_bs[l] += colsum[l]
         return (d_feat, d_freq, d_phase, d_fw.to(final_w.dtype), d_fb.to(final_b.dtype), None, None, None, None,
                 *[g.to(p.dtype) for g, p in zip(d_ws, wb[:L])], *[g.to(p.dtype) for g, p in zip(d_bs, wb[L:])])
 

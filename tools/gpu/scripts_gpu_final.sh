@@ -5,5 +5,6 @@ timeout 1200 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/p
 tail -3 gpurun_out/pytest_gpu.log >> gpurun_out/final.log
 timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/final.log
 timeout 600 python bench.py > gpurun_out/bench_default.log 2>&1; echo "bench (no flags) exit $?" >> gpurun_out/final.log
-timeout 600 python tools/bench_c5.py --rays-max 4 --json gpurun_out/c5.json > gpurun_out/c5.log 2>&1; echo "c5 exit $?" >> gpurun_out/final.log
-cat gpurun_out/final.log; python tools/show_bench.py gpurun_out/bench_default.log; grep merge_composite gpurun_out/c5.log
+timeout 600 python bench.py --workload train --steps 4 --warmup 3 > gpurun_out/bench_train.log 2>&1; echo "train exit $?" >> gpurun_out/final.log
+timeout 300 python tools/profile_gan_step.py 4 > gpurun_out/profile_gan_step_b4.log 2>&1
+cat gpurun_out/final.log; python tools/show_bench.py gpurun_out/bench_default.log; python tools/show_bench.py gpurun_out/bench_train.log | head -2; head -1 gpurun_out/profile_gan_step_b4.log; grep -E "Self C(PU|UDA) time total" gpurun_out/profile_gan_step_b4.log
