@@ -270,11 +270,14 @@ constexpr size_t kResScratchPerSlot = static_cast<size_t>(kHID / 4) * kTileM * s
 // trace layout: [iter < 4][layer <= 8][slot < 2][event < 8]; events: 0 MMA thread saw act_ready, 1 MMAs issued,
 // 2 epilogue (warp 0 of the slot) saw acc_full, 3 epilogue done (before its arrive), 4 cycles the MMA thread
 // spent waiting for weight blocks of this slot-layer, 5 cycles it spent issuing MMAs + commits
+#ifndef CNG_TC_TRACE
+#define CNG_TC_TRACE 1        // 0: compile the clock64 timeline hooks out
+#endif
 __device__ __forceinline__ void trace_event(long long* trace, int iter, int l, int x, int ev) {
-  if (trace != nullptr && blockIdx.x == 0 && iter < 3 && l <= 8) trace[((iter * 9 + l) * 2 + x) * 8 + ev] = clock64();
+  if (CNG_TC_TRACE && trace != nullptr && blockIdx.x == 0 && iter < 3 && l <= 8) trace[((iter * 9 + l) * 2 + x) * 8 + ev] = clock64();
 }
 __device__ __forceinline__ void trace_value(long long* trace, int iter, int l, int x, int ev, long long v) {
-  if (trace != nullptr && blockIdx.x == 0 && iter < 3 && l <= 8) trace[((iter * 9 + l) * 2 + x) * 8 + ev] = v;
+  if (CNG_TC_TRACE && trace != nullptr && blockIdx.x == 0 && iter < 3 && l <= 8) trace[((iter * 9 + l) * 2 + x) * 8 + ev] = v;
 }
 
 struct TileInfo {
