@@ -218,6 +218,8 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        from conditioned_nerf_gan_b200 import parallel
+        parallel.bind_to_gpu_numa_node(local)        # pinned host buffers next to the GPU they feed (end-to-end leg)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
@@ -368,6 +370,8 @@ def _setup_ranks(args):
     from conditioned_nerf_gan_b200 import _lib, parallel
     _lib.load()
     rank, world, local = parallel.init_distributed("nccl")
+    if world > 1:
+        parallel.bind_to_gpu_numa_node(local)
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)

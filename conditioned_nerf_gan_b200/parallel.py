@@ -39,6 +39,26 @@ def init_distributed(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, world, local
 
 
+def bind_to_gpu_numa_node(local_rank: int) -> Optional[List[int]]:
+    """Pin this process to the CPU cores NVML reports as closest to GPU ``local_rank`` (its NUMA node), so that pinned host
+    buffers allocated afterwards land in that node's memory and the H2D / D2H copies of the ranks of one box do not all cross
+    the same socket link.  Returns the core list, or None when NVML / affinity control is unavailable (nothing changes then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous, balanced slice [start, stop) of n units for ``rank`` (the first n % world ranks get one more)."""
     if not (0 <= rank < world):
