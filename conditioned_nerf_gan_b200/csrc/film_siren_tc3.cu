@@ -7,7 +7,7 @@
 // -> MMA ..., 6700-6800 cycles per pair of tile-layers although the tensor pipe and the MUFU unit each need only
 // 2 x 2048.  The dependency that matters is finer than a layer: k-step j of layer l+1 needs only columns
 // [16j, 16j+16) of layer l's output.  Here the 16 epilogue warps all work on the same tile, column sub-block by
-// sub-block (4 * kCW columns: every warp takes kCW columns of its 32 rows), and signal each sub-block on its own
+// sub-block (4 * w columns: every warp takes w columns of its 32 rows, w from the schedule below), and signal each sub-block on its own
 // mbarrier; the MMA warp issues the k-steps of the NEXT layer as the sub-blocks land, into the OTHER accumulator
 // (TMEM: 2 x 256 fp32 columns).  The tensor pipe is therefore busy during the epilogue and only the last sub-block's
 // k-steps plus the commit -> epilogue hand-off are exposed per layer.
@@ -19,9 +19,10 @@
 //   right behind the current tile's head.
 //
 // Shared memory: A tile 64 KB + layer-0 operand 16 KB + weight ring 4 x 32 KB + barriers + shift rows 8 KB = 217 KB.
-// Same operand images and fold kernel as film_siren_tc.cu (which stays in the tree for the training-mode dumps, L > 8
-// and as the A/B baseline); the shift is added after the accumulation instead of before it, so results agree to
-// fp32 rounding, not bit for bit.
+// Same operand images, fold kernel and arithmetic order as film_siren_tc.cu: the two give bit-identical results
+// (tests/test_gpu_parity.py).  Measured 10 % slower than that kernel (DESIGN.md 5 explains where the time goes), so it
+// is the alternative (CNG_TC_V=3), not the default; film_siren_tc.cu also serves the training-mode dumps, L > 8 and
+// the residual-block variants.
 #include <stdlib.h>
 
 #include <utility>
@@ -29,10 +30,8 @@
 #include "film_siren_tc_common.cuh"
 
 #ifndef CNG_TC3_EXP
-#define CNG_TC3_EXP 0         // timing experiments only (WRONG results): 1 no weight copies after the first tile, 2 no operand stores, 4 no sines
-#endif
-#ifndef CNG_TC3_LAG
-#define CNG_TC3_LAG 0         // 1: a sub-block's proxy fence + arrive is issued behind the NEXT sub-block's sines
+#define CNG_TC3_EXP 0         // bottleneck experiments only (WRONG results), bit flags: 1 no weight copies after the first tile, 2 no operand
+                              // stores, 4 no sines, 16 no proxy fence, 32 the issuing warp does not wait for sub-blocks
 #endif
 #ifndef CNG_TC3_SCHED
 #define CNG_TC3_SCHED 8       // epilogue sub-block schedule, see make_sched()
@@ -46,7 +45,6 @@ constexpr int kEpiWarps = 16;
 constexpr int kMmaWarp = kEpiWarps;
 constexpr int kProducerWarp = kMmaWarp + 1;
 constexpr int kNumThreads = 32 * (kProducerWarp + 1);
-constexpr bool kLag = CNG_TC3_LAG != 0;
 constexpr uint32_t kSmemA = 0;                                        // [4 K-blocks][128][64] 16-bit, 128B swizzle
 constexpr uint32_t kSmemA0 = kATileBytes;                             // [128][64]: [x_hi(32) | x_lo(32)] of the next tile
 constexpr uint32_t kSmemW = kSmemA0 + kABlockBytes;                   // 81920
@@ -83,29 +81,6 @@ __device__ __forceinline__ void tmem_ld_w(uint32_t taddr, uint32_t (&v)[16]) {  
     CNG_TMEM_LD_16(taddr, v);
   }
 }
-template <int N>
-__device__ __forceinline__ void tmem_st_n(uint32_t taddr, const float (&s)[N]) {
-  if constexpr (N == 4) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "f"(s[0]), "f"(s[1]), "f"(s[2]), "f"(s[3]) : "memory");
-  } else if constexpr (N == 8) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "f"(s[0]), "f"(s[1]),
-                 "f"(s[2]), "f"(s[3]), "f"(s[4]), "f"(s[5]), "f"(s[6]), "f"(s[7]) : "memory");
-  } else {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-        ::"r"(taddr), "f"(s[0]), "f"(s[1]), "f"(s[2]), "f"(s[3]), "f"(s[4]), "f"(s[5]), "f"(s[6]), "f"(s[7]), "f"(s[8]), "f"(s[9]),
-          "f"(s[10]), "f"(s[11]), "f"(s[12]), "f"(s[13]), "f"(s[14]), "f"(s[15]) : "memory");
-  }
-}
-template <int N>
-__device__ __forceinline__ void ldg_n(const float* __restrict__ src, float (&s)[N]) {
-#pragma unroll
-  for (int i = 0; i < N; i += 4) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(src + i));
-    s[i] = t.x; s[i + 1] = t.y; s[i + 2] = t.z; s[i + 3] = t.w;
-  }
-}
-
 // Sub-block schedule of a layer's epilogue: step s covers 4*w(s) accumulator columns (every warp takes w(s) of them).
 // Wide steps amortise the per-step chain (TMEM load wait -> sine -> pack -> store -> proxy fence -> arrive, ~300 cycles
 // of latency per warp), narrow last steps keep short what is left for the tensor pipe after the epilogue's last arrive.
