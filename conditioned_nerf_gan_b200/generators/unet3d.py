@@ -80,13 +80,40 @@ class DoubleConv(nn.Sequential):
             self.add_module(f"SingleConv{i}", SingleConv(ci, co, kernel_size, order, num_groups))
 
 
-class Encoder(nn.Module):
-    """Optional 2x2x2 max pooling + DoubleConv (unet3d.py:268-323)."""
+class ExtResNetBlock(nn.Module):
+    """SingleConv followed by a two-convolution residual block, the non-linearity of the last one applied after the sum
+    (unet3d.py:195-265)."""
 
-    def __init__(self, in_channels: int, out_channels: int, apply_pooling: bool = True, conv_layer_order: str = "gcr", num_groups: int = 8):
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: int = 3, order: str = "cge", num_groups: int = 8, **kwargs):
+        super().__init__()
+        self.conv1 = SingleConv(in_channels, out_channels, kernel_size=kernel_size, order=order, num_groups=num_groups)
+        self.conv2 = SingleConv(out_channels, out_channels, kernel_size=kernel_size, order=order, num_groups=num_groups)
+        n_order = order
+        for c in "rel":
+            n_order = n_order.replace(c, "")
+        self.conv3 = SingleConv(out_channels, out_channels, kernel_size=kernel_size, order=n_order, num_groups=num_groups)
+        if "l" in order:
+            self.non_linearity = nn.LeakyReLU(negative_slope=0.1, inplace=True)
+        elif "e" in order:
+            self.non_linearity = nn.ELU(inplace=True)
+        else:
+            self.non_linearity = nn.ReLU(inplace=True)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        out = self.conv1(x)
+        residual = out
+        out = self.conv3(self.conv2(out))
+        return self.non_linearity(out + residual)
+
+
+class Encoder(nn.Module):
+    """Optional 2x2x2 max pooling + basic module (unet3d.py:268-323)."""
+
+    def __init__(self, in_channels: int, out_channels: int, apply_pooling: bool = True, basic_module=DoubleConv,
+                 conv_layer_order: str = "gcr", num_groups: int = 8):
         super().__init__()
         self.pooling = nn.MaxPool3d(kernel_size=(2, 2, 2)) if apply_pooling else None
-        self.basic_module = DoubleConv(in_channels, out_channels, encoder=True, order=conv_layer_order, num_groups=num_groups)
+        self.basic_module = basic_module(in_channels, out_channels, encoder=True, kernel_size=3, order=conv_layer_order, num_groups=num_groups)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.pooling is not None:
@@ -94,20 +121,38 @@ class Encoder(nn.Module):
         return self.basic_module(x)
 
 
-class Decoder(nn.Module):
-    """Nearest-neighbour upsampling to the skip connection's size, channel concatenation (skip first), DoubleConv
-    (unet3d.py:326-403, 405-452)."""
+class _TransposedUpsampling(nn.Module):
+    """Parameter holder + forward of the learned upsampling (unet3d.py:405-452): ConvTranspose3d(kernel 3, stride 2,
+    padding 1) to the skip connection's size.  Key: ``upsample.{weight,bias}``."""
 
-    def __init__(self, in_channels: int, out_channels: int, conv_layer_order: str = "gcr", num_groups: int = 8):
+    def __init__(self, in_channels: int, out_channels: int):
         super().__init__()
-        self.basic_module = DoubleConv(in_channels, out_channels, encoder=False, order=conv_layer_order, num_groups=num_groups)
+        self.upsample = nn.ConvTranspose3d(in_channels, out_channels, kernel_size=3, stride=(2, 2, 2), padding=1)
 
     def forward(self, encoder_features: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-        x = F.interpolate(x, size=encoder_features.shape[2:], mode="nearest")
-        return self.basic_module(torch.cat((encoder_features, x), dim=1))
+        return self.upsample(x, encoder_features.size()[2:])
 
 
-class UNet3D(nn.Module):
+class Decoder(nn.Module):
+    """DoubleConv: nearest-neighbour upsampling to the skip connection's size, channel concatenation (skip first);
+    ExtResNetBlock: transposed-convolution upsampling, summation (unet3d.py:326-403, 405-452)."""
+
+    def __init__(self, in_channels: int, out_channels: int, basic_module=DoubleConv, conv_layer_order: str = "gcr", num_groups: int = 8):
+        super().__init__()
+        self.concat = basic_module is DoubleConv
+        if not self.concat:
+            self.upsampling = _TransposedUpsampling(in_channels, out_channels)
+            in_channels = out_channels
+        self.basic_module = basic_module(in_channels, out_channels, encoder=False, kernel_size=3, order=conv_layer_order, num_groups=num_groups)
+
+    def forward(self, encoder_features: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+        if self.concat:
+            x = F.interpolate(x, size=encoder_features.shape[2:], mode="nearest")
+            return self.basic_module(torch.cat((encoder_features, x), dim=1))
+        return self.basic_module(encoder_features + self.upsampling(encoder_features, x))
+
+
+class _UNet3DBase(nn.Module):
     """``UNet3D(in_channels, out_channels, final_sigmoid=True, f_maps=64, layer_order="gcr", num_groups=8, num_levels=4,
     is_segmentation=True, return_global=False)`` -- unet3d.py:793-827.
 
@@ -116,23 +161,27 @@ class UNet3D(nn.Module):
 
     def __init__(self, in_channels: int, out_channels: int, final_sigmoid: bool = True, f_maps: Union[int, Sequence[int]] = 64,
                  layer_order: str = "gcr", num_groups: int = 8, num_levels: int = 4, is_segmentation: bool = True,
-                 testing: bool = False, return_global: bool = False, **kwargs):
+                 testing: bool = False, return_global: bool = False, basic_module=DoubleConv, pyramid: bool = False, **kwargs):
         super().__init__()
         self.testing = testing
+        self.pyramid = pyramid
         if isinstance(f_maps, int):
             f_maps = number_of_features_per_level(f_maps, num_levels=num_levels)
         f_maps = list(f_maps)
         self.encoders = nn.ModuleList(
-            Encoder(in_channels if i == 0 else f_maps[i - 1], f, apply_pooling=i > 0, conv_layer_order=layer_order, num_groups=num_groups)
+            Encoder(in_channels if i == 0 else f_maps[i - 1], f, apply_pooling=i > 0, basic_module=basic_module,
+                    conv_layer_order=layer_order, num_groups=num_groups)
             for i, f in enumerate(f_maps))
         rev = f_maps[::-1]
         self.decoders = nn.ModuleList(
-            Decoder(rev[i] + rev[i + 1], rev[i + 1], conv_layer_order=layer_order, num_groups=num_groups) for i in range(len(rev) - 1))
-        self.final_conv = nn.Conv3d(f_maps[0], out_channels, 1)
-        if is_segmentation:
-            self.final_activation = nn.Sigmoid() if final_sigmoid else nn.Softmax(dim=1)
-        else:
-            self.final_activation = None
+            Decoder(rev[i] + rev[i + 1] if basic_module is DoubleConv else rev[i], rev[i + 1], basic_module=basic_module,
+                    conv_layer_order=layer_order, num_groups=num_groups) for i in range(len(rev) - 1))
+        if not pyramid:                                    # the pyramid network has no final convolution (unet3d.py:640-791)
+            self.final_conv = nn.Conv3d(f_maps[0], out_channels, 1)
+            if is_segmentation:
+                self.final_activation = nn.Sigmoid() if final_sigmoid else nn.Softmax(dim=1)
+            else:
+                self.final_activation = None
         self.return_global = return_global
 
     def forward(self, x: torch.Tensor):
@@ -143,6 +192,12 @@ class UNet3D(nn.Module):
             x = encoder(x)
             skips.insert(0, x)
         global_features = x.mean(dim=(2, 3, 4)) if self.return_global else None      # full-extent average pool of the bottleneck
+        if self.pyramid:
+            levels = []
+            for decoder, skip in zip(self.decoders, skips[1:]):
+                x = decoder(skip, x)
+                levels.append(x)
+            return (levels, global_features) if self.return_global else levels
         for decoder, skip in zip(self.decoders, skips[1:]):
             x = decoder(skip, x)
         x = self.final_conv(x)
@@ -151,3 +206,31 @@ class UNet3D(nn.Module):
         if x.dim() == 5 and not x.is_contiguous(memory_format=torch.channels_last_3d):
             x = x.contiguous(memory_format=torch.channels_last_3d)                    # the layout the gather kernel reads
         return (x, global_features) if self.return_global else x
+
+
+class UNet3D(_UNet3DBase):
+    """unet3d.py:793-827: DoubleConv blocks, nearest-neighbour upsampling, concatenation joining."""
+
+    def __init__(self, in_channels, out_channels, final_sigmoid=True, f_maps=64, layer_order="gcr", num_groups=8, num_levels=4,
+                 is_segmentation=True, return_global=False, **kwargs):
+        super().__init__(in_channels, out_channels, final_sigmoid=final_sigmoid, f_maps=f_maps, layer_order=layer_order, num_groups=num_groups,
+                         num_levels=num_levels, is_segmentation=is_segmentation, return_global=return_global, basic_module=DoubleConv, **kwargs)
+
+
+class PyramidUNet3D(_UNet3DBase):
+    """unet3d.py:829-863: the same network without the final convolution; returns every decoder level (coarse to fine)."""
+
+    def __init__(self, in_channels, out_channels, final_sigmoid=True, f_maps=64, layer_order="gcr", num_groups=8, num_levels=4,
+                 is_segmentation=True, return_global=False, **kwargs):
+        super().__init__(in_channels, out_channels, final_sigmoid=final_sigmoid, f_maps=f_maps, layer_order=layer_order, num_groups=num_groups,
+                         num_levels=num_levels, is_segmentation=is_segmentation, return_global=return_global, basic_module=DoubleConv,
+                         pyramid=True, **kwargs)
+
+
+class ResidualUNet3D(_UNet3DBase):
+    """unet3d.py:865-898: ExtResNetBlock blocks, transposed-convolution upsampling, summation joining, five levels by default."""
+
+    def __init__(self, in_channels, out_channels, final_sigmoid=True, f_maps=64, layer_order="gcr", num_groups=8, num_levels=5,
+                 is_segmentation=True, return_global=False, **kwargs):
+        super().__init__(in_channels, out_channels, final_sigmoid=final_sigmoid, f_maps=f_maps, layer_order=layer_order, num_groups=num_groups,
+                         num_levels=num_levels, is_segmentation=is_segmentation, return_global=return_global, basic_module=ExtResNetBlock, **kwargs)

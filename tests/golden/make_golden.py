@@ -251,6 +251,16 @@ def make_train_step_fixture(steps=2):
         for size in (16, 64):
             img = torch.rand((2, 3, size, size), generator=torch.Generator().manual_seed(size)) * 2 - 1
             fx[f"disc/in{size}"], fx[f"disc/out{size}"] = img.numpy(), disc(img, 0.3).numpy()
+        # the other two encoders of generators/unet3d.py (:829-898) on the same voxels
+        pyr = ref_unet.PyramidUNet3D(**dict(ts.TINY_UNET, num_levels=3))
+        res = ref_unet.ResidualUNet3D(**dict(ts.TINY_UNET, num_levels=3, return_global=False, out_channels=16))
+        ts.fill_params(pyr, 3)
+        ts.fill_params(res, 4)
+        levels, pglob = pyr(sample["voxel"])
+        for i, lv in enumerate(levels):
+            fx[f"unet_pyramid/level{i}"] = lv.numpy()
+        fx["unet_pyramid/global"] = pglob.numpy()
+        fx["unet_residual/volume"] = res(sample["voxel"]).numpy()
     harness = ts.RefTrainStep(ReplayedRefGenerator(gen), enc, disc, dict(md, draws=ts.tiny_draws()), alpha=0.3)
     for i in range(steps):
         rec = harness.step(sample)

@@ -46,6 +46,27 @@ def test_unet_and_discriminator_match_reference_outputs():
             torch.testing.assert_close(disc(fx[f"disc/in{size}"], 0.3), fx[f"disc/out{size}"], rtol=1e-4, atol=1e-6)
 
 
+def test_pyramid_and_residual_unets_match_reference_outputs():
+    """PyramidUNet3D (every decoder level, no final convolution) and ResidualUNet3D (ExtResNetBlock, transposed-convolution
+    upsampling, summation joining), generators/unet3d.py:829-898, against outputs of the reference's classes."""
+    from conditioned_nerf_gan_b200.generators.unet3d import PyramidUNet3D, ResidualUNet3D
+    fx, _ = load_golden("train_step")
+    voxel = ts.tiny_sample()["voxel"]
+    pyr = PyramidUNet3D(**dict(ts.TINY_UNET, num_levels=3))
+    res = ResidualUNet3D(**dict(ts.TINY_UNET, num_levels=3, return_global=False, out_channels=16))
+    ts.fill_params(pyr, 3)
+    ts.fill_params(res, 4)
+    assert not any(k.startswith("final_conv") for k in pyr.state_dict())
+    assert "decoders.0.upsampling.upsample.weight" in res.state_dict() and "encoders.1.basic_module.conv3.groupnorm.weight" in res.state_dict()
+    with torch.no_grad():
+        levels, glob = pyr(voxel)
+        assert len(levels) == 2
+        for i, lv in enumerate(levels):
+            torch.testing.assert_close(lv.contiguous(), fx[f"unet_pyramid/level{i}"], rtol=1e-4, atol=2e-5)
+        torch.testing.assert_close(glob, fx["unet_pyramid/global"], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(res(voxel).contiguous(), fx["unet_residual/volume"], rtol=1e-4, atol=2e-5)
+
+
 def test_discriminator_ignores_curriculum_keys_and_fades_in():
     _, disc = _modules()
     img = torch.rand((1, 3, 32, 32)) * 2 - 1
