@@ -1,1 +1,1 @@
-from .discriminators import ProgressiveDiscriminator  # noqa: F401
+from .discriminators import ProgressiveDiscriminator, ProgressiveDiscriminator_inputCat, ProgressiveEncoderDiscriminator  # noqa: F401

@@ -174,6 +174,8 @@ class ResidualCoordConvBlock(nn.Module):
 class ProgressiveDiscriminator(nn.Module):
     """discriminators.py:138-199: eight residual CoordConv blocks, entered at the block matching the image size, with the
     progressive-GAN fade-in of the next-lower resolution after the first block."""
+    image_channels = 3        # channels the fromRGB adapters read
+    final_channels = 1        # outputs of the 2x2 head convolution
 
     def __init__(self, **kwargs):
         super().__init__()
@@ -181,15 +183,41 @@ class ProgressiveDiscriminator(nn.Module):
         self.step = 0
         planes = [16, 32, 64, 128, 256, 400, 400, 400, 400]
         self.layers = nn.ModuleList(ResidualCoordConvBlock(planes[i], planes[i + 1], downsample=True) for i in range(8))
-        self.fromRGB = nn.ModuleList(AdapterBlock(p) for p in planes)
-        self.final_layer = R1Conv2d(400, 1, 2)
+        self.fromRGB = nn.ModuleList(AdapterBlock(p, self.image_channels) for p in planes)
+        self.final_layer = R1Conv2d(400, self.final_channels, 2)
         self.img_size_to_layer = {2: 8, 4: 7, 8: 6, 16: 5, 32: 4, 64: 3, 128: 2, 256: 1, 512: 0}
 
-    def forward(self, input, alpha, instance_noise=0, cond=None, **kwargs):
+    def _trunk(self, input, alpha):
         start = self.img_size_to_layer[input.shape[-1]]
         x = self.fromRGB[start](input)
         for i, layer in enumerate(self.layers[start:]):
             if i == 1:
                 x = alpha * x + (1 - alpha) * self.fromRGB[start + 1](F.interpolate(input, scale_factor=0.5, mode="nearest"))
             x = layer(x)
-        return self.final_layer(x).reshape(x.shape[0], 1)
+        return self.final_layer(x)
+
+    def forward(self, input, alpha, instance_noise=0, cond=None, **kwargs):
+        x = self._trunk(input, alpha)
+        return x.reshape(x.shape[0], 1)
+
+
+class ProgressiveEncoderDiscriminator(ProgressiveDiscriminator):
+    """discriminators.py:202-271: the same trunk with a 1 + 256 + 2 channel head; also predicts a latent code and a camera
+    position, optional instance noise on the input.  Returns (prediction [B,1], latent [B,256], position [B,2])."""
+    final_channels = 1 + 256 + 2
+
+    def forward(self, input, alpha, instance_noise=0, cond=None, **kwargs):
+        if instance_noise > 0:
+            input = input + torch.randn_like(input) * instance_noise
+        x = self._trunk(input, alpha)
+        x = x.reshape(x.shape[0], -1)
+        return x[..., 0:1], x[..., 1:257], x[..., 257:259]
+
+
+class ProgressiveDiscriminator_inputCat(ProgressiveDiscriminator):
+    """discriminators.py:274-335: conditional variant, the condition image is concatenated to the input (6 channels)."""
+    image_channels = 6
+
+    def forward(self, input, alpha, instance_noise=0, cond=None, **kwargs):
+        x = self._trunk(torch.cat([input, cond], dim=1), alpha)
+        return x.reshape(x.shape[0], 1)

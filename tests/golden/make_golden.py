@@ -251,6 +251,12 @@ def make_train_step_fixture(steps=2):
         for size in (16, 64):
             img = torch.rand((2, 3, size, size), generator=torch.Generator().manual_seed(size)) * 2 - 1
             fx[f"disc/in{size}"], fx[f"disc/out{size}"] = img.numpy(), disc(img, 0.3).numpy()
+        for cls, tag in ((ref_disc.ProgressiveEncoderDiscriminator, "enc"), (ref_disc.ProgressiveDiscriminator_inputCat, "cat")):
+            d2 = cls()
+            ts.fill_params(d2, 5)
+            img = torch.tensor(fx["disc/in16"])
+            out = d2(img, 0.3, cond=img.flip(0)) if tag == "cat" else torch.cat(d2(img, 0.3), dim=1)
+            fx[f"disc_{tag}/out16"] = out.numpy()
         # the other two encoders of generators/unet3d.py (:829-898) on the same voxels
         pyr = ref_unet.PyramidUNet3D(**dict(ts.TINY_UNET, num_levels=3))
         res = ref_unet.ResidualUNet3D(**dict(ts.TINY_UNET, num_levels=3, return_global=False, out_channels=16))

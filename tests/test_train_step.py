@@ -67,6 +67,22 @@ def test_pyramid_and_residual_unets_match_reference_outputs():
         torch.testing.assert_close(res(voxel).contiguous(), fx["unet_residual/volume"], rtol=1e-4, atol=2e-5)
 
 
+def test_discriminator_variants_match_reference_outputs():
+    """ProgressiveEncoderDiscriminator (prediction + latent + position heads) and ProgressiveDiscriminator_inputCat (condition
+    image concatenated to the input), discriminators.py:202-335."""
+    from conditioned_nerf_gan_b200.discriminators import ProgressiveDiscriminator_inputCat, ProgressiveEncoderDiscriminator
+    fx, _ = load_golden("train_step")
+    img = fx["disc/in16"]
+    enc, cat = ProgressiveEncoderDiscriminator(), ProgressiveDiscriminator_inputCat()
+    ts.fill_params(enc, 5)
+    ts.fill_params(cat, 5)
+    with torch.no_grad():
+        pred, latent, position = enc(img, 0.3)
+        assert pred.shape == (2, 1) and latent.shape == (2, 256) and position.shape == (2, 2)
+        torch.testing.assert_close(torch.cat([pred, latent, position], dim=1), fx["disc_enc/out16"], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(cat(img, 0.3, cond=img.flip(0)), fx["disc_cat/out16"], rtol=1e-4, atol=1e-6)
+
+
 def test_discriminator_ignores_curriculum_keys_and_fades_in():
     _, disc = _modules()
     img = torch.rand((1, 3, 32, 32)) * 2 - 1
