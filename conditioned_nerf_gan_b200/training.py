@@ -47,7 +47,8 @@ class GanTrainStep:
     generator and the discriminator, which ignore the keys they do not know."""
 
     def __init__(self, generator, encoder, discriminator, metadata: Dict, device, *, amp: bool = True, amp_dtype=torch.float16,
-                 ddp: bool = False, local_rank: int = 0, fade_steps: Optional[int] = None, last_upsample_step: int = 0):
+                 ddp: bool = False, local_rank: int = 0, fade_steps: Optional[int] = None, last_upsample_step: int = 0,
+                 curriculum: Optional[Dict] = None):
         self.device = torch.device(device)
         self.metadata = dict(metadata)
         self.generator, self.encoder, self.discriminator = generator, encoder, discriminator
@@ -70,6 +71,7 @@ class GanTrainStep:
         self.scaler = torch.amp.GradScaler(self.device.type, enabled=self.amp and amp_dtype == torch.float16)
         self.fade_steps = fade_steps if fade_steps is not None else md.get("fade_steps", 2000)
         self.last_upsample_step = last_upsample_step
+        self.curriculum = curriculum             # optional: the reference's curriculum dict; ``set_alpha`` then reads the stage start from it
         self.alpha = 1.0
         self.ddp = ddp
         self.losses: Dict[str, torch.Tensor] = {}
@@ -87,6 +89,9 @@ class GanTrainStep:
     def set_alpha(self) -> None:
         """utils.py:610-618"""
         step = getattr(self.generator, "step", 0)
+        if self.curriculum is not None:
+            from . import curriculums
+            self.last_upsample_step = curriculums.last_upsample_step(self.curriculum, step)
         self.alpha = min(1, (step - self.last_upsample_step) / self.fade_steps)
         self.metadata["nerf_noise"] = max(0, 1.0 - step / 5000.0)
 

@@ -71,6 +71,13 @@ def tiny_config() -> Dict:
     }
 
 
+def tiny_curriculum() -> Dict:
+    """Four stages as in configs/thousand/default.py:11-60 (32 -> 64 -> 128 -> 128 pixels) plus global keys."""
+    return {0: {"batch_size": 32, "img_size": 32, "num_steps": 48}, 5000: {"batch_size": 24, "img_size": 64, "num_steps": 48},
+            15000: {"batch_size": 4, "img_size": 128, "num_steps": 48}, 25000: {"batch_size": 4, "img_size": 128, "num_steps": 64},
+            "fade_steps": 2000, "fov": 30}
+
+
 TINY_UNET = dict(in_channels=4, out_channels=32, f_maps=8, num_levels=2, is_segmentation=False, final_sigmoid=False, return_global=True)
 TINY_SIREN, TINY_ZDIM, TINY_BATCH, TINY_VOXEL = "DOUBLESIREN_FG", 16, 2, 8
 

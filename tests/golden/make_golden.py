@@ -267,6 +267,13 @@ def make_train_step_fixture(steps=2):
             fx[f"unet_pyramid/level{i}"] = lv.numpy()
         fx["unet_pyramid/global"] = pglob.numpy()
         fx["unet_residual/volume"] = res(sample["voxel"]).numpy()
+    # curriculum helpers (configs/curriculums.py:83-137) on a four-stage curriculum shaped like configs/thousand/default.py
+    from configs import curriculums as ref_cur
+    cur = ts.tiny_curriculum()
+    table = {str(st): [ref_cur.extract_metadata(cur, st)["img_size"], ref_cur.extract_metadata(cur, st)["batch_size"],
+                       ref_cur.last_upsample_step(cur, st), float(min(ref_cur.next_upsample_step(cur, st), 1e9))]
+             for st in (0, 1, 4999, 5000, 7000, 15000, 24999, 25000, 90000)}
+    fx["curriculum/json"] = np.array(__import__("json").dumps(table))
     harness = ts.RefTrainStep(ReplayedRefGenerator(gen), enc, disc, dict(md, draws=ts.tiny_draws()), alpha=0.3)
     for i in range(steps):
         rec = harness.step(sample)

@@ -67,6 +67,21 @@ def test_pyramid_and_residual_unets_match_reference_outputs():
         torch.testing.assert_close(res(voxel).contiguous(), fx["unet_residual/volume"], rtol=1e-4, atol=2e-5)
 
 
+def test_curriculum_helpers_match_reference():
+    """extract_metadata / last_upsample_step / next_upsample_step (configs/curriculums.py:83-137) on a four-stage curriculum,
+    against values computed by the reference's own functions; GanTrainStep.set_alpha reads the stage start from them."""
+    from conditioned_nerf_gan_b200 import curriculums
+    fx, _ = load_golden("train_step")
+    cur = ts.tiny_curriculum()
+    for step, (img, batch, last, nxt) in fx["curriculum/json"].items():
+        step = int(step)
+        md = curriculums.extract_metadata(cur, step)
+        assert (md["img_size"], md["batch_size"], md["fade_steps"]) == (img, batch, 2000)
+        assert curriculums.last_upsample_step(cur, step) == last
+        assert min(curriculums.next_upsample_step(cur, step), 1e9) == nxt
+    assert curriculums.update_recursive({"a": {"b": 1}}, {"a": {"c": 2}, "d": 3}) == {"a": {"b": 1, "c": 2}, "d": 3}
+
+
 def test_discriminator_variants_match_reference_outputs():
     """ProgressiveEncoderDiscriminator (prediction + latent + position heads) and ProgressiveDiscriminator_inputCat (condition
     image concatenated to the input), discriminators.py:202-335."""
