@@ -13,9 +13,10 @@ CONFIGS = [("c1: B1 64x64 12+12 V32", 1, 64, 12, 32), ("c2: B8 128x128 24+24 V64
            ("B1 128x128 48+48 V64", 1, 128, 48, 64), ("B4 256x256 48+48 V64", 4, 256, 48, 64)]
 print(f"{'config':28s} {'siren':16s} {'prec':5s} {'ms':>8s} {'M rays/s':>9s} {'MLP TFLOP/s (algorithmic, whole step)':>10s}")
 for name, B, img, S, V in CONFIGS:
-    for siren in ("TALLSIREN_FG", "SHORTSIREN_FG", "DOUBLESIREN_FG", "SingleSIREN_dg", "SHORTSIREN_F"):
+    for siren in ("TALLSIREN_FG", "SHORTSIREN_FG", "DOUBLESIREN_FG", "SingleSIREN_dg", "SHORTSIREN_F", "TALLSIREN_dRes", "TALLSIREN_dResLong",
+                  "SHORTSIREN_FRes"):
         spec = oracle.SIREN_SPECS[siren]
-        gen = ImplicitGenerator3d(siren, 256, 32, 4, 256)
+        gen = ImplicitGenerator3d(siren, 32 if siren.startswith("TALLSIREN_dRes") else 256, 32, 4, 256)
         gen.load_state_dict(oracle.init_generator_state(siren, seed=0), strict=True)
         gen = gen.to(dev).eval()
         vol, glob, cam = (t.to(dev) for t in bench.synthetic_inputs(B, V, 0))
