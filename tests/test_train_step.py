@@ -123,6 +123,51 @@ def test_train_step_harness_with_our_encoder_and_discriminator_matches_reference
             assert abs(v - want) <= 2e-3 * abs(want) + 1e-5, (i, k, v, want)
 
 
+def test_gan_train_step_host_logic_matches_reference_on_cpu():
+    """training.GanTrainStep itself (optimizers, GradScaler order, clipping, loss bookkeeping) on CPU, with the oracle renderer
+    standing in for the CUDA generator: two optimisation steps against the numbers recorded with the reference's modules.
+    Also: batch_split = 2 accumulates the two half-batch gradients exactly as the reference's loop does (sum of the two means)."""
+    from conditioned_nerf_gan_b200.training import GanTrainStep
+    fx, _ = load_golden("train_step")
+    enc, disc = _modules()
+    gen = ts.OracleGenerator(ts.TINY_SIREN, oracle.init_generator_state(ts.TINY_SIREN, z_dim=ts.TINY_ZDIM, seed=0))
+    trainer = GanTrainStep(gen, enc, disc, dict(ts.tiny_config(), draws=ts.tiny_draws()), "cpu", amp=False)
+    trainer.alpha = 0.3
+    sample = ts.tiny_sample()
+    for i in range(2):
+        trainer.train_discriminator(sample)
+        trainer.train_generator(sample)
+        got = {"d_loss": trainer.losses["d_loss"], "g_loss": trainer.losses["g_loss"], "photo_loss": trainer.losses["photo_loss"],
+               "norm_D": trainer.grad_norms["D"], "norm_G": trainer.grad_norms["G"], "norm_E": trainer.grad_norms["E"]}
+        for k, v in got.items():
+            want = float(fx[f"step{i}/{k}"])
+            assert abs(float(v) - want) <= 2e-3 * abs(want) + 1e-5, (i, k, float(v), want)
+    # batch_split: per-image draws make the two halves independent, so split 2 = sum of the half-batch gradients
+    norms = {}
+    for splits in (1, 2):
+        enc2, disc2 = _modules()
+        gen2 = ts.OracleGenerator(ts.TINY_SIREN, oracle.init_generator_state(ts.TINY_SIREN, z_dim=ts.TINY_ZDIM, seed=0))
+
+        class _PerSplitDraws(torch.nn.Module):
+            """hands the generator the draws of the images it is asked to render"""
+            def __init__(self, inner):
+                super().__init__()
+                self.inner, self.step, self.calls = inner, 0, 0
+            def forward(self, z, cam, **md):
+                b, R = cam.shape[0], md["img_size"] ** 2
+                lo = (self.calls * b) % ts.TINY_BATCH if b < ts.TINY_BATCH else 0
+                self.calls += 1
+                d = {k: (v[lo * R:(lo + b) * R] if k == "u_resample" else v[lo:lo + b]) for k, v in ts.tiny_draws().items()}
+                return self.inner(z, cam, **dict(md, draws=d))
+
+        tr = GanTrainStep(_PerSplitDraws(gen2), enc2, disc2, dict(ts.tiny_config(), batch_split=splits, enable_discriminator=False), "cpu", amp=False)
+        tr.train_generator(sample)
+        norms[splits] = (float(tr.grad_norms["G"]), float(tr.grad_norms["E"]), float(tr.losses["photo_loss"]))
+    # each split's loss is a mean over half the images: the accumulated gradient is twice the whole-batch-mean gradient
+    assert norms[2][0] == pytest.approx(2 * norms[1][0], rel=2e-3) and norms[2][1] == pytest.approx(2 * norms[1][1], rel=2e-3)
+    assert norms[2][2] == pytest.approx(norms[1][2], rel=1e-4)
+
+
 @pytest.mark.gpu
 def test_gan_train_step_matches_reference_on_gpu():
     """The product's GanTrainStep (CUDA rendering path in exact-fp32 mode, cuDNN U-Net / discriminator) against the
