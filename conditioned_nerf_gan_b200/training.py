@@ -15,7 +15,10 @@ Differences that do not change the mathematics:
     micro-batch backward, ``utils.py:711``);
   * losses are accumulated on the device and read back once per step (the reference calls ``.item()`` three times per
     micro-batch, ``utils.py:707-709``, a host synchronisation each);
-  * the encoder emits the feature volume in the gather kernel's NDHWC layout (``generators/unet3d.py``).
+  * the encoder emits the feature volume in the gather kernel's NDHWC layout (``generators/unet3d.py``);
+  * in the generator step the discriminator only relays d loss / d image: it is called as the bare module with frozen
+    parameters, so its weight gradients are neither computed nor all-reduced (the reference computes them, lets DDP
+    average them and zeroes them at the next discriminator step, ``utils.py:836``).
 """
 from __future__ import annotations
 
@@ -151,25 +154,16 @@ class GanTrainStep:
         use_d = md.get("enable_discriminator", True) and self.discriminator_ddp is not None
         zero = torch.zeros((), device=self.device)
         acc = {"g_loss": zero.clone(), "photo_loss": zero.clone(), "depth_loss": zero.clone()}
-        for s in range(splits):
-            last = s == splits - 1
-            sl = slice(s * sb, (s + 1) * sb)
-            with self._no_sync(self.generator_ddp, last), self._no_sync(self.encoder_ddp, last):
-                with self._autocast():
-                    z = self.encoder_ddp(voxels[sl])
-                    gen_imgs, gen_depths = self.generator_ddp(z, cam2worlds[sl], **md)
-                    if use_d:
-                        g_preds = self.discriminator_ddp(gen_imgs, self.alpha, cond=None, **md)
-                        loss_G = F.softplus(-g_preds).mean()
-                    else:
-                        loss_G = zero
-                    photo = loss_mse(imgs[sl], gen_imgs) if md.get("photo_loss", False) else zero
-                    depth = loss_depth(depths[sl].to(self.device), gen_depths) if md.get("depth_loss", False) else zero
-                    loss = loss_G + photo + depth * md.get("depth_loss_weight", 1)
-                acc["g_loss"] += loss_G.detach().float()
-                acc["photo_loss"] += photo.detach().float()
-                acc["depth_loss"] += depth.detach().float()
-                self.scaler.scale(loss).backward()
+        # The generator loss needs d loss / d image through the discriminator, not the discriminator's weight gradients
+        # (the reference computes, all-reduces and then discards them): score with the bare module and frozen parameters.
+        d_params = [p for p in self.discriminator.parameters() if p.requires_grad] if use_d else []
+        for p in d_params:
+            p.requires_grad_(False)
+        try:
+            self._generator_micro_batches(md, imgs, cam2worlds, voxels, depths, splits, sb, use_d, zero, acc)
+        finally:
+            for p in d_params:
+                p.requires_grad_(True)
         for k, v in acc.items():
             self.losses[k] = v / splits
         clip = md.get("grad_clip", 0.3)
@@ -182,8 +176,27 @@ class GanTrainStep:
         self.scaler.step(self.optimizer_E)
         self.optimizer_E.zero_grad()
         self.scaler.update()
-        if use_d:
-            self.optimizer_D.zero_grad(set_to_none=True)        # the generator loss also left gradients in the discriminator
+
+    def _generator_micro_batches(self, md, imgs, cam2worlds, voxels, depths, splits, sb, use_d, zero, acc) -> None:
+        for s in range(splits):
+            last = s == splits - 1
+            sl = slice(s * sb, (s + 1) * sb)
+            with self._no_sync(self.generator_ddp, last), self._no_sync(self.encoder_ddp, last):
+                with self._autocast():
+                    z = self.encoder_ddp(voxels[sl])
+                    gen_imgs, gen_depths = self.generator_ddp(z, cam2worlds[sl], **md)
+                    if use_d:
+                        g_preds = self.discriminator(gen_imgs, self.alpha, cond=None, **md)
+                        loss_G = F.softplus(-g_preds).mean()
+                    else:
+                        loss_G = zero
+                    photo = loss_mse(imgs[sl], gen_imgs) if md.get("photo_loss", False) else zero
+                    depth = loss_depth(depths[sl].to(self.device), gen_depths) if md.get("depth_loss", False) else zero
+                    loss = loss_G + photo + depth * md.get("depth_loss_weight", 1)
+                acc["g_loss"] += loss_G.detach().float()
+                acc["photo_loss"] += photo.detach().float()
+                acc["depth_loss"] += depth.detach().float()
+                self.scaler.scale(loss).backward()
 
     # ------------------------------------------------------------------------------------------------------------
     def step(self, sample: Dict) -> Dict[str, torch.Tensor]:
