@@ -168,9 +168,42 @@ static int launch_composite(const CompositeParams& p, cudaStream_t stream) {
   return check_launch(MERGE ? "cng_merge_composite" : "cng_composite_fwd");
 }
 
+// a11 on its own: stable (fine-first) order of a ray's 2S distances, and optionally the sorted distances.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) merge_sort_kernel(const float* __restrict__ t_fine, const float* __restrict__ t_coarse,
+                                                                         long long n_rays, int S, int32_t* __restrict__ order,
+                                                                         float* __restrict__ t_sorted) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long ray = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + warp;
+  if (ray >= n_rays) return;
+  const int n = 2 * S, n2 = next_pow2_min32(n);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem) + static_cast<size_t>(warp) * merge_smem_words(n, S);
+  load_and_sort_ray(keys, t_fine, t_coarse, ray, S, n, n2, lane);
+  for (int s = lane; s < n; s += 32) {
+    const unsigned long long k = keys[s];
+    if (order) order[ray * n + s] = key_src(k);
+    if (t_sorted) t_sorted[ray * n + s] = key_t(k);
+  }
+}
+
 }  // namespace cng
 
 extern "C" {
+
+int cng_merge_sort(const float* t_fine, const float* t_coarse, long long n_rays, int S, int32_t* order, float* t_sorted,
+                   cng_stream_t stream) {
+  CNG_REQUIRE(n_rays >= 0 && S >= 1, CNG_ERR_INVALID_ARGUMENT, "merge_sort: n_rays=%lld S=%d", n_rays, S);
+  CNG_REQUIRE(2 * S <= 512, CNG_ERR_UNSUPPORTED, "merge_sort: %d samples per ray > 512", 2 * S);
+  CNG_REQUIRE(n_rays == 0 || (t_fine && t_coarse && (order || t_sorted)), CNG_ERR_INVALID_ARGUMENT, "merge_sort: NULL pointer");
+  if (n_rays == 0) return CNG_OK;
+  if (int e = cng_device_check()) return e;
+  const unsigned grid = static_cast<unsigned>((n_rays + cng::kWarpsPerBlock - 1) / cng::kWarpsPerBlock);
+  const size_t smem = static_cast<size_t>(cng::kWarpsPerBlock) * cng::merge_smem_words(2 * S, S) * sizeof(unsigned long long);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(cng::merge_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  cng::merge_sort_kernel<<<grid, cng::kWarpsPerBlock * 32, smem, cng::as_stream(stream)>>>(t_fine, t_coarse, n_rays, S, order, t_sorted);
+  return cng::check_launch("cng_merge_sort");
+}
+
 
 int cng_composite_fwd(const float* rgb_sigma, const float* t, const float* noise, long long n_rays, int S,
                       float noise_std, int clamp_mode, int white_back, int last_back, float* rgb, float* dist,

@@ -453,6 +453,20 @@ def film_grad_from_g(dy_bf16, g_bf16, colsum) -> torch.Tensor:
     return dz
 
 
+def merge_sort(t_fine, t_coarse, want_sorted: bool = False):
+    """a11 alone: order [n_rays, 2S] int32 of the stable fine-first sort of cat([t_fine, t_coarse]) (and the sorted distances)."""
+    t_fine, t_coarse = _f32(t_fine, "t_fine"), _f32(t_coarse, "t_coarse")
+    S = t_coarse.shape[-1] if t_coarse.shape[-1] != 1 else t_coarse.shape[-2]
+    n_rays = t_coarse.numel() // S
+    tf, tc = t_fine.reshape(n_rays, S), t_coarse.reshape(n_rays, S)
+    order = torch.empty((n_rays, 2 * S), dtype=torch.int32, device=tc.device)
+    t_sorted = torch.empty((n_rays, 2 * S), dtype=torch.float32, device=tc.device) if want_sorted else None
+    with torch.cuda.device(tc.device), _timed("cng_merge_sort"):
+        _lib.call("cng_merge_sort", _ptr(tf), _ptr(tc), n_rays, S, _ptr(order), _ptr(t_sorted), _stream(tc))
+    _count()
+    return (order, t_sorted) if want_sorted else order
+
+
 def composite_bwd(rgb_sigma, t, noise, d_rgb, d_dist, noise_std: float, clamp_mode, white_back=False, last_back=False) -> torch.Tensor:
     """Backward of composite_fwd w.r.t. rgb_sigma: d_rgb [..., 3] and / or d_dist [...] (None allowed) -> [..., S, 4]."""
     code = clamp_code(clamp_mode)

@@ -188,6 +188,13 @@ CNG_API int cng_resample_from_coarse(const float* t_coarse, const float* weights
                              long long n, int S, float* t_fine, int64_t* inds,
                              cng_stream_t stream);
 
+/* a11 alone: the order of torch.sort over cat([fine, coarse]) along the sample axis (generators/generators.py:163-167),
+ * stable with the fine samples first among equal distances.
+ *   t_fine, t_coarse [n_rays, S]; order [n_rays, 2S] int32 out (index into the fine-first concatenation) and / or
+ *   t_sorted [n_rays, 2S] out; either may be NULL.   2S <= 512. */
+CNG_API int cng_merge_sort(const float* t_fine, const float* t_coarse, long long n_rays, int S, int32_t* order,
+                   float* t_sorted, cng_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * K3 final: merge coarse+fine by depth (stable: fine first), composite, format the image.
  * Replaces cat/sort/gather (generators/generators.py:163-167), the final fancy_integration

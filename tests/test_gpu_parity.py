@@ -389,6 +389,23 @@ def test_merge_composite_vs_oracle(ops, B, img, S, white, last, noise_std, clamp
     _assert_rel(depth.cpu(), depth_ref, what="depth")
 
 
+@pytest.mark.parametrize("n_rays,S", [(100, 24), (7, 100), (33, 256), (1, 1), (50, 12)])
+def test_merge_sort_is_torch_stable_sort(ops, n_rays, S):
+    """cng_merge_sort: bit-exact order of torch.sort(stable) over cat([fine, coarse]) -- ties (fine == coarse, runs of equal
+    fine distances), an unsorted coarse ray, sorted and unsorted fine lists."""
+    g = torch.Generator().manual_seed(S)
+    t_c = torch.sort(torch.rand((n_rays, S), generator=g) * 1.7 + 0.25, dim=1).values
+    t_f = torch.rand((n_rays, S), generator=g) * 1.7 + 0.25
+    t_f[0, : min(3, S)] = t_c[0, : min(3, S)]
+    if n_rays > 2:
+        t_f[1] = t_f[1, 0]
+        t_c[2] = t_c[2].flip(0)
+    order, t_sorted = ops.merge_sort(dev(t_f), dev(t_c), want_sorted=True)
+    cat = torch.cat([t_f, t_c], dim=1)
+    ref_t, ref_i = torch.sort(cat, dim=1, stable=True)
+    assert torch.equal(order.cpu().long(), ref_i) and torch.equal(t_sorted.cpu(), ref_t)
+
+
 def test_merge_composite_rejects_more_than_512_samples(ops):
     """Documented limit of the per-warp sort (include/cng_b200.h): 2S <= 512 samples per ray; beyond it the call fails loudly."""
     from conditioned_nerf_gan_b200._lib import CngError
