@@ -15,7 +15,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libcng_b200.so")
 STAMP = os.path.join(PKG, "csrc", ".build_stamp")
-SOURCES = ["cng_api.cu", "raymarch_gather.cu", "film_siren_simt.cu", "film_siren_tc.cu", "film_siren_tc2.cu", "film_siren_tc3.cu", "composite.cu", "sample_pdf.cu", "backward.cu", "render.cu"]
+SOURCES = ["cng_api.cu", "raymarch_gather.cu", "film_siren_simt.cu", "film_siren_tc.cu", "film_siren_tc2.cu", "film_siren_tc3.cu", "composite.cu", "sample_pdf.cu", "backward.cu", "film_siren_bwd.cu", "render.cu"]
 # CNG_TC_EPI_WARPS (4 or 8): epilogue warps per tile slot of the one-CTA-per-SM tcgen05 kernel (film_siren_tc.cu)
 EPI_WARPS = os.environ.get("CNG_TC_EPI_WARPS", "8")
 EPI_PIPELINE = os.environ.get("CNG_TC_EPI_PIPELINE", "1")    # 1: double-buffer the epilogue's TMEM loads
@@ -70,7 +70,7 @@ def build(force: bool = False, verbose: bool = False, out: str = None, extra_fla
             raise RuntimeError(f"nvcc failed on {s}:\n{out}")
         if verbose and out:
             print(out)
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-ldl"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
@@ -95,7 +95,7 @@ def _build_variant(out: str, extra_flags, verbose: bool) -> str:
             raise RuntimeError(f"nvcc failed on {s}:\n{o}")
         if verbose and o:
             print(o)
-    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, *objs], stdout=subprocess.PIPE,
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, *objs, "-ldl"], stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")

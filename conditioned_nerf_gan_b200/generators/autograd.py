@@ -25,7 +25,12 @@ import torch
 from .. import ops
 from .volumetric_rendering import camera_tables
 
+import os
+
 HAS_BACKWARD = True
+# "lib": one cng_film_siren_bwd call per chunk (recompute, dz, cuBLAS GEMMs issued inside the library);
+# "py": the same sequence issued kernel by kernel from here (torch.mm for the GEMMs) -- kept for A/B, same numbers
+BWD_IMPL = os.environ.get("CNG_BWD_IMPL", "lib")
 CHUNK_ROWS = 1 << 20          # points per recompute chunk of the MLP backward (~8.6 GB of x / g dumps at L = 8)
 
 
@@ -143,6 +148,11 @@ class _FilmSiren(torch.autograd.Function):
             colsum = torch.zeros((L, H), dtype=torch.float32, device=dev)
             for r0 in range(0, N, CHUNK_ROWS):
                 r1 = min(N, r0 + CHUNK_ROWS)
+                if BWD_IMPL == "lib" and C == 32 and H == 256:
+                    ops.film_siren_bwd(feat[b, r0:r1].detach().contiguous(), d_out[b, r0:r1].contiguous(), out[b, r0:r1].contiguous(), ws, bs,
+                                       ws_bf, fr_all[0], ph_all[0], fw, fb, fw_bf, ctx.sigmoid_rgb, d_feat[b, r0:r1], dW_item, colsum, d_fw, d_fb,
+                                       ctx.res_save, ctx.res_add)
+                    continue
                 x0 = feat[b:b + 1, r0:r1].detach().contiguous()
                 _, xs, gs = ops.film_siren_fwd_train(x0, ws, bs, fr_all, ph_all, fw, fb, ctx.sigmoid_rgb, ctx.res_save, ctx.res_add)
                 xs, gs = xs[:, 0], gs[:, 0]                                    # [L, P, H]

@@ -438,6 +438,39 @@ def film_siren_fwd_train(feat, layer_w, layer_b, freq, phase, final_w, final_b, 
     return out, xs, gs
 
 
+_BWD_WS = {}
+
+
+def film_siren_bwd(feat, d_out, out, layer_w, layer_b, layer_w_bf16, freq, phase, final_w, final_b, final_w_bf16, sigmoid_rgb: bool,
+                   d_feat, d_w_acc, colsum_acc, d_final_w_acc, d_final_b_acc, res_save_mask: int = 0, res_add_mask: int = 0) -> None:
+    """The MLP backward of one chunk of points of one item as ONE library call (cng_film_siren_bwd): feat [P,C], d_out / out
+    [P,4]; writes d_feat [P,C], accumulates into d_w_acc[l], colsum_acc [L,HID], d_final_w_acc, d_final_b_acc (all fp32)."""
+    P, C = feat.shape
+    L = len(layer_w)
+    HID = layer_w[0].shape[0]
+    dev = feat.device
+    for name, t in (("feat", feat), ("d_out", d_out), ("d_feat", d_feat), ("colsum_acc", colsum_acc), ("d_final_w_acc", d_final_w_acc),
+                    ("d_final_b_acc", d_final_b_acc), ("freq", freq), ("phase", phase)):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise RuntimeError(f"film_siren_bwd: {name} must be a contiguous float32 CUDA tensor")
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        need = int(lib.cng_film_siren_bwd_workspace_bytes(P, C, HID, L))
+        key = (dev.index, torch.cuda.current_stream().cuda_stream)
+        ws = _BWD_WS.get(key)
+        if ws is None or ws.numel() < need:
+            _BWD_WS.pop(key, None)
+            ws = _BWD_WS[key] = torch.empty((need,), dtype=torch.uint8, device=dev)
+        scratch = _res_scratch(dev) if (res_save_mask or res_add_mask) else None
+        arr = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+        with _timed("cng_film_siren_bwd"):
+            _lib.call("cng_film_siren_bwd", _ptr(feat), _ptr(d_out), _ptr(out), P, C, HID, L, arr(layer_w), arr(layer_b), arr(layer_w_bf16),
+                      _ptr(freq), _ptr(phase), _ptr(final_w), _ptr(final_b), _ptr(final_w_bf16), int(bool(sigmoid_rgb)), int(res_save_mask),
+                      int(res_add_mask), _ptr(ws), ws.numel(), _ptr(scratch), scratch.numel() if scratch is not None else 0, _ptr(d_feat),
+                      arr(d_w_acc), _ptr(colsum_acc), _ptr(d_final_w_acc), _ptr(d_final_b_acc), _stream(feat))
+    _count(5 + 4 * L)
+
+
 def film_grad_from_g(dy_bf16, g_bf16, colsum) -> torch.Tensor:
     """dz = dy * g (dy, dz bf16, g fp16, [P,HID]); accumulates the column sums of dz into colsum (fp32 [HID], in place)."""
     for name, t, dt in (("dy", dy_bf16, torch.bfloat16), ("g", g_bf16, torch.float16)):

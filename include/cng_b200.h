@@ -301,6 +301,25 @@ CNG_API int cng_film_siren_fwd_train_res(const float* feat, int B, long long N, 
                                  size_t workspace_bytes, float* rgb_sigma, void* x_dump_bf16,
                                  void* g_dump_f16, unsigned res_save_mask, unsigned res_add_mask,
                                  void* res_scratch, size_t res_scratch_bytes, cng_stream_t stream);
+/* The whole MLP backward of one chunk of points of ONE batch item (autograd through FiLMLayer.forward x L + head,
+ * siren.py:146-160, 573-579; utils.py:711): recompute with dumps, head, then per layer dz = dy * g, dW += dz^T x,
+ * dy = dz W; the GEMMs are cuBLAS bf16 -> fp32 library calls issued from inside (cuBLAS is bound at run time).
+ *   feat [P, C]; d_out [P, 4] gradient w.r.t. rgb_sigma; out [P, 4] the forward output (read when sigmoid_rgb);
+ *   layer_w_host / layer_b_host: HOST arrays of L device pointers (fp32), layer_w_bf16_host: the same weights in bf16;
+ *   freq, phase [L*HID] of this item; final_w [4, HID], final_b [4], final_w_bf16 [4, HID];
+ *   outputs: d_feat [P, C] (written); accumulated (+=): d_w_acc_host[l] [HID, K_l] fp32, colsum_acc [L, HID] (column sums
+ *   of dz_l: d_bias = colsum, d_phase = colsum / freq, d_freq = rowsum(W * dW) / freq + b * d_phase on the host),
+ *   d_final_w_acc [4, HID], d_final_b_acc [4].
+ *   workspace: cng_film_siren_bwd_workspace_bytes(P, C, HID, L), 256-byte aligned.  Residual masks / scratch as in
+ *   cng_film_siren_fwd_res.  HID == 256, C == 32, P < 2^31. */
+CNG_API size_t cng_film_siren_bwd_workspace_bytes(long long P, int C, int HID, int L);
+CNG_API int cng_film_siren_bwd(const float* feat, const float* d_out, const float* out, long long P, int C, int HID, int L,
+                       const float* const* layer_w_host, const float* const* layer_b_host,
+                       const void* const* layer_w_bf16_host, const float* freq, const float* phase,
+                       const float* final_w, const float* final_b, const void* final_w_bf16, int sigmoid_rgb,
+                       unsigned res_save_mask, unsigned res_add_mask, void* workspace, size_t workspace_bytes,
+                       void* res_scratch, size_t res_scratch_bytes, float* d_feat, float* const* d_w_acc_host,
+                       float* colsum_acc, float* d_final_w_acc, float* d_final_b_acc, cng_stream_t stream);
 /* dz = dy * g elementwise (dy, dz bf16, g fp16, all [P,HID]); colsum [HID] += column sums of dz (fp32, atomic). HID == 256. */
 CNG_API int cng_film_grad_from_g(const void* dy_bf16, const void* g_f16, long long P, int HID, void* dz_bf16,
                          float* colsum, cng_stream_t stream);
