@@ -580,10 +580,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--siren", default="TALLSIREN_FG", choices=sorted(SIREN_LAYERS))
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--precision", default=None, choices=["bf16", "fp16", "fp32"],
+                    help="default: bf16 operands; fp16 for the classes offered with fp16 operands only (SHORTSIREN_FG)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="render", choices=["render", "train", "train_generator", "video"])
     args = ap.parse_args()
+    if args.precision is None:
+        args.precision = "fp16" if args.siren.startswith("SHORT") else "bf16"
     if args.warmup < 3 and args.impl == "b200":
         print(f"note: --warmup {args.warmup} < 3 (timing rules ask for >= 3)", file=sys.stderr)
     if args.impl == "reference":

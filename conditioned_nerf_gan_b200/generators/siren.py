@@ -29,8 +29,10 @@ __all__ = ["FiLMLayer", "SirenLayer", "ResSirenBlock", "TALLSIREN_dRes", "TALLSI
 
 def default_precision(class_default: str = "bf16") -> str:
     """Arithmetic of the fused MLP: 'bf16' / 'fp16' (tcgen05 tensor-core path, 16-bit operands, fp32 accumulate)
-    or 'fp32' (exact FFMA path).  CNG_PRECISION overrides the class default."""
-    return os.environ.get("CNG_PRECISION", class_default)
+    or 'fp32' (exact FFMA path).  CNG_PRECISION overrides the class default; asking for bf16 on a class that is only
+    offered with fp16 operands (see ``_FiLMSirenFG.precision``) selects fp16."""
+    p = os.environ.get("CNG_PRECISION", class_default)
+    return "fp16" if (p == "bf16" and class_default == "fp16") else p
 
 
 class FiLMLayer(nn.Module):
@@ -98,6 +100,23 @@ class _FiLMSirenFG(nn.Module):
 
     res_save_mask = 0       # residual blocks, see cng_film_siren_fwd_res (include/cng_b200.h)
     res_add_mask = 0
+
+    @property
+    def precision(self) -> str:
+        """'bf16' | 'fp16' (tcgen05 path, 16-bit operands, fp32 accumulate) | 'fp32' (exact FFMA path).  The classes built
+        with ``frequency_init(12)`` (SHORTSIREN_FG / _F / _FRes) are offered with fp16 operands only: their pre-activations
+        are twice as large and bf16 operands gave 1.7e-2 max-abs, over the 1e-2 contract (BASELINE north_star); fp16 runs at
+        the same tensor-core rate and is the reference's own autocast dtype."""
+        return self._precision
+
+    @precision.setter
+    def precision(self, value: str) -> None:
+        if value not in ops.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(ops.PRECISIONS)}, got {value!r}")
+        if value == "bf16" and self.tensor_core_operands == "fp16":
+            raise ValueError(f"{type(self).__name__} is not offered with bf16 operands (1.7e-2 max-abs, over the 1e-2 contract); "
+                             "use precision='fp16' (same tensor-core rate) or 'fp32'")
+        self._precision = value
 
     def linear_layers(self) -> List[nn.Linear]:
         """The network's linear layers in execution order."""

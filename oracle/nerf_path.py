@@ -35,6 +35,8 @@ __all__ = [
     "layer_keys",
     "resolve_siren_type",
     "init_generator_state",
+    "dense_head_state",
+    "DENSE_HEAD_GAINS",
     "camera_rays",
     "jitter_samples",
     "camera_to_world",
@@ -139,6 +141,35 @@ def init_generator_state(
     state["siren.mapping_network.weight"] = uniform((n_map, z_dim), 1.0 / math.sqrt(z_dim))
     state["siren.mapping_network.bias"] = uniform((n_map,), 1.0 / math.sqrt(z_dim))
     return state
+
+
+# Random-init heads give sigma ~ 1e-2 (alpha ~ 1e-3 per sample, no occlusion, every relu-mode pixel decided by the far-plane
+# sample).  The parity fixtures with REAL density scale the head rows of the SAME random-init network: (sigma gain, rgb gain),
+# chosen per class so that alpha spans 0..~0.9 per sample, rays saturate before the far plane (mean far-plane weight < 1e-2)
+# and the rendered image has texture.  The reference is run on these weights unchanged (tests/golden/make_golden.py).
+# FiLM classes only: the unmodulated ones (SHORTSIREN_F, *_dRes*) are constant in space to ~1e-5 at random init whatever the
+# head gain, so their image-level fixtures stay the near-empty ones (whole-image PSNR asserted in fp32 only).
+DENSE_HEAD_GAINS = {           # class -> (sigma gain, rgb gain, first-layer gain)
+    "TALLSIREN_FG": (300.0, 10.0, 1.0),
+    "SHORTSIREN_FG": (300.0, 3.0, 1.0),
+    "DOUBLESIREN_FG": (300.0, 3.0, 1.0),
+    "SingleSIREN_dg": (1000.0, 3.0, 1.0),
+}
+
+
+def dense_head_state(state: Dict[str, torch.Tensor], sigma_gain: float, rgb_gain: float = 1.0, first_layer_gain: float = 1.0,
+                     sigma_bias: float = 0.0) -> Dict[str, torch.Tensor]:
+    """Copy of ``state`` whose head (``final_layer`` = nn.Linear(hidden, 4), siren.py:533) has its sigma row scaled by
+    ``sigma_gain`` (bias set to ``sigma_bias``) and its three colour rows by ``rgb_gain``, and whose first linear layer is
+    scaled by ``first_layer_gain``: a network with occlusion and texture."""
+    st = {k: v.clone() for k, v in state.items()}
+    st["siren.final_layer.weight"][3] *= sigma_gain
+    st["siren.final_layer.bias"][3] = sigma_bias
+    st["siren.final_layer.weight"][:3] *= rgb_gain
+    if first_layer_gain != 1.0:
+        first = "siren.network.0.layer.weight"
+        st[first] *= first_layer_gain
+    return st
 
 
 # --------------------------------------------------------------------------------------------

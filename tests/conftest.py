@@ -44,6 +44,9 @@ def load_golden(name):
 FORWARD_FIXTURES = ["fwd_TALLSIREN_FG", "fwd_SHORTSIREN_FG", "fwd_DOUBLESIREN_FG", "fwd_SingleSIREN_dg", "fwd_SHORTSIREN_F", "fwd_TALLSIREN_dRes", "fwd_TALLSIREN_dResLong", "fwd_SHORTSIREN_FRes"]
 
 
+DENSE_FIXTURES = ["fwd_dense_TALLSIREN_FG", "fwd_dense_SHORTSIREN_FG", "fwd_dense_DOUBLESIREN_FG", "fwd_dense_SingleSIREN_dg"]
+
+
 def fixture_inputs(name):
     """Rebuild (state, z, cam2world, draws, meta, taps) of a forward fixture."""
     from oracle import nerf_path as oracle
@@ -52,6 +55,9 @@ def fixture_inputs(name):
     seed = meta.pop("seed")
     siren_type = meta.pop("siren_type")
     state = oracle.init_generator_state(siren_type, 256, 32, 256, seed=seed)
+    gains = meta.pop("dense_head_gains", None)
+    if gains is not None:
+        state = oracle.dense_head_state(state, *gains)
     checksum = sum(float(v.double().abs().sum()) for v in state.values())
     assert abs(checksum - float(fx["state/checksum"])) < 1e-9 * checksum, "torch CPU generator drifted"
     film = oracle.SIREN_SPECS[oracle.resolve_siren_type(siren_type)].get("film", True)

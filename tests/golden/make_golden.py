@@ -115,9 +115,15 @@ def run_reference_forward(siren_type, state, z, cam, draws, meta):
 
 
 def make_forward_fixture(siren_type, seed, hierarchical=True, clamp_mode="relu", nerf_noise=0.0,
-                         white_back=True, last_back=False, img_size=12, S=8, V=12, B=2, feat_std=0.3):
+                         white_back=True, last_back=False, img_size=12, S=8, V=12, B=2, feat_std=0.3, dense=False):
+    """``dense``: the head rows of the random-init network are scaled by oracle.DENSE_HEAD_GAINS (alpha spans 0..~0.9, rays
+    saturate, the image has texture) before the REFERENCE renders it; the gains are stored in the fixture's meta."""
     g = torch.Generator().manual_seed(seed)
     state = oracle.init_generator_state(siren_type, z_dim=256, input_dim=32, hidden_dim=256, seed=seed)
+    gains = None
+    if dense:
+        gains = list(oracle.DENSE_HEAD_GAINS[oracle.resolve_siren_type(siren_type)])
+        state = oracle.dense_head_state(state, *gains)
     vol = torch.randn((B, 32, V, V, V), generator=g) * feat_std
     glob = torch.randn((B, 256), generator=g) * 0.05 + 0.19
     rng = np.random.RandomState(seed)
@@ -144,7 +150,12 @@ def make_forward_fixture(siren_type, seed, hierarchical=True, clamp_mode="relu",
     fx.update({f"draw/{k}": v.numpy() for k, v in draws.items()})
     fx.update({f"tap/{k}": v.numpy() for k, v in taps.items()})
     fx["in/volume"], fx["in/global"], fx["in/cam2world"] = vol.numpy(), glob.numpy(), cam.numpy()
-    fx["meta/json"] = np.array(__import__("json").dumps(dict(meta, siren_type=siren_type, seed=seed)))
+    extra = dict(siren_type=siren_type, seed=seed)
+    if gains is not None:
+        extra["dense_head_gains"] = gains
+        w = taps["weights_final"][..., 0]
+        print(f"  dense {siren_type}: far-plane weight mean {float(w[..., -1].mean()):.4f}, pixel std {float(taps['pixels'].std()):.3f}")
+    fx["meta/json"] = np.array(__import__("json").dumps(dict(meta, **extra)))
     return fx
 
 
@@ -283,8 +294,24 @@ def make_train_step_fixture(steps=2):
     return fx
 
 
+def dense_fixtures():
+    """Forward fixtures with real density: 16x16, 12+12 samples, 16^3 volume, batch 2."""
+    kw = dict(img_size=16, S=12, V=16, B=2, dense=True)
+    return {
+        "fwd_dense_TALLSIREN_FG": make_forward_fixture("TALLSIREN_FG", 31, **kw),
+        "fwd_dense_SHORTSIREN_FG": make_forward_fixture("SHORTSIREN_dg", 32, nerf_noise=0.5, **kw),
+        "fwd_dense_DOUBLESIREN_FG": make_forward_fixture("DoubleSIREN_dg", 33, white_back=False, last_back=True, **kw),
+        "fwd_dense_SingleSIREN_dg": make_forward_fixture("SingleSIREN_dg", 34, hierarchical=False, **kw),
+    }
+
+
 def main():
     out = {}
+    if "--dense-only" in sys.argv:
+        for name, fx in dense_fixtures().items():
+            np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
+            print(f"{name}: {os.path.getsize(os.path.join(HERE, name + '.npz')) / 1024:.0f} KiB")
+        return
     if "--dres-only" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "fwd_TALLSIREN_dRes.npz"), **make_forward_fixture("TALLSIREN_dRes", 16))
         np.savez_compressed(os.path.join(HERE, "fwd_TALLSIREN_dResLong.npz"), **make_forward_fixture("TALLSIREN_dResLong", 17, hierarchical=False))
@@ -304,6 +331,7 @@ def main():
     out["fwd_TALLSIREN_dResLong"] = make_forward_fixture("TALLSIREN_dResLong", 17, hierarchical=False)
     out["fwd_SHORTSIREN_FRes"] = make_forward_fixture("SHORTSIREN_FRes", 18, clamp_mode="softplus", nerf_noise=0.3)
     out["functions"] = make_function_fixture()
+    out.update(dense_fixtures())
     for name, fx in out.items():
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **fx)

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import FORWARD_FIXTURES, fixture_inputs, load_golden
+from conftest import DENSE_FIXTURES, FORWARD_FIXTURES, fixture_inputs, load_golden
 from oracle import nerf_path as oracle
 
 pytestmark = pytest.mark.gpu
@@ -162,21 +162,37 @@ def test_film_siren_fp32_vs_oracle(ops, siren_type, B, N):
     assert err < 5e-4, err       # fp32 accumulation-order differences amplified by freq ~ 30 per layer
 
 
-@pytest.mark.parametrize("siren_type", ["TALLSIREN_FG", "SHORTSIREN_FG", "DOUBLESIREN_FG", "SingleSIREN_dg"])
-@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+# (class, operand format) pairs the host API offers: the frequency_init(12) classes are fp16-only (bf16 operands gave 1.7e-2
+# max-abs on SHORTSIREN_FG, over north_star's 1e-2, so that mode was removed; generators/siren.py::_FiLMSirenFG.precision)
+TC_CASES = [("TALLSIREN_FG", "bf16"), ("TALLSIREN_FG", "fp16"), ("SHORTSIREN_FG", "fp16"), ("DOUBLESIREN_FG", "bf16"),
+            ("DOUBLESIREN_FG", "fp16"), ("SingleSIREN_dg", "bf16"), ("SingleSIREN_dg", "fp16")]
+
+
+@pytest.mark.parametrize("siren_type,precision", TC_CASES)
 @pytest.mark.parametrize("B,N", [(2, 4096), (1, 100), (3, 129), (1, 128 * 300 + 5)])
 def test_film_siren_tensor_core_vs_oracle(ops, siren_type, precision, B, N):
     """tcgen05 path, bf16 or fp16 operands.  Features ~ N(0, 0.3^2) (std of a random-init UNet3D output).
-    Bar: 1e-2 max-abs.  bf16 operands miss it on SHORTSIREN_FG (frequency_init(12) doubles the pre-activations; measured
-    1.4e-2, which is why that class defaults to fp16 operands); fp16 operands meet it everywhere."""
+    Bar (north_star): 1e-2 max-abs on rgb and sigma, for every offered (class, operand format) pair."""
     spec, ws, bs, feat, freq, phase, fw, fb, ref = _mlp_setup(siren_type, B, N, 0.3)
     out = _run_mlp(ops, precision, spec, ws, bs, feat, freq, phase, fw, fb)
     assert torch.isfinite(out).all()
     err = (out - ref).abs().max().item()
     rms = (out - ref).pow(2).mean().sqrt().item()
     print(f"{siren_type} {precision} B={B} N={N}: max-abs err {err:.3e}, rms {rms:.3e}")
-    tol = 3e-2 if (precision == "bf16" and siren_type == "SHORTSIREN_FG") else 1e-2
-    assert err < tol, err
+    assert err < 1e-2, err
+
+
+@pytest.mark.parametrize("siren_type,precision", TC_CASES)
+def test_film_siren_tensor_core_stress_features(ops, siren_type, precision):
+    """SURVEY.md 8(d) / BASELINE.md 5.5 "stress" case: features ~ N(0, 1) instead of the realistic N(0, 0.3^2).  The layer-0
+    pre-activations grow 3.3x; layer 0 runs split (hi/lo) so its own error does not grow, but every later layer sees the
+    same sin() outputs, so the error stays at the realistic-case level.  Reported for DESIGN.md; the bar stays 1e-2."""
+    spec, ws, bs, feat, freq, phase, fw, fb, ref = _mlp_setup(siren_type, 2, 20000, 1.0, seed=3)
+    out = _run_mlp(ops, precision, spec, ws, bs, feat, freq, phase, fw, fb)
+    err = (out - ref).abs().max().item()
+    rms = (out - ref).pow(2).mean().sqrt().item()
+    print(f"STRESS N(0,1) features {siren_type} {precision}: max-abs err {err:.3e}, rms {rms:.3e}")
+    assert err < 1e-2, err
 
 
 def test_film_siren_bf16_matches_fp32_kernel_on_large_batch(ops):
@@ -187,8 +203,7 @@ def test_film_siren_bf16_matches_fp32_kernel_on_large_batch(ops):
     assert (a - b).abs().max().item() < 1e-2
 
 
-@pytest.mark.parametrize("siren_type", ["TALLSIREN_FG", "SHORTSIREN_FG", "DOUBLESIREN_FG", "SingleSIREN_dg"])
-@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("siren_type,precision", TC_CASES)
 @pytest.mark.parametrize("B,N", [(1, 100), (3, 129), (5, 128 * 9), (2, 128 * 700 + 17)])
 def test_film_siren_pipelined_kernel_is_bit_identical_to_ping_pong_kernel(ops, siren_type, precision, B, N):
     """The layer-pipelined tcgen05 kernel (film_siren_tc3.cu: one tile per CTA, double-buffered accumulator, the next
@@ -212,11 +227,10 @@ def test_film_siren_pipelined_kernel_is_bit_identical_to_ping_pong_kernel(ops, s
         lib.cng_internal_set_tc_version(0)
     assert torch.equal(a, b), f"max |v1 - v3| = {(a - b).abs().max().item():.3e}"
     assert torch.equal(a, c), f"max |v1 - v2| = {(a - c).abs().max().item():.3e}"
-    tol = 3e-2 if (precision == "bf16" and siren_type == "SHORTSIREN_FG") else 1e-2
-    assert (b - ref).abs().max().item() < tol
+    assert (b - ref).abs().max().item() < 1e-2
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 3e-2), ("fp16", 5e-3)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 1e-2), ("fp16", 5e-3)])
 @pytest.mark.parametrize("B,N", [(1, 100), (3, 129), (2, 128 * 700 + 17)])
 def test_film_siren_residual_blocks_vs_oracle(ops, precision, tol, B, N):
     """cng_film_siren_fwd_res: TALLSIREN_dRes as six linear layers with the block input kept and re-added (siren.py:218-230,
@@ -445,9 +459,20 @@ def _generator(siren_type, state, precision):
     return gen
 
 
-@pytest.mark.parametrize("name", FORWARD_FIXTURES)
-@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
-def test_forward_vs_reference_golden(name, precision):
+FP16_ONLY = ("SHORTSIREN_FG", "SHORTSIREN_dg", "SHORTSIREN_F", "SHORTSIREN_FRes")       # classes whose tensor-core mode is fp16 operands
+
+
+def _fixture_cases(names):
+    out = []
+    for n in names:
+        for precision in ("fp32", "bf16", "fp16"):
+            if precision == "bf16" and any(n.endswith(c) for c in FP16_ONLY):
+                continue
+            out.append((n, precision))
+    return out
+
+
+def _render_fixture(name, precision):
     state, siren_type, z, cam, draws, meta, taps = fixture_inputs(name)
     gen = _generator(siren_type, state, precision)
     zc = dev_z(z)
@@ -462,29 +487,55 @@ def test_forward_vs_reference_golden(name, precision):
     B, img, S = cam.shape[0], meta["img_size"], meta["num_steps"]
     assert pixels.shape == (B, 3, img, img) and depth.shape == (B, img, img) and pixels.is_contiguous()
     assert torch.allclose(out["points_coarse"].cpu(), taps["points_coarse"].reshape(B, -1, S, 3), rtol=0, atol=5e-7)
-    mlp_tol = 5e-4 if precision == "fp32" else (3e-2 if ("SHORT" in name and precision == "bf16") else 1e-2)
-    if name in ("fwd_SHORTSIREN_F", "fwd_TALLSIREN_dRes", "fwd_TALLSIREN_dResLong", "fwd_SHORTSIREN_FRes") and precision == "bf16":
-        mlp_tol = 1e-2       # no freq ~ 30 in front of the pre-activations: bf16 operands are comfortably inside the bar
+    return state, siren_type, z, cam, draws, meta, taps, out, pixels.cpu(), depth.cpu()
+
+
+@pytest.mark.parametrize("name,precision", _fixture_cases(FORWARD_FIXTURES))
+def test_forward_vs_reference_golden(name, precision):
+    """Random-init fixtures recorded from the reference (near-empty scenes: sigma ~ 1e-2, every relu-mode pixel is decided by
+    the far-plane sample, oracle.far_plane_sigma).  Asserted: the MLP bar (1e-2 max-abs in tensor-core modes) on the coarse
+    pass and the whole-image PSNR / pixel / depth bars in fp32 mode.  The reduced-precision image PSNR of these scenes is
+    printed, not asserted: the image-level bar is asserted on the fixtures WITH density (test_forward_vs_reference_dense)."""
+    state, siren_type, z, cam, draws, meta, taps, out, pixels, depth = _render_fixture(name, precision)
+    B, img, S = cam.shape[0], meta["img_size"], meta["num_steps"]
+    mlp_tol = 5e-4 if precision == "fp32" else 1e-2
     err_c = (out["rgb_sigma_coarse"].cpu() - taps["rgb_sigma_coarse"].reshape(B, -1, S, 4)).abs().max().item()
-    err_p = (pixels.cpu() - taps["pixels"]).abs().max().item()
-    psnr_full = oracle.psnr(pixels.cpu(), taps["pixels"])
-    # pixels decided by the sign of a far-plane density that is zero within the MLP tolerance are excluded
-    # from the image metric (oracle.far_plane_sigma explains why); their fraction is reported
-    ref = oracle.render(state, siren_type, z, cam, draws, **meta)
-    assert torch.equal(ref["pixels"], taps["pixels"].reshape(ref["pixels"].shape)) or torch.allclose(ref["pixels"], taps["pixels"], atol=2e-5)
-    decided = torch.ones((B, img * img), dtype=torch.bool)
-    if meta["clamp_mode"] == "relu":
-        decided = oracle.far_plane_sigma(ref, meta["nerf_noise"]).abs() >= 2 * mlp_tol
-    mask = decided.reshape(B, 1, img, img).expand(B, 3, img, img)
-    psnr = oracle.psnr(pixels.cpu()[mask], taps["pixels"][mask])
-    print(f"{name} {precision}: coarse rgb_sigma max-abs {err_c:.3e}; pixels max-abs {err_p:.3e}, PSNR {psnr_full:.1f} dB "
-          f"(full image), {psnr:.1f} dB on the {decided.float().mean().item():.1%} far-plane-decided pixels")
+    err_p = (pixels - taps["pixels"]).abs().max().item()
+    psnr_full = oracle.psnr(pixels, taps["pixels"])
+    print(f"{name} {precision}: coarse rgb_sigma max-abs {err_c:.3e}; pixels max-abs {err_p:.3e}, PSNR {psnr_full:.1f} dB (whole image)")
     assert err_c < mlp_tol
-    assert decided.float().mean().item() > 0.5
-    assert psnr >= (60.0 if precision == "fp32" else 40.0)
     if precision == "fp32":
         assert psnr_full >= 60.0 and err_p < 2e-3
-        assert torch.allclose(depth.cpu(), taps["depth"], rtol=0, atol=2e-3)
+        assert torch.allclose(depth, taps["depth"], rtol=0, atol=2e-3)
+    elif meta["clamp_mode"] == "softplus":
+        assert psnr_full >= 40.0            # continuous clamp: the whole-image bar holds on the near-empty scenes too
+
+
+@pytest.mark.parametrize("name,precision", _fixture_cases(DENSE_FIXTURES))
+def test_forward_vs_reference_dense(name, precision):
+    """Fixtures with real density recorded from the reference (head rows of the random-init network scaled,
+    oracle.DENSE_HEAD_GAINS: alpha spans 0..~0.9, rays saturate, occlusion decides the pixel).  All clamp_mode "relu".
+    Whole image, every pixel: PSNR >= 40 dB in tensor-core modes (north_star), >= 60 dB in fp32 mode.  The MLP bar is
+    1e-2 max-abs on the colours and 1e-2 x sigma gain on sigma (the same relative error of the same hidden activations)."""
+    state, siren_type, z, cam, draws, meta, taps, out, pixels, depth = _render_fixture(name, precision)
+    B, img, S = cam.shape[0], meta["img_size"], meta["num_steps"]
+    sigma_gain, rgb_gain, _ = oracle.DENSE_HEAD_GAINS[oracle.resolve_siren_type(siren_type)]
+    d_c = (out["rgb_sigma_coarse"].cpu() - taps["rgb_sigma_coarse"].reshape(B, -1, S, 4)).abs()
+    err_rgb, err_sigma = d_c[..., :3].max().item(), d_c[..., 3].max().item()
+    psnr = oracle.psnr(pixels, taps["pixels"])
+    err_p = (pixels - taps["pixels"]).abs().max().item()
+    err_d = (depth - taps["depth"]).abs().max().item()
+    w = taps["weights_final"][..., 0]
+    print(f"{name} {precision}: coarse rgb max-abs {err_rgb:.3e}, sigma {err_sigma:.3e} (gain {sigma_gain:g}); pixels max-abs {err_p:.3e}, "
+          f"depth {err_d:.3e}, PSNR {psnr:.1f} dB whole image; reference far-plane weight mean {float(w[..., -1].mean()):.4f}")
+    if precision == "fp32":
+        assert err_rgb < 5e-4 * max(1.0, rgb_gain) and err_sigma < 5e-4 * sigma_gain
+        assert psnr >= 60.0
+        assert err_d < 5e-3
+    else:
+        assert err_rgb < 1e-2 * (rgb_gain if not oracle.SIREN_SPECS[oracle.resolve_siren_type(siren_type)]["sigmoid_rgb"] else 1.0)
+        assert err_sigma < 1e-2 * sigma_gain
+        assert psnr >= 40.0
 
 
 @pytest.mark.parametrize("siren_type", ["TALLSIREN_FG", "SHORTSIREN_FG", "DOUBLESIREN_FG"])
@@ -618,74 +669,141 @@ def test_channels_last_3d_volume_needs_no_layout_kernel(ops):
     assert ops.volume_to_channels_last(vol_cl3d).data_ptr() == vol_cl3d.data_ptr()
 
 
-def test_config1_full_size_vs_oracle():
-    """BASELINE configs[0] at full size: 64x64, 12+12 samples, batch 1, 32^3 x 32 volume, TALLSIREN_FG -- the reference's own
-    CPU-runnable case, rendered by the CUDA path (fp32 and bf16 modes) and by the oracle on the same draws."""
-    B, img, S, V = 1, 64, 12, 32
+def _full_size_case(B, img, S, V, seed, dense, n_items=None):
+    """Seeded inputs of a BASELINE config at full size; ``dense``: TALLSIREN_FG with the dense head (oracle.DENSE_HEAD_GAINS)."""
     siren_type = "TALLSIREN_FG"
-    state = oracle.init_generator_state(siren_type, seed=21)
-    g = torch.Generator().manual_seed(22)
+    state = oracle.init_generator_state(siren_type, seed=seed)
+    if dense:
+        state = oracle.dense_head_state(state, *oracle.DENSE_HEAD_GAINS[siren_type])
+    g = torch.Generator().manual_seed(seed + 1)
     z = (torch.randn((B, 32, V, V, V), generator=g) * 0.3, torch.randn((B, 256), generator=g) * 0.05 + 0.19)
-    cam = oracle.look_at_cam2world(oracle.random_camera_origins(B, 0.7, 1.5, "y", np.random.RandomState(23)), "y")
+    cam = oracle.look_at_cam2world(oracle.random_camera_origins(B, 0.7, 1.5, "y", np.random.RandomState(seed + 2)), "y")
     draws = oracle.draw_randoms(B, img, S, True, g)
     meta = dict(img_size=img, fov=FOV, ray_start=0.25, ray_end=1.95, num_steps=S, hierarchical_sample=True,
                 clamp_mode="relu", nerf_noise=0.0, white_back=True)
+    return siren_type, state, z, cam, draws, meta
+
+
+def _slice_item(z, cam, draws, i, R):
+    return ((z[0][i:i + 1], z[1][i:i + 1]), cam[i:i + 1],
+            {"u_jitter": draws["u_jitter"][i:i + 1], "noise_coarse": draws["noise_coarse"][i:i + 1],
+             "u_resample": draws["u_resample"][i * R:(i + 1) * R], "noise_final": draws["noise_final"][i:i + 1]})
+
+
+def _check_indexing_bit_exact(out, draws_i, S, item):
+    """sample_pdf indices / samples and the merge order, bit-exact GIVEN the kernel's own upstream values (its coarse weights
+    differ from the oracle's in the last ulps; near-ties may then legitimately resolve differently)."""
+    B1 = 1
+    t_c = out["t_coarse"][item:item + 1].cpu()
+    w_c = out["weights_coarse"][item:item + 1].cpu()
+    t_f = out["t_fine"][item:item + 1].cpu().reshape(B1, -1, S)
+    o_s, o_i, _, _ = oracle.coarse_to_fine_t(w_c.unsqueeze(-1), t_c.unsqueeze(-1), draws_i["u_resample"], S)
+    R = t_c.shape[1]
+    assert torch.equal(out["resample_inds"].cpu().reshape(-1, R, S)[item].reshape(-1, S), o_i), "sample_pdf bin indices"
+    assert torch.equal(t_f.reshape(-1, S), o_s), "sample_pdf samples"
+    order = torch.sort(torch.cat([t_f, t_c], dim=-1), dim=-1, stable=True).indices
+    assert torch.equal(out["merge_order"][item:item + 1].cpu().long(), order), "merge order differs from the stable sort"
+
+
+@pytest.mark.parametrize("dense", [False, True])
+def test_config1_full_size_vs_oracle(dense):
+    """BASELINE configs[0] at full size: 64x64, 12+12 samples, batch 1, 32^3 x 32 volume, TALLSIREN_FG -- the reference's own
+    CPU-runnable case, rendered by the CUDA path (fp32 and bf16 modes) and by the oracle on the same draws.  ``dense``: the
+    same network with density (whole-image PSNR asserted in every mode); random init: the MLP bar in every mode, the image
+    bars in fp32 mode (its relu-mode pixels are all far-plane decisions, see oracle.far_plane_sigma)."""
+    B, img, S, V = 1, 64, 12, 32
+    siren_type, state, z, cam, draws, meta = _full_size_case(B, img, S, V, 21, dense)
     ref = oracle.render(state, siren_type, z, cam, draws, **meta)
-    decided = (oracle.far_plane_sigma(ref, 0.0).abs() >= 2e-2).reshape(B, 1, img, img).expand(B, 3, img, img)
     d = {k: dev(v) for k, v in draws.items()}
-    for precision, min_psnr in (("fp32", 60.0), ("bf16", 40.0)):
+    sigma_gain = oracle.DENSE_HEAD_GAINS[siren_type][0] if dense else 1.0
+    for precision, min_psnr in (("fp32", 60.0), ("bf16", 40.0), ("fp16", 40.0)):
         gen = _generator(siren_type, state, precision)
         with torch.no_grad():
             out = gen._render(dev(z[0]), dev(z[1]), dev(cam), img, FOV, 0.25, 1.95, S, True, dict(meta, draws=d), taps=True)
         pixels = out["pixels"].cpu()
+        assert torch.equal(out["t_coarse"].cpu(), ref["t_coarse"].squeeze(-1))
+        _check_indexing_bit_exact(out, draws, S, 0)
+        d_c = (out["rgb_sigma_coarse"].cpu() - ref["rgb_sigma_coarse"]).abs()
+        tol = 5e-4 if precision == "fp32" else 1e-2
+        assert d_c[..., :3].max().item() < tol and d_c[..., 3].max().item() < tol * sigma_gain
+        psnr = oracle.psnr(pixels, ref["pixels"])
+        print(f"config 1 {'dense' if dense else 'random-init'} {precision}: PSNR {psnr:.1f} dB whole image, coarse rgb err {d_c[..., :3].max().item():.2e}, "
+              f"sigma err {d_c[..., 3].max().item():.2e}")
         if precision == "fp32":
-            assert torch.equal(out["t_coarse"].cpu(), ref["t_coarse"].squeeze(-1))
-            # merge order: bit-exact against a stable sort of the kernel's OWN distances (its t_fine differ from the oracle's by
-            # ulps of the coarse weights, so near-ties may legitimately swap relative to the oracle's order)
-            all_t = torch.cat([out["t_fine"].cpu().reshape(B, -1, S), out["t_coarse"].cpu()], dim=-1)
-            order = torch.sort(all_t, dim=-1, stable=True).indices
-            assert torch.equal(out["merge_order"].cpu().long(), order), "merge order differs from the stable sort at full size"
-            assert (out["merge_order"].cpu().long() != ref["merge_order"].squeeze(-1)).float().mean().item() < 1e-3
-            # resampling indices: bit-exact when fed the kernel's own coarse weights (the oracle's differ in the last ulps)
-            o_s, o_i, _, _ = oracle.coarse_to_fine_t(out["weights_coarse"].cpu().unsqueeze(-1), out["t_coarse"].cpu().unsqueeze(-1),
-                                                     draws["u_resample"], S)
-            assert torch.equal(out["resample_inds"].cpu(), o_i) and torch.equal(out["t_fine"].cpu().reshape(-1, S), o_s)
-            assert oracle.psnr(pixels, ref["pixels"]) >= min_psnr
-            assert torch.allclose(out["depth"].cpu(), ref["depth"], atol=2e-3)
-        else:
-            assert oracle.psnr(pixels[decided], ref["pixels"][decided]) >= min_psnr
-        print(f"config 1 {precision}: PSNR {oracle.psnr(pixels, ref['pixels']):.1f} dB whole image, decided {decided.float().mean().item():.1%}")
+            assert (out["merge_order"].cpu().long() != ref["merge_order"].squeeze(-1)).float().mean().item() < 2e-3
+            assert psnr >= min_psnr
+            assert torch.allclose(out["depth"].cpu(), ref["depth"], atol=5e-3)
+        elif dense:
+            assert psnr >= min_psnr
 
 
-def test_config2_full_size_properties():
-    """BASELINE configs[1] at full size (batch 8, 128x128, 24+24, 64^3): finite, in range, deterministic, and every image of
-    the batch equals the same image rendered alone (rays and images are independent: the sharding argument of DESIGN.md 6)."""
+def test_config2_full_size_vs_oracle():
+    """BASELINE configs[1] -- the headline workload -- at FULL size against the oracle: batch 8, 128x128, 24+24 samples, 64^3
+    volume, TALLSIREN_FG with density.  The CUDA path renders the whole batch (bf16 tensor-core mode, the benchmarked one, and
+    fp32 mode); the oracle renders images 2 and 6 of the 8 on the same draws (~2 s each).  Asserted per image: coarse MLP
+    <= 1e-2 (sigma: x gain), sample_pdf indices / samples and merge order bit-exact given the kernel's own upstream values,
+    PSNR >= 40 dB over the whole image (fp32 mode: >= 60 dB), depth; and the batch render equals the single-image render
+    bit for bit (rays and images are independent: the sharding argument of DESIGN.md 6)."""
     B, img, S, V = 8, 128, 24, 64
-    siren_type = "TALLSIREN_FG"
-    state = oracle.init_generator_state(siren_type, seed=0)
-    gen = _generator(siren_type, state, "bf16")
-    g = torch.Generator(device="cuda").manual_seed(0)
-    vol = torch.randn((B, 32, V, V, V), generator=g, device="cuda") * 0.3
-    glob = torch.randn((B, 256), generator=g, device="cuda") * 0.05 + 0.19
-    cam = dev(oracle.look_at_cam2world(oracle.random_camera_origins(B, 0.7, 1.5, "y", np.random.RandomState(1)), "y"))
     R = img * img
-    d = {"u_jitter": torch.rand((B, R, S, 1), generator=g, device="cuda"), "noise_coarse": torch.zeros((B, R, S, 1), device="cuda"),
-         "u_resample": torch.rand((B * R, S), generator=g, device="cuda"), "noise_final": torch.zeros((B, R, 2 * S, 1), device="cuda")}
-    meta = dict(img_size=img, fov=FOV, ray_start=0.25, ray_end=1.95, num_steps=S, hierarchical_sample=True,
-                clamp_mode="relu", nerf_noise=0.0, white_back=True)
-    with torch.no_grad():
-        a, da = gen((vol, glob), cam, draws=d, **meta)
-        b, db = gen((vol, glob), cam, draws=d, **meta)
-    assert torch.equal(a, b) and torch.equal(da, db)
-    assert torch.isfinite(a).all() and torch.isfinite(da).all()
-    assert float(a.min()) >= -1 - 1e-5 and float(a.max()) <= 1 + 1e-5
-    assert float(da.min()) >= 0 and float(da.max()) <= 1.95 + 0.5 * 1.7 / (S - 1) + 1e-4      # last sample jitters by up to half a spacing
-    for i in (0, 5):
-        di = {"u_jitter": d["u_jitter"][i:i + 1], "noise_coarse": d["noise_coarse"][i:i + 1],
-              "u_resample": d["u_resample"][i * R:(i + 1) * R], "noise_final": d["noise_final"][i:i + 1]}
+    siren_type, state, z, cam, draws, meta = _full_size_case(B, img, S, V, 40, True)
+    sigma_gain = oracle.DENSE_HEAD_GAINS[siren_type][0]
+    d = {k: dev(v) for k, v in draws.items()}
+    zc, camc = (dev(z[0]), dev(z[1])), dev(cam)
+    refs = {}
+    for i in (2, 6):
+        zi, ci, di = _slice_item(z, cam, draws, i, R)
+        refs[i] = (oracle.render(state, siren_type, zi, ci, di, **meta), di)
+    for precision, min_psnr in (("bf16", 40.0), ("fp32", 60.0)):
+        gen = _generator(siren_type, state, precision)
         with torch.no_grad():
-            s, ds = gen((vol[i:i + 1], glob[i:i + 1]), cam[i:i + 1], draws=di, **meta)
-        assert torch.equal(s[0], a[i]) and torch.equal(ds[0], da[i])
+            out = gen._render(zc[0], zc[1], camc, img, FOV, 0.25, 1.95, S, True, dict(meta, draws=d), taps=True)
+            a, da = gen(zc, camc, draws=d, **meta)
+        assert torch.equal(a, out["pixels"]) and torch.isfinite(a).all() and torch.isfinite(da).all()
+        assert float(a.min()) >= -1 - 1e-5 and float(a.max()) <= 1 + 1e-5
+        for i, (ref, di) in refs.items():
+            assert torch.equal(out["t_coarse"][i].cpu(), ref["t_coarse"][0].squeeze(-1))
+            _check_indexing_bit_exact(out, di, S, i)
+            d_c = (out["rgb_sigma_coarse"][i].cpu() - ref["rgb_sigma_coarse"][0]).abs()
+            tol = 5e-4 if precision == "fp32" else 1e-2
+            psnr = oracle.psnr(a[i].cpu(), ref["pixels"][0])
+            err_d = (da[i].cpu() - ref["depth"][0]).abs()
+            w_last = float(ref["weights_final"][..., -1, 0].mean())
+            print(f"config 2 image {i} {precision}: PSNR {psnr:.1f} dB whole image, coarse rgb err {d_c[..., :3].max().item():.2e}, sigma err "
+                  f"{d_c[..., 3].max().item():.2e} (gain {sigma_gain:g}), depth err max {err_d.max().item():.2e} mean {err_d.mean().item():.2e}, "
+                  f"reference far-plane weight mean {w_last:.4f}")
+            assert d_c[..., :3].max().item() < tol and d_c[..., 3].max().item() < tol * sigma_gain
+            assert psnr >= min_psnr
+            if precision == "fp32":
+                assert err_d.mean().item() < 1e-4
+            # the same image rendered alone: bit-identical
+            zi, ci, dii = _slice_item(zc, camc, d, i, R)
+            with torch.no_grad():
+                s1, ds1 = gen(zi, ci, draws=dii, **meta)
+            assert torch.equal(s1[0], a[i]) and torch.equal(ds1[0], da[i])
+
+
+def test_config4_frame_vs_oracle():
+    """BASELINE configs[3]: one frame of the video workload at full size -- 256x256, 48+48 samples, 64^3 volume -- through
+    staged_forward (chunked), against the oracle on the same draws (~15 s of CPU)."""
+    B, img, S, V = 1, 256, 48, 64
+    siren_type, state, z, cam, draws, meta = _full_size_case(B, img, S, V, 50, True)
+    ref = oracle.render(state, siren_type, z, cam, draws, **meta)
+    sigma_gain = oracle.DENSE_HEAD_GAINS[siren_type][0]
+    d = {k: dev(v) for k, v in draws.items()}
+    zc = (dev(z[0]), dev(z[1]))
+    gen = _generator(siren_type, state, "bf16")
+    with torch.no_grad():
+        out = gen._render(zc[0], zc[1], dev(cam), img, FOV, 0.25, 1.95, S, True, dict(meta, draws=d), taps=True)
+        px, dp = gen.staged_forward(zc, dev(cam), max_batch_size=1, draws=d, **meta)
+    assert torch.equal(px, out["pixels"]) and torch.equal(dp, out["depth"])
+    _check_indexing_bit_exact(out, draws, S, 0)
+    d_c = (out["rgb_sigma_coarse"].cpu() - ref["rgb_sigma_coarse"]).abs()
+    psnr = oracle.psnr(px.cpu(), ref["pixels"])
+    print(f"config 4 frame bf16: PSNR {psnr:.1f} dB whole image, coarse rgb err {d_c[..., :3].max().item():.2e}, sigma err {d_c[..., 3].max().item():.2e}, "
+          f"depth err mean {(dp.cpu() - ref['depth']).abs().mean().item():.2e}")
+    assert d_c[..., :3].max().item() < 1e-2 and d_c[..., 3].max().item() < 1e-2 * sigma_gain
+    assert psnr >= 40.0
 
 
 def test_film_parameters_kernel(ops):

@@ -105,13 +105,18 @@ def test_camera_helpers_match_oracle():
     assert torch.equal(vr.create_cam2world_matrix(o, "z"), oracle.look_at_cam2world(o, "z"))
 
 
-def test_grad_mode_fails_loudly_until_backward_exists():
-    from conditioned_nerf_gan_b200.generators import autograd
-    if getattr(autograd, "HAS_BACKWARD", False):
-        pytest.skip("backward kernels are built")
-    gen = ImplicitGenerator3d("DOUBLESIREN_FG", 256, 32, 4, 256)
-    with pytest.raises(NotImplementedError):
-        gen(make_z(), torch.eye(4).unsqueeze(0), **META)
+def test_fp16_only_classes_reject_bf16_operands():
+    """The frequency_init(12) classes are offered with fp16 operands only (bf16 misses the 1e-2 contract)."""
+    gen = ImplicitGenerator3d("SHORTSIREN_FG", 256, 32, 4, 256)
+    assert gen.siren.precision == "fp16"
+    with pytest.raises(ValueError):
+        gen.siren.precision = "bf16"
+    gen.siren.precision = "fp32"
+    with pytest.raises(ValueError):
+        gen.siren.precision = "fp64"
+    tall = ImplicitGenerator3d("TALLSIREN_FG", 256, 32, 4, 256)
+    assert tall.siren.precision == "bf16"
+    tall.siren.precision = "fp16"
 
 
 def test_alias_classes():

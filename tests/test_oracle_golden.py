@@ -4,11 +4,11 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import FORWARD_FIXTURES, fixture_inputs, load_golden
+from conftest import DENSE_FIXTURES, FORWARD_FIXTURES, fixture_inputs, load_golden
 from oracle import nerf_path as oracle
 
 
-@pytest.mark.parametrize("name", FORWARD_FIXTURES)
+@pytest.mark.parametrize("name", FORWARD_FIXTURES + DENSE_FIXTURES)
 def test_forward_matches_reference(name):
     state, siren_type, z, cam, draws, meta, taps = fixture_inputs(name)
     out = oracle.render(state, siren_type, z, cam, draws, **meta)
@@ -18,16 +18,23 @@ def test_forward_matches_reference(name):
         exact += ["weights_coarse"]
     for k in exact:
         assert torch.equal(out[k], taps[k].reshape(out[k].shape)), k
+    dense = name in DENSE_FIXTURES
     if meta["hierarchical_sample"]:
         # sum(weights) association order differs (see oracle docstring): 1 ulp on the cdf, which
         # (u - cdf_lo) / denom amplifies by up to bin_width / denom (denom >= 1e-5): almost every
-        # sample agrees to a few ulp, a rare one in a near-empty bin to ~1e-5.
+        # sample agrees to a few ulp, a rare one in a near-empty bin to ~1e-5.  The dense fixtures have truly empty bins
+        # (weight = the 2e-5 floor, denom ~ 1e-5 .. 1e-4): there the bound bin_width * ulp / denom reaches ~1e-3 for a
+        # handful of samples -- which carry no weight in the image (pixels agree to 1e-4 below).
         dt = (out["t_fine"] - taps["t_fine"]).abs()
-        assert float(dt.max()) < 1e-4 and float((dt > 2e-6).float().mean()) < 2e-3
-        assert torch.allclose(out["points_fine"], taps["points_fine"], rtol=0, atol=1e-4)
-        assert torch.allclose(out["rgb_sigma_fine"], taps["rgb_sigma_fine"], rtol=0, atol=2e-4)
+        assert float(dt.max()) < (2e-3 if dense else 1e-4) and float((dt > 2e-6).float().mean()) < (1e-2 if dense else 2e-3)
+        assert torch.allclose(out["points_fine"], taps["points_fine"], rtol=0, atol=2e-3 if dense else 1e-4)
+        d_fine = (out["rgb_sigma_fine"] - taps["rgb_sigma_fine"]).abs()
+        if dense:
+            assert float((d_fine > 1e-3).float().mean()) < 0.1      # sigma carries a gain of 300: the moved samples move it
+        else:
+            assert float(d_fine.max()) < 2e-4
     for k, tol in (("rgb", 1e-5), ("dist", 1e-5), ("pixels", 2e-5), ("depth", 1e-5)):
-        assert torch.allclose(out[k], taps[k].reshape(out[k].shape), rtol=0, atol=tol), k
+        assert torch.allclose(out[k], taps[k].reshape(out[k].shape), rtol=0, atol=1e-4 if dense else tol), k
     assert out["pixels"].shape == (cam.shape[0], 3, meta["img_size"], meta["img_size"])
     assert out["depth"].shape == (cam.shape[0], meta["img_size"], meta["img_size"])
 
