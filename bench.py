@@ -324,7 +324,9 @@ def run_gpu(args):
     pk = peaks()
     flops_per_launch = mlp_flops_per_point(L) * B * R * S            # one pass (coarse or fine) per launch
     achieved = flops_per_launch / (mlp_ms * 1e-3) / 1e12
-    peak = pk["tflops_sustained"] if args.precision != "fp32" else None
+    # the kernel is CUDA-event timed inside a sub-second region at ~1.9 GHz: the matching denominator is the BURST bf16 peak
+    # (the sustained figure was measured at ~1.3 GHz over seconds; the fraction against it is kept as frac_vs_sustained)
+    peak = pk["tflops_burst"] if args.precision != "fp32" else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "k2_dram_traffic.json")
     if args.precision != "fp32" and os.path.exists(tpath):
@@ -333,11 +335,22 @@ def run_gpu(args):
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": (achieved / peak) if peak else None, "traffic": traffic,
                 "algorithmic_bytes_per_launch": B * R * S * (WORKLOAD["channels"] * 4 + 16) + B * ((2 + 4 * (L - 1)) * 32768 + 8192),
-                "peak_source": f"{pk['source']} bf16 sustained (kernel timed inside a long step)",
+                "peak_source": f"{pk['source']} bf16 burst (cuBLAS 8192^3 best-of-10; the kernel is event-timed inside a sub-second region)",
+                "frac_vs_sustained": (achieved / pk["tflops_sustained"]) if peak else None,
+                "traffic_source": "profiles/k2_dram_traffic.json (committed ncu --set full capture of this kernel at this shape, not measured live)" if traffic else None,
                 "flops_per_launch": flops_per_launch, "ms_per_launch": mlp_ms,
                 "share_of_step": float(np.sum(per_kernel["cng_film_siren_fwd"]) / args.steps / sum(step_kernel_ms.values())),
                 "step_ms_by_entry_point": step_kernel_ms}
 
+    # ---- second half of BASELINE's metric: train images/s of config 3 at this N (global batch 32, strong scaling)
+    train = None
+    if not args.no_train:
+        train = measure_train(args, rank, world, local, dev, barrier, max_over_ranks, args.train_steps, 3)
+    c5 = eager = None
+    if rank == 0 and not args.no_extras:
+        c5 = measure_c5()
+        eager = measure_gpu_eager(args)
+    barrier()
     if rank == 0:
         cores = os.cpu_count() or 1
         cpu = None
@@ -359,6 +372,7 @@ def run_gpu(args):
                     "ms_per_step": ms_e2e / args.steps, "api": "streaming.render_host_batches (H2D / kernels / D2H on three streams, double-buffered)",
                     "unpipelined_value": rays / (ms_e2e_sync * 1e-3), "passes_ms_per_step": [t / args.steps for t in e2e_passes]},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "train": train, "gpu_eager_baseline": eager, "c5": c5,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -408,26 +422,28 @@ def _timed_steps(fn, steps, warmup, barrier, max_over_ranks):
     return max_over_ranks(start.elapsed_time(end)), ops.launch_count - n0
 
 
-def run_train(args):
+def measure_train(args, rank, world, local, dev, barrier, max_over_ranks, steps, warmup):
     """Full GAN train step of BASELINE config 3: 3D U-Net encoder + FiLM-SIREN generator (CUDA rendering path, forward and
-    backward) + progressive discriminator with R1, following utils.py:621-842 (conditioned_nerf_gan_b200/training.py)."""
+    backward) + progressive discriminator with R1, following utils.py:621-842 (conditioned_nerf_gan_b200/training.py).
+    Global batch 32 split over the ranks (strong scaling); returns the metrics of the timed steps (max over ranks)."""
     import torch.distributed as dist
     from conditioned_nerf_gan_b200.discriminators import ProgressiveDiscriminator
     from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d
     from conditioned_nerf_gan_b200.generators.unet3d import UNet3D
     from conditioned_nerf_gan_b200.generators.volumetric_rendering import create_cam2world_matrix, sample_camera_positions
     from conditioned_nerf_gan_b200.training import GanTrainStep
-    rank, world, local, dev, barrier, max_over_ranks = _setup_ranks(args)
     GLOBAL_B, img, S, V = 32, 128, 48, 64
     if GLOBAL_B % world:
         raise SystemExit("global batch 32 must divide by the number of GPUs")
     b = GLOBAL_B // world
+    rng = torch.random.get_rng_state()
     torch.manual_seed(0)                                            # same random-init weights on every rank (reference init distributions)
     np.random.seed(rank)
     gen = ImplicitGenerator3d(args.siren, 256, 32, 4, 256)
     gen.siren.precision = args.precision
     enc = UNet3D(in_channels=4, out_channels=32, f_maps=32, num_levels=4, is_segmentation=False, final_sigmoid=False, return_global=True)   # configs/thousand/special.py:53-62
     disc = ProgressiveDiscriminator()
+    torch.random.set_rng_state(rng)
     gen, enc, disc = gen.to(dev), enc.to(dev), disc.to(dev)
     md = dict(render_meta(img, S), nerf_noise=1.0, batch_split=1, r1_lambda=10, grad_clip=1, betas=(0.0, 0.9), weight_decay=0,
               gen_lr=10e-6, disc_lr=10e-5, enc_lr=2e-5, photo_loss=True, depth_loss=False, depth_loss_weight=1, enable_discriminator=True,
@@ -446,28 +462,139 @@ def run_train(args):
         results.append(float(losses["d_loss"].item()) + float(losses["g_loss"].item()))     # device->host read of the step's result
 
     sampler = ClockSampler(local) if rank == 0 else None
-    ms, launches = _timed_steps(step, args.steps, args.warmup, barrier, max_over_ranks)
+    t_host = time.perf_counter()
+    ms, launches = _timed_steps(step, steps, warmup, barrier, max_over_ranks)
     clocks = sampler.stop() if sampler else None
+    # the gradient all-reduce alone: one flat buffer of the step's gradient bytes (G + E + D parameters, fp32) over NCCL,
+    # timed with CUDA events (inside the step DDP overlaps it with the backward kernels)
+    n_param = sum(p.numel() for m in (gen, enc, disc) for p in m.parameters())
+    allreduce_ms = 0.0
+    if world > 1:
+        flat = torch.zeros((n_param,), dtype=torch.float32, device=dev)
+        for _ in range(2):
+            dist.all_reduce(flat)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(5):
+            dist.all_reduce(flat)
+        s1.record()
+        barrier()
+        allreduce_ms = max_over_ranks(s0.elapsed_time(s1)) / 5
+        del flat
+    L = SIREN_LAYERS[args.siren]
+    pts = GLOBAL_B * img * img * 2 * S
+    out = {"images_per_s": GLOBAL_B * steps / (ms * 1e-3), "ms_per_step": ms / steps, "global_batch": GLOBAL_B, "batch_per_gpu": b,
+           "steps": steps, "warmup": warmup, "launches": launches // max(steps, 1), "allreduce_ms": allreduce_ms,
+           "allreduce_bytes": 4 * n_param, "scaling": "strong", "final_loss": results[-1], "clocks": clocks,
+           "h2d_bytes_per_step": int((voxel_h.numel() + img_h.numel() + cam_h.numel()) * 4), "d2h_bytes_per_step": 8,
+           "mlp_flops_per_step": 3 * 2 * mlp_flops_per_point(L) * pts,
+           "workload": "full GAN train step (3D U-Net encoder + FiLM-SIREN generator + progressive discriminator, D step with R1 then G/E step), "
+                       "128x128, 48+48 samples/ray, global batch 32 (BASELINE configs[2]); autocast fp16 + GradScaler, Adam x3; "
+                       "host voxels / images / cameras copied in and the losses read back every step"}
+    del trainer, gen, enc, disc
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_train(args):
+    import torch.distributed as dist
+    rank, world, local, dev, barrier, max_over_ranks = _setup_ranks(args)
+    t = measure_train(args, rank, world, local, dev, barrier, max_over_ranks, args.steps, args.warmup)
     if rank == 0:
-        L = SIREN_LAYERS[args.siren]
-        pts = GLOBAL_B * img * img * 2 * S
-        val = GLOBAL_B * args.steps / (ms * 1e-3)
-        line = {"metric": "train_images_per_sec_128x128_48+48spp_global_batch32", "value": val,
-                "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        line = {"metric": "train_images_per_sec_128x128_48+48spp_global_batch32", "value": t["images_per_s"],
+                "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t["ms_per_step"],
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": "full GAN train step (3D U-Net encoder + FiLM-SIREN generator + progressive discriminator, D step with R1 then G/E step) "
-                                       "128x128, 48+48spp, global batch 32 (BASELINE configs[2])",
-                           "siren_type": args.siren, "batch_per_gpu": b, "batch_split": 1, "amp": "autocast fp16 + GradScaler (as utils.py:643,711)",
+                "config": {"workload": t["workload"], "siren_type": args.siren, "batch_per_gpu": t["batch_per_gpu"], "batch_split": 1,
+                           "amp": "autocast fp16 + GradScaler (as utils.py:643,711)",
                            "optimizers": "Adam x3", "grad_allreduce": "DDP/NCCL, once per optimizer step" if world > 1 else "none",
                            "encoder": "cuDNN (library), channels_last_3d, emits the NDHWC volume zero-copy", "discriminator": "cuDNN (library)",
                            "generator": "hand-written CUDA path: forward x2 (no-grad for the D step, with grad for the G step) + backward"},
-                "e2e": {"value": val, "unit": "images/s",
-                        "h2d_bytes_per_step": int((voxel_h.numel() + img_h.numel() + cam_h.numel()) * 4), "d2h_bytes_per_step": 8},
-                "gpu_launches": launches, "clocks": clocks, "final_loss": results[-1],
-                "mlp_flops_per_step": 3 * 2 * mlp_flops_per_point(L) * pts}
+                "e2e": {"value": t["images_per_s"], "unit": "images/s", "h2d_bytes_per_step": t["h2d_bytes_per_step"], "d2h_bytes_per_step": 8},
+                "gpu_launches": t["launches"] * args.steps, "clocks": t["clocks"], "final_loss": t["final_loss"],
+                "allreduce_ms": t["allreduce_ms"], "mlp_flops_per_step": t["mlp_flops_per_step"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_c5(rays_m: int = 2):
+    """BASELINE configs[4] (compositing + sample_pdf micro-benchmark): achieved HBM GB/s of the compositing, resampling and
+    merge+composite kernels at 64 / 128 / 256 samples per ray on ``rays_m`` Mi rays, algorithmic bytes per ray from
+    SURVEY.md 8(d), against the measured copy bandwidth.  Working sets (0.3 - 5 GB) exceed the 126 MB L2."""
+    from conditioned_nerf_gan_b200 import ops
+    peak = peaks()["hbm_gbs"]
+    dev = "cuda"
+
+    def timeit(fn, reps=5):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / reps
+
+    rows = []
+    n = rays_m << 20
+    for S in (64, 128, 256):
+        g = torch.Generator(device=dev).manual_seed(0)
+        rs = torch.randn((n, S, 4), generator=g, device=dev)
+        rs[..., :3].sigmoid_()
+        t = torch.rand((n, S), generator=g, device=dev).mul_(1.7).add_(0.25).sort(dim=1).values
+        w = torch.rand((n, S), generator=g, device=dev)
+        u = torch.rand((n, S), generator=g, device=dev)
+        rs2 = torch.randn((n, S, 4), generator=g, device=dev)
+        t2 = torch.rand((n, S), generator=g, device=dev).mul_(1.7).add_(0.25).sort(dim=1).values
+        rays = torch.nn.functional.normalize(torch.randn((1024, 3), generator=g, device=dev), dim=-1)
+        cases = [("composite", lambda: ops.composite_fwd(rs, t, None, 0.0, "relu", True, False), n * (S * 20 + 16 + 4 * S)),
+                 ("resample", lambda: ops.resample_from_coarse(t, w, u), n * 16 * S),
+                 ("merge", lambda: ops.merge_composite(rs2, rs, t2, t, None, rays, n // 1024, 32, 32, 0.0, "relu", True, False), n * (2 * S * 20 + 16))]
+        for name, fn, by in cases:
+            ms = timeit(fn)
+            rows.append({"kernel": name, "samples_per_ray": S if name != "merge" else f"{S}+{S}", "rays": n, "ms": ms, "gbs": by / ms / 1e6,
+                         "frac": by / ms / 1e6 / peak})
+        del rs, t, w, u, rs2, t2
+        torch.cuda.empty_cache()
+    return {"peak_gbs": peak, "unit": "GB/s", "rays": n, "rows": rows,
+            "bytes_per_ray": "composite S*20+16+4S (weights emitted), resample 16*S, merge 2S*20+16 (SURVEY.md 8d)"}
+
+
+def measure_gpu_eager(args, steps=5, warmup=3):
+    """The same-box GPU comparator BASELINE.md 5.3 asks for: the reference's eager PyTorch path on THIS B200 -- the torch
+    port of it (oracle/nerf_path.py, every statement citing the reference line it restates; the reference itself cannot travel
+    to the GPU box) on CUDA tensors, same workload, weights and draws -- in fp32 and under the trainer's autocast (fp16),
+    CUDA-event timed.  A baseline leg: nothing of it is on the product path."""
+    from oracle import nerf_path as oracle
+    B, img, S, V = WORKLOAD["batch"], WORKLOAD["img_size"], WORKLOAD["num_steps"], WORKLOAD["volume"]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    state = {k: v.to(dev) for k, v in oracle.init_generator_state(args.siren, seed=0).items()}
+    vol, glob, cam = (t.to(dev) for t in synthetic_inputs(B, V, 0))
+    meta = render_meta(img, S)
+    g = torch.Generator().manual_seed(1)
+    draws = {k: v.to(dev) for k, v in oracle.draw_randoms(B, img, S, True, g).items()}
+    out = {"kind": "port", "what": "oracle/nerf_path.py (torch restatement of generators/generators.py:33-187) run eagerly on cuda, batch 8, same workload",
+           "unit": UNIT, "steps": steps, "warmup": warmup}
+    for name, amp in (("fp32", False), ("amp_fp16", True)):
+        def fn():
+            with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
+                return oracle.render(state, args.siren, (vol, glob), cam, draws, taps=False, **meta)
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / steps
+        out[name] = {"value": B * img * img / (ms * 1e-3), "ms_per_step": ms}
+        torch.cuda.empty_cache()
+    return out
 
 
 def run_train_generator(args):
@@ -583,6 +710,9 @@ def main():
     ap.add_argument("--precision", default=None, choices=["bf16", "fp16", "fp32"],
                     help="default: bf16 operands; fp16 for the classes offered with fp16 operands only (SHORTSIREN_FG)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the config-3 train-step leg of the default line")
+    ap.add_argument("--train-steps", type=int, default=4)
+    ap.add_argument("--no-extras", action="store_true", help="skip the c5 micro-benchmark table and the GPU-eager comparator")
     ap.add_argument("--workload", default="render", choices=["render", "train", "train_generator", "video"])
     args = ap.parse_args()
     if args.precision is None:

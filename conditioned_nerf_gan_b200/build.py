@@ -15,12 +15,17 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libcng_b200.so")
 STAMP = os.path.join(PKG, "csrc", ".build_stamp")
-SOURCES = ["cng_api.cu", "raymarch_gather.cu", "film_siren_simt.cu", "film_siren_tc.cu", "film_siren_tc2.cu", "film_siren_tc3.cu", "composite.cu", "sample_pdf.cu", "backward.cu", "film_siren_bwd.cu", "render.cu"]
+SOURCES = ["cng_api.cu", "raymarch_gather.cu", "film_siren_simt.cu", "film_siren_tc.cu", "composite.cu", "sample_pdf.cu", "backward.cu", "film_siren_bwd.cu", "render.cu"]
+# CNG_BUILD_EXPERIMENTAL=1 adds the two measured-slower K2 organisations kept for A/B work: CTA pairs
+# (cta_group::2) and the layer-pipelined single-tile kernel; selected at run time with CNG_TC_CG=2 / CNG_TC_V=3
+EXPERIMENTAL = os.environ.get("CNG_BUILD_EXPERIMENTAL", "0") == "1"
+if EXPERIMENTAL:
+    SOURCES += ["film_siren_tc2.cu", "film_siren_tc3.cu"]
 # CNG_TC_EPI_WARPS (4 or 8): epilogue warps per tile slot of the one-CTA-per-SM tcgen05 kernel (film_siren_tc.cu)
 EPI_WARPS = os.environ.get("CNG_TC_EPI_WARPS", "8")
 EPI_PIPELINE = os.environ.get("CNG_TC_EPI_PIPELINE", "1")    # 1: double-buffer the epilogue's TMEM loads
 NVCC_FLAGS = [
-    f"-DCNG_TC_EPI_WARPS={EPI_WARPS}", f"-DCNG_TC_EPI_PIPELINE={EPI_PIPELINE}",
+    f"-DCNG_TC_EPI_WARPS={EPI_WARPS}", f"-DCNG_TC_EPI_PIPELINE={EPI_PIPELINE}", *(["-DCNG_WITH_EXPERIMENTAL_K2"] if EXPERIMENTAL else []),
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
 ]

@@ -22,9 +22,9 @@
 //   warp  16    MMA issuer (one elected lane) + TMEM allocator
 //   warp  17    weight producer: cp.async.bulk (TMA unit, SASS UBLKCP) global -> smem ring,
 //               completion on mbarriers (complete_tx)
-//   The FiLM shift is not added in the epilogue: after an epilogue warp has read a block of
-//   accumulator columns it writes the NEXT layer's shift into them (tcgen05.st) and every MMA
-//   accumulates on top, so the epilogue per element is FMUL(1/2pi) + MUFU.SIN + half a pack.
+//   The FiLM shift row of the layer in flight (1 KB per tile slot) lives in shared memory and is added to the
+//   accumulator in registers (LDS.128, warp-broadcast), so the epilogue per element is FADD + FMUL(1/2pi) +
+//   MUFU.SIN + half a pack; the next row is published between two named barriers off the critical chain.
 //   Two 128-point tiles are in flight per CTA ("ping-pong"): while the tensor pipe runs layer l
 //   of one tile, the epilogue warps of the other tile run sin() on their accumulator and write
 //   the next layer's bf16 A operand back into shared memory (128B-swizzled, K-major), so MUFU and
@@ -69,10 +69,14 @@ constexpr uint32_t kSmemBar = kSmemW + kRing * kChunkBytes;          // 229376
 constexpr uint32_t kSmemShift = kSmemBar + 128;                      // FiLM shift row of the layer each slot is working on: [2][256] fp32
 constexpr uint32_t kSmemTotal = kSmemShift + 2 * kHID * 4;           // 231552 <= 232448
 
+// The two measured-slower alternative organisations (film_siren_tc2.cu: CTA pairs / cta_group::2; film_siren_tc3.cu: one tile per
+// CTA, layer-pipelined) are compiled only with CNG_BUILD_EXPERIMENTAL=1 (build.py defines CNG_WITH_EXPERIMENTAL_K2).
+#ifdef CNG_WITH_EXPERIMENTAL_K2
 int film_siren_tc2_launch(TcParams p, cudaStream_t stream);   // film_siren_tc2.cu
 int film_siren_tc3_launch(TcParams p, int poly, cudaStream_t stream);   // film_siren_tc3.cu
+#endif
 // 1: the two-tile ping-pong kernel below, 8 epilogue warps bound to each tile slot; 2: the same with all 16 epilogue warps
-// shared between the slots; 3: the layer-pipelined kernel (film_siren_tc3.cu).  All three give bit-identical results.
+// shared between the slots; 3 (experimental builds only): the layer-pipelined kernel (film_siren_tc3.cu).  All give bit-identical results.
 constexpr int kDefaultKernelVersion = 1;   // measured (profiles/r1g_k2_versions.txt): 1 and 2 within 1-2 % on TALLSIREN_FG, 1 ahead for fewer layers, 3 behind by 10 %
 
 static long long* g_tc_trace = nullptr;   // debug hook, see cng_internal_set_tc_trace
@@ -705,7 +709,11 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
     const int v = e ? atoi(e) : kDefaultCtaGroup;
     return (v == 1 || v == 2) ? v : kDefaultCtaGroup;
   }();
+#ifdef CNG_WITH_EXPERIMENTAL_K2
   if (cta_group == 2 && sm_count() >= 2 && !half_operands && p.dump_x == nullptr) return film_siren_tc2_launch(p, stream);
+#else
+  (void)cta_group;
+#endif
   // share of the sines evaluated on the FMA pipe instead of the MUFU unit (tuning knob, default from measurement)
   static const int poly = [] {
     const char* e = getenv("CNG_TC_POLY");
@@ -719,7 +727,9 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
     return (v >= 1 && v <= 3) ? v : kDefaultKernelVersion;
   }();
   const int ver = (res_save_mask | res_add_mask) ? 1 : (g_tc_version ? g_tc_version : version);     // residual blocks: the slot-bound kernel
+#ifdef CNG_WITH_EXPERIMENTAL_K2
   if (ver == 3 && !train && L <= 8) return film_siren_tc3_launch(p, poly, stream);
+#endif
   const bool shared = (ver == 2) && !train && kEpiWarpsPerSlot == 8;
   using KernelFn = void (*)(TcParams);
   const int pl = (poly == 0 || poly == 4) ? poly : 8;          // shared mode and fp16 come in these three flavours
@@ -732,12 +742,15 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
                       : half_operands ? (pl == 0 ? film_siren_tc_kernel<0, true> : pl == 4 ? film_siren_tc_kernel<4, true> : film_siren_tc_kernel<8, true>)
                       : poly == 0 ? film_siren_tc_kernel<0, false> : poly == 2 ? film_siren_tc_kernel<2, false>
                       : poly == 3 ? film_siren_tc_kernel<3, false> : poly == 4 ? film_siren_tc_kernel<4, false> : film_siren_tc_kernel<8, false>;
-  static bool attr_set[8][9] = {};
+  // function attributes are per device: the opt-in is cached per device ordinal (a process may render on several GPUs)
+  static bool attr_set[64][8][9] = {};
   const int variant = res ? 5 + (train ? 2 : half_operands ? 1 : 0) : train ? 2 : (half_operands ? 1 : 0) + (shared ? 3 : 0);
-  if (!attr_set[variant][poly]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = -1;
+  if (dev < 0 || !attr_set[dev][variant][poly]) {
     ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTotal));
     if (ce != cudaSuccess) return fail(static_cast<int>(ce), "film_siren_fwd(bf16): smem attribute: %s", cudaGetErrorString(ce));
-    attr_set[variant][poly] = true;
+    if (dev >= 0) attr_set[dev][variant][poly] = true;
   }
   const long long grid = min(static_cast<long long>(sm_count()), p.total_tiles);
   fn<<<static_cast<unsigned>(grid), kNumThreads, kSmemTotal, stream>>>(p);

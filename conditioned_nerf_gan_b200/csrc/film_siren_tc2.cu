@@ -344,11 +344,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) film
 int film_siren_tc2_launch(TcParams p, cudaStream_t stream) {
   p.tiles_per_item = (p.N + tc2::kSuperM - 1) / tc2::kSuperM;
   p.total_tiles = p.tiles_per_item * p.B;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return fail(CNG_ERR_NO_DEVICE, "film_siren_fwd(bf16, pairs): no current device");
+  if (!attr_set[dev]) {
     cudaError_t ce = cudaFuncSetAttribute(tc2::film_siren_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tc2::kSmemTotal));
     if (ce != cudaSuccess) return fail(static_cast<int>(ce), "film_siren_fwd(bf16, pairs): smem attribute: %s", cudaGetErrorString(ce));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const long long pairs = min(static_cast<long long>(sm_count() / 2), p.total_tiles);
   tc2::film_siren_tc2_kernel<<<static_cast<unsigned>(2 * pairs), tc2::kNumThreads, tc2::kSmemTotal, stream>>>(p);

@@ -149,11 +149,13 @@ def init_generator_state(
 # and the rendered image has texture.  The reference is run on these weights unchanged (tests/golden/make_golden.py).
 # FiLM classes only: the unmodulated ones (SHORTSIREN_F, *_dRes*) are constant in space to ~1e-5 at random init whatever the
 # head gain, so their image-level fixtures stay the near-empty ones (whole-image PSNR asserted in fp32 only).
-DENSE_HEAD_GAINS = {           # class -> (sigma gain, rgb gain, first-layer gain)
-    "TALLSIREN_FG": (300.0, 10.0, 1.0),
-    "SHORTSIREN_FG": (300.0, 3.0, 1.0),
-    "DOUBLESIREN_FG": (300.0, 3.0, 1.0),
-    "SingleSIREN_dg": (1000.0, 3.0, 1.0),
+# The sigma bias of +6 (TALLSIREN_FG) is a thin fog: no ray reaches the far plane with weight left (mean far-plane weight
+# < 1e-3), so the far-plane step function (far_plane_sigma below) cannot decide a pixel; ~20 % of the samples stay empty.
+DENSE_HEAD_GAINS = {           # class -> (sigma gain, rgb gain, first-layer gain, sigma bias)
+    "TALLSIREN_FG": (300.0, 10.0, 1.0, 6.0),
+    "SHORTSIREN_FG": (300.0, 3.0, 1.0, 0.0),
+    "DOUBLESIREN_FG": (300.0, 3.0, 1.0, 0.0),
+    "SingleSIREN_dg": (1000.0, 3.0, 1.0, 0.0),
 }
 
 
@@ -366,7 +368,7 @@ def siren_forward(state, siren_type, pts_world, z, img_size, num_steps):
     else:
         volume = z                                   # siren.py:867: forward(points, feature_volume, ...); sin(1 * x + 0) == sin(x)
         n = spec["layers"] * ws[0].shape[0]
-        freq, phase = torch.ones((volume.shape[0], n)), torch.zeros((volume.shape[0], n))
+        freq, phase = torch.ones((volume.shape[0], n), device=volume.device), torch.zeros((volume.shape[0], n), device=volume.device)
     feat = trilinear_lookup(volume, pts_world, img_size, num_steps)
     return film_siren_mlp(feat, ws, bs, freq, phase, state["siren.final_layer.weight"],
                           state["siren.final_layer.bias"], spec["sigmoid_rgb"], spec.get("res_save", 0), spec.get("res_add", 0))
@@ -503,7 +505,8 @@ def _render(state, siren_type, z, cam2worlds, draws, *, img_size, fov, ray_start
     R, S = img_size * img_size, num_steps
     out: Dict[str, torch.Tensor] = {}
     with torch.no_grad():
-        pts_cam, t, d_cam = camera_rays(B, S, img_size, fov, ray_start, ray_end)
+        # the reference builds its rays on the generator's device (generators.py:57-66); here: where the cameras live
+        pts_cam, t, d_cam = (x.to(cam2worlds.device) for x in camera_rays(B, S, img_size, fov, ray_start, ray_end))
         pts_cam, t = jitter_samples(pts_cam, t, d_cam, draws["u_jitter"])
         pts_w, d_w, o_w = camera_to_world(pts_cam, d_cam, cam2worlds)
     coarse = siren_forward(state, siren_type, pts_w.reshape(B, R * S, 3), z, img_size, S).reshape(B, R, S, 4)
