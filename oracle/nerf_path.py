@@ -223,11 +223,11 @@ def camera_to_world(pts_cam, d_cam, cam2world):
     cam2world applied to (0,0,0,1).  Returns pts_world[B,R,S,3], d_world[B,R,3], o_world[B,R,3].
     """
     B, R, S, _ = pts_cam.shape
-    homo = torch.ones((B, R, S, 4))
+    homo = torch.ones((B, R, S, 4), device=pts_cam.device)
     homo[..., :3] = pts_cam
     pts_w = torch.bmm(cam2world, homo.reshape(B, -1, 4).permute(0, 2, 1)).permute(0, 2, 1).reshape(B, R, S, 4)
     d_w = torch.bmm(cam2world[..., :3, :3], d_cam.reshape(B, -1, 3).permute(0, 2, 1)).permute(0, 2, 1).reshape(B, R, 3)
-    o_h = torch.zeros((B, 4, R))
+    o_h = torch.zeros((B, 4, R), device=pts_cam.device)
     o_h[:, 3, :] = 1
     o_w = torch.bmm(cam2world, o_h).permute(0, 2, 1).reshape(B, R, 4)[..., :3]
     return pts_w[..., :3], d_w, o_w
