@@ -45,18 +45,18 @@ SIGNATURES = {
                                         c_float, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "cng_scatter_points": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p]),
     "cng_volume_from_channels_last": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "cng_film_sin_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
-    "cng_film_sin_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cng_film_siren_fwd_train": (c_int, [c_void_p, c_int, c_longlong, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                         c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "cng_film_siren_fwd_train_res": (c_int, [c_void_p, c_int, c_longlong, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                             c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, ctypes.c_uint,
-                                             ctypes.c_uint, c_void_p, c_size_t, c_void_p]),
+                                         c_void_p, c_void_p, c_int, c_int, ctypes.c_uint, ctypes.c_uint, c_void_p, c_size_t, c_void_p, c_size_t,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cng_film_siren_wt_image_bytes": (c_size_t, [c_int]),
+    "cng_film_siren_wt_images": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "cng_film_siren_dgrad": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     ctypes.c_uint, ctypes.c_uint, c_void_p, c_size_t, c_void_p]),
+    "cng_film_siren_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "cng_film_siren_bwd_workspace_bytes": (c_size_t, [c_longlong, c_int, c_int, c_int]),
-    "cng_film_siren_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                   c_void_p, c_void_p, c_void_p, c_void_p, c_int, ctypes.c_uint, ctypes.c_uint, c_void_p, c_size_t, c_void_p,
+    "cng_film_siren_bwd": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_int, ctypes.c_uint, ctypes.c_uint, c_void_p, c_size_t, c_void_p,
                                    c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "cng_film_grad_from_g": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p]),
     "cng_composite_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_int, c_int, c_int,
                                   c_void_p, c_void_p]),
     "cng_render_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int]),

@@ -8,9 +8,7 @@
 //                             (siren.py:555-571); sample positions carry no gradient (they are built
 //                             under torch.no_grad(), generators.py:57,111)
 //   cng_volume_from_channels_last   NDHWC -> NCDHW (gradient back into the encoder's layout)
-//   cng_film_sin_apply / cng_film_sin_grad   the elementwise halves of FiLMLayer forward / backward
-//                             (siren.py:153-157) around the GEMMs of the activation-recomputing
-//                             backward (see generators/autograd.py)
+//   (the MLP part -- dgrad chain and weight gradients on tcgen05 -- is film_siren_bwd_tc.cu)
 //
 // One warp per ray for the compositing backward: the forward quantities (merge order, alpha,
 // transmittance) are recomputed, the suffix sum over later samples is a reverse warp scan.
@@ -244,122 +242,9 @@ __global__ void __launch_bounds__(256) channels_first_kernel(const float* __rest
     if (lane < nv) d[static_cast<size_t>(c) * vox + v0 + lane] = tile[c * 33 + lane];
 }
 
-// ---- FiLM + sine, elementwise halves --------------------------------------------------------------
-// y = sin(freq * (z + b) + phase) as bf16 (the next GEMM's operand);  z [P, HID] fp32 GEMM output
-__global__ void __launch_bounds__(256) film_sin_apply_kernel(const float* __restrict__ z, const float* __restrict__ bias,
-                                                              const float* __restrict__ freq, const float* __restrict__ phase,
-                                                              long long P, int HID, __nv_bfloat16* __restrict__ y) {
-  const long long total4 = P * HID / 4;
-  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total4; e += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>((e * 4) % HID);
-    const float4 v = __ldg(reinterpret_cast<const float4*>(z) + e);
-    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c));
-    const float4 f = __ldg(reinterpret_cast<const float4*>(freq + c));
-    const float4 ph = __ldg(reinterpret_cast<const float4*>(phase + c));
-    __nv_bfloat162 lo = __floats2bfloat162_rn(sinf(fmaf(f.x, v.x + bb.x, ph.x)), sinf(fmaf(f.y, v.y + bb.y, ph.y)));
-    __nv_bfloat162 hi = __floats2bfloat162_rn(sinf(fmaf(f.z, v.z + bb.z, ph.z)), sinf(fmaf(f.w, v.w + bb.w, ph.w)));
-    uint2 o;
-    o.x = *reinterpret_cast<uint32_t*>(&lo);
-    o.y = *reinterpret_cast<uint32_t*>(&hi);
-    reinterpret_cast<uint2*>(y)[e] = o;
-  }
-}
-
-// du = dy * cos(u), u = freq*(z+b)+phase;  dz = du*freq (bf16 out);  dfreq += sum_p du*(z+b);  dphase += sum_p du
-// block = 256 threads = 64 column groups (4 columns each, HID == 256) x 4 row lanes; walks kGradRows rows with
-// 8-byte (dy, dz) and 16-byte (z) accesses; the column sums go through shared memory and one atomicAdd per column.
-constexpr int kGradRows = 128;
-__global__ void __launch_bounds__(256) film_sin_grad_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ z,
-                                                             const float* __restrict__ bias, const float* __restrict__ freq,
-                                                             const float* __restrict__ phase, long long P,
-                                                             __nv_bfloat16* __restrict__ dz, float* __restrict__ dfreq,
-                                                             float* __restrict__ dphase) {
-  __shared__ float red[2][4][256];
-  const int cgp = threadIdx.x & 63, ty = threadIdx.x >> 6;
-  const int c = cgp * 4;
-  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c));
-  const float4 f4 = __ldg(reinterpret_cast<const float4*>(freq + c));
-  const float4 p4 = __ldg(reinterpret_cast<const float4*>(phase + c));
-  const long long r0 = static_cast<long long>(blockIdx.x) * kGradRows;
-  const long long r1 = min(P, r0 + kGradRows);
-  float af[4] = {0.f, 0.f, 0.f, 0.f}, ap[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-  for (long long r = r0 + ty; r < r1; r += 4) {
-    const float4 zv = __ldg(reinterpret_cast<const float4*>(z + r * 256 + c));
-    const uint2 g2 = __ldg(reinterpret_cast<const uint2*>(dy + r * 256 + c));
-    const __nv_bfloat162 g01 = *reinterpret_cast<const __nv_bfloat162*>(&g2.x), g23 = *reinterpret_cast<const __nv_bfloat162*>(&g2.y);
-    const float g[4] = {__low2float(g01), __high2float(g01), __low2float(g23), __high2float(g23)};
-    const float zb[4] = {zv.x + b4.x, zv.y + b4.y, zv.z + b4.z, zv.w + b4.w};
-    const float fr[4] = {f4.x, f4.y, f4.z, f4.w}, ph[4] = {p4.x, p4.y, p4.z, p4.w};
-    float o[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float du = g[k] * cosf(fmaf(fr[k], zb[k], ph[k]));
-      af[k] = fmaf(du, zb[k], af[k]);
-      ap[k] += du;
-      o[k] = du * fr[k];
-    }
-    __nv_bfloat162 o01 = __floats2bfloat162_rn(o[0], o[1]), o23 = __floats2bfloat162_rn(o[2], o[3]);
-    uint2 w2;
-    w2.x = *reinterpret_cast<uint32_t*>(&o01);
-    w2.y = *reinterpret_cast<uint32_t*>(&o23);
-    *reinterpret_cast<uint2*>(dz + r * 256 + c) = w2;
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) { red[0][ty][c + k] = af[k]; red[1][ty][c + k] = ap[k]; }
-  __syncthreads();
-  const int col = threadIdx.x;
-  atomicAdd(dfreq + col, red[0][0][col] + red[0][1][col] + red[0][2][col] + red[0][3][col]);
-  atomicAdd(dphase + col, red[1][0][col] + red[1][1][col] + red[1][2][col] + red[1][3][col]);
-}
-
-// dz = dy * g (bf16 x fp16 -> bf16), colsum[c] += sum_p dz[p][c];  g = freq * cos(u) dumped by the training-mode forward.
-// Same thread layout as film_sin_grad_kernel.
-__global__ void __launch_bounds__(256) film_grad_from_g_kernel(const __nv_bfloat16* __restrict__ dy, const __half* __restrict__ g,
-                                                                long long P, __nv_bfloat16* __restrict__ dz, float* __restrict__ colsum) {
-  __shared__ float red[4][256];
-  const int cgp = threadIdx.x & 63, ty = threadIdx.x >> 6;
-  const int c = cgp * 4;
-  const long long r0 = static_cast<long long>(blockIdx.x) * kGradRows;
-  const long long r1 = min(P, r0 + kGradRows);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-  for (long long r = r0 + ty; r < r1; r += 4) {
-    const uint2 a2 = __ldg(reinterpret_cast<const uint2*>(dy + r * 256 + c));
-    const uint2 b2 = __ldg(reinterpret_cast<const uint2*>(g + r * 256 + c));
-    const __nv_bfloat162 a01 = *reinterpret_cast<const __nv_bfloat162*>(&a2.x), a23 = *reinterpret_cast<const __nv_bfloat162*>(&a2.y);
-    const float2 b01 = __half22float2(*reinterpret_cast<const __half2*>(&b2.x)), b23 = __half22float2(*reinterpret_cast<const __half2*>(&b2.y));
-    const float o0 = __low2float(a01) * b01.x, o1 = __high2float(a01) * b01.y;
-    const float o2 = __low2float(a23) * b23.x, o3 = __high2float(a23) * b23.y;
-    acc[0] += o0; acc[1] += o1; acc[2] += o2; acc[3] += o3;
-    __nv_bfloat162 o01 = __floats2bfloat162_rn(o0, o1), o23 = __floats2bfloat162_rn(o2, o3);
-    uint2 w2;
-    w2.x = *reinterpret_cast<uint32_t*>(&o01);
-    w2.y = *reinterpret_cast<uint32_t*>(&o23);
-    *reinterpret_cast<uint2*>(dz + r * 256 + c) = w2;
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) red[ty][c + k] = acc[k];
-  __syncthreads();
-  const int col = threadIdx.x;
-  atomicAdd(colsum + col, red[0][col] + red[1][col] + red[2][col] + red[3][col]);
-}
-
 }  // namespace cng
 
 extern "C" {
-
-int cng_film_grad_from_g(const void* dy_bf16, const void* g_f16, long long P, int HID, void* dz_bf16, float* colsum, cng_stream_t stream) {
-  CNG_REQUIRE(P >= 0, CNG_ERR_INVALID_ARGUMENT, "film_grad_from_g: P=%lld", P);
-  CNG_REQUIRE(HID == 256, CNG_ERR_UNSUPPORTED, "film_grad_from_g: HID=%d (only 256 is built)", HID);
-  if (P == 0) return CNG_OK;
-  CNG_REQUIRE(dy_bf16 && g_f16 && dz_bf16 && colsum, CNG_ERR_INVALID_ARGUMENT, "film_grad_from_g: NULL pointer");
-  CNG_REQUIRE((P + cng::kGradRows - 1) / cng::kGradRows < 0x7fffffffLL, CNG_ERR_UNSUPPORTED, "film_grad_from_g: too many rows");
-  if (int e = cng_device_check()) return e;
-  cng::film_grad_from_g_kernel<<<static_cast<unsigned>((P + cng::kGradRows - 1) / cng::kGradRows), 256, 0, cng::as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dy_bf16), static_cast<const __half*>(g_f16), P, static_cast<__nv_bfloat16*>(dz_bf16), colsum);
-  return cng::check_launch("cng_film_grad_from_g");
-}
 
 int cng_merge_composite_bwd(const float* rgb_sigma_fine, const float* rgb_sigma_coarse, const float* t_fine,
                             const float* t_coarse, const float* noise, const float* rays_d_cam, const float* d_pixels,
@@ -442,31 +327,6 @@ int cng_volume_from_channels_last(const float* vol_ndhwc, float* vol_ncdhw, int 
   dim3 grid(static_cast<unsigned>((vox + 31) / 32), B);
   cng::channels_first_kernel<<<grid, 256, static_cast<size_t>(C) * 33 * sizeof(float), cng::as_stream(stream)>>>(vol_ndhwc, vol_ncdhw, C, vox);
   return cng::check_launch("cng_volume_from_channels_last");
-}
-
-int cng_film_sin_apply(const float* z, const float* bias, const float* freq, const float* phase, long long P, int HID,
-                       void* y_bf16, cng_stream_t stream) {
-  CNG_REQUIRE(P >= 0 && HID >= 4 && HID % 4 == 0, CNG_ERR_INVALID_ARGUMENT, "film_sin_apply: P=%lld HID=%d", P, HID);
-  if (P == 0) return CNG_OK;
-  CNG_REQUIRE(z && bias && freq && phase && y_bf16, CNG_ERR_INVALID_ARGUMENT, "film_sin_apply: NULL pointer");
-  if (int e = cng_device_check()) return e;
-  const long long total4 = P * HID / 4;
-  const unsigned grid = static_cast<unsigned>(min((total4 + 255) / 256, static_cast<long long>(cng::sm_count()) * 16));
-  cng::film_sin_apply_kernel<<<grid, 256, 0, cng::as_stream(stream)>>>(z, bias, freq, phase, P, HID, static_cast<__nv_bfloat16*>(y_bf16));
-  return cng::check_launch("cng_film_sin_apply");
-}
-
-int cng_film_sin_grad(const void* dy_bf16, const float* z, const float* bias, const float* freq, const float* phase, long long P,
-                      int HID, void* dz_bf16, float* dfreq, float* dphase, cng_stream_t stream) {
-  CNG_REQUIRE(P >= 0, CNG_ERR_INVALID_ARGUMENT, "film_sin_grad: P=%lld", P);
-  CNG_REQUIRE(HID == 256, CNG_ERR_UNSUPPORTED, "film_sin_grad: HID=%d (only 256 is built)", HID);
-  if (P == 0) return CNG_OK;
-  CNG_REQUIRE(dy_bf16 && z && bias && freq && phase && dz_bf16 && dfreq && dphase, CNG_ERR_INVALID_ARGUMENT, "film_sin_grad: NULL pointer");
-  CNG_REQUIRE((P + cng::kGradRows - 1) / cng::kGradRows < 0x7fffffffLL, CNG_ERR_UNSUPPORTED, "film_sin_grad: too many rows");
-  if (int e = cng_device_check()) return e;
-  cng::film_sin_grad_kernel<<<static_cast<unsigned>((P + cng::kGradRows - 1) / cng::kGradRows), 256, 0, cng::as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dy_bf16), z, bias, freq, phase, P, static_cast<__nv_bfloat16*>(dz_bf16), dfreq, dphase);
-  return cng::check_launch("cng_film_sin_grad");
 }
 
 }  // extern "C"

@@ -165,9 +165,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
   static_assert(!(kShared && kRes), "residual blocks run on the slot-bound epilogue");
   static_assert(!(kShared && kTrain), "the shared epilogue is an inference path");
   // (built with CNG_TC_EPI_WARPS=4 the shared mode is not instantiated: shared_kernel() below returns nullptr)
-  // training mode gives one weight-ring slot (32 KB) to the per-warp staging buffers of the activation dumps
-  constexpr int kRingN = kTrain ? kRing - 1 : kRing;
-  constexpr uint32_t kSmemStage = kSmemW + kRingN * kChunkBytes;     // 16 epilogue warps x 2 KB (kTrain only)
+  constexpr int kRingN = kRing;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t s_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -443,6 +441,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
       for (int i = 0; i < kRowPerThread; ++i) row_x[ts + i * kSlotThreads] = row_next[i];
       named_bar_sync(1 + x, kSlotThreads);
     };
+    // training mode: the A tile leaves for HBM as one bulk store per layer (issued by one thread of the slot); before the
+    // tile is written again that store must have finished READING shared memory
+    const bool storer = (warp % kEpiWarpsPerSlot) == 0 && lane == 0;
+    auto tile_free = [&]() {
+      if (storer) bulk_wait_read_all();
+      named_bar_sync(1 + x, kSlotThreads);
+    };
     for (long long t = first + x * G; t < p.total_tiles; t += 2 * G, ++iter) {
       const TileInfo ti = tile_info(p, t);
       const float* shift_item = p.shift + static_cast<size_t>(ti.item) * L * kHID;
@@ -452,6 +457,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
         for (int i = 0; i < kRowPerThread; ++i) row_next[i] = __ldg(shift_item + ts + i * kSlotThreads);
       }
       publish_row();
+      if constexpr (kTrain) tile_free();
       // ---- features -> A block 0 as [x_hi(32) | x_lo(32)] ----
       {
         const float4* f = reinterpret_cast<const float4*>(p.feat + (static_cast<size_t>(ti.item) * p.N + ti.n0) * kC0);
@@ -471,6 +477,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
       }
       tc_fence_before();
       fence_proxy_async();
+      if constexpr (kTrain) {                                      // the layer-0 operand block -> HBM (operand of the layer-0 weight gradient)
+        named_bar_sync(1 + x, kSlotThreads);
+        if (storer) {
+          bulk_s2g(p.dump_feat + static_cast<size_t>(t) * kABlockBytes, s_base + a_base, kABlockBytes);
+          bulk_commit();
+        }
+      }
       mbar_arrive(act_ready(x));
       for (int l = 0; l < L; ++l) {
         const bool more = l + 1 < L;
@@ -485,6 +498,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
         acc_phase ^= 1;
         tc_fence_after();
         if (tracer) trace_event(p.trace, iter, l, x, 2);
+        if constexpr (kTrain) tile_free();
         auto finish_block = [&](uint32_t (&v)[32], int cc) {
           {
             const float4* rs = reinterpret_cast<const float4*>(row_x + cc * 32);
@@ -518,48 +532,29 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
             }
           }
           if constexpr (kTrain) {
-            // sin -> next layer's operand (shared memory A tile) and bf16 dump; freq*cos -> fp16 dump.  The dumps are
-            // row-major [point][256] in HBM; a lane owns one row, so its 64 bytes go through a 2 KB per-warp staging
-            // buffer and leave as 8 rows x 64 B per store instruction (8 LSU wavefronts instead of 32).
-            uint8_t* stage = smem + kSmemStage + warp * 2048;
-            const size_t dbase = ((static_cast<size_t>(l) * p.B + ti.item) * p.N + ti.n0 + q * 32) * kHID + cc * 32;   // row q*32 of the tile
+            // sin -> next layer's operand (shared memory A tile; the whole tile leaves as one bulk store after the layer);
+            // freq*cos -> fp16, stored straight from registers in the epilogue's own order: [cc][q][i][lane] x 16 B, i.e.
+            // 512 contiguous bytes per warp and store instruction.  The dgrad kernel reads it back with the same mapping.
+            uint4* gt = reinterpret_cast<uint4*>(p.dump_g + (static_cast<size_t>(l) * p.total_tiles + t) * (kTileM * kHID * 2));
             const float* fq = p.freq + (static_cast<size_t>(ti.item) * L + l) * kHID + cc * 32;
             uint8_t* blk = smem + a_base + (cc >> 1) * kABlockBytes + row * 128;
-            auto copy_out = [&](__nv_bfloat16* dst) {
-              __syncwarp();
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int rl = k * 8 + (lane >> 2), ch = lane & 3;
-                const uint4 val = *reinterpret_cast<const uint4*>(stage + (rl * 4 + (ch ^ ((rl >> 1) & 3))) * 16);
-                if (q * 32 + rl < ti.rows) *reinterpret_cast<uint4*>(dst + dbase + static_cast<size_t>(rl) * kHID + ch * 8) = val;
-              }
-              __syncwarp();
-            };
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint32_t xs[4], xo[4];
-#pragma unroll
-              for (int j = 0; j < 8; j += 2) {
-                const float s0 = __sinf(__uint_as_float(v[8 * i + j])), s1 = __sinf(__uint_as_float(v[8 * i + j + 1]));
-                xs[j / 2] = pack2<false>(s0, s1);                  // dump: bf16, the dtype of the gradient GEMMs
-                xo[j / 2] = pack2<kHalf>(s0, s1);                  // next layer's tensor-core operand
-              }
-              const int chunk = ((cc & 1) * 4 + i) ^ (row & 7);
-              *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(xo[0], xo[1], xo[2], xo[3]);
-              *reinterpret_cast<uint4*>(stage + (lane * 4 + (i ^ ((lane >> 1) & 3))) * 16) = make_uint4(xs[0], xs[1], xs[2], xs[3]);
-            }
-            copy_out(p.dump_x);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float4 f0 = __ldg(reinterpret_cast<const float4*>(fq + 8 * i)), f1 = __ldg(reinterpret_cast<const float4*>(fq + 8 * i + 4));
               const float fr[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-              uint32_t gs[4];
+              uint32_t xo[4], gs[4];
 #pragma unroll
-              for (int j = 0; j < 8; j += 2)
-                gs[j / 2] = pack2<true>(fr[j] * __cosf(__uint_as_float(v[8 * i + j])), fr[j + 1] * __cosf(__uint_as_float(v[8 * i + j + 1])));
-              *reinterpret_cast<uint4*>(stage + (lane * 4 + (i ^ ((lane >> 1) & 3))) * 16) = make_uint4(gs[0], gs[1], gs[2], gs[3]);
+              for (int j = 0; j < 8; j += 2) {
+                float s0, c0, s1, c1;
+                __sincosf(__uint_as_float(v[8 * i + j]), &s0, &c0);
+                __sincosf(__uint_as_float(v[8 * i + j + 1]), &s1, &c1);
+                xo[j / 2] = pack2<kHalf>(s0, s1);                  // next layer's tensor-core operand == the x dump
+                gs[j / 2] = pack2<true>(fr[j] * c0, fr[j + 1] * c1);
+              }
+              const int chunk = ((cc & 1) * 4 + i) ^ (row & 7);
+              *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(xo[0], xo[1], xo[2], xo[3]);
+              gt[((cc * 4 + q) * 4 + i) * 32 + lane] = make_uint4(gs[0], gs[1], gs[2], gs[3]);
             }
-            copy_out(p.dump_g);
             return;
           }
           // 32 columns = 64 bytes = 4 x 16-byte chunks of K-block cc/2, logical chunk (cc&1)*4 + i
@@ -613,6 +608,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
         tc_fence_before();
         fence_proxy_async();
         if (tracer) trace_event(p.trace, iter, l, x, 3);
+        if constexpr (kTrain) {                                    // x_{l+1} tile image -> HBM
+          named_bar_sync(1 + x, kSlotThreads);
+          if (storer) {
+            bulk_s2g(p.dump_x + (static_cast<size_t>(l) * p.total_tiles + t) * kATileBytes, s_base + a_base, kATileBytes);
+            bulk_commit();
+          }
+        }
         mbar_arrive(act_ready(x));
         if (more) publish_row();        // the last layer's prefetch (next tile's layer 0) is published at the top of the tile loop
       }
@@ -642,6 +644,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
       }
       tc_fence_before();   // orders the TMEM reads above before the next tile's stores / first MMA (via act_ready)
     }
+    if constexpr (kTrain) {
+      if (storer) bulk_wait_all();      // the last tile images have left shared memory before the CTA exits
+    }
   }
   // ---- teardown ----
   tc_fence_before();
@@ -667,7 +672,7 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
                          const float* const* b, const float* freq, const float* phase, const float* final_w,
                          const float* final_b_dev, int sigmoid_rgb, int half_operands, void* workspace, size_t workspace_bytes,
                          float* out, void* dump_x, void* dump_g, cudaStream_t stream, unsigned res_save_mask = 0, unsigned res_add_mask = 0,
-                         float* res_scratch = nullptr) {
+                         float* res_scratch = nullptr, void* dump_feat = nullptr) {
   CNG_REQUIRE(HID == kHID && C == kC0, CNG_ERR_UNSUPPORTED, "film_siren_fwd(bf16): needs HID=256, C=32 (got %d, %d)", HID, C);
   CNG_REQUIRE(L >= 1 && L <= 16, CNG_ERR_UNSUPPORTED, "film_siren_fwd(bf16): L=%d", L);
   CNG_REQUIRE(workspace != nullptr && workspace_bytes >= film_siren_tc_workspace(B, L), CNG_ERR_WORKSPACE,
@@ -682,16 +687,17 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
   fp.shift = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + static_cast<size_t>(B) * item_image_bytes(L));
   const long long per_item = 256LL * 4 + static_cast<long long>(L - 1) * 256 * 32 + 16 * 32;
   const long long fold_threads = per_item * B;
-  if (half_operands || dump_x != nullptr) film_fold_kernel<true><<<static_cast<unsigned>((fold_threads + 255) / 256), 256, 0, stream>>>(fp);
+  if (half_operands) film_fold_kernel<true><<<static_cast<unsigned>((fold_threads + 255) / 256), 256, 0, stream>>>(fp);
   else film_fold_kernel<false><<<static_cast<unsigned>((fold_threads + 255) / 256), 256, 0, stream>>>(fp);
   if (int e = check_launch("cng_film_siren_fwd(bf16): fold")) return e;
 
   TcParams p{};
-  p.half_operands = (dump_x != nullptr) ? 1 : half_operands;     // the recompute runs with fp16 operands (11-bit significands)
-  p.dump_x = static_cast<__nv_bfloat16*>(dump_x); p.dump_g = static_cast<__nv_bfloat16*>(dump_g); p.freq = freq;
-  CNG_REQUIRE((dump_x == nullptr) == (dump_g == nullptr), CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd_train: dump_x and dump_g go together");
-  CNG_REQUIRE(((reinterpret_cast<uintptr_t>(dump_x) | reinterpret_cast<uintptr_t>(dump_g)) & 15) == 0, CNG_ERR_INVALID_ARGUMENT,
-              "film_siren_fwd_train: dump buffers not 16-byte aligned");
+  p.half_operands = half_operands;
+  p.dump_x = static_cast<uint8_t*>(dump_x); p.dump_g = static_cast<uint8_t*>(dump_g); p.dump_feat = static_cast<uint8_t*>(dump_feat); p.freq = freq;
+  CNG_REQUIRE((dump_x == nullptr) == (dump_g == nullptr) && (dump_x == nullptr) == (dump_feat == nullptr), CNG_ERR_INVALID_ARGUMENT,
+              "film_siren_fwd_train: the x, g and feature dumps go together");
+  CNG_REQUIRE(((reinterpret_cast<uintptr_t>(dump_x) | reinterpret_cast<uintptr_t>(dump_g) | reinterpret_cast<uintptr_t>(dump_feat)) & 15) == 0,
+              CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd_train: dump buffers not 16-byte aligned");
   p.trace = g_tc_trace;
   p.res_save_mask = res_save_mask; p.res_add_mask = res_add_mask; p.res_scratch = res_scratch;
   CNG_REQUIRE(((res_save_mask | res_add_mask) == 0) || res_scratch != nullptr, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd: residual masks without a scratch buffer");
@@ -734,9 +740,9 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
   using KernelFn = void (*)(TcParams);
   const int pl = (poly == 0 || poly == 4) ? poly : 8;          // shared mode and fp16 come in these three flavours
   const bool res = (res_save_mask | res_add_mask) != 0;
-  const KernelFn fn = res ? (train ? film_siren_tc_kernel<0, true, true, false, true>
+  const KernelFn fn = res ? (train ? (half_operands ? film_siren_tc_kernel<0, true, true, false, true> : film_siren_tc_kernel<0, false, true, false, true>)
                                    : half_operands ? film_siren_tc_kernel<8, true, false, false, true> : film_siren_tc_kernel<8, false, false, false, true>)
-                      : train ? film_siren_tc_kernel<0, true, true>
+                      : train ? (half_operands ? film_siren_tc_kernel<0, true, true> : film_siren_tc_kernel<0, false, true>)
                       : shared ? (half_operands ? (pl == 0 ? shared_kernel<0, true>() : pl == 4 ? shared_kernel<4, true>() : shared_kernel<8, true>())
                                                 : (pl == 0 ? shared_kernel<0, false>() : pl == 4 ? shared_kernel<4, false>() : shared_kernel<8, false>()))
                       : half_operands ? (pl == 0 ? film_siren_tc_kernel<0, true> : pl == 4 ? film_siren_tc_kernel<4, true> : film_siren_tc_kernel<8, true>)
@@ -745,16 +751,26 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
   // function attributes are per device: the opt-in is cached per device ordinal (a process may render on several GPUs)
   static bool attr_set[64][8][9] = {};
   const int variant = res ? 5 + (train ? 2 : half_operands ? 1 : 0) : train ? 2 : (half_operands ? 1 : 0) + (shared ? 3 : 0);
+  const int pslot = train ? (half_operands ? 1 : 5) : poly;       // the two operand formats of the training kernel share a variant row
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = -1;
-  if (dev < 0 || !attr_set[dev][variant][poly]) {
+  if (dev < 0 || !attr_set[dev][variant][pslot]) {
     ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTotal));
     if (ce != cudaSuccess) return fail(static_cast<int>(ce), "film_siren_fwd(bf16): smem attribute: %s", cudaGetErrorString(ce));
-    if (dev >= 0) attr_set[dev][variant][poly] = true;
+    if (dev >= 0) attr_set[dev][variant][pslot] = true;
   }
   const long long grid = min(static_cast<long long>(sm_count()), p.total_tiles);
   fn<<<static_cast<unsigned>(grid), kNumThreads, kSmemTotal, stream>>>(p);
   return check_launch("cng_film_siren_fwd(bf16)");
+}
+
+// the backward's recompute: one item, dumps in the formats of TcParams (film_siren_bwd_tc.cu)
+int film_siren_tc_train_launch(const float* feat, long long N, int L, const float* const* w, const float* const* b, const float* freq,
+                               const float* phase, const float* final_w, const float* final_b_dev, int sigmoid_rgb, int half_operands,
+                               void* workspace, size_t workspace_bytes, float* out, void* dump_x, void* dump_g, void* dump_feat,
+                               cudaStream_t stream, unsigned res_save_mask, unsigned res_add_mask, float* res_scratch) {
+  return film_siren_tc_launch(feat, 1, N, kC0, kHID, L, w, b, freq, phase, final_w, final_b_dev, sigmoid_rgb, half_operands, workspace,
+                              workspace_bytes, out, dump_x, dump_g, stream, res_save_mask, res_add_mask, res_scratch, dump_feat);
 }
 
 // defined in film_siren_simt.cu
@@ -836,36 +852,22 @@ int cng_film_siren_fwd_res(const float* feat, int B, long long N, int C, int HID
 
 int cng_film_siren_fwd_train(const float* feat, int B, long long N, int C, int HID, int L, const float* const* layer_w_host,
                              const float* const* layer_b_host, const float* freq, const float* phase, const float* final_w,
-                             const float* final_b, int sigmoid_rgb, void* workspace, size_t workspace_bytes, float* rgb_sigma,
-                             void* x_dump_bf16, void* g_dump_bf16, cng_stream_t stream) {
+                             const float* final_b, int sigmoid_rgb, int precision, unsigned res_save_mask, unsigned res_add_mask,
+                             void* workspace, size_t workspace_bytes, void* res_scratch, size_t res_scratch_bytes, float* rgb_sigma,
+                             void* x_dump, void* g_dump, void* feat_dump, cng_stream_t stream) {
   CNG_REQUIRE(B >= 0 && N >= 0 && C >= 1 && HID >= 1 && L >= 1, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd_train: bad shape");
   if (B == 0 || N == 0) return CNG_OK;
-  CNG_REQUIRE(feat && layer_w_host && layer_b_host && freq && phase && final_w && final_b && rgb_sigma && x_dump_bf16 && g_dump_bf16,
+  CNG_REQUIRE(feat && layer_w_host && layer_b_host && freq && phase && final_w && final_b && rgb_sigma && x_dump && g_dump && feat_dump,
               CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd_train: NULL pointer");
-  for (int l = 0; l < L && l < 16; ++l)
-    CNG_REQUIRE(layer_w_host[l] && layer_b_host[l], CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd_train: NULL layer %d", l);
-  if (int e = cng_device_check()) return e;
-  return cng::film_siren_tc_launch(feat, B, N, C, HID, L, layer_w_host, layer_b_host, freq, phase, final_w, final_b, sigmoid_rgb, 0,
-                                   workspace, workspace_bytes, rgb_sigma, x_dump_bf16, g_dump_bf16, cng::as_stream(stream));
-}
-
-int cng_film_siren_fwd_train_res(const float* feat, int B, long long N, int C, int HID, int L, const float* const* layer_w_host,
-                             const float* const* layer_b_host, const float* freq, const float* phase, const float* final_w,
-                             const float* final_b, int sigmoid_rgb, void* workspace, size_t workspace_bytes, float* rgb_sigma,
-                             void* x_dump_bf16, void* g_dump_bf16, unsigned res_save_mask, unsigned res_add_mask, void* res_scratch,
-                                 size_t res_scratch_bytes, cng_stream_t stream) {
-  CNG_REQUIRE(B >= 0 && N >= 0 && C >= 1 && HID >= 1 && L >= 1, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd_train: bad shape");
-  if (B == 0 || N == 0) return CNG_OK;
-  CNG_REQUIRE(feat && layer_w_host && layer_b_host && freq && phase && final_w && final_b && rgb_sigma && x_dump_bf16 && g_dump_bf16,
-              CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd_train: NULL pointer");
+  CNG_REQUIRE(precision == CNG_PREC_BF16 || precision == CNG_PREC_FP16, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd_train: precision must be bf16 or fp16");
   for (int l = 0; l < L && l < 16; ++l)
     CNG_REQUIRE(layer_w_host[l] && layer_b_host[l], CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd_train: NULL layer %d", l);
   if (int e = cng_device_check()) return e;
   CNG_REQUIRE((res_save_mask | res_add_mask) == 0 || (res_scratch != nullptr && res_scratch_bytes >= cng_film_siren_res_scratch_bytes()),
-              CNG_ERR_WORKSPACE, "film_siren_fwd_train_res: residual scratch %zu < %zu bytes", res_scratch_bytes, cng_film_siren_res_scratch_bytes());
-  return cng::film_siren_tc_launch(feat, B, N, C, HID, L, layer_w_host, layer_b_host, freq, phase, final_w, final_b, sigmoid_rgb, 0,
-                                   workspace, workspace_bytes, rgb_sigma, x_dump_bf16, g_dump_bf16, cng::as_stream(stream), res_save_mask, res_add_mask,
-                                   static_cast<float*>(res_scratch));
+              CNG_ERR_WORKSPACE, "film_siren_fwd_train: residual scratch %zu < %zu bytes", res_scratch_bytes, cng_film_siren_res_scratch_bytes());
+  return cng::film_siren_tc_launch(feat, B, N, C, HID, L, layer_w_host, layer_b_host, freq, phase, final_w, final_b, sigmoid_rgb,
+                                   precision == CNG_PREC_FP16 ? 1 : 0, workspace, workspace_bytes, rgb_sigma, x_dump, g_dump, cng::as_stream(stream),
+                                   res_save_mask, res_add_mask, static_cast<float*>(res_scratch), feat_dump);
 }
 
 }  // extern "C"

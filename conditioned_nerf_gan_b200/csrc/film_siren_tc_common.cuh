@@ -111,6 +111,13 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// shared -> global bulk copies (TMA unit, bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // true in exactly one lane of the (converged) warp
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -254,10 +261,16 @@ struct TcParams {
   long long tiles_per_item;
   long long total_tiles;
   int half_operands;        // 1: fp16 operands, 0: bf16
-  // training-mode dump (backward recompute): per layer l the layer output x_{l+1} = sin(u_l) and the local derivative
-  // g_l = freq * cos(u_l), [L][B][N][256] each, x as bf16 (a GEMM operand next to bf16 gradients), g as fp16; NULL in inference
-  __nv_bfloat16* dump_x;
-  __nv_bfloat16* dump_g;    // holds fp16 bit patterns
+  // training-mode dumps (backward recompute), NULL in inference.  T = total_tiles:
+  //   dump_x  [L][T][64 KB]  the layer output x_{l+1} = sin(u_l) as the 128-point operand TILE IMAGE the next layer's MMA reads
+  //           ([4 K-blocks][128 rows][64 x 16 bit], 128B-swizzled, operand format) -- one bulk store per tile-layer; the
+  //           weight-gradient kernel (film_siren_bwd_tc.cu) reads it back with MN-major descriptors
+  //   dump_g  [L][T][64 KB]  the local derivative g_l = freq * cos(u_l) in fp16, in the epilogue's own register order
+  //           [32-column block cc][lane quarter q][16-byte piece i][lane]: every store / load is 512 contiguous bytes per warp
+  //   dump_feat [T][16 KB]   the layer-0 operand block [x_hi(32) | x_lo(32)]
+  uint8_t* dump_x;
+  uint8_t* dump_g;
+  uint8_t* dump_feat;
   const float* freq;        // [B, L*256], only read when dumping
   long long* trace;         // debug: clock64 timeline of CTA 0 (tools/trace_tc.py), NULL in production
   // residual blocks (TALLSIREN_dRes, generators/siren.py:218-230): bit l of res_save_mask = layer l's output is kept as the

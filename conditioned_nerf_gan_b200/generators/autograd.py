@@ -5,11 +5,11 @@ The forward kernels stay the no-grad ones (K1, K2, K3', nothing saved per layer)
 
     _ToChannelsLast   NCDHW <-> NDHWC                               cng_volume_{to,from}_channels_last
     _Gather*          d feat -> d volume (scatter-add)               cng_scatter_points
-    _FilmSiren        d rgb_sigma -> d feat, d W/b, d freq/phase     activations recomputed per chunk by the
-                      training-mode K2 (cng_film_siren_fwd_train: the fused tcgen05 forward that also
-                      streams x_{l+1} and g_l = freq*cos(u_l) per layer), cng_film_grad_from_g for
-                      dz = dy*g; the dgrad / wgrad GEMMs are cuBLAS bf16 x bf16 -> fp32 (``torch.mm``
-                      with ``out_dtype``) -- library GEMMs, NOT hand-written tcgen05 yet
+    _FilmSiren        d rgb_sigma -> d feat, d W/b, d freq/phase     cng_film_siren_bwd per chunk: activations
+                      recomputed by the training-mode K2 (the fused tcgen05 forward that also writes
+                      x_{l+1} tile images and g_l = freq*cos(u_l)), then the tcgen05 dgrad chain
+                      (dz = dy*g formed in its epilogue) and the tcgen05 split-K weight gradient --
+                      no library GEMM (csrc/film_siren_bwd_tc.cu)
     _MergeComposite   d pixels, d depth -> d rgb_sigma (fine, coarse)  cng_merge_composite_bwd
 
 Sample positions, distances and the coarse weights used for resampling carry no gradient, exactly
@@ -25,13 +25,8 @@ import torch
 from .. import ops
 from .volumetric_rendering import camera_tables
 
-import os
-
 HAS_BACKWARD = True
-# "lib": one cng_film_siren_bwd call per chunk (recompute, dz, cuBLAS GEMMs issued inside the library);
-# "py": the same sequence issued kernel by kernel from here (torch.mm for the GEMMs) -- kept for A/B, same numbers
-BWD_IMPL = os.environ.get("CNG_BWD_IMPL", "lib")
-CHUNK_ROWS = 1 << 20          # points per recompute chunk of the MLP backward (~8.6 GB of x / g dumps at L = 8)
+CHUNK_ROWS = 1 << 20          # points per recompute chunk of the MLP backward (~13 GB of x / g / dz dumps at L = 8)
 
 
 class _ToChannelsLast(torch.autograd.Function):
@@ -113,21 +108,20 @@ class _FilmSiren(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out):
-        """Chunked recompute: the training-mode K2 (cng_film_siren_fwd_train) re-runs the fused forward on a chunk of
-        points and streams every layer's output x_{l+1} and local derivative g_l = freq*cos(u_l) to HBM (bf16); then, per
-        layer from last to first:  dz = dy*g (cng_film_grad_from_g, with column sums),  dW += dz^T x_l and dy = dz W_l
-        (cuBLAS bf16 GEMMs, fp32 accumulate),  db = colsum(dz),  dphase = colsum(dz)/freq,
-        dfreq = rowsum(W * dW_chunk)/freq + b * dphase.
+        """Chunked: per item and chunk of points one cng_film_siren_bwd call (recompute with dumps, dgrad chain, split-K
+        weight gradient, head -- all tcgen05, csrc/film_siren_bwd_tc.cu) accumulates dW_l = dz_l^T x_l and the column sums
+        of dz_l = dy_l * freq * cos(u_l); from them, per item:  db = colsum,  dphase = colsum / freq,
+        dfreq = rowsum(W * dW_item) / freq + b * dphase.
         Residual blocks (``res_add`` / ``res_save`` masks, siren.py:218-230): g_l is taken at the pre-activation that includes
         the re-added block input, so the per-layer rule is unchanged; the kept activation (output of the last ``save`` layer
-        before l) additionally receives dz_l of the adding layer."""
+        before l) additionally receives dz_l of the adding layer (inside the dgrad kernel)."""
         feat, freq, phase, final_w, final_b, out, *wb = ctx.saved_tensors
         L, H = ctx.L, final_w.shape[1]
-        ws, bs = [w.detach().float() for w in wb[:L]], [b.detach().float() for b in wb[L:]]
-        ws_bf = [w.to(torch.bfloat16) for w in ws]
-        fw, fb = final_w.detach().float(), final_b.detach().float()
-        fw_bf = fw.to(torch.bfloat16)
         B, N, C = feat.shape
+        if C != 32 or H != 256:
+            raise NotImplementedError(f"the MLP backward is built for input_dim=32, hidden_dim=256 (got {C}, {H})")
+        ws, bs = [w.detach().float().contiguous() for w in wb[:L]], [b.detach().float().contiguous() for b in wb[L:]]
+        fw, fb = final_w.detach().float().contiguous(), final_b.detach().float().contiguous()
         dev = feat.device
         d_out = d_out.contiguous().float()
         d_feat = torch.empty_like(feat)
@@ -137,49 +131,18 @@ class _FilmSiren(torch.autograd.Function):
         d_bs = [torch.zeros_like(b) for b in bs]
         d_fw = torch.zeros_like(fw)
         d_fb = torch.zeros((4,), dtype=torch.float32, device=dev)
-        kept_of = {l: max(s_ for s_ in range(l) if (ctx.res_save >> s_) & 1) for l in range(L) if (ctx.res_add >> l) & 1}
         b_stack = torch.stack(bs)                                                  # [L, H]
         for b in range(B):
-            fr_all, ph_all = freq[b:b + 1].detach().float().contiguous(), phase[b:b + 1].detach().float().contiguous()
-            safe_fr = torch.where(fr_all[0].abs() < 1e-12, torch.ones_like(fr_all[0]), fr_all[0]).view(L, H)
+            fr_all, ph_all = freq[b].detach().float().contiguous(), phase[b].detach().float().contiguous()
+            safe_fr = torch.where(fr_all.abs() < 1e-12, torch.ones_like(fr_all), fr_all).view(L, H)
             # per item: weight gradients and column sums are accumulated over the chunks and turned into db / dphase / dfreq
-            # once at the end (they depend on the item's freq) -- the chunk loop below is 4 launches per layer
+            # once at the end (they depend on the item's freq)
             dW_item = [torch.zeros_like(w) for w in ws]
             colsum = torch.zeros((L, H), dtype=torch.float32, device=dev)
             for r0 in range(0, N, CHUNK_ROWS):
                 r1 = min(N, r0 + CHUNK_ROWS)
-                if BWD_IMPL == "lib" and C == 32 and H == 256:
-                    ops.film_siren_bwd(feat[b, r0:r1].detach().contiguous(), d_out[b, r0:r1].contiguous(), out[b, r0:r1].contiguous(), ws, bs,
-                                       ws_bf, fr_all[0], ph_all[0], fw, fb, fw_bf, ctx.sigmoid_rgb, d_feat[b, r0:r1], dW_item, colsum, d_fw, d_fb,
-                                       ctx.res_save, ctx.res_add)
-                    continue
-                x0 = feat[b:b + 1, r0:r1].detach().contiguous()
-                _, xs, gs = ops.film_siren_fwd_train(x0, ws, bs, fr_all, ph_all, fw, fb, ctx.sigmoid_rgb, ctx.res_save, ctx.res_add)
-                xs, gs = xs[:, 0], gs[:, 0]                                    # [L, P, H]
-                # ---- head: out = x_L Wf^T + bf, rgb = sigmoid(out[:, :3])
-                d_o = d_out[b, r0:r1]
-                if ctx.sigmoid_rgb:
-                    rgb = out[b, r0:r1, :3]
-                    d_o = torch.cat([d_o[:, :3] * (rgb * (1 - rgb)), d_o[:, 3:]], dim=1)
-                d_o_bf = d_o.to(torch.bfloat16)
-                d_fw += torch.mm(d_o_bf.t(), xs[L - 1], out_dtype=torch.float32)
-                d_fb += d_o.sum(0)
-                dy = torch.mm(d_o_bf, fw_bf)                                   # [P,4] x [4,H] -> bf16 [P,H]
-                x0_bf = x0[0].to(torch.bfloat16)
-                pending = {}                                                   # save layer -> gradient arriving through the skip
-                for l in reversed(range(L)):
-                    dz = ops.film_grad_from_g(dy, gs[l], colsum[l])
-                    if l in kept_of:
-                        pending[kept_of[l]] = dz
-                    x_in = xs[l - 1] if l > 0 else x0_bf
-                    dW_item[l] += torch.mm(dz.t(), x_in, out_dtype=torch.float32)   # this chunk's share, [H, K_l]
-                    if l == 0:
-                        d_feat[b, r0:r1] = torch.mm(dz, ws_bf[0], out_dtype=torch.float32)
-                    else:
-                        dy = torch.mm(dz, ws_bf[l])
-                        if (l - 1) in pending:
-                            dy = dy + pending.pop(l - 1)
-                del xs, gs
+                ops.film_siren_bwd(feat[b, r0:r1].detach().contiguous(), d_out[b, r0:r1].contiguous(), ws, bs, fr_all, ph_all, fw, fb,
+                                   ctx.sigmoid_rgb, d_feat[b, r0:r1], dW_item, colsum, d_fw, d_fb, ctx.res_save, ctx.res_add)
             dph = colsum / safe_fr                                             # [L, H]
             d_phase[b] += dph.reshape(-1)
             wdw = torch.stack([(ws[l] * dW_item[l]).sum(1) for l in range(L)])  # [L, H]

@@ -376,38 +376,18 @@ def volume_from_channels_last(vol_cl: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def film_sin_apply(z, bias, freq, phase) -> torch.Tensor:
-    """bf16(sin(freq * (z + bias) + phase)); z [P,HID] fp32, bias/freq/phase [HID]."""
-    z = _f32(z, "z")
-    P, HID = z.shape
-    y = torch.empty((P, HID), dtype=torch.bfloat16, device=z.device)
-    with torch.cuda.device(z.device), _timed("cng_film_sin_apply"):
-        _lib.call("cng_film_sin_apply", _ptr(z), _ptr(_f32(bias, "bias")), _ptr(_f32(freq, "freq")), _ptr(_f32(phase, "phase")),
-                  P, HID, _ptr(y), _stream(z))
-    _count()
-    return y
+TILE_POINTS = 128            # points per operand tile of the tcgen05 kernels
+TILE_IMAGE_BYTES = 65536     # one tile-layer of x / dz / g (include/cng_b200.h, "Dump formats")
+FEAT_IMAGE_BYTES = 16384
 
 
-def film_sin_grad(dy_bf16, z, bias, freq, phase, dfreq, dphase) -> torch.Tensor:
-    """Returns dz (bf16 [P,HID]); accumulates into dfreq / dphase (fp32 [HID], in place)."""
-    z = _f32(z, "z")
-    P, HID = z.shape
-    if not (dy_bf16.is_cuda and dy_bf16.dtype == torch.bfloat16 and dy_bf16.is_contiguous() and dy_bf16.shape == z.shape):
-        raise RuntimeError("film_sin_grad: dy must be a contiguous bf16 CUDA tensor of z's shape")
-    for name, t in (("dfreq", dfreq), ("dphase", dphase)):
-        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == HID):
-            raise RuntimeError(f"film_sin_grad: {name} must be a contiguous fp32 CUDA tensor with HID elements")
-    dz = torch.empty((P, HID), dtype=torch.bfloat16, device=z.device)
-    with torch.cuda.device(z.device), _timed("cng_film_sin_grad"):
-        _lib.call("cng_film_sin_grad", _ptr(dy_bf16), _ptr(z), _ptr(_f32(bias, "bias")), _ptr(_f32(freq, "freq")),
-                  _ptr(_f32(phase, "phase")), P, HID, _ptr(dz), _ptr(dfreq), _ptr(dphase), _stream(z))
-    _count()
-    return dz
-
-
-def film_siren_fwd_train(feat, layer_w, layer_b, freq, phase, final_w, final_b, sigmoid_rgb: bool, res_save_mask: int = 0,
-                         res_add_mask: int = 0):
-    """Training-mode K2: rgb_sigma [B,N,4] plus the per-layer dumps x [L,B,N,HID] (bf16) and g = freq*cos(u) [L,B,N,HID] (fp16)."""
+def film_siren_fwd_train(feat, layer_w, layer_b, freq, phase, final_w, final_b, sigmoid_rgb: bool, precision: str = "fp16",
+                         res_save_mask: int = 0, res_add_mask: int = 0):
+    """Training-mode K2 (the backward's recompute): rgb_sigma [B,N,4] plus the dumps in the formats of include/cng_b200.h --
+    x [L,T,65536] uint8 (operand tile images), g [L,T,65536] uint8 (fp16, epilogue order), feat [T,16384] uint8 -- with
+    T = B * ceil(N / 128)."""
+    if precision not in ("bf16", "fp16"):
+        raise ValueError("film_siren_fwd_train: precision must be 'bf16' or 'fp16'")
     feat = _f32(feat, "feat")
     B, N, C = feat.shape
     L = len(layer_w)
@@ -417,34 +397,77 @@ def film_siren_fwd_train(feat, layer_w, layer_b, freq, phase, final_w, final_b, 
     freq, phase = _f32(freq, "freq"), _f32(phase, "phase")
     final_w, final_b = _f32(final_w, "final_w"), _f32(final_b, "final_b")
     dev = feat.device
+    T = B * ((N + TILE_POINTS - 1) // TILE_POINTS)
     out = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
-    xs = torch.empty((L, B, N, HID), dtype=torch.bfloat16, device=dev)
-    gs = torch.empty((L, B, N, HID), dtype=torch.float16, device=dev)
+    xs = torch.empty((L, T, TILE_IMAGE_BYTES), dtype=torch.uint8, device=dev)
+    gs = torch.empty((L, T, TILE_IMAGE_BYTES), dtype=torch.uint8, device=dev)
+    fd = torch.empty((T, FEAT_IMAGE_BYTES), dtype=torch.uint8, device=dev)
     w_arr = (ctypes.c_void_p * L)(*[w.data_ptr() for w in ws])
     b_arr = (ctypes.c_void_p * L)(*[b.data_ptr() for b in bs])
     lib = _lib.load()
-    ws_bytes = int(lib.cng_film_siren_workspace_bytes(B, C, HID, L, _lib.PREC_BF16))
+    code = PRECISIONS[precision]
+    ws_bytes = int(lib.cng_film_siren_workspace_bytes(B, C, HID, L, code))
     workspace = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
+    scratch = _res_scratch(dev) if (res_save_mask or res_add_mask) else None
     with torch.cuda.device(dev), _timed("cng_film_siren_fwd_train"):
-        if res_save_mask or res_add_mask:
-            scratch = _res_scratch(dev)
-            _lib.call("cng_film_siren_fwd_train_res", _ptr(feat), B, N, C, HID, L, w_arr, b_arr, _ptr(freq), _ptr(phase), _ptr(final_w),
-                      _ptr(final_b), int(bool(sigmoid_rgb)), _ptr(workspace), ws_bytes, _ptr(out), _ptr(xs), _ptr(gs),
-                      int(res_save_mask), int(res_add_mask), _ptr(scratch), scratch.numel(), _stream(feat))
-        else:
-            _lib.call("cng_film_siren_fwd_train", _ptr(feat), B, N, C, HID, L, w_arr, b_arr, _ptr(freq), _ptr(phase), _ptr(final_w),
-                      _ptr(final_b), int(bool(sigmoid_rgb)), _ptr(workspace), ws_bytes, _ptr(out), _ptr(xs), _ptr(gs), _stream(feat))
+        _lib.call("cng_film_siren_fwd_train", _ptr(feat), B, N, C, HID, L, w_arr, b_arr, _ptr(freq), _ptr(phase), _ptr(final_w),
+                  _ptr(final_b), int(bool(sigmoid_rgb)), code, int(res_save_mask), int(res_add_mask), _ptr(workspace), ws_bytes,
+                  _ptr(scratch), scratch.numel() if scratch is not None else 0, _ptr(out), _ptr(xs), _ptr(gs), _ptr(fd), _stream(feat))
     _count(2)
-    return out, xs, gs
+    return out, xs, gs, fd
+
+
+def film_siren_wt_images(layer_w, final_w) -> torch.Tensor:
+    """Operand images of W_l^T and of the head for the dgrad chain (cng_film_siren_wt_images)."""
+    L = len(layer_w)
+    ws = [_f32(w, f"layer_w[{i}]") for i, w in enumerate(layer_w)]
+    final_w = _f32(final_w, "final_w")
+    dev = final_w.device
+    lib = _lib.load()
+    img = torch.empty((int(lib.cng_film_siren_wt_image_bytes(L)),), dtype=torch.uint8, device=dev)
+    w_arr = (ctypes.c_void_p * L)(*[w.data_ptr() for w in ws])
+    with torch.cuda.device(dev), _timed("cng_film_siren_wt_images"):
+        _lib.call("cng_film_siren_wt_images", w_arr, _ptr(final_w), ws[0].shape[1], ws[0].shape[0], L, _ptr(img), _stream(final_w))
+    _count()
+    return img
+
+
+def film_siren_dgrad(d_out, out, sigmoid_rgb: bool, L: int, wt_images, g_dump, d_final_b_acc, res_save_mask: int = 0, res_add_mask: int = 0):
+    """The fused dgrad chain (cng_film_siren_dgrad): d_out / out [P,4] -> (d_feat [P,32], dz tile images [L,T,65536] uint8);
+    accumulates the head bias gradient into d_final_b_acc [4]."""
+    d_out = _f32(d_out, "d_out")
+    P = d_out.shape[0]
+    out = _f32(out, "out") if out is not None else None
+    dev = d_out.device
+    T = (P + TILE_POINTS - 1) // TILE_POINTS
+    dz = torch.empty((L, T, TILE_IMAGE_BYTES), dtype=torch.uint8, device=dev)
+    d_feat = torch.empty((P, 32), dtype=torch.float32, device=dev)
+    scratch = _res_scratch(dev) if (res_save_mask or res_add_mask) else None
+    with torch.cuda.device(dev), _timed("cng_film_siren_dgrad"):
+        _lib.call("cng_film_siren_dgrad", _ptr(d_out), _ptr(out), int(bool(sigmoid_rgb)), P, L, _ptr(wt_images), _ptr(g_dump), _ptr(dz),
+                  _ptr(d_feat), _ptr(d_final_b_acc), int(res_save_mask), int(res_add_mask), _ptr(scratch),
+                  scratch.numel() if scratch is not None else 0, _stream(d_out))
+    _count()
+    return d_feat, dz
+
+
+def film_siren_wgrad(dz_dump, x_dump, feat_dump, P: int, L: int, x_is_fp16: bool, d_w_acc, colsum_acc) -> None:
+    """Weight gradients by split-K over the points (cng_film_siren_wgrad): d_w_acc[l] [256,K_l] += dz_l^T x_l, colsum_acc [L,256] +=
+    column sums of dz_l."""
+    arr = (ctypes.c_void_p * L)(*[t.data_ptr() for t in d_w_acc])
+    with torch.cuda.device(dz_dump.device), _timed("cng_film_siren_wgrad"):
+        _lib.call("cng_film_siren_wgrad", _ptr(dz_dump), _ptr(x_dump), _ptr(feat_dump), P, L, int(bool(x_is_fp16)), arr, _ptr(colsum_acc),
+                  _stream(dz_dump))
+    _count()
 
 
 _BWD_WS = {}
 
 
-def film_siren_bwd(feat, d_out, out, layer_w, layer_b, layer_w_bf16, freq, phase, final_w, final_b, final_w_bf16, sigmoid_rgb: bool,
+def film_siren_bwd(feat, d_out, layer_w, layer_b, freq, phase, final_w, final_b, sigmoid_rgb: bool,
                    d_feat, d_w_acc, colsum_acc, d_final_w_acc, d_final_b_acc, res_save_mask: int = 0, res_add_mask: int = 0) -> None:
-    """The MLP backward of one chunk of points of one item as ONE library call (cng_film_siren_bwd): feat [P,C], d_out / out
-    [P,4]; writes d_feat [P,C], accumulates into d_w_acc[l], colsum_acc [L,HID], d_final_w_acc, d_final_b_acc (all fp32)."""
+    """The MLP backward of one chunk of points of one item as ONE library call (cng_film_siren_bwd): feat [P,C], d_out [P,4];
+    writes d_feat [P,C], accumulates into d_w_acc[l], colsum_acc [L,HID], d_final_w_acc, d_final_b_acc (all fp32)."""
     P, C = feat.shape
     L = len(layer_w)
     HID = layer_w[0].shape[0]
@@ -456,34 +479,22 @@ def film_siren_bwd(feat, d_out, out, layer_w, layer_b, layer_w_bf16, freq, phase
     lib = _lib.load()
     with torch.cuda.device(dev):
         need = int(lib.cng_film_siren_bwd_workspace_bytes(P, C, HID, L))
+        if need == 0:
+            raise _lib.CngError("cng_film_siren_bwd", -2, f"the MLP backward is built for C=32, HID=256, L<=16 (got C={C}, HID={HID}, L={L})")
         key = (dev.index, torch.cuda.current_stream().cuda_stream)
         ws = _BWD_WS.get(key)
-        if ws is None or ws.numel() < need:
+        if ws is None or ws.numel() < need + 256:
             _BWD_WS.pop(key, None)
-            ws = _BWD_WS[key] = torch.empty((need,), dtype=torch.uint8, device=dev)
+            ws = _BWD_WS[key] = torch.empty((need + 256,), dtype=torch.uint8, device=dev)
+        base = (-ws.data_ptr()) % 256
         scratch = _res_scratch(dev) if (res_save_mask or res_add_mask) else None
         arr = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
         with _timed("cng_film_siren_bwd"):
-            _lib.call("cng_film_siren_bwd", _ptr(feat), _ptr(d_out), _ptr(out), P, C, HID, L, arr(layer_w), arr(layer_b), arr(layer_w_bf16),
-                      _ptr(freq), _ptr(phase), _ptr(final_w), _ptr(final_b), _ptr(final_w_bf16), int(bool(sigmoid_rgb)), int(res_save_mask),
-                      int(res_add_mask), _ptr(ws), ws.numel(), _ptr(scratch), scratch.numel() if scratch is not None else 0, _ptr(d_feat),
-                      arr(d_w_acc), _ptr(colsum_acc), _ptr(d_final_w_acc), _ptr(d_final_b_acc), _stream(feat))
-    _count(5 + 4 * L)
-
-
-def film_grad_from_g(dy_bf16, g_bf16, colsum) -> torch.Tensor:
-    """dz = dy * g (dy, dz bf16, g fp16, [P,HID]); accumulates the column sums of dz into colsum (fp32 [HID], in place)."""
-    for name, t, dt in (("dy", dy_bf16, torch.bfloat16), ("g", g_bf16, torch.float16)):
-        if not (t.is_cuda and t.dtype == dt and t.is_contiguous()):
-            raise RuntimeError(f"film_grad_from_g: {name} must be a contiguous {dt} CUDA tensor")
-    P, HID = dy_bf16.shape
-    if g_bf16.shape != dy_bf16.shape or not (colsum.is_cuda and colsum.dtype == torch.float32 and colsum.is_contiguous() and colsum.numel() == HID):
-        raise RuntimeError("film_grad_from_g: shape mismatch")
-    dz = torch.empty((P, HID), dtype=torch.bfloat16, device=dy_bf16.device)
-    with torch.cuda.device(dy_bf16.device), _timed("cng_film_grad_from_g"):
-        _lib.call("cng_film_grad_from_g", _ptr(dy_bf16), _ptr(g_bf16), P, HID, _ptr(dz), _ptr(colsum), _stream(dy_bf16))
-    _count()
-    return dz
+            _lib.call("cng_film_siren_bwd", _ptr(feat), _ptr(d_out), P, C, HID, L, arr(layer_w), arr(layer_b),
+                      _ptr(freq), _ptr(phase), _ptr(final_w), _ptr(final_b), int(bool(sigmoid_rgb)), int(res_save_mask),
+                      int(res_add_mask), ctypes.c_void_p(ws.data_ptr() + base), need, _ptr(scratch), scratch.numel() if scratch is not None else 0,
+                      _ptr(d_feat), arr(d_w_acc), _ptr(colsum_acc), _ptr(d_final_w_acc), _ptr(d_final_b_acc), _stream(feat))
+    _count(6)
 
 
 def merge_sort(t_fine, t_coarse, want_sorted: bool = False):

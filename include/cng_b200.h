@@ -248,17 +248,6 @@ CNG_API int cng_scatter_points(float* dvol_ndhwc, int B, int C, int D, int H, in
 CNG_API int cng_volume_from_channels_last(const float* vol_ndhwc, float* vol_ncdhw, int B, int C, int D,
                                   int H, int W, cng_stream_t stream);
 
-/* Elementwise halves of FiLMLayer (siren.py:153-157) around the GEMMs of the activation-
- * recomputing backward; z [P,HID] fp32 is the Linear output WITHOUT bias, bias/freq/phase [HID]:
- *   apply: y = bf16(sin(freq * (z + bias) + phase))                              [P,HID] bf16
- *   grad:  du = dy * cos(freq*(z+bias)+phase); dz = bf16(du * freq);
- *          dfreq += sum_p du * (z+bias); dphase += sum_p du   (atomic accumulation, HID == 256) */
-CNG_API int cng_film_sin_apply(const float* z, const float* bias, const float* freq, const float* phase,
-                       long long P, int HID, void* y_bf16, cng_stream_t stream);
-CNG_API int cng_film_sin_grad(const void* dy_bf16, const float* z, const float* bias, const float* freq,
-                      const float* phase, long long P, int HID, void* dz_bf16, float* dfreq,
-                      float* dphase, cng_stream_t stream);
-
 /* ------------------------------------------------------------------------------------------
  * The whole forward of ImplicitGenerator3d.forward (generators/generators.py:33-187) in one call: K1 coarse, K2, K3,
  * K4, K1 fine, K2, K3' sequenced on `stream` with every intermediate in `workspace`
@@ -280,49 +269,67 @@ CNG_API int cng_render_fwd(const float* vol_ndhwc, long long vol_item_stride, in
                    int white_back, int last_back, void* workspace, size_t workspace_bytes,
                    float* pixels, float* depth, cng_stream_t stream);
 
-/* Training-mode forward of K2 for the backward's activation recompute: the same fused tcgen05 kernel (bf16
- * operands) that ALSO streams, for every FiLM layer l, its output x_{l+1} = sin(u_l) and its local derivative
- * g_l = freq * cos(u_l) to HBM, x_dump (bf16) / g_dump (fp16) [L, B, N, HID].  With them the layer backward is
- *   dz_l = dy_l * g_l (cng_film_grad_from_g),  dW_l = dz_l^T x_l,  dy_{l-1} = dz_l W_l,  db_l = colsum(dz_l),
- *   dphase_l = colsum(dz_l) / freq_l,  dfreq_l = rowsum(W_l * dW_l) / freq_l + b_l * dphase_l. */
+/* ------------------------------------------------------------------------------------------
+ * a14: backward of the FiLM-SIREN MLP (autograd through FiLMLayer.forward x L + head, generators/siren.py:146-160,
+ * 573-579; what loss.backward() runs at utils.py:711), all contractions on tcgen05 / TMEM (film_siren_bwd_tc.cu).
+ * T = ceil(points / 128) tiles.  Dump formats (device buffers the caller owns):
+ *   x_dump    [L][T][65536]  output of layer l, x_{l+1} = sin(u_l), as 128-point operand tile images
+ *                            ([4 K-blocks of 64 columns][128 rows][128 B], 128-byte swizzle: element (row, k) of a block at
+ *                            row*128 + (((k>>3) ^ (row&7)) << 4) + (k&7)*2), in the operand format of `precision`
+ *   g_dump    [L][T][65536]  g_l = freq * cos(u_l) in fp16, [32-column block cc 8][row quarter q 4][piece i 4][lane 32] x 16 B:
+ *                            row = 32 q + lane, columns 32 cc + 8 i .. + 7
+ *   feat_dump [T][16384]     the layer-0 operand block [x_hi(32) | x_lo(32)] (same swizzle)
+ *   dz_dump   [L][T][65536]  dz_l = dy_l * g_l as bf16 tile images (written by the dgrad chain, read by the weight gradient)
+ * ---------------------------------------------------------------------------------------- */
+/* Training-mode forward of K2 (the backward's activation recompute): the fused tcgen05 kernel of cng_film_siren_fwd(_res) that
+ * ALSO writes the three dumps above (one bulk store per tile-layer for x, direct register stores for g).  `precision`:
+ * CNG_PREC_BF16 or CNG_PREC_FP16 (operand format of the recompute and of x_dump).  With B > 1 the tile index runs over items:
+ * T = B * ceil(N / 128).  Residual masks / scratch as in cng_film_siren_fwd_res (0 / NULL for plain networks); g_l is then the
+ * derivative at the pre-activation INCLUDING the re-added block input. */
 CNG_API int cng_film_siren_fwd_train(const float* feat, int B, long long N, int C, int HID, int L,
                              const float* const* layer_w_host, const float* const* layer_b_host,
                              const float* freq, const float* phase, const float* final_w,
-                             const float* final_b, int sigmoid_rgb, void* workspace,
-                             size_t workspace_bytes, float* rgb_sigma, void* x_dump_bf16,
-                             void* g_dump_f16, cng_stream_t stream);
-/* The same for a network with residual blocks (masks and scratch as in cng_film_siren_fwd_res); g_l is the derivative at the
- * pre-activation INCLUDING the re-added block input, so the layer backward above holds unchanged and the kept activation
- * receives dz_l of the adding layer on top of its own gradient. */
-CNG_API int cng_film_siren_fwd_train_res(const float* feat, int B, long long N, int C, int HID, int L,
-                                 const float* const* layer_w_host, const float* const* layer_b_host,
-                                 const float* freq, const float* phase, const float* final_w,
-                                 const float* final_b, int sigmoid_rgb, void* workspace,
-                                 size_t workspace_bytes, float* rgb_sigma, void* x_dump_bf16,
-                                 void* g_dump_f16, unsigned res_save_mask, unsigned res_add_mask,
-                                 void* res_scratch, size_t res_scratch_bytes, cng_stream_t stream);
-/* The whole MLP backward of one chunk of points of ONE batch item (autograd through FiLMLayer.forward x L + head,
- * siren.py:146-160, 573-579; utils.py:711): recompute with dumps, head, then per layer dz = dy * g, dW += dz^T x,
- * dy = dz W; the GEMMs are cuBLAS bf16 -> fp32 library calls issued from inside (cuBLAS is bound at run time).
- *   feat [P, C]; d_out [P, 4] gradient w.r.t. rgb_sigma; out [P, 4] the forward output (read when sigmoid_rgb);
- *   layer_w_host / layer_b_host: HOST arrays of L device pointers (fp32), layer_w_bf16_host: the same weights in bf16;
- *   freq, phase [L*HID] of this item; final_w [4, HID], final_b [4], final_w_bf16 [4, HID];
+                             const float* final_b, int sigmoid_rgb, int precision, unsigned res_save_mask,
+                             unsigned res_add_mask, void* workspace, size_t workspace_bytes, void* res_scratch,
+                             size_t res_scratch_bytes, float* rgb_sigma, void* x_dump, void* g_dump,
+                             void* feat_dump, cng_stream_t stream);
+/* Operand images of W_l^T (bf16) and of the head for the dgrad chain; item independent.  `images`:
+ * cng_film_siren_wt_image_bytes(L) bytes, 16-byte aligned. */
+CNG_API size_t cng_film_siren_wt_image_bytes(int L);
+CNG_API int cng_film_siren_wt_images(const float* const* layer_w_host, const float* final_w, int C, int HID, int L,
+                             void* images, cng_stream_t stream);
+/* The dgrad chain of P points, all layers fused per 128-point tile (gradients stay in TMEM / shared memory between layers):
+ *   d_o = d_out (* rgb (1 - rgb) when sigmoid_rgb, with `out` the forward output), d_final_b_acc [4] += colsum(d_o),
+ *   dy = d_o Wf, then for l = L-1 .. 0: dz_l = dy * g_l (-> dz_dump), dy = dz_l W_l; d_feat [P, 32] = dz_0 W_0 (written).
+ * A kept activation of a residual block additionally receives the adding layer's dz (masks / scratch as in
+ * cng_film_siren_fwd_res; only patterns where an add sits exactly two layers after its kept layer: CNG_ERR_UNSUPPORTED
+ * otherwise). */
+CNG_API int cng_film_siren_dgrad(const float* d_out, const float* out, int sigmoid_rgb, long long P, int L,
+                         const void* wt_images, const void* g_dump, void* dz_dump, float* d_feat,
+                         float* d_final_b_acc, unsigned res_save_mask, unsigned res_add_mask, void* res_scratch,
+                         size_t res_scratch_bytes, cng_stream_t stream);
+/* Weight gradients as a split-K contraction over the points: d_w_acc_host[l] [HID, K_l] += dz_l^T x_l (x_0 = the features,
+ * hi + lo), colsum_acc [L, HID] += column sums of dz_l.  Both operands are read from the tile images with MN-major
+ * descriptors; fp32 accumulation in TMEM, one red.global.add flush per CTA and layer.  x_is_fp16: format of x_dump / feat_dump. */
+CNG_API int cng_film_siren_wgrad(const void* dz_dump, const void* x_dump, const void* feat_dump, long long P, int L,
+                         int x_is_fp16, float* const* d_w_acc_host, float* colsum_acc, cng_stream_t stream);
+/* The whole MLP backward of one chunk of points of ONE batch item in one call: recompute with dumps (fp16 operands), W^T
+ * images, dgrad chain, weight gradients, head weights.
+ *   feat [P, C]; d_out [P, 4] gradient w.r.t. rgb_sigma;
+ *   layer_w_host / layer_b_host: HOST arrays of L device pointers (fp32); freq, phase [L*HID] of this item; final_w [4, HID], final_b [4];
  *   outputs: d_feat [P, C] (written); accumulated (+=): d_w_acc_host[l] [HID, K_l] fp32, colsum_acc [L, HID] (column sums
  *   of dz_l: d_bias = colsum, d_phase = colsum / freq, d_freq = rowsum(W * dW) / freq + b * d_phase on the host),
  *   d_final_w_acc [4, HID], d_final_b_acc [4].
  *   workspace: cng_film_siren_bwd_workspace_bytes(P, C, HID, L), 256-byte aligned.  Residual masks / scratch as in
  *   cng_film_siren_fwd_res.  HID == 256, C == 32, P < 2^31. */
 CNG_API size_t cng_film_siren_bwd_workspace_bytes(long long P, int C, int HID, int L);
-CNG_API int cng_film_siren_bwd(const float* feat, const float* d_out, const float* out, long long P, int C, int HID, int L,
+CNG_API int cng_film_siren_bwd(const float* feat, const float* d_out, long long P, int C, int HID, int L,
                        const float* const* layer_w_host, const float* const* layer_b_host,
-                       const void* const* layer_w_bf16_host, const float* freq, const float* phase,
-                       const float* final_w, const float* final_b, const void* final_w_bf16, int sigmoid_rgb,
-                       unsigned res_save_mask, unsigned res_add_mask, void* workspace, size_t workspace_bytes,
-                       void* res_scratch, size_t res_scratch_bytes, float* d_feat, float* const* d_w_acc_host,
-                       float* colsum_acc, float* d_final_w_acc, float* d_final_b_acc, cng_stream_t stream);
-/* dz = dy * g elementwise (dy, dz bf16, g fp16, all [P,HID]); colsum [HID] += column sums of dz (fp32, atomic). HID == 256. */
-CNG_API int cng_film_grad_from_g(const void* dy_bf16, const void* g_f16, long long P, int HID, void* dz_bf16,
-                         float* colsum, cng_stream_t stream);
+                       const float* freq, const float* phase, const float* final_w, const float* final_b,
+                       int sigmoid_rgb, unsigned res_save_mask, unsigned res_add_mask, void* workspace,
+                       size_t workspace_bytes, void* res_scratch, size_t res_scratch_bytes, float* d_feat,
+                       float* const* d_w_acc_host, float* colsum_acc, float* d_final_w_acc, float* d_final_b_acc,
+                       cng_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -93,25 +93,130 @@ def test_scatter_points_vs_grid_sample_backward(ops, C, D, H, W, N):
     assert torch.equal(ops.volume_to_channels_last(dvol), dvol_cl)
 
 
-def test_film_sin_elementwise_halves(ops):
-    g = torch.Generator().manual_seed(0)
-    P, H = 1000, 256
-    z = torch.randn((P, H), generator=g)
-    bias, freq, phase = torch.randn(H, generator=g) * 0.1, torch.randn(H, generator=g) * 5 + 30, torch.randn(H, generator=g)
-    dy = (torch.randn((P, H), generator=g)).to(torch.bfloat16)
-    y = ops.film_sin_apply(dev(z), dev(bias), dev(freq), dev(phase))
-    u = freq * (z + bias) + phase
-    assert y.dtype == torch.bfloat16
-    assert (y.float().cpu() - torch.sin(u)).abs().max().item() < 5e-3            # bf16 rounding of a value in [-1, 1]
-    dfreq, dphase = torch.zeros(H, device="cuda"), torch.zeros(H, device="cuda")
-    dz = ops.film_sin_grad(dev(dy), dev(z), dev(bias), dev(freq), dev(phase), dfreq, dphase)
-    du = dy.float() * torch.cos(u)
-    assert rel_l2(dz.float().cpu(), du * freq) < 4e-3
-    assert rel_l2(dphase.cpu(), du.sum(0)) < 1e-4
-    assert rel_l2(dfreq.cpu(), (du * (z + bias)).sum(0)) < 1e-4
-    # accumulation semantics
-    ops.film_sin_grad(dev(dy), dev(z), dev(bias), dev(freq), dev(phase), dfreq, dphase)
-    assert rel_l2(dphase.cpu(), 2 * du.sum(0)) < 1e-4
+# ------------------------------------------------------------------------------------------------
+# a14, MLP part: the tcgen05 dgrad chain and split-K weight gradient on synthetic dumps (formats: include/cng_b200.h)
+# ------------------------------------------------------------------------------------------------
+def to_tile_images(x, dtype):
+    """[P, 64*nb] float -> uint8 [T, nb*16384]: per 128-point tile nb K-blocks of [128 rows][64 x 16 bit], 128-byte swizzle."""
+    P, W = x.shape
+    nb, T = W // 64, (P + 127) // 128
+    xp = torch.zeros((T * 128, W), dtype=torch.float32)
+    xp[:P] = x
+    x16 = xp.to(dtype).view(torch.int16).view(T, 128, nb, 8, 8)          # [tile, row, block, 16-byte chunk, element]
+    out = torch.empty((T, nb, 128, 8, 8), dtype=torch.int16)
+    rows = torch.arange(128)
+    for c in range(8):
+        out[:, :, rows, c ^ (rows & 7), :] = x16[:, :, :, c, :].permute(0, 2, 1, 3)
+    return out.view(torch.uint8).reshape(T, nb * 16384)
+
+
+def from_tile_images(img, P, dtype, nb=4):
+    T = img.shape[0]
+    v = img.cpu().contiguous().view(torch.int16).view(T, nb, 128, 8, 8)
+    out = torch.empty((T, 128, nb, 8, 8), dtype=torch.int16)
+    rows = torch.arange(128)
+    for c in range(8):
+        out[:, :, :, c, :] = v[:, :, rows, c ^ (rows & 7), :].permute(0, 2, 1, 3)
+    return out.view(dtype).reshape(T * 128, nb * 64)[:P].float()
+
+
+def to_g_images(g):
+    """[P, 256] float -> uint8 [T, 65536]: fp16 in the epilogue's register order [cc 8][q 4][i 4][lane 32][8]."""
+    P = g.shape[0]
+    T = (P + 127) // 128
+    gp = torch.zeros((T * 128, 256), dtype=torch.float32)
+    gp[:P] = g
+    v = gp.to(torch.float16).view(T, 4, 32, 8, 4, 8)                     # [tile, q, lane, cc, i, e]
+    return v.permute(0, 3, 1, 4, 2, 5).contiguous().view(torch.uint8).reshape(T, 65536)
+
+
+@pytest.mark.parametrize("x_dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("P,L", [(1000, 3), (128, 1), (128 * 301 + 5, 2), (77, 4)])
+def test_wgrad_kernel_vs_torch(ops, x_dtype, P, L):
+    """cng_film_siren_wgrad: dW_l = dz_l^T x_l by tcgen05 with MN-major operands read from the tile images (dz bf16; x bf16, or
+    fp16 converted to bf16 in shared memory), fp32 TMEM accumulation, red.global.add flush; column sums of dz."""
+    g = torch.Generator().manual_seed(P + L)
+    dz = [torch.randn((P, 256), generator=g) * (0.5 + l) for l in range(L)]
+    xs = [torch.sin(torch.randn((P, 256), generator=g) * 3) for _ in range(max(L - 1, 1))]
+    feat = torch.randn((P, 32), generator=g) * 0.3
+    hi = feat.to(x_dtype).float()
+    lo = (feat - hi).to(x_dtype).float()
+    dz_img = torch.stack([to_tile_images(d, torch.bfloat16) for d in dz]).cuda()
+    x_img = torch.stack([to_tile_images(x, x_dtype) for x in xs]).cuda()
+    f_img = to_tile_images(torch.cat([hi, lo], dim=1), x_dtype).cuda()
+    dW = [torch.zeros((256, 32 if l == 0 else 256), device="cuda") for l in range(L)]
+    colsum = torch.zeros((L, 256), device="cuda")
+    for rep in range(2):                                                  # accumulation semantics: the second call doubles everything
+        ops.film_siren_wgrad(dz_img, x_img, f_img, P, L, x_dtype == torch.float16, dW, colsum)
+    torch.cuda.synchronize()
+    for l in range(L):
+        dzr = dz[l].to(torch.bfloat16).double()
+        # an fp16 dump is rounded to bf16 element by element before the MMA
+        rb = (lambda t: t.to(torch.bfloat16).double()) if x_dtype == torch.float16 else (lambda t: t.double())
+        xr = (rb(hi) + rb(lo)) if l == 0 else rb(xs[l - 1].to(x_dtype).float())
+        ref = 2 * dzr.t() @ xr
+        e = rel_l2(dW[l].cpu(), ref)
+        print(f"wgrad P={P} L={L} {x_dtype} layer {l}: rel-L2 {e:.2e}")
+        assert e < 1e-5, (l, e)
+        assert rel_l2(colsum[l].cpu(), 2 * dzr.sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("P,L,sig", [(1000, 3, True), (128, 1, False), (128 * 301 + 5, 2, True), (77, 8, False)])
+def test_dgrad_kernel_vs_torch(ops, P, L, sig):
+    """cng_film_siren_dgrad: the fused chain d_o -> dy -> dz_l = dy * g_l -> dy = dz_l W_l ... -> d_feat on synthetic g."""
+    g = torch.Generator().manual_seed(P * 3 + L)
+    ws = [torch.randn((256, 32 if l == 0 else 256), generator=g) * (0.2 if l == 0 else 0.06) for l in range(L)]
+    fw = torch.randn((4, 256), generator=g) * 0.1
+    gs = [torch.randn((P, 256), generator=g) * 1.5 for _ in range(L)]
+    d_out = torch.randn((P, 4), generator=g)
+    out = torch.rand((P, 4), generator=g)
+    wt = ops.film_siren_wt_images([w.cuda() for w in ws], fw.cuda())
+    g_img = torch.stack([to_g_images(x) for x in gs]).cuda()
+    d_fb = torch.zeros((4,), device="cuda")
+    d_feat, dz_img = ops.film_siren_dgrad(d_out.cuda(), out.cuda(), sig, L, wt, g_img, d_fb)
+    torch.cuda.synchronize()
+    bf = lambda t: t.to(torch.bfloat16).double()
+    d_o = d_out.clone().double()
+    if sig:
+        d_o[:, :3] *= (out[:, :3] * (1 - out[:, :3])).double()
+    assert rel_l2(d_fb.cpu(), d_o.sum(0)) < 1e-5
+    dy = d_o @ bf(fw)                       # d_o enters as hi + lo (~fp32), Wf as bf16
+    for l in reversed(range(L)):
+        dz = dy * gs[l].to(torch.float16).double()
+        got = from_tile_images(dz_img[l], P, torch.bfloat16)
+        e = rel_l2(got, dz)
+        print(f"dgrad P={P} L={L} layer {l}: dz rel-L2 {e:.2e}")
+        assert e < 6e-3, (l, e)             # bf16 rounding of dz (2^-9 relative per element), accumulated over the layers
+        dy = bf(dz.float()) @ bf(ws[l])
+    e = rel_l2(d_feat.cpu(), dy)
+    print(f"dgrad P={P} L={L}: d_feat rel-L2 {e:.2e}")
+    assert e < 6e-3 and d_feat.shape == (P, 32)
+
+
+def test_fwd_train_dumps_vs_oracle(ops):
+    """cng_film_siren_fwd_train: x tile images, g = freq * cos(u) and the layer-0 operand block against the oracle's activations."""
+    from test_gpu_parity import _mlp_setup
+    B, N = 2, 300
+    spec, ws, bs, feat, freq, phase, fw, fb, ref = _mlp_setup("SHORTSIREN_FG", B, N, 0.3)
+    out, xs, gs, fd = ops.film_siren_fwd_train(dev(feat), [dev(w) for w in ws], [dev(b) for b in bs], dev(freq), dev(phase), dev(fw), dev(fb),
+                                               spec["sigmoid_rgb"], "fp16")
+    torch.cuda.synchronize()
+    assert (out.cpu() - ref).abs().max().item() < 1e-2
+    L, tpi = len(ws), (N + 127) // 128
+    x = feat
+    for l in range(L):
+        u = freq[:, l * 256:(l + 1) * 256].unsqueeze(1) * torch.nn.functional.linear(x, ws[l], bs[l]) + phase[:, l * 256:(l + 1) * 256].unsqueeze(1)
+        x = torch.sin(u)
+        gref = freq[:, l * 256:(l + 1) * 256].unsqueeze(1) * torch.cos(u)
+        for b in range(B):
+            got_x = from_tile_images(xs[l, b * tpi:(b + 1) * tpi], N, torch.float16)
+            assert (got_x - x[b]).abs().max().item() < 5e-2, (l, b)        # hidden activations of SHORTSIREN_FG carry the fp16-operand error of the layers before
+            gi = gs[l, b * tpi:(b + 1) * tpi].cpu().contiguous().view(torch.float16).view(tpi, 8, 4, 4, 32, 8)
+            got_g = gi.permute(0, 2, 4, 1, 3, 5).reshape(tpi * 128, 256)[:N].float()
+            assert (got_g - gref[b]).abs().max().item() < 1.5, (l, b, (got_g - gref[b]).abs().max().item())     # |g| ~ 30, u carries the 16-bit operand error
+    for b in range(B):
+        f = from_tile_images(fd[b * tpi:(b + 1) * tpi], N, torch.float16, nb=1)
+        assert (f[:, :32] + f[:, 32:] - feat[b]).abs().max().item() < 1e-5
 
 
 def _oracle_grads(state, siren_type, z, cam, draws, meta, d_pix, d_dep):
