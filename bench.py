@@ -432,9 +432,9 @@ def measure_train(args, rank, world, local, dev, barrier, max_over_ranks, steps,
     from conditioned_nerf_gan_b200.generators.unet3d import UNet3D
     from conditioned_nerf_gan_b200.generators.volumetric_rendering import create_cam2world_matrix, sample_camera_positions
     from conditioned_nerf_gan_b200.training import GanTrainStep
-    GLOBAL_B, img, S, V = 32, 128, 48, 64
+    GLOBAL_B, img, S, V = args.global_batch, 128, 48, 64
     if GLOBAL_B % world:
-        raise SystemExit("global batch 32 must divide by the number of GPUs")
+        raise SystemExit(f"global batch {GLOBAL_B} must divide by the number of GPUs")
     b = GLOBAL_B // world
     rng = torch.random.get_rng_state()
     torch.manual_seed(0)                                            # same random-init weights on every rank (reference init distributions)
@@ -462,9 +462,15 @@ def measure_train(args, rank, world, local, dev, barrier, max_over_ranks, steps,
         results.append(float(losses["d_loss"].item()) + float(losses["g_loss"].item()))     # device->host read of the step's result
 
     sampler = ClockSampler(local) if rank == 0 else None
-    t_host = time.perf_counter()
     ms, launches = _timed_steps(step, steps, warmup, barrier, max_over_ranks)
     clocks = sampler.stop() if sampler else None
+    # host time to ISSUE one step (no device wait inside: the losses are not read), against the device time above
+    torch.cuda.synchronize()
+    t_host = time.perf_counter()
+    sample = {"img": img_h.to(dev, non_blocking=True), "voxel": voxel_h.to(dev, non_blocking=True), "cam2world": cam_h.to(dev, non_blocking=True)}
+    trainer.step(sample)
+    host_issue_ms = (time.perf_counter() - t_host) * 1e3
+    torch.cuda.synchronize()
     # the gradient all-reduce alone: one flat buffer of the step's gradient bytes (G + E + D parameters, fp32) over NCCL,
     # timed with CUDA events (inside the step DDP overlaps it with the backward kernels)
     n_param = sum(p.numel() for m in (gen, enc, disc) for p in m.parameters())
@@ -485,7 +491,7 @@ def measure_train(args, rank, world, local, dev, barrier, max_over_ranks, steps,
     L = SIREN_LAYERS[args.siren]
     pts = GLOBAL_B * img * img * 2 * S
     out = {"images_per_s": GLOBAL_B * steps / (ms * 1e-3), "ms_per_step": ms / steps, "global_batch": GLOBAL_B, "batch_per_gpu": b,
-           "steps": steps, "warmup": warmup, "launches": launches // max(steps, 1), "allreduce_ms": allreduce_ms,
+           "steps": steps, "warmup": warmup, "launches": launches // max(steps, 1), "host_issue_ms": host_issue_ms, "allreduce_ms": allreduce_ms,
            "allreduce_bytes": 4 * n_param, "scaling": "strong", "final_loss": results[-1], "clocks": clocks,
            "h2d_bytes_per_step": int((voxel_h.numel() + img_h.numel() + cam_h.numel()) * 4), "d2h_bytes_per_step": 8,
            "mlp_flops_per_step": 3 * 2 * mlp_flops_per_point(L) * pts,
@@ -601,9 +607,9 @@ def run_train_generator(args):
     """Generator-only train step (BASELINE config 3 minus the out-of-scope encoder / discriminator)."""
     import torch.distributed as dist
     rank, world, local, dev, barrier, max_over_ranks = _setup_ranks(args)
-    GLOBAL_B, img, S, V = 32, 128, 48, 64
+    GLOBAL_B, img, S, V = args.global_batch, 128, 48, 64
     if GLOBAL_B % world:
-        raise SystemExit("global batch 32 must divide by the number of GPUs")
+        raise SystemExit(f"global batch {GLOBAL_B} must divide by the number of GPUs")
     b = GLOBAL_B // world
     meta = render_meta(img, S)
     meta["nerf_noise"] = 0.5
@@ -643,7 +649,7 @@ def run_train_generator(args):
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": "generator_train_step_128x128_48+48spp_global_batch32 (BASELINE configs[2] without the out-of-scope U-Net encoder and discriminator)",
                            "siren_type": args.siren, "batch_per_gpu": b, "optimizer": "Adam", "grad_allreduce": "DDP/NCCL" if world > 1 else "none",
-                           "backward": "hand-written compositing/scatter/FiLM-sin kernels + cuBLAS bf16 layer GEMMs (activation recompute)"},
+                           "backward": "hand-written kernels throughout: compositing / scatter, training-mode forward (recompute), tcgen05 dgrad chain, tcgen05 split-K weight gradient"},
                 "e2e": {"value": GLOBAL_B * args.steps / (ms * 1e-3), "unit": "images/s",
                         "h2d_bytes_per_step": int((vol_h.numel() + glob_h.numel() + cam_h.numel() + target_h.numel()) * 4), "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "clocks": clocks, "final_loss": final_loss,
@@ -712,6 +718,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the config-3 train-step leg of the default line")
     ap.add_argument("--train-steps", type=int, default=4)
+    ap.add_argument("--global-batch", type=int, default=32, help="train legs: global batch (BASELINE configs[2]: 32; other values are experiments)")
     ap.add_argument("--no-extras", action="store_true", help="skip the c5 micro-benchmark table and the GPU-eager comparator")
     ap.add_argument("--workload", default="render", choices=["render", "train", "train_generator", "video"])
     args = ap.parse_args()

@@ -4,7 +4,9 @@
 // Replaces autograd's walk back through FiLMLayer.forward x L + head (generators/siren.py:146-160, 573-579; what
 // loss.backward() runs at utils.py:711) for one chunk of P points of one batch item, given the dumps of the training-mode
 // forward (film_siren_tc.cu, kTrain): per layer l the output x_{l+1} = sin(u_l) as ready-made 128-point operand tile
-// images, and the local derivative g_l = freq * cos(u_l) (fp16) in the epilogue's own register order.
+// images, and g_l = cos(u_l) (fp16) in the epilogue's own register order.  The FiLM frequency never appears elementwise:
+// with dz'_l = dy_l * cos(u_l) the chain is dy_{l-1} = dz'_l (diag(freq_l) W_l) -- the forward's folded weights, transposed --
+// and the host recovers dW_l = diag(freq_l) dz'^T x, db = freq * colsum', dphase = colsum', dfreq = rowsum(W * dW') + b * colsum'.
 //
 //   B1  film_siren_dgrad_kernel   per 128-point tile, all layers fused, gradients never leave the SM between layers:
 //         d_o = d_out (* rgb (1 - rgb))                                  prologue, split hi/lo -> A tile
@@ -57,6 +59,7 @@ __host__ __device__ inline size_t wt_offset(int L, int l, int c) {      // l == 
 
 struct WtFoldParams {
   const float* w[16];
+  const float* freq;        // [L*256] or NULL: row n of W_l is scaled by freq_l[n] (the FiLM frequency folded into the dgrad operand)
   const float* final_w;
   int L;
   uint8_t* images;
@@ -85,7 +88,8 @@ __global__ void __launch_bounds__(256) wt_fold_kernel(WtFoldParams p) {
     const int r = static_cast<int>(e % (256 * 32));
     const int k = r >> 5, n0 = (r & 31) * 8;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = to16<false>(__ldg(p.w[l] + static_cast<size_t>(n0 + i) * kHID + k));
+    for (int i = 0; i < 8; ++i)
+      v[i] = to16<false>(__ldg(p.w[l] + static_cast<size_t>(n0 + i) * kHID + k) * (p.freq ? __ldg(p.freq + l * kHID + n0 + i) : 1.f));
     *reinterpret_cast<uint4*>(p.images + wt_offset(L, l, n0 >> 6) + sw128_offset(k, n0 & 63)) = *reinterpret_cast<uint4*>(v);
     return;
   }
@@ -93,7 +97,7 @@ __global__ void __launch_bounds__(256) wt_fold_kernel(WtFoldParams p) {
   {                                                    // layer 0: B[k < 32][n] = W_0[n][k], 4 K-blocks of [32 rows][64 n] (4 KB each)
     const int k = static_cast<int>(e >> 5), n0 = static_cast<int>(e & 31) * 8;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = to16<false>(__ldg(p.w[0] + static_cast<size_t>(n0 + i) * kC0 + k));
+    for (int i = 0; i < 8; ++i) v[i] = to16<false>(__ldg(p.w[0] + static_cast<size_t>(n0 + i) * kC0 + k) * (p.freq ? __ldg(p.freq + n0 + i) : 1.f));
     *reinterpret_cast<uint4*>(p.images + wt_offset(L, 0, 0) + (n0 >> 6) * 4096 + sw128_offset(k, n0 & 63)) = *reinterpret_cast<uint4*>(v);
   }
 }
@@ -589,46 +593,73 @@ __global__ void __launch_bounds__(kThreadsW, 1) film_siren_wgrad_kernel(WgradPar
 }
 
 // ---- head: d_final_w[c][j] += sum_p d_o[p][c] x_L[p][j] ---------------------------------------------------------------
-// one block per slab of tiles, thread j owns hidden column j; x_L is read from its tile images (un-swizzled on the fly)
+// One block per slab of tiles; x_L is read from its tile images 16 bytes at a time: lane = (K-block, logical 16-byte chunk) of
+// one row, so a warp reads the four 128-byte lines of a row per load; warp w takes rows w, w + 8, ... of every tile.
 template <bool kHalf>
 __global__ void __launch_bounds__(256) head_wgrad_kernel(const float* __restrict__ d_out, const float* __restrict__ out, int sigmoid_rgb,
                                                          const uint8_t* __restrict__ xL, long long P, long long T, float* __restrict__ d_final_w) {
   __shared__ float4 s_do[kTileM];
-  const int j = threadIdx.x;
+  __shared__ float s_red[8][4][kHID];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const long long t_begin = blockIdx.x * T / gridDim.x, t_end = (blockIdx.x + 1) * T / gridDim.x;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  const int blk = j >> 6, kc = (j & 63) >> 3, kb = (j & 7) * 2;
+  float acc[4][8];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[c][e] = 0.f;
+  const int blk = lane >> 3, ch = lane & 7;               // columns 64 blk + 8 ch .. + 7
   for (long long t = t_begin; t < t_end; ++t) {
     const long long n0 = t * kTileM;
     __syncthreads();
-    if (j < kTileM) {
+    if (tid < kTileM) {
       float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n0 + j < P) {
-        d = __ldg(reinterpret_cast<const float4*>(d_out) + n0 + j);
+      if (n0 + tid < P) {
+        d = __ldg(reinterpret_cast<const float4*>(d_out) + n0 + tid);
         if (sigmoid_rgb) {
-          const float4 y = __ldg(reinterpret_cast<const float4*>(out) + n0 + j);
+          const float4 y = __ldg(reinterpret_cast<const float4*>(out) + n0 + tid);
           d.x *= y.x * (1.f - y.x);
           d.y *= y.y * (1.f - y.y);
           d.z *= y.z * (1.f - y.z);
         }
       }
-      s_do[j] = d;
+      s_do[tid] = d;
     }
     __syncthreads();
     const uint8_t* img = xL + static_cast<size_t>(t) * kTileImageBytes + blk * kABlockBytes;
-#pragma unroll 8
-    for (int r = 0; r < kTileM; ++r) {
-      const uint16_t hv = __ldg(reinterpret_cast<const uint16_t*>(img + r * 128 + ((kc ^ (r & 7)) << 4) + kb));
-      const float xv = from16<kHalf>(hv);
+#pragma unroll 4
+    for (int r = w; r < kTileM; r += 8) {
+      const uint4 q4 = __ldg(reinterpret_cast<const uint4*>(img + r * 128 + ((ch ^ (r & 7)) << 4)));
+      const uint32_t qw[4] = {q4.x, q4.y, q4.z, q4.w};
       const float4 d = s_do[r];
-      acc[0] = fmaf(d.x, xv, acc[0]);
-      acc[1] = fmaf(d.y, xv, acc[1]);
-      acc[2] = fmaf(d.z, xv, acc[2]);
-      acc[3] = fmaf(d.w, xv, acc[3]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float x0, x1;
+        if (kHalf) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&qw[e]));
+          x0 = f.x; x1 = f.y;
+        } else {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qw[e]));
+          x0 = f.x; x1 = f.y;
+        }
+        acc[0][2 * e] = fmaf(d.x, x0, acc[0][2 * e]); acc[0][2 * e + 1] = fmaf(d.x, x1, acc[0][2 * e + 1]);
+        acc[1][2 * e] = fmaf(d.y, x0, acc[1][2 * e]); acc[1][2 * e + 1] = fmaf(d.y, x1, acc[1][2 * e + 1]);
+        acc[2][2 * e] = fmaf(d.z, x0, acc[2][2 * e]); acc[2][2 * e + 1] = fmaf(d.z, x1, acc[2][2 * e + 1]);
+        acc[3][2 * e] = fmaf(d.w, x0, acc[3][2 * e]); acc[3][2 * e + 1] = fmaf(d.w, x1, acc[3][2 * e + 1]);
+      }
     }
   }
 #pragma unroll
-  for (int c = 0; c < 4; ++c) atomicAdd(d_final_w + c * kHID + j, acc[c]);
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_red[w][c][blk * 64 + ch * 8 + e] = acc[c][e];
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float a = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) a += s_red[ww][c][tid];
+    atomicAdd(d_final_w + c * kHID + tid, a);
+  }
 }
 
 struct Layout {
@@ -692,7 +723,8 @@ size_t cng_film_siren_bwd_workspace_bytes(long long P, int C, int HID, int L) {
 
 size_t cng_film_siren_wt_image_bytes(int L) { return (L < 1 || L > 16) ? 0 : cng::bwdtc::wt_image_bytes(L); }
 
-int cng_film_siren_wt_images(const float* const* layer_w_host, const float* final_w, int C, int HID, int L, void* images, cng_stream_t stream) {
+int cng_film_siren_wt_images(const float* const* layer_w_host, const float* freq, const float* final_w, int C, int HID, int L, void* images,
+                             cng_stream_t stream) {
   using namespace cng;
   using namespace cng::bwdtc;
   CNG_REQUIRE(C == kC0 && HID == kHID && L >= 1 && L <= 16, CNG_ERR_UNSUPPORTED, "film_siren_wt_images: needs C=32, HID=256, L<=16");
@@ -704,7 +736,7 @@ int cng_film_siren_wt_images(const float* const* layer_w_host, const float* fina
     CNG_REQUIRE(layer_w_host[l], CNG_ERR_INVALID_ARGUMENT, "film_siren_wt_images: NULL layer %d", l);
     fp.w[l] = layer_w_host[l];
   }
-  fp.final_w = final_w; fp.L = L; fp.images = static_cast<uint8_t*>(images);
+  fp.freq = freq; fp.final_w = final_w; fp.L = L; fp.images = static_cast<uint8_t*>(images);
   const long long n = 256 * 8 + static_cast<long long>(L - 1) * 256 * 32 + 32 * 32;
   wt_fold_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(fp);
   return check_launch("cng_film_siren_wt_images");
@@ -801,7 +833,7 @@ int cng_film_siren_bwd(const float* feat, const float* d_out, long long P, int C
                                          res_add_mask, static_cast<float*>(res_scratch)))
     return e;
   // 2. W^T operand images
-  if (int e = cng_film_siren_wt_images(layer_w_host, final_w, C, HID, L, ws + lay.wt, stream)) return e;
+  if (int e = cng_film_siren_wt_images(layer_w_host, freq, final_w, C, HID, L, ws + lay.wt, stream)) return e;
   // 3. dgrad chain: d_feat, d_final_b, dz tile images
   if (int e = cng_film_siren_dgrad(d_out, out_tmp, sigmoid_rgb, P, L, ws + lay.wt, ws + lay.gs, ws + lay.dzs, d_feat, d_final_b_acc, res_save_mask,
                                    res_add_mask, res_scratch, res_scratch_bytes, stream))

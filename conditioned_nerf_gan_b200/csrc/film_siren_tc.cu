@@ -57,6 +57,7 @@ namespace cng {
 
 constexpr int kRing = 3;
 constexpr int kDefaultCtaGroup = 1;   // measured: the pair kernel pays ~1300 cycles of cross-CTA hand-off per layer
+constexpr int kDefaultTrainPolyOneIn = 4;   // training-mode epilogue: one (sin, cos) pair in four on the FMA pipe (measured: 1.93 -> 1.80 ms per 1M points, profiles/r2_bwd_kernels.txt)
 constexpr int kDefaultPolyOneIn = 8;   // one sine in 8 on the FMA pipe: measured 2.77 -> 2.68 ms per launch once the shift handling left the epilogue chain (it was neutral before)
 constexpr int kEpiWarpsPerSlot = CNG_TC_EPI_WARPS;   // 4 or 8 (build-time knob, see build.py)
 constexpr int kBlocksPerWarp = 32 / kEpiWarpsPerSlot;      // 32-column accumulator blocks per epilogue warp
@@ -533,23 +534,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
           }
           if constexpr (kTrain) {
             // sin -> next layer's operand (shared memory A tile; the whole tile leaves as one bulk store after the layer);
-            // freq*cos -> fp16, stored straight from registers in the epilogue's own order: [cc][q][i][lane] x 16 B, i.e.
+            // cos -> fp16, stored straight from registers in the epilogue's own order: [cc][q][i][lane] x 16 B, i.e.
             // 512 contiguous bytes per warp and store instruction.  The dgrad kernel reads it back with the same mapping.
             uint4* gt = reinterpret_cast<uint4*>(p.dump_g + (static_cast<size_t>(l) * p.total_tiles + t) * (kTileM * kHID * 2));
-            const float* fq = p.freq + (static_cast<size_t>(ti.item) * L + l) * kHID + cc * 32;
             uint8_t* blk = smem + a_base + (cc >> 1) * kABlockBytes + row * 128;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 f0 = __ldg(reinterpret_cast<const float4*>(fq + 8 * i)), f1 = __ldg(reinterpret_cast<const float4*>(fq + 8 * i + 4));
-              const float fr[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
               uint32_t xo[4], gs[4];
 #pragma unroll
               for (int j = 0; j < 8; j += 2) {
                 float s0, c0, s1, c1;
-                __sincosf(__uint_as_float(v[8 * i + j]), &s0, &c0);
-                __sincosf(__uint_as_float(v[8 * i + j + 1]), &s1, &c1);
+                film_sincos<kPolyOneIn>(__uint_as_float(v[8 * i + j]), 8 * i + j, s0, c0);
+                film_sincos<kPolyOneIn>(__uint_as_float(v[8 * i + j + 1]), 8 * i + j + 1, s1, c1);
                 xo[j / 2] = pack2<kHalf>(s0, s1);                  // next layer's tensor-core operand == the x dump
-                gs[j / 2] = pack2<true>(fr[j] * c0, fr[j + 1] * c1);
+                gs[j / 2] = pack2<true>(c0, c1);
               }
               const int chunk = ((cc & 1) * 4 + i) ^ (row & 7);
               *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(xo[0], xo[1], xo[2], xo[3]);
@@ -693,7 +691,7 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
 
   TcParams p{};
   p.half_operands = half_operands;
-  p.dump_x = static_cast<uint8_t*>(dump_x); p.dump_g = static_cast<uint8_t*>(dump_g); p.dump_feat = static_cast<uint8_t*>(dump_feat); p.freq = freq;
+  p.dump_x = static_cast<uint8_t*>(dump_x); p.dump_g = static_cast<uint8_t*>(dump_g); p.dump_feat = static_cast<uint8_t*>(dump_feat);
   CNG_REQUIRE((dump_x == nullptr) == (dump_g == nullptr) && (dump_x == nullptr) == (dump_feat == nullptr), CNG_ERR_INVALID_ARGUMENT,
               "film_siren_fwd_train: the x, g and feature dumps go together");
   CNG_REQUIRE(((reinterpret_cast<uintptr_t>(dump_x) | reinterpret_cast<uintptr_t>(dump_g) | reinterpret_cast<uintptr_t>(dump_feat)) & 15) == 0,
@@ -740,18 +738,28 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
   using KernelFn = void (*)(TcParams);
   const int pl = (poly == 0 || poly == 4) ? poly : 8;          // shared mode and fp16 come in these three flavours
   const bool res = (res_save_mask | res_add_mask) != 0;
+  // share of the (sin, cos) pairs of the training-mode epilogue evaluated on the FMA pipe (it needs two MUFU ops per element otherwise)
+  static const int train_poly = [] {
+    const char* e = getenv("CNG_TC_TRAIN_POLY");
+    const int v = e ? atoi(e) : kDefaultTrainPolyOneIn;
+    return (v == 0 || v == 2 || v == 3 || v == 4) ? v : kDefaultTrainPolyOneIn;
+  }();
+  const KernelFn train_fn = half_operands ? (train_poly == 0 ? film_siren_tc_kernel<0, true, true> : train_poly == 2 ? film_siren_tc_kernel<2, true, true>
+                                             : train_poly == 3 ? film_siren_tc_kernel<3, true, true> : film_siren_tc_kernel<4, true, true>)
+                                          : (train_poly == 0 ? film_siren_tc_kernel<0, false, true> : train_poly == 2 ? film_siren_tc_kernel<2, false, true>
+                                             : train_poly == 3 ? film_siren_tc_kernel<3, false, true> : film_siren_tc_kernel<4, false, true>);
   const KernelFn fn = res ? (train ? (half_operands ? film_siren_tc_kernel<0, true, true, false, true> : film_siren_tc_kernel<0, false, true, false, true>)
                                    : half_operands ? film_siren_tc_kernel<8, true, false, false, true> : film_siren_tc_kernel<8, false, false, false, true>)
-                      : train ? (half_operands ? film_siren_tc_kernel<0, true, true> : film_siren_tc_kernel<0, false, true>)
+                      : train ? train_fn
                       : shared ? (half_operands ? (pl == 0 ? shared_kernel<0, true>() : pl == 4 ? shared_kernel<4, true>() : shared_kernel<8, true>())
                                                 : (pl == 0 ? shared_kernel<0, false>() : pl == 4 ? shared_kernel<4, false>() : shared_kernel<8, false>()))
                       : half_operands ? (pl == 0 ? film_siren_tc_kernel<0, true> : pl == 4 ? film_siren_tc_kernel<4, true> : film_siren_tc_kernel<8, true>)
                       : poly == 0 ? film_siren_tc_kernel<0, false> : poly == 2 ? film_siren_tc_kernel<2, false>
                       : poly == 3 ? film_siren_tc_kernel<3, false> : poly == 4 ? film_siren_tc_kernel<4, false> : film_siren_tc_kernel<8, false>;
   // function attributes are per device: the opt-in is cached per device ordinal (a process may render on several GPUs)
-  static bool attr_set[64][8][9] = {};
+  static bool attr_set[64][8][12] = {};
   const int variant = res ? 5 + (train ? 2 : half_operands ? 1 : 0) : train ? 2 : (half_operands ? 1 : 0) + (shared ? 3 : 0);
-  const int pslot = train ? (half_operands ? 1 : 5) : poly;       // the two operand formats of the training kernel share a variant row
+  const int pslot = train ? (half_operands ? 0 : 5) + (res ? 0 : train_poly) : poly;   // operand formats x poly shares of the training kernel share a variant row
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = -1;
   if (dev < 0 || !attr_set[dev][variant][pslot]) {

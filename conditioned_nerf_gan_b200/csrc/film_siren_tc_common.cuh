@@ -220,6 +220,28 @@ __device__ __forceinline__ float sin_fma(float x) {
   const uint32_t sign = __float_as_uint(t) << 31;       // parity of k
   return __uint_as_float(__float_as_uint(p * f) ^ sign);
 }
+// sin(x) and cos(x) together on the FMA/ALU pipes (shared range reduction; cos(pi f) as an even degree-6 minimax polynomial,
+// max error 6.7e-6): the training-mode epilogue needs both per element and would otherwise be MUFU-bound (2 ops per element)
+__device__ __forceinline__ void sincos_fma(float x, float& s, float& c) {
+  const float kMagic = 12582912.f;
+  const float t = fmaf(x, 0.31830988618379067f, kMagic);
+  const float k = t - kMagic;
+  const float f = fmaf(x, 0.31830988618379067f, -k);
+  const float f2 = f * f;
+  float ps = fmaf(f2, 2.2995474338531494f, -5.136905193328857f);
+  ps = fmaf(ps, f2, 3.1406400203704834f);
+  float pc = fmaf(f2, -1.222126841545105f, 4.04128360748291f);
+  pc = fmaf(pc, f2, -4.933938026428223f);
+  pc = fmaf(pc, f2, 0.9999933242797852f);
+  const uint32_t sign = __float_as_uint(t) << 31;
+  s = __uint_as_float(__float_as_uint(ps * f) ^ sign);
+  c = __uint_as_float(__float_as_uint(pc) ^ sign);
+}
+template <int kPolyOneIn>
+__device__ __forceinline__ void film_sincos(float x, int j, float& s, float& c) {
+  if (kPolyOneIn > 0 && (j % (kPolyOneIn > 0 ? kPolyOneIn : 1)) == kPolyOneIn - 1) sincos_fma(x, s, c);
+  else __sincosf(x, &s, &c);
+}
 template <int kPolyOneIn>
 __device__ __forceinline__ float film_sin(float x, int j) {
   if (kPolyOneIn > 0 && (j % (kPolyOneIn > 0 ? kPolyOneIn : 1)) == kPolyOneIn - 1) return sin_fma(x);
@@ -265,13 +287,13 @@ struct TcParams {
   //   dump_x  [L][T][64 KB]  the layer output x_{l+1} = sin(u_l) as the 128-point operand TILE IMAGE the next layer's MMA reads
   //           ([4 K-blocks][128 rows][64 x 16 bit], 128B-swizzled, operand format) -- one bulk store per tile-layer; the
   //           weight-gradient kernel (film_siren_bwd_tc.cu) reads it back with MN-major descriptors
-  //   dump_g  [L][T][64 KB]  the local derivative g_l = freq * cos(u_l) in fp16, in the epilogue's own register order
+  //   dump_g  [L][T][64 KB]  the local derivative g_l = cos(u_l) in fp16 (the FiLM frequency is folded into the backward's
+  //           weight images instead), in the epilogue's own register order
   //           [32-column block cc][lane quarter q][16-byte piece i][lane]: every store / load is 512 contiguous bytes per warp
   //   dump_feat [T][16 KB]   the layer-0 operand block [x_hi(32) | x_lo(32)]
   uint8_t* dump_x;
   uint8_t* dump_g;
   uint8_t* dump_feat;
-  const float* freq;        // [B, L*256], only read when dumping
   long long* trace;         // debug: clock64 timeline of CTA 0 (tools/trace_tc.py), NULL in production
   // residual blocks (TALLSIREN_dRes, generators/siren.py:218-230): bit l of res_save_mask = layer l's output is kept as the
   // residual, bit l of res_add_mask = the kept residual is added to layer l's pre-activation.  res_scratch: per CTA and

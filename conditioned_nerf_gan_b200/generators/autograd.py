@@ -109,9 +109,9 @@ class _FilmSiren(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out):
         """Chunked: per item and chunk of points one cng_film_siren_bwd call (recompute with dumps, dgrad chain, split-K
-        weight gradient, head -- all tcgen05, csrc/film_siren_bwd_tc.cu) accumulates dW_l = dz_l^T x_l and the column sums
-        of dz_l = dy_l * freq * cos(u_l); from them, per item:  db = colsum,  dphase = colsum / freq,
-        dfreq = rowsum(W * dW_item) / freq + b * dphase.
+        weight gradient, head -- all tcgen05, csrc/film_siren_bwd_tc.cu) accumulates dW'_l = dz'_l^T x_l and the column sums
+        of dz'_l = dy_l * cos(u_l) (the FiLM frequency is folded into the dgrad operand, never applied elementwise); from them,
+        per item:  dW = freq * dW',  db = freq * colsum',  dphase = colsum',  dfreq = rowsum(W * dW') + b * colsum'.
         Residual blocks (``res_add`` / ``res_save`` masks, siren.py:218-230): g_l is taken at the pre-activation that includes
         the re-added block input, so the per-layer rule is unchanged; the kept activation (output of the last ``save`` layer
         before l) additionally receives dz_l of the adding layer (inside the dgrad kernel)."""
@@ -125,31 +125,26 @@ class _FilmSiren(torch.autograd.Function):
         dev = feat.device
         d_out = d_out.contiguous().float()
         d_feat = torch.empty_like(feat)
-        d_freq = torch.zeros((B, L * H), dtype=torch.float32, device=dev)
-        d_phase = torch.zeros((B, L * H), dtype=torch.float32, device=dev)
-        d_ws = [torch.zeros_like(w) for w in ws]
-        d_bs = [torch.zeros_like(b) for b in bs]
         d_fw = torch.zeros_like(fw)
         d_fb = torch.zeros((4,), dtype=torch.float32, device=dev)
-        b_stack = torch.stack(bs)                                                  # [L, H]
+        # per item: dW' and the column sums of dz' (they are turned into dW / db / dphase / dfreq with the item's freq below,
+        # batched over the items: a handful of launches per backward instead of a handful per item)
+        dW_all = [torch.zeros((B,) + tuple(w.shape), dtype=torch.float32, device=dev) for w in ws]
+        colsum_all = torch.zeros((B, L, H), dtype=torch.float32, device=dev)
+        fr = freq.detach().float().contiguous()
+        ph = phase.detach().float().contiguous()
         for b in range(B):
-            fr_all, ph_all = freq[b].detach().float().contiguous(), phase[b].detach().float().contiguous()
-            safe_fr = torch.where(fr_all.abs() < 1e-12, torch.ones_like(fr_all), fr_all).view(L, H)
-            # per item: weight gradients and column sums are accumulated over the chunks and turned into db / dphase / dfreq
-            # once at the end (they depend on the item's freq)
-            dW_item = [torch.zeros_like(w) for w in ws]
-            colsum = torch.zeros((L, H), dtype=torch.float32, device=dev)
+            dW_item = [d[b] for d in dW_all]
             for r0 in range(0, N, CHUNK_ROWS):
                 r1 = min(N, r0 + CHUNK_ROWS)
-                ops.film_siren_bwd(feat[b, r0:r1].detach().contiguous(), d_out[b, r0:r1].contiguous(), ws, bs, fr_all, ph_all, fw, fb,
-                                   ctx.sigmoid_rgb, d_feat[b, r0:r1], dW_item, colsum, d_fw, d_fb, ctx.res_save, ctx.res_add)
-            dph = colsum / safe_fr                                             # [L, H]
-            d_phase[b] += dph.reshape(-1)
-            wdw = torch.stack([(ws[l] * dW_item[l]).sum(1) for l in range(L)])  # [L, H]
-            d_freq[b] += (wdw / safe_fr + b_stack * dph).reshape(-1)
-            for l in range(L):
-                d_ws[l] += dW_item[l]
-                d_bs[l] += colsum[l]
+                ops.film_siren_bwd(feat[b, r0:r1].detach().contiguous(), d_out[b, r0:r1].contiguous(), ws, bs, fr[b], ph[b], fw, fb,
+                                   ctx.sigmoid_rgb, d_feat[b, r0:r1], dW_item, colsum_all[b], d_fw, d_fb, ctx.res_save, ctx.res_add)
+        frv = fr.view(B, L, H)
+        d_phase = colsum_all.reshape(B, L * H)
+        wdw = torch.stack([(ws[l].unsqueeze(0) * dW_all[l]).sum(2) for l in range(L)], dim=1)       # [B, L, H]
+        d_freq = (wdw + torch.stack(bs).unsqueeze(0) * colsum_all).reshape(B, L * H)
+        d_ws = [(dW_all[l] * frv[:, l, :, None]).sum(0) for l in range(L)]
+        d_bs = [(colsum_all[:, l] * frv[:, l]).sum(0) for l in range(L)]
         return (d_feat, d_freq, d_phase, d_fw.to(final_w.dtype), d_fb.to(final_b.dtype), None, None, None, None,
                 *[g.to(p.dtype) for g, p in zip(d_ws, wb[:L])], *[g.to(p.dtype) for g, p in zip(d_bs, wb[L:])])
 

@@ -384,7 +384,7 @@ FEAT_IMAGE_BYTES = 16384
 def film_siren_fwd_train(feat, layer_w, layer_b, freq, phase, final_w, final_b, sigmoid_rgb: bool, precision: str = "fp16",
                          res_save_mask: int = 0, res_add_mask: int = 0):
     """Training-mode K2 (the backward's recompute): rgb_sigma [B,N,4] plus the dumps in the formats of include/cng_b200.h --
-    x [L,T,65536] uint8 (operand tile images), g [L,T,65536] uint8 (fp16, epilogue order), feat [T,16384] uint8 -- with
+    x [L,T,65536] uint8 (operand tile images), g = cos(u) [L,T,65536] uint8 (fp16, epilogue order), feat [T,16384] uint8 -- with
     T = B * ceil(N / 128)."""
     if precision not in ("bf16", "fp16"):
         raise ValueError("film_siren_fwd_train: precision must be 'bf16' or 'fp16'")
@@ -417,8 +417,8 @@ def film_siren_fwd_train(feat, layer_w, layer_b, freq, phase, final_w, final_b, 
     return out, xs, gs, fd
 
 
-def film_siren_wt_images(layer_w, final_w) -> torch.Tensor:
-    """Operand images of W_l^T and of the head for the dgrad chain (cng_film_siren_wt_images)."""
+def film_siren_wt_images(layer_w, final_w, freq=None) -> torch.Tensor:
+    """Operand images of (diag(freq_l) W_l)^T (plain W_l^T without ``freq`` [L*HID]) and of the head for the dgrad chain."""
     L = len(layer_w)
     ws = [_f32(w, f"layer_w[{i}]") for i, w in enumerate(layer_w)]
     final_w = _f32(final_w, "final_w")
@@ -427,7 +427,8 @@ def film_siren_wt_images(layer_w, final_w) -> torch.Tensor:
     img = torch.empty((int(lib.cng_film_siren_wt_image_bytes(L)),), dtype=torch.uint8, device=dev)
     w_arr = (ctypes.c_void_p * L)(*[w.data_ptr() for w in ws])
     with torch.cuda.device(dev), _timed("cng_film_siren_wt_images"):
-        _lib.call("cng_film_siren_wt_images", w_arr, _ptr(final_w), ws[0].shape[1], ws[0].shape[0], L, _ptr(img), _stream(final_w))
+        _lib.call("cng_film_siren_wt_images", w_arr, _ptr(_f32(freq, "freq")) if freq is not None else None, _ptr(final_w), ws[0].shape[1],
+                  ws[0].shape[0], L, _ptr(img), _stream(final_w))
     _count()
     return img
 
@@ -467,7 +468,8 @@ _BWD_WS = {}
 def film_siren_bwd(feat, d_out, layer_w, layer_b, freq, phase, final_w, final_b, sigmoid_rgb: bool,
                    d_feat, d_w_acc, colsum_acc, d_final_w_acc, d_final_b_acc, res_save_mask: int = 0, res_add_mask: int = 0) -> None:
     """The MLP backward of one chunk of points of one item as ONE library call (cng_film_siren_bwd): feat [P,C], d_out [P,4];
-    writes d_feat [P,C], accumulates into d_w_acc[l], colsum_acc [L,HID], d_final_w_acc, d_final_b_acc (all fp32)."""
+    writes d_feat [P,C], accumulates into d_w_acc[l] (= dz'^T x), colsum_acc [L,HID] (= colsum dz'), both without the FiLM
+    frequency (include/cng_b200.h), d_final_w_acc, d_final_b_acc (all fp32)."""
     P, C = feat.shape
     L = len(layer_w)
     HID = layer_w[0].shape[0]

@@ -276,10 +276,13 @@ CNG_API int cng_render_fwd(const float* vol_ndhwc, long long vol_item_stride, in
  *   x_dump    [L][T][65536]  output of layer l, x_{l+1} = sin(u_l), as 128-point operand tile images
  *                            ([4 K-blocks of 64 columns][128 rows][128 B], 128-byte swizzle: element (row, k) of a block at
  *                            row*128 + (((k>>3) ^ (row&7)) << 4) + (k&7)*2), in the operand format of `precision`
- *   g_dump    [L][T][65536]  g_l = freq * cos(u_l) in fp16, [32-column block cc 8][row quarter q 4][piece i 4][lane 32] x 16 B:
- *                            row = 32 q + lane, columns 32 cc + 8 i .. + 7
+ *   g_dump    [L][T][65536]  g_l = cos(u_l) in fp16, [32-column block cc 8][row quarter q 4][piece i 4][lane 32] x 16 B:
+ *                            row = 32 q + lane, columns 32 cc + 8 i .. + 7.  The FiLM frequency is not applied elementwise:
+ *                            with dz'_l = dy_l * cos(u_l) the chain is dy_{l-1} = dz'_l (diag(freq_l) W_l) and
+ *                            dW_l = diag(freq_l) dz'_l^T x_l, db_l = freq_l * colsum(dz'_l), dphase_l = colsum(dz'_l),
+ *                            dfreq_l = rowsum(W_l * dz'_l^T x_l) + b_l * colsum(dz'_l)
  *   feat_dump [T][16384]     the layer-0 operand block [x_hi(32) | x_lo(32)] (same swizzle)
- *   dz_dump   [L][T][65536]  dz_l = dy_l * g_l as bf16 tile images (written by the dgrad chain, read by the weight gradient)
+ *   dz_dump   [L][T][65536]  dz'_l = dy_l * g_l as bf16 tile images (written by the dgrad chain, read by the weight gradient)
  * ---------------------------------------------------------------------------------------- */
 /* Training-mode forward of K2 (the backward's activation recompute): the fused tcgen05 kernel of cng_film_siren_fwd(_res) that
  * ALSO writes the three dumps above (one bulk store per tile-layer for x, direct register stores for g).  `precision`:
@@ -293,11 +296,11 @@ CNG_API int cng_film_siren_fwd_train(const float* feat, int B, long long N, int 
                              unsigned res_add_mask, void* workspace, size_t workspace_bytes, void* res_scratch,
                              size_t res_scratch_bytes, float* rgb_sigma, void* x_dump, void* g_dump,
                              void* feat_dump, cng_stream_t stream);
-/* Operand images of W_l^T (bf16) and of the head for the dgrad chain; item independent.  `images`:
- * cng_film_siren_wt_image_bytes(L) bytes, 16-byte aligned. */
+/* Operand images (bf16) of (diag(freq_l) W_l)^T and of the head for the dgrad chain.  freq [L*HID] of the item, or NULL for
+ * plain W_l.  `images`: cng_film_siren_wt_image_bytes(L) bytes, 16-byte aligned. */
 CNG_API size_t cng_film_siren_wt_image_bytes(int L);
-CNG_API int cng_film_siren_wt_images(const float* const* layer_w_host, const float* final_w, int C, int HID, int L,
-                             void* images, cng_stream_t stream);
+CNG_API int cng_film_siren_wt_images(const float* const* layer_w_host, const float* freq, const float* final_w, int C,
+                             int HID, int L, void* images, cng_stream_t stream);
 /* The dgrad chain of P points, all layers fused per 128-point tile (gradients stay in TMEM / shared memory between layers):
  *   d_o = d_out (* rgb (1 - rgb) when sigmoid_rgb, with `out` the forward output), d_final_b_acc [4] += colsum(d_o),
  *   dy = d_o Wf, then for l = L-1 .. 0: dz_l = dy * g_l (-> dz_dump), dy = dz_l W_l; d_feat [P, 32] = dz_0 W_0 (written).
@@ -317,9 +320,9 @@ CNG_API int cng_film_siren_wgrad(const void* dz_dump, const void* x_dump, const 
  * images, dgrad chain, weight gradients, head weights.
  *   feat [P, C]; d_out [P, 4] gradient w.r.t. rgb_sigma;
  *   layer_w_host / layer_b_host: HOST arrays of L device pointers (fp32); freq, phase [L*HID] of this item; final_w [4, HID], final_b [4];
- *   outputs: d_feat [P, C] (written); accumulated (+=): d_w_acc_host[l] [HID, K_l] fp32, colsum_acc [L, HID] (column sums
- *   of dz_l: d_bias = colsum, d_phase = colsum / freq, d_freq = rowsum(W * dW) / freq + b * d_phase on the host),
- *   d_final_w_acc [4, HID], d_final_b_acc [4].
+ *   outputs: d_feat [P, C] (written); accumulated (+=): d_w_acc_host[l] [HID, K_l] fp32 = dz'_l^T x_l and colsum_acc [L, HID] =
+ *   column sums of dz'_l, both WITHOUT the FiLM frequency (see g_dump above: the host forms dW = freq * dW', d_bias =
+ *   freq * colsum', d_phase = colsum', d_freq = rowsum(W * dW') + b * colsum'), d_final_w_acc [4, HID], d_final_b_acc [4].
  *   workspace: cng_film_siren_bwd_workspace_bytes(P, C, HID, L), 256-byte aligned.  Residual masks / scratch as in
  *   cng_film_siren_fwd_res.  HID == 256, C == 32, P < 2^31. */
 CNG_API size_t cng_film_siren_bwd_workspace_bytes(long long P, int C, int HID, int L);

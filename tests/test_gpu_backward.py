@@ -194,7 +194,7 @@ def test_dgrad_kernel_vs_torch(ops, P, L, sig):
 
 
 def test_fwd_train_dumps_vs_oracle(ops):
-    """cng_film_siren_fwd_train: x tile images, g = freq * cos(u) and the layer-0 operand block against the oracle's activations."""
+    """cng_film_siren_fwd_train: x tile images, g = cos(u) and the layer-0 operand block against the oracle's activations."""
     from test_gpu_parity import _mlp_setup
     B, N = 2, 300
     spec, ws, bs, feat, freq, phase, fw, fb, ref = _mlp_setup("SHORTSIREN_FG", B, N, 0.3)
@@ -207,13 +207,13 @@ def test_fwd_train_dumps_vs_oracle(ops):
     for l in range(L):
         u = freq[:, l * 256:(l + 1) * 256].unsqueeze(1) * torch.nn.functional.linear(x, ws[l], bs[l]) + phase[:, l * 256:(l + 1) * 256].unsqueeze(1)
         x = torch.sin(u)
-        gref = freq[:, l * 256:(l + 1) * 256].unsqueeze(1) * torch.cos(u)
+        gref = torch.cos(u)
         for b in range(B):
             got_x = from_tile_images(xs[l, b * tpi:(b + 1) * tpi], N, torch.float16)
             assert (got_x - x[b]).abs().max().item() < 5e-2, (l, b)        # hidden activations of SHORTSIREN_FG carry the fp16-operand error of the layers before
             gi = gs[l, b * tpi:(b + 1) * tpi].cpu().contiguous().view(torch.float16).view(tpi, 8, 4, 4, 32, 8)
             got_g = gi.permute(0, 2, 4, 1, 3, 5).reshape(tpi * 128, 256)[:N].float()
-            assert (got_g - gref[b]).abs().max().item() < 1.5, (l, b, (got_g - gref[b]).abs().max().item())     # |g| ~ 30, u carries the 16-bit operand error
+            assert (got_g - gref[b]).abs().max().item() < 0.3, (l, b, (got_g - gref[b]).abs().max().item())     # u carries the 16-bit operand error x freq ~ 30
     for b in range(B):
         f = from_tile_images(fd[b * tpi:(b + 1) * tpi], N, torch.float16, nb=1)
         assert (f[:, :32] + f[:, 32:] - feat[b]).abs().max().item() < 1e-5
