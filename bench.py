@@ -233,6 +233,9 @@ def run_gpu(args):
     gen.siren.precision = args.precision
     vol_h, glob_h, cam_h = (t.pin_memory() for t in synthetic_inputs(B, V, seed=rank))
     vol, glob, cam = vol_h.to(dev), glob_h.to(dev), cam_h.to(dev)
+    # end-to-end leg: the host holds the feature volumes in fp16 (the dtype the encoder emits under the trainer's autocast,
+    # utils.py:643-647) unless --e2e-volume fp32; they are widened on the device in the layout pass (cng_volume_f16_to_channels_last)
+    vol_e2e_h = vol_h.half().pin_memory() if args.e2e_volume == "fp16" else vol_h
     torch.manual_seed(rank)
 
     def barrier():
@@ -256,7 +259,7 @@ def run_gpu(args):
     dep_h = torch.empty((B, img, img), dtype=torch.float32).pin_memory()
 
     def step_e2e():
-        v, g, c = vol_h.to(dev, non_blocking=True), glob_h.to(dev, non_blocking=True), cam_h.to(dev, non_blocking=True)
+        v, g, c = vol_e2e_h.to(dev, non_blocking=True), glob_h.to(dev, non_blocking=True), cam_h.to(dev, non_blocking=True)
         with torch.no_grad():
             px, dp = gen((v, g), c, **meta)
         pix_h.copy_(px, non_blocking=True)
@@ -278,21 +281,22 @@ def run_gpu(args):
 
     from conditioned_nerf_gan_b200.streaming import render_host_batches
 
-    def e2e_pipelined(steps):
+    def e2e_pipelined(steps, volume_h):
         """The public host-buffer API: every step's inputs start in pinned host memory and its image ends there;
         H2D of step i+1 and D2H of step i-1 overlap the kernels of step i (three streams, two buffer sets)."""
         n = 0
-        for px_h, dp_h in render_host_batches(gen, ((vol_h, glob_h, cam_h) for _ in range(steps)), meta, device=dev):
+        for px_h, dp_h in render_host_batches(gen, ((volume_h, glob_h, cam_h) for _ in range(steps)), meta, device=dev):
             n += 1
         assert n == steps
         torch.cuda.synchronize()
 
-    def timed_e2e(steps, warmup):
-        e2e_pipelined(warmup)
+    def timed_e2e(steps, warmup, volume_h=None):
+        volume_h = vol_e2e_h if volume_h is None else volume_h
+        e2e_pipelined(warmup, volume_h)
         barrier()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
-        e2e_pipelined(steps)
+        e2e_pipelined(steps, volume_h)
         end.record()
         barrier()
         return max_over_ranks(start.elapsed_time(end))
@@ -304,6 +308,8 @@ def run_gpu(args):
     # two complete K-step passes; the faster one is reported (host-side copies on shared hosts see neighbour traffic), both are listed
     e2e_passes = [timed_e2e(args.steps, max(3, args.warmup)), timed_e2e(args.steps, 1)]
     ms_e2e = min(e2e_passes)
+    # the same with fp32 host volumes (two passes, the faster one: the first re-allocates the device staging buffers)
+    ms_e2e_fp32 = min(timed_e2e(args.steps, 3, vol_h), timed_e2e(args.steps, 1, vol_h)) if args.e2e_volume == "fp16" else ms_e2e
 
     # ---- roofline leg: per-entry-point CUDA-event durations over an instrumented pass of the same steps
     # (the timed steps above go through the one-call cng_render_fwd; here the same kernels are launched entry point by entry
@@ -361,7 +367,7 @@ def run_gpu(args):
                    "sample": f"batch 1 of 8, {img_cpu}x{img_cpu} rays, 24+24 samples, 64^3x32 volume, 1 timed render after 1 warm-up "
                              f"(torch-CPU oracle port of the reference path, fp32, {cores} threads)"}
         rays = world * B * R * args.steps
-        h2d = vol_h.numel() * 4 + glob_h.numel() * 4 + cam_h.numel() * 4
+        h2d = vol_e2e_h.numel() * vol_e2e_h.element_size() + glob_h.numel() * 4 + cam_h.numel() * 4
         d2h = pix_h.numel() * 4 + dep_h.numel() * 4
         line = {
             "metric": METRIC, "value": rays / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -370,7 +376,9 @@ def run_gpu(args):
             "config": workload_config(args, "gpu"),
             "e2e": {"value": rays / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "api": "streaming.render_host_batches (H2D / kernels / D2H on three streams, double-buffered)",
-                    "unpipelined_value": rays / (ms_e2e_sync * 1e-3), "passes_ms_per_step": [t / args.steps for t in e2e_passes]},
+                    "unpipelined_value": rays / (ms_e2e_sync * 1e-3), "passes_ms_per_step": [t / args.steps for t in e2e_passes],
+                    "host_volume_dtype": args.e2e_volume, "fp32_host_volume_value": rays / (ms_e2e_fp32 * 1e-3),
+                    "fp32_host_volume_h2d_bytes_per_step": vol_h.numel() * 4 + glob_h.numel() * 4 + cam_h.numel() * 4},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "train": train, "gpu_eager_baseline": eager, "c5": c5,
         }
@@ -518,7 +526,7 @@ def run_train(args):
                            "generator": "hand-written CUDA path: forward x2 (no-grad for the D step, with grad for the G step) + backward"},
                 "e2e": {"value": t["images_per_s"], "unit": "images/s", "h2d_bytes_per_step": t["h2d_bytes_per_step"], "d2h_bytes_per_step": 8},
                 "gpu_launches": t["launches"] * args.steps, "clocks": t["clocks"], "final_loss": t["final_loss"],
-                "allreduce_ms": t["allreduce_ms"], "mlp_flops_per_step": t["mlp_flops_per_step"]}
+                "allreduce_ms": t["allreduce_ms"], "host_issue_ms": t["host_issue_ms"], "mlp_flops_per_step": t["mlp_flops_per_step"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -716,6 +724,8 @@ def main():
     ap.add_argument("--precision", default=None, choices=["bf16", "fp16", "fp32"],
                     help="default: bf16 operands; fp16 for the classes offered with fp16 operands only (SHORTSIREN_FG)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-volume", default="fp16", choices=["fp16", "fp32"],
+                    help="dtype of the feature volumes in host memory for the end-to-end leg (fp16 = the encoder's autocast output dtype)")
     ap.add_argument("--no-train", action="store_true", help="skip the config-3 train-step leg of the default line")
     ap.add_argument("--train-steps", type=int, default=4)
     ap.add_argument("--global-batch", type=int, default=32, help="train legs: global batch (BASELINE configs[2]: 32; other values are experiments)")

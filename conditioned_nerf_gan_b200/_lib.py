@@ -24,6 +24,7 @@ SIGNATURES = {
     "cng_device_check": (c_int, []),
     "cng_camera_tables_host": (c_int, [c_int, c_int, c_int, c_double, c_double, c_double, c_void_p, c_void_p]),
     "cng_volume_to_channels_last": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "cng_volume_f16_to_channels_last": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "cng_raymarch_gather_coarse": (c_int, [c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cng_raymarch_gather_fine": (c_int, [c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,

@@ -19,6 +19,8 @@
 // explicit round-to-nearest intrinsics so no FMA contraction changes a floor():
 //   g = p / 0.6;  i = ((g + 1) * size - 1) / 2;  i = min(size-1, max(i, 0));  i0 = floor(i);
 //   w_lo = (i0 + 1) - i, w_hi = i - i0;  corners accumulated in ATen's order tnw..bse.
+#include <cuda_fp16.h>
+
 #include "cng_common.cuh"
 
 #ifndef CNG_K1_MIN_BLOCKS
@@ -269,19 +271,23 @@ __global__ void __launch_bounds__(256) gather_points_kernel(const float4* __rest
 // NCDHW -> NDHWC: block = one run of 32 voxels x all channels, staged through shared memory so
 // both the reads (32 consecutive voxels of one channel) and the writes (32 voxels x C floats,
 // contiguous) are full 128-byte lines.  CT = C when known at compile time (32: shifts instead of divisions).
-template <int CT>
-__global__ void __launch_bounds__(256) channels_last_kernel(const float* __restrict__ src, float* __restrict__ dst, int C_rt,
+__device__ __forceinline__ float load_as_float(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float load_as_float(const __half* p) { return __half2float(__ldg(p)); }
+
+// TIn: float, or __half for a volume uploaded in 16 bits (half the host->device bytes; widened here, in the pass that re-lays it)
+template <int CT, typename TIn>
+__global__ void __launch_bounds__(256) channels_last_kernel(const TIn* __restrict__ src, float* __restrict__ dst, int C_rt,
                                                              long long vox) {
   extern __shared__ float tile[];   // [C][33]
   const int C = CT > 0 ? CT : C_rt;
   const long long v0 = static_cast<long long>(blockIdx.x) * 32;
   const int b = blockIdx.y;
-  const float* s = src + static_cast<size_t>(b) * C * vox;
+  const TIn* s = src + static_cast<size_t>(b) * C * vox;
   float* d = dst + static_cast<size_t>(b) * C * vox;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long v = v0 + lane;
 #pragma unroll 4
-  for (int c = w; c < C; c += 8) tile[c * 33 + lane] = v < vox ? __ldg(s + static_cast<size_t>(c) * vox + v) : 0.f;
+  for (int c = w; c < C; c += 8) tile[c * 33 + lane] = v < vox ? load_as_float(s + static_cast<size_t>(c) * vox + v) : 0.f;
   __syncthreads();
   const int nv = static_cast<int>(min(32LL, vox - v0));
 #pragma unroll 4
@@ -299,12 +305,8 @@ static int check_volume(const void* vol, int B, int C, int D, int H, int W, cons
   return CNG_OK;
 }
 
-}  // namespace cng
-
-extern "C" {
-
-int cng_volume_to_channels_last(const float* vol_ncdhw, float* vol_ndhwc, int B, int C, int D, int H, int W,
-                                cng_stream_t stream) {
+template <typename TIn>
+static int volume_to_channels_last_impl(const TIn* vol_ncdhw, float* vol_ndhwc, int B, int C, int D, int H, int W, cng_stream_t stream) {
   CNG_REQUIRE(vol_ncdhw && vol_ndhwc, CNG_ERR_INVALID_ARGUMENT, "volume_to_channels_last: NULL pointer");
   CNG_REQUIRE(B >= 0 && C >= 1 && D >= 1 && H >= 1 && W >= 1, CNG_ERR_INVALID_ARGUMENT, "volume_to_channels_last: bad shape");
   CNG_REQUIRE(C <= 256 && B <= 65535, CNG_ERR_UNSUPPORTED, "volume_to_channels_last: C=%d B=%d", C, B);
@@ -313,9 +315,21 @@ int cng_volume_to_channels_last(const float* vol_ncdhw, float* vol_ndhwc, int B,
   const long long vox = static_cast<long long>(D) * H * W;
   dim3 grid(static_cast<unsigned>((vox + 31) / 32), B);
   const size_t smem = static_cast<size_t>(C) * 33 * sizeof(float);
-  if (C == 32) cng::channels_last_kernel<32><<<grid, 256, smem, cng::as_stream(stream)>>>(vol_ncdhw, vol_ndhwc, C, vox);
-  else cng::channels_last_kernel<0><<<grid, 256, smem, cng::as_stream(stream)>>>(vol_ncdhw, vol_ndhwc, C, vox);
-  return cng::check_launch("cng_volume_to_channels_last");
+  if (C == 32) channels_last_kernel<32, TIn><<<grid, 256, smem, as_stream(stream)>>>(vol_ncdhw, vol_ndhwc, C, vox);
+  else channels_last_kernel<0, TIn><<<grid, 256, smem, as_stream(stream)>>>(vol_ncdhw, vol_ndhwc, C, vox);
+  return check_launch("cng_volume_to_channels_last");
+}
+
+}  // namespace cng
+
+extern "C" {
+
+int cng_volume_to_channels_last(const float* vol_ncdhw, float* vol_ndhwc, int B, int C, int D, int H, int W, cng_stream_t stream) {
+  return cng::volume_to_channels_last_impl<float>(vol_ncdhw, vol_ndhwc, B, C, D, H, W, stream);
+}
+
+int cng_volume_f16_to_channels_last(const void* vol_ncdhw_f16, float* vol_ndhwc, int B, int C, int D, int H, int W, cng_stream_t stream) {
+  return cng::volume_to_channels_last_impl<__half>(static_cast<const __half*>(vol_ncdhw_f16), vol_ndhwc, B, C, D, H, W, stream);
 }
 
 static int raymarch_common(bool fine, const float* vol, long long vol_item_stride, int B, int C, int D, int H, int W, const float* cam2world,

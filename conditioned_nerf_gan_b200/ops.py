@@ -84,9 +84,19 @@ def volume_to_channels_last(vol: torch.Tensor) -> torch.Tensor:
     A volume the encoder already emits in ``torch.channels_last_3d`` memory format IS the kernel's layout: its
     storage is returned as a view and no kernel runs (the encoder emitting the volume in the
     gather kernel's layout)."""
-    if (isinstance(vol, torch.Tensor) and vol.is_cuda and vol.dtype == torch.float32 and vol.dim() == 5
+    if (isinstance(vol, torch.Tensor) and vol.is_cuda and vol.dim() == 5 and vol.dtype in (torch.float32, torch.float16, torch.bfloat16)
             and not vol.is_contiguous() and vol.is_contiguous(memory_format=torch.channels_last_3d)):
-        return vol.permute(0, 2, 3, 4, 1)
+        # (a 16-bit channels-last volume -- the encoder under autocast -- is widened in place of being re-laid: .float() keeps
+        # the memory format, so this is one pass and still no layout kernel)
+        return vol.float().permute(0, 2, 3, 4, 1)
+    if isinstance(vol, torch.Tensor) and vol.is_cuda and vol.dtype == torch.float16 and vol.dim() == 5:
+        vol = vol.contiguous()
+        B, C, D, H, W = vol.shape
+        out = torch.empty((B, D, H, W, C), dtype=torch.float32, device=vol.device)
+        with torch.cuda.device(vol.device), _timed("cng_volume_to_channels_last"):
+            _lib.call("cng_volume_f16_to_channels_last", _ptr(vol), _ptr(out), B, C, D, H, W, _stream(vol))
+        _count()
+        return out
     vol = _f32(vol, "volume")
     B, C, D, H, W = vol.shape
     out = torch.empty((B, D, H, W, C), dtype=torch.float32, device=vol.device)

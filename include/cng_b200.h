@@ -83,6 +83,10 @@ CNG_API int cng_camera_tables_host(int img_w, int img_h, int S, double fov_deg, 
  * ---------------------------------------------------------------------------------------- */
 CNG_API int cng_volume_to_channels_last(const float* vol_ncdhw, float* vol_ndhwc, int B, int C, int D,
                                 int H, int W, cng_stream_t stream);
+/* The same for a volume held in fp16 (the dtype the encoder emits under the trainer's autocast, utils.py:643-647; half the
+ * host->device bytes when volumes are streamed from host memory): widened to fp32 in the pass that re-lays it. */
+CNG_API int cng_volume_f16_to_channels_last(const void* vol_ncdhw_f16, float* vol_ndhwc, int B, int C, int D,
+                                    int H, int W, cng_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K1 coarse: sample generation + stratified jitter + cam->world + trilinear gather, fused.

@@ -804,6 +804,28 @@ def test_config2_full_size_vs_oracle():
             assert torch.equal(s1[0], a[i]) and torch.equal(ds1[0], da[i])
 
 
+def test_fp16_host_volume_path(ops):
+    """A feature volume held in fp16 (the encoder's autocast dtype; what bench.py's end-to-end leg uploads): the layout pass widens
+    it exactly (cng_volume_f16_to_channels_last), and the image stays at the tensor-core bar against the oracle on the fp32 volume."""
+    B, img, S, V = 1, 64, 12, 32
+    siren_type, state, z, cam, draws, meta = _full_size_case(B, img, S, V, 60, True)
+    v16 = dev(z[0]).half()
+    assert torch.equal(ops.volume_to_channels_last(v16), ops.volume_to_channels_last(v16.float()))
+    cl3 = v16.contiguous(memory_format=torch.channels_last_3d)          # 16-bit channels-last (U-Net under autocast): no layout kernel
+    n0 = ops.launch_count
+    assert torch.equal(ops.volume_to_channels_last(cl3), ops.volume_to_channels_last(v16))
+    assert ops.launch_count - n0 == 1
+    ref = oracle.render(state, siren_type, z, cam, draws, **meta)
+    d = {k: dev(v) for k, v in draws.items()}
+    for precision, min_psnr in (("fp32", 50.0), ("bf16", 40.0)):
+        gen = _generator(siren_type, state, precision)
+        with torch.no_grad():
+            px, dp = gen((v16, dev(z[1])), dev(cam), draws=d, **meta)
+        psnr = oracle.psnr(px.cpu(), ref["pixels"])
+        print(f"fp16 host volume, {precision} MLP: PSNR {psnr:.1f} dB vs the oracle on the fp32 volume")
+        assert psnr >= min_psnr
+
+
 def test_config4_frame_vs_oracle():
     """BASELINE configs[3]: one frame of the video workload at full size -- 256x256, 48+48 samples, 64^3 volume -- through
     staged_forward (chunked), against the oracle on the same draws (~15 s of CPU)."""
