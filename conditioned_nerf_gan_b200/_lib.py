@@ -58,6 +58,10 @@ SIGNATURES = {
     "cng_film_siren_bwd": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int, ctypes.c_uint, ctypes.c_uint, c_void_p, c_size_t, c_void_p,
                                    c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cng_group_norm_fwd": (c_int, [c_void_p, c_int, c_int, c_longlong, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p]),
+    "cng_group_norm_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p]),
     "cng_composite_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_int, c_int, c_int,
                                   c_void_p, c_void_p]),
     "cng_render_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int]),

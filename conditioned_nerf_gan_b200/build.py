@@ -15,7 +15,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libcng_b200.so")
 STAMP = os.path.join(PKG, "csrc", ".build_stamp")
-SOURCES = ["cng_api.cu", "raymarch_gather.cu", "film_siren_simt.cu", "film_siren_tc.cu", "composite.cu", "sample_pdf.cu", "backward.cu", "film_siren_bwd_tc.cu", "render.cu"]
+SOURCES = ["cng_api.cu", "raymarch_gather.cu", "film_siren_simt.cu", "film_siren_tc.cu", "composite.cu", "sample_pdf.cu", "backward.cu", "film_siren_bwd_tc.cu", "group_norm.cu", "render.cu"]
 # CNG_BUILD_EXPERIMENTAL=1 adds the two measured-slower K2 organisations kept for A/B work: CTA pairs
 # (cta_group::2) and the layer-pipelined single-tile kernel; selected at run time with CNG_TC_CG=2 / CNG_TC_V=3
 EXPERIMENTAL = os.environ.get("CNG_BUILD_EXPERIMENTAL", "0") == "1"

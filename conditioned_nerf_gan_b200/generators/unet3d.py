@@ -14,7 +14,11 @@ What is different, B200-first:
     ``cng_volume_to_channels_last`` launch, no 2 x 33.5 MB per image of layout traffic) and its backward hands the
     scatter-added volume gradient back in the same layout;
   * the bottleneck's global feature is one ``mean`` over the spatial axes instead of building an ``nn.AvgPool3d``
-    module per call (``unet3d.py:616-619``).
+    module per call (``unet3d.py:616-619``);
+  * GroupNorm (``nn.GroupNorm`` inside every ``SingleConv``, ``unet3d.py:21-132``) runs on the library's own channels-last
+    kernels (``cng_group_norm_fwd / _bwd``, csrc/group_norm.cu): ATen's group norm reads a channels-last tensor with a
+    stride of D*H*W elements per channel (0.44 ms per call on B200, 13 % of a batch-4 train step) after autocast has
+    widened it to fp32; the kernels here read and write the 16-bit tensor as it is, 16 bytes per access.
 """
 from __future__ import annotations
 
@@ -26,6 +30,48 @@ import torch.nn.functional as F
 
 
 FORCE_CONTIGUOUS = False     # tools/bench_unet.py: run the network NCDHW (the library then converts layouts per convolution)
+NATIVE_GROUP_NORM = True     # False: torch's F.group_norm everywhere (A/B and the CPU tests' path)
+
+
+class _GroupNormCL(torch.autograd.Function):
+    """GroupNorm on a channels-last CUDA tensor through cng_group_norm_fwd / cng_group_norm_bwd (output in the input's dtype)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, num_groups, eps):
+        from .. import ops
+        y, mean, rstd = ops.group_norm_channels_last(x, num_groups, weight, bias, eps)
+        ctx.save_for_backward(x, weight, mean, rstd)
+        ctx.num_groups = num_groups
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from .. import ops
+        x, weight, mean, rstd = ctx.saved_tensors
+        fmt = torch.channels_last_3d if x.dim() == 5 else torch.channels_last
+        dy = dy.to(x.dtype).contiguous(memory_format=fmt)
+        dx, ds, db = ops.group_norm_channels_last_bwd(dy, x, ctx.num_groups, weight, mean, rstd)
+        d_w = ds.sum(0).to(weight.dtype) if (weight is not None and ctx.needs_input_grad[1]) else None
+        d_b = db.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, d_w, d_b, None, None
+
+
+class GroupNormCL(nn.GroupNorm):
+    """``nn.GroupNorm`` (same parameters, same state-dict keys) that serves channels-last CUDA tensors with the library's kernels;
+    anything else (CPU, NCDHW) goes to ``F.group_norm``.  Under autocast the result keeps the input's dtype: the convolution
+    that follows would round torch's fp32 result to the same 16-bit values."""
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        fmt = torch.channels_last_3d if x.dim() == 5 else (torch.channels_last if x.dim() == 4 else None)
+        if (NATIVE_GROUP_NORM and x.is_cuda and fmt is not None and x.dtype in (torch.float32, torch.float16, torch.bfloat16)
+                and x.is_contiguous(memory_format=fmt) and x.shape[1] <= 1024 and self.num_groups <= 64):
+            cpg = x.shape[1] // self.num_groups
+            v = 8 if (x.dtype != torch.float32 and cpg % 8 == 0) else (4 if cpg % 4 == 0 else (2 if cpg % 2 == 0 else 1))
+            if x.shape[1] // v <= 256:
+                with torch.autocast("cuda", enabled=False):
+                    return _GroupNormCL.apply(x, self.weight, self.bias, self.num_groups, self.eps)
+        return super().forward(x)
 
 
 def number_of_features_per_level(init_channel_number: int, num_levels: int) -> List[int]:
@@ -53,7 +99,7 @@ class SingleConv(nn.Sequential):
                 groups = 1 if channels < num_groups else num_groups
                 if channels % groups:
                     raise AssertionError(f"Expected number of channels in input to be divisible by num_groups. num_channels={channels}, num_groups={groups}")
-                self.add_module("groupnorm", nn.GroupNorm(num_groups=groups, num_channels=channels))
+                self.add_module("groupnorm", GroupNormCL(num_groups=groups, num_channels=channels))
             elif ch == "b":
                 self.add_module("batchnorm", nn.BatchNorm3d(in_channels if before_conv else out_channels))
             elif ch == "r":

@@ -509,6 +509,45 @@ def film_siren_bwd(feat, d_out, layer_w, layer_b, freq, phase, final_w, final_b,
     _count(6)
 
 
+_GN_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def group_norm_channels_last(x, num_groups: int, weight, bias, eps: float):
+    """GroupNorm forward on a channels-last tensor (cng_group_norm_fwd).  x: [N, C, *spatial] whose memory is [N, *spatial, C]
+    (channels_last / channels_last_3d), fp32 / fp16 / bf16.  Returns (y in x's dtype and format, mean [N,G], rstd [N,G])."""
+    N, C = x.shape[0], x.shape[1]
+    S = x.numel() // max(N * C, 1)
+    dev = x.device
+    y = torch.empty_like(x)               # preserves the channels-last strides
+    mean = torch.empty((N, num_groups), dtype=torch.float32, device=dev)
+    rstd = torch.empty((N, num_groups), dtype=torch.float32, device=dev)
+    sums = torch.empty((N, num_groups, 2), dtype=torch.float64, device=dev)
+    w = _f32(weight, "weight") if weight is not None else None
+    b = _f32(bias, "bias") if bias is not None else None
+    with torch.cuda.device(dev), _timed("cng_group_norm_fwd"):
+        _lib.call("cng_group_norm_fwd", _ptr(x), _GN_DTYPES[x.dtype], N, S, C, num_groups, _ptr(w), _ptr(b), float(eps), _ptr(y), _ptr(mean),
+                  _ptr(rstd), _ptr(sums), _stream(x))
+    _count(2)
+    return y, mean, rstd
+
+
+def group_norm_channels_last_bwd(dy, x, num_groups: int, weight, mean, rstd):
+    """GroupNorm backward (cng_group_norm_bwd): returns (dx in x's dtype / format, ds [N,C], db [N,C]) with ds = sum dy * xhat,
+    db = sum dy per item and channel (d_weight = ds.sum(0), d_bias = db.sum(0))."""
+    N, C = x.shape[0], x.shape[1]
+    S = x.numel() // max(N * C, 1)
+    dev = x.device
+    dx = torch.empty_like(x)
+    ds = torch.empty((N, C), dtype=torch.float32, device=dev)
+    db = torch.empty((N, C), dtype=torch.float32, device=dev)
+    w = _f32(weight, "weight") if weight is not None else None
+    with torch.cuda.device(dev), _timed("cng_group_norm_bwd"):
+        _lib.call("cng_group_norm_bwd", _ptr(dy), _ptr(x), _GN_DTYPES[x.dtype], N, S, C, num_groups, _ptr(w), _ptr(mean), _ptr(rstd), _ptr(dx),
+                  _ptr(ds), _ptr(db), _stream(x))
+    _count(2)
+    return dx, ds, db
+
+
 def merge_sort(t_fine, t_coarse, want_sorted: bool = False):
     """a11 alone: order [n_rays, 2S] int32 of the stable fine-first sort of cat([t_fine, t_coarse]) (and the sorted distances)."""
     t_fine, t_coarse = _f32(t_fine, "t_fine"), _f32(t_coarse, "t_coarse")

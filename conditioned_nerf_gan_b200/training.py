@@ -125,8 +125,13 @@ class GanTrainStep:
             r_preds = self.discriminator_ddp(real_imgs, self.alpha, cond=None, **md)
         r1 = md.get("r1_lambda", 0)
         if r1 > 0:
-            grad_real = torch.autograd.grad(outputs=self.scaler.scale(r_preds.sum()), inputs=real_imgs, create_graph=True)[0]
-            grad_real = grad_real * (1.0 / self.scaler.get_scale() if self.scaler.is_enabled() else 1.0)
+            from .discriminators.discriminators import r1_pass
+            with r1_pass():
+                grad_real = torch.autograd.grad(outputs=self.scaler.scale(r_preds.sum()), inputs=real_imgs, create_graph=True)[0]
+            if self.scaler.is_enabled():
+                # un-scale on the device (GradScaler keeps its scale in a device tensor): get_scale() would be a host
+                # synchronisation in the middle of the step
+                grad_real = grad_real * self.scaler._scale.reciprocal().to(grad_real.dtype)
         with self._autocast():
             if r1 > 0:
                 grad_penalty = 0.5 * r1 * (grad_real.reshape(grad_real.size(0), -1).norm(2, dim=1) ** 2).mean()
@@ -202,7 +207,8 @@ class GanTrainStep:
     def step(self, sample: Dict) -> Dict[str, torch.Tensor]:
         """train.py:92-105 and :122-125: modes, ``set_alpha``, D step, G step, step counters.  Returns the step's losses as
         device scalars (read them with ``.item()`` when needed)."""
-        if self.scaler.is_enabled() and self.scaler.get_scale() < 1:
+        self._steps_done = getattr(self, "_steps_done", 0) + 1
+        if self.scaler.is_enabled() and self._steps_done % 64 == 1 and self.scaler.get_scale() < 1:      # (a host sync: not every step)
             self.scaler.update(1.0)
         self.generator_ddp.train()
         self.encoder_ddp.train()

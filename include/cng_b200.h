@@ -338,6 +338,23 @@ CNG_API int cng_film_siren_bwd(const float* feat, const float* d_out, long long 
                        float* const* d_w_acc_host, float* colsum_acc, float* d_final_w_acc, float* d_final_b_acc,
                        cng_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * GroupNorm of the 3D U-Net encoder (generators/unet3d.py:21-132, nn.GroupNorm in every SingleConv) on
+ * channels-last volumes x [N, S, C] (S = D*H*W; the memory of a channels_last_3d [N,C,D,H,W] tensor), the layout in which
+ * the encoder emits the feature volume the gather kernel reads.  dtype: 0 fp32, 1 fp16, 2 bf16 (x, y, dy, dx share it;
+ * statistics in fp32 / fp64).  gamma / beta [C] fp32 or NULL.  C <= 1024, G <= 64.
+ *   fwd: y = (x - mean) * rstd * gamma + beta; mean, rstd [N, G] are written (the backward reads them);
+ *        sums_scratch: N*G*2 doubles.
+ *   bwd: dx from dy; ds_scratch / db_scratch [N, C] fp32 receive sum_s dy * xhat and sum_s dy per item and channel
+ *        (d_gamma = their sum over N of ds, d_beta = of db: left to the caller).
+ * ---------------------------------------------------------------------------------------- */
+CNG_API int cng_group_norm_fwd(const void* x, int dtype, int N, long long S, int C, int G, const float* gamma,
+                       const float* beta, float eps, void* y, float* mean, float* rstd, double* sums_scratch,
+                       cng_stream_t stream);
+CNG_API int cng_group_norm_bwd(const void* dy, const void* x, int dtype, int N, long long S, int C, int G,
+                       const float* gamma, const float* mean, const float* rstd, void* dx, float* ds_scratch,
+                       float* db_scratch, cng_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -168,6 +168,40 @@ def test_gan_train_step_host_logic_matches_reference_on_cpu():
     assert norms[2][2] == pytest.approx(norms[1][2], rel=1e-4)
 
 
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("N,C,G,shape", [(2, 32, 8, (16, 16, 16)), (3, 4, 1, (9, 10, 11)), (1, 384, 8, (8, 8, 8)), (2, 96, 8, (5, 6, 7)), (2, 16, 8, (12, 12)),
+                                         (1, 256, 8, (32, 32, 32)), (2, 6, 3, (7, 5, 3))])
+def test_group_norm_channels_last_kernels_vs_torch(dtype, N, C, G, shape):
+    """cng_group_norm_fwd / _bwd (the U-Net's GroupNorm on channels-last tensors) against torch's group norm in float64."""
+    from conditioned_nerf_gan_b200.generators.unet3d import GroupNormCL
+    g = torch.Generator().manual_seed(C * 7 + N)
+    x = (torch.randn((N, C, *shape), generator=g) * 1.7 + 0.4)
+    fmt = torch.channels_last_3d if len(shape) == 3 else torch.channels_last
+    gn = GroupNormCL(G, C)
+    with torch.no_grad():
+        gn.weight.copy_(torch.randn(C, generator=g) * 0.5 + 1)
+        gn.bias.copy_(torch.randn(C, generator=g) * 0.3)
+    dy = torch.randn(x.shape, generator=g)
+    xr = x.to(dtype).double().requires_grad_(True)
+    ref = torch.nn.functional.group_norm(xr, G, gn.weight.detach().double(), gn.bias.detach().double(), gn.eps)
+    ref.backward(dy.to(dtype).double())
+    gn = gn.cuda()
+    xd = x.to(dtype).cuda().contiguous(memory_format=fmt).requires_grad_(True)
+    y = gn(xd)
+    assert y.dtype == dtype and y.is_contiguous(memory_format=fmt)
+    y.backward(dy.to(dtype).cuda().contiguous(memory_format=fmt))
+    tol = 2e-5 if dtype == torch.float32 else (2e-3 if dtype == torch.float16 else 1.6e-2)
+    assert (y.detach().cpu().double() - ref.detach()).abs().max().item() < tol * 4
+    rel = lambda a, b: float((a.double().cpu() - b).norm() / (b.norm() + 1e-30))
+    assert rel(xd.grad, xr.grad) < tol, rel(xd.grad, xr.grad)
+    # d_weight / d_bias against float64 on the same (rounded) input
+    w64, b64 = gn.weight.detach().double().cpu().requires_grad_(True), gn.bias.detach().double().cpu().requires_grad_(True)
+    torch.nn.functional.group_norm(x.to(dtype).double(), G, w64, b64, gn.eps).backward(dy.to(dtype).double())
+    ew, eb = rel(gn.weight.grad, w64.grad), rel(gn.bias.grad, b64.grad)
+    assert ew < tol and eb < tol, (ew, eb)
+
 @pytest.mark.gpu
 def test_gan_train_step_matches_reference_on_gpu():
     """The product's GanTrainStep (CUDA rendering path in exact-fp32 mode, cuDNN U-Net / discriminator) against the

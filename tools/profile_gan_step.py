@@ -43,3 +43,7 @@ print(f"no-grad forwards: encoder {t_enc:.1f} ms, generator {t_gen:.1f} ms, disc
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     tr.step(sample); torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=80))
+print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=25, max_name_column_width=80))
+import time
+torch.cuda.synchronize(); t0 = time.perf_counter(); tr.step(sample); t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+print(f"host time to issue one step {1e3 * (t1 - t0):.1f} ms; until the device is done {1e3 * (t2 - t0):.1f} ms")
