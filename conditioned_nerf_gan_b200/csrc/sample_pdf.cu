@@ -105,9 +105,92 @@ __global__ void __launch_bounds__(kPdfWarps * 32) sample_pdf_kernel(PdfParams p)
   }
 }
 
+// The same arithmetic with the ray's weights / pdf values in REGISTERS (PER consecutive elements per lane, PER = ceil(M / 32) <= 4;
+// measured on B200, 1M rays: 64 samples 0.650 -> 0.537 ms, 128 samples 1.046 -> 0.905 ms, 256 samples slower with 8 per lane)
+// and a branch-free search: the shared-memory round trips of the scan and the data-dependent loop of the binary search were
+// what kept the kernel at 25-31 % of the HBM roofline (issue-bound, profiles/r1g_sample_pdf_kernel_raw.txt).  Every
+// floating-point operation and its order are those of the kernel above, so the results are bit-identical.
+template <bool FROM_COARSE, int PER>
+__global__ void __launch_bounds__(kPdfWarps * 32) sample_pdf_reg_kernel(PdfParams p, int P2) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long ray = static_cast<long long>(blockIdx.x) * kPdfWarps + warp;
+  if (ray >= p.n) return;
+  const int M = p.M;
+  float* cdf = smem + static_cast<size_t>(warp) * (P2 + M + 1);      // cdf[0 .. P2): entries beyond M are +inf
+  float* bins = cdf + P2;                                             // bins[0 .. M]
+  const int j0 = lane * PER;
+  float w[PER];
+  if (FROM_COARSE) {
+    const float* tc = p.bins + ray * p.S;
+    const float* wc = p.weights + ray * p.S;
+    for (int j = lane; j <= M; j += 32) bins[j] = __fmul_rn(0.5f, __fadd_rn(__ldg(tc + j), __ldg(tc + j + 1)));
+#pragma unroll
+    for (int i = 0; i < PER; ++i) w[i] = (j0 + i < M) ? __fadd_rn(__fadd_rn(__ldg(wc + j0 + i + 1), 1e-5f), p.eps) : 0.f;
+  } else {
+    for (int j = lane; j <= M; j += 32) bins[j] = __ldg(p.bins + ray * (M + 1) + j);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) w[i] = (j0 + i < M) ? __fadd_rn(__ldg(p.weights + ray * M + j0 + i), p.eps) : 0.f;
+  }
+  for (int j = M + 1 + lane; j < P2; j += 32) cdf[j] = __int_as_float(0x7f800000);
+  double part = 0.0;                               // exact in float64 (see the kernel above): any association order gives the same bits
+#pragma unroll
+  for (int i = 0; i < PER; ++i) part += static_cast<double>(w[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  const float total = static_cast<float>(part);
+  double run = 0.0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    w[i] = (j0 + i < M) ? __fdiv_rn(w[i], total) : 0.f;
+    run += static_cast<double>(w[i]);
+  }
+  double incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  double acc = incl - run;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    acc += static_cast<double>(w[i]);
+    if (j0 + i < M) cdf[j0 + i + 1] = static_cast<float>(acc);
+  }
+  if (lane == 0) cdf[0] = 0.f;
+  __syncwarp();
+  // searchsorted(cdf, u, right=False) = number of cdf[0..M] that are < u; the +inf padding never counts
+  for (int k = lane; k < p.K; k += 32) {
+    const float u = __ldg(p.u + ray * p.K + k);
+    int pos = 0;
+    for (int step = P2 >> 1; step > 0; step >>= 1) pos += (cdf[pos + step - 1] < u) ? step : 0;
+    const int ind = pos;
+    const int below = max(ind - 1, 0);
+    const int above = min(ind, M);
+    const float c0 = cdf[below], c1 = cdf[above];
+    const float b0 = bins[below], b1 = bins[above];
+    float denom = __fsub_rn(c1, c0);
+    if (denom < p.eps) denom = 1.f;
+    const float frac = __fdiv_rn(__fsub_rn(u, c0), denom);
+    p.samples[ray * p.K + k] = __fadd_rn(b0, __fmul_rn(frac, __fsub_rn(b1, b0)));
+    if (p.inds) p.inds[ray * p.K + k] = ind;
+  }
+}
+
 template <bool FROM_COARSE>
 static int launch_pdf(const PdfParams& p, cudaStream_t stream, const char* what) {
   const unsigned grid = static_cast<unsigned>((p.n + kPdfWarps - 1) / kPdfWarps);
+  const int per = (p.M + 31) / 32;
+  if (per <= 4) {
+    int P2 = 2;
+    while (P2 < p.M + 2) P2 <<= 1;                 // P2 - 1 >= M + 1 searched entries
+    const size_t smem = static_cast<size_t>(kPdfWarps) * (P2 + p.M + 1) * sizeof(float);
+    if (per <= 1) sample_pdf_reg_kernel<FROM_COARSE, 1><<<grid, kPdfWarps * 32, smem, stream>>>(p, P2);
+    else if (per <= 2) sample_pdf_reg_kernel<FROM_COARSE, 2><<<grid, kPdfWarps * 32, smem, stream>>>(p, P2);
+    else sample_pdf_reg_kernel<FROM_COARSE, 4><<<grid, kPdfWarps * 32, smem, stream>>>(p, P2);
+    return check_launch(what);
+  }
   const size_t smem = static_cast<size_t>(kPdfWarps) * (2 * (p.M + 1) + 2) * sizeof(float);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(sample_pdf_kernel<FROM_COARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
