@@ -34,6 +34,8 @@ SIGNATURES = {
     "cng_film_siren_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "cng_film_siren_fwd": (c_int, [c_void_p, c_int, c_longlong, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "cng_film_siren_fwd_gather": (c_int, [c_void_p, c_longlong, c_int, c_int, c_int, c_void_p, c_int, c_longlong, c_int, c_int, c_int, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "cng_film_siren_res_scratch_bytes": (c_size_t, []),
     "cng_film_siren_fwd_res": (c_int, [c_void_p, c_int, c_longlong, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_int, c_int, ctypes.c_uint, ctypes.c_uint, c_void_p, c_size_t, c_void_p, c_size_t,

@@ -42,6 +42,7 @@
 #include "cng_common.cuh"
 
 #include "film_siren_tc_common.cuh"
+#include "trilinear.cuh"
 
 #ifndef CNG_TC_EPI_WARPS
 #define CNG_TC_EPI_WARPS 8
@@ -79,6 +80,14 @@ int film_siren_tc3_launch(TcParams p, int poly, cudaStream_t stream);   // film_
 // 1: the two-tile ping-pong kernel below, 8 epilogue warps bound to each tile slot; 2: the same with all 16 epilogue warps
 // shared between the slots; 3 (experimental builds only): the layer-pipelined kernel (film_siren_tc3.cu).  All give bit-identical results.
 constexpr int kDefaultKernelVersion = 1;   // measured (profiles/r1g_k2_versions.txt): 1 and 2 within 1-2 % on TALLSIREN_FG, 1 ahead for fewer layers, 3 behind by 10 %
+
+// fused-gather mode of film_siren_tc_launch: the features are looked up by the kernel itself
+struct GatherSource {
+  const float* vol_ndhwc;
+  long long vol_item_stride;     // floats; 0 = shared volume
+  int D, H, W;
+  const float* points;           // [B, N, 3]
+};
 
 static long long* g_tc_trace = nullptr;   // debug hook, see cng_internal_set_tc_trace
 static int g_tc_version = 0;              // 0: CNG_TC_V / default; 1 or 3: forced (cng_internal_set_tc_version, tests and A/B tools)
@@ -161,9 +170,10 @@ __global__ void __launch_bounds__(256) film_fold_kernel(FoldParams p) {
 // two strictly alternate: the tensor pipe runs back to back ("what the K2 numbers taught").
 // kRes: residual blocks (res_save_mask / res_add_mask of TcParams).  A separate instantiation: merely having the branch in the
 // epilogue costs the plain networks 4-5 % (same-box A/B, 2.95 vs 2.81 ms).
-template <int kPolyOneIn, bool kHalf, bool kTrain = false, bool kShared = false, bool kRes = false>
+template <int kPolyOneIn, bool kHalf, bool kTrain = false, bool kShared = false, bool kRes = false, bool kGather = false>
 __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams p) {
   static_assert(!(kShared && kRes), "residual blocks run on the slot-bound epilogue");
+  static_assert(!kGather || (!kTrain && !kShared && !kRes), "the fused gather is an inference path of the slot-bound kernel");
   static_assert(!(kShared && kTrain), "the shared epilogue is an inference path");
   // (built with CNG_TC_EPI_WARPS=4 the shared mode is not instantiated: shared_kernel() below returns nullptr)
   constexpr int kRingN = kRing;
@@ -461,13 +471,22 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
       if constexpr (kTrain) tile_free();
       // ---- features -> A block 0 as [x_hi(32) | x_lo(32)] ----
       {
-        const float4* f = reinterpret_cast<const float4*>(p.feat + (static_cast<size_t>(ti.item) * p.N + ti.n0) * kC0);
+        const float4* f = kGather ? nullptr : reinterpret_cast<const float4*>(p.feat + (static_cast<size_t>(ti.item) * p.N + ti.n0) * kC0);
+        const float* pts = kGather ? p.points + (static_cast<size_t>(ti.item) * p.N + ti.n0) * 3 : nullptr;
+        const float4* vol = kGather ? p.vol + static_cast<size_t>(ti.item) * p.vol_item_stride : nullptr;
 #pragma unroll
         for (int it = kB * half; it < kB * half + kB; ++it) {
           const int r = q * 32 + it * 4 + (lane >> 3);
           const int c4 = lane & 7;                               // float4 index within the row: k = 4*c4
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (r < ti.rows) v = __ldg(f + r * 8 + c4);
+          if constexpr (kGather) {
+            if (r < ti.rows) {                                   // 8 lanes x float4 = the 32 channels of one point, 8 corner loads per lane
+              const CornerRec rec = corner_record(__ldg(pts + 3 * r), __ldg(pts + 3 * r + 1), __ldg(pts + 3 * r + 2), p.D, p.H, p.W);
+              v = gather_c4(vol, p.H, p.W, kC0 / 4, rec, c4);
+            }
+          } else {
+            if (r < ti.rows) v = __ldg(f + r * 8 + c4);
+          }
           uint2 hi, lo;
           hi.x = pack2<kHalf>(v.x, v.y); hi.y = pack2<kHalf>(v.z, v.w);
           lo.x = pack2<kHalf>(v.x - from16<kHalf>(to16<kHalf>(v.x)), v.y - from16<kHalf>(to16<kHalf>(v.y)));
@@ -670,7 +689,7 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
                          const float* const* b, const float* freq, const float* phase, const float* final_w,
                          const float* final_b_dev, int sigmoid_rgb, int half_operands, void* workspace, size_t workspace_bytes,
                          float* out, void* dump_x, void* dump_g, cudaStream_t stream, unsigned res_save_mask = 0, unsigned res_add_mask = 0,
-                         float* res_scratch = nullptr, void* dump_feat = nullptr) {
+                         float* res_scratch = nullptr, void* dump_feat = nullptr, const GatherSource* gather = nullptr) {
   CNG_REQUIRE(HID == kHID && C == kC0, CNG_ERR_UNSUPPORTED, "film_siren_fwd(bf16): needs HID=256, C=32 (got %d, %d)", HID, C);
   CNG_REQUIRE(L >= 1 && L <= 16, CNG_ERR_UNSUPPORTED, "film_siren_fwd(bf16): L=%d", L);
   CNG_REQUIRE(workspace != nullptr && workspace_bytes >= film_siren_tc_workspace(B, L), CNG_ERR_WORKSPACE,
@@ -678,6 +697,9 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
   CNG_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 127) == 0, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd(bf16): workspace not 128-byte aligned");
   CNG_REQUIRE((reinterpret_cast<uintptr_t>(feat) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, CNG_ERR_INVALID_ARGUMENT,
               "film_siren_fwd(bf16): feat/out not 16-byte aligned");
+  CNG_REQUIRE((feat != nullptr) != (gather != nullptr), CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd(bf16): exactly one of gathered features / gather source");
+  CNG_REQUIRE(gather == nullptr || (dump_x == nullptr && (res_save_mask | res_add_mask) == 0), CNG_ERR_UNSUPPORTED,
+              "film_siren_fwd_gather: inference of the plain FiLM networks only");
   FoldParams fp{};
   for (int l = 0; l < L; ++l) { fp.w[l] = w[l]; fp.b[l] = b[l]; }
   fp.freq = freq; fp.phase = phase; fp.final_w = final_w; fp.B = B; fp.L = L;
@@ -701,6 +723,10 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
   CNG_REQUIRE(((res_save_mask | res_add_mask) == 0) || res_scratch != nullptr, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd: residual masks without a scratch buffer");
   CNG_REQUIRE(((res_save_mask | res_add_mask) >> L) == 0, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd: residual mask bit beyond layer %d", L - 1);
   p.feat = feat; p.N = N; p.B = B; p.L = L; p.images = fp.images; p.shift = fp.shift;
+  if (gather != nullptr) {
+    p.vol = reinterpret_cast<const float4*>(gather->vol_ndhwc); p.vol_item_stride = gather->vol_item_stride / 4;
+    p.D = gather->D; p.H = gather->H; p.W = gather->W; p.points = gather->points;
+  }
   CNG_REQUIRE((reinterpret_cast<uintptr_t>(final_b_dev) & 15) == 0, CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd(bf16): final_b not 16-byte aligned");
   p.final_b = final_b_dev;
   cudaError_t ce = cudaSuccess;
@@ -730,7 +756,7 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
     const int v = e ? atoi(e) : kDefaultKernelVersion;
     return (v >= 1 && v <= 3) ? v : kDefaultKernelVersion;
   }();
-  const int ver = (res_save_mask | res_add_mask) ? 1 : (g_tc_version ? g_tc_version : version);     // residual blocks: the slot-bound kernel
+  const int ver = ((res_save_mask | res_add_mask) || gather) ? 1 : (g_tc_version ? g_tc_version : version);     // residual blocks, fused gather: the slot-bound kernel
 #ifdef CNG_WITH_EXPERIMENTAL_K2
   if (ver == 3 && !train && L <= 8) return film_siren_tc3_launch(p, poly, stream);
 #endif
@@ -748,7 +774,8 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
                                              : train_poly == 3 ? film_siren_tc_kernel<3, true, true> : film_siren_tc_kernel<4, true, true>)
                                           : (train_poly == 0 ? film_siren_tc_kernel<0, false, true> : train_poly == 2 ? film_siren_tc_kernel<2, false, true>
                                              : train_poly == 3 ? film_siren_tc_kernel<3, false, true> : film_siren_tc_kernel<4, false, true>);
-  const KernelFn fn = res ? (train ? (half_operands ? film_siren_tc_kernel<0, true, true, false, true> : film_siren_tc_kernel<0, false, true, false, true>)
+  const KernelFn fn = gather ? (half_operands ? film_siren_tc_kernel<8, true, false, false, false, true> : film_siren_tc_kernel<8, false, false, false, false, true>)
+                      : res ? (train ? (half_operands ? film_siren_tc_kernel<0, true, true, false, true> : film_siren_tc_kernel<0, false, true, false, true>)
                                    : half_operands ? film_siren_tc_kernel<8, true, false, false, true> : film_siren_tc_kernel<8, false, false, false, true>)
                       : train ? train_fn
                       : shared ? (half_operands ? (pl == 0 ? shared_kernel<0, true>() : pl == 4 ? shared_kernel<4, true>() : shared_kernel<8, true>())
@@ -759,7 +786,8 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
   // function attributes are per device: the opt-in is cached per device ordinal (a process may render on several GPUs)
   static bool attr_set[64][8][12] = {};
   const int variant = res ? 5 + (train ? 2 : half_operands ? 1 : 0) : train ? 2 : (half_operands ? 1 : 0) + (shared ? 3 : 0);
-  const int pslot = train ? (half_operands ? 0 : 5) + (res ? 0 : train_poly) : poly;   // operand formats x poly shares of the training kernel share a variant row
+  const int gslot = gather ? 10 : -1;                                 // the fused-gather instantiations: variant rows 0 / 1, column 10
+  const int pslot = gslot >= 0 ? gslot : train ? (half_operands ? 0 : 5) + (res ? 0 : train_poly) : poly;   // operand formats x poly shares of the training kernel share a variant row
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = -1;
   if (dev < 0 || !attr_set[dev][variant][pslot]) {
@@ -825,6 +853,28 @@ int cng_film_siren_fwd(const float* feat, int B, long long N, int C, int HID, in
                                      sigmoid_rgb, precision == CNG_PREC_FP16 ? 1 : 0, workspace, workspace_bytes, rgb_sigma,
                                      nullptr, nullptr, cng::as_stream(stream));
   return cng::fail(CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd: unknown precision %d", precision);
+}
+
+int cng_film_siren_fwd_gather(const float* vol_ndhwc, long long vol_item_stride, int D, int H, int W, const float* points, int B, long long N,
+                              int C, int HID, int L, const float* const* layer_w_host, const float* const* layer_b_host, const float* freq,
+                              const float* phase, const float* final_w, const float* final_b, int sigmoid_rgb, int precision,
+                              void* workspace, size_t workspace_bytes, float* rgb_sigma, cng_stream_t stream) {
+  CNG_REQUIRE(B >= 0 && N >= 0 && C == cng::kC0 && HID == cng::kHID && L >= 1, CNG_ERR_UNSUPPORTED, "film_siren_fwd_gather: needs C=32, HID=256");
+  if (B == 0 || N == 0) return CNG_OK;
+  CNG_REQUIRE(vol_ndhwc && points && layer_w_host && layer_b_host && freq && phase && final_w && final_b && rgb_sigma, CNG_ERR_INVALID_ARGUMENT,
+              "film_siren_fwd_gather: NULL pointer");
+  CNG_REQUIRE(D >= 1 && H >= 1 && W >= 1 && (reinterpret_cast<uintptr_t>(vol_ndhwc) & 15) == 0, CNG_ERR_INVALID_ARGUMENT,
+              "film_siren_fwd_gather: bad volume");
+  CNG_REQUIRE(vol_item_stride == 0 || vol_item_stride == static_cast<long long>(C) * D * H * W, CNG_ERR_INVALID_ARGUMENT,
+              "film_siren_fwd_gather: vol_item_stride must be 0 (shared volume) or C*D*H*W");
+  CNG_REQUIRE(precision == CNG_PREC_BF16 || precision == CNG_PREC_FP16, CNG_ERR_UNSUPPORTED, "film_siren_fwd_gather: tensor-core precisions only");
+  for (int l = 0; l < L && l < 16; ++l)
+    CNG_REQUIRE(layer_w_host[l] && layer_b_host[l], CNG_ERR_INVALID_ARGUMENT, "film_siren_fwd_gather: NULL layer %d", l);
+  if (int e = cng_device_check()) return e;
+  const cng::GatherSource src{vol_ndhwc, vol_item_stride, D, H, W, points};
+  return cng::film_siren_tc_launch(nullptr, B, N, C, HID, L, layer_w_host, layer_b_host, freq, phase, final_w, final_b, sigmoid_rgb,
+                                   precision == CNG_PREC_FP16 ? 1 : 0, workspace, workspace_bytes, rgb_sigma, nullptr, nullptr,
+                                   cng::as_stream(stream), 0, 0, nullptr, nullptr, &src);
 }
 
 size_t cng_film_siren_res_scratch_bytes(void) {

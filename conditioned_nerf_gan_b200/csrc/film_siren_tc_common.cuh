@@ -272,7 +272,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 
 struct TcParams {
-  const float* feat;        // [B, N, 32]
+  const float* feat;        // [B, N, 32]; NULL in fused-gather mode:
+  // fused gather (kGather instantiations): the prologue of a tile looks its 128 points up in the NDHWC volume itself
+  // (trilinear, ATen index arithmetic: trilinear.cuh) instead of reading gathered features back from HBM
+  const float4* vol;        // [B, D, H, W, 8] float4
+  long long vol_item_stride;   // float4 units; 0 = every item reads item 0's volume
+  int D, H, W;
+  const float* points;      // [B, N, 3] world positions
   long long N;
   int B, L;
   const uint8_t* images;    // fold output

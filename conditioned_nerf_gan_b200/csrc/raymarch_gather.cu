@@ -22,6 +22,7 @@
 #include <cuda_fp16.h>
 
 #include "cng_common.cuh"
+#include "trilinear.cuh"
 
 #ifndef CNG_K1_MIN_BLOCKS
 #define CNG_K1_MIN_BLOCKS 3     // resident blocks per SM the register allocation aims at (A/B knob)
@@ -37,16 +38,6 @@ struct Corner {
   int x0, y0, z0;
   float fx1, fx0, fy1, fy0, fz1, fz0;    // weights of the high / low corner per axis
 };
-
-__device__ __forceinline__ void axis_index(float p, int size, int& i0, float& w_lo, float& w_hi) {
-  const float g = __fdiv_rn(p, 0.6f);                                 // points / (voxel_length / 2)
-  float i = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.f), static_cast<float>(size)), 1.f), 2.f);
-  i = fminf(static_cast<float>(size - 1), fmaxf(i, 0.f));             // border: clip_coordinates
-  const float f = floorf(i);
-  i0 = static_cast<int>(f);
-  w_lo = __fsub_rn(__fadd_rn(f, 1.f), i);
-  w_hi = __fsub_rn(i, f);
-}
 
 // Accumulate the 8 corners for channel group `cg4` (float4 index) of one point.
 __device__ __forceinline__ float4 trilinear_c4(const float4* __restrict__ vol, int D, int H, int W, int C4,
@@ -81,16 +72,16 @@ __device__ __forceinline__ float4 trilinear_c4(const float4* __restrict__ vol, i
   const float w101 = (xin && zin) ? __fmul_rn(__fmul_rn(xh, yl), zh) : 0.f;
   const float w110 = (yin && zin) ? __fmul_rn(__fmul_rn(xl, yh), zh) : 0.f;
   const float w111 = (xin && yin && zin) ? __fmul_rn(__fmul_rn(xh, yh), zh) : 0.f;
-  float4 o;
+  float4 o;                                        // same fused multiply-add chain as gather_c4 (trilinear.cuh): the two gathers agree bit for bit
 #define CNG_ACC(comp)                                                          \
   o.comp = __fmul_rn(v000.comp, w000);                                         \
-  o.comp = __fadd_rn(o.comp, __fmul_rn(v001.comp, w001));                      \
-  o.comp = __fadd_rn(o.comp, __fmul_rn(v010.comp, w010));                      \
-  o.comp = __fadd_rn(o.comp, __fmul_rn(v011.comp, w011));                      \
-  o.comp = __fadd_rn(o.comp, __fmul_rn(v100.comp, w100));                      \
-  o.comp = __fadd_rn(o.comp, __fmul_rn(v101.comp, w101));                      \
-  o.comp = __fadd_rn(o.comp, __fmul_rn(v110.comp, w110));                      \
-  o.comp = __fadd_rn(o.comp, __fmul_rn(v111.comp, w111));
+  o.comp = fmaf(v001.comp, w001, o.comp);                                      \
+  o.comp = fmaf(v010.comp, w010, o.comp);                                      \
+  o.comp = fmaf(v011.comp, w011, o.comp);                                      \
+  o.comp = fmaf(v100.comp, w100, o.comp);                                      \
+  o.comp = fmaf(v101.comp, w101, o.comp);                                      \
+  o.comp = fmaf(v110.comp, w110, o.comp);                                      \
+  o.comp = fmaf(v111.comp, w111, o.comp);
   CNG_ACC(x) CNG_ACC(y) CNG_ACC(z) CNG_ACC(w)
 #undef CNG_ACC
   return o;
@@ -110,56 +101,6 @@ struct RayParams {
   float* t_out;             // [B, R, S]    (coarse)
   float* points_out;        // [B, R, S, 3] or NULL
 };
-
-// Voxel-corner record of one sample point, computed once (phase A) and broadcast by shuffles (phase B).
-struct CornerRec {
-  int base;                               // ((z0 * H + y0) * W + x0), in voxels
-  int flags;                              // bit0: x0+1 in range, bit1: y0+1, bit2: z0+1
-  float xl, xh, yl, yh, zl, zh;
-};
-
-__device__ __forceinline__ CornerRec corner_record(float px, float py, float pz, int D, int H, int W) {
-  CornerRec r;
-  int x0, y0, z0;
-  axis_index(px, W, x0, r.xl, r.xh);
-  axis_index(py, H, y0, r.yl, r.yh);
-  axis_index(pz, D, z0, r.zl, r.zh);
-  r.base = (z0 * H + y0) * W + x0;
-  r.flags = (x0 + 1 <= W - 1 ? 1 : 0) | (y0 + 1 <= H - 1 ? 2 : 0) | (z0 + 1 <= D - 1 ? 4 : 0);
-  return r;
-}
-
-// 8 lanes x float4 = the 32 channels of ONE point: 8 independent 16-byte loads per lane, ATen's accumulation order.
-__device__ __forceinline__ float4 gather_c4(const float4* __restrict__ vol, int H, int W, int C4, const CornerRec& r, int cg4) {
-  const bool xin = r.flags & 1, yin = r.flags & 2, zin = r.flags & 4;
-  const size_t sx = xin ? C4 : 0, sy = yin ? static_cast<size_t>(W) * C4 : 0, sz = zin ? static_cast<size_t>(H) * W * C4 : 0;
-  const float4* b = vol + static_cast<size_t>(r.base) * C4 + cg4;
-  const float4 v000 = __ldg(b), v001 = __ldg(b + sx), v010 = __ldg(b + sy), v011 = __ldg(b + sy + sx);
-  const float4 v100 = __ldg(b + sz), v101 = __ldg(b + sz + sx), v110 = __ldg(b + sz + sy), v111 = __ldg(b + sz + sy + sx);
-  const float w000 = __fmul_rn(__fmul_rn(r.xl, r.yl), r.zl);
-  const float w001 = xin ? __fmul_rn(__fmul_rn(r.xh, r.yl), r.zl) : 0.f;
-  const float w010 = yin ? __fmul_rn(__fmul_rn(r.xl, r.yh), r.zl) : 0.f;
-  const float w011 = (xin && yin) ? __fmul_rn(__fmul_rn(r.xh, r.yh), r.zl) : 0.f;
-  const float w100 = zin ? __fmul_rn(__fmul_rn(r.xl, r.yl), r.zh) : 0.f;
-  const float w101 = (xin && zin) ? __fmul_rn(__fmul_rn(r.xh, r.yl), r.zh) : 0.f;
-  const float w110 = (yin && zin) ? __fmul_rn(__fmul_rn(r.xl, r.yh), r.zh) : 0.f;
-  const float w111 = (xin && yin && zin) ? __fmul_rn(__fmul_rn(r.xh, r.yh), r.zh) : 0.f;
-  // ATen's corner order, fused multiply-adds: the voxel indices and weights above are bit-exact, the 8-term sum differs from
-  // grid_sample's separate mul / add by < 1 ulp per term (the parity bar on features is 5e-6 abs) at half the FP instructions
-  float4 o;
-#define CNG_ACC(comp)                                                          \
-  o.comp = __fmul_rn(v000.comp, w000);                                         \
-  o.comp = fmaf(v001.comp, w001, o.comp);                                      \
-  o.comp = fmaf(v010.comp, w010, o.comp);                                      \
-  o.comp = fmaf(v011.comp, w011, o.comp);                                      \
-  o.comp = fmaf(v100.comp, w100, o.comp);                                      \
-  o.comp = fmaf(v101.comp, w101, o.comp);                                      \
-  o.comp = fmaf(v110.comp, w110, o.comp);                                      \
-  o.comp = fmaf(v111.comp, w111, o.comp);
-  CNG_ACC(x) CNG_ACC(y) CNG_ACC(z) CNG_ACC(w)
-#undef CNG_ACC
-  return o;
-}
 
 __device__ __forceinline__ CornerRec shfl_record(const CornerRec& r, int src) {
   CornerRec o;
@@ -236,6 +177,7 @@ __global__ void __launch_bounds__(256, CNG_K1_MIN_BLOCKS) raymarch_gather_kernel
       float* o = p.points_out + 3 * (base + s);
       o[0] = px; o[1] = py; o[2] = pz;
     }
+    if (p.feat == nullptr) continue;                       // points-only mode: the gather happens in the consumer (fused K2 prologue)
     const CornerRec mine = corner_record(px, py, pz, p.D, p.H, p.W);
     const long long my_row = live ? static_cast<long long>(base + s) : -1;
     // ---- phase B: 4 points per round, 8 lanes x float4 each ----
@@ -340,7 +282,7 @@ static int raymarch_common(bool fine, const float* vol, long long vol_item_strid
                            cng_stream_t stream) {
   const char* who = fine ? "raymarch_gather_fine" : "raymarch_gather_coarse";
   if (int e = cng::check_volume(vol, B, C, D, H, W, who)) return e;
-  CNG_REQUIRE(B == 0 || (cam2world && rays_d_cam && feat), CNG_ERR_INVALID_ARGUMENT, "%s: NULL pointer", who);
+  CNG_REQUIRE(B == 0 || (cam2world && rays_d_cam && (feat || points_out)), CNG_ERR_INVALID_ARGUMENT, "%s: NULL pointer", who);
   CNG_REQUIRE(B == 0 || (fine ? (t_fine != nullptr) : (t_lin != nullptr && t_out != nullptr)), CNG_ERR_INVALID_ARGUMENT,
               "%s: NULL distance buffer", who);
   CNG_REQUIRE(img_w >= 1 && img_h >= 1 && S >= (fine ? 1 : 2), CNG_ERR_INVALID_ARGUMENT, "%s: img=%dx%d S=%d", who, img_w, img_h, S);

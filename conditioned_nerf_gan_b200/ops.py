@@ -245,6 +245,34 @@ def film_siren_fwd(feat, layer_w: Sequence[torch.Tensor], layer_b: Sequence[torc
     return out
 
 
+def film_siren_fwd_gather(vol_cl, points, layer_w, layer_b, freq, phase, final_w, final_b, sigmoid_rgb: bool, precision: str = "bf16") -> torch.Tensor:
+    """K2 with the trilinear lookup fused into its prologue (cng_film_siren_fwd_gather): vol_cl [B or 1, D,H,W,32], points [B,N,3]
+    -> rgb_sigma [B,N,4]; the gathered features never go to HBM."""
+    if precision not in ("bf16", "fp16"):
+        raise ValueError("film_siren_fwd_gather: precision must be 'bf16' or 'fp16'")
+    vol_cl, points = _f32(vol_cl, "vol_ndhwc"), _f32(points, "points")
+    Bv, D, H, W, C = vol_cl.shape
+    B, N = points.shape[0], points.shape[1]
+    stride = 0 if (Bv == 1 and B > 1) else C * D * H * W
+    L = len(layer_w)
+    ws = [_f32(w, f"layer_w[{i}]") for i, w in enumerate(layer_w)]
+    bs = [_f32(b, f"layer_b[{i}]") for i, b in enumerate(layer_b)]
+    HID = ws[0].shape[0]
+    freq, phase, final_w, final_b = _f32(freq, "freq"), _f32(phase, "phase"), _f32(final_w, "final_w"), _f32(final_b, "final_b")
+    dev = vol_cl.device
+    out = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
+    w_arr = (ctypes.c_void_p * L)(*[w.data_ptr() for w in ws])
+    b_arr = (ctypes.c_void_p * L)(*[b.data_ptr() for b in bs])
+    code = PRECISIONS[precision]
+    ws_bytes = int(_lib.load().cng_film_siren_workspace_bytes(B, C, HID, L, code))
+    workspace = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev), _timed("cng_film_siren_fwd_gather"):
+        _lib.call("cng_film_siren_fwd_gather", _ptr(vol_cl), stride, D, H, W, _ptr(points), B, N, C, HID, L, w_arr, b_arr, _ptr(freq), _ptr(phase),
+                  _ptr(final_w), _ptr(final_b), int(bool(sigmoid_rgb)), code, _ptr(workspace), ws_bytes, _ptr(out), _stream(vol_cl))
+    _count(2)
+    return out
+
+
 def composite_fwd(rgb_sigma, t, noise, noise_std: float, clamp_mode, white_back=False, last_back=False,
                   want_weights=True) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
     """K3.  rgb_sigma [..., S, 4], t [..., S(,1)] -> rgb [..., 3], dist [...], weights [..., S]."""

@@ -153,6 +153,16 @@ CNG_API int cng_film_siren_fwd(const float* feat, int B, long long N, int C, int
  * bit l of res_add_mask = the kept x is added to layer l's pre-activation (a layer may do both: add, then keep).
  * res_scratch: cng_film_siren_res_scratch_bytes() of device memory for the 16-bit modes (the kept activations of the
  * tiles in flight, fp32, L2-resident), unused for CNG_PREC_FP32.  Masks 0 = cng_film_siren_fwd. */
+/* K2 with the trilinear lookup (a4) fused into its prologue: every 128-point tile looks its points [B, N, 3] (world space, as
+ * written by cng_raymarch_gather_{coarse,fine} with feat == NULL) up in the NDHWC volume itself, so the gathered features
+ * [B, N, 32] never go to HBM (403 MB written + read per pass at BASELINE configs[1]).  Tensor-core precisions, plain FiLM
+ * networks, C == 32.  Same arithmetic as cng_gather_points followed by cng_film_siren_fwd: bit-identical output. */
+CNG_API int cng_film_siren_fwd_gather(const float* vol_ndhwc, long long vol_item_stride, int D, int H, int W,
+                              const float* points, int B, long long N, int C, int HID, int L,
+                              const float* const* layer_w_host, const float* const* layer_b_host,
+                              const float* freq, const float* phase, const float* final_w,
+                              const float* final_b, int sigmoid_rgb, int precision, void* workspace,
+                              size_t workspace_bytes, float* rgb_sigma, cng_stream_t stream);
 CNG_API size_t cng_film_siren_res_scratch_bytes(void);
 CNG_API int cng_film_siren_fwd_res(const float* feat, int B, long long N, int C, int HID, int L,
                            const float* const* layer_w_host, const float* const* layer_b_host,

@@ -804,6 +804,41 @@ def test_config2_full_size_vs_oracle():
             assert torch.equal(s1[0], a[i]) and torch.equal(ds1[0], da[i])
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_fused_gather_forward_is_bit_identical(ops, precision):
+    """cng_film_siren_fwd_gather (trilinear lookup fused into K2's prologue, no feat[B,N,32] in HBM) against the separate
+    K1 gather + K2: the same arithmetic in the same order, hence the same image bit for bit; ragged tiles and a shared volume."""
+    import ctypes
+    from conditioned_nerf_gan_b200 import _lib
+    lib = _lib.load()
+    lib.cng_internal_set_fused_gather.argtypes = [ctypes.c_int]
+    lib.cng_internal_set_fused_gather.restype = None
+    for (B, img, S, V) in ((2, 20, 7, 16), (1, 64, 12, 32)):
+        siren_type, state, z, cam, draws, meta = _full_size_case(B, img, S, V, 70 + B, True)
+        gen = _generator(siren_type, state, precision)
+        d = {k: dev(v) for k, v in draws.items()}
+        outs = []
+        try:
+            for mode in (0, 1):
+                lib.cng_internal_set_fused_gather(mode)
+                with torch.no_grad():
+                    outs.append(gen((dev(z[0]), dev(z[1])), dev(cam), draws=d, **meta))
+        finally:
+            lib.cng_internal_set_fused_gather(-1)
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), (outs[0][0] - outs[1][0]).abs().max().item()
+    # the entry point itself against gather_points + film_siren_fwd
+    spec, ws, bs, feat, freq, phase, fw, fb, _ = _mlp_setup("TALLSIREN_FG", 2, 777, 0.3)
+    g = torch.Generator().manual_seed(5)
+    vol = dev(torch.randn((2, 32, 9, 10, 11), generator=g))
+    pts = dev((torch.rand((2, 777, 3), generator=g) - 0.5) * 1.6)
+    vol_cl = ops.volume_to_channels_last(vol)
+    ref = ops.film_siren_fwd(ops.gather_points(vol_cl, pts), [dev(w) for w in ws], [dev(b) for b in bs], dev(freq), dev(phase), dev(fw), dev(fb),
+                             spec["sigmoid_rgb"], precision)
+    out = ops.film_siren_fwd_gather(vol_cl, pts, [dev(w) for w in ws], [dev(b) for b in bs], dev(freq), dev(phase), dev(fw), dev(fb),
+                                    spec["sigmoid_rgb"], precision)
+    assert torch.equal(out, ref)
+
+
 def test_fp16_host_volume_path(ops):
     """A feature volume held in fp16 (the encoder's autocast dtype; what bench.py's end-to-end leg uploads): the layout pass widens
     it exactly (cng_volume_f16_to_channels_last), and the image stays at the tensor-core bar against the oracle on the fp32 volume."""
