@@ -194,11 +194,18 @@ def render_with_grad(gen, volume, global_feature, cam2worlds, img_size, fov, ray
         t = draws.get(name)
         return fn(shape, device=dev) if t is None else t.to(dev)
 
-    vol_cl = _ToChannelsLast.apply(volume.float())
     freq, phase = net.film_parameters(global_feature, B, dev)
-    C = vol_cl.shape[-1]
     u_jitter = draw("u_jitter", torch.rand, (B, R, S, 1))
-    feat_c, t_c = _GatherCoarse.apply(vol_cl, cam2worlds, rays_d_cam, t_lin, u_jitter, img_size)
+    if net.latent:
+        # position-input SIREN (siren.py:1172-1224): no volume; the sample positions (no gradient, generators.py:57) are the operand rows
+        vol_cl, C = None, 32
+        with torch.no_grad():
+            t_c, pts_c = ops.raymarch_points_coarse(cam2worlds, rays_d_cam, t_lin, u_jitter, img_size, img_size)
+            feat_c = net.point_features(pts_c.view(B, R * S, 3))
+    else:
+        vol_cl = _ToChannelsLast.apply(volume.float())
+        C = vol_cl.shape[-1]
+        feat_c, t_c = _GatherCoarse.apply(vol_cl, cam2worlds, rays_d_cam, t_lin, u_jitter, img_size)
     coarse = _mlp(net, feat_c.view(B, R * S, C), freq, phase)
     if hierarchical_sample:
         with torch.no_grad():
@@ -206,7 +213,11 @@ def render_with_grad(gen, volume, global_feature, cam2worlds, img_size, fov, ray
             _, _, w_c = ops.composite_fwd(coarse.detach().view(B, R, S, 4), t_c, noise_c, nerf_noise, clamp_mode)
             u_re = draw("u_resample", torch.rand, (B * R, S))
             t_f = ops.resample_from_coarse(t_c, w_c, u_re)
-        feat_f = _GatherFine.apply(vol_cl, cam2worlds, rays_d_cam, t_f, img_size)
+        if net.latent:
+            with torch.no_grad():
+                feat_f = net.point_features(ops.raymarch_points_fine(cam2worlds, rays_d_cam, t_f, img_size, img_size).view(B, R * S, 3))
+        else:
+            feat_f = _GatherFine.apply(vol_cl, cam2worlds, rays_d_cam, t_f, img_size)
         fine = _mlp(net, feat_f.view(B, R * S, C), freq, phase)
         noise_f = draw("noise_final", torch.randn, (B, R, 2 * S, 1))
         return _MergeComposite.apply(fine, coarse, t_f, t_c, noise_f, rays_d_cam, B, img_size, nerf_noise, clamp_mode,

@@ -56,7 +56,7 @@ class ImplicitGenerator3d(nn.Module):
         ``last_back`` default to False, every other key is ignored."""
         volume, global_feature = self.siren.split_z(z)
         needs_grad = torch.is_grad_enabled() and (
-            volume.requires_grad or (global_feature is not None and global_feature.requires_grad)
+            (volume is not None and volume.requires_grad) or (global_feature is not None and global_feature.requires_grad)
             or any(p.requires_grad for p in self.siren.parameters()))
         if needs_grad:
             from .autograd import render_with_grad
@@ -79,9 +79,11 @@ class ImplicitGenerator3d(nn.Module):
         dev = cam2worlds.device
         net = self.siren
         rays_d_cam, t_lin = camera_tables((img_size, img_size), S, fov, ray_start, ray_end, dev)
+        freq, phase = film if film is not None else net.film_parameters(global_feature, B, dev)
+        if net.latent:
+            return self._render_latent(net, freq, phase, cam2worlds, rays_d_cam, t_lin, img_size, S, hierarchical_sample, kwargs, taps)
         if vol_cl is None:
             vol_cl = ops.volume_to_channels_last(volume)
-        freq, phase = film if film is not None else net.film_parameters(global_feature, B, dev)
         C = vol_cl.shape[-1]
         out: Dict[str, torch.Tensor] = {}
 
@@ -136,6 +138,45 @@ class ImplicitGenerator3d(nn.Module):
                        rgb=res[2]["rgb"], dist=res[2]["dist"], merge_order=res[2]["order"])
         return out
 
+    @torch.no_grad()
+    def _render_latent(self, net, freq, phase, cam2worlds, rays_d_cam, t_lin, img_size, S, hierarchical_sample, kwargs, taps):
+        """The same sequence for the position-input SIREN (``SHORTSIREN``, siren.py:1172-1224): K1 in points-only mode (no volume,
+        no gather), the positions as the MLP's operand rows, then K3 / K4 / K3' unchanged."""
+        clamp_mode, nerf_noise = kwargs["clamp_mode"], kwargs["nerf_noise"]
+        white_back, last_back = kwargs.get("white_back", False), kwargs.get("last_back", False)
+        draws = kwargs.get("draws") or {}
+        B, R, dev = cam2worlds.shape[0], int(img_size) ** 2, cam2worlds.device
+
+        def draw(name, fn, shape):
+            t = draws.get(name)
+            return fn(shape, device=dev) if t is None else t.to(dev)
+
+        out: Dict[str, torch.Tensor] = {}
+        u_jitter = draw("u_jitter", torch.rand, (B, R, S, 1))
+        t_c, pts_c = ops.raymarch_points_coarse(cam2worlds, rays_d_cam, t_lin, u_jitter, img_size, img_size)
+        coarse = net.mlp(net.point_features(pts_c.view(B, R * S, 3)), freq, phase)
+        if hierarchical_sample:
+            noise_c = draw("noise_coarse", torch.randn, (B, R, S, 1))
+            _, _, w_c = ops.composite_fwd(coarse.view(B, R, S, 4), t_c, noise_c, nerf_noise, clamp_mode)
+            u_re = draw("u_resample", torch.rand, (B * R, S))
+            t_f = ops.resample_from_coarse(t_c, w_c, u_re)
+            pts_f = ops.raymarch_points_fine(cam2worlds, rays_d_cam, t_f, img_size, img_size)
+            fine = net.mlp(net.point_features(pts_f.view(B, R * S, 3)), freq, phase)
+            noise_f = draw("noise_final", torch.randn, (B, R, 2 * S, 1))
+            res = ops.merge_composite(fine, coarse, t_f, t_c, noise_f, rays_d_cam, B, img_size, img_size, nerf_noise, clamp_mode, white_back,
+                                      last_back, taps=taps)
+            if taps:
+                out.update(weights_coarse=w_c, t_fine=t_f.view(B, R, S), points_fine=pts_f, rgb_sigma_fine=fine.view(B, R, S, 4))
+        else:
+            noise_f = draw("noise_final" if "noise_final" in draws else "noise_coarse", torch.randn, (B, R, S, 1))
+            res = ops.merge_composite(None, coarse, None, t_c, noise_f, rays_d_cam, B, img_size, img_size, nerf_noise, clamp_mode, white_back,
+                                      last_back, taps=taps)
+        out["pixels"], out["depth"] = res[0], res[1]
+        if taps:
+            out.update(points_coarse=pts_c, t_coarse=t_c, rgb_sigma_coarse=coarse.view(B, R, S, 4), rgb=res[2]["rgb"], dist=res[2]["dist"],
+                       merge_order=res[2]["order"])
+        return out
+
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
     def staged_forward(self, z, cam2worlds, img_size, fov, ray_start, ray_end, num_steps, hierarchical_sample,
@@ -146,13 +187,14 @@ class ImplicitGenerator3d(nn.Module):
         (per-frame fov sweep, inference.py:459).  ``nerf_noise`` is forced to 0."""
         volume, global_feature = self.siren.split_z(z)
         P = cam2worlds.shape[0]
-        shared = volume.shape[0] == 1 and P > 1
+        n_obj = global_feature.shape[0] if self.siren.latent else volume.shape[0]
+        shared = n_obj == 1 and P > 1
         kwargs = dict(kwargs)
         kwargs["nerf_noise"] = 0
         kwargs.setdefault("clamp_mode", "relu")
         fovs = [float(fov)] * P if not hasattr(fov, "__len__") else [float(f) for f in fov]
-        vol_cl = ops.volume_to_channels_last(volume)
-        film = self.siren.film_parameters(global_feature, volume.shape[0], cam2worlds.device)
+        vol_cl = None if self.siren.latent else ops.volume_to_channels_last(volume)
+        film = self.siren.film_parameters(global_feature, n_obj, cam2worlds.device)
         pixels = torch.empty((P, 3, img_size, img_size), dtype=torch.float32, device=cam2worlds.device)
         depth = torch.empty((P, img_size, img_size), dtype=torch.float32, device=cam2worlds.device)
         start = 0
@@ -165,7 +207,7 @@ class ImplicitGenerator3d(nn.Module):
                 v = vol_cl                                                 # K1 reads item 0's volume for every pose (stride 0)
                 f = tuple(t.expand(n, -1).contiguous() for t in film)
             else:
-                v, f = vol_cl[start:stop], tuple(t[start:stop] for t in film)
+                v, f = (vol_cl[start:stop] if vol_cl is not None else None), tuple(t[start:stop] for t in film)
             o = self._render(None, None, cam2worlds[start:stop], img_size, fovs[start], ray_start, ray_end, num_steps,
                              hierarchical_sample, kwargs, vol_cl=v, film=f)
             pixels[start:stop], depth[start:stop] = o["pixels"], o["depth"]

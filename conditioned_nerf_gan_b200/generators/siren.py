@@ -23,7 +23,7 @@ import torch.nn.functional as F
 
 from .. import ops
 
-__all__ = ["FiLMLayer", "SirenLayer", "ResSirenBlock", "TALLSIREN_dRes", "TALLSIREN_dResLong", "SHORTSIREN_FRes", "TALLSIREN_FG", "SHORTSIREN_FG", "DOUBLESIREN_FG", "SingleSIREN_dg", "SHORTSIREN_F",
+__all__ = ["CustomMappingNetwork", "SHORTSIREN", "FiLMLayer", "SirenLayer", "ResSirenBlock", "TALLSIREN_dRes", "TALLSIREN_dResLong", "SHORTSIREN_FRes", "TALLSIREN_FG", "SHORTSIREN_FG", "DOUBLESIREN_FG", "SingleSIREN_dg", "SHORTSIREN_F",
            "TALLSIREN_dg", "SHORTSIREN_dg", "DoubleSIREN_dg", "DOUBLESIREN_dg", "default_precision"]
 
 
@@ -63,6 +63,7 @@ class _FiLMSirenFG(nn.Module):
     sigmoid_rgb = True      # _sigmoid_rgb on the head (siren.py:579) or raw rgb (:1064)
     tensor_core_operands = "bf16"   # 16-bit operand format of the tcgen05 path that keeps this variant <= 1e-2 max-abs
     film = True             # False: plain sin(W x + b) layers, no mapping network, z is the feature volume alone
+    latent = False          # True (SHORTSIREN): no feature volume, the input of layer 0 is the sample position, z is a latent vector
 
     def __init__(self, input_dim=3, z_dim=100, hidden_dim=256, output_dim=4, drop_out=0, device=None, **kwargs):
         super().__init__()
@@ -152,6 +153,84 @@ class _FiLMSirenFG(nn.Module):
             return siren_forward_with_grad(self, points, volume, global_feature)
         freq, phase = self.film_parameters(global_feature, volume.shape[0], volume.device)
         feat = ops.gather_points(ops.volume_to_channels_last(volume), points)
+        return self.mlp(feat, freq, phase)
+
+
+class CustomMappingNetwork(nn.Module):
+    """generators/siren.py:55-78: z -> (frequencies, phase shifts) through three hidden Linear + LeakyReLU(0.2) layers; same module
+    tree (``network.{0,2,4,6}``), kaiming_leaky_init (``:47-52``), last weight scaled by 0.25.  A [B, z_dim] x [z_dim, 256] chain per
+    forward: plain torch ops (differentiable), not on the per-point path."""
+
+    def __init__(self, z_dim: int, map_hidden_dim: int, map_output_dim: int):
+        super().__init__()
+        self.network = nn.Sequential(nn.Linear(z_dim, map_hidden_dim), nn.LeakyReLU(0.2, inplace=True),
+                                     nn.Linear(map_hidden_dim, map_hidden_dim), nn.LeakyReLU(0.2, inplace=True),
+                                     nn.Linear(map_hidden_dim, map_hidden_dim), nn.LeakyReLU(0.2, inplace=True),
+                                     nn.Linear(map_hidden_dim, map_output_dim))
+        for m in self.network:
+            if isinstance(m, nn.Linear):
+                torch.nn.init.kaiming_normal_(m.weight, a=0.2, mode="fan_in", nonlinearity="leaky_relu")
+        with torch.no_grad():
+            self.network[-1].weight *= 0.25
+
+    def forward(self, z):
+        fo = self.network(z)
+        half = fo.shape[-1] // 2
+        return fo[..., :half], fo[..., half:]
+
+
+class SHORTSIREN(_FiLMSirenFG):
+    """generators/siren.py:1172-1224, the generator of the default config (configs/thousand/special.py:45-51): four FiLM layers
+    on the WORLD POSITION of a sample (``input_dim`` = 3, no feature volume), FiLM parameters from a latent vector ``z`` [B, z_dim]
+    (PointNet encoder) through ``CustomMappingNetwork``.  On the fused kernels the positions travel as the first ``input_dim`` of
+    the 32 operand channels (the rest zero) and layer 0's weight is zero-padded to [256, 32] -- layer 0 then runs in the split
+    hi/lo format, i.e. the positions enter at ~fp32 precision."""
+    num_layers, freq_div, sigmoid_rgb = 4, 25.0, True
+    latent = True
+
+    def __init__(self, input_dim=2, z_dim=100, hidden_dim=256, output_dim=1, drop_out=0, mapping_network="CustomMappingNetwork", device=None, **kwargs):
+        nn.Module.__init__(self)
+        if mapping_network != "CustomMappingNetwork":
+            raise NotImplementedError(f"mapping network {mapping_network!r} (only CustomMappingNetwork is built)")
+        if not 1 <= input_dim <= 32:
+            raise ValueError("SHORTSIREN: input_dim must be in [1, 32]")
+        self.device = device
+        self.input_dim, self.z_dim, self.hidden_dim, self.output_dim = input_dim, z_dim, hidden_dim, output_dim
+        self.network = nn.ModuleList([FiLMLayer(input_dim if i == 0 else hidden_dim, hidden_dim, drop_out) for i in range(self.num_layers)])
+        self.final_layer = nn.Linear(hidden_dim, 4)
+        self.mapping_network = CustomMappingNetwork(z_dim, 256, self.num_layers * hidden_dim * 2)
+        for i, film in enumerate(self.network):
+            fan_in = film.layer.weight.shape[-1]
+            _uniform_(film.layer, 1.0 / fan_in if i == 0 else math.sqrt(6.0 / fan_in) / self.freq_div)
+        _uniform_(self.final_layer, math.sqrt(6.0 / hidden_dim) / self.freq_div)
+        self.precision = default_precision(self.tensor_core_operands)
+
+    def split_z(self, z):
+        if isinstance(z, (tuple, list)) or z.dim() != 2:
+            raise ValueError("SHORTSIREN takes a latent vector z [B, z_dim] (generators/siren.py:1206-1208)")
+        return None, z
+
+    def film_parameters(self, z, batch: int = 1, device=None):
+        with torch.autocast(device_type=z.device.type, enabled=False):
+            freq, phase = self.mapping_network(z.float())
+            return (freq * 15 + 30).contiguous(), phase.contiguous()
+
+    def layer_parameters(self):
+        lin = self.linear_layers()
+        ws = [F.pad(lin[0].weight, (0, 32 - self.input_dim))] + [m.weight for m in lin[1:]]      # positions occupy operand channels 0..input_dim-1
+        return ws, [m.bias for m in lin]
+
+    def point_features(self, points: torch.Tensor) -> torch.Tensor:
+        """[B, N, input_dim] positions -> the kernels' 32-channel operand rows [B, N, 32]."""
+        return F.pad(points.float(), (0, 32 - points.shape[-1])).contiguous()
+
+    def forward(self, input: torch.Tensor, z, *args) -> torch.Tensor:
+        _, latent = self.split_z(z)
+        freq, phase = self.film_parameters(latent, input.shape[0], input.device)
+        feat = self.point_features(input)
+        if torch.is_grad_enabled() and (latent.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from .autograd import _mlp
+            return _mlp(self, feat, freq, phase)
         return self.mlp(feat, freq, phase)
 
 

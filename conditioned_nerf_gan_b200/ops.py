@@ -157,6 +157,50 @@ def raymarch_gather_fine(vol_cl, cam2world, rays_d_cam, t_fine, img_w, img_h, wa
     return feat, pts
 
 
+_DUMMY_VOL = {}
+
+
+def _dummy_volume(dev) -> torch.Tensor:
+    """A 1x1x1x32 volume for K1's points-only mode (the position-input SIREN has no feature volume; the kernel never reads it)."""
+    key = (dev.type, dev.index)
+    v = _DUMMY_VOL.get(key)
+    if v is None:
+        v = _DUMMY_VOL[key] = torch.zeros((1, 1, 1, 1, 32), dtype=torch.float32, device=dev)
+    return v
+
+
+def raymarch_points_coarse(cam2world, rays_d_cam, t_lin, u_jitter, img_w, img_h):
+    """K1 coarse in points-only mode (a1-a3 without a4).  Returns t[B,R,S], points[B,R,S,3]."""
+    cam2world, rays_d_cam, t_lin = _f32(cam2world, "cam2world"), _f32(rays_d_cam, "rays_d_cam"), _f32(t_lin, "t_lin")
+    B, S, R = cam2world.shape[0], t_lin.numel(), img_w * img_h
+    dev = cam2world.device
+    if u_jitter is not None:
+        u_jitter = _f32(u_jitter, "u_jitter")
+    vol = _dummy_volume(dev)
+    t_out = torch.empty((B, R, S), dtype=torch.float32, device=dev)
+    pts = torch.empty((B, R, S, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev), _timed("cng_raymarch_gather_coarse"):
+        _lib.call("cng_raymarch_gather_coarse", _ptr(vol), 0, B, 32, 1, 1, 1, _ptr(cam2world), _ptr(rays_d_cam), _ptr(t_lin), _ptr(u_jitter),
+                  img_w, img_h, S, None, _ptr(t_out), _ptr(pts), _stream(cam2world))
+    _count()
+    return t_out, pts
+
+
+def raymarch_points_fine(cam2world, rays_d_cam, t_fine, img_w, img_h):
+    """K1 fine in points-only mode (a10).  t_fine [B,R,S] -> points[B,R,S,3]."""
+    cam2world, rays_d_cam, t_fine = _f32(cam2world, "cam2world"), _f32(rays_d_cam, "rays_d_cam"), _f32(t_fine, "t_fine")
+    B, R = cam2world.shape[0], img_w * img_h
+    S = t_fine.numel() // (B * R)
+    dev = cam2world.device
+    vol = _dummy_volume(dev)
+    pts = torch.empty((B, R, S, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev), _timed("cng_raymarch_gather_fine"):
+        _lib.call("cng_raymarch_gather_fine", _ptr(vol), 0, B, 32, 1, 1, 1, _ptr(cam2world), _ptr(rays_d_cam), _ptr(t_fine), img_w, img_h, S,
+                  None, _ptr(pts), _stream(cam2world))
+    _count()
+    return pts
+
+
 def gather_points(vol_cl, points, want_index=False):
     """Trilinear lookup at caller-supplied world points [B,N,3] -> feat[B,N,C] (+ corner index)."""
     vol_cl = _f32(vol_cl, "vol_ndhwc")

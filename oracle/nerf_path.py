@@ -87,6 +87,10 @@ SIREN_SPECS = {
     # :906-979: one residual block, frequency_init(12), sigmoid on rgb
     "SHORTSIREN_FRes": {"layers": 4, "freq_init": 12.0, "sigmoid_rgb": True, "film": False, "res_save": 0b0001, "res_add": 0b0100,
                         "keys": ["network.0.layer", "network.1.fc1", "network.1.fc2", "network.2.layer"]},
+    # generators/siren.py:1172-1224 (the default of configs/thousand/special.py:46): no feature volume -- the input of layer 0 is
+    # the world position itself (input_dim = 3), z is a latent vector [B, z_dim] (PointNet encoder) mapped to the FiLM parameters
+    # by CustomMappingNetwork (:55-78: three hidden Linear + LeakyReLU(0.2), kaiming_leaky_init, last weight x 0.25)
+    "SHORTSIREN": {"layers": 4, "freq_init": 25.0, "sigmoid_rgb": True, "latent": True},
 }
 
 
@@ -136,6 +140,15 @@ def init_generator_state(
     state["siren.final_layer.weight"] = uniform((4, hidden_dim), math.sqrt(6.0 / hidden_dim) / spec["freq_init"])
     state["siren.final_layer.bias"] = uniform((4,), 1.0 / math.sqrt(hidden_dim))
     if not spec.get("film", True):
+        return state
+    if spec.get("latent"):
+        # CustomMappingNetwork(z_dim, 256, L * hidden * 2): kaiming_normal_(a=0.2, fan_in) weights, default Linear biases, last weight x 0.25
+        dims = [z_dim, 256, 256, 256, spec["layers"] * hidden_dim * 2]
+        for i in range(4):
+            std = math.sqrt(2.0 / (1 + 0.2 ** 2)) / math.sqrt(dims[i])
+            w = torch.randn((dims[i + 1], dims[i]), generator=g) * std
+            state[f"siren.mapping_network.network.{2 * i}.weight"] = w * (0.25 if i == 3 else 1.0)
+            state[f"siren.mapping_network.network.{2 * i}.bias"] = uniform((dims[i + 1],), 1.0 / math.sqrt(dims[i]))
         return state
     n_map = spec["layers"] * hidden_dim * 2
     state["siren.mapping_network.weight"] = uniform((n_map, z_dim), 1.0 / math.sqrt(z_dim))
@@ -327,6 +340,17 @@ def film_parameters(global_feature, map_weight, map_bias):
     return fo[..., :half] * 15 + 30, fo[..., half:]
 
 
+def custom_mapping_network(z, state):
+    """generators/siren.py:55-78 (CustomMappingNetwork.forward) + :1212-1215: freq = first half * 15 + 30, phase = second half."""
+    x = z
+    for i in range(4):
+        x = F.linear(x, state[f"siren.mapping_network.network.{2 * i}.weight"], state[f"siren.mapping_network.network.{2 * i}.bias"])
+        if i < 3:
+            x = F.leaky_relu(x, 0.2)
+    half = x.shape[-1] // 2
+    return x[..., :half] * 15 + 30, x[..., half:]
+
+
 def film_siren_mlp(feat, layer_weights, layer_biases, freq, phase, final_w, final_b, sigmoid_rgb=True, res_save=0, res_add=0):
     """generators/siren.py:573-579 + FiLMLayer.forward :153-160 + _sigmoid_rgb :1227-1234.
 
@@ -362,6 +386,9 @@ def _split_state(state, siren_type):
 def siren_forward(state, siren_type, pts_world, z, img_size, num_steps):
     """``SIREN.forward(points, z, img_size, num_steps)`` for the FG family (siren.py:540-580)."""
     spec, ws, bs = _split_state(state, siren_type)
+    if spec.get("latent"):                           # siren.py:1206-1224: x = input points, z = latent vector
+        freq, phase = custom_mapping_network(z, state)
+        return film_siren_mlp(pts_world, ws, bs, freq, phase, state["siren.final_layer.weight"], state["siren.final_layer.bias"], spec["sigmoid_rgb"])
     if spec.get("film", True):
         volume, global_feature = z
         freq, phase = film_parameters(global_feature, state["siren.mapping_network.weight"], state["siren.mapping_network.bias"])

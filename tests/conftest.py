@@ -65,3 +65,18 @@ def fixture_inputs(name):
     draws = {k[5:]: v for k, v in fx.items() if k.startswith("draw/")}
     taps = {k[4:]: v for k, v in fx.items() if k.startswith("tap/")}
     return state, siren_type, z, fx["in/cam2world"], draws, meta, taps
+
+
+def latent_fixture_inputs(name="fwd_SHORTSIREN"):
+    """(state, latent z, cam2world, draws, meta, taps) of the position-input SHORTSIREN fixture."""
+    from oracle import nerf_path as oracle
+
+    fx, meta = load_golden(name)
+    seed, z_dim, gains = meta.pop("seed"), meta.pop("z_dim"), meta.pop("dense_head_gains")
+    meta.pop("siren_type")
+    state = oracle.dense_head_state(oracle.init_generator_state("SHORTSIREN", z_dim=z_dim, input_dim=3, hidden_dim=256, seed=seed), *gains)
+    checksum = sum(float(v.double().abs().sum()) for v in state.values())
+    assert abs(checksum - float(fx["state/checksum"])) < 1e-9 * checksum, "torch CPU generator drifted"
+    draws = {k[5:]: v for k, v in fx.items() if k.startswith("draw/")}
+    taps = {k[4:]: v for k, v in fx.items() if k.startswith("tap/")}
+    return state, fx["in/latent"], fx["in/cam2world"], draws, meta, taps

@@ -294,6 +294,50 @@ def make_train_step_fixture(steps=2):
     return fx
 
 
+def make_latent_fixture(seed=41, img_size=16, S=12, B=2, z_dim=512):
+    """``SHORTSIREN`` (siren.py:1172-1224; the default generator of configs/thousand/special.py:45-51): position input, latent z."""
+    g = torch.Generator().manual_seed(seed)
+    state = oracle.init_generator_state("SHORTSIREN", z_dim=z_dim, input_dim=3, hidden_dim=256, seed=seed)
+    gains = [300.0, 3.0, 1.0, 6.0]                  # sigma gain, rgb gain, first-layer gain, sigma bias (thin fog: see oracle.DENSE_HEAD_GAINS)
+    state = oracle.dense_head_state(state, *gains)
+    latent = torch.randn((B, z_dim), generator=g)
+    cam = oracle.look_at_cam2world(oracle.random_camera_origins(B, 0.7, 1.5, "y", np.random.RandomState(seed)), "y")
+    draws = oracle.draw_randoms(B, img_size, S, True, g)
+    meta = dict(img_size=img_size, fov=49.134342641202636, ray_start=0.25, ray_end=1.95, num_steps=S, hierarchical_sample=True,
+                clamp_mode="relu", nerf_noise=0.0, white_back=True, last_back=False)
+    gen = ref_gen.ImplicitGenerator3d("SHORTSIREN", z_dim=z_dim, input_dim=3, output_dim=4, hidden_dim=256)
+    gen.load_state_dict(state, strict=True)
+    gen.set_device(torch.device("cpu"))
+    gen.eval()
+    rp = Replay([("rand", draws["u_jitter"]), ("randn", draws["noise_coarse"]), ("rand", draws["u_resample"]), ("randn", draws["noise_final"])])
+    calls = []
+    orig_fwd = gen.siren.forward
+
+    def tap(points, zz, *a):
+        out = orig_fwd(points, zz, *a)
+        calls.append((points.detach().clone(), out.detach().clone()))
+        return out
+
+    gen.siren.forward = tap
+    orig = torch.rand, torch.randn
+    torch.rand, torch.randn = rp.rand, rp.randn
+    try:
+        with torch.no_grad():
+            pixels, depth = gen(latent, cam, **meta)
+    finally:
+        torch.rand, torch.randn = orig
+    R = img_size ** 2
+    fx = {"state/checksum": np.array(sum(float(v.double().abs().sum()) for v in state.values()))}
+    fx.update({f"draw/{k}": v.numpy() for k, v in draws.items()})
+    fx["in/latent"], fx["in/cam2world"] = latent.numpy(), cam.numpy()
+    fx["tap/pixels"], fx["tap/depth"] = pixels.numpy(), depth.numpy()
+    fx["tap/points_coarse"] = calls[0][0].reshape(B, R, S, 3).numpy()
+    fx["tap/rgb_sigma_coarse"] = calls[0][1].reshape(B, R, S, 4).numpy()
+    fx["tap/rgb_sigma_fine"] = calls[1][1].reshape(B, R, S, 4).numpy()
+    fx["meta/json"] = np.array(__import__("json").dumps(dict(meta, siren_type="SHORTSIREN", seed=seed, z_dim=z_dim, dense_head_gains=gains)))
+    return fx
+
+
 def dense_fixtures():
     """Forward fixtures with real density: 16x16, 12+12 samples, 16^3 volume, batch 2."""
     kw = dict(img_size=16, S=12, V=16, B=2, dense=True)
@@ -307,6 +351,9 @@ def dense_fixtures():
 
 def main():
     out = {}
+    if "--latent-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "fwd_SHORTSIREN.npz"), **make_latent_fixture())
+        return
     if "--dense-only" in sys.argv:
         for name, fx in dense_fixtures().items():
             np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
@@ -332,6 +379,7 @@ def main():
     out["fwd_SHORTSIREN_FRes"] = make_forward_fixture("SHORTSIREN_FRes", 18, clamp_mode="softplus", nerf_noise=0.3)
     out["functions"] = make_function_fixture()
     out.update(dense_fixtures())
+    out["fwd_SHORTSIREN"] = make_latent_fixture()
     for name, fx in out.items():
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **fx)

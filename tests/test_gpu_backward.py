@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import fixture_inputs
+from conftest import fixture_inputs, latent_fixture_inputs
 from oracle import nerf_path as oracle
 
 pytestmark = pytest.mark.gpu
@@ -269,6 +269,32 @@ def test_generator_backward_vs_oracle_autograd(name):
         print(f"  {name} {k}: rel-L2 {e:.3e} cos {c:.6f} |ref| {float(r.norm()):.3e}")
         assert c > 0.9995 and e < 2e-2, (k, e, c)
     print(f"{name}: worst relative L2 gradient error {worst:.3e}")
+
+
+def test_latent_shortsiren_backward_vs_oracle_autograd():
+    """Gradients of the position-input SHORTSIREN w.r.t. every parameter (mapping network included) and the latent vector."""
+    from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d
+    state, latent, cam, draws, meta, _ = latent_fixture_inputs()
+    B, img = cam.shape[0], meta["img_size"]
+    g = torch.Generator().manual_seed(2)
+    d_pix, d_dep = torch.randn((B, 3, img, img), generator=g), torch.randn((B, img, img), generator=g)
+    st = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+    z_r = latent.clone().requires_grad_(True)
+    out = oracle.render_with_grad(st, "SHORTSIREN", z_r, cam, draws, **meta)
+    ((out["pixels"] * d_pix).sum() + (out["depth"] * d_dep).sum()).backward()
+    gen = ImplicitGenerator3d("SHORTSIREN", latent.shape[1], 3, 4, 256)
+    gen.load_state_dict(state, strict=True)
+    gen = gen.to("cuda")
+    gen.siren.precision = "fp32"
+    z_d = dev(latent).requires_grad_(True)
+    pixels, depth = gen(z_d, dev(cam), draws={k: dev(v) for k, v in draws.items()}, **meta)
+    ((pixels * dev(d_pix)).sum() + (depth * dev(d_dep)).sum()).backward()
+    pairs = [("latent", z_d.grad, z_r.grad)] + [(k, p.grad, st["siren." + k].grad) for k, p in gen.siren.named_parameters()]
+    for k, got, ref in pairs:
+        assert got is not None and got.shape == ref.shape, k
+        e, c = rel_l2(got.cpu(), ref), cosine(got.cpu(), ref)
+        print(f"  SHORTSIREN {k}: rel-L2 {e:.3e} cos {c:.6f}")
+        assert c > 0.9995 and e < 2e-2, (k, e, c)
 
 
 def test_siren_boundary_backward_and_amp():

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import DENSE_FIXTURES, FORWARD_FIXTURES, fixture_inputs, load_golden
+from conftest import DENSE_FIXTURES, FORWARD_FIXTURES, fixture_inputs, latent_fixture_inputs, load_golden
 from oracle import nerf_path as oracle
 
 pytestmark = pytest.mark.gpu
@@ -837,6 +837,34 @@ def test_fused_gather_forward_is_bit_identical(ops, precision):
     out = ops.film_siren_fwd_gather(vol_cl, pts, [dev(w) for w in ws], [dev(b) for b in bs], dev(freq), dev(phase), dev(fw), dev(fb),
                                     spec["sigmoid_rgb"], precision)
     assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
+def test_latent_shortsiren_forward_vs_reference(precision):
+    """SHORTSIREN (siren.py:1172-1224, the generator of the default config): sample positions as the MLP input, FiLM parameters from a
+    latent vector through CustomMappingNetwork.  K1 runs in points-only mode, the positions ride in 3 of the 32 operand channels."""
+    from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d
+    state, latent, cam, draws, meta, taps = latent_fixture_inputs()
+    gen = ImplicitGenerator3d("SHORTSIREN", latent.shape[1], 3, 4, 256)
+    gen.load_state_dict(state, strict=True)
+    gen = gen.to("cuda")
+    gen.set_device(torch.device("cuda"))
+    gen.siren.precision = precision
+    d = {k: dev(v) for k, v in draws.items()}
+    B, img, S = cam.shape[0], meta["img_size"], meta["num_steps"]
+    with torch.no_grad():
+        out = gen._render(None, dev(latent), dev(cam), img, meta["fov"], meta["ray_start"], meta["ray_end"], S, True, dict(meta, draws=d), taps=True)
+        pixels, depth = gen(dev(latent), dev(cam), draws=d, **meta)
+        rs = gen.siren(dev(taps["points_coarse"].reshape(B, -1, 3)), dev(latent), img, S)       # the secondary boundary
+    assert torch.equal(pixels, out["pixels"])
+    assert torch.allclose(out["points_coarse"].cpu(), taps["points_coarse"], rtol=0, atol=5e-7)
+    d_c = (out["rgb_sigma_coarse"].cpu() - taps["rgb_sigma_coarse"]).abs()
+    tol = 5e-4 if precision == "fp32" else 1e-2
+    psnr = oracle.psnr(pixels.cpu(), taps["pixels"])
+    print(f"SHORTSIREN {precision}: coarse rgb err {d_c[..., :3].max().item():.2e}, sigma err {d_c[..., 3].max().item():.2e} (gain 300), PSNR {psnr:.1f} dB")
+    assert d_c[..., :3].max().item() < tol and d_c[..., 3].max().item() < tol * 300
+    assert (rs.cpu().reshape(B, -1, S, 4) - taps["rgb_sigma_coarse"]).abs()[..., :3].max().item() < tol
+    assert psnr >= (60.0 if precision == "fp32" else 40.0)
 
 
 def test_fp16_host_volume_path(ops):

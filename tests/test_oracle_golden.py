@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import DENSE_FIXTURES, FORWARD_FIXTURES, fixture_inputs, load_golden
+from conftest import DENSE_FIXTURES, FORWARD_FIXTURES, fixture_inputs, latent_fixture_inputs, load_golden
 from oracle import nerf_path as oracle
 
 
@@ -37,6 +37,15 @@ def test_forward_matches_reference(name):
         assert torch.allclose(out[k], taps[k].reshape(out[k].shape), rtol=0, atol=1e-4 if dense else tol), k
     assert out["pixels"].shape == (cam.shape[0], 3, meta["img_size"], meta["img_size"])
     assert out["depth"].shape == (cam.shape[0], meta["img_size"], meta["img_size"])
+
+
+def test_latent_shortsiren_matches_reference():
+    """SHORTSIREN (position input, latent z through CustomMappingNetwork; siren.py:1172-1224) against the fixture recorded from the
+    reference's own class."""
+    state, latent, cam, draws, meta, taps = latent_fixture_inputs()
+    out = oracle.render(state, "SHORTSIREN", latent, cam, draws, **meta)
+    assert torch.equal(out["points_coarse"], taps["points_coarse"]) and torch.equal(out["rgb_sigma_coarse"], taps["rgb_sigma_coarse"])
+    assert torch.allclose(out["pixels"], taps["pixels"], rtol=0, atol=1e-4) and torch.allclose(out["depth"], taps["depth"], rtol=0, atol=1e-4)
 
 
 def test_composite_matches_reference():
