@@ -172,6 +172,7 @@ class _MergeComposite(torch.autograd.Function):
 
 
 def _mlp(net, feat, freq, phase):
+    net.check_dropout()
     ws, bs = net.layer_parameters()
     return _FilmSiren.apply(feat, freq, phase, net.final_layer.weight, net.final_layer.bias, net.sigmoid_rgb, net.precision,
                             net.res_save_mask, net.res_add_mask, *ws, *bs)

@@ -91,6 +91,7 @@ class ImplicitGenerator3d(nn.Module):
             t = draws.get(name)
             return fn(shape, device=dev) if t is None else t.to(dev)
 
+        net.check_dropout()
         if not taps and kwargs.get("fused_call", True) and not net.res_add_mask:
             # production path: one C-ABI call (cng_render_fwd) sequences K1, K2, K3, K4, K1', K2, K3'; draws in the reference's order
             u_jitter = draw("u_jitter", torch.rand, (B, R, S, 1))

@@ -44,9 +44,8 @@ class FiLMLayer(nn.Module):
     def __init__(self, input_dim: int, hidden_dim: int, drop_out_prob: float = 0):
         super().__init__()
         self.layer = nn.Linear(input_dim, hidden_dim)
+        self.dropout_layer = nn.Dropout(drop_out_prob)        # no parameters; kept for the module tree of siren.py:146-151
         self.drop_out_prob = drop_out_prob
-        if drop_out_prob:
-            raise NotImplementedError("FiLM dropout > 0 is not built (every shipped config uses 0, special.py:39)")
 
 
 SirenLayer = FiLMLayer     # siren.py:180-199: the unmodulated layer holds the same single nn.Linear
@@ -127,8 +126,17 @@ class _FiLMSirenFG(nn.Module):
         lin = self.linear_layers()
         return [m.weight for m in lin], [m.bias for m in lin]
 
+    def check_dropout(self) -> None:
+        """siren.py:157-159 applies ``nn.Dropout`` to a layer's output only in training mode: in eval mode (every inference
+        caller) a network built with drop_out > 0 is exactly the network the fused kernels evaluate.  Training WITH dropout
+        would need the mask inside the kernels (forward, recompute and backward) and is not built; no shipped config uses it
+        (``dropout_ratio: 0``, configs/thousand/special.py:39)."""
+        if self.training and any(getattr(m, "drop_out_prob", 0) > 0 for m in self.network):
+            raise NotImplementedError("FiLM dropout > 0 in training mode is not built (call .eval(), or construct with drop_out=0)")
+
     def mlp(self, feat: torch.Tensor, freq: torch.Tensor, phase: torch.Tensor) -> torch.Tensor:
         """feat [B,N,C] -> rgb_sigma [B,N,4] through the fused FiLM-SIREN kernel."""
+        self.check_dropout()
         ws, bs = self.layer_parameters()
         return ops.film_siren_fwd(feat, ws, bs, freq, phase, self.final_layer.weight, self.final_layer.bias,
                                   self.sigmoid_rgb, self.precision, self.res_save_mask, self.res_add_mask)

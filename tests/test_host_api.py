@@ -119,6 +119,21 @@ def test_fp16_only_classes_reject_bf16_operands():
     tall.siren.precision = "fp16"
 
 
+def test_dropout_networks_load_and_only_training_mode_is_refused():
+    """siren.py:146-160: nn.Dropout acts in training mode only; a network built with drop_out > 0 keeps the reference's module tree
+    (no extra state-dict keys), renders in eval mode, and refuses training mode loudly (the mask is not built into the kernels)."""
+    gen = ImplicitGenerator3d("TALLSIREN_FG", 256, 32, 4, 256, drop_out=0.1)
+    plain = ImplicitGenerator3d("TALLSIREN_FG", 256, 32, 4, 256)
+    assert set(gen.state_dict()) == set(plain.state_dict())
+    gen.eval()
+    gen.siren.check_dropout()
+    gen.train()
+    with pytest.raises(NotImplementedError):
+        gen.siren.check_dropout()
+    plain.train()
+    plain.siren.check_dropout()
+
+
 def test_alias_classes():
     assert siren.TALLSIREN_dg is siren.TALLSIREN_FG and siren.DoubleSIREN_dg is siren.DOUBLESIREN_FG
 
