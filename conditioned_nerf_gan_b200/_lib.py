@@ -53,9 +53,10 @@ SIGNATURES = {
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cng_film_siren_wt_image_bytes": (c_size_t, [c_int]),
     "cng_film_siren_wt_images": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "cng_film_siren_dgrad": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    "cng_film_siren_dgrad": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_int, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
                                      ctypes.c_uint, ctypes.c_uint, c_void_p, c_size_t, c_void_p]),
-    "cng_film_siren_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "cng_film_siren_wgrad": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "cng_film_siren_head_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
     "cng_film_siren_bwd_workspace_bytes": (c_size_t, [c_longlong, c_int, c_int, c_int]),
     "cng_film_siren_bwd": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int, ctypes.c_uint, ctypes.c_uint, c_void_p, c_size_t, c_void_p,

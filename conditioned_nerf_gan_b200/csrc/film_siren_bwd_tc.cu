@@ -120,7 +120,8 @@ struct DgradParams {
   long long P, T;            // points, tiles
   int L;
   const uint8_t* wt;         // W^T images
-  const uint8_t* g;          // [L][T][65536]
+  const uint8_t* g;          // [L][g_stride tiles][65536]: layer l of this call's tiles starts at g + l * g_stride * 65536
+  long long g_stride;        // >= T (a dump that holds more tiles than this call processes, e.g. all items of a batch)
   uint8_t* dz;               // [L][T][65536] tile images (bf16), written
   float* d_feat;             // [P, 32]
   float* d_final_b;          // [4], accumulated
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) film_siren_dgrad_kernel(DgradPar
       mbar_arrive(act_ready(x));
       for (int s = 0; s < L; ++s) {
         const int l = L - 1 - s;                                           // this epilogue forms dz_l from dy_l (accumulator) and g_l
-        const uint4* gt = reinterpret_cast<const uint4*>(p.g + (static_cast<size_t>(l) * p.T + t) * kGTileBytes);
+        const uint4* gt = reinterpret_cast<const uint4*>(p.g + (static_cast<size_t>(l) * p.g_stride + t) * kGTileBytes);
         uint4 ga[4], gb[4];
         auto load_g = [&](uint4 (&gg)[4], int cc) {
 #pragma unroll
@@ -389,9 +390,9 @@ constexpr int kFlushWarps = 16, kMmaWarpW = 16, kProducerWarpW = 17, kThreadsW =
 
 struct WgradParams {
   const uint8_t* dz;         // [L][T][65536] (bf16)
-  const uint8_t* x;          // [L][T][65536]: x[l] = output of layer l
+  const uint8_t* x;          // [L][x_stride tiles][65536]: x[l] = output of layer l
   const uint8_t* feat;       // [T][16384]: layer-0 operand blocks [x_hi | x_lo]
-  long long T;
+  long long T, x_stride;
   int L;
   int x_half;                // 1: x / feat hold fp16, 0: bf16
   float* dW[16];             // [256][K_l] fp32, accumulated
@@ -464,7 +465,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) film_siren_wgrad_kernel(WgradPar
             if (l == 0) {
               bulk_g2s(st + 32768, p.feat + static_cast<size_t>(t) * kFeatImageBytes + hf * 8192, 8192, full(slot));
             } else {
-              const uint8_t* xs = p.x + (static_cast<size_t>(l - 1) * p.T + t) * kTileImageBytes + hf * 8192;
+              const uint8_t* xs = p.x + (static_cast<size_t>(l - 1) * p.x_stride + t) * kTileImageBytes + hf * 8192;
 #pragma unroll
               for (int j = 0; j < 4; ++j) bulk_g2s(st + 32768 + j * 8192, xs + j * kABlockBytes, 8192, full(slot));
             }
@@ -743,8 +744,8 @@ int cng_film_siren_wt_images(const float* const* layer_w_host, const float* freq
 }
 
 int cng_film_siren_dgrad(const float* d_out, const float* out, int sigmoid_rgb, long long P, int L, const void* wt_images,
-                         const void* g_dump, void* dz_dump, float* d_feat, float* d_final_b_acc, unsigned res_save_mask,
-                         unsigned res_add_mask, void* res_scratch, size_t res_scratch_bytes, cng_stream_t stream) {
+                         const void* g_dump, long long g_layer_stride_tiles, void* dz_dump, float* d_feat, float* d_final_b_acc,
+                         unsigned res_save_mask, unsigned res_add_mask, void* res_scratch, size_t res_scratch_bytes, cng_stream_t stream) {
   using namespace cng;
   using namespace cng::bwdtc;
   CNG_REQUIRE(P >= 0 && L >= 1 && L <= 16, CNG_ERR_INVALID_ARGUMENT, "film_siren_dgrad: bad shape");
@@ -776,13 +777,15 @@ int cng_film_siren_dgrad(const float* d_out, const float* out, int sigmoid_rgb, 
   DgradParams dp{};
   dp.d_out = d_out; dp.out = out; dp.sigmoid_rgb = sigmoid_rgb; dp.P = P; dp.T = (P + kTileM - 1) / kTileM; dp.L = L;
   dp.wt = static_cast<const uint8_t*>(wt_images); dp.g = static_cast<const uint8_t*>(g_dump); dp.dz = static_cast<uint8_t*>(dz_dump);
+  dp.g_stride = g_layer_stride_tiles > 0 ? g_layer_stride_tiles : dp.T;
+  CNG_REQUIRE(dp.g_stride >= dp.T, CNG_ERR_INVALID_ARGUMENT, "film_siren_dgrad: g_layer_stride_tiles %lld < %lld tiles", dp.g_stride, dp.T);
   dp.d_feat = d_feat; dp.d_final_b = d_final_b_acc;
   dp.res_save_mask = res_save_mask; dp.res_add_mask = res_add_mask; dp.res_scratch = static_cast<float*>(res_scratch);
   return dgrad_launch(dp, as_stream(stream));
 }
 
-int cng_film_siren_wgrad(const void* dz_dump, const void* x_dump, const void* feat_dump, long long P, int L, int x_is_fp16,
-                         float* const* d_w_acc_host, float* colsum_acc, cng_stream_t stream) {
+int cng_film_siren_wgrad(const void* dz_dump, const void* x_dump, long long x_layer_stride_tiles, const void* feat_dump, long long P, int L,
+                         int x_is_fp16, float* const* d_w_acc_host, float* colsum_acc, cng_stream_t stream) {
   using namespace cng;
   using namespace cng::bwdtc;
   CNG_REQUIRE(P >= 0 && L >= 1 && L <= 16, CNG_ERR_INVALID_ARGUMENT, "film_siren_wgrad: bad shape");
@@ -794,12 +797,31 @@ int cng_film_siren_wgrad(const void* dz_dump, const void* x_dump, const void* fe
   WgradParams wp{};
   wp.dz = static_cast<const uint8_t*>(dz_dump); wp.x = static_cast<const uint8_t*>(x_dump); wp.feat = static_cast<const uint8_t*>(feat_dump);
   wp.T = (P + kTileM - 1) / kTileM; wp.L = L; wp.x_half = x_is_fp16 ? 1 : 0; wp.colsum = colsum_acc;
+  wp.x_stride = x_layer_stride_tiles > 0 ? x_layer_stride_tiles : wp.T;
+  CNG_REQUIRE(wp.x_stride >= wp.T, CNG_ERR_INVALID_ARGUMENT, "film_siren_wgrad: x_layer_stride_tiles %lld < %lld tiles", wp.x_stride, wp.T);
   for (int l = 0; l < L; ++l) {
     CNG_REQUIRE(d_w_acc_host[l] && (reinterpret_cast<uintptr_t>(d_w_acc_host[l]) & 15) == 0, CNG_ERR_INVALID_ARGUMENT,
                 "film_siren_wgrad: d_w_acc[%d] NULL or not 16-byte aligned", l);
     wp.dW[l] = d_w_acc_host[l];
   }
   return wgrad_launch(wp, as_stream(stream));
+}
+
+int cng_film_siren_head_wgrad(const float* d_out, const float* out, int sigmoid_rgb, const void* x_last_tiles, long long P, int x_is_fp16,
+                              float* d_final_w_acc, cng_stream_t stream) {
+  using namespace cng;
+  using namespace cng::bwdtc;
+  CNG_REQUIRE(P >= 0, CNG_ERR_INVALID_ARGUMENT, "film_siren_head_wgrad: P=%lld", P);
+  if (P == 0) return CNG_OK;
+  CNG_REQUIRE(d_out && x_last_tiles && d_final_w_acc && (!sigmoid_rgb || out), CNG_ERR_INVALID_ARGUMENT, "film_siren_head_wgrad: NULL pointer");
+  CNG_REQUIRE(((reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(x_last_tiles)) & 15) == 0,
+              CNG_ERR_INVALID_ARGUMENT, "film_siren_head_wgrad: buffers not 16-byte aligned");
+  if (int e = cng_device_check()) return e;
+  const long long T = (P + kTileM - 1) / kTileM;
+  const unsigned grid = static_cast<unsigned>(min(static_cast<long long>(2 * sm_count()), T));
+  if (x_is_fp16) head_wgrad_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(d_out, out, sigmoid_rgb, static_cast<const uint8_t*>(x_last_tiles), P, T, d_final_w_acc);
+  else head_wgrad_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(d_out, out, sigmoid_rgb, static_cast<const uint8_t*>(x_last_tiles), P, T, d_final_w_acc);
+  return check_launch("cng_film_siren_head_wgrad");
 }
 
 int cng_film_siren_bwd(const float* feat, const float* d_out, long long P, int C, int HID, int L, const float* const* layer_w_host,
@@ -835,19 +857,13 @@ int cng_film_siren_bwd(const float* feat, const float* d_out, long long P, int C
   // 2. W^T operand images
   if (int e = cng_film_siren_wt_images(layer_w_host, freq, final_w, C, HID, L, ws + lay.wt, stream)) return e;
   // 3. dgrad chain: d_feat, d_final_b, dz tile images
-  if (int e = cng_film_siren_dgrad(d_out, out_tmp, sigmoid_rgb, P, L, ws + lay.wt, ws + lay.gs, ws + lay.dzs, d_feat, d_final_b_acc, res_save_mask,
+  if (int e = cng_film_siren_dgrad(d_out, out_tmp, sigmoid_rgb, P, L, ws + lay.wt, ws + lay.gs, 0, ws + lay.dzs, d_feat, d_final_b_acc, res_save_mask,
                                    res_add_mask, res_scratch, res_scratch_bytes, stream))
     return e;
   // 4. weight gradients + column sums
-  if (int e = cng_film_siren_wgrad(ws + lay.dzs, ws + lay.xs, ws + lay.feat, P, L, 1, d_w_acc_host, colsum_acc, stream)) return e;
+  if (int e = cng_film_siren_wgrad(ws + lay.dzs, ws + lay.xs, 0, ws + lay.feat, P, L, 1, d_w_acc_host, colsum_acc, stream)) return e;
   // 5. head weights
-  {
-    const unsigned grid = static_cast<unsigned>(min(static_cast<long long>(2 * sm_count()), T));
-    head_wgrad_kernel<true><<<grid, 256, 0, st>>>(d_out, out_tmp, sigmoid_rgb, ws + lay.xs + static_cast<size_t>(L - 1) * T * kTileImageBytes, P, T,
-                                                   d_final_w_acc);
-    if (int e = check_launch("cng_film_siren_bwd: head weights")) return e;
-  }
-  return CNG_OK;
+  return cng_film_siren_head_wgrad(d_out, out_tmp, sigmoid_rgb, ws + lay.xs + static_cast<size_t>(L - 1) * T * kTileImageBytes, P, 1, d_final_w_acc, stream);
 }
 
 }  // extern "C"

@@ -25,8 +25,64 @@ import torch
 from .. import ops
 from .volumetric_rendering import camera_tables
 
+import os
+
 HAS_BACKWARD = True
 CHUNK_ROWS = 1 << 20          # points per recompute chunk of the MLP backward (~13 GB of x / g / dz dumps at L = 8)
+# "auto": when the x / g dumps of the WHOLE batch fit comfortably in free device memory (small per-GPU batches: the 8-GPU
+# operating point), the forward of a training step runs the training-mode kernel once and keeps its dumps for the backward,
+# which then skips the recompute; otherwise (and with "0") the forward keeps nothing and the backward recomputes per chunk.
+KEEP_DUMPS = os.environ.get("CNG_KEEP_DUMPS", "auto")
+KEEP_DUMPS_MEMORY_FRACTION = 0.35     # of the memory that is free (plus cached by the allocator) when the forward runs
+
+
+class _DumpBuffers:
+    """x / g / feature dump buffers of one kept forward, taken from a per-device pool and handed back after the backward (or when
+    the graph is dropped without one).  The pool keeps them allocated across steps: tens of GB going through the caching
+    allocator every step fragment it into cudaMalloc / cudaFree cycles, which synchronise the device (measured: the kept path
+    was 19 % SLOWER than recomputing inside a full GAN step until the buffers became persistent)."""
+    _pool = {}
+
+    def __init__(self, L: int, tiles: int, dev):
+        self.key = (dev.index if dev.index is not None else torch.cuda.current_device(), L, tiles)
+        free = self._pool.setdefault(self.key, [])
+        if free:
+            self.tensors = free.pop()
+        else:
+            self.tensors = (torch.empty((L, tiles, ops.TILE_IMAGE_BYTES), dtype=torch.uint8, device=dev),
+                            torch.empty((L, tiles, ops.TILE_IMAGE_BYTES), dtype=torch.uint8, device=dev),
+                            torch.empty((tiles, ops.FEAT_IMAGE_BYTES), dtype=torch.uint8, device=dev))
+
+    def release(self) -> None:
+        if self.tensors is not None:
+            self._pool[self.key].append(self.tensors)
+            self.tensors = None
+
+    def __del__(self):
+        self.release()
+
+    @classmethod
+    def pooled_bytes(cls, dev_index: int) -> int:
+        return sum(sum(t.numel() for t in ts) for k, free in cls._pool.items() if k[0] == dev_index for ts in free)
+
+    @classmethod
+    def clear(cls) -> None:
+        cls._pool.clear()
+
+
+def _keep_dumps(B: int, N: int, L: int, dev) -> bool:
+    if KEEP_DUMPS == "0" or N > CHUNK_ROWS:
+        return False
+    if KEEP_DUMPS == "1":
+        return True
+    tiles = B * ((N + ops.TILE_POINTS - 1) // ops.TILE_POINTS)
+    need = 2 * L * tiles * ops.TILE_IMAGE_BYTES + tiles * ops.FEAT_IMAGE_BYTES
+    need += L * ((N + ops.TILE_POINTS - 1) // ops.TILE_POINTS) * ops.TILE_IMAGE_BYTES      # one item's dz dump at backward time
+    if _DumpBuffers._pool.get((dev.index if dev.index is not None else torch.cuda.current_device(), L, tiles)):
+        return True                                   # a pooled buffer of this shape is waiting: no new memory needed
+    free, _ = torch.cuda.mem_get_info(dev)
+    cached = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+    return need <= KEEP_DUMPS_MEMORY_FRACTION * (free + cached)
 
 
 class _ToChannelsLast(torch.autograd.Function):
@@ -110,7 +166,16 @@ class _FilmSiren(torch.autograd.Function):
             # fail here, not deep inside backward(): the tcgen05 backward kernels are built for the shipped shape only
             raise NotImplementedError(f"training needs input_dim=32 and hidden_dim=256 (got {feat.shape[-1]}, {final_w.shape[1]}): "
                                       "the MLP backward (cng_film_siren_bwd) is built for that shape")
-        out = ops.film_siren_fwd(feat, ws, bs, freq, phase, final_w, final_b, sigmoid_rgb, precision, res_save, res_add)
+        B, N = feat.shape[0], feat.shape[1]
+        ctx.dumps = None
+        if precision != "fp32" and _keep_dumps(B, N, L, feat.device):
+            # the training-mode kernel IS the forward (fp16 operands): its dumps stay alive until backward, no recompute there
+            tiles = B * ((N + ops.TILE_POINTS - 1) // ops.TILE_POINTS)
+            ctx.dumps = _DumpBuffers(L, tiles, feat.device)
+            out = ops.film_siren_fwd_train(feat, ws, bs, freq, phase, final_w, final_b, sigmoid_rgb, "fp16", res_save, res_add,
+                                           dumps=ctx.dumps.tensors)[0]
+        else:
+            out = ops.film_siren_fwd(feat, ws, bs, freq, phase, final_w, final_b, sigmoid_rgb, precision, res_save, res_add)
         ctx.save_for_backward(feat, freq, phase, final_w, final_b, out, *wb)
         ctx.sigmoid_rgb, ctx.L, ctx.res_save, ctx.res_add = sigmoid_rgb, L, res_save, res_add
         return out
@@ -142,12 +207,27 @@ class _FilmSiren(torch.autograd.Function):
         colsum_all = torch.zeros((B, L, H), dtype=torch.float32, device=dev)
         fr = freq.detach().float().contiguous()
         ph = phase.detach().float().contiguous()
+        dumps, ctx.dumps = ctx.dumps, None
+        tiles_per_item = (N + ops.TILE_POINTS - 1) // ops.TILE_POINTS
         for b in range(B):
             dW_item = [d[b] for d in dW_all]
+            if dumps is not None:
+                # kept dumps (one training-mode forward for the whole batch): dgrad chain, weight gradient and head per item,
+                # each reading its own tiles of every layer
+                xs, gs, fd = dumps.tensors
+                wt = ops.film_siren_wt_images(ws, fw, fr[b])
+                _, dz = ops.film_siren_dgrad(d_out[b], out[b], ctx.sigmoid_rgb, L, wt, gs, d_fb, ctx.res_save, ctx.res_add,
+                                             tile_offset=b * tiles_per_item, d_feat=d_feat[b])
+                ops.film_siren_wgrad(dz, xs, fd, N, L, True, dW_item, colsum_all[b], tile_offset=b * tiles_per_item)
+                ops.film_siren_head_wgrad(d_out[b], out[b], ctx.sigmoid_rgb, xs, L, N, True, d_fw, tile_offset=b * tiles_per_item)
+                del dz
+                continue
             for r0 in range(0, N, CHUNK_ROWS):
                 r1 = min(N, r0 + CHUNK_ROWS)
                 ops.film_siren_bwd(feat[b, r0:r1].detach().contiguous(), d_out[b, r0:r1].contiguous(), ws, bs, fr[b], ph[b], fw, fb,
                                    ctx.sigmoid_rgb, d_feat[b, r0:r1], dW_item, colsum_all[b], d_fw, d_fb, ctx.res_save, ctx.res_add)
+        if dumps is not None:
+            dumps.release()                               # stream-ordered: the next forward's writes queue behind this backward's reads
         frv = fr.view(B, L, H)
         d_phase = colsum_all.reshape(B, L * H)
         wdw = torch.stack([(ws[l].unsqueeze(0) * dW_all[l]).sum(2) for l in range(L)], dim=1)       # [B, L, H]

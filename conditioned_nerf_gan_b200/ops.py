@@ -464,7 +464,7 @@ FEAT_IMAGE_BYTES = 16384
 
 
 def film_siren_fwd_train(feat, layer_w, layer_b, freq, phase, final_w, final_b, sigmoid_rgb: bool, precision: str = "fp16",
-                         res_save_mask: int = 0, res_add_mask: int = 0):
+                         res_save_mask: int = 0, res_add_mask: int = 0, dumps=None):
     """Training-mode K2 (the backward's recompute): rgb_sigma [B,N,4] plus the dumps in the formats of include/cng_b200.h --
     x [L,T,65536] uint8 (operand tile images), g = cos(u) [L,T,65536] uint8 (fp16, epilogue order), feat [T,16384] uint8 -- with
     T = B * ceil(N / 128)."""
@@ -481,9 +481,14 @@ def film_siren_fwd_train(feat, layer_w, layer_b, freq, phase, final_w, final_b, 
     dev = feat.device
     T = B * ((N + TILE_POINTS - 1) // TILE_POINTS)
     out = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
-    xs = torch.empty((L, T, TILE_IMAGE_BYTES), dtype=torch.uint8, device=dev)
-    gs = torch.empty((L, T, TILE_IMAGE_BYTES), dtype=torch.uint8, device=dev)
-    fd = torch.empty((T, FEAT_IMAGE_BYTES), dtype=torch.uint8, device=dev)
+    if dumps is not None:                      # caller-owned (pooled) dump buffers of exactly this shape
+        xs, gs, fd = dumps
+        if xs.shape != (L, T, TILE_IMAGE_BYTES) or gs.shape != xs.shape or fd.shape != (T, FEAT_IMAGE_BYTES):
+            raise ValueError("film_siren_fwd_train: dump buffers of the wrong shape")
+    else:
+        xs = torch.empty((L, T, TILE_IMAGE_BYTES), dtype=torch.uint8, device=dev)
+        gs = torch.empty((L, T, TILE_IMAGE_BYTES), dtype=torch.uint8, device=dev)
+        fd = torch.empty((T, FEAT_IMAGE_BYTES), dtype=torch.uint8, device=dev)
     w_arr = (ctypes.c_void_p * L)(*[w.data_ptr() for w in ws])
     b_arr = (ctypes.c_void_p * L)(*[b.data_ptr() for b in bs])
     lib = _lib.load()
@@ -515,32 +520,55 @@ def film_siren_wt_images(layer_w, final_w, freq=None) -> torch.Tensor:
     return img
 
 
-def film_siren_dgrad(d_out, out, sigmoid_rgb: bool, L: int, wt_images, g_dump, d_final_b_acc, res_save_mask: int = 0, res_add_mask: int = 0):
+def _tile_ptr(dump: torch.Tensor, layer: int, tile: int, stride_tiles: int):
+    """Address of tile ``tile`` of layer ``layer`` inside a [L, stride_tiles, 65536] uint8 dump."""
+    return ctypes.c_void_p(dump.data_ptr() + (layer * stride_tiles + tile) * TILE_IMAGE_BYTES)
+
+
+def film_siren_dgrad(d_out, out, sigmoid_rgb: bool, L: int, wt_images, g_dump, d_final_b_acc, res_save_mask: int = 0, res_add_mask: int = 0,
+                     tile_offset: int = 0, d_feat=None):
     """The fused dgrad chain (cng_film_siren_dgrad): d_out / out [P,4] -> (d_feat [P,32], dz tile images [L,T,65536] uint8);
-    accumulates the head bias gradient into d_final_b_acc [4]."""
+    accumulates the head bias gradient into d_final_b_acc [4].  ``g_dump`` [L, T_total, 65536]: this call reads tiles
+    [tile_offset, tile_offset + T) of every layer (a batch's dumps consumed item by item)."""
     d_out = _f32(d_out, "d_out")
     P = d_out.shape[0]
     out = _f32(out, "out") if out is not None else None
     dev = d_out.device
     T = (P + TILE_POINTS - 1) // TILE_POINTS
     dz = torch.empty((L, T, TILE_IMAGE_BYTES), dtype=torch.uint8, device=dev)
-    d_feat = torch.empty((P, 32), dtype=torch.float32, device=dev)
+    if d_feat is None:
+        d_feat = torch.empty((P, 32), dtype=torch.float32, device=dev)
+    elif not (d_feat.is_cuda and d_feat.dtype == torch.float32 and d_feat.is_contiguous() and d_feat.shape == (P, 32)):
+        raise RuntimeError("film_siren_dgrad: d_feat must be a contiguous float32 CUDA tensor [P, 32]")
     scratch = _res_scratch(dev) if (res_save_mask or res_add_mask) else None
     with torch.cuda.device(dev), _timed("cng_film_siren_dgrad"):
-        _lib.call("cng_film_siren_dgrad", _ptr(d_out), _ptr(out), int(bool(sigmoid_rgb)), P, L, _ptr(wt_images), _ptr(g_dump), _ptr(dz),
+        _lib.call("cng_film_siren_dgrad", _ptr(d_out), _ptr(out), int(bool(sigmoid_rgb)), P, L, _ptr(wt_images),
+                  _tile_ptr(g_dump, 0, tile_offset, g_dump.shape[1]), g_dump.shape[1], _ptr(dz),
                   _ptr(d_feat), _ptr(d_final_b_acc), int(res_save_mask), int(res_add_mask), _ptr(scratch),
                   scratch.numel() if scratch is not None else 0, _stream(d_out))
     _count()
     return d_feat, dz
 
 
-def film_siren_wgrad(dz_dump, x_dump, feat_dump, P: int, L: int, x_is_fp16: bool, d_w_acc, colsum_acc) -> None:
+def film_siren_wgrad(dz_dump, x_dump, feat_dump, P: int, L: int, x_is_fp16: bool, d_w_acc, colsum_acc, tile_offset: int = 0) -> None:
     """Weight gradients by split-K over the points (cng_film_siren_wgrad): d_w_acc[l] [256,K_l] += dz_l^T x_l, colsum_acc [L,256] +=
-    column sums of dz_l."""
+    column sums of dz_l.  ``x_dump`` [>= L-1, T_total, 65536] / ``feat_dump`` [T_total, 16384]: tiles from ``tile_offset`` on."""
     arr = (ctypes.c_void_p * L)(*[t.data_ptr() for t in d_w_acc])
+    stride = x_dump.shape[1] if x_dump is not None else 0
+    xp = _tile_ptr(x_dump, 0, tile_offset, stride) if x_dump is not None else None
+    fp = ctypes.c_void_p(feat_dump.data_ptr() + tile_offset * FEAT_IMAGE_BYTES)
     with torch.cuda.device(dz_dump.device), _timed("cng_film_siren_wgrad"):
-        _lib.call("cng_film_siren_wgrad", _ptr(dz_dump), _ptr(x_dump), _ptr(feat_dump), P, L, int(bool(x_is_fp16)), arr, _ptr(colsum_acc),
-                  _stream(dz_dump))
+        _lib.call("cng_film_siren_wgrad", _ptr(dz_dump), xp, stride, fp, P, L, int(bool(x_is_fp16)), arr, _ptr(colsum_acc), _stream(dz_dump))
+    _count()
+
+
+def film_siren_head_wgrad(d_out, out, sigmoid_rgb: bool, x_dump, L: int, P: int, x_is_fp16: bool, d_final_w_acc, tile_offset: int = 0) -> None:
+    """d_final_w_acc [4,256] += d_o^T x_L from the last layer's tile images of ``x_dump`` (cng_film_siren_head_wgrad)."""
+    d_out = _f32(d_out, "d_out")
+    out = _f32(out, "out") if out is not None else None
+    with torch.cuda.device(d_out.device), _timed("cng_film_siren_head_wgrad"):
+        _lib.call("cng_film_siren_head_wgrad", _ptr(d_out), _ptr(out), int(bool(sigmoid_rgb)), _tile_ptr(x_dump, L - 1, tile_offset, x_dump.shape[1]),
+                  P, int(bool(x_is_fp16)), _ptr(d_final_w_acc), _stream(d_out))
     _count()
 
 

@@ -320,16 +320,23 @@ CNG_API int cng_film_siren_wt_images(const float* const* layer_w_host, const flo
  *   dy = d_o Wf, then for l = L-1 .. 0: dz_l = dy * g_l (-> dz_dump), dy = dz_l W_l; d_feat [P, 32] = dz_0 W_0 (written).
  * A kept activation of a residual block additionally receives the adding layer's dz (masks / scratch as in
  * cng_film_siren_fwd_res; only patterns where an add sits exactly two layers after its kept layer: CNG_ERR_UNSUPPORTED
- * otherwise). */
+ * otherwise).  g_layer_stride_tiles (here) / x_layer_stride_tiles (below): tiles per layer of a dump that holds more tiles than
+ * this call processes -- the dumps of a whole batch written by ONE cng_film_siren_fwd_train call and consumed item by item, g_dump /
+ * x_dump pointing at the item's first tile; 0 = this call's own tile count. */
 CNG_API int cng_film_siren_dgrad(const float* d_out, const float* out, int sigmoid_rgb, long long P, int L,
-                         const void* wt_images, const void* g_dump, void* dz_dump, float* d_feat,
-                         float* d_final_b_acc, unsigned res_save_mask, unsigned res_add_mask, void* res_scratch,
-                         size_t res_scratch_bytes, cng_stream_t stream);
+                         const void* wt_images, const void* g_dump, long long g_layer_stride_tiles, void* dz_dump,
+                         float* d_feat, float* d_final_b_acc, unsigned res_save_mask, unsigned res_add_mask,
+                         void* res_scratch, size_t res_scratch_bytes, cng_stream_t stream);
 /* Weight gradients as a split-K contraction over the points: d_w_acc_host[l] [HID, K_l] += dz_l^T x_l (x_0 = the features,
  * hi + lo), colsum_acc [L, HID] += column sums of dz_l.  Both operands are read from the tile images with MN-major
  * descriptors; fp32 accumulation in TMEM, one red.global.add flush per CTA and layer.  x_is_fp16: format of x_dump / feat_dump. */
-CNG_API int cng_film_siren_wgrad(const void* dz_dump, const void* x_dump, const void* feat_dump, long long P, int L,
-                         int x_is_fp16, float* const* d_w_acc_host, float* colsum_acc, cng_stream_t stream);
+CNG_API int cng_film_siren_wgrad(const void* dz_dump, const void* x_dump, long long x_layer_stride_tiles,
+                         const void* feat_dump, long long P, int L, int x_is_fp16, float* const* d_w_acc_host,
+                         float* colsum_acc, cng_stream_t stream);
+/* Head weights: d_final_w_acc [4, HID] += d_o^T x_L, d_o as in cng_film_siren_dgrad, x_L = the tile images of the last layer's
+ * output (x_dump + (L - 1) * stride * 65536 [+ the item's tile offset]). */
+CNG_API int cng_film_siren_head_wgrad(const float* d_out, const float* out, int sigmoid_rgb, const void* x_last_tiles,
+                              long long P, int x_is_fp16, float* d_final_w_acc, cng_stream_t stream);
 /* The whole MLP backward of one chunk of points of ONE batch item in one call: recompute with dumps (fp16 operands), W^T
  * images, dgrad chain, weight gradients, head weights.
  *   feat [P, C]; d_out [P, 4] gradient w.r.t. rgb_sigma;

@@ -297,6 +297,45 @@ def test_latent_shortsiren_backward_vs_oracle_autograd():
         assert c > 0.9995 and e < 2e-2, (k, e, c)
 
 
+@pytest.mark.parametrize("name", ["fwd_TALLSIREN_FG", "fwd_TALLSIREN_dRes"])
+def test_kept_dumps_backward_equals_recompute_backward(name):
+    """Training with the forward's dumps kept for the backward (CNG_KEEP_DUMPS: one training-mode forward for the whole batch, the
+    dgrad / weight-gradient kernels reading each item's tiles out of the batch dump) against the recomputing backward."""
+    from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d, autograd
+    state, siren_type, z, cam, draws, meta, _ = fixture_inputs(name)
+    B, img = cam.shape[0], meta["img_size"]
+    g = torch.Generator().manual_seed(3)
+    d_pix, d_dep = dev(torch.randn((B, 3, img, img), generator=g)), dev(torch.randn((B, img, img), generator=g))
+    gen = ImplicitGenerator3d(siren_type, 32 if "dRes" in siren_type else 256, 32, 4, 256)
+    gen.load_state_dict(state, strict=True)
+    gen = gen.to("cuda")
+    gen.siren.precision = "fp16"
+    film = isinstance(z, tuple)
+    grads = {}
+    prev = autograd.KEEP_DUMPS
+    try:
+        for mode in ("0", "1"):
+            autograd.KEEP_DUMPS = mode
+            gen.zero_grad(set_to_none=True)
+            vol = dev(z[0] if film else z).requires_grad_(True)
+            glob = dev(z[1]).requires_grad_(True) if film else None
+            pixels, depth = gen((vol, glob) if film else vol, dev(cam), draws={k: dev(v) for k, v in draws.items()}, **meta)
+            ((pixels * d_pix).sum() + (depth * d_dep).sum()).backward()
+            grads[mode] = {"volume": vol.grad.clone(), **{k: p.grad.clone() for k, p in gen.siren.named_parameters()}}
+            if film:
+                grads[mode]["global"] = glob.grad.clone()
+    finally:
+        autograd.KEEP_DUMPS = prev
+    worst = 0.0
+    for k in grads["0"]:
+        e = rel_l2(grads["1"][k].cpu(), grads["0"][k].cpu())
+        worst = max(worst, e)
+        print(f"  kept vs recompute {name} {k}: rel-L2 {e:.2e}")
+    # same backward kernels on the same dumps; the two forwards differ in which sines take the FMA-pipe polynomial (1 in 8 vs 1 in 4,
+    # 7e-5 each), which the FiLM frequencies (~30 per layer) amplify into the loss gradient
+    assert worst < 1e-2, worst
+
+
 def test_siren_boundary_backward_and_amp():
     """gen.siren(points, z, ...) with grad, under autocast + GradScaler-style scaling (utils.py:645-711)."""
     from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d
