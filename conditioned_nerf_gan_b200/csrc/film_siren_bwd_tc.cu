@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) film_siren_wgrad_kernel(WgradPar
 // One block per slab of tiles; x_L is read from its tile images 16 bytes at a time: lane = (K-block, logical 16-byte chunk) of
 // one row, so a warp reads the four 128-byte lines of a row per load; warp w takes rows w, w + 8, ... of every tile.
 template <bool kHalf>
-__global__ void __launch_bounds__(256) head_wgrad_kernel(const float* __restrict__ d_out, const float* __restrict__ out, int sigmoid_rgb,
+__global__ void __launch_bounds__(256, 3) head_wgrad_kernel(const float* __restrict__ d_out, const float* __restrict__ out, int sigmoid_rgb,
                                                          const uint8_t* __restrict__ xL, long long P, long long T, float* __restrict__ d_final_w) {
   __shared__ float4 s_do[kTileM];
   __shared__ float s_red[8][4][kHID];
@@ -627,7 +627,7 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const float* __restrict
     }
     __syncthreads();
     const uint8_t* img = xL + static_cast<size_t>(t) * kTileImageBytes + blk * kABlockBytes;
-#pragma unroll 4
+#pragma unroll 8
     for (int r = w; r < kTileM; r += 8) {
       const uint4 q4 = __ldg(reinterpret_cast<const uint4*>(img + r * 128 + ((ch ^ (r & 7)) << 4)));
       const uint32_t qw[4] = {q4.x, q4.y, q4.z, q4.w};
@@ -818,7 +818,7 @@ int cng_film_siren_head_wgrad(const float* d_out, const float* out, int sigmoid_
               CNG_ERR_INVALID_ARGUMENT, "film_siren_head_wgrad: buffers not 16-byte aligned");
   if (int e = cng_device_check()) return e;
   const long long T = (P + kTileM - 1) / kTileM;
-  const unsigned grid = static_cast<unsigned>(min(static_cast<long long>(2 * sm_count()), T));
+  const unsigned grid = static_cast<unsigned>(min(static_cast<long long>(3 * sm_count()), T));     // latency-bound streaming: 3 blocks per SM
   if (x_is_fp16) head_wgrad_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(d_out, out, sigmoid_rgb, static_cast<const uint8_t*>(x_last_tiles), P, T, d_final_w_acc);
   else head_wgrad_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(d_out, out, sigmoid_rgb, static_cast<const uint8_t*>(x_last_tiles), P, T, d_final_w_acc);
   return check_launch("cng_film_siren_head_wgrad");
