@@ -867,6 +867,26 @@ def test_latent_shortsiren_forward_vs_reference(precision):
     assert psnr >= (60.0 if precision == "fp32" else 40.0)
 
 
+def test_second_device_renders_like_the_first(ops):
+    """The shared-memory opt-in of the large kernels is cached per device ordinal: a process that renders on
+    cuda:0 and then on cuda:1 must get the same image from both.  Needs two visible GPUs (skipped on a one-GPU box)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    siren_type, state, z, cam, draws, meta = _full_size_case(1, 32, 8, 16, 80, True)
+    imgs = []
+    for index in (0, 1):
+        d = torch.device("cuda", index)
+        from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d
+        gen = ImplicitGenerator3d(siren_type, 256, 32, 4, 256)
+        gen.load_state_dict(state, strict=True)
+        gen = gen.to(d)
+        gen.set_device(d)
+        with torch.no_grad():
+            px, _ = gen((z[0].to(d), z[1].to(d)), cam.to(d), draws={k: v.to(d) for k, v in draws.items()}, **meta)
+        imgs.append(px.cpu())
+    assert torch.equal(imgs[0], imgs[1])
+
+
 def test_fp16_host_volume_path(ops):
     """A feature volume held in fp16 (the encoder's autocast dtype; what bench.py's end-to-end leg uploads): the layout pass widens
     it exactly (cng_volume_f16_to_channels_last), and the image stays at the tensor-core bar against the oracle on the fp32 volume."""
