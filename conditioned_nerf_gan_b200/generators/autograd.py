@@ -317,6 +317,47 @@ def render_with_grad(gen, volume, global_feature, cam2worlds, img_size, fov, ray
                                  white_back, last_back)
 
 
+def render_library(gen, z, cam2worlds, img_size, fov, ray_start, ray_end, num_steps, hierarchical_sample, kwargs):
+    """generators/generators.py:33-187 for the decoders whose MLP is a PyTorch op chain (generators/siren_library.py): K1 in
+    points-only mode, ``gen.siren(points, z, ...)`` (library MLP around the library's trilinear kernels, differentiable when grad
+    is enabled), K3 / K4 for the resampling (no gradient, generators.py:111), K3' (with its backward kernel when grad is enabled)."""
+    clamp_mode, nerf_noise = kwargs["clamp_mode"], kwargs["nerf_noise"]
+    white_back, last_back = kwargs.get("white_back", False), kwargs.get("last_back", False)
+    ops.clamp_code(clamp_mode)
+    draws = kwargs.get("draws") or {}
+    net = gen.siren
+    B, S, R = cam2worlds.shape[0], int(num_steps), int(img_size) ** 2
+    dev = cam2worlds.device
+    rays_d_cam, t_lin = camera_tables((img_size, img_size), S, fov, ray_start, ray_end, dev)
+    grad = torch.is_grad_enabled()
+
+    def draw(name, fn, shape):
+        t = draws.get(name)
+        return fn(shape, device=dev) if t is None else t.to(dev)
+
+    def composite(fine, coarse, t_f, t_c, noise):
+        if grad and (coarse.requires_grad or (fine is not None and fine.requires_grad)):
+            return _MergeComposite.apply(fine, coarse, t_f, t_c, noise, rays_d_cam, B, img_size, nerf_noise, clamp_mode, white_back, last_back)
+        return ops.merge_composite(fine, coarse, t_f, t_c, noise, rays_d_cam, B, img_size, img_size, nerf_noise, clamp_mode, white_back, last_back)
+
+    u_jitter = draw("u_jitter", torch.rand, (B, R, S, 1))
+    with torch.no_grad():
+        t_c, pts_c = ops.raymarch_points_coarse(cam2worlds, rays_d_cam, t_lin, u_jitter, img_size, img_size)
+    coarse = net(pts_c.view(B, R * S, 3), z, img_size, S).float().contiguous()
+    if hierarchical_sample:
+        with torch.no_grad():
+            noise_c = draw("noise_coarse", torch.randn, (B, R, S, 1))
+            _, _, w_c = ops.composite_fwd(coarse.detach().view(B, R, S, 4), t_c, noise_c, nerf_noise, clamp_mode)
+            u_re = draw("u_resample", torch.rand, (B * R, S))
+            t_f = ops.resample_from_coarse(t_c, w_c, u_re)
+            pts_f = ops.raymarch_points_fine(cam2worlds, rays_d_cam, t_f, img_size, img_size)
+        fine = net(pts_f.view(B, R * S, 3), z, img_size, S).float().contiguous()
+        noise_f = draw("noise_final", torch.randn, (B, R, 2 * S, 1))
+        return composite(fine, coarse, t_f, t_c, noise_f)
+    noise_f = draw("noise_final" if "noise_final" in draws else "noise_coarse", torch.randn, (B, R, S, 1))
+    return composite(None, coarse, None, t_c, noise_f)
+
+
 def siren_forward_with_grad(net, points, volume, global_feature):
     """``siren(points, z, img_size, num_steps)`` with gradients (siren.py:540-580)."""
     vol_cl = _ToChannelsLast.apply(volume.float())

@@ -55,6 +55,10 @@ class ImplicitGenerator3d(nn.Module):
         and ``nerf_noise`` are required (KeyError otherwise, as in the reference), ``white_back`` /
         ``last_back`` default to False, every other key is ignored."""
         volume, global_feature = self.siren.split_z(z)
+        if getattr(self.siren, "library_mlp", False):
+            # TALLSIREN / TALLSIREN_dgx / SHORTSIREN_FG_Pyrmd: the library's kernels around a PyTorch MLP (generators/siren_library.py)
+            from .autograd import render_library
+            return render_library(self, z, cam2worlds, img_size, fov, ray_start, ray_end, num_steps, hierarchical_sample, kwargs)
         needs_grad = torch.is_grad_enabled() and (
             (volume is not None and volume.requires_grad) or (global_feature is not None and global_feature.requires_grad)
             or any(p.requires_grad for p in self.siren.parameters()))
@@ -188,6 +192,8 @@ class ImplicitGenerator3d(nn.Module):
         (per-frame fov sweep, inference.py:459).  ``nerf_noise`` is forced to 0."""
         volume, global_feature = self.siren.split_z(z)
         P = cam2worlds.shape[0]
+        if getattr(self.siren, "library_mlp", False):
+            return self._staged_forward_library(z, cam2worlds, img_size, fov, ray_start, ray_end, num_steps, hierarchical_sample, max_batch_size, kwargs)
         n_obj = global_feature.shape[0] if self.siren.latent else volume.shape[0]
         shared = n_obj == 1 and P > 1
         kwargs = dict(kwargs)
@@ -212,6 +218,36 @@ class ImplicitGenerator3d(nn.Module):
             o = self._render(None, None, cam2worlds[start:stop], img_size, fovs[start], ray_start, ray_end, num_steps,
                              hierarchical_sample, kwargs, vol_cl=v, film=f)
             pixels[start:stop], depth[start:stop] = o["pixels"], o["depth"]
+            start = stop
+        return pixels, depth
+
+    def _staged_forward_library(self, z, cam2worlds, img_size, fov, ray_start, ray_end, num_steps, hierarchical_sample, max_batch_size, kwargs):
+        """``staged_forward`` for the library-MLP decoders: pose chunks through ``autograd.render_library``; one object is expanded
+        to the chunk's poses."""
+        from .autograd import render_library
+        P = cam2worlds.shape[0]
+        kwargs = dict(kwargs)
+        kwargs["nerf_noise"] = 0
+        kwargs.setdefault("clamp_mode", "relu")
+        fovs = [float(fov)] * P if not hasattr(fov, "__len__") else [float(f) for f in fov]
+
+        def take(t, start, stop):
+            if isinstance(t, (list, tuple)):
+                return type(t)(take(x, start, stop) for x in t)
+            if t.shape[0] == 1 and P > 1:
+                return t.expand(stop - start, *t.shape[1:]).contiguous()
+            return t[start:stop]
+
+        pixels = torch.empty((P, 3, img_size, img_size), dtype=torch.float32, device=cam2worlds.device)
+        depth = torch.empty((P, img_size, img_size), dtype=torch.float32, device=cam2worlds.device)
+        start = 0
+        while start < P:
+            stop = min(start + max_batch_size, P)
+            while stop > start + 1 and fovs[stop - 1] != fovs[start]:
+                stop -= 1
+            px, dp = render_library(self, take(z, start, stop), cam2worlds[start:stop], img_size, fovs[start], ray_start, ray_end, num_steps,
+                                    hierarchical_sample, kwargs)
+            pixels[start:stop], depth[start:stop] = px, dp
             start = stop
         return pixels, depth
 

@@ -344,3 +344,8 @@ TALLSIREN_dg = TALLSIREN_FG
 SHORTSIREN_dg = SHORTSIREN_FG
 DoubleSIREN_dg = DOUBLESIREN_FG
 DOUBLESIREN_dg = DOUBLESIREN_FG
+
+
+# the decoders whose MLP is a library (PyTorch) op chain rather than the fused kernels: TALLSIREN (per-point FiLM), TALLSIREN_dgx,
+# SHORTSIREN_FG_Pyrmd -- imported here so that ``getattr(siren, siren_type)`` (generators.py:15) resolves every reference class
+from .siren_library import PointFeaturesMappingNetwork, PointwiseFiLMLayer, SHORTSIREN_FG_Pyrmd, TALLSIREN, TALLSIREN_dgx  # noqa: E402,F401

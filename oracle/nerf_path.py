@@ -91,6 +91,13 @@ SIREN_SPECS = {
     # the world position itself (input_dim = 3), z is a latent vector [B, z_dim] (PointNet encoder) mapped to the FiLM parameters
     # by CustomMappingNetwork (:55-78: three hidden Linear + LeakyReLU(0.2), kaiming_leaky_init, last weight x 0.25)
     "SHORTSIREN": {"layers": 4, "freq_init": 25.0, "sigmoid_rgb": True, "latent": True},
+    # generators/siren.py:232-331: FiLM layers on the POSITION; frequencies / phases per point from PointFeaturesMappingNetwork
+    # (:81-101) on the point's trilinear features; z = the feature volume alone; raw head (:326)
+    "TALLSIREN": {"layers": 8, "freq_init": 25.0, "sigmoid_rgb": False, "pointwise": True},
+    # :1068-1169: layer 0 reads cat([features, position]) (:1153); per-item FiLM from the global feature; raw head (:1164)
+    "TALLSIREN_dgx": {"layers": 8, "freq_init": 25.0, "sigmoid_rgb": False, "xyz": True},
+    # :671-741 + feature_pyramid_interpolation :1444-1473: layer 0 reads the concatenated trilinear features of every pyramid level
+    "SHORTSIREN_FG_Pyrmd": {"layers": 4, "freq_init": 12.0, "sigmoid_rgb": True, "pyramid": True},
 }
 
 
@@ -140,6 +147,15 @@ def init_generator_state(
     state["siren.final_layer.weight"] = uniform((4, hidden_dim), math.sqrt(6.0 / hidden_dim) / spec["freq_init"])
     state["siren.final_layer.bias"] = uniform((4,), 1.0 / math.sqrt(hidden_dim))
     if not spec.get("film", True):
+        return state
+    if spec.get("pointwise"):
+        # PointFeaturesMappingNetwork(z_dim, 256, L * hidden * 2): kaiming_normal_(a=0.2, fan_in), default biases, last weight x 0.25
+        dims = [z_dim, 256, spec["layers"] * hidden_dim * 2]
+        for i in range(2):
+            std = math.sqrt(2.0 / (1 + 0.2 ** 2)) / math.sqrt(dims[i])
+            w = torch.randn((dims[i + 1], dims[i]), generator=g) * std
+            state[f"siren.mapping_network.network.{2 * i}.weight"] = w * (0.25 if i == 1 else 1.0)
+            state[f"siren.mapping_network.network.{2 * i}.bias"] = uniform((dims[i + 1],), 1.0 / math.sqrt(dims[i]))
         return state
     if spec.get("latent"):
         # CustomMappingNetwork(z_dim, 256, L * hidden * 2): kaiming_normal_(a=0.2, fan_in) weights, default Linear biases, last weight x 0.25
@@ -386,6 +402,26 @@ def _split_state(state, siren_type):
 def siren_forward(state, siren_type, pts_world, z, img_size, num_steps):
     """``SIREN.forward(points, z, img_size, num_steps)`` for the FG family (siren.py:540-580)."""
     spec, ws, bs = _split_state(state, siren_type)
+    fw_, fb_ = state["siren.final_layer.weight"], state["siren.final_layer.bias"]
+    if spec.get("pointwise"):                        # siren.py:292-326
+        feat = trilinear_lookup(z, pts_world, img_size, num_steps)
+        h = F.leaky_relu(F.linear(feat, state["siren.mapping_network.network.0.weight"], state["siren.mapping_network.network.0.bias"]), 0.2)
+        fo = F.linear(h, state["siren.mapping_network.network.2.weight"], state["siren.mapping_network.network.2.bias"])
+        half = fo.shape[-1] // 2
+        freq, phase = fo[..., :half] * 15 + 30, fo[..., half:]
+        x, H = pts_world, ws[0].shape[0]
+        for i, (w, b) in enumerate(zip(ws, bs)):      # PointwiseFiLMLayer.forward :170-177
+            x = torch.sin(freq[..., i * H:(i + 1) * H] * F.linear(x, w, b) + phase[..., i * H:(i + 1) * H])
+        return F.linear(x, fw_, fb_)
+    if spec.get("xyz") or spec.get("pyramid"):
+        volumes, global_feature = z
+        freq, phase = film_parameters(global_feature, state["siren.mapping_network.weight"], state["siren.mapping_network.bias"])
+        if spec.get("xyz"):                          # siren.py:1136-1153
+            x0 = torch.cat([trilinear_lookup(volumes, pts_world, img_size, num_steps), pts_world], dim=-1)
+        else:                                        # feature_pyramid_interpolation, siren.py:1444-1473
+            levels = volumes if isinstance(volumes, (list, tuple)) else [volumes]
+            x0 = torch.cat([trilinear_lookup(v, pts_world, img_size, num_steps) for v in levels], dim=2)
+        return film_siren_mlp(x0, ws, bs, freq, phase, fw_, fb_, spec["sigmoid_rgb"])
     if spec.get("latent"):                           # siren.py:1206-1224: x = input points, z = latent vector
         freq, phase = custom_mapping_network(z, state)
         return film_siren_mlp(pts_world, ws, bs, freq, phase, state["siren.final_layer.weight"], state["siren.final_layer.bias"], spec["sigmoid_rgb"])
@@ -575,6 +611,31 @@ def far_plane_sigma(out: Dict[str, torch.Tensor], nerf_noise: float) -> torch.Te
     clamp_mode "softplus" (alpha_last == 1 always) or exclude those pixels and report their fraction.
     """
     return out["rgb_sigma_all"][:, :, -1, 3] + out["noise_final"][:, :, -1, 0] * nerf_noise
+
+
+LIBRARY_CASES = {       # siren_type -> (z_dim, input_dim, channels of the volume(s), seed) of the fixtures tests/golden/fwd_<type>.npz
+    "TALLSIREN": (32, 3, [32], 51),
+    "TALLSIREN_dgx": (256, 35, [32], 52),
+    "SHORTSIREN_FG_Pyrmd": (256, 224, [32, 64, 128], 53),
+}
+
+
+def library_case_inputs(siren_type: str, B: int = 2, V: int = 12):
+    """Seeded (state, z, cam2world, generator) of the three decoders above: z = the volume alone (TALLSIREN), (volume, global)
+    (TALLSIREN_dgx) or (list of pyramid volumes at V, V/2, V/4, global) (SHORTSIREN_FG_Pyrmd)."""
+    z_dim, input_dim, plan, seed = LIBRARY_CASES[siren_type]
+    g = torch.Generator().manual_seed(seed)
+    state = init_generator_state(siren_type, z_dim=z_dim, input_dim=input_dim, hidden_dim=256, seed=seed)
+    vols = [torch.randn((B, c, max(V >> i, 2), max(V >> i, 2), max(V >> i, 2)), generator=g) * 0.3 for i, c in enumerate(plan)]
+    glob = torch.randn((B, 256), generator=g) * 0.05 + 0.19
+    if siren_type == "TALLSIREN":
+        z = vols[0]
+    elif siren_type == "TALLSIREN_dgx":
+        z = (vols[0], glob)
+    else:
+        z = (vols, glob)
+    cam = look_at_cam2world(random_camera_origins(B, 0.7, 1.5, "y", np.random.RandomState(seed)), "y")
+    return state, z, cam, g
 
 
 def dense_grid_samples(N: int, voxel_origin=(0, 0, 0), cube_length: float = 2.0):

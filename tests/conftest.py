@@ -80,3 +80,20 @@ def latent_fixture_inputs(name="fwd_SHORTSIREN"):
     draws = {k[5:]: v for k, v in fx.items() if k.startswith("draw/")}
     taps = {k[4:]: v for k, v in fx.items() if k.startswith("tap/")}
     return state, fx["in/latent"], fx["in/cam2world"], draws, meta, taps
+
+
+LIBRARY_FIXTURES = ["fwd_TALLSIREN", "fwd_TALLSIREN_dgx", "fwd_SHORTSIREN_FG_Pyrmd"]
+
+
+def library_fixture_inputs(name):
+    """(siren_type, state, z, cam2world, draws, meta, taps, (z_dim, input_dim)) of a library-MLP decoder fixture."""
+    from oracle import nerf_path as oracle
+
+    fx, meta = load_golden(name)
+    siren_type = meta.pop("siren_type")
+    state, z, cam, g = oracle.library_case_inputs(siren_type)
+    checksum = sum(float(v.double().abs().sum()) for v in state.values())
+    assert abs(checksum - float(fx["state/checksum"])) < 1e-9 * checksum, "torch CPU generator drifted"
+    draws = {k[5:]: v for k, v in fx.items() if k.startswith("draw/")}
+    taps = {k[4:]: v for k, v in fx.items() if k.startswith("tap/")}
+    return siren_type, state, z, cam, draws, meta, taps, oracle.LIBRARY_CASES[siren_type][:2]

@@ -338,6 +338,49 @@ def make_latent_fixture(seed=41, img_size=16, S=12, B=2, z_dim=512):
     return fx
 
 
+LIBRARY_CASES = oracle.LIBRARY_CASES
+library_inputs = oracle.library_case_inputs
+
+
+def make_library_fixture(siren_type, img_size=12, S=8):
+    z_dim, input_dim, plan, seed = LIBRARY_CASES[siren_type]
+    state, z, cam, g = library_inputs(siren_type)
+    B = cam.shape[0]
+    draws = oracle.draw_randoms(B, img_size, S, True, g)
+    meta = dict(img_size=img_size, fov=49.134342641202636, ray_start=0.25, ray_end=1.95, num_steps=S, hierarchical_sample=True,
+                clamp_mode="softplus", nerf_noise=0.3, white_back=True, last_back=False)
+    gen = ref_gen.ImplicitGenerator3d(siren_type, z_dim=z_dim, input_dim=input_dim, output_dim=4, hidden_dim=256)
+    gen.load_state_dict(state, strict=True)
+    gen.set_device(torch.device("cpu"))
+    gen.eval()
+    rp = Replay([("rand", draws["u_jitter"]), ("randn", draws["noise_coarse"]), ("rand", draws["u_resample"]), ("randn", draws["noise_final"])])
+    calls = []
+    orig_fwd = gen.siren.forward
+
+    def tap(points, zz, *a):
+        out = orig_fwd(points, zz, *a)
+        calls.append((points.detach().clone(), out.detach().clone()))
+        return out
+
+    gen.siren.forward = tap
+    orig = torch.rand, torch.randn
+    torch.rand, torch.randn = rp.rand, rp.randn
+    try:
+        with torch.no_grad():
+            pixels, depth = gen(z, cam, **meta)
+    finally:
+        torch.rand, torch.randn = orig
+    R = img_size ** 2
+    fx = {"state/checksum": np.array(sum(float(v.double().abs().sum()) for v in state.values()))}
+    fx.update({f"draw/{k}": v.numpy() for k, v in draws.items()})
+    fx["tap/pixels"], fx["tap/depth"] = pixels.numpy(), depth.numpy()
+    fx["tap/points_coarse"] = calls[0][0].reshape(B, R, S, 3).numpy()
+    fx["tap/rgb_sigma_coarse"] = calls[0][1].reshape(B, R, S, 4).numpy()
+    fx["tap/rgb_sigma_fine"] = calls[1][1].reshape(B, R, S, 4).numpy()
+    fx["meta/json"] = np.array(__import__("json").dumps(dict(meta, siren_type=siren_type)))
+    return fx
+
+
 def dense_fixtures():
     """Forward fixtures with real density: 16x16, 12+12 samples, 16^3 volume, batch 2."""
     kw = dict(img_size=16, S=12, V=16, B=2, dense=True)
@@ -351,6 +394,10 @@ def dense_fixtures():
 
 def main():
     out = {}
+    if "--library-only" in sys.argv:
+        for st in LIBRARY_CASES:
+            np.savez_compressed(os.path.join(HERE, f"fwd_{st}.npz"), **make_library_fixture(st))
+        return
     if "--latent-only" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "fwd_SHORTSIREN.npz"), **make_latent_fixture())
         return
@@ -380,6 +427,8 @@ def main():
     out["functions"] = make_function_fixture()
     out.update(dense_fixtures())
     out["fwd_SHORTSIREN"] = make_latent_fixture()
+    for st in LIBRARY_CASES:
+        out[f"fwd_{st}"] = make_library_fixture(st)
     for name, fx in out.items():
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **fx)

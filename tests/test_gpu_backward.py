@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import fixture_inputs, latent_fixture_inputs
+from conftest import LIBRARY_FIXTURES, fixture_inputs, latent_fixture_inputs, library_fixture_inputs
 from oracle import nerf_path as oracle
 
 pytestmark = pytest.mark.gpu
@@ -334,6 +334,43 @@ def test_kept_dumps_backward_equals_recompute_backward(name):
     # same backward kernels on the same dumps; the two forwards differ in which sines take the FMA-pipe polynomial (1 in 8 vs 1 in 4,
     # 7e-5 each), which the FiLM frequencies (~30 per layer) amplify into the loss gradient
     assert worst < 1e-2, worst
+
+
+@pytest.mark.parametrize("name", LIBRARY_FIXTURES)
+def test_library_mlp_decoders_backward_vs_oracle_autograd(name):
+    """Gradients of the library-MLP decoders (checkpointed PyTorch MLP between the library's gather / scatter and compositing
+    kernels) w.r.t. every parameter, every feature volume and the global feature."""
+    from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d
+    siren_type, state, z, cam, draws, meta, _, (z_dim, input_dim) = library_fixture_inputs(name)
+    B, img = cam.shape[0], meta["img_size"]
+    g = torch.Generator().manual_seed(4)
+    d_pix, d_dep = torch.randn((B, 3, img, img), generator=g), torch.randn((B, img, img), generator=g)
+
+    def leaves(zz, to_dev):
+        if isinstance(zz, (list, tuple)):
+            return type(zz)(leaves(t, to_dev) for t in zz)
+        return (dev(zz) if to_dev else zz.clone()).requires_grad_(True)
+
+    def flat(zz):
+        return [t for x in zz for t in flat(x)] if isinstance(zz, (list, tuple)) else [zz]
+
+    st = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+    z_r = leaves(z, False)
+    out = oracle.render_with_grad(st, siren_type, z_r, cam, draws, **meta)
+    ((out["pixels"] * d_pix).sum() + (out["depth"] * d_dep).sum()).backward()
+    gen = ImplicitGenerator3d(siren_type, z_dim, input_dim, 4, 256)
+    gen.load_state_dict(state, strict=True)
+    gen = gen.to("cuda")
+    z_d = leaves(z, True)
+    pixels, depth = gen(z_d, dev(cam), draws={k: dev(v) for k, v in draws.items()}, **meta)
+    ((pixels * dev(d_pix)).sum() + (depth * dev(d_dep)).sum()).backward()
+    pairs = [(f"z[{i}]", a.grad, b.grad) for i, (a, b) in enumerate(zip(flat(z_d), flat(z_r)))]
+    pairs += [(k, p.grad, st["siren." + k].grad) for k, p in gen.siren.named_parameters()]
+    for k, got, ref in pairs:
+        assert got is not None and got.shape == ref.shape, k
+        e, c = rel_l2(got.cpu(), ref), cosine(got.cpu(), ref)
+        assert c > 0.9995 and e < 2e-2, (k, e, c)
+    print(f"{name}: worst rel-L2 {max(rel_l2(a.cpu(), b) for _, a, b in pairs):.2e}")
 
 
 def test_siren_boundary_backward_and_amp():

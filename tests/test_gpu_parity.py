@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import DENSE_FIXTURES, FORWARD_FIXTURES, fixture_inputs, latent_fixture_inputs, load_golden
+from conftest import DENSE_FIXTURES, FORWARD_FIXTURES, LIBRARY_FIXTURES, fixture_inputs, latent_fixture_inputs, library_fixture_inputs, load_golden
 from oracle import nerf_path as oracle
 
 pytestmark = pytest.mark.gpu
@@ -885,6 +885,37 @@ def test_second_device_renders_like_the_first(ops):
             px, _ = gen((z[0].to(d), z[1].to(d)), cam.to(d), draws={k: v.to(d) for k, v in draws.items()}, **meta)
         imgs.append(px.cpu())
     assert torch.equal(imgs[0], imgs[1])
+
+
+def _dev_tree(z):
+    if isinstance(z, (list, tuple)):
+        return type(z)(_dev_tree(t) for t in z)
+    return dev(z)
+
+
+@pytest.mark.parametrize("name", LIBRARY_FIXTURES)
+def test_library_mlp_decoders_forward_vs_reference(name):
+    """TALLSIREN (per-point FiLM, configs/thousand/direct_volume/indirect.py), TALLSIREN_dgx, SHORTSIREN_FG_Pyrmd: the library's
+    ray / gather / compositing kernels around a PyTorch MLP (generators/siren_library.py) against fixtures recorded from the
+    reference classes; also the secondary boundary and staged_forward."""
+    from conditioned_nerf_gan_b200.generators import ImplicitGenerator3d
+    siren_type, state, z, cam, draws, meta, taps, (z_dim, input_dim) = library_fixture_inputs(name)
+    gen = ImplicitGenerator3d(siren_type, z_dim, input_dim, 4, 256)
+    gen.load_state_dict(state, strict=True)
+    gen = gen.to("cuda").eval()
+    gen.set_device(torch.device("cuda"))
+    zc, d = _dev_tree(z), {k: dev(v) for k, v in draws.items()}
+    B, img, S = cam.shape[0], meta["img_size"], meta["num_steps"]
+    with torch.no_grad():
+        pixels, depth = gen(zc, dev(cam), draws=d, **meta)
+        rs = gen.siren(dev(taps["points_coarse"].reshape(B, -1, 3)), zc, img, S)
+        px2, _ = gen.staged_forward(zc, dev(cam), max_batch_size=1, draws=None, **dict(meta, nerf_noise=0.0))
+    err_mlp = (rs.cpu().reshape(B, -1, S, 4) - taps["rgb_sigma_coarse"]).abs().max().item()
+    psnr = oracle.psnr(pixels.cpu(), taps["pixels"])
+    print(f"{name}: MLP max-abs {err_mlp:.2e}, pixels max-abs {(pixels.cpu() - taps['pixels']).abs().max().item():.2e}, PSNR {psnr:.1f} dB")
+    assert err_mlp < 5e-4 and psnr >= 60.0
+    assert torch.allclose(depth.cpu(), taps["depth"], rtol=0, atol=2e-3)
+    assert px2.shape == pixels.shape and torch.isfinite(px2).all()
 
 
 def test_fp16_host_volume_path(ops):

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import DENSE_FIXTURES, FORWARD_FIXTURES, fixture_inputs, latent_fixture_inputs, load_golden
+from conftest import DENSE_FIXTURES, FORWARD_FIXTURES, LIBRARY_FIXTURES, fixture_inputs, latent_fixture_inputs, library_fixture_inputs, load_golden
 from oracle import nerf_path as oracle
 
 
@@ -45,6 +45,16 @@ def test_latent_shortsiren_matches_reference():
     state, latent, cam, draws, meta, taps = latent_fixture_inputs()
     out = oracle.render(state, "SHORTSIREN", latent, cam, draws, **meta)
     assert torch.equal(out["points_coarse"], taps["points_coarse"]) and torch.equal(out["rgb_sigma_coarse"], taps["rgb_sigma_coarse"])
+    assert torch.allclose(out["pixels"], taps["pixels"], rtol=0, atol=1e-4) and torch.allclose(out["depth"], taps["depth"], rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", LIBRARY_FIXTURES)
+def test_library_mlp_decoders_match_reference(name):
+    """TALLSIREN (per-point FiLM), TALLSIREN_dgx, SHORTSIREN_FG_Pyrmd: the oracle against fixtures recorded from the reference classes."""
+    siren_type, state, z, cam, draws, meta, taps, _ = library_fixture_inputs(name)
+    out = oracle.render(state, siren_type, z, cam, draws, **meta)
+    assert torch.equal(out["points_coarse"], taps["points_coarse"])
+    assert torch.allclose(out["rgb_sigma_coarse"], taps["rgb_sigma_coarse"], rtol=0, atol=1e-6)
     assert torch.allclose(out["pixels"], taps["pixels"], rtol=0, atol=1e-4) and torch.allclose(out["depth"], taps["depth"], rtol=0, atol=1e-4)
 
 
