@@ -46,7 +46,7 @@ namespace bwdtc {
 
 constexpr int kTileImageBytes = kATileBytes;                 // 65536: [4 K-blocks][128 rows][64 x 16 bit], 128B-swizzled
 constexpr int kFeatImageBytes = kABlockBytes;                // 16384: layer-0 operand block [x_hi(32) | x_lo(32)]
-constexpr int kGTileBytes = kTileM * kHID * 2;               // 65536: g of one tile-layer, [cc 8][q 4][i 4][lane 32] x 16 B
+constexpr int kGTileBytes = kTileM * kHID;                   // 32768: g of one tile-layer, [cc 8][q 4][h 2][lane 32] x 16 B of 8-bit codes
 
 // ---- W^T images for B1 (bf16, item independent) ------------------------------------------------------------------
 // [head 32 KB][layer L-1: 4 x 32 KB] ... [layer 1: 4 x 32 KB][layer 0: 16 KB]
@@ -120,7 +120,7 @@ struct DgradParams {
   long long P, T;            // points, tiles
   int L;
   const uint8_t* wt;         // W^T images
-  const uint8_t* g;          // [L][g_stride tiles][65536]: layer l of this call's tiles starts at g + l * g_stride * 65536
+  const uint8_t* g;          // [L][g_stride tiles][32768]: layer l of this call's tiles starts at g + l * g_stride * 32768
   long long g_stride;        // >= T (a dump that holds more tiles than this call processes, e.g. all items of a batch)
   uint8_t* dz;               // [L][T][65536] tile images (bf16), written
   float* d_feat;             // [P, 32]
@@ -281,10 +281,10 @@ __global__ void __launch_bounds__(kThreadsB, 1) film_siren_dgrad_kernel(DgradPar
       for (int s = 0; s < L; ++s) {
         const int l = L - 1 - s;                                           // this epilogue forms dz_l from dy_l (accumulator) and g_l
         const uint4* gt = reinterpret_cast<const uint4*>(p.g + (static_cast<size_t>(l) * p.g_stride + t) * kGTileBytes);
-        uint4 ga[4], gb[4];
-        auto load_g = [&](uint4 (&gg)[4], int cc) {
+        uint4 ga[2], gb[2];
+        auto load_g = [&](uint4 (&gg)[2], int cc) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) gg[i] = __ldg(gt + ((cc * 4 + q) * 4 + i) * 32 + lane);
+          for (int h = 0; h < 2; ++h) gg[h] = __ldg(gt + ((cc * 4 + q) * 2 + h) * 32 + lane);
         };
         load_g(ga, 4 * half);
         mbar_wait(acc_full(x), acc_phase);
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) film_siren_dgrad_kernel(DgradPar
         tile_free();
         float4* rsd = nullptr;
         if constexpr (kRes) rsd = reinterpret_cast<float4*>(p.res_scratch) + (static_cast<size_t>(blockIdx.x) * 2 + x) * (kHID / 4) * kTileM;
-        auto finish_block = [&](const uint4 (&gg)[4], int cc) {
+        auto finish_block = [&](const uint4 (&gg)[2], int cc) {
           uint32_t v[32];
           CNG_TMEM_LD_32(t_lane + cc * 32, v);
           tmem_ld_wait();
@@ -314,11 +314,16 @@ __global__ void __launch_bounds__(kThreadsB, 1) film_siren_dgrad_kernel(DgradPar
           float dzv[32];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const uint32_t gw[4] = {gg[i].x, gg[i].y, gg[i].z, gg[i].w};
+            // columns 8 i .. 8 i + 7 of the block: two words of 8-bit codes u = round(127 cos) + 128.  A code is placed in mantissa
+            // bits 8..15 of 1.0f (one PRMT: 1 + u 2^-15) and scaled back with one FMA: (f - 1 - 2^-8) 2^15 / 127 = (u - 128) / 127
+            const uint32_t gw[2] = {(i & 1) ? gg[i >> 1].z : gg[i >> 1].x, (i & 1) ? gg[i >> 1].w : gg[i >> 1].y};
+            constexpr float kGs = 32768.f / 127.f, kGo = -(1.f + 1.f / 256.f) * (32768.f / 127.f);
             uint32_t o[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float2 gf = __half22float2(*reinterpret_cast<const __half2*>(&gw[j]));
+              float2 gf;
+              gf.x = fmaf(__uint_as_float(__byte_perm(gw[j >> 1], 0x3F800000u, (j & 1) ? 0x7624 : 0x7604)), kGs, kGo);
+              gf.y = fmaf(__uint_as_float(__byte_perm(gw[j >> 1], 0x3F800000u, (j & 1) ? 0x7634 : 0x7614)), kGs, kGo);
               const float a = __uint_as_float(v[8 * i + 2 * j]) * gf.x, b = __uint_as_float(v[8 * i + 2 * j + 1]) * gf.y;
               dzv[8 * i + 2 * j] = a; dzv[8 * i + 2 * j + 1] = b;
               o[j] = pack2<false>(a, b);

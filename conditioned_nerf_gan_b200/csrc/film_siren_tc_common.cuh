@@ -293,9 +293,9 @@ struct TcParams {
   //   dump_x  [L][T][64 KB]  the layer output x_{l+1} = sin(u_l) as the 128-point operand TILE IMAGE the next layer's MMA reads
   //           ([4 K-blocks][128 rows][64 x 16 bit], 128B-swizzled, operand format) -- one bulk store per tile-layer; the
   //           weight-gradient kernel (film_siren_bwd_tc.cu) reads it back with MN-major descriptors
-  //   dump_g  [L][T][64 KB]  the local derivative g_l = cos(u_l) in fp16 (the FiLM frequency is folded into the backward's
-  //           weight images instead), in the epilogue's own register order
-  //           [32-column block cc][lane quarter q][16-byte piece i][lane]: every store / load is 512 contiguous bytes per warp
+  //   dump_g  [L][T][32 KB]  the local derivative g_l = cos(u_l) as 8-bit codes round(127 cos) + 128 (the FiLM frequency is folded
+  //           into the backward's weight images instead), in the epilogue's own register order
+  //           [32-column block cc][lane quarter q][16-column half h][lane] x 16 B: every store / load is 512 contiguous bytes per warp
   //   dump_feat [T][16 KB]   the layer-0 operand block [x_hi(32) | x_lo(32)]
   uint8_t* dump_x;
   uint8_t* dump_g;

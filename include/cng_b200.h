@@ -290,8 +290,10 @@ CNG_API int cng_render_fwd(const float* vol_ndhwc, long long vol_item_stride, in
  *   x_dump    [L][T][65536]  output of layer l, x_{l+1} = sin(u_l), as 128-point operand tile images
  *                            ([4 K-blocks of 64 columns][128 rows][128 B], 128-byte swizzle: element (row, k) of a block at
  *                            row*128 + (((k>>3) ^ (row&7)) << 4) + (k&7)*2), in the operand format of `precision`
- *   g_dump    [L][T][65536]  g_l = cos(u_l) in fp16, [32-column block cc 8][row quarter q 4][piece i 4][lane 32] x 16 B:
- *                            row = 32 q + lane, columns 32 cc + 8 i .. + 7.  The FiLM frequency is not applied elementwise:
+ *   g_dump    [L][T][32768]  g_l = cos(u_l) as 8-bit codes round(127 g) + 128 (|error| <= 1/254, the size of the bf16 rounding of
+ *                            dz; as fp16 the dump made the training forward write-bound), [32-column block cc 8][row quarter q 4]
+ *                            [half h 2][lane 32] x 16 B: row = 32 q + lane, byte e = column 32 cc + 16 h + e.
+ *                            The FiLM frequency is not applied elementwise:
  *                            with dz'_l = dy_l * cos(u_l) the chain is dy_{l-1} = dz'_l (diag(freq_l) W_l) and
  *                            dW_l = diag(freq_l) dz'_l^T x_l, db_l = freq_l * colsum(dz'_l), dphase_l = colsum(dz'_l),
  *                            dfreq_l = rowsum(W_l * dz'_l^T x_l) + b_l * colsum(dz'_l)
@@ -299,7 +301,7 @@ CNG_API int cng_render_fwd(const float* vol_ndhwc, long long vol_item_stride, in
  *   dz_dump   [L][T][65536]  dz'_l = dy_l * g_l as bf16 tile images (written by the dgrad chain, read by the weight gradient)
  * ---------------------------------------------------------------------------------------- */
 /* Training-mode forward of K2 (the backward's activation recompute): the fused tcgen05 kernel of cng_film_siren_fwd(_res) that
- * ALSO writes the three dumps above (one bulk store per tile-layer for x, direct register stores for g).  `precision`:
+ * ALSO writes the three dumps above (one bulk store per tile-layer for x, two 16-byte register stores per thread and 32-column block for g).  `precision`:
  * CNG_PREC_BF16 or CNG_PREC_FP16 (operand format of the recompute and of x_dump).  With B > 1 the tile index runs over items:
  * T = B * ceil(N / 128).  Residual masks / scratch as in cng_film_siren_fwd_res (0 / NULL for plain networks); g_l is then the
  * derivative at the pre-activation INCLUDING the re-added block input. */

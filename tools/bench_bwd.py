@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-kernel timing of the tcgen05 MLP backward (a14) on one chunk of points: training-mode forward (recompute with dumps),
 dgrad chain, split-K weight gradient, and the one-call cng_film_siren_bwd.  Algorithmic bytes per point and layer: recompute
-1 KB written (x + g), dgrad 1 KB (g read, dz written), wgrad 1 KB (dz + x read); FLOPs per point and hidden layer 2*256^2 each.
+768 B written (x + 8-bit g), dgrad 768 B (g read, dz written), wgrad 1 KB (dz + x read); FLOPs per point and hidden layer 2*256^2 each.
     python tools/bench_bwd.py [--points 1048576] [--siren TALLSIREN_FG]"""
 import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -46,12 +46,12 @@ ms = timeit(lambda: ops.film_siren_fwd(feat, ws, bs, freq, phase, fw, fb, net.si
 rows.append(("inference forward (fp16 operands)", ms, None, hidden_flops))
 out, xs, gs, fd = ops.film_siren_fwd_train(feat, ws, bs, freq, phase, fw, fb, net.sigmoid_rgb, "fp16")
 ms = timeit(lambda: ops.film_siren_fwd_train(feat, ws, bs, freq, phase, fw, fb, net.sigmoid_rgb, "fp16"))
-rows.append(("training forward (recompute + dumps)", ms, P * L * 1024 + P * 128 * 2, hidden_flops))
+rows.append(("training forward (recompute + dumps)", ms, P * L * 768 + P * 128 * 2, hidden_flops))
 wt = ops.film_siren_wt_images(ws, fw)
 d_fb = torch.zeros(4, device=dev)
 d_feat, dz = ops.film_siren_dgrad(d_out, out[0], net.sigmoid_rgb, L, wt, gs, d_fb)
 ms = timeit(lambda: ops.film_siren_dgrad(d_out, out[0], net.sigmoid_rgb, L, wt, gs, d_fb))
-rows.append(("dgrad chain", ms, P * L * 1024 + P * 160, hidden_flops))
+rows.append(("dgrad chain", ms, P * L * 768 + P * 160, hidden_flops))
 dW = [torch.zeros_like(w) for w in ws]
 colsum = torch.zeros((L, 256), device=dev)
 ms = timeit(lambda: ops.film_siren_wgrad(dz, xs, fd, P, L, True, dW, colsum))
@@ -60,7 +60,7 @@ del xs, gs, fd, dz
 torch.cuda.empty_cache()
 d_fw, d_feat2 = torch.zeros_like(fw), torch.empty((P, 32), device=dev)
 ms = timeit(lambda: ops.film_siren_bwd(feat[0], d_out, ws, bs, freq[0].contiguous(), phase[0].contiguous(), fw, fb, net.sigmoid_rgb, d_feat2, dW, colsum, d_fw, d_fb))
-rows.append(("cng_film_siren_bwd (all of the above but the inference forward)", ms, 3 * P * L * 1024, 3 * hidden_flops))
+rows.append(("cng_film_siren_bwd (all of the above but the inference forward)", ms, P * L * (768 + 768 + 1024), 3 * hidden_flops))
 print(f"# {args.siren} L={L}, {P} points per chunk")
 for name, ms, by, fl in rows:
     gbs = f"{by / ms / 1e6:7.0f} GB/s" if by else "            "
