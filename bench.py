@@ -562,7 +562,7 @@ def measure_c5(rays_m: int = 2):
         w = torch.rand((n, S), generator=g, device=dev)
         u = torch.rand((n, S), generator=g, device=dev)
         rs2 = torch.randn((n, S, 4), generator=g, device=dev)
-        t2 = torch.rand((n, S), generator=g, device=dev).mul_(1.7).add_(0.25).sort(dim=1).values
+        t2 = torch.rand((n, S), generator=g, device=dev).mul_(1.7).add_(0.25)      # fine distances arrive UNSORTED (inverse-CDF of random u)
         rays = torch.nn.functional.normalize(torch.randn((1024, 3), generator=g, device=dev), dim=-1)
         cases = [("composite", lambda: ops.composite_fwd(rs, t, None, 0.0, "relu", True, False), n * (S * 20 + 16 + 4 * S)),
                  ("resample", lambda: ops.resample_from_coarse(t, w, u), n * 16 * S),

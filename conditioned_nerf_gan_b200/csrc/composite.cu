@@ -42,7 +42,7 @@ __device__ __forceinline__ float clamp_sigma(float s, int mode) {
 
 constexpr int kWarpsPerBlock = 8;
 
-template <int IPL, bool MERGE>
+template <int IPL, bool MERGE, bool CHUNKED>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(CompositeParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31;
@@ -60,75 +60,85 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
     load_and_sort_ray(keys, p.rgb_sigma_fine ? p.t_fine : nullptr, p.t, ray, S, n, n2, lane);
   }
 
-  float alpha[IPL], fac[IPL], tt[IPL], cr[IPL], cg[IPL], cb[IPL];
-  float lane_prod = 1.f;
+  // The ray is processed in chunks of 32 * IPL samples: one chunk for up to 128 samples (CHUNKED = false: no loop), chunks of 128
+  // beyond -- IPL is capped at 4 so that the per-lane arrays stay in ~24 registers: with 8 or 16 samples per lane the kernel lost
+  // its occupancy and fell to 46 % of the HBM roofline at 256 samples per ray (80 % chunked).  The transmittance at the start of
+  // a chunk is carried in t_carry.
+  float ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, wsum = 0.f, t_carry = 1.f;
+  const int n_loop = CHUNKED ? n : 1;
+  for (int base = 0; base < n_loop; base += 32 * IPL) {
+    float alpha[IPL], fac[IPL], tt[IPL], cr[IPL], cg[IPL], cb[IPL];
+    float lane_prod = 1.f;
 #pragma unroll
-  for (int i = 0; i < IPL; ++i) {
-    const int s = lane * IPL + i;
-    alpha[i] = 0.f; fac[i] = 1.f; tt[i] = 0.f; cr[i] = cg[i] = cb[i] = 0.f;
-    if (s < n) {
-      float4 c;
-      float t0, t1 = 0.f;
-      if (MERGE) {
-        const unsigned long long k0 = keys[s];
-        t0 = key_t(k0);
-        if (s + 1 < n) t1 = key_t(keys[s + 1]);
-        const int e = key_src(k0);
-        const float4* src = (p.rgb_sigma_fine != nullptr && e < S)
-                                ? reinterpret_cast<const float4*>(p.rgb_sigma_fine) + ray * S + e
-                                : reinterpret_cast<const float4*>(p.rgb_sigma) + ray * S + (p.rgb_sigma_fine ? e - S : e);
-        c = __ldg(src);
-        if (p.order) p.order[ray * n + s] = e;
-      } else {
-        c = __ldg(reinterpret_cast<const float4*>(p.rgb_sigma) + ray * S + s);
-        t0 = __ldg(p.t + ray * S + s);
-        if (s + 1 < n) t1 = __ldg(p.t + ray * S + s + 1);
+    for (int i = 0; i < IPL; ++i) {
+      const int s = base + lane * IPL + i;
+      alpha[i] = 0.f; fac[i] = 1.f; tt[i] = 0.f; cr[i] = cg[i] = cb[i] = 0.f;
+      if (s < n) {
+        float4 c;
+        float t0, t1 = 0.f;
+        if (MERGE) {
+          const unsigned long long k0 = keys[s];
+          t0 = key_t(k0);
+          if (s + 1 < n) t1 = key_t(keys[s + 1]);
+          const int e = key_src(k0);
+          const float4* src = (p.rgb_sigma_fine != nullptr && e < S)
+                                  ? reinterpret_cast<const float4*>(p.rgb_sigma_fine) + ray * S + e
+                                  : reinterpret_cast<const float4*>(p.rgb_sigma) + ray * S + (p.rgb_sigma_fine ? e - S : e);
+          c = __ldg(src);
+          if (p.order) p.order[ray * n + s] = e;
+        } else {
+          c = __ldg(reinterpret_cast<const float4*>(p.rgb_sigma) + ray * S + s);
+          t0 = __ldg(p.t + ray * S + s);
+          if (s + 1 < n) t1 = __ldg(p.t + ray * S + s + 1);
+        }
+        const float delta = (s + 1 < n) ? (t1 - t0) : 1e10f;
+        float sg = c.w;
+        if (p.noise != nullptr) sg = sg + __ldg(p.noise + ray * n + s) * p.noise_std;
+        sg = clamp_sigma(sg, p.clamp_mode);
+        const float a = 1.f - expf(-delta * sg);
+        alpha[i] = a;
+        fac[i] = (1.f - a) + 1e-10f;
+        tt[i] = t0; cr[i] = c.x; cg[i] = c.y; cb[i] = c.z;
+        lane_prod *= fac[i];
       }
-      const float delta = (s + 1 < n) ? (t1 - t0) : 1e10f;
-      float sg = c.w;
-      if (p.noise != nullptr) sg = sg + __ldg(p.noise + ray * n + s) * p.noise_std;
-      sg = clamp_sigma(sg, p.clamp_mode);
-      const float a = 1.f - expf(-delta * sg);
-      alpha[i] = a;
-      fac[i] = (1.f - a) + 1e-10f;
-      tt[i] = t0; cr[i] = c.x; cg[i] = c.y; cb[i] = c.z;
-      lane_prod *= fac[i];
     }
-  }
-  // exclusive multiplicative scan of lane_prod across the warp
-  float incl = lane_prod;
+    // exclusive multiplicative scan of lane_prod across the warp
+    float incl = lane_prod;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const float up = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl *= up;
-  }
-  float T = __shfl_up_sync(0xffffffffu, incl, 1);
-  if (lane == 0) T = 1.f;
+    for (int o = 1; o < 32; o <<= 1) {
+      const float up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl *= up;
+    }
+    float T = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) T = 1.f;
+    T *= t_carry;
+    t_carry *= __shfl_sync(0xffffffffu, incl, 31);
 
-  float w[IPL];
-  float wsum = 0.f;
+    float w[IPL];
 #pragma unroll
-  for (int i = 0; i < IPL; ++i) {
-    w[i] = alpha[i] * T;
-    T *= fac[i];
-    wsum += w[i];
-  }
-  wsum = warp_sum(wsum);
-  if (p.last_back) {
-    // weights[:, :, -1] += 1 - weights_sum   (volumetric_rendering.py:54-55)
-    const int s_last = n - 1;
-    if (lane == s_last / IPL) {
-#pragma unroll
-      for (int i = 0; i < IPL; ++i)
-        if (lane * IPL + i == s_last) w[i] += 1.f - wsum;
+    for (int i = 0; i < IPL; ++i) {
+      w[i] = alpha[i] * T;
+      T *= fac[i];
+      wsum += w[i];
     }
-  }
-  float ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f;
+    if (!CHUNKED || base + 32 * IPL >= n) {     // last chunk: the ray's weight sum is complete
+      wsum = warp_sum(wsum);
+      if (p.last_back) {
+        // weights[:, :, -1] += 1 - weights_sum   (volumetric_rendering.py:54-55)
+        const int s_last = n - 1 - base;
+        if (lane == s_last / IPL) {
 #pragma unroll
-  for (int i = 0; i < IPL; ++i) {
-    ar += w[i] * cr[i]; ag += w[i] * cg[i]; ab += w[i] * cb[i]; ad += w[i] * tt[i];
-    const int s = lane * IPL + i;
-    if (p.weights != nullptr && s < n) p.weights[ray * n + s] = w[i];
+          for (int i = 0; i < IPL; ++i)
+            if (lane * IPL + i == s_last) w[i] += 1.f - wsum;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < IPL; ++i) {
+      ar += w[i] * cr[i]; ag += w[i] * cg[i]; ab += w[i] * cb[i]; ad += w[i] * tt[i];
+      const int s = base + lane * IPL + i;
+      if (p.weights != nullptr && s < n) p.weights[ray * n + s] = w[i];
+    }
   }
   ar = warp_sum(ar); ag = warp_sum(ag); ab = warp_sum(ab); ad = warp_sum(ad);
   if (p.white_back) { const float bg = 1.f - wsum; ar = ar + bg; ag = ag + bg; ab = ab + bg; }
@@ -149,21 +159,19 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
 
 template <bool MERGE>
 static int launch_composite(const CompositeParams& p, cudaStream_t stream) {
-  const int ipl = (p.n + 31) / 32;
+  const int ipl = (p.n + 31) / 32;                    // more than 128 samples: chunks of 128 (IPL = 4)
   const unsigned grid = static_cast<unsigned>((p.n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock);
   const size_t smem = MERGE ? static_cast<size_t>(kWarpsPerBlock) * merge_smem_words(p.n, p.S) * sizeof(unsigned long long) : 0;
-#define CNG_LAUNCH(I)                                                                              \
+#define CNG_LAUNCH(I, CH)                                                                          \
   {                                                                                               \
     if (smem > 48 * 1024)                                                                         \
-      cudaFuncSetAttribute(composite_kernel<I, MERGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    composite_kernel<I, MERGE><<<grid, kWarpsPerBlock * 32, smem, stream>>>(p);                   \
+      cudaFuncSetAttribute(composite_kernel<I, MERGE, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    composite_kernel<I, MERGE, CH><<<grid, kWarpsPerBlock * 32, smem, stream>>>(p);               \
   }
-  if (ipl <= 1) CNG_LAUNCH(1)
-  else if (ipl <= 2) CNG_LAUNCH(2)
-  else if (ipl <= 4) CNG_LAUNCH(4)
-  else if (ipl <= 8) CNG_LAUNCH(8)
-  else if (ipl <= 16) CNG_LAUNCH(16)
-  else CNG_LAUNCH(32)
+  if (ipl <= 1) CNG_LAUNCH(1, false)
+  else if (ipl <= 2) CNG_LAUNCH(2, false)
+  else if (ipl <= 4) CNG_LAUNCH(4, false)
+  else CNG_LAUNCH(4, true)
 #undef CNG_LAUNCH
   return check_launch(MERGE ? "cng_merge_composite" : "cng_composite_fwd");
 }

@@ -14,6 +14,8 @@ __device__ __forceinline__ float from_sortable_bits(uint32_t s) {
   return __uint_as_float((s & 0x80000000u) ? (s & 0x7fffffffu) : ~s);
 }
 
+__device__ __forceinline__ float key_t_bits(unsigned long long k) { return from_sortable_bits(static_cast<uint32_t>(k >> 32)); }
+
 // keys[0..n2): the first n entries valid, the rest padded by the caller with 0xffff....; n2 a power of two >= 32
 __device__ __forceinline__ void warp_bitonic_sort(unsigned long long* keys, int n2, int lane) {
   for (int k = 2; k <= n2; k <<= 1) {
@@ -52,12 +54,45 @@ __device__ __forceinline__ void warp_bitonic_sort_regs(unsigned long long (&key)
       } else {
 #pragma unroll
         for (int s = 0; s < SLOTS; ++s) {
+          // keys are unique: the lane keeps its own key iff (own < other) == (this position takes the minimum)
           const unsigned long long a = key[s];
           const unsigned long long o = __shfl_xor_sync(0xffffffffu, a, j);
-          const bool up = (((s * 32 + lane) & k) == 0);
-          const bool lower = (lane & j) == 0;
-          const unsigned long long mn = a < o ? a : o, mx = a < o ? o : a;
-          key[s] = (lower == up) ? mn : mx;
+          const bool take_min = (((s * 32 + lane) & k) == 0) == ((lane & j) == 0);
+          key[s] = ((a < o) == take_min) ? a : o;
+        }
+      }
+    }
+  }
+}
+
+// The network on LANE-MAJOR keys: key index i = lane * SLOTS + slot.  Exchanges at distance < SLOTS stay inside a lane; only the
+// 15 stages at lane distance 1..16 of each merge level shuffle (slot-major: every stage below distance 32 does), which is what
+// the sort of the fine keys spends most on (a 64-bit shuffle is two SHFL, and SHFL issues at a quarter of the ALU rate).
+template <int SLOTS>
+__device__ __forceinline__ void warp_bitonic_sort_lane_major(unsigned long long (&key)[SLOTS], int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32 * SLOTS; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j < SLOTS) {
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+          if ((s & j) == 0) {
+            const bool up = k < SLOTS ? ((s & k) == 0) : ((lane & (k / SLOTS)) == 0);
+            const unsigned long long a = key[s], b = key[s | j];
+            const bool sw = (a > b) == up;
+            key[s] = sw ? b : a;
+            key[s | j] = sw ? a : b;
+          }
+        }
+      } else {
+        const int jl = j / SLOTS;                                 // lane distance (k > j >= SLOTS: the direction depends on the lane only)
+        const bool take_min = ((lane & (k / SLOTS)) == 0) == ((lane & jl) == 0);
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+          const unsigned long long a = key[s];
+          const unsigned long long o = __shfl_xor_sync(0xffffffffu, a, jl);
+          key[s] = ((a < o) == take_min) ? a : o;
         }
       }
     }
@@ -92,39 +127,68 @@ __device__ __forceinline__ void load_and_sort_ray_regs(unsigned long long* keys,
 }
 
 // Fast path of load_and_sort_ray when the coarse distances are already non-decreasing (they are: stratified jitter never
-// crosses a neighbour): sort only the S fine keys in registers, then MERGE -- the rank of a key in the merged order is its
-// rank in its own list plus the number of keys of the other list that precede it (binary search in shared memory).
-// Keys are unique (t bits, source index), fine indices < coarse indices, so this is exactly the stable fine-first order.
-// scratch: 2 * 32*SLOTS + ... 64-bit words after keys[0..n): fine list at keys + n2, coarse list at keys + n2 + 32*SLOTS.
+// crosses a neighbour): sort only the S fine keys in registers, then MERGE.  A fine key's place in the merged order is its rank
+// among the fine keys plus the number of coarse distances strictly below it (ties: fine first, generators.py:163-165 -- the
+// stable sort of the fine-first concatenation), found by a branch-free binary search over the coarse distances in shared
+// memory; the coarse keys then fill the places the fine keys left empty, in order (an occupancy byte per place, a zero count
+// per lane and one warp scan) -- no second search and no shared-memory copy of the sorted fine list.
+// scratch after keys[0..n2): `aux` = at least next_pow2_min32(S) + S 64-bit words (merge_smem_words).
 template <int SLOTS>
-__device__ __forceinline__ void sort_fine_and_merge(unsigned long long* keys, unsigned long long* fine_s, unsigned long long* coarse_s,
+__device__ __forceinline__ void sort_fine_and_merge(unsigned long long* keys, unsigned long long* aux,
                                                     const float* __restrict__ t_fine, const float* __restrict__ t_coarse, long long ray,
                                                     int S, int lane) {
-  unsigned long long key[SLOTS];
+  const int n = 2 * S;
+  int p2c = 32;                                   // power of two > S: the search below then never needs a bound check
+  while (p2c <= S) p2c <<= 1;
+  float* ct = reinterpret_cast<float*>(aux);                                   // [p2c] coarse distances, padded with +inf
+  uint32_t* occ = reinterpret_cast<uint32_t*>(ct + p2c);                       // one byte per merged place, padded to 128 places
+  const int occ_words = ((n + 127) / 128) * 32;
+  unsigned long long key[SLOTS];                  // lane-major: key index e = lane * SLOTS + slot
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
-    const int e = s * 32 + lane;
+    const int e = lane * SLOTS + s;
     key[s] = ~0ull;
     if (e < S) key[s] = (static_cast<unsigned long long>(sortable_bits(__ldg(t_fine + ray * S + e))) << 32) | static_cast<unsigned>(e);
   }
-  warp_bitonic_sort_regs<SLOTS>(key, lane);
-#pragma unroll
-  for (int s = 0; s < SLOTS; ++s) fine_s[s * 32 + lane] = key[s];
-  for (int e = lane; e < S; e += 32)
-    coarse_s[e] = (static_cast<unsigned long long>(sortable_bits(__ldg(t_coarse + ray * S + e))) << 32) | static_cast<unsigned>(S + e);
+  for (int e = lane; e < p2c; e += 32) ct[e] = e < S ? __ldg(t_coarse + ray * S + e) : __int_as_float(0x7f800000);
+  for (int w = lane; w < occ_words; w += 32) {    // places >= n count as occupied
+    const int left = n - 4 * w;
+    occ[w] = left >= 4 ? 0u : (left <= 0 ? 0x01010101u : (0x01010101u << (8 * left)));
+  }
+  warp_bitonic_sort_lane_major<SLOTS>(key, lane);
   __syncwarp();
-  auto lower_bound = [&](const unsigned long long* a, unsigned long long k) {     // number of a[0..S) that are < k
-    int lo = 0, hi = S;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (a[mid] < k) lo = mid + 1; else hi = mid;
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int e = lane * SLOTS + s;
+    if (e < S) {
+      const float tf = key_t_bits(key[s]);
+      int r = 0;                                                               // number of coarse distances < tf
+      for (int step = p2c >> 1; step > 0; step >>= 1)
+        if (ct[r + step - 1] < tf) r += step;
+      keys[e + r] = key[s];
+      reinterpret_cast<unsigned char*>(occ)[e + r] = 1;
     }
-    return lo;
-  };
-  for (int e = lane; e < S; e += 32) {
-    const unsigned long long kf = fine_s[e], kc = coarse_s[e];
-    keys[e + lower_bound(coarse_s, kf)] = kf;
-    keys[e + lower_bound(fine_s, kc)] = kc;
+  }
+  __syncwarp();
+  int z_carry = 0;
+  for (int base = 0; base < n; base += 128) {
+    const uint32_t o = occ[(base >> 2) + lane];
+    const int z = 4 - __popc(o & 0x01010101u);
+    int incl = z;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += up;
+    }
+    int zi = z_carry + incl - z;                                               // index of this lane's first coarse distance
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (((o >> (8 * i)) & 1u) == 0) {
+        keys[base + 4 * lane + i] = (static_cast<unsigned long long>(sortable_bits(ct[min(zi, S - 1)])) << 32) | static_cast<unsigned>(S + zi);   // (zi < S unless a NaN broke the ranks)
+        ++zi;
+      }
+    }
+    z_carry += __shfl_sync(0xffffffffu, incl, 31);
   }
   __syncwarp();
 }
@@ -144,13 +208,12 @@ __device__ __forceinline__ void load_and_sort_ray(unsigned long long* keys, cons
                                                   const float* __restrict__ t_coarse, long long ray, int S, int n, int n2, int lane) {
   const bool two = t_fine != nullptr;
   if (two && S <= 256 && coarse_is_sorted(t_coarse, ray, S, lane)) {
-    unsigned long long* fine_s = keys + n2;
-    unsigned long long* coarse_s = fine_s + next_pow2_min32(S);
+    unsigned long long* aux = keys + n2;
     switch (next_pow2_min32(S)) {
-      case 32: sort_fine_and_merge<1>(keys, fine_s, coarse_s, t_fine, t_coarse, ray, S, lane); return;
-      case 64: sort_fine_and_merge<2>(keys, fine_s, coarse_s, t_fine, t_coarse, ray, S, lane); return;
-      case 128: sort_fine_and_merge<4>(keys, fine_s, coarse_s, t_fine, t_coarse, ray, S, lane); return;
-      default: sort_fine_and_merge<8>(keys, fine_s, coarse_s, t_fine, t_coarse, ray, S, lane); return;
+      case 32: sort_fine_and_merge<1>(keys, aux, t_fine, t_coarse, ray, S, lane); return;
+      case 64: sort_fine_and_merge<2>(keys, aux, t_fine, t_coarse, ray, S, lane); return;
+      case 128: sort_fine_and_merge<4>(keys, aux, t_fine, t_coarse, ray, S, lane); return;
+      default: sort_fine_and_merge<8>(keys, aux, t_fine, t_coarse, ray, S, lane); return;
     }
   }
   // up to 256 keys: sort in registers (1 to 8 keys per lane)
