@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32) composite_bwd_kernel(Composite
   const bool two = p.rgb_sigma_fine != nullptr;
   const int n2 = next_pow2_min32(n);
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem) + static_cast<size_t>(warp) * merge_smem_words(n, S);
-  load_and_sort_ray(keys, two ? p.t_fine : nullptr, p.t, ray, S, n, n2, lane);
+  load_and_sort_ray<1, 8>(keys, two ? p.t_fine : nullptr, p.t, ray, S, n, n2, lane);
 
   const long long b = ray / p.R;
   const int r = static_cast<int>(ray - b * p.R);

@@ -35,11 +35,6 @@ struct CompositeParams {
   int32_t* order;                // MERGE: [n_rays, n] or NULL
 };
 
-__device__ __forceinline__ float clamp_sigma(float s, int mode) {
-  if (mode == CNG_CLAMP_RELU) return fmaxf(s, 0.f);
-  return s > 20.f ? s : log1pf(expf(s));  // F.softplus(beta=1, threshold=20)
-}
-
 constexpr int kWarpsPerBlock = 8;
 
 template <int IPL, bool MERGE, bool CHUNKED>
@@ -51,14 +46,30 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
   if (ray >= p.n_rays) return;
   const int n = p.n;
   const int S = p.S;
+  const bool two = MERGE && p.rgb_sigma_fine != nullptr;
 
   unsigned long long* keys = nullptr;
   if (MERGE) {
-    // concatenation order of the reference: fine first, then coarse (generators.py:163-164); stable sort by t
+    // concatenation order of the reference: fine first, then coarse (generators.py:163-164); stable sort by t.
+    // Samples per list this instantiation can meet: n <= 32 * IPL (not chunked), n <= 512 (chunked).
+    constexpr int kMinSlots = CHUNKED ? 4 : (IPL == 4 ? 2 : 1), kMaxSlots = CHUNKED ? 8 : (IPL == 4 ? 2 : 1);
     const int n2 = next_pow2_min32(n);
     keys = reinterpret_cast<unsigned long long*>(smem) + static_cast<size_t>(warp) * merge_smem_words(n, S);
-    load_and_sort_ray(keys, p.rgb_sigma_fine ? p.t_fine : nullptr, p.t, ray, S, n, n2, lane);
+    load_and_sort_ray<kMinSlots, kMaxSlots>(keys, two ? p.t_fine : nullptr, p.t, ray, S, n, n2, lane);
   }
+  // per-ray bases, hoisted out of the sample loop (the 64-bit ray * S products were a quarter of its instructions)
+  const float4* cbase = reinterpret_cast<const float4*>(p.rgb_sigma) + ray * S;          // coarse, or the only list
+  const float4* fbase = two ? reinterpret_cast<const float4*>(p.rgb_sigma_fine) + ray * S : cbase;
+  const int s_sel = two ? S : 0;                                                           // source index < s_sel: fine list
+  const float* tbase = p.t + ray * S;
+  const bool has_noise = p.noise != nullptr;
+  const float* nbase = has_noise ? p.noise + ray * n : nullptr;
+  const bool has_order = MERGE && p.order != nullptr;
+  int32_t* obase = has_order ? p.order + ray * n : nullptr;
+  const bool has_weights = p.weights != nullptr;
+  float* wbase = has_weights ? p.weights + ray * n : nullptr;
+  const bool relu = p.clamp_mode == CNG_CLAMP_RELU;
+  const float noise_std = p.noise_std;
 
   // The ray is processed in chunks of 32 * IPL samples: one chunk for up to 128 samples (CHUNKED = false: no loop), chunks of 128
   // beyond -- IPL is capped at 4 so that the per-lane arrays stay in ~24 registers: with 8 or 16 samples per lane the kernel lost
@@ -67,40 +78,48 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
   float ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, wsum = 0.f, t_carry = 1.f;
   const int n_loop = CHUNKED ? n : 1;
   for (int base = 0; base < n_loop; base += 32 * IPL) {
-    float alpha[IPL], fac[IPL], tt[IPL], cr[IPL], cg[IPL], cb[IPL];
+    const int s0 = base + lane * IPL;
+    // the lane's IPL distances and the one after them (the last interval of the lane)
+    float tv[IPL + 1];
+    int src[IPL];
+    if (MERGE) {
+      // keys[n .. ] is readable scratch, so the loads need no guard; a place past n gets t = 0 (its weight is 0, and 0 * garbage
+      // could be NaN in the depth sum)
+#pragma unroll
+      for (int i = 0; i <= IPL; ++i) {
+        const unsigned long long k = keys[s0 + i];
+        tv[i] = (s0 + i < n) ? key_t(k) : 0.f;
+        if (i < IPL) src[i] = key_src(k);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i <= IPL; ++i) tv[i] = (s0 + i < n) ? __ldg(tbase + s0 + i) : 0.f;
+    }
+    float alpha[IPL], fac[IPL], cr[IPL], cg[IPL], cb[IPL];
     float lane_prod = 1.f;
 #pragma unroll
     for (int i = 0; i < IPL; ++i) {
-      const int s = base + lane * IPL + i;
-      alpha[i] = 0.f; fac[i] = 1.f; tt[i] = 0.f; cr[i] = cg[i] = cb[i] = 0.f;
-      if (s < n) {
-        float4 c;
-        float t0, t1 = 0.f;
+      const int s = s0 + i;
+      const bool valid = s < n;
+      float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) {
         if (MERGE) {
-          const unsigned long long k0 = keys[s];
-          t0 = key_t(k0);
-          if (s + 1 < n) t1 = key_t(keys[s + 1]);
-          const int e = key_src(k0);
-          const float4* src = (p.rgb_sigma_fine != nullptr && e < S)
-                                  ? reinterpret_cast<const float4*>(p.rgb_sigma_fine) + ray * S + e
-                                  : reinterpret_cast<const float4*>(p.rgb_sigma) + ray * S + (p.rgb_sigma_fine ? e - S : e);
-          c = __ldg(src);
-          if (p.order) p.order[ray * n + s] = e;
+          const int e = src[i];
+          c = __ldg((e < s_sel ? fbase : cbase - s_sel) + e);
+          if (has_order) obase[s] = e;
         } else {
-          c = __ldg(reinterpret_cast<const float4*>(p.rgb_sigma) + ray * S + s);
-          t0 = __ldg(p.t + ray * S + s);
-          if (s + 1 < n) t1 = __ldg(p.t + ray * S + s + 1);
+          c = __ldg(cbase + s);
         }
-        const float delta = (s + 1 < n) ? (t1 - t0) : 1e10f;
-        float sg = c.w;
-        if (p.noise != nullptr) sg = sg + __ldg(p.noise + ray * n + s) * p.noise_std;
-        sg = clamp_sigma(sg, p.clamp_mode);
-        const float a = 1.f - expf(-delta * sg);
-        alpha[i] = a;
-        fac[i] = (1.f - a) + 1e-10f;
-        tt[i] = t0; cr[i] = c.x; cg[i] = c.y; cb[i] = c.z;
-        lane_prod *= fac[i];
       }
+      float sg = c.w;
+      if (has_noise && valid) sg = sg + __ldg(nbase + s) * noise_std;
+      sg = relu ? fmaxf(sg, 0.f) : (sg > 20.f ? sg : log1pf(expf(sg)));        // F.softplus(beta=1, threshold=20)
+      const float delta = (s + 1 < n) ? (tv[i + 1] - tv[i]) : 1e10f;
+      const float a = valid ? 1.f - expf(-delta * sg) : 0.f;
+      alpha[i] = a;
+      fac[i] = valid ? (1.f - a) + 1e-10f : 1.f;
+      cr[i] = c.x; cg[i] = c.y; cb[i] = c.z;
+      lane_prod *= fac[i];
     }
     // exclusive multiplicative scan of lane_prod across the warp
     float incl = lane_prod;
@@ -111,8 +130,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
     }
     float T = __shfl_up_sync(0xffffffffu, incl, 1);
     if (lane == 0) T = 1.f;
-    T *= t_carry;
-    t_carry *= __shfl_sync(0xffffffffu, incl, 31);
+    if (CHUNKED) {
+      T *= t_carry;
+      t_carry *= __shfl_sync(0xffffffffu, incl, 31);
+    }
 
     float w[IPL];
 #pragma unroll
@@ -135,9 +156,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
     }
 #pragma unroll
     for (int i = 0; i < IPL; ++i) {
-      ar += w[i] * cr[i]; ag += w[i] * cg[i]; ab += w[i] * cb[i]; ad += w[i] * tt[i];
-      const int s = base + lane * IPL + i;
-      if (p.weights != nullptr && s < n) p.weights[ray * n + s] = w[i];
+      ar += w[i] * cr[i]; ag += w[i] * cg[i]; ab += w[i] * cb[i]; ad += w[i] * tv[i];
+      if (has_weights && s0 + i < n) wbase[s0 + i] = w[i];
     }
   }
   ar = warp_sum(ar); ag = warp_sum(ag); ab = warp_sum(ab); ad = warp_sum(ad);
@@ -186,7 +206,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) merge_sort_kernel(const f
   if (ray >= n_rays) return;
   const int n = 2 * S, n2 = next_pow2_min32(n);
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem) + static_cast<size_t>(warp) * merge_smem_words(n, S);
-  load_and_sort_ray(keys, t_fine, t_coarse, ray, S, n, n2, lane);
+  load_and_sort_ray<1, 8>(keys, t_fine, t_coarse, ray, S, n, n2, lane);
   for (int s = lane; s < n; s += 32) {
     const unsigned long long k = keys[s];
     if (order) order[ray * n + s] = key_src(k);
