@@ -82,9 +82,13 @@ __device__ __forceinline__ void warp_bitonic_sort_lane_major(K (&key)[SLOTS], in
 }
 
 __host__ __device__ inline int next_pow2_min32(int n) {
+#ifdef __CUDA_ARCH__
+  return n <= 32 ? 32 : 1 << (32 - __clz(n - 1));
+#else
   int p = 32;
   while (p < n) p <<= 1;
   return p;
+#endif
 }
 
 // 64-bit words of shared memory one warp needs for n samples (S per list): keys[next_pow2(n)], then the fast path's scratch --

@@ -110,30 +110,47 @@ __global__ void __launch_bounds__(kPdfWarps * 32) sample_pdf_kernel(PdfParams p)
 // and a branch-free search: the shared-memory round trips of the scan and the data-dependent loop of the binary search were
 // what kept the kernel at 25-31 % of the HBM roofline (issue-bound, profiles/r1g_sample_pdf_kernel_raw.txt).  Every
 // floating-point operation and its order are those of the kernel above, so the results are bit-identical.
-template <bool FROM_COARSE, int PER>
-__global__ void __launch_bounds__(kPdfWarps * 32) sample_pdf_reg_kernel(PdfParams p, int P2) {
+template <bool FROM_COARSE, int PER, int P2>
+__global__ void __launch_bounds__(kPdfWarps * 32) sample_pdf_reg_kernel(PdfParams p) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const long long ray = static_cast<long long>(blockIdx.x) * kPdfWarps + warp;
   if (ray >= p.n) return;
-  const int M = p.M;
+  const int M = p.M;                                                  // M + 2 <= P2 <= 64 * PER
   float* cdf = smem + static_cast<size_t>(warp) * (P2 + M + 1);      // cdf[0 .. P2): entries beyond M are +inf
   float* bins = cdf + P2;                                             // bins[0 .. M]
   const int j0 = lane * PER;
+  const float eps = p.eps;
   float w[PER];
+  // (loops over the ray's elements are unrolled with compile-time trip counts: the run-time ones cost ~100 instructions of loop
+  //  control and address arithmetic per ray, a fifth of the kernel, profiles/r2h_c5_sass_counts.txt)
   if (FROM_COARSE) {
     const float* tc = p.bins + ray * p.S;
     const float* wc = p.weights + ray * p.S;
-    for (int j = lane; j <= M; j += 32) bins[j] = __fmul_rn(0.5f, __fadd_rn(__ldg(tc + j), __ldg(tc + j + 1)));
 #pragma unroll
-    for (int i = 0; i < PER; ++i) w[i] = (j0 + i < M) ? __fadd_rn(__fadd_rn(__ldg(wc + j0 + i + 1), 1e-5f), p.eps) : 0.f;
+    for (int i = 0; i <= PER; ++i) {
+      const int j = lane + 32 * i;
+      if (j <= M) bins[j] = __fmul_rn(0.5f, __fadd_rn(__ldg(tc + j), __ldg(tc + j + 1)));
+    }
+#pragma unroll
+    for (int i = 0; i < PER; ++i) w[i] = (j0 + i < M) ? __fadd_rn(__fadd_rn(__ldg(wc + j0 + i + 1), 1e-5f), eps) : 0.f;
   } else {
-    for (int j = lane; j <= M; j += 32) bins[j] = __ldg(p.bins + ray * (M + 1) + j);
+    const float* bn = p.bins + ray * (M + 1);
+    const float* wn = p.weights + ray * M;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) w[i] = (j0 + i < M) ? __fadd_rn(__ldg(p.weights + ray * M + j0 + i), p.eps) : 0.f;
+    for (int i = 0; i <= PER; ++i) {
+      const int j = lane + 32 * i;
+      if (j <= M) bins[j] = __ldg(bn + j);
+    }
+#pragma unroll
+    for (int i = 0; i < PER; ++i) w[i] = (j0 + i < M) ? __fadd_rn(__ldg(wn + j0 + i), eps) : 0.f;
   }
-  for (int j = M + 1 + lane; j < P2; j += 32) cdf[j] = __int_as_float(0x7f800000);
+#pragma unroll
+  for (int i = 0; i < P2 / 32; ++i) {
+    const int j = lane + 32 * i;
+    if (j > M) cdf[j] = __int_as_float(0x7f800000);
+  }
   double part = 0.0;                               // exact in float64 (see the kernel above): any association order gives the same bits
 #pragma unroll
   for (int i = 0; i < PER; ++i) part += static_cast<double>(w[i]);
@@ -161,9 +178,15 @@ __global__ void __launch_bounds__(kPdfWarps * 32) sample_pdf_reg_kernel(PdfParam
   if (lane == 0) cdf[0] = 0.f;
   __syncwarp();
   // searchsorted(cdf, u, right=False) = number of cdf[0..M] that are < u; the +inf padding never counts
-  for (int k = lane; k < p.K; k += 32) {
-    const float u = __ldg(p.u + ray * p.K + k);
+  const int K = p.K;
+  const float* u_ray = p.u + ray * K;
+  float* s_ray = p.samples + ray * K;
+  const bool has_inds = p.inds != nullptr;
+  int64_t* i_ray = has_inds ? p.inds + ray * K : nullptr;
+  for (int k = lane; k < K; k += 32) {
+    const float u = __ldg(u_ray + k);
     int pos = 0;
+#pragma unroll
     for (int step = P2 >> 1; step > 0; step >>= 1) pos += (cdf[pos + step - 1] < u) ? step : 0;
     const int ind = pos;
     const int below = max(ind - 1, 0);
@@ -171,10 +194,10 @@ __global__ void __launch_bounds__(kPdfWarps * 32) sample_pdf_reg_kernel(PdfParam
     const float c0 = cdf[below], c1 = cdf[above];
     const float b0 = bins[below], b1 = bins[above];
     float denom = __fsub_rn(c1, c0);
-    if (denom < p.eps) denom = 1.f;
+    if (denom < eps) denom = 1.f;
     const float frac = __fdiv_rn(__fsub_rn(u, c0), denom);
-    p.samples[ray * p.K + k] = __fadd_rn(b0, __fmul_rn(frac, __fsub_rn(b1, b0)));
-    if (p.inds) p.inds[ray * p.K + k] = ind;
+    s_ray[k] = __fadd_rn(b0, __fmul_rn(frac, __fsub_rn(b1, b0)));
+    if (has_inds) i_ray[k] = ind;
   }
 }
 
@@ -185,10 +208,13 @@ static int launch_pdf(const PdfParams& p, cudaStream_t stream, const char* what)
   if (per <= 4) {
     int P2 = 2;
     while (P2 < p.M + 2) P2 <<= 1;                 // P2 - 1 >= M + 1 searched entries
+    if (P2 < 32) P2 = 32;
     const size_t smem = static_cast<size_t>(kPdfWarps) * (P2 + p.M + 1) * sizeof(float);
-    if (per <= 1) sample_pdf_reg_kernel<FROM_COARSE, 1><<<grid, kPdfWarps * 32, smem, stream>>>(p, P2);
-    else if (per <= 2) sample_pdf_reg_kernel<FROM_COARSE, 2><<<grid, kPdfWarps * 32, smem, stream>>>(p, P2);
-    else sample_pdf_reg_kernel<FROM_COARSE, 4><<<grid, kPdfWarps * 32, smem, stream>>>(p, P2);
+#define CNG_PDF(PER_, P2_) sample_pdf_reg_kernel<FROM_COARSE, PER_, P2_><<<grid, kPdfWarps * 32, smem, stream>>>(p)
+    if (per <= 1) { if (P2 == 32) CNG_PDF(1, 32); else CNG_PDF(1, 64); }
+    else if (per <= 2) { if (P2 == 64) CNG_PDF(2, 64); else CNG_PDF(2, 128); }
+    else { if (P2 == 128) CNG_PDF(4, 128); else CNG_PDF(4, 256); }
+#undef CNG_PDF
     return check_launch(what);
   }
   const size_t smem = static_cast<size_t>(kPdfWarps) * (2 * (p.M + 1) + 2) * sizeof(float);
