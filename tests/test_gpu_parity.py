@@ -440,6 +440,71 @@ def test_merge_sort_is_torch_stable_sort(ops, n_rays, S):
     assert torch.equal(order.cpu().long(), ref_i) and torch.equal(t_sorted.cpu(), ref_t)
 
 
+@pytest.mark.parametrize("S", [2, 16, 17, 32, 33, 48, 64, 65, 128, 129, 255, 256])
+@pytest.mark.parametrize("spread", ["narrow", "wide", "signed"])
+def test_merge_sort_key_widths(ops, S, spread):
+    """The register sort of the fine keys runs on 32-bit keys when the ray's distances span few enough floats and on 64-bit keys
+    otherwise (csrc/merge_sort.cuh): both, at every per-lane key count, against torch's stable sort -- distances within a few
+    percent of 1 (the generator's ray_start / ray_end: always the 32-bit path), over six decades (always the 64-bit path), and of
+    both signs with zeros of both signs; with ties between and inside the lists."""
+    g = torch.Generator().manual_seed(S * 7 + len(spread))
+    n_rays = 37
+    if spread == "narrow":
+        t_c = torch.rand((n_rays, S), generator=g) * 0.24 + 0.88
+        t_f = torch.rand((n_rays, S), generator=g) * 0.24 + 0.88
+    elif spread == "wide":
+        t_c = torch.exp(torch.rand((n_rays, S), generator=g) * 14 - 7)
+        t_f = torch.exp(torch.rand((n_rays, S), generator=g) * 14 - 7)
+    else:
+        t_c = torch.randn((n_rays, S), generator=g)
+        t_f = torch.randn((n_rays, S), generator=g)
+        t_f[3, 0] = 0.0
+        t_c[3, 0] = -0.0
+    t_c = torch.sort(t_c, dim=1).values
+    t_f[0, : min(3, S)] = t_c[0, : min(3, S)]                 # fine == coarse: fine first
+    t_f[1] = t_f[1, 0]                                        # all fine distances equal: index order
+    t_c[2] = t_c[2, 0]                                        # all coarse distances equal
+    order, t_sorted = ops.merge_sort(dev(t_f), dev(t_c), want_sorted=True)
+    ref_t, ref_i = torch.sort(torch.cat([t_f, t_c], dim=1), dim=1, stable=True)
+    if spread == "signed":
+        # -0.0 and +0.0 compare equal for torch; the kernel orders the fine list by bit pattern (-0 before +0).  Row 3 holds the
+        # only zeros: compare it by value, the rest bit for bit.
+        keep = torch.ones(n_rays, dtype=torch.bool)
+        keep[3] = False
+        assert torch.equal(t_sorted.cpu()[3], ref_t[3])
+        assert torch.equal(order.cpu().long()[keep], ref_i[keep]) and torch.equal(t_sorted.cpu()[keep], ref_t[keep])
+    else:
+        assert torch.equal(order.cpu().long(), ref_i) and torch.equal(t_sorted.cpu(), ref_t)
+
+
+@pytest.mark.parametrize("S", [24, 64, 100, 200, 256])
+def test_merge_composite_unsorted_fine_vs_oracle(ops, S):
+    """The merge as the generator calls it: the fine distances arrive in the order of the random draws (unsorted), at every
+    chunking of the compositing loop (2S <= 128: one pass; beyond: chunks of 128 with the transmittance carried)."""
+    from conditioned_nerf_gan_b200.generators.volumetric_rendering import camera_tables
+    g = torch.Generator().manual_seed(S)
+    B, img = 1, 5
+    R = img * img
+    fine = torch.randn((B, R, S, 4), generator=g)
+    coarse = torch.randn((B, R, S, 4), generator=g)
+    for x in (fine, coarse):
+        x[..., :3] = torch.sigmoid(x[..., :3])
+        x[..., 3] *= 6
+    t_c = torch.sort(torch.rand((B, R, S, 1), generator=g) * 0.24 + 0.88, dim=2).values
+    t_f = torch.rand((B, R, S, 1), generator=g) * 0.24 + 0.88
+    noise = torch.randn((B, R, 2 * S, 1), generator=g)
+    rays, _ = camera_tables((img, img), S, FOV, 0.88, 1.12, "cuda")
+    for white, last, noise_std, clamp in ((True, False, 0.0, "relu"), (False, True, 0.5, "softplus")):
+        pixels, depth, taps = ops.merge_composite(dev(fine), dev(coarse), dev(t_f), dev(t_c), dev(noise), rays, B, img, img,
+                                                  noise_std, clamp, white, last, taps=True)
+        all_out, all_t, order = oracle.merge_by_depth(fine, coarse, t_f, t_c)
+        assert torch.equal(taps["order"].cpu().long(), order.squeeze(-1)), "merge order differs from the stable sort"
+        rgb, dist, _ = oracle.composite(all_out, all_t, noise, noise_std, clamp, white, last)
+        _assert_rel(taps["rgb"].cpu(), rgb, what="rgb")
+        _assert_rel(taps["dist"].cpu(), dist.squeeze(-1), what="dist")
+        assert torch.isfinite(depth).all() and torch.isfinite(pixels).all()
+
+
 def test_merge_composite_rejects_more_than_512_samples(ops):
     """Documented limit of the per-warp sort (include/cng_b200.h): 2S <= 512 samples per ray; beyond it the call fails loudly."""
     from conditioned_nerf_gan_b200._lib import CngError
