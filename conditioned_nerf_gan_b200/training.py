@@ -42,6 +42,13 @@ def loss_depth(gt: torch.Tensor, preds: torch.Tensor) -> torch.Tensor:
     return ((gt[mask] - preds[mask]) ** 2).mean()
 
 
+def _detach(z):
+    """detach() through the (volume, global feature) tuples / pyramids an encoder may return"""
+    if isinstance(z, (tuple, list)):
+        return type(z)(_detach(t) for t in z)
+    return z.detach()
+
+
 class GanTrainStep:
     """Owns the three optimizers and the GradScaler; ``step(sample)`` = one discriminator update + one generator/encoder
     update on ``sample = {"img": [B,3,H,W], "voxel": [B,4,V,V,V], "cam2world": [B,4,4] (, "depth": [B,H,W])}``.
@@ -77,12 +84,22 @@ class GanTrainStep:
         self.curriculum = curriculum             # optional: the reference's curriculum dict; ``set_alpha`` then reads the stage start from it
         self.alpha = 1.0
         self.ddp = ddp
+        self.share_encoder_forward = True        # step(): one encoder forward serves the D step and the G/E step (see there)
+        self._shared_z = None
+        self._encoder_deterministic = None
         self.losses: Dict[str, torch.Tensor] = {}
         self.grad_norms: Dict[str, torch.Tensor] = {}          # total norms returned by clip_grad_norm_ (device scalars)
         if hasattr(generator, "set_device"):
             generator.set_device(self.device)
 
     # ------------------------------------------------------------------------------------------------------------
+    def _encoder_is_deterministic(self) -> bool:
+        if self._encoder_deterministic is None:
+            bad = (torch.nn.modules.batchnorm._BatchNorm, torch.nn.modules.dropout._DropoutNd)
+            self._encoder_deterministic = not any(isinstance(m, bad) and (not isinstance(m, torch.nn.modules.dropout._DropoutNd) or m.p > 0)
+                                                  for m in self.encoder_ddp.modules())
+        return self._encoder_deterministic
+
     def _autocast(self):
         return torch.autocast(self.device.type, dtype=self.amp_dtype, enabled=self.amp)
 
@@ -117,7 +134,7 @@ class GanTrainStep:
                     cam2worlds = sample["cam2world"].to(self.device)
                 gen_imgs = []
                 for s in range(splits):
-                    z = self.encoder_ddp(voxels[s * sb:(s + 1) * sb])
+                    z = _detach(self._shared_z) if self._shared_z is not None else self.encoder_ddp(voxels[s * sb:(s + 1) * sb])
                     gen_img, _ = self.generator_ddp(z, cam2worlds[s * sb:(s + 1) * sb], **md)
                     gen_imgs.append(gen_img)
                 gen_imgs = torch.cat(gen_imgs, dim=0)
@@ -188,7 +205,7 @@ class GanTrainStep:
             sl = slice(s * sb, (s + 1) * sb)
             with self._no_sync(self.generator_ddp, last), self._no_sync(self.encoder_ddp, last):
                 with self._autocast():
-                    z = self.encoder_ddp(voxels[sl])
+                    z = self._shared_z if self._shared_z is not None else self.encoder_ddp(voxels[sl])
                     gen_imgs, gen_depths = self.generator_ddp(z, cam2worlds[sl], **md)
                     if use_d:
                         g_preds = self.discriminator(gen_imgs, self.alpha, cond=None, **md)
@@ -216,9 +233,20 @@ class GanTrainStep:
         if use_d:
             self.discriminator_ddp.train()
         self.set_alpha()
-        if use_d:
-            self.train_discriminator(sample)
-        self.train_generator(sample)
+        # The reference encodes the voxels twice per step -- without grad for the D step's fake images (utils.py:771-775), with
+        # grad for the G/E step (:652-655).  The encoder's weights do not change in between (only optimizer_D steps) and a
+        # deterministic encoder (no dropout, no batch statistics) returns the same bits both times: encode once, with grad, and
+        # give the D step the detached result.  Micro-batched steps (batch_split > 1) keep the two passes.
+        self._shared_z = None
+        if use_d and self.share_encoder_forward and self.metadata.get("batch_split", 1) == 1 and self._encoder_is_deterministic():
+            with self._autocast():
+                self._shared_z = self.encoder_ddp(sample["voxel"].to(self.device, non_blocking=True))
+        try:
+            if use_d:
+                self.train_discriminator(sample)
+            self.train_generator(sample)
+        finally:
+            self._shared_z = None
         self.generator.step = getattr(self.generator, "step", 0) + 1
         if use_d:
             self.discriminator.step = getattr(self.discriminator, "step", 0) + 1

@@ -123,6 +123,32 @@ def test_train_step_harness_with_our_encoder_and_discriminator_matches_reference
             assert abs(v - want) <= 2e-3 * abs(want) + 1e-5, (i, k, v, want)
 
 
+def test_step_shares_one_encoder_forward_without_changing_the_update():
+    """GanTrainStep.step() encodes the voxels once for the D step and the G/E step (the reference does it twice with unchanged
+    encoder weights, utils.py:771-775 and :652-655): same losses, gradient norms and updated parameters as the two-pass form."""
+    from conditioned_nerf_gan_b200.training import GanTrainStep
+    results = []
+    for share in (True, False):
+        torch.manual_seed(11)
+        enc, disc = _modules()
+        gen = ts.OracleGenerator(ts.TINY_SIREN, oracle.init_generator_state(ts.TINY_SIREN, z_dim=ts.TINY_ZDIM, seed=0))
+        calls = {"n": 0}
+        enc.register_forward_hook(lambda *a: calls.__setitem__("n", calls["n"] + 1))
+        tr = GanTrainStep(gen, enc, disc, dict(ts.tiny_config(), draws=ts.tiny_draws()), "cpu", amp=False)
+        tr.share_encoder_forward = share
+        tr.alpha = 0.3
+        torch.manual_seed(5)
+        for _ in range(2):
+            losses = tr.step(ts.tiny_sample())
+        assert calls["n"] == (2 if share else 4)
+        results.append(({k: float(v) for k, v in losses.items()}, {k: float(v) for k, v in tr.grad_norms.items()},
+                        [p.detach().clone() for p in enc.parameters()], [p.detach().clone() for p in gen.parameters()]))
+    (l0, n0, e0, g0), (l1, n1, e1, g1) = results
+    assert l0 == pytest.approx(l1, rel=1e-6) and n0 == pytest.approx(n1, rel=1e-6)
+    for a, b in zip(e0 + g0, e1 + g1):
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-8)
+
+
 def test_gan_train_step_host_logic_matches_reference_on_cpu():
     """training.GanTrainStep itself (optimizers, GradScaler order, clipping, loss bookkeeping) on CPU, with the oracle renderer
     standing in for the CUDA generator: two optimisation steps against the numbers recorded with the reference's modules.
