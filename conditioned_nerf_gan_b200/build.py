@@ -21,7 +21,7 @@ SOURCES = ["cng_api.cu", "raymarch_gather.cu", "film_siren_simt.cu", "film_siren
 EXPERIMENTAL = os.environ.get("CNG_BUILD_EXPERIMENTAL", "0") == "1"
 if EXPERIMENTAL:
     SOURCES += ["film_siren_tc2.cu", "film_siren_tc3.cu"]
-# CNG_TC_EPI_WARPS (4 or 8): epilogue warps per tile slot of the one-CTA-per-SM tcgen05 kernel (film_siren_tc.cu)
+# CNG_TC_EPI_WARPS (4, 8 or 12; 12 needs CNG_TC_EPI_PIPELINE=0 to fit 72 registers): epilogue warps per tile slot of the one-CTA-per-SM tcgen05 kernel (film_siren_tc.cu)
 EPI_WARPS = os.environ.get("CNG_TC_EPI_WARPS", "8")
 EPI_PIPELINE = os.environ.get("CNG_TC_EPI_PIPELINE", "1")    # 1: double-buffer the epilogue's TMEM loads
 NVCC_FLAGS = [

@@ -60,8 +60,11 @@ constexpr int kRing = 3;
 constexpr int kDefaultCtaGroup = 1;   // measured: the pair kernel pays ~1300 cycles of cross-CTA hand-off per layer
 constexpr int kDefaultTrainPolyOneIn = 4;   // training-mode epilogue: one (sin, cos) pair in four on the FMA pipe (measured: 1.93 -> 1.80 ms per 1M points, profiles/r2_bwd_kernels.txt)
 constexpr int kDefaultPolyOneIn = 8;   // one sine in 8 on the FMA pipe: measured 2.77 -> 2.68 ms per launch once the shift handling left the epilogue chain (it was neutral before)
-constexpr int kEpiWarpsPerSlot = CNG_TC_EPI_WARPS;   // 4 or 8 (build-time knob, see build.py)
-constexpr int kBlocksPerWarp = 32 / kEpiWarpsPerSlot;      // 32-column accumulator blocks per epilogue warp
+constexpr int kEpiWarpsPerSlot = CNG_TC_EPI_WARPS;   // 4, 8 or 12 (build-time knob, see build.py)
+static_assert(kEpiWarpsPerSlot == 4 || kEpiWarpsPerSlot == 8 || kEpiWarpsPerSlot == 12, "CNG_TC_EPI_WARPS: 4, 8 or 12");
+constexpr int kEpiGroups = kEpiWarpsPerSlot / 4;           // warps per TMEM lane quarter = column groups of the accumulator
+constexpr bool kEpiEven = (8 % kEpiGroups) == 0;           // every group owns the same number of 32-column blocks
+constexpr int kBlocksPerWarp = (8 + kEpiGroups - 1) / kEpiGroups;   // 32-column accumulator blocks per epilogue warp (the most any group owns)
 constexpr int kMmaWarp = 2 * kEpiWarpsPerSlot;
 constexpr int kProducerWarp = kMmaWarp + 1;
 constexpr int kNumThreads = 32 * (kProducerWarp + 1);
@@ -427,8 +430,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
     // =========================== epilogue warps (slot x = warp / 8) ===========================
     const int x = warp / kEpiWarpsPerSlot;
     const int q = warp & 3;                       // TMEM lane quarter == warp_id % 4
-    const int half = (warp % kEpiWarpsPerSlot) >> 2;   // column group: blocks [kBlocksPerWarp*half, kBlocksPerWarp*(half+1))
+    const int half = (warp % kEpiWarpsPerSlot) >> 2;   // column group: accumulator blocks [cc0, cc1) of 32 columns (4 + 4, or 2 + 3 + 3 with 12 warps)
     constexpr int kB = kBlocksPerWarp;
+    const int cc0 = (8 * half) / kEpiGroups, cc1 = (8 * (half + 1)) / kEpiGroups;
     const int row = q * 32 + lane;
     const uint32_t a_base = kSmemA + x * kATileBytes;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(x) * kHID;
@@ -441,7 +445,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
     // layer -- off the critical chain.  (Measured on the pipelined kernel: pre-storing the shift in the accumulator
     // with tcgen05.st put an L2-latency load and a TMEM store on every block's chain, ~900 cycles per layer.)
     constexpr int kSlotThreads = 32 * kEpiWarpsPerSlot;
-    constexpr int kRowPerThread = kHID / kSlotThreads;
+    constexpr int kRowPerThread = (kHID + kSlotThreads - 1) / kSlotThreads;
     const int ts = (warp % kEpiWarpsPerSlot) * 32 + lane;
     float* row_x = reinterpret_cast<float*>(smem + kSmemShift) + x * kHID;
     float row_next[kRowPerThread];
@@ -449,7 +453,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
     auto publish_row = [&]() {
       named_bar_sync(1 + x, kSlotThreads);            // every warp of the slot is done reading the old row
 #pragma unroll
-      for (int i = 0; i < kRowPerThread; ++i) row_x[ts + i * kSlotThreads] = row_next[i];
+      for (int i = 0; i < kRowPerThread; ++i)
+        if (ts + i * kSlotThreads < kHID) row_x[ts + i * kSlotThreads] = row_next[i];
       named_bar_sync(1 + x, kSlotThreads);
     };
     // training mode: the A tile leaves for HBM as one bulk store per layer (issued by one thread of the slot); before the
@@ -465,7 +470,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
       // ---- shift row of layer 0 -> shared memory (prefetched during the previous tile's last layer, see below) ----
       if (iter == 0) {
 #pragma unroll
-        for (int i = 0; i < kRowPerThread; ++i) row_next[i] = __ldg(shift_item + ts + i * kSlotThreads);
+        for (int i = 0; i < kRowPerThread; ++i)
+          if (ts + i * kSlotThreads < kHID) row_next[i] = __ldg(shift_item + ts + i * kSlotThreads);
       }
       publish_row();
       if constexpr (kTrain) tile_free();
@@ -475,7 +481,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
         const float* pts = kGather ? p.points + (static_cast<size_t>(ti.item) * p.N + ti.n0) * 3 : nullptr;
         const float4* vol = kGather ? p.vol + static_cast<size_t>(ti.item) * p.vol_item_stride : nullptr;
 #pragma unroll
-        for (int it = kB * half; it < kB * half + kB; ++it) {
+        for (int it = cc0; it < cc1; ++it) {
           const int r = q * 32 + it * 4 + (lane >> 3);
           const int c4 = lane & 7;                               // float4 index within the row: k = 4*c4
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -512,7 +518,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
           const float* src = more ? shift_item + (l + 1) * kHID
                                   : p.shift + static_cast<size_t>(tn < p.total_tiles ? tn / p.tiles_per_item : ti.item) * L * kHID;
 #pragma unroll
-          for (int i = 0; i < kRowPerThread; ++i) row_next[i] = __ldg(src + ts + i * kSlotThreads);
+          for (int i = 0; i < kRowPerThread; ++i)
+            if (ts + i * kSlotThreads < kHID) row_next[i] = __ldg(src + ts + i * kSlotThreads);
         }
         mbar_wait(acc_full(x), acc_phase);
         acc_phase ^= 1;
@@ -609,20 +616,25 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
         if constexpr (kEpiWarpsPerSlot == 4 || CNG_TC_EPI_PIPELINE) {
           // keep the TMEM load of block i+1 in flight under the sines of block i (needs 2 x 32 accumulator registers)
           uint32_t va[32], vb[32];
-          CNG_TMEM_LD_32(t_lane + (kB * half) * 32, va);
+          CNG_TMEM_LD_32(t_lane + cc0 * 32, va);
 #pragma unroll
           for (int i = 0; i < kB; i += 2) {
-            const int cc = kB * half + i;
-            tmem_ld_wait();
-            CNG_TMEM_LD_32(t_lane + (cc + 1) * 32, vb);
-            finish_block(va, cc);
-            tmem_ld_wait();
-            if (i + 2 < kB) CNG_TMEM_LD_32(t_lane + (cc + 2) * 32, va);
-            finish_block(vb, cc + 1);
+            const int cc = cc0 + i;
+            if (kEpiEven || cc < cc1) {
+              const bool more1 = kEpiEven ? (i + 1 < kB) : (cc + 1 < cc1), more2 = kEpiEven ? (i + 2 < kB) : (cc + 2 < cc1);
+              tmem_ld_wait();
+              if (more1) CNG_TMEM_LD_32(t_lane + (cc + 1) * 32, vb);
+              finish_block(va, cc);
+              if (more1) {
+                tmem_ld_wait();
+                if (more2) CNG_TMEM_LD_32(t_lane + (cc + 2) * 32, va);
+                finish_block(vb, cc + 1);
+              }
+            }
           }
         } else {
 #pragma unroll 1
-          for (int cc = kB * half; cc < kB * half + kB; ++cc) {
+          for (int cc = cc0; cc < cc1; ++cc) {
             uint32_t v[32];
             CNG_TMEM_LD_32(t_lane + cc * 32, v);
             tmem_ld_wait();
