@@ -537,6 +537,7 @@ def measure_c5(rays_m: int = 2):
     merge+composite kernels at 64 / 128 / 256 samples per ray on ``rays_m`` Mi rays, algorithmic bytes per ray from
     SURVEY.md 8(d), against the measured copy bandwidth.  Working sets (0.3 - 5 GB) exceed the 126 MB L2."""
     from conditioned_nerf_gan_b200 import ops
+    from oracle import nerf_path as oracle
     peak = peaks()["hbm_gbs"]
     dev = "cuda"
 
@@ -567,14 +568,27 @@ def measure_c5(rays_m: int = 2):
         cases = [("composite", lambda: ops.composite_fwd(rs, t, None, 0.0, "relu", True, False), n * (S * 20 + 16 + 4 * S)),
                  ("resample", lambda: ops.resample_from_coarse(t, w, u), n * 16 * S),
                  ("merge", lambda: ops.merge_composite(rs2, rs, t2, t, None, rays, n // 1024, 32, 32, 0.0, "relu", True, False), n * (2 * S * 20 + 16))]
+        # same-box comparator: the reference's own eager op chain for the same step -- its torch-port restatement
+        # (oracle/nerf_path.py: fancy_integration, the sample_pdf call site, cat + sort + gather) on cuda tensors, on a slice of
+        # the rays (its temporaries are ~10x the inputs); a baseline leg, nothing of it is on the product path
+        ne = min(n, 1 << 18)
+        z4 = lambda a: a[:ne].unsqueeze(0)
+        zero_noise = torch.zeros((1, ne, 2 * S, 1), device=dev)
+        eager = {"composite": lambda: oracle.composite(z4(rs), z4(t).unsqueeze(-1), zero_noise[:, :, :S], 0.0, "relu", True, False),
+                 "resample": lambda: oracle.coarse_to_fine_t(z4(w), z4(t), u[:ne], S),
+                 "merge": lambda: oracle.composite(*oracle.merge_by_depth(z4(rs2), z4(rs), z4(t2).unsqueeze(-1), z4(t).unsqueeze(-1))[:2],
+                                                   zero_noise, 0.0, "relu", True, False)}
         for name, fn, by in cases:
             ms = timeit(fn)
+            ems = timeit(eager[name], reps=3) * (n / ne)
             rows.append({"kernel": name, "samples_per_ray": S if name != "merge" else f"{S}+{S}", "rays": n, "ms": ms, "gbs": by / ms / 1e6,
-                         "frac": by / ms / 1e6 / peak})
-        del rs, t, w, u, rs2, t2
+                         "frac": by / ms / 1e6 / peak, "gpu_eager_ms": ems, "speedup_vs_gpu_eager": ems / ms})
+        del rs, t, w, u, rs2, t2, zero_noise
         torch.cuda.empty_cache()
     return {"peak_gbs": peak, "unit": "GB/s", "rays": n, "rows": rows,
-            "bytes_per_ray": "composite S*20+16+4S (weights emitted), resample 16*S, merge 2S*20+16 (SURVEY.md 8d)"}
+            "bytes_per_ray": "composite S*20+16+4S (weights emitted), resample 16*S, merge 2S*20+16 (SURVEY.md 8d)",
+            "gpu_eager": "oracle/nerf_path.py (torch port of fancy_integration / the sample_pdf call site / cat+sort+gather+fancy_integration) "
+                         "run eagerly on cuda on 262144 of the rays, scaled to the full ray count"}
 
 
 def measure_gpu_eager(args, steps=5, warmup=3):
