@@ -11,6 +11,8 @@
 // sequential loop; the divide, the search and the lerp run in parallel with IEEE fp32 ops in
 // the reference's order (no FMA contraction: every op is an explicit __f*_rn intrinsic).
 // Algorithmic bytes per ray: 4*((M+1) + M + K) read + 4*K written (+8*K if indices are emitted).
+#include <stdlib.h>
+
 #include "cng_common.cuh"
 
 namespace cng {
@@ -205,7 +207,10 @@ template <bool FROM_COARSE>
 static int launch_pdf(const PdfParams& p, cudaStream_t stream, const char* what) {
   const unsigned grid = static_cast<unsigned>((p.n + kPdfWarps - 1) / kPdfWarps);
   const int per = (p.M + 31) / 32;
-  if (per <= 4) {
+  // elements per lane the register kernel is used up to: 8 (129..256 bins) measured slower than the shared-memory kernel on B200
+  // (2 Mi rays: 200 samples 3.82 vs 3.14 ms, 256 samples 4.67 vs 4.28 ms, same bits), so the default stays 4; CNG_PDF_MAX_PER=8 for A/B
+  static const int max_per = [] { const char* e = getenv("CNG_PDF_MAX_PER"); return e ? atoi(e) : 4; }();
+  if (per <= max_per && per <= 8) {
     int P2 = 2;
     while (P2 < p.M + 2) P2 <<= 1;                 // P2 - 1 >= M + 1 searched entries
     if (P2 < 32) P2 = 32;
@@ -213,7 +218,8 @@ static int launch_pdf(const PdfParams& p, cudaStream_t stream, const char* what)
 #define CNG_PDF(PER_, P2_) sample_pdf_reg_kernel<FROM_COARSE, PER_, P2_><<<grid, kPdfWarps * 32, smem, stream>>>(p)
     if (per <= 1) { if (P2 == 32) CNG_PDF(1, 32); else CNG_PDF(1, 64); }
     else if (per <= 2) { if (P2 == 64) CNG_PDF(2, 64); else CNG_PDF(2, 128); }
-    else { if (P2 == 128) CNG_PDF(4, 128); else CNG_PDF(4, 256); }
+    else if (per <= 4) { if (P2 == 128) CNG_PDF(4, 128); else CNG_PDF(4, 256); }
+    else { if (P2 == 256) CNG_PDF(8, 256); else CNG_PDF(8, 512); }
 #undef CNG_PDF
     return check_launch(what);
   }
