@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) film_siren_dgrad_kernel(DgradPar
             mbar_wait(w_empty(slot), phase ^ 1);
             if (elected) {
               mbar_arrive_expect_tx(w_full(slot), bytes);
-              bulk_g2s(s_base + kSmemW_B + slot * kChunkBytes, p.wt + wt_offset(L, l, c), bytes, w_full(slot));
+              bulk_g2s_hint(s_base + kSmemW_B + slot * kChunkBytes, p.wt + wt_offset(L, l, c), bytes, w_full(slot), kL2EvictLast);
             }
             __syncwarp();
             if (++slot == kRingB) { slot = 0; phase ^= 1; }
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) film_siren_dgrad_kernel(DgradPar
         uint4 ga[2], gb[2];
         auto load_g = [&](uint4 (&gg)[2], int cc) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) gg[h] = __ldg(gt + ((cc * 4 + q) * 2 + h) * 32 + lane);
+          for (int h = 0; h < 2; ++h) gg[h] = ld_global_evict_first(gt + ((cc * 4 + q) * 2 + h) * 32 + lane);
         };
         load_g(ga, 4 * half);
         mbar_wait(acc_full(x), acc_phase);
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) film_siren_dgrad_kernel(DgradPar
         fence_proxy_async();
         named_bar_sync(1 + x, kSlotThreads);              // the whole dz_l tile is in shared memory (and fenced for the async proxy)
         if (storer) {
-          bulk_s2g(p.dz + (static_cast<size_t>(l) * p.T + t) * kTileImageBytes, s_base + a_base, kTileImageBytes);
+          bulk_s2g_hint(p.dz + (static_cast<size_t>(l) * p.T + t) * kTileImageBytes, s_base + a_base, kTileImageBytes, kL2EvictFirst);
           bulk_commit();
         }
         mbar_arrive(act_ready(x));
@@ -466,13 +466,13 @@ __global__ void __launch_bounds__(kThreadsW, 1) film_siren_wgrad_kernel(WgradPar
             mbar_arrive_expect_tx(full(slot), 32768u + (l == 0 ? 8192u : 32768u));
             const uint8_t* dz = p.dz + (static_cast<size_t>(l) * p.T + t) * kTileImageBytes + hf * 8192;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bulk_g2s(st + j * 8192, dz + j * kABlockBytes, 8192, full(slot));
+            for (int j = 0; j < 4; ++j) bulk_g2s_hint(st + j * 8192, dz + j * kABlockBytes, 8192, full(slot), kL2EvictFirst);
             if (l == 0) {
-              bulk_g2s(st + 32768, p.feat + static_cast<size_t>(t) * kFeatImageBytes + hf * 8192, 8192, full(slot));
+              bulk_g2s_hint(st + 32768, p.feat + static_cast<size_t>(t) * kFeatImageBytes + hf * 8192, 8192, full(slot), kL2EvictFirst);
             } else {
               const uint8_t* xs = p.x + (static_cast<size_t>(l - 1) * p.x_stride + t) * kTileImageBytes + hf * 8192;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) bulk_g2s(st + 32768 + j * 8192, xs + j * kABlockBytes, 8192, full(slot));
+              for (int j = 0; j < 4; ++j) bulk_g2s_hint(st + 32768 + j * 8192, xs + j * kABlockBytes, 8192, full(slot), kL2EvictFirst);
             }
           }
           __syncwarp();

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
               mbar_wait(w_empty(slot), phase ^ 1);
               if (elected) {
                 mbar_arrive_expect_tx(w_full(slot), bytes);
-                bulk_g2s(s_base + kSmemW + slot * kChunkBytes, img + chunk_offset(L, l, c), bytes, w_full(slot));
+                bulk_g2s_hint(s_base + kSmemW + slot * kChunkBytes, img + chunk_offset(L, l, c), bytes, w_full(slot), kL2EvictLast);
               }
               __syncwarp();
               if (++slot == kRingN) { slot = 0; phase ^= 1; }
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
       if constexpr (kTrain) {                                      // the layer-0 operand block -> HBM (operand of the layer-0 weight gradient)
         named_bar_sync(1 + x, kSlotThreads);
         if (storer) {
-          bulk_s2g(p.dump_feat + static_cast<size_t>(t) * kABlockBytes, s_base + a_base, kABlockBytes);
+          bulk_s2g_hint(p.dump_feat + static_cast<size_t>(t) * kABlockBytes, s_base + a_base, kABlockBytes, kL2EvictFirst);
           bulk_commit();
         }
       }
@@ -584,8 +584,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
               gs[2 * i] = __byte_perm(gq[0], gq[1], 0x5410);
               gs[2 * i + 1] = __byte_perm(gq[2], gq[3], 0x5410);
             }
-            gt[((cc * 4 + q) * 2 + 0) * 32 + lane] = make_uint4(gs[0], gs[1], gs[2], gs[3]);
-            gt[((cc * 4 + q) * 2 + 1) * 32 + lane] = make_uint4(gs[4], gs[5], gs[6], gs[7]);
+            st_global_evict_first(gt + ((cc * 4 + q) * 2 + 0) * 32 + lane, make_uint4(gs[0], gs[1], gs[2], gs[3]));
+            st_global_evict_first(gt + ((cc * 4 + q) * 2 + 1) * 32 + lane, make_uint4(gs[4], gs[5], gs[6], gs[7]));
             return;
           }
           // 32 columns = 64 bytes = 4 x 16-byte chunks of K-block cc/2, logical chunk (cc&1)*4 + i
@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
         if constexpr (kTrain) {                                    // x_{l+1} tile image -> HBM
           named_bar_sync(1 + x, kSlotThreads);
           if (storer) {
-            bulk_s2g(p.dump_x + (static_cast<size_t>(l) * p.total_tiles + t) * kATileBytes, s_base + a_base, kATileBytes);
+            bulk_s2g_hint(p.dump_x + (static_cast<size_t>(l) * p.total_tiles + t) * kATileBytes, s_base + a_base, kATileBytes, kL2EvictFirst);
             bulk_commit();
           }
         }

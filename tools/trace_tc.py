@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Clock64 timeline of CTA 0 of the cta_group::1 FiLM-SIREN kernel (debug hook cng_internal_set_tc_trace)."""
+"""Clock64 timeline of CTA 0 of the cta_group::1 FiLM-SIREN kernel (debug hook cng_internal_set_tc_trace).
+    python tools/trace_tc.py [cta_group=1] [infer|train]      (train: the training-mode kernel with its dumps, 1 Mi points)"""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ["CNG_TC_CG"] = sys.argv[1] if len(sys.argv) > 1 else "1"
@@ -9,7 +10,8 @@ from oracle import nerf_path as oracle
 lib = _lib.load()
 lib.cng_internal_set_tc_trace.argtypes = [ctypes.c_void_p]
 lib.cng_internal_set_tc_trace.restype = None
-B, N, L = 8, 128 * 128 * 24, 8
+MODE = sys.argv[2] if len(sys.argv) > 2 else "infer"
+B, N, L = (8, 128 * 128 * 24, 8) if MODE == "infer" else (1, 1 << 20, 8)
 st = oracle.init_generator_state("TALLSIREN_FG", seed=0)
 dev = "cuda"
 ws = [st[f"siren.network.{i}.layer.weight"].to(dev) for i in range(L)]
@@ -19,7 +21,8 @@ glob = torch.randn((B, 256), generator=g) * 0.05 + 0.19
 freq, phase = (t.to(dev) for t in oracle.film_parameters(glob, st["siren.mapping_network.weight"], st["siren.mapping_network.bias"]))
 feat = (torch.randn((B, N, 32), generator=g) * 0.3).to(dev)
 fw, fb = st["siren.final_layer.weight"].to(dev), st["siren.final_layer.bias"].to(dev)
-run = lambda: ops.film_siren_fwd(feat, ws, bs, freq, phase, fw, fb, True, "bf16")
+run = (lambda: ops.film_siren_fwd(feat, ws, bs, freq, phase, fw, fb, True, "bf16")) if MODE == "infer" else \
+      (lambda: ops.film_siren_fwd_train(feat, ws, bs, freq, phase, fw, fb, True, "fp16"))
 run(); torch.cuda.synchronize()
 trace = torch.zeros((4, 9, 2, 8), dtype=torch.int64, device=dev)
 lib.cng_internal_set_tc_trace(ctypes.c_void_p(trace.data_ptr()))
