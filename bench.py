@@ -502,7 +502,7 @@ def measure_train(args, rank, world, local, dev, barrier, max_over_ranks, steps,
            "steps": steps, "warmup": warmup, "launches": launches // max(steps, 1), "host_issue_ms": host_issue_ms, "allreduce_ms": allreduce_ms,
            "allreduce_bytes": 4 * n_param, "scaling": "strong", "final_loss": results[-1], "clocks": clocks,
            "h2d_bytes_per_step": int((voxel_h.numel() + img_h.numel() + cam_h.numel()) * 4), "d2h_bytes_per_step": 8,
-           "mlp_flops_per_step": 3 * 2 * mlp_flops_per_point(L) * pts,
+           "mlp_flops_per_step": 3 * 2 * mlp_flops_per_point(L) * pts, "cos_dump_bits": _cos_dump_bits(),
            "workload": "full GAN train step (3D U-Net encoder + FiLM-SIREN generator + progressive discriminator, D step with R1 then G/E step), "
                        "128x128, 48+48 samples/ray, global batch 32 (BASELINE configs[2]); autocast fp16 + GradScaler, Adam x3; "
                        "host voxels / images / cameras copied in and the losses read back every step"}
@@ -526,10 +526,17 @@ def run_train(args):
                            "generator": "hand-written CUDA path: forward x2 (no-grad for the D step, with grad for the G step) + backward"},
                 "e2e": {"value": t["images_per_s"], "unit": "images/s", "h2d_bytes_per_step": t["h2d_bytes_per_step"], "d2h_bytes_per_step": 8},
                 "gpu_launches": t["launches"] * args.steps, "clocks": t["clocks"], "final_loss": t["final_loss"],
-                "allreduce_ms": t["allreduce_ms"], "host_issue_ms": t["host_issue_ms"], "mlp_flops_per_step": t["mlp_flops_per_step"]}
+                "allreduce_ms": t["allreduce_ms"], "host_issue_ms": t["host_issue_ms"], "mlp_flops_per_step": t["mlp_flops_per_step"],
+                "cos_dump_bits": t.get("cos_dump_bits")}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _cos_dump_bits() -> int:
+    """format of the MLP backward's cos(u) dump (16 = fp16, default; 8 = CNG_G_DUMP_BITS=8, faster, 1/254 quantisation)"""
+    from conditioned_nerf_gan_b200 import ops
+    return ops.g_image_bytes() * 8 // (128 * 256)
 
 
 def measure_c5(rays_m: int = 2):

@@ -52,6 +52,7 @@ SIGNATURES = {
                                          c_void_p, c_void_p, c_int, c_int, ctypes.c_uint, ctypes.c_uint, c_void_p, c_size_t, c_void_p, c_size_t,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cng_film_siren_wt_image_bytes": (c_size_t, [c_int]),
+    "cng_film_siren_g_dump_bits": (c_int, []),
     "cng_film_siren_wt_images": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cng_film_siren_dgrad": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_int, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
                                      ctypes.c_uint, ctypes.c_uint, c_void_p, c_size_t, c_void_p]),

@@ -46,7 +46,8 @@ namespace bwdtc {
 
 constexpr int kTileImageBytes = kATileBytes;                 // 65536: [4 K-blocks][128 rows][64 x 16 bit], 128B-swizzled
 constexpr int kFeatImageBytes = kABlockBytes;                // 16384: layer-0 operand block [x_hi(32) | x_lo(32)]
-constexpr int kGTileBytes = kTileM * kHID;                   // 32768: g of one tile-layer, [cc 8][q 4][h 2][lane 32] x 16 B of 8-bit codes
+// g of one tile-layer: fp16 [cc 8][q 4][i 4][lane 32] x 16 B = 65536 bytes, or 8-bit codes [cc 8][q 4][h 2][lane 32] x 16 B = 32768
+__host__ __device__ constexpr int g_tile_bytes(int g_bits) { return kTileM * kHID * g_bits / 8; }
 
 // ---- W^T images for B1 (bf16, item independent) ------------------------------------------------------------------
 // [head 32 KB][layer L-1: 4 x 32 KB] ... [layer 1: 4 x 32 KB][layer 0: 16 KB]
@@ -120,7 +121,8 @@ struct DgradParams {
   long long P, T;            // points, tiles
   int L;
   const uint8_t* wt;         // W^T images
-  const uint8_t* g;          // [L][g_stride tiles][32768]: layer l of this call's tiles starts at g + l * g_stride * 32768
+  const uint8_t* g;          // [L][g_stride tiles][g_tile_bytes]: layer l of this call's tiles starts at g + l * g_stride * g_tile_bytes
+  int g_bits;                // 16 (fp16) or 8 (codes round(127 cos) + 128)
   long long g_stride;        // >= T (a dump that holds more tiles than this call processes, e.g. all items of a batch)
   uint8_t* dz;               // [L][T][65536] tile images (bf16), written
   float* d_feat;             // [P, 32]
@@ -130,7 +132,7 @@ struct DgradParams {
   float* res_scratch;        // per CTA and slot [64 column quads][128 rows] float4
 };
 
-template <bool kRes>
+template <bool kRes, bool kG8>
 __global__ void __launch_bounds__(kThreadsB, 1) film_siren_dgrad_kernel(DgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t s_base = smem_u32(smem);
@@ -280,11 +282,17 @@ __global__ void __launch_bounds__(kThreadsB, 1) film_siren_dgrad_kernel(DgradPar
       mbar_arrive(act_ready(x));
       for (int s = 0; s < L; ++s) {
         const int l = L - 1 - s;                                           // this epilogue forms dz_l from dy_l (accumulator) and g_l
-        const uint4* gt = reinterpret_cast<const uint4*>(p.g + (static_cast<size_t>(l) * p.g_stride + t) * kGTileBytes);
-        uint4 ga[2], gb[2];
-        auto load_g = [&](uint4 (&gg)[2], int cc) {
+        constexpr bool g8 = kG8;
+        const uint4* gt = reinterpret_cast<const uint4*>(p.g + (static_cast<size_t>(l) * p.g_stride + t) * g_tile_bytes(g8 ? 8 : 16));
+        uint4 ga[4], gb[4];
+        auto load_g = [&](uint4 (&gg)[4], int cc) {
+          if constexpr (g8) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) gg[h] = ld_global_evict_first(gt + ((cc * 4 + q) * 2 + h) * 32 + lane);
+            for (int h = 0; h < 2; ++h) gg[h] = ld_global_evict_first(gt + ((cc * 4 + q) * 2 + h) * 32 + lane);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) gg[i] = ld_global_evict_first(gt + ((cc * 4 + q) * 4 + i) * 32 + lane);
+          }
         };
         load_g(ga, 4 * half);
         mbar_wait(acc_full(x), acc_phase);
@@ -293,7 +301,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) film_siren_dgrad_kernel(DgradPar
         tile_free();
         float4* rsd = nullptr;
         if constexpr (kRes) rsd = reinterpret_cast<float4*>(p.res_scratch) + (static_cast<size_t>(blockIdx.x) * 2 + x) * (kHID / 4) * kTileM;
-        auto finish_block = [&](const uint4 (&gg)[2], int cc) {
+        auto finish_block = [&](const uint4 (&gg)[4], int cc) {
           uint32_t v[32];
           CNG_TMEM_LD_32(t_lane + cc * 32, v);
           tmem_ld_wait();
@@ -314,16 +322,22 @@ __global__ void __launch_bounds__(kThreadsB, 1) film_siren_dgrad_kernel(DgradPar
           float dzv[32];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            // columns 8 i .. 8 i + 7 of the block: two words of 8-bit codes u = round(127 cos) + 128.  A code is placed in mantissa
-            // bits 8..15 of 1.0f (one PRMT: 1 + u 2^-15) and scaled back with one FMA: (f - 1 - 2^-8) 2^15 / 127 = (u - 128) / 127
-            const uint32_t gw[2] = {(i & 1) ? gg[i >> 1].z : gg[i >> 1].x, (i & 1) ? gg[i >> 1].w : gg[i >> 1].y};
+            // columns 8 i .. 8 i + 7 of the block.  fp16: the four words of piece i.  8-bit: two words of codes u = round(127 cos) + 128;
+            // a code is placed in mantissa bits 8..15 of 1.0f (one PRMT: 1 + u 2^-15) and scaled back with one FMA:
+            // (f - 1 - 2^-8) 2^15 / 127 = (u - 128) / 127
+            const uint32_t gw16[4] = {gg[i].x, gg[i].y, gg[i].z, gg[i].w};
+            const uint32_t gw8[2] = {(i & 1) ? gg[i >> 1].z : gg[i >> 1].x, (i & 1) ? gg[i >> 1].w : gg[i >> 1].y};
             constexpr float kGs = 32768.f / 127.f, kGo = -(1.f + 1.f / 256.f) * (32768.f / 127.f);
             uint32_t o[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float2 gf;
-              gf.x = fmaf(__uint_as_float(__byte_perm(gw[j >> 1], 0x3F800000u, (j & 1) ? 0x7624 : 0x7604)), kGs, kGo);
-              gf.y = fmaf(__uint_as_float(__byte_perm(gw[j >> 1], 0x3F800000u, (j & 1) ? 0x7634 : 0x7614)), kGs, kGo);
+              if constexpr (g8) {
+                gf.x = fmaf(__uint_as_float(__byte_perm(gw8[j >> 1], 0x3F800000u, (j & 1) ? 0x7624 : 0x7604)), kGs, kGo);
+                gf.y = fmaf(__uint_as_float(__byte_perm(gw8[j >> 1], 0x3F800000u, (j & 1) ? 0x7634 : 0x7614)), kGs, kGo);
+              } else {
+                gf = __half22float2(*reinterpret_cast<const __half2*>(&gw16[j]));
+              }
               const float a = __uint_as_float(v[8 * i + 2 * j]) * gf.x, b = __uint_as_float(v[8 * i + 2 * j + 1]) * gf.y;
               dzv[8 * i + 2 * j] = a; dzv[8 * i + 2 * j + 1] = b;
               o[j] = pack2<false>(a, b);
@@ -679,7 +693,7 @@ static Layout layout(long long P, int L) {
   l.fold = off; off += up(film_siren_tc_workspace(1, L));
   l.wt = off; off += up(wt_image_bytes(L));
   l.xs = off; off += up(static_cast<size_t>(L) * T * kTileImageBytes);
-  l.gs = off; off += up(static_cast<size_t>(L) * T * kGTileBytes);
+  l.gs = off; off += up(static_cast<size_t>(L) * T * g_tile_bytes(16));      // sized for the larger format
   l.dzs = off; off += up(static_cast<size_t>(L) * T * kTileImageBytes);
   l.feat = off; off += up(T * kFeatImageBytes);
   l.out = off; off += up(static_cast<size_t>(P) * 16);
@@ -699,13 +713,13 @@ static int set_smem(const void* fn, uint32_t bytes, bool (&cache)[64], const cha
 }
 
 int dgrad_launch(const DgradParams& p, cudaStream_t st) {
-  static bool c0[64] = {}, c1[64] = {};
-  const bool res = (p.res_save_mask | p.res_add_mask) != 0;
-  if (res) { if (int e = set_smem(reinterpret_cast<const void*>(film_siren_dgrad_kernel<true>), kSmemTotal_B, c1, "film_siren_dgrad")) return e; }
-  else { if (int e = set_smem(reinterpret_cast<const void*>(film_siren_dgrad_kernel<false>), kSmemTotal_B, c0, "film_siren_dgrad")) return e; }
+  static bool cached[4][64] = {};
+  const bool res = (p.res_save_mask | p.res_add_mask) != 0, g8 = p.g_bits == 8;
+  void (*fn)(DgradParams) = res ? (g8 ? film_siren_dgrad_kernel<true, true> : film_siren_dgrad_kernel<true, false>)
+                                : (g8 ? film_siren_dgrad_kernel<false, true> : film_siren_dgrad_kernel<false, false>);
+  if (int e = set_smem(reinterpret_cast<const void*>(fn), kSmemTotal_B, cached[(res ? 2 : 0) + (g8 ? 1 : 0)], "film_siren_dgrad")) return e;
   const unsigned grid = static_cast<unsigned>(min(static_cast<long long>(sm_count()), p.T));
-  if (res) film_siren_dgrad_kernel<true><<<grid, kThreadsB, kSmemTotal_B, st>>>(p);
-  else film_siren_dgrad_kernel<false><<<grid, kThreadsB, kSmemTotal_B, st>>>(p);
+  fn<<<grid, kThreadsB, kSmemTotal_B, st>>>(p);
   return check_launch("cng_film_siren_dgrad");
 }
 
@@ -726,6 +740,8 @@ size_t cng_film_siren_bwd_workspace_bytes(long long P, int C, int HID, int L) {
   if (P <= 0 || C != 32 || HID != 256 || L < 1 || L > 16) return 0;
   return cng::bwdtc::layout(P, L).total;
 }
+
+int cng_film_siren_g_dump_bits(void) { return cng::film_siren_g_dump_bits(); }
 
 size_t cng_film_siren_wt_image_bytes(int L) { return (L < 1 || L > 16) ? 0 : cng::bwdtc::wt_image_bytes(L); }
 
@@ -782,6 +798,7 @@ int cng_film_siren_dgrad(const float* d_out, const float* out, int sigmoid_rgb, 
   DgradParams dp{};
   dp.d_out = d_out; dp.out = out; dp.sigmoid_rgb = sigmoid_rgb; dp.P = P; dp.T = (P + kTileM - 1) / kTileM; dp.L = L;
   dp.wt = static_cast<const uint8_t*>(wt_images); dp.g = static_cast<const uint8_t*>(g_dump); dp.dz = static_cast<uint8_t*>(dz_dump);
+  dp.g_bits = film_siren_g_dump_bits();
   dp.g_stride = g_layer_stride_tiles > 0 ? g_layer_stride_tiles : dp.T;
   CNG_REQUIRE(dp.g_stride >= dp.T, CNG_ERR_INVALID_ARGUMENT, "film_siren_dgrad: g_layer_stride_tiles %lld < %lld tiles", dp.g_stride, dp.T);
   dp.d_feat = d_feat; dp.d_final_b = d_final_b_acc;

@@ -92,6 +92,15 @@ struct GatherSource {
   const float* points;           // [B, N, 3]
 };
 
+static int g_dump_bits_override = 0;   // debug hook / tests: cng_internal_set_g_dump_bits
+int film_siren_g_dump_bits() {
+  if (g_dump_bits_override) return g_dump_bits_override;
+  static const int bits = [] {
+    const char* e = getenv("CNG_G_DUMP_BITS");
+    return (e && atoi(e) == 8) ? 8 : 16;
+  }();
+  return bits;
+}
 static long long* g_tc_trace = nullptr;   // debug hook, see cng_internal_set_tc_trace
 static int g_tc_version = 0;              // 0: CNG_TC_V / default; 1 or 3: forced (cng_internal_set_tc_version, tests and A/B tools)
 
@@ -173,7 +182,7 @@ __global__ void __launch_bounds__(256) film_fold_kernel(FoldParams p) {
 // two strictly alternate: the tensor pipe runs back to back ("what the K2 numbers taught").
 // kRes: residual blocks (res_save_mask / res_add_mask of TcParams).  A separate instantiation: merely having the branch in the
 // epilogue costs the plain networks 4-5 % (same-box A/B, 2.95 vs 2.81 ms).
-template <int kPolyOneIn, bool kHalf, bool kTrain = false, bool kShared = false, bool kRes = false, bool kGather = false>
+template <int kPolyOneIn, bool kHalf, bool kTrain = false, bool kShared = false, bool kRes = false, bool kGather = false, bool kG8 = false>
 __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams p) {
   static_assert(!(kShared && kRes), "residual blocks run on the slot-bound epilogue");
   static_assert(!kGather || (!kTrain && !kShared && !kRes), "the fused gather is an inference path of the slot-bound kernel");
@@ -560,11 +569,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
           }
           if constexpr (kTrain) {
             // sin -> next layer's operand (shared memory A tile; the whole tile leaves as one bulk store after the layer);
-            // cos -> 8 bits, u = round(127 cos) + 128 (the kernel is bound by its HBM writes: with cos as fp16, 512 B per point and
-            // layer, it took 1.80 ms per 1 M points; |error| <= 1/254 here is the size of the bf16 rounding dz gets anyway),
-            // stored straight from registers in the epilogue's own order: [cc][q][h][lane] x 16 B (h = columns 16 h .. 16 h + 15 of
-            // the block), 512 contiguous bytes per warp and store instruction.  The dgrad kernel reads it back with the same mapping.
-            uint4* gt = reinterpret_cast<uint4*>(p.dump_g + (static_cast<size_t>(l) * p.total_tiles + t) * (kTileM * kHID));
+            // cos -> HBM straight from registers in the epilogue's own order, 512 contiguous bytes per warp and store instruction;
+            // the dgrad kernel reads it back with the same mapping.  Two formats (kG8; as a run-time branch the pair cost both 10 %):
+            //   16: fp16, [cc][q][i][lane] x 16 B -- 512 B per point and layer;
+            //    8: u = round(127 cos) + 128, [cc][q][h][lane] x 16 B (h = columns 16 h .. 16 h + 15 of the block) -- 256 B per point
+            //       and layer: the kernel is bound by its HBM writes (1.80 -> 1.66 ms per 1 M points), at the price of a
+            //       quantisation error of <= 1/254 per element
+            constexpr bool g8 = kG8;
+            uint4* gt = reinterpret_cast<uint4*>(p.dump_g + (static_cast<size_t>(l) * p.total_tiles + t) * (g8 ? kTileM * kHID : kTileM * kHID * 2));
             uint8_t* blk = smem + a_base + (cc >> 1) * kABlockBytes + row * 128;
             uint32_t gs[8];
 #pragma unroll
@@ -576,16 +588,23 @@ __global__ void __launch_bounds__(kNumThreads, 1) film_siren_tc_kernel(TcParams 
                 film_sincos<kPolyOneIn>(__uint_as_float(v[8 * i + j]), 8 * i + j, s0, c0);
                 film_sincos<kPolyOneIn>(__uint_as_float(v[8 * i + j + 1]), 8 * i + j + 1, s1, c1);
                 xo[j / 2] = pack2<kHalf>(s0, s1);                  // next layer's tensor-core operand == the x dump
-                // low byte of (127 c + 1.5 * 2^23 + 128) = round(127 c) + 128
-                gq[j / 2] = __byte_perm(__float_as_uint(fmaf(c0, 127.f, 12583040.f)), __float_as_uint(fmaf(c1, 127.f, 12583040.f)), 0x0040);
+                // 8 bits: the low byte of (127 c + 1.5 * 2^23 + 128) = round(127 c) + 128
+                gq[j / 2] = g8 ? __byte_perm(__float_as_uint(fmaf(c0, 127.f, 12583040.f)), __float_as_uint(fmaf(c1, 127.f, 12583040.f)), 0x0040)
+                               : pack2<true>(c0, c1);
               }
               const int chunk = ((cc & 1) * 4 + i) ^ (row & 7);
               *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(xo[0], xo[1], xo[2], xo[3]);
-              gs[2 * i] = __byte_perm(gq[0], gq[1], 0x5410);
-              gs[2 * i + 1] = __byte_perm(gq[2], gq[3], 0x5410);
+              if constexpr (g8) {
+                gs[2 * i] = __byte_perm(gq[0], gq[1], 0x5410);
+                gs[2 * i + 1] = __byte_perm(gq[2], gq[3], 0x5410);
+              } else {
+                st_global_evict_first(gt + ((cc * 4 + q) * 4 + i) * 32 + lane, make_uint4(gq[0], gq[1], gq[2], gq[3]));
+              }
             }
-            st_global_evict_first(gt + ((cc * 4 + q) * 2 + 0) * 32 + lane, make_uint4(gs[0], gs[1], gs[2], gs[3]));
-            st_global_evict_first(gt + ((cc * 4 + q) * 2 + 1) * 32 + lane, make_uint4(gs[4], gs[5], gs[6], gs[7]));
+            if constexpr (g8) {
+              st_global_evict_first(gt + ((cc * 4 + q) * 2 + 0) * 32 + lane, make_uint4(gs[0], gs[1], gs[2], gs[3]));
+              st_global_evict_first(gt + ((cc * 4 + q) * 2 + 1) * 32 + lane, make_uint4(gs[4], gs[5], gs[6], gs[7]));
+            }
             return;
           }
           // 32 columns = 64 bytes = 4 x 16-byte chunks of K-block cc/2, logical chunk (cc&1)*4 + i
@@ -733,6 +752,7 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
   TcParams p{};
   p.half_operands = half_operands;
   p.dump_x = static_cast<uint8_t*>(dump_x); p.dump_g = static_cast<uint8_t*>(dump_g); p.dump_feat = static_cast<uint8_t*>(dump_feat);
+  p.g_bits = film_siren_g_dump_bits();
   CNG_REQUIRE((dump_x == nullptr) == (dump_g == nullptr) && (dump_x == nullptr) == (dump_feat == nullptr), CNG_ERR_INVALID_ARGUMENT,
               "film_siren_fwd_train: the x, g and feature dumps go together");
   CNG_REQUIRE(((reinterpret_cast<uintptr_t>(dump_x) | reinterpret_cast<uintptr_t>(dump_g) | reinterpret_cast<uintptr_t>(dump_feat)) & 15) == 0,
@@ -783,18 +803,20 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
   using KernelFn = void (*)(TcParams);
   const int pl = (poly == 0 || poly == 4) ? poly : 8;          // shared mode and fp16 come in these three flavours
   const bool res = (res_save_mask | res_add_mask) != 0;
-  // share of the (sin, cos) pairs of the training-mode epilogue evaluated on the FMA pipe (it needs two MUFU ops per element otherwise)
+  // share of the (sin, cos) pairs of the training-mode epilogue evaluated on the FMA pipe (it needs two MUFU ops per element otherwise):
+  // one in four (default) or none (CNG_TC_TRAIN_POLY=0); and the format of the cos dump (film_siren_g_dump_bits)
   static const int train_poly = [] {
     const char* e = getenv("CNG_TC_TRAIN_POLY");
-    const int v = e ? atoi(e) : kDefaultTrainPolyOneIn;
-    return (v == 0 || v == 2 || v == 3 || v == 4) ? v : kDefaultTrainPolyOneIn;
+    return (e && atoi(e) == 0) ? 0 : kDefaultTrainPolyOneIn;
   }();
-  const KernelFn train_fn = half_operands ? (train_poly == 0 ? film_siren_tc_kernel<0, true, true> : train_poly == 2 ? film_siren_tc_kernel<2, true, true>
-                                             : train_poly == 3 ? film_siren_tc_kernel<3, true, true> : film_siren_tc_kernel<4, true, true>)
-                                          : (train_poly == 0 ? film_siren_tc_kernel<0, false, true> : train_poly == 2 ? film_siren_tc_kernel<2, false, true>
-                                             : train_poly == 3 ? film_siren_tc_kernel<3, false, true> : film_siren_tc_kernel<4, false, true>);
+  const bool g8 = p.g_bits == 8;
+#define CNG_TRAIN_FN(POLY, HALF, RES) (g8 ? film_siren_tc_kernel<POLY, HALF, true, false, RES, false, true> : film_siren_tc_kernel<POLY, HALF, true, false, RES, false, false>)
+  const KernelFn train_fn = half_operands ? (train_poly == 0 ? CNG_TRAIN_FN(0, true, false) : CNG_TRAIN_FN(4, true, false))
+                                          : (train_poly == 0 ? CNG_TRAIN_FN(0, false, false) : CNG_TRAIN_FN(4, false, false));
+  const KernelFn train_res_fn = half_operands ? CNG_TRAIN_FN(0, true, true) : CNG_TRAIN_FN(0, false, true);
+#undef CNG_TRAIN_FN
   const KernelFn fn = gather ? (half_operands ? film_siren_tc_kernel<8, true, false, false, false, true> : film_siren_tc_kernel<8, false, false, false, false, true>)
-                      : res ? (train ? (half_operands ? film_siren_tc_kernel<0, true, true, false, true> : film_siren_tc_kernel<0, false, true, false, true>)
+                      : res ? (train ? train_res_fn
                                    : half_operands ? film_siren_tc_kernel<8, true, false, false, true> : film_siren_tc_kernel<8, false, false, false, true>)
                       : train ? train_fn
                       : shared ? (half_operands ? (pl == 0 ? shared_kernel<0, true>() : pl == 4 ? shared_kernel<4, true>() : shared_kernel<8, true>())
@@ -806,9 +828,10 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
   static bool attr_set[64][8][12] = {};
   const int variant = res ? 5 + (train ? 2 : half_operands ? 1 : 0) : train ? 2 : (half_operands ? 1 : 0) + (shared ? 3 : 0);
   const int gslot = gather ? 10 : -1;                                 // the fused-gather instantiations: variant rows 0 / 1, column 10
-  const int pslot = gslot >= 0 ? gslot : train ? (half_operands ? 0 : 5) + (res ? 0 : train_poly) : poly;   // operand formats x poly shares of the training kernel share a variant row
+  const int pslot = gslot >= 0 ? gslot : train ? 0 : poly;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = -1;
+  if (train) dev = -1;                                                // the training-mode instantiations (operand format x poly x dump format) are not cached
   if (dev < 0 || !attr_set[dev][variant][pslot]) {
     ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTotal));
     if (ce != cudaSuccess) return fail(static_cast<int>(ce), "film_siren_fwd(bf16): smem attribute: %s", cudaGetErrorString(ce));
@@ -840,6 +863,9 @@ extern "C" {
 
 // Debug hook (not part of the ABI in include/cng_b200.h): device buffer of 4*9*2*8 int64 that receives the clock64
 // timeline of CTA 0 of the next cta_group::1 launches; NULL switches it off.  Used by tools/trace_tc.py.
+// format of the cos(u) dump of the NEXT training-mode forward / dgrad calls: 8, 16, or 0 = back to CNG_G_DUMP_BITS / the default (16).
+// Switch only between complete backward passes: a dump must be read in the format it was written in.
+CNG_API void cng_internal_set_g_dump_bits(int bits) { cng::g_dump_bits_override = (bits == 8 || bits == 16) ? bits : 0; }
 CNG_API void cng_internal_set_tc_trace(void* dev_buffer) { cng::g_tc_trace = static_cast<long long*>(dev_buffer); }
 
 // Debug hook: which tcgen05 kernel serves cng_film_siren_fwd -- 1 / 2 the two-tile ping-pong kernel (this file) with slot-bound /

@@ -317,13 +317,15 @@ struct TcParams {
   //   dump_x  [L][T][64 KB]  the layer output x_{l+1} = sin(u_l) as the 128-point operand TILE IMAGE the next layer's MMA reads
   //           ([4 K-blocks][128 rows][64 x 16 bit], 128B-swizzled, operand format) -- one bulk store per tile-layer; the
   //           weight-gradient kernel (film_siren_bwd_tc.cu) reads it back with MN-major descriptors
-  //   dump_g  [L][T][32 KB]  the local derivative g_l = cos(u_l) as 8-bit codes round(127 cos) + 128 (the FiLM frequency is folded
-  //           into the backward's weight images instead), in the epilogue's own register order
-  //           [32-column block cc][lane quarter q][16-column half h][lane] x 16 B: every store / load is 512 contiguous bytes per warp
+  //   dump_g  [L][T][64 KB | 32 KB]  the local derivative g_l = cos(u_l) (the FiLM frequency is folded into the backward's weight
+  //           images instead) in the epilogue's own register order -- every store / load is 512 contiguous bytes per warp -- as
+  //           fp16, [32-column block cc][lane quarter q][16-byte piece i][lane], or, with g_bits == 8, as codes round(127 cos) + 128,
+  //           [cc][q][16-column half h][lane] x 16 B (cng_film_siren_g_dump_bits)
   //   dump_feat [T][16 KB]   the layer-0 operand block [x_hi(32) | x_lo(32)]
   uint8_t* dump_x;
   uint8_t* dump_g;
   uint8_t* dump_feat;
+  int g_bits;               // format of dump_g: 16 = fp16 (64 KB per tile-layer, [cc][q][i][lane] x 16 B), 8 = codes (32 KB, [cc][q][h][lane] x 16 B)
   long long* trace;         // debug: clock64 timeline of CTA 0 (tools/trace_tc.py), NULL in production
   // residual blocks (TALLSIREN_dRes, generators/siren.py:218-230): bit l of res_save_mask = layer l's output is kept as the
   // residual, bit l of res_add_mask = the kept residual is added to layer l's pre-activation.  res_scratch: per CTA and
@@ -357,6 +359,9 @@ __device__ __forceinline__ TileInfo tile_info(const TcParams& p, long long t) {
   ti.rows = static_cast<int>(min(static_cast<long long>(kTileM), p.N - ti.n0));
   return ti;
 }
+
+// format of the cos(u) dump shared by the training-mode forward and the dgrad chain (16 or 8 bits per element): film_siren_tc.cu
+int film_siren_g_dump_bits();
 
 // kPolyOneIn: 0 = every sine on the MUFU unit; n > 0 = one element in n uses sin_fma instead
 

@@ -7,7 +7,7 @@ The forward kernels stay the no-grad ones (K1, K2, K3', nothing saved per layer)
     _Gather*          d feat -> d volume (scatter-add)               cng_scatter_points
     _FilmSiren        d rgb_sigma -> d feat, d W/b, d freq/phase     cng_film_siren_bwd per chunk: activations
                       recomputed by the training-mode K2 (the fused tcgen05 forward that also writes
-                      x_{l+1} tile images and g_l = cos(u_l) as 8-bit codes), then the tcgen05 dgrad chain
+                      x_{l+1} tile images and g_l = cos(u_l)), then the tcgen05 dgrad chain
                       (dz = dy*g formed in its epilogue) and the tcgen05 split-K weight gradient --
                       no library GEMM (csrc/film_siren_bwd_tc.cu)
     _MergeComposite   d pixels, d depth -> d rgb_sigma (fine, coarse)  cng_merge_composite_bwd
@@ -28,7 +28,7 @@ from .volumetric_rendering import camera_tables
 import os
 
 HAS_BACKWARD = True
-CHUNK_ROWS = 1 << 20          # points per recompute chunk of the MLP backward (~11 GB of x / g / dz dumps at L = 8)
+CHUNK_ROWS = 1 << 20          # points per recompute chunk of the MLP backward (~13 GB of x / g / dz dumps at L = 8)
 # "auto": when the x / g dumps of the WHOLE batch fit comfortably in free device memory (small per-GPU batches: the 8-GPU
 # operating point), the forward of a training step runs the training-mode kernel once and keeps its dumps for the backward,
 # which then skips the recompute; otherwise (and with "0") the forward keeps nothing and the backward recomputes per chunk.
@@ -44,13 +44,13 @@ class _DumpBuffers:
     _pool = {}
 
     def __init__(self, L: int, tiles: int, dev):
-        self.key = (dev.index if dev.index is not None else torch.cuda.current_device(), L, tiles)
+        self.key = (dev.index if dev.index is not None else torch.cuda.current_device(), L, tiles, ops.g_image_bytes())
         free = self._pool.setdefault(self.key, [])
         if free:
             self.tensors = free.pop()
         else:
             self.tensors = (torch.empty((L, tiles, ops.TILE_IMAGE_BYTES), dtype=torch.uint8, device=dev),
-                            torch.empty((L, tiles, ops.G_IMAGE_BYTES), dtype=torch.uint8, device=dev),
+                            torch.empty((L, tiles, ops.g_image_bytes()), dtype=torch.uint8, device=dev),
                             torch.empty((tiles, ops.FEAT_IMAGE_BYTES), dtype=torch.uint8, device=dev))
 
     def release(self) -> None:
@@ -76,9 +76,9 @@ def _keep_dumps(B: int, N: int, L: int, dev) -> bool:
     if KEEP_DUMPS == "1":
         return True
     tiles = B * ((N + ops.TILE_POINTS - 1) // ops.TILE_POINTS)
-    need = L * tiles * (ops.TILE_IMAGE_BYTES + ops.G_IMAGE_BYTES) + tiles * ops.FEAT_IMAGE_BYTES
+    need = L * tiles * (ops.TILE_IMAGE_BYTES + ops.g_image_bytes()) + tiles * ops.FEAT_IMAGE_BYTES
     need += L * ((N + ops.TILE_POINTS - 1) // ops.TILE_POINTS) * ops.TILE_IMAGE_BYTES      # one item's dz dump at backward time
-    if _DumpBuffers._pool.get((dev.index if dev.index is not None else torch.cuda.current_device(), L, tiles)):
+    if _DumpBuffers._pool.get((dev.index if dev.index is not None else torch.cuda.current_device(), L, tiles, ops.g_image_bytes())):
         return True                                   # a pooled buffer of this shape is waiting: no new memory needed
     free, _ = torch.cuda.mem_get_info(dev)
     cached = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)

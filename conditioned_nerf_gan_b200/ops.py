@@ -460,14 +460,20 @@ def volume_from_channels_last(vol_cl: torch.Tensor) -> torch.Tensor:
 
 TILE_POINTS = 128            # points per operand tile of the tcgen05 kernels
 TILE_IMAGE_BYTES = 65536     # one tile-layer of x / dz (include/cng_b200.h, "Dump formats")
-G_IMAGE_BYTES = 32768        # one tile-layer of g = cos(u) as 8-bit codes
+
+
+def g_image_bytes() -> int:
+    """Bytes of one tile-layer of the cos(u) dump in the library's current format (cng_film_siren_g_dump_bits: fp16 -> 65536,
+    8-bit codes -> 32768)."""
+    return TILE_POINTS * 256 * int(_lib.load().cng_film_siren_g_dump_bits()) // 8
+
 FEAT_IMAGE_BYTES = 16384
 
 
 def film_siren_fwd_train(feat, layer_w, layer_b, freq, phase, final_w, final_b, sigmoid_rgb: bool, precision: str = "fp16",
                          res_save_mask: int = 0, res_add_mask: int = 0, dumps=None):
     """Training-mode K2 (the backward's recompute): rgb_sigma [B,N,4] plus the dumps in the formats of include/cng_b200.h --
-    x [L,T,65536] uint8 (operand tile images), g = cos(u) [L,T,32768] uint8 (8-bit codes, epilogue order), feat [T,16384] uint8 -- with
+    x [L,T,65536] uint8 (operand tile images), g = cos(u) [L,T,g_image_bytes()] uint8 (fp16 or 8-bit codes, epilogue order), feat [T,16384] uint8 -- with
     T = B * ceil(N / 128)."""
     if precision not in ("bf16", "fp16"):
         raise ValueError("film_siren_fwd_train: precision must be 'bf16' or 'fp16'")
@@ -484,11 +490,11 @@ def film_siren_fwd_train(feat, layer_w, layer_b, freq, phase, final_w, final_b, 
     out = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
     if dumps is not None:                      # caller-owned (pooled) dump buffers of exactly this shape
         xs, gs, fd = dumps
-        if xs.shape != (L, T, TILE_IMAGE_BYTES) or gs.shape != (L, T, G_IMAGE_BYTES) or fd.shape != (T, FEAT_IMAGE_BYTES):
+        if xs.shape != (L, T, TILE_IMAGE_BYTES) or gs.shape != (L, T, g_image_bytes()) or fd.shape != (T, FEAT_IMAGE_BYTES):
             raise ValueError("film_siren_fwd_train: dump buffers of the wrong shape")
     else:
         xs = torch.empty((L, T, TILE_IMAGE_BYTES), dtype=torch.uint8, device=dev)
-        gs = torch.empty((L, T, G_IMAGE_BYTES), dtype=torch.uint8, device=dev)
+        gs = torch.empty((L, T, g_image_bytes()), dtype=torch.uint8, device=dev)
         fd = torch.empty((T, FEAT_IMAGE_BYTES), dtype=torch.uint8, device=dev)
     w_arr = (ctypes.c_void_p * L)(*[w.data_ptr() for w in ws])
     b_arr = (ctypes.c_void_p * L)(*[b.data_ptr() for b in bs])
@@ -529,10 +535,10 @@ def _tile_ptr(dump: torch.Tensor, layer: int, tile: int, stride_tiles: int):
 def film_siren_dgrad(d_out, out, sigmoid_rgb: bool, L: int, wt_images, g_dump, d_final_b_acc, res_save_mask: int = 0, res_add_mask: int = 0,
                      tile_offset: int = 0, d_feat=None):
     """The fused dgrad chain (cng_film_siren_dgrad): d_out / out [P,4] -> (d_feat [P,32], dz tile images [L,T,65536] uint8);
-    accumulates the head bias gradient into d_final_b_acc [4].  ``g_dump`` [L, T_total, 32768]: this call reads tiles
+    accumulates the head bias gradient into d_final_b_acc [4].  ``g_dump`` [L, T_total, g_image_bytes()]: this call reads tiles
     [tile_offset, tile_offset + T) of every layer (a batch's dumps consumed item by item)."""
-    if g_dump.dim() != 3 or g_dump.shape[2] != G_IMAGE_BYTES:
-        raise ValueError("film_siren_dgrad: g_dump must be [L, T, 32768] uint8")
+    if g_dump.dim() != 3 or g_dump.shape[2] != g_image_bytes():
+        raise ValueError(f"film_siren_dgrad: g_dump must be [L, T, {g_image_bytes()}] uint8 (cng_film_siren_g_dump_bits)")
     d_out = _f32(d_out, "d_out")
     P = d_out.shape[0]
     out = _f32(out, "out") if out is not None else None

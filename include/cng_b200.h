@@ -290,9 +290,14 @@ CNG_API int cng_render_fwd(const float* vol_ndhwc, long long vol_item_stride, in
  *   x_dump    [L][T][65536]  output of layer l, x_{l+1} = sin(u_l), as 128-point operand tile images
  *                            ([4 K-blocks of 64 columns][128 rows][128 B], 128-byte swizzle: element (row, k) of a block at
  *                            row*128 + (((k>>3) ^ (row&7)) << 4) + (k&7)*2), in the operand format of `precision`
- *   g_dump    [L][T][32768]  g_l = cos(u_l) as 8-bit codes round(127 g) + 128 (|error| <= 1/254, the size of the bf16 rounding of
- *                            dz; as fp16 the dump made the training forward write-bound), [32-column block cc 8][row quarter q 4]
- *                            [half h 2][lane 32] x 16 B: row = 32 q + lane, byte e = column 32 cc + 16 h + e.
+ *   g_dump    [L][T][G]      g_l = cos(u_l) in the epilogue's register order (row = 32 q + lane), G = 128 * 256 * bits / 8 bytes with
+ *                            bits = cng_film_siren_g_dump_bits():
+ *                              16 (default): fp16, [32-column block cc 8][row quarter q 4][piece i 4][lane 32] x 16 B, columns
+ *                                  32 cc + 8 i .. + 7 (G = 65536);
+ *                               8 (CNG_G_DUMP_BITS=8): codes round(127 g) + 128, [cc 8][q 4][half h 2][lane 32] x 16 B, byte e = column
+ *                                  32 cc + 16 h + e (G = 32768).  Halves the dump's traffic (the training forward is bound by its
+ *                                  HBM writes: MLP backward 4.9 -> 4.5 ms per 1 M points) for a quantisation error <= 1/254 per
+ *                                  element: gradients of the 16 x 16 test scenes move from 0.9 % to 1.2 % relative L2.
  *                            The FiLM frequency is not applied elementwise:
  *                            with dz'_l = dy_l * cos(u_l) the chain is dy_{l-1} = dz'_l (diag(freq_l) W_l) and
  *                            dW_l = diag(freq_l) dz'_l^T x_l, db_l = freq_l * colsum(dz'_l), dphase_l = colsum(dz'_l),
@@ -301,7 +306,7 @@ CNG_API int cng_render_fwd(const float* vol_ndhwc, long long vol_item_stride, in
  *   dz_dump   [L][T][65536]  dz'_l = dy_l * g_l as bf16 tile images (written by the dgrad chain, read by the weight gradient)
  * ---------------------------------------------------------------------------------------- */
 /* Training-mode forward of K2 (the backward's activation recompute): the fused tcgen05 kernel of cng_film_siren_fwd(_res) that
- * ALSO writes the three dumps above (one bulk store per tile-layer for x, two 16-byte register stores per thread and 32-column block for g).  `precision`:
+ * ALSO writes the three dumps above (one bulk store per tile-layer for x, 16-byte register stores in the epilogue's order for g).  `precision`:
  * CNG_PREC_BF16 or CNG_PREC_FP16 (operand format of the recompute and of x_dump).  With B > 1 the tile index runs over items:
  * T = B * ceil(N / 128).  Residual masks / scratch as in cng_film_siren_fwd_res (0 / NULL for plain networks); g_l is then the
  * derivative at the pre-activation INCLUDING the re-added block input. */
@@ -315,6 +320,9 @@ CNG_API int cng_film_siren_fwd_train(const float* feat, int B, long long N, int 
 /* Operand images (bf16) of (diag(freq_l) W_l)^T and of the head for the dgrad chain.  freq [L*HID] of the item, or NULL for
  * plain W_l.  `images`: cng_film_siren_wt_image_bytes(L) bytes, 16-byte aligned. */
 CNG_API size_t cng_film_siren_wt_image_bytes(int L);
+/* Bits per element of g_dump (16 or 8, see "Dump formats"): process-wide, read by cng_film_siren_fwd_train, cng_film_siren_dgrad
+ * and cng_film_siren_bwd at call time; a dump must be consumed in the format it was written in. */
+CNG_API int cng_film_siren_g_dump_bits(void);
 CNG_API int cng_film_siren_wt_images(const float* const* layer_w_host, const float* freq, const float* final_w, int C,
                              int HID, int L, void* images, cng_stream_t stream);
 /* The dgrad chain of P points, all layers fused per 128-point tile (gradients stay in TMEM / shared memory between layers):

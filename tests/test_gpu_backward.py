@@ -125,21 +125,48 @@ def g_codes(g):
     return (torch.round(g.float() * 127.0) + 128).to(torch.uint8)
 
 
-def to_g_images(g):
-    """[P, 256] float -> uint8 [T, 32768]: 8-bit codes in the epilogue's register order [cc 8][q 4][h 2][lane 32][16]."""
+def g_dequant(g, bits):
+    """The value the dgrad chain multiplies with: fp16 rounding of cos, or (code - 128) / 127."""
+    return g.to(torch.float16).double() if bits == 16 else (g_codes(g).double() - 128) / 127
+
+
+def to_g_images(g, bits):
+    """[P, 256] float -> uint8 [T, 128 * 256 * bits / 8] in the epilogue's register order: fp16 [cc 8][q 4][i 4][lane 32][8], or
+    8-bit codes [cc 8][q 4][h 2][lane 32][16]."""
     P = g.shape[0]
     T = (P + 127) // 128
+    if bits == 16:
+        gp = torch.zeros((T * 128, 256), dtype=torch.float32)
+        gp[:P] = g
+        v = gp.to(torch.float16).view(T, 4, 32, 8, 4, 8)                 # [tile, q, lane, cc, i, e]
+        return v.permute(0, 3, 1, 4, 2, 5).contiguous().view(torch.uint8).reshape(T, 65536)
     gp = torch.full((T * 128, 256), 128, dtype=torch.uint8)
     gp[:P] = g_codes(g)
     v = gp.view(T, 4, 32, 8, 2, 16)                                      # [tile, q, lane, cc, h, e]
     return v.permute(0, 3, 1, 4, 2, 5).contiguous().reshape(T, 32768)
 
 
-def from_g_images(img, P):
-    """uint8 [T, 32768] -> [P, 256] float, (code - 128) / 127."""
+def from_g_images(img, P, bits):
+    """uint8 [T, G] -> [P, 256] float."""
     T = img.shape[0]
+    if bits == 16:
+        v = img.cpu().contiguous().view(torch.float16).view(T, 8, 4, 4, 32, 8)       # [tile, cc, q, i, lane, e]
+        return v.permute(0, 2, 4, 1, 3, 5).reshape(T * 128, 256)[:P].float()
     v = img.cpu().contiguous().view(T, 8, 4, 2, 32, 16)                  # [tile, cc, q, h, lane, e]
     return (v.permute(0, 2, 4, 1, 3, 5).reshape(T * 128, 256)[:P].float() - 128) / 127
+
+
+@pytest.fixture(params=[16, 8])
+def g_bits(request):
+    """Runs a test in both formats of the cos(u) dump (cng_internal_set_g_dump_bits; 16 is the default)."""
+    import ctypes
+    from conditioned_nerf_gan_b200 import _lib
+    lib = _lib.load()
+    lib.cng_internal_set_g_dump_bits.argtypes = [ctypes.c_int]
+    lib.cng_internal_set_g_dump_bits.restype = None
+    lib.cng_internal_set_g_dump_bits(request.param)
+    yield request.param
+    lib.cng_internal_set_g_dump_bits(0)
 
 
 @pytest.mark.parametrize("x_dtype", [torch.float16, torch.bfloat16])
@@ -174,8 +201,8 @@ def test_wgrad_kernel_vs_torch(ops, x_dtype, P, L):
 
 
 @pytest.mark.parametrize("P,L,sig", [(1000, 3, True), (128, 1, False), (128 * 301 + 5, 2, True), (77, 8, False)])
-def test_dgrad_kernel_vs_torch(ops, P, L, sig):
-    """cng_film_siren_dgrad: the fused chain d_o -> dy -> dz_l = dy * g_l -> dy = dz_l W_l ... -> d_feat on synthetic g (8-bit codes)."""
+def test_dgrad_kernel_vs_torch(ops, P, L, sig, g_bits):
+    """cng_film_siren_dgrad: the fused chain d_o -> dy -> dz_l = dy * g_l -> dy = dz_l W_l ... -> d_feat on synthetic g, in both dump formats."""
     g = torch.Generator().manual_seed(P * 3 + L)
     ws = [torch.randn((256, 32 if l == 0 else 256), generator=g) * (0.2 if l == 0 else 0.06) for l in range(L)]
     fw = torch.randn((4, 256), generator=g) * 0.1
@@ -184,7 +211,8 @@ def test_dgrad_kernel_vs_torch(ops, P, L, sig):
     d_out = torch.randn((P, 4), generator=g)
     out = torch.rand((P, 4), generator=g)
     wt = ops.film_siren_wt_images([w.cuda() for w in ws], fw.cuda())
-    g_img = torch.stack([to_g_images(x) for x in gs]).cuda()
+    assert ops.g_image_bytes() == 128 * 256 * g_bits // 8
+    g_img = torch.stack([to_g_images(x, g_bits) for x in gs]).cuda()
     d_fb = torch.zeros((4,), device="cuda")
     d_feat, dz_img = ops.film_siren_dgrad(d_out.cuda(), out.cuda(), sig, L, wt, g_img, d_fb)
     torch.cuda.synchronize()
@@ -195,7 +223,7 @@ def test_dgrad_kernel_vs_torch(ops, P, L, sig):
     assert rel_l2(d_fb.cpu(), d_o.sum(0)) < 1e-5
     dy = d_o @ bf(fw)                       # d_o enters as hi + lo (~fp32), Wf as bf16
     for l in reversed(range(L)):
-        dz = dy * ((g_codes(gs[l]).double() - 128) / 127)
+        dz = dy * g_dequant(gs[l], g_bits)
         got = from_tile_images(dz_img[l], P, torch.bfloat16)
         e = rel_l2(got, dz)
         print(f"dgrad P={P} L={L} layer {l}: dz rel-L2 {e:.2e}")
@@ -206,7 +234,7 @@ def test_dgrad_kernel_vs_torch(ops, P, L, sig):
     assert e < 6e-3 and d_feat.shape == (P, 32)
 
 
-def test_fwd_train_dumps_vs_oracle(ops):
+def test_fwd_train_dumps_vs_oracle(ops, g_bits):
     """cng_film_siren_fwd_train: x tile images, g = cos(u) and the layer-0 operand block against the oracle's activations."""
     from test_gpu_parity import _mlp_setup
     B, N = 2, 300
@@ -224,7 +252,7 @@ def test_fwd_train_dumps_vs_oracle(ops):
         for b in range(B):
             got_x = from_tile_images(xs[l, b * tpi:(b + 1) * tpi], N, torch.float16)
             assert (got_x - x[b]).abs().max().item() < 5e-2, (l, b)        # hidden activations of SHORTSIREN_FG carry the fp16-operand error of the layers before
-            got_g = from_g_images(gs[l, b * tpi:(b + 1) * tpi], N)
+            got_g = from_g_images(gs[l, b * tpi:(b + 1) * tpi], N, g_bits)
             assert (got_g - gref[b]).abs().max().item() < 0.3, (l, b, (got_g - gref[b]).abs().max().item())     # u carries the 16-bit operand error x freq ~ 30
     for b in range(B):
         f = from_tile_images(fd[b * tpi:(b + 1) * tpi], N, torch.float16, nb=1)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-kernel timing of the tcgen05 MLP backward (a14) on one chunk of points: training-mode forward (recompute with dumps),
 dgrad chain, split-K weight gradient, and the one-call cng_film_siren_bwd.  Algorithmic bytes per point and layer: recompute
-768 B written (x + 8-bit g), dgrad 768 B (g read, dz written), wgrad 1 KB (dz + x read); FLOPs per point and hidden layer 2*256^2 each.
+512 + G B written (x + g), dgrad G + 512 B (g read, dz written), wgrad 1 KB (dz + x read), G = 512 (fp16 cos, default) or 256 (CNG_G_DUMP_BITS=8); FLOPs per point and hidden layer 2*256^2 each.
     python tools/bench_bwd.py [--points 1048576] [--siren TALLSIREN_FG]"""
 import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -41,17 +41,18 @@ def timeit(fn):
 
 
 hidden_flops = 2 * 256 * 256 * (L - 1) * P
+G = ops.g_image_bytes() // 128          # bytes of cos(u) per point and layer
 rows = []
 ms = timeit(lambda: ops.film_siren_fwd(feat, ws, bs, freq, phase, fw, fb, net.sigmoid_rgb, "fp16"))
 rows.append(("inference forward (fp16 operands)", ms, None, hidden_flops))
 out, xs, gs, fd = ops.film_siren_fwd_train(feat, ws, bs, freq, phase, fw, fb, net.sigmoid_rgb, "fp16")
 ms = timeit(lambda: ops.film_siren_fwd_train(feat, ws, bs, freq, phase, fw, fb, net.sigmoid_rgb, "fp16"))
-rows.append(("training forward (recompute + dumps)", ms, P * L * 768 + P * 128 * 2, hidden_flops))
+rows.append(("training forward (recompute + dumps)", ms, P * L * (512 + G) + P * 128 * 2, hidden_flops))
 wt = ops.film_siren_wt_images(ws, fw)
 d_fb = torch.zeros(4, device=dev)
 d_feat, dz = ops.film_siren_dgrad(d_out, out[0], net.sigmoid_rgb, L, wt, gs, d_fb)
 ms = timeit(lambda: ops.film_siren_dgrad(d_out, out[0], net.sigmoid_rgb, L, wt, gs, d_fb))
-rows.append(("dgrad chain", ms, P * L * 768 + P * 160, hidden_flops))
+rows.append(("dgrad chain", ms, P * L * (512 + G) + P * 160, hidden_flops))
 dW = [torch.zeros_like(w) for w in ws]
 colsum = torch.zeros((L, 256), device=dev)
 ms = timeit(lambda: ops.film_siren_wgrad(dz, xs, fd, P, L, True, dW, colsum))
@@ -60,8 +61,8 @@ del xs, gs, fd, dz
 torch.cuda.empty_cache()
 d_fw, d_feat2 = torch.zeros_like(fw), torch.empty((P, 32), device=dev)
 ms = timeit(lambda: ops.film_siren_bwd(feat[0], d_out, ws, bs, freq[0].contiguous(), phase[0].contiguous(), fw, fb, net.sigmoid_rgb, d_feat2, dW, colsum, d_fw, d_fb))
-rows.append(("cng_film_siren_bwd (all of the above but the inference forward)", ms, P * L * (768 + 768 + 1024), 3 * hidden_flops))
-print(f"# {args.siren} L={L}, {P} points per chunk")
+rows.append(("cng_film_siren_bwd (all of the above but the inference forward)", ms, P * L * (2 * (512 + G) + 1024), 3 * hidden_flops))
+print(f"# {args.siren} L={L}, {P} points per chunk, cos dump {8 * G // 256} bits")
 for name, ms, by, fl in rows:
     gbs = f"{by / ms / 1e6:7.0f} GB/s" if by else "            "
     print(f"{name:66s} {ms:8.3f} ms  {gbs}  {fl / ms / 1e9:7.1f} TFLOP/s (hidden layers)")
