@@ -503,6 +503,7 @@ def measure_train(args, rank, world, local, dev, barrier, max_over_ranks, steps,
            "allreduce_bytes": 4 * n_param, "scaling": "strong", "final_loss": results[-1], "clocks": clocks,
            "h2d_bytes_per_step": int((voxel_h.numel() + img_h.numel() + cam_h.numel()) * 4), "d2h_bytes_per_step": 8,
            "mlp_flops_per_step": 3 * 2 * mlp_flops_per_point(L) * pts, "cos_dump_bits": _cos_dump_bits(),
+           "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2**30, "reserved_mem_gb": torch.cuda.memory_reserved(dev) / 2**30,
            "workload": "full GAN train step (3D U-Net encoder + FiLM-SIREN generator + progressive discriminator, D step with R1 then G/E step), "
                        "128x128, 48+48 samples/ray, global batch 32 (BASELINE configs[2]); autocast fp16 + GradScaler, Adam x3; "
                        "host voxels / images / cameras copied in and the losses read back every step"}

@@ -23,6 +23,7 @@ Differences that do not change the mathematics:
 from __future__ import annotations
 
 import contextlib
+import os
 from typing import Dict, Optional
 
 import torch
@@ -84,7 +85,8 @@ class GanTrainStep:
         self.curriculum = curriculum             # optional: the reference's curriculum dict; ``set_alpha`` then reads the stage start from it
         self.alpha = 1.0
         self.ddp = ddp
-        self.share_encoder_forward = True        # step(): one encoder forward serves the D step and the G/E step (see there)
+        # step(): one encoder forward serves the D step and the G/E step (see there); CNG_SHARE_ENCODER=0 restores the two passes
+        self.share_encoder_forward = os.environ.get("CNG_SHARE_ENCODER", "1") != "0"
         self._shared_z = None
         self._encoder_deterministic = None
         self.losses: Dict[str, torch.Tensor] = {}
