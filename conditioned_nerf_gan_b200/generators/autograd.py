@@ -70,19 +70,29 @@ class _DumpBuffers:
         cls._pool.clear()
 
 
-def _keep_dumps(B: int, N: int, L: int, dev) -> bool:
+def _kept_items(B: int, N: int, L: int, dev) -> int:
+    """How many of the B items run the training-mode kernel as their forward and keep its dumps for the backward (the first k; the
+    others are recomputed chunk by chunk in the backward): as many as fit in KEEP_DUMPS_MEMORY_FRACTION of the free memory --
+    all of them at the small per-GPU batches of multi-GPU training, a part of the batch at 16-32 images per GPU."""
     if KEEP_DUMPS == "0" or N > CHUNK_ROWS:
-        return False
+        return 0
     if KEEP_DUMPS == "1":
-        return True
-    tiles = B * ((N + ops.TILE_POINTS - 1) // ops.TILE_POINTS)
-    need = L * tiles * (ops.TILE_IMAGE_BYTES + ops.g_image_bytes()) + tiles * ops.FEAT_IMAGE_BYTES
-    need += L * ((N + ops.TILE_POINTS - 1) // ops.TILE_POINTS) * ops.TILE_IMAGE_BYTES      # one item's dz dump at backward time
-    if _DumpBuffers._pool.get((dev.index if dev.index is not None else torch.cuda.current_device(), L, tiles, ops.g_image_bytes())):
-        return True                                   # a pooled buffer of this shape is waiting: no new memory needed
+        return B
+    if KEEP_DUMPS.startswith("first:"):                             # tests: exactly the first k items
+        return min(B, int(KEEP_DUMPS[6:]))
+    tpi = (N + ops.TILE_POINTS - 1) // ops.TILE_POINTS
+    di = dev.index if dev.index is not None else torch.cuda.current_device()
+    # a pooled buffer of a previous step is waiting: no new memory needed (and the choice is the same every step)
+    pooled = [key[2] // tpi for key, free in _DumpBuffers._pool.items()
+              if free and key[0] == di and key[1] == L and key[3] == ops.g_image_bytes() and key[2] % tpi == 0 and 0 < key[2] // tpi <= B]
+    if pooled:
+        return max(pooled)
+    per_item = L * tpi * (ops.TILE_IMAGE_BYTES + ops.g_image_bytes()) + tpi * ops.FEAT_IMAGE_BYTES
+    dz_item = L * tpi * ops.TILE_IMAGE_BYTES                        # one item's dz dump at backward time
     free, _ = torch.cuda.mem_get_info(dev)
     cached = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
-    return need <= KEEP_DUMPS_MEMORY_FRACTION * (free + cached)
+    budget = KEEP_DUMPS_MEMORY_FRACTION * (free + cached) - dz_item
+    return int(max(0, min(B, budget // per_item)))
 
 
 class _ToChannelsLast(torch.autograd.Function):
@@ -167,13 +177,18 @@ class _FilmSiren(torch.autograd.Function):
             raise NotImplementedError(f"training needs input_dim=32 and hidden_dim=256 (got {feat.shape[-1]}, {final_w.shape[1]}): "
                                       "the MLP backward (cng_film_siren_bwd) is built for that shape")
         B, N = feat.shape[0], feat.shape[1]
-        ctx.dumps = None
-        if precision != "fp32" and _keep_dumps(B, N, L, feat.device):
-            # the training-mode kernel IS the forward (fp16 operands): its dumps stay alive until backward, no recompute there
-            tiles = B * ((N + ops.TILE_POINTS - 1) // ops.TILE_POINTS)
-            ctx.dumps = _DumpBuffers(L, tiles, feat.device)
-            out = ops.film_siren_fwd_train(feat, ws, bs, freq, phase, final_w, final_b, sigmoid_rgb, "fp16", res_save, res_add,
+        ctx.dumps, ctx.kept = None, 0
+        k = _kept_items(B, N, L, feat.device) if precision != "fp32" else 0
+        if k > 0:
+            # the training-mode kernel IS the forward of the first k items (fp16 operands): its dumps stay alive until backward,
+            # no recompute there; the other items take the inference kernel
+            ctx.kept = k
+            ctx.dumps = _DumpBuffers(L, k * ((N + ops.TILE_POINTS - 1) // ops.TILE_POINTS), feat.device)
+            out = ops.film_siren_fwd_train(feat[:k], ws, bs, freq[:k], phase[:k], final_w, final_b, sigmoid_rgb, "fp16", res_save, res_add,
                                            dumps=ctx.dumps.tensors)[0]
+            if k < B:
+                rest = ops.film_siren_fwd(feat[k:], ws, bs, freq[k:], phase[k:], final_w, final_b, sigmoid_rgb, precision, res_save, res_add)
+                out = torch.cat([out, rest], dim=0)
         else:
             out = ops.film_siren_fwd(feat, ws, bs, freq, phase, final_w, final_b, sigmoid_rgb, precision, res_save, res_add)
         ctx.save_for_backward(feat, freq, phase, final_w, final_b, out, *wb)
@@ -211,8 +226,8 @@ class _FilmSiren(torch.autograd.Function):
         tiles_per_item = (N + ops.TILE_POINTS - 1) // ops.TILE_POINTS
         for b in range(B):
             dW_item = [d[b] for d in dW_all]
-            if dumps is not None:
-                # kept dumps (one training-mode forward for the whole batch): dgrad chain, weight gradient and head per item,
+            if dumps is not None and b < ctx.kept:
+                # kept dumps (one training-mode forward for the first ctx.kept items): dgrad chain, weight gradient and head per item,
                 # each reading its own tiles of every layer
                 xs, gs, fd = dumps.tensors
                 wt = ops.film_siren_wt_images(ws, fw, fr[b])
