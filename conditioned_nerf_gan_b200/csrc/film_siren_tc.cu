@@ -910,6 +910,7 @@ int cng_film_siren_fwd_gather(const float* vol_ndhwc, long long vol_item_stride,
               "film_siren_fwd_gather: NULL pointer");
   CNG_REQUIRE(D >= 1 && H >= 1 && W >= 1 && (reinterpret_cast<uintptr_t>(vol_ndhwc) & 15) == 0, CNG_ERR_INVALID_ARGUMENT,
               "film_siren_fwd_gather: bad volume");
+  CNG_REQUIRE(static_cast<long long>(D) * H * W < (1LL << 28), CNG_ERR_UNSUPPORTED, "film_siren_fwd_gather: volume exceeds the gather's 32-bit offsets");
   CNG_REQUIRE(vol_item_stride == 0 || vol_item_stride == static_cast<long long>(C) * D * H * W, CNG_ERR_INVALID_ARGUMENT,
               "film_siren_fwd_gather: vol_item_stride must be 0 (shared volume) or C*D*H*W");
   CNG_REQUIRE(precision == CNG_PREC_BF16 || precision == CNG_PREC_FP16, CNG_ERR_UNSUPPORTED, "film_siren_fwd_gather: tensor-core precisions only");

@@ -24,12 +24,16 @@
 #include "cng_common.cuh"
 #include "trilinear.cuh"
 
+#ifndef CNG_K1_UNROLL
+#define CNG_K1_UNROLL 2         // rounds of phase B unrolled together (A/B knob)
+#endif
 #ifndef CNG_K1_MIN_BLOCKS
 #define CNG_K1_MIN_BLOCKS 3     // resident blocks per SM the register allocation aims at (A/B knob)
 #endif
 
 namespace cng {
 
+constexpr int kK1Unroll = CNG_K1_UNROLL;
 constexpr int kLanesPerPoint = 8;
 constexpr int kPointsPerBlock = 32;      // 8x4 pixel patch
 constexpr int kTileW = 8, kTileH = 4;
@@ -102,20 +106,26 @@ struct RayParams {
   float* points_out;        // [B, R, S, 3] or NULL
 };
 
-__device__ __forceinline__ CornerRec shfl_record(const CornerRec& r, int src) {
-  CornerRec o;
-  o.base = __shfl_sync(0xffffffffu, r.base, src);
-  o.flags = __shfl_sync(0xffffffffu, r.flags, src);
-  o.xl = __shfl_sync(0xffffffffu, r.xl, src); o.xh = __shfl_sync(0xffffffffu, r.xh, src);
-  o.yl = __shfl_sync(0xffffffffu, r.yl, src); o.yh = __shfl_sync(0xffffffffu, r.yh, src);
-  o.zl = __shfl_sync(0xffffffffu, r.zl, src); o.zh = __shfl_sync(0xffffffffu, r.zh, src);
+// What travels from the lane that owns a point (phase A) to the 8 lanes that gather it (phase B): voxel base index with the three
+// in-range flags in bits 28..30, the 8 corner weights (formed once per point, not once per lane), and the point's row in feat.
+struct PointRec {
+  int base_flags;
+  int row;                                // ray * S + s inside the batch item, -1 for a dead lane
+  float w[8];
+};
+__device__ __forceinline__ PointRec shfl_point(const PointRec& r, int src) {
+  PointRec o;
+  o.base_flags = __shfl_sync(0xffffffffu, r.base_flags, src);
+  o.row = __shfl_sync(0xffffffffu, r.row, src);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o.w[i] = __shfl_sync(0xffffffffu, r.w[i], src);
   return o;
 }
 
 // grid = (ceil(R / 32), B); block = 8 warps.  The block owns an 8x4 pixel patch (32 rays, lane = ray in phase A);
-// warp w marches the samples s = w, w + 8, ...  Phase A: one lane = one ray, position + voxel index arithmetic once
-// per point (it used to be repeated by the 8 lanes that share a point).  Phase B: 8 rounds, each serving 4 of the
-// warp's 32 points with 8 lanes x float4 per point; the corner record travels by warp shuffle.
+// warp w marches the samples s = w, w + 8, ...  Phase A: one lane = one ray, position, voxel index arithmetic and the 8 corner
+// weights once per point (they used to be repeated by the 8 lanes that share a point).  Phase B: 8 rounds, each serving 4 of the
+// warp's 32 points with 8 lanes x float4 per point; the point record travels by warp shuffle.  32-bit offsets inside a batch item.
 template <bool FINE>
 __global__ void __launch_bounds__(256, CNG_K1_MIN_BLOCKS) raymarch_gather_kernel(RayParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -137,6 +147,7 @@ __global__ void __launch_bounds__(256, CNG_K1_MIN_BLOCKS) raymarch_gather_kernel
   const float dx = __ldg(p.rays_d_cam + 3 * rr), dy = __ldg(p.rays_d_cam + 3 * rr + 1), dz = __ldg(p.rays_d_cam + 3 * rr + 2);
   const size_t base = (static_cast<size_t>(b) * p.R + rr) * p.S;
   const float4* vol = p.vol + static_cast<size_t>(b) * p.vol_item_stride;
+  float4* feat_item = p.feat ? p.feat + static_cast<size_t>(b) * p.R * p.S * p.C4 : nullptr;
   float wx = 0.f, wy = 0.f, wz = 0.f, spacing = 0.f;
   if (FINE) {
     // world-space direction: bmm(cam2world[:3,:3], d_cam)      (volumetric_rendering.py:172-180)
@@ -178,17 +189,18 @@ __global__ void __launch_bounds__(256, CNG_K1_MIN_BLOCKS) raymarch_gather_kernel
       o[0] = px; o[1] = py; o[2] = pz;
     }
     if (p.feat == nullptr) continue;                       // points-only mode: the gather happens in the consumer (fused K2 prologue)
-    const CornerRec mine = corner_record(px, py, pz, p.D, p.H, p.W);
-    const long long my_row = live ? static_cast<long long>(base + s) : -1;
+    const CornerRec rec = corner_record(px, py, pz, p.D, p.H, p.W);
+    PointRec mine;
+    mine.base_flags = rec.base | (rec.flags << 28);
+    mine.row = live ? rr * p.S + s : -1;
+    corner_weights(rec, mine.w);
     // ---- phase B: 4 points per round, 8 lanes x float4 each ----
-#pragma unroll 2
+#pragma unroll kK1Unroll
     for (int round = 0; round < 8; ++round) {
-      const int src = round * 4 + grp;
-      const CornerRec r = shfl_record(mine, src);
-      const long long row = __shfl_sync(0xffffffffu, my_row, src);
+      const PointRec r = shfl_point(mine, round * 4 + grp);
       for (int cg = sub; cg < p.C4; cg += kLanesPerPoint) {
-        const float4 f = gather_c4(vol, p.H, p.W, p.C4, r, cg);
-        if (row >= 0) p.feat[row * p.C4 + cg] = f;
+        const float4 f = gather_c4_w(vol, p.H, p.W, p.C4, r.base_flags & 0x0fffffff, r.base_flags >> 28, r.w, cg);
+        if (r.row >= 0) feat_item[r.row * p.C4 + cg] = f;
       }
     }
   }
@@ -246,6 +258,9 @@ static int check_volume(const void* vol, int B, int C, int D, int H, int W, cons
   CNG_REQUIRE(B >= 0 && C >= 1 && D >= 1 && H >= 1 && W >= 1, CNG_ERR_INVALID_ARGUMENT, "%s: bad volume shape", who);
   CNG_REQUIRE(C % 4 == 0 && C <= 128, CNG_ERR_UNSUPPORTED, "%s: C=%d (need C %% 4 == 0 and C <= 128)", who, C);
   CNG_REQUIRE((reinterpret_cast<uintptr_t>(vol) & 15) == 0, CNG_ERR_INVALID_ARGUMENT, "%s: volume not 16-byte aligned", who);
+  // the gather addresses a batch item with 32-bit float4 offsets and carries the voxel index in 28 bits (trilinear.cuh, PointRec)
+  CNG_REQUIRE(static_cast<long long>(D) * H * W < (1LL << 28) && static_cast<long long>(D) * H * W * (C / 4) < (1LL << 31), CNG_ERR_UNSUPPORTED,
+              "%s: volume of %d x %d x %d x %d exceeds the gather's 32-bit offsets", who, D, H, W, C);
   return CNG_OK;
 }
 
@@ -287,6 +302,8 @@ static int raymarch_common(bool fine, const float* vol, long long vol_item_strid
               "%s: NULL distance buffer", who);
   CNG_REQUIRE(img_w >= 1 && img_h >= 1 && S >= (fine ? 1 : 2), CNG_ERR_INVALID_ARGUMENT, "%s: img=%dx%d S=%d", who, img_w, img_h, S);
   CNG_REQUIRE(B <= 65535, CNG_ERR_UNSUPPORTED, "%s: B=%d > 65535", who, B);
+  CNG_REQUIRE(static_cast<long long>(img_w) * img_h * S * (C / 4) < (1LL << 31), CNG_ERR_UNSUPPORTED,
+              "%s: %d x %d rays x %d samples x %d channels per item exceeds the 32-bit row offsets", who, img_w, img_h, S, C);
   CNG_REQUIRE((reinterpret_cast<uintptr_t>(feat) & 15) == 0, CNG_ERR_INVALID_ARGUMENT, "%s: feat not 16-byte aligned", who);
   if (B == 0) return CNG_OK;
   if (int e = cng_device_check()) return e;

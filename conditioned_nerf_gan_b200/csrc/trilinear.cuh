@@ -34,36 +34,50 @@ __device__ __forceinline__ CornerRec corner_record(float px, float py, float pz,
   return r;
 }
 
-// 8 lanes x float4 = the 32 channels of ONE point: 8 independent 16-byte loads per lane, ATen's accumulation order.
-__device__ __forceinline__ float4 gather_c4(const float4* __restrict__ vol, int H, int W, int C4, const CornerRec& r, int cg4) {
+// The 8 corner weights of a point in ATen's order tnw..bse (w[z*4 + y*2 + x]); an out-of-range high corner weighs exactly 0.
+__device__ __forceinline__ void corner_weights(const CornerRec& r, float (&w)[8]) {
   const bool xin = r.flags & 1, yin = r.flags & 2, zin = r.flags & 4;
-  const size_t sx = xin ? C4 : 0, sy = yin ? static_cast<size_t>(W) * C4 : 0, sz = zin ? static_cast<size_t>(H) * W * C4 : 0;
-  const float4* b = vol + static_cast<size_t>(r.base) * C4 + cg4;
+  w[0] = __fmul_rn(__fmul_rn(r.xl, r.yl), r.zl);
+  w[1] = xin ? __fmul_rn(__fmul_rn(r.xh, r.yl), r.zl) : 0.f;
+  w[2] = yin ? __fmul_rn(__fmul_rn(r.xl, r.yh), r.zl) : 0.f;
+  w[3] = (xin && yin) ? __fmul_rn(__fmul_rn(r.xh, r.yh), r.zl) : 0.f;
+  w[4] = zin ? __fmul_rn(__fmul_rn(r.xl, r.yl), r.zh) : 0.f;
+  w[5] = (xin && zin) ? __fmul_rn(__fmul_rn(r.xh, r.yl), r.zh) : 0.f;
+  w[6] = (yin && zin) ? __fmul_rn(__fmul_rn(r.xl, r.yh), r.zh) : 0.f;
+  w[7] = (xin && yin && zin) ? __fmul_rn(__fmul_rn(r.xh, r.yh), r.zh) : 0.f;
+}
+
+// 8 lanes x float4 = the 32 channels of ONE point: 8 independent 16-byte loads per lane, ATen's accumulation order, with the
+// point's corner weights given (fused multiply-adds: the voxel indices and weights are bit-exact, the 8-term sum differs from
+// grid_sample's separate mul / add by < 1 ulp per term -- the parity bar on features is 5e-6 abs -- at half the FP instructions).
+// 32-bit element offsets: a volume item holds at most 2^31 float4 (checked by the callers).
+__device__ __forceinline__ float4 gather_c4_w(const float4* __restrict__ vol, int H, int W, int C4, int base, int flags, const float (&w)[8],
+                                              int cg4) {
+  const int sx = (flags & 1) ? C4 : 0, sy = (flags & 2) ? W * C4 : 0, sz = (flags & 4) ? H * W * C4 : 0;
+  const float4* b = vol + (base * C4 + cg4);
   const float4 v000 = __ldg(b), v001 = __ldg(b + sx), v010 = __ldg(b + sy), v011 = __ldg(b + sy + sx);
   const float4 v100 = __ldg(b + sz), v101 = __ldg(b + sz + sx), v110 = __ldg(b + sz + sy), v111 = __ldg(b + sz + sy + sx);
-  const float w000 = __fmul_rn(__fmul_rn(r.xl, r.yl), r.zl);
-  const float w001 = xin ? __fmul_rn(__fmul_rn(r.xh, r.yl), r.zl) : 0.f;
-  const float w010 = yin ? __fmul_rn(__fmul_rn(r.xl, r.yh), r.zl) : 0.f;
-  const float w011 = (xin && yin) ? __fmul_rn(__fmul_rn(r.xh, r.yh), r.zl) : 0.f;
-  const float w100 = zin ? __fmul_rn(__fmul_rn(r.xl, r.yl), r.zh) : 0.f;
-  const float w101 = (xin && zin) ? __fmul_rn(__fmul_rn(r.xh, r.yl), r.zh) : 0.f;
-  const float w110 = (yin && zin) ? __fmul_rn(__fmul_rn(r.xl, r.yh), r.zh) : 0.f;
-  const float w111 = (xin && yin && zin) ? __fmul_rn(__fmul_rn(r.xh, r.yh), r.zh) : 0.f;
-  // ATen's corner order, fused multiply-adds: the voxel indices and weights above are bit-exact, the 8-term sum differs from
-  // grid_sample's separate mul / add by < 1 ulp per term (the parity bar on features is 5e-6 abs) at half the FP instructions
   float4 o;
 #define CNG_ACC(comp)                                                          \
-  o.comp = __fmul_rn(v000.comp, w000);                                         \
-  o.comp = fmaf(v001.comp, w001, o.comp);                                      \
-  o.comp = fmaf(v010.comp, w010, o.comp);                                      \
-  o.comp = fmaf(v011.comp, w011, o.comp);                                      \
-  o.comp = fmaf(v100.comp, w100, o.comp);                                      \
-  o.comp = fmaf(v101.comp, w101, o.comp);                                      \
-  o.comp = fmaf(v110.comp, w110, o.comp);                                      \
-  o.comp = fmaf(v111.comp, w111, o.comp);
+  o.comp = __fmul_rn(v000.comp, w[0]);                                         \
+  o.comp = fmaf(v001.comp, w[1], o.comp);                                      \
+  o.comp = fmaf(v010.comp, w[2], o.comp);                                      \
+  o.comp = fmaf(v011.comp, w[3], o.comp);                                      \
+  o.comp = fmaf(v100.comp, w[4], o.comp);                                      \
+  o.comp = fmaf(v101.comp, w[5], o.comp);                                      \
+  o.comp = fmaf(v110.comp, w[6], o.comp);                                      \
+  o.comp = fmaf(v111.comp, w[7], o.comp);
   CNG_ACC(x) CNG_ACC(y) CNG_ACC(z) CNG_ACC(w)
 #undef CNG_ACC
   return o;
+}
+
+// The same from a corner record (the weights are formed here: callers that serve one point with 8 lanes form them once per point
+// and call gather_c4_w instead).
+__device__ __forceinline__ float4 gather_c4(const float4* __restrict__ vol, int H, int W, int C4, const CornerRec& r, int cg4) {
+  float w[8];
+  corner_weights(r, w);
+  return gather_c4_w(vol, H, W, C4, r.base, r.flags, w, cg4);
 }
 
 }  // namespace cng
