@@ -126,7 +126,7 @@ __device__ __forceinline__ PointRec shfl_point(const PointRec& r, int src) {
 // warp w marches the samples s = w, w + 8, ...  Phase A: one lane = one ray, position, voxel index arithmetic and the 8 corner
 // weights once per point (they used to be repeated by the 8 lanes that share a point).  Phase B: 8 rounds, each serving 4 of the
 // warp's 32 points with 8 lanes x float4 per point; the point record travels by warp shuffle.  32-bit offsets inside a batch item.
-template <bool FINE>
+template <bool FINE, bool kC8>
 __global__ void __launch_bounds__(256, CNG_K1_MIN_BLOCKS) raymarch_gather_kernel(RayParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
@@ -158,6 +158,8 @@ __global__ void __launch_bounds__(256, CNG_K1_MIN_BLOCKS) raymarch_gather_kernel
     spacing = __fsub_rn(__ldg(p.t_lin + 1), __ldg(p.t_lin));    // z_vals[...,1] - z_vals[...,0]
   }
   const int sub = lane & 7, grp = lane >> 3;
+  const char* vol_lane_bytes = reinterpret_cast<const char*>(vol + sub);                       // kC8: this lane's channel group of voxel 0
+  char* feat_lane_bytes = reinterpret_cast<char*>(feat_item ? feat_item + sub : nullptr);       // ... and of the item's row 0
   for (int s = warp; s < p.S; s += 8) {
     // ---- phase A: this lane's ray, sample s ----
     float px, py, pz;
@@ -198,9 +200,15 @@ __global__ void __launch_bounds__(256, CNG_K1_MIN_BLOCKS) raymarch_gather_kernel
 #pragma unroll kK1Unroll
     for (int round = 0; round < 8; ++round) {
       const PointRec r = shfl_point(mine, round * 4 + grp);
-      for (int cg = sub; cg < p.C4; cg += kLanesPerPoint) {
-        const float4 f = gather_c4_w(vol, p.H, p.W, p.C4, r.base_flags & 0x0fffffff, r.base_flags >> 28, r.w, cg);
-        if (r.row >= 0) feat_item[r.row * p.C4 + cg] = f;
+      if constexpr (kC8) {
+        // 32 channels: lane `sub` owns float4 `sub` of the point; all strides are compile-time multiples of 8 float4
+        const float4 f = gather_c4_w_bytes(vol_lane_bytes, 128u, p.H, p.W, static_cast<unsigned>(r.base_flags) & 0x0fffffffu, r.base_flags >> 28, r.w);
+        if (r.row >= 0) *reinterpret_cast<float4*>(feat_lane_bytes + static_cast<unsigned>(r.row) * 128u) = f;
+      } else {
+        for (int cg = sub; cg < p.C4; cg += kLanesPerPoint) {
+          const float4 f = gather_c4_w(vol, p.H, p.W, p.C4, r.base_flags & 0x0fffffff, r.base_flags >> 28, r.w, cg);
+          if (r.row >= 0) feat_item[r.row * p.C4 + cg] = f;
+        }
       }
     }
   }
@@ -258,8 +266,8 @@ static int check_volume(const void* vol, int B, int C, int D, int H, int W, cons
   CNG_REQUIRE(B >= 0 && C >= 1 && D >= 1 && H >= 1 && W >= 1, CNG_ERR_INVALID_ARGUMENT, "%s: bad volume shape", who);
   CNG_REQUIRE(C % 4 == 0 && C <= 128, CNG_ERR_UNSUPPORTED, "%s: C=%d (need C %% 4 == 0 and C <= 128)", who, C);
   CNG_REQUIRE((reinterpret_cast<uintptr_t>(vol) & 15) == 0, CNG_ERR_INVALID_ARGUMENT, "%s: volume not 16-byte aligned", who);
-  // the gather addresses a batch item with 32-bit float4 offsets and carries the voxel index in 28 bits (trilinear.cuh, PointRec)
-  CNG_REQUIRE(static_cast<long long>(D) * H * W < (1LL << 28) && static_cast<long long>(D) * H * W * (C / 4) < (1LL << 31), CNG_ERR_UNSUPPORTED,
+  // the gather addresses a batch item with 32-bit BYTE offsets (items under 4 GB) and carries the voxel index in 28 bits (trilinear.cuh, PointRec)
+  CNG_REQUIRE(static_cast<long long>(D) * H * W * (C / 4) < (1LL << 28), CNG_ERR_UNSUPPORTED,
               "%s: volume of %d x %d x %d x %d exceeds the gather's 32-bit offsets", who, D, H, W, C);
   return CNG_OK;
 }
@@ -302,8 +310,8 @@ static int raymarch_common(bool fine, const float* vol, long long vol_item_strid
               "%s: NULL distance buffer", who);
   CNG_REQUIRE(img_w >= 1 && img_h >= 1 && S >= (fine ? 1 : 2), CNG_ERR_INVALID_ARGUMENT, "%s: img=%dx%d S=%d", who, img_w, img_h, S);
   CNG_REQUIRE(B <= 65535, CNG_ERR_UNSUPPORTED, "%s: B=%d > 65535", who, B);
-  CNG_REQUIRE(static_cast<long long>(img_w) * img_h * S * (C / 4) < (1LL << 31), CNG_ERR_UNSUPPORTED,
-              "%s: %d x %d rays x %d samples x %d channels per item exceeds the 32-bit row offsets", who, img_w, img_h, S, C);
+  CNG_REQUIRE(static_cast<long long>(img_w) * img_h * S * (C / 4) < (1LL << 28), CNG_ERR_UNSUPPORTED,
+              "%s: %d x %d rays x %d samples x %d channels per item exceeds the 32-bit byte offsets of feat (4 GB per batch item)", who, img_w, img_h, S, C);
   CNG_REQUIRE((reinterpret_cast<uintptr_t>(feat) & 15) == 0, CNG_ERR_INVALID_ARGUMENT, "%s: feat not 16-byte aligned", who);
   if (B == 0) return CNG_OK;
   if (int e = cng_device_check()) return e;
@@ -315,8 +323,13 @@ static int raymarch_common(bool fine, const float* vol, long long vol_item_strid
   p.img_w = img_w; p.img_h = img_h; p.R = img_w * img_h; p.S = S;
   p.feat = reinterpret_cast<float4*>(feat); p.t_out = t_out; p.points_out = points_out;
   dim3 grid((p.R + cng::kPointsPerBlock - 1) / cng::kPointsPerBlock, B);
-  if (fine) cng::raymarch_gather_kernel<true><<<grid, 256, 0, cng::as_stream(stream)>>>(p);
-  else cng::raymarch_gather_kernel<false><<<grid, 256, 0, cng::as_stream(stream)>>>(p);
+  if (p.C4 == 8) {                                          // the shipped shape: 32 feature channels
+    if (fine) cng::raymarch_gather_kernel<true, true><<<grid, 256, 0, cng::as_stream(stream)>>>(p);
+    else cng::raymarch_gather_kernel<false, true><<<grid, 256, 0, cng::as_stream(stream)>>>(p);
+  } else {
+    if (fine) cng::raymarch_gather_kernel<true, false><<<grid, 256, 0, cng::as_stream(stream)>>>(p);
+    else cng::raymarch_gather_kernel<false, false><<<grid, 256, 0, cng::as_stream(stream)>>>(p);
+  }
   return cng::check_launch(who);
 }
 

@@ -72,6 +72,33 @@ __device__ __forceinline__ float4 gather_c4_w(const float4* __restrict__ vol, in
   return o;
 }
 
+// The same with the 8 corner addresses formed as ONE 64-bit base plus 32-bit BYTE offsets (nvcc otherwise carries every corner as a
+// 64-bit element index and spends ~5 integer instructions per load on it: 45 of the gather kernel's 110 instructions per lane and
+// round).  `vol_lane_bytes` = the lane's float4 of voxel 0 of the batch item; `row_bytes` = bytes per voxel (16 * C/4); a volume item
+// is smaller than 4 GB (checked by the callers).
+__device__ __forceinline__ float4 gather_c4_w_bytes(const char* __restrict__ vol_lane_bytes, unsigned row_bytes, int H, int W, unsigned base,
+                                                    int flags, const float (&w)[8]) {
+  const unsigned o0 = base * row_bytes;
+  const unsigned ox = (flags & 1) ? row_bytes : 0u, oy = (flags & 2) ? static_cast<unsigned>(W) * row_bytes : 0u,
+                 oz = (flags & 4) ? static_cast<unsigned>(H) * static_cast<unsigned>(W) * row_bytes : 0u;
+  auto ld = [&](unsigned off) { return __ldg(reinterpret_cast<const float4*>(vol_lane_bytes + off)); };
+  const float4 v000 = ld(o0), v001 = ld(o0 + ox), v010 = ld(o0 + oy), v011 = ld(o0 + oy + ox);
+  const float4 v100 = ld(o0 + oz), v101 = ld(o0 + oz + ox), v110 = ld(o0 + oz + oy), v111 = ld(o0 + oz + oy + ox);
+  float4 o;
+#define CNG_ACC(comp)                                                          \
+  o.comp = __fmul_rn(v000.comp, w[0]);                                         \
+  o.comp = fmaf(v001.comp, w[1], o.comp);                                      \
+  o.comp = fmaf(v010.comp, w[2], o.comp);                                      \
+  o.comp = fmaf(v011.comp, w[3], o.comp);                                      \
+  o.comp = fmaf(v100.comp, w[4], o.comp);                                      \
+  o.comp = fmaf(v101.comp, w[5], o.comp);                                      \
+  o.comp = fmaf(v110.comp, w[6], o.comp);                                      \
+  o.comp = fmaf(v111.comp, w[7], o.comp);
+  CNG_ACC(x) CNG_ACC(y) CNG_ACC(z) CNG_ACC(w)
+#undef CNG_ACC
+  return o;
+}
+
 // The same from a corner record (the weights are formed here: callers that serve one point with 8 lanes form them once per point
 // and call gather_c4_w instead).
 __device__ __forceinline__ float4 gather_c4(const float4* __restrict__ vol, int H, int W, int C4, const CornerRec& r, int cg4) {
