@@ -27,6 +27,9 @@
 #ifndef CNG_K1_UNROLL
 #define CNG_K1_UNROLL 2         // rounds of phase B unrolled together (A/B knob)
 #endif
+#ifndef CNG_K1_MIN_BLOCKS_C8
+#define CNG_K1_MIN_BLOCKS_C8 4  // ... of the 32-channel instantiation: it fits 64 registers without spilling (measured: c2 step 6.44 -> 6.41 ms)
+#endif
 #ifndef CNG_K1_MIN_BLOCKS
 #define CNG_K1_MIN_BLOCKS 3     // resident blocks per SM the register allocation aims at (A/B knob)
 #endif
@@ -127,7 +130,7 @@ __device__ __forceinline__ PointRec shfl_point(const PointRec& r, int src) {
 // weights once per point (they used to be repeated by the 8 lanes that share a point).  Phase B: 8 rounds, each serving 4 of the
 // warp's 32 points with 8 lanes x float4 per point; the point record travels by warp shuffle.  32-bit offsets inside a batch item.
 template <bool FINE, bool kC8>
-__global__ void __launch_bounds__(256, CNG_K1_MIN_BLOCKS) raymarch_gather_kernel(RayParams p) {
+__global__ void __launch_bounds__(256, kC8 ? CNG_K1_MIN_BLOCKS_C8 : CNG_K1_MIN_BLOCKS) raymarch_gather_kernel(RayParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
   int ray;
