@@ -505,6 +505,16 @@ def test_merge_composite_unsorted_fine_vs_oracle(ops, S):
         assert torch.isfinite(depth).all() and torch.isfinite(pixels).all()
 
 
+def test_order_and_index_kernels_random_stress(ops):
+    """40 random rounds of tools/gpu/stress_c5.py: merge order against torch's stable sort and sample_pdf against the oracle, bit
+    for bit, over random sample counts, value ranges spanning many binades, heavy ties, unsorted coarse lists, empty bins."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("stress_c5", os.path.join(os.path.dirname(__file__), "..", "tools", "gpu", "stress_c5.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.run(40, seed=99) == 0
+
+
 def test_merge_composite_rejects_more_than_512_samples(ops):
     """Documented limit of the per-warp sort (include/cng_b200.h): 2S <= 512 samples per ray; beyond it the call fails loudly."""
     from conditioned_nerf_gan_b200._lib import CngError
