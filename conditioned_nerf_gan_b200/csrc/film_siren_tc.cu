@@ -59,7 +59,7 @@ namespace cng {
 constexpr int kRing = 3;
 constexpr int kDefaultCtaGroup = 1;   // measured: the pair kernel pays ~1300 cycles of cross-CTA hand-off per layer
 constexpr int kDefaultTrainPolyOneIn = 4;   // training-mode epilogue: one (sin, cos) pair in four on the FMA pipe (measured: 1.93 -> 1.80 ms per 1M points, profiles/r2_bwd_kernels.txt)
-constexpr int kDefaultPolyOneIn = 8;   // one sine in 8 on the FMA pipe: measured 2.77 -> 2.68 ms per launch once the shift handling left the epilogue chain (it was neutral before)
+constexpr int kDefaultPolyOneIn = 0;   // every sine on the MUFU unit.  One in 8 on the FMA pipe (CNG_TC_POLY=8) won 2 % in round 1 (2.77 -> 2.70 ms per launch); measured again on the round-2 kernel it loses 1-3 % for every class (TALLSIREN_FG 2.72 vs 2.80 ms, SHORTSIREN_FG fp16 1.32 vs 1.36 ms; profiles/r2l_k2_poly_sweep.txt)
 constexpr int kEpiWarpsPerSlot = CNG_TC_EPI_WARPS;   // 4, 8 or 12 (build-time knob, see build.py)
 static_assert(kEpiWarpsPerSlot == 4 || kEpiWarpsPerSlot == 8 || kEpiWarpsPerSlot == 12, "CNG_TC_EPI_WARPS: 4, 8 or 12");
 constexpr int kEpiGroups = kEpiWarpsPerSlot / 4;           // warps per TMEM lane quarter = column groups of the accumulator
@@ -815,9 +815,12 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
                                           : (train_poly == 0 ? CNG_TRAIN_FN(0, false, false) : CNG_TRAIN_FN(4, false, false));
   const KernelFn train_res_fn = half_operands ? CNG_TRAIN_FN(0, true, true) : CNG_TRAIN_FN(0, false, true);
 #undef CNG_TRAIN_FN
-  const KernelFn fn = gather ? (half_operands ? film_siren_tc_kernel<8, true, false, false, false, true> : film_siren_tc_kernel<8, false, false, false, false, true>)
+  const bool p0 = poly == 0;                                  // residual / fused-gather instantiations: all sines on the MUFU unit, or one in eight on the FMA pipe
+  const KernelFn fn = gather ? (half_operands ? (p0 ? film_siren_tc_kernel<0, true, false, false, false, true> : film_siren_tc_kernel<8, true, false, false, false, true>)
+                                              : (p0 ? film_siren_tc_kernel<0, false, false, false, false, true> : film_siren_tc_kernel<8, false, false, false, false, true>))
                       : res ? (train ? train_res_fn
-                                   : half_operands ? film_siren_tc_kernel<8, true, false, false, true> : film_siren_tc_kernel<8, false, false, false, true>)
+                                   : half_operands ? (p0 ? film_siren_tc_kernel<0, true, false, false, true> : film_siren_tc_kernel<8, true, false, false, true>)
+                                                   : (p0 ? film_siren_tc_kernel<0, false, false, false, true> : film_siren_tc_kernel<8, false, false, false, true>))
                       : train ? train_fn
                       : shared ? (half_operands ? (pl == 0 ? shared_kernel<0, true>() : pl == 4 ? shared_kernel<4, true>() : shared_kernel<8, true>())
                                                 : (pl == 0 ? shared_kernel<0, false>() : pl == 4 ? shared_kernel<4, false>() : shared_kernel<8, false>()))
@@ -827,7 +830,7 @@ int film_siren_tc_launch(const float* feat, int B, long long N, int C, int HID, 
   // function attributes are per device: the opt-in is cached per device ordinal (a process may render on several GPUs)
   static bool attr_set[64][8][12] = {};
   const int variant = res ? 5 + (train ? 2 : half_operands ? 1 : 0) : train ? 2 : (half_operands ? 1 : 0) + (shared ? 3 : 0);
-  const int gslot = gather ? 10 : -1;                                 // the fused-gather instantiations: variant rows 0 / 1, column 10
+  const int gslot = gather ? (p0 ? 11 : 10) : -1;                     // the fused-gather instantiations: variant rows 0 / 1, columns 10 / 11
   const int pslot = gslot >= 0 ? gslot : train ? 0 : poly;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = -1;
